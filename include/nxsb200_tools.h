@@ -1,0 +1,102 @@
+/*
+ * nxsearch-b200: bulk tooling around the index files (additive; the
+ * reference has no counterpart beyond nxs_index_add()).
+ *
+ *  - the deterministic synthetic corpus / query generator of SURVEY.md
+ *    section 8(d) (Zipf(1.0) vocabulary, seed 0x6E78735F42323030);
+ *  - a bulk writer that emits `nxsterms` / `nxsdtmap` files in the
+ *    reference's on-disk format (reference: src/index/storage.h:12-133;
+ *    golden bytes: src/tests/t_index_terms.c:23-37,
+ *    src/tests/t_index_dtmap.c:25-41), so that this engine and the
+ *    reference open byte-identical files.
+ *
+ * Everything here is host-only integer work; no CUDA.
+ */
+#ifndef NXSB200_TOOLS_H
+#define NXSB200_TOOLS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NXSB_CORPUS_SEED	UINT64_C(0x6E78735F42323030)	/* "nxs_B200" */
+
+/*
+ * A corpus in document-major form, host memory, native endianness.
+ * This is the in-memory twin of an `nxsdtmap` file: for document i
+ * (0-based, in file order) pairs[2*j], pairs[2*j+1] for j in
+ * [doc_off[i], doc_off[i+1]) are (term id, count), ascending term id.
+ */
+typedef struct nxsb_corpus {
+	uint32_t	n_docs;
+	uint32_t	n_terms;	/* vocabulary size; term ids 1..n_terms */
+	uint64_t	n_pairs;
+	uint64_t	token_count;	/* sum of doc_len (file: header field) */
+	uint32_t	doc_count;	/* N used for scoring (file: header field) */
+	uint64_t *	doc_ids;	/* [n_docs] external ids (non-zero) */
+	uint32_t *	doc_len;	/* [n_docs] tokens incl. repeats */
+	uint64_t *	doc_off;	/* [n_docs + 1] */
+	uint32_t *	pairs;		/* [2 * n_pairs] */
+	/* Vocabulary: term i (id i+1) = term_blob[term_off[i]..term_off[i+1]). */
+	char *		term_blob;
+	uint32_t *	term_off;	/* [n_terms + 1] */
+	uint64_t *	term_total;	/* [n_terms] occurrences in the corpus */
+	uint32_t *	term_df;	/* [n_terms] documents containing it */
+} nxsb_corpus_t;
+
+/*
+ * Generate the SURVEY section 8(d) corpus: V distinct [a-z0-9]{4,12} terms
+ * (term id = Zipf rank), documents of 16..111 tokens drawn Zipf(1.0), ids
+ * 1..n_docs (or, with sparse_ids, a strictly increasing pseudo-random 64-bit
+ * sequence).  first_doc/n_docs select a slice of the same global corpus, so
+ * shards can be generated independently; the vocabulary is always the whole.
+ * nthreads <= 0 means "all online CPUs".  NULL on allocation failure.
+ */
+nxsb_corpus_t *	nxsb_corpus_generate(uint64_t seed, uint32_t n_terms,
+		    uint64_t first_doc, uint32_t n_docs, int sparse_ids,
+		    int nthreads);
+void		nxsb_corpus_free(nxsb_corpus_t *);
+
+/*
+ * Synthetic query terms: fills term_ids[0..n) with Zipf(1.0) draws over the
+ * vocabulary restricted to terms with df[t] >= 1 (SURVEY 8d "Queries");
+ * df may be NULL (no restriction).  Deterministic in (seed, n_terms).
+ */
+void		nxsb_corpus_query_terms(uint64_t seed, uint32_t n_terms,
+		    const uint32_t *df, uint32_t *term_ids, size_t n);
+
+/*
+ * Fuzzy workload (SURVEY 8d "C4"): n query strings, each a random
+ * vocabulary term with 1-2 random byte edits (substitute / insert / delete
+ * over [a-z0-9]), re-drawn if it equals a vocabulary term.  Strings are
+ * written NUL-terminated into out (stride bytes apart, stride >= 16).
+ */
+void		nxsb_corpus_fuzzy_terms(uint64_t seed, const nxsb_corpus_t *,
+		    char *out, size_t stride, size_t n);
+
+/*
+ * Write the corpus as reference-format index files (big-endian, 32 KB file
+ * granularity as the reference's idx_db_map, src/index/idxmap.c:119-177).
+ * Returns 0, or -1 with errno set.
+ */
+int		nxsb_write_terms_file(const char *path, const nxsb_corpus_t *);
+int		nxsb_write_dtmap_file(const char *path, const nxsb_corpus_t *);
+
+/*
+ * Read reference-format index files back into a corpus (doc_ids in file
+ * order; deleted blocks and deletion markers applied as the reference's
+ * idx_dtmap_sync does, src/index/dtmap.c:357-384,440-544).  term_df is
+ * recomputed; term_total is taken from the file.  NULL + errno on error
+ * (EINVAL for a corrupt file).
+ */
+nxsb_corpus_t *	nxsb_read_index_files(const char *terms_path,
+		    const char *dtmap_path);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif
