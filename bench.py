@@ -1,0 +1,445 @@
+#!/usr/bin/env python
+"""Headline benchmark: BM25 top-10 queries/s on a 10M-document synthetic index.
+
+    python bench.py --gpus N --steps K --warmup W            (our arm)
+    python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm)
+
+A step is one batch of 1024 synthetic OR-queries (1-4 Zipf terms each, SURVEY
+section 8d "C2") scored against the whole index, top-10 per query.  With N > 1
+the SAME 10M-document index is document-sharded over the N GPUs (strong
+scaling, as BASELINE.json's metric is quoted), each rank scores its shard with
+global statistics and the per-shard top-k lists are merged after an NCCL
+all-gather.
+
+One JSON line on stdout (rank 0): see the contract in the task description.
+`value`  = device-resident throughput (batches already in HBM),
+`e2e`    = the same through the reference-facing C API with host buffers
+           (query strings in, result arrays out; N > 1: engine C ABI + merge),
+`roofline` = score_tiles_kernel against the measured HBM peak,
+`cpu_baseline` = the oracle port on this box's host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+METRIC = "BM25 top-10 queries/s, 10M-doc synthetic index"
+UNIT = "queries/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# --------------------------------------------------------------------------
+# workload
+
+
+def make_queries(term_ids: np.ndarray, n_queries: int):
+    """n_queries OR-queries with 1..4 terms (cycling), as (tokens, program, string-ids).
+
+    Token order follows the reference: leaves right-to-left, duplicates merged
+    (ref src/query/query.c:89-103, src/core/tokenizer.c:94-117)."""
+    OP_OR = -3
+    out, pos = [], 0
+    for i in range(n_queries):
+        nt = 1 + (i % 4)
+        leaves = [int(t) for t in term_ids[pos:pos + nt]]
+        pos += nt
+        toks: list[int] = []
+        for t in reversed(leaves):
+            if t not in toks:
+                toks.append(t)
+        slot = {t: s for s, t in enumerate(toks)}
+        prog = [slot[leaves[0]]]
+        for t in leaves[1:]:
+            prog += [slot[t], OP_OR]
+        out.append((toks, prog, leaves))
+    return out
+
+
+def batch_bytes(batch_items, df) -> int:
+    """Algorithmic bytes: 8 B x sum of df over the resolved tokens."""
+    return int(sum(8 * int(df[t - 1]) for toks, _, _ in batch_items for t in toks))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
+                     "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def stop(self) -> dict:
+        self._stop.set()
+        self.join(timeout=6)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(s[3 + j].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]),
+                "power_w_max": max(float(s[2]) for s in self.samples), "samples": len(sm), "reasons": reasons}
+
+
+def measured_peak() -> tuple[float, str]:
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic():
+    """DRAM bytes per launch of score_tiles_kernel from the committed ncu capture."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get("score_tiles_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# --------------------------------------------------------------------------
+# reference arm (CPU)
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    """The reference's CPU path on this box's host cores, bounded sample.
+
+    The compiled reference (oracle/_ref) needs ~60 s per million documents to
+    open an index (measured; DESIGN.md "Oracle"), i.e. ~10 min at 10M, so the
+    arm times the oracle port -- the restatement pinned bit-for-bit to the
+    reference -- on the full-size index instead, one query per host thread."""
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+    from nxsearch_b200 import tools
+    import _oracle
+
+    t0 = time.time()
+    corpus = tools.Corpus.generate(args.docs, args.vocab)
+    log(f"[ref] corpus {corpus.n_docs} docs / {corpus.n_pairs} postings in {time.time() - t0:.1f}s")
+    t0 = time.time()
+    ora = _oracle.OracleIndex(corpus)
+    log(f"[ref] oracle index in {time.time() - t0:.1f}s")
+    cores = len(os.sched_getaffinity(0))
+    per_step = max(cores, min(args.ref_sample, args.batch))
+    n_steps = args.warmup + args.steps
+    qt = corpus.query_terms(4 * per_step * n_steps)
+    queries = make_queries(qt, per_step * n_steps)
+
+    def one(q):
+        toks, prog, _ = q
+        return ora.search(_oracle.BM25, args.limit, toks, prog)
+
+    times = []
+    with ThreadPoolExecutor(max_workers=cores) as pool:
+        for s in range(n_steps):
+            chunk = queries[s * per_step:(s + 1) * per_step]
+            t0 = time.perf_counter()
+            list(pool.map(one, chunk))
+            dt = time.perf_counter() - t0
+            if s >= args.warmup:
+                times.append(dt)
+            if sum(times) > args.ref_budget and len(times) >= 1:
+                break
+    steps_done = len(times)
+    total = sum(times)
+    value = per_step * steps_done / total
+    sample = f"{per_step} queries/step x {steps_done} steps of the same query stream, full {args.docs}-doc index"
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps_done,
+        "warmup": args.warmup, "ms_per_step": 1000 * total / steps_done, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": workload_name(args), "docs": args.docs, "vocab": args.vocab,
+                   "batch": per_step, "limit": args.limit},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args) -> str:
+    return (f"C2: {args.docs} synthetic docs (Zipf(1.0) over {args.vocab} terms, 16-111 tokens), "
+            f"batches of {args.batch} BM25 OR-queries (1-4 terms), top-{args.limit}")
+
+
+# --------------------------------------------------------------------------
+# our arm
+
+
+def run_ours(args, rank: int, world: int, local_rank: int) -> None:
+    import torch
+    import torch.distributed as dist
+    from nxsearch_b200 import capi, dist as nxdist, engine as eng_mod, tools
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- corpus shard + global statistics
+    lo, hi = nxdist.shard_range(args.docs, rank, world)
+    t0 = time.time()
+    corpus = tools.Corpus.generate(hi - lo, args.vocab, first_doc=lo)
+    log(f"[{rank}] shard docs [{lo},{hi}) {corpus.n_pairs} postings generated in {time.time() - t0:.1f}s")
+    df, tokens, ndocs = nxdist.allreduce_stats(np.asarray(corpus.term_df), corpus.token_count, corpus.n_docs, device=dev)
+
+    t0 = time.time()
+    engine = eng_mod.Engine(local_rank)
+    engine.load_corpus(corpus, df=df, token_count=tokens, doc_count=ndocs)
+    log(f"[{rank}] HBM image built in {time.time() - t0:.1f}s")
+    stream = torch.cuda.current_stream()
+    engine.set_stream(stream.cuda_stream)
+    searcher = nxdist.ShardedSearcher(engine, rank, world)
+
+    # ---- queries: identical on every rank (deterministic in the global df)
+    n_steps = args.warmup + args.steps
+    n_distinct = min(n_steps, 48)
+    qt = tools.query_terms(corpus.n_terms, df, 4 * args.batch * n_distinct)
+    queries = make_queries(qt, args.batch * n_distinct)
+    batches = [queries[i * args.batch:(i + 1) * args.batch] for i in range(n_distinct)]
+    local_df = np.asarray(corpus.term_df)
+    bytes_local = [batch_bytes(b, local_df) for b in batches]
+    host_batches = [eng_mod.Batch.from_lists(eng_mod.ALGO_BM25, args.limit, [(t, p) for t, p, _ in b]) for b in batches]
+    handles = [engine.upload(hb) for hb in host_batches]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: batches resident in HBM
+    for s in range(args.warmup):
+        searcher.run(handles[s % n_distinct], args.batch, args.limit)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = engine.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for s in range(args.steps):
+        searcher.run(handles[(args.warmup + s) % n_distinct], args.batch, args.limit)
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    launches = engine.launches - launches0
+    kern = engine.timings(min(args.steps, 256))
+    timed_bytes = sum(bytes_local[(args.warmup + s) % n_distinct] for s in range(max(0, args.steps - 256), args.steps))
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = args.batch * args.steps / (elapsed_ms / 1000)
+
+    # ---- e2e: host buffers in, host results out, every step
+    if world == 1:
+        e2e, h2d, d2h, e2e_note = e2e_capi(args, corpus, batches, capi)
+    else:
+        e2e, h2d, d2h, e2e_note = e2e_sharded(args, engine, searcher, host_batches, barrier, dist, dev)
+
+    # ---- roofline of the dominant kernel
+    peak, peak_src = measured_peak()
+    tile_ms = kern.get("score_tiles", 0.0)
+    achieved = timed_bytes / (tile_ms / 1000) / 1e9 if tile_ms > 0 else 0.0
+    runs_timed = min(args.steps, 256)
+    roofline = {
+        "bound": "hbm", "kernel": "score_tiles_kernel<false,false>",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+        "traffic": recorded_traffic(), "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": timed_bytes / max(runs_timed, 1),
+        "kernel_ms_per_launch": tile_ms / max(runs_timed, 1),
+        "kernel_share_of_step": (tile_ms / runs_timed) / (elapsed_ms / args.steps) if tile_ms else None,
+        "other_kernels_ms_per_step": {k: v / runs_timed for k, v in kern.items() if k != "score_tiles"},
+        "note": "algorithmic bytes = 8 B x sum of df over query tokens (SURVEY 8d); popular posting "
+                "slices are re-read from L2 across the queries of a batch, so DRAM traffic is lower",
+    }
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "docs": args.docs, "vocab": args.vocab,
+                   "batch": args.batch, "limit": args.limit, "parallelism": f"doc-shard x{world}",
+                   "distinct_batches": n_distinct,
+                   "l2": "inputs larger than L2: %.1f GB of postings per GPU, a different batch every step"
+                         % (corpus.n_pairs * 8 / 1e9)},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "path": e2e_note},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, corpus, batches[args.warmup % n_distinct], engine, host_batches[args.warmup % n_distinct])
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    for h in handles:
+        engine.release(h)
+    engine.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def e2e_capi(args, corpus, batches, capi):
+    """N = 1: the public C API, query strings in -> result arrays out."""
+    base = tempfile.mkdtemp(prefix="nxsb_bench_", dir=args.tmpdir)
+    try:
+        nxs = capi.Nxs(base)
+        nxs.create_index("bench").close()
+        t0 = time.time()
+        corpus.write(f"{base}/data/bench/nxsterms", f"{base}/data/bench/nxsdtmap")
+        idx = nxs.open_index("bench")
+        log(f"[0] index files written + opened through nxs_index_open in {time.time() - t0:.1f}s")
+        strings = [[" OR ".join(corpus.term(t) for t in leaves).encode() for _, _, leaves in b] for b in batches]
+        params = dict(limit=args.limit, algo="BM25", fuzzymatch=False)
+        t0 = time.time()
+        idx.search_batch(strings[0][:8], **params)          # builds the HBM image
+        log(f"[0] first search (image build) {time.time() - t0:.1f}s")
+        n = len(batches)
+        for s in range(args.warmup):
+            idx.search_batch(strings[s % n], **params)
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            res = idx.search_batch(strings[(args.warmup + s) % n], **params)
+        dt = time.perf_counter() - t0
+        assert len(res) == args.batch and all(r is not None for r in res)
+        ntok = np.mean([sum(len(t) for t, _, _ in b) for b in batches])
+        nprog = np.mean([sum(len(p) for _, p, _ in b) for b in batches])
+        h2d = int(args.batch * 16 + 4 * ntok + 4 * nprog + 8 * args.batch)
+        d2h = int(args.batch * args.limit * 16 + 4 * args.batch)
+        idx.close()
+        nxs.close()
+        return args.batch * args.steps / dt, h2d, d2h, "nxs_index_search_batch (C API, query strings)"
+    finally:
+        import shutil
+        shutil.rmtree(base, ignore_errors=True)
+
+
+def e2e_sharded(args, engine, searcher, host_batches, barrier, dist, dev):
+    """N > 1: engine C ABI with host descriptor arrays + all-gather merge + D2H."""
+    import torch
+
+    n = len(host_batches)
+
+    def step(hb):
+        h = engine.upload(hb)
+        out = searcher.run(h, args.batch, args.limit)
+        recs = searcher.to_host(out, args.batch, args.limit)
+        engine.release(h)
+        return recs
+
+    for s in range(args.warmup):
+        step(host_batches[s % n])
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        step(host_batches[(args.warmup + s) % n])
+    barrier()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    hb = host_batches[0]
+    h2d = int(hb.queries.nbytes + hb.tokens.nbytes + hb.prog.nbytes)
+    d2h = int(args.batch * args.limit * 16)
+    return args.batch * args.steps / float(t.item()), h2d, d2h, "engine C ABI (host descriptors) + NCCL all-gather + merge"
+
+
+def cpu_baseline(args, corpus, batch_items, engine, host_batch):
+    """Oracle port on a bounded sample of one timed batch, 1 core; the same
+    queries double as an in-run parity check of the GPU results."""
+    import _oracle
+
+    t0 = time.time()
+    ora = _oracle.OracleIndex(corpus)
+    log(f"[0] oracle index built in {time.time() - t0:.1f}s")
+    counts, ids, scores = engine.search(host_batch)
+    done, checked = 0, 0
+    t0 = time.perf_counter()
+    for i, (toks, prog, _) in enumerate(batch_items[:args.cpu_sample]):
+        ora.search(_oracle.BM25, args.limit, toks, prog)
+        done += 1
+        if time.perf_counter() - t0 > args.cpu_budget:
+            break
+    dt = time.perf_counter() - t0
+    for i, (toks, prog, _) in enumerate(batch_items[:min(done, 8)]):
+        all_ids, all_sc = ora.search_all(_oracle.BM25, toks, prog)
+        _oracle.check_topk(ids[i, :counts[i]], scores[i, :counts[i]], all_ids, all_sc, args.limit)
+        checked += 1
+    ora.close()
+    return {"value": done / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"first {done} queries of one timed batch, full {args.docs}-doc index",
+            "parity_checked_queries": checked}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--docs", type=int, default=10_000_000)
+    ap.add_argument("--vocab", type=int, default=1_000_000)
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--limit", type=int, default=10)
+    ap.add_argument("--cpu-sample", type=int, default=64)
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
+    ap.add_argument("--ref-sample", type=int, default=64, help="queries per step of the reference arm")
+    ap.add_argument("--ref-budget", type=float, default=60.0, help="seconds of timed CPU work, reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tmpdir", default=None)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if world != args.gpus:
+            log(f"note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world} rank(s)")
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -29,6 +29,9 @@
 extern "C" {
 #endif
 
+/* Everything declared here is exported; the rest of the library is hidden. */
+#pragma GCC visibility push(default)
+
 typedef uint64_t nxs_doc_id_t;			/* ref nxs.h:21; 0 is invalid */
 
 typedef struct nxs nxs_t;
@@ -101,6 +104,8 @@ void		nxs_resp_release(nxs_resp_t *);
  */
 int		nxs_index_search_batch(nxs_index_t *, nxs_params_t *,
 		    const char *const *queries, size_t n, nxs_resp_t **resps);
+
+#pragma GCC visibility pop
 
 #ifdef __cplusplus
 }

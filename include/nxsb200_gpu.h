@@ -1,0 +1,191 @@
+/*
+ * nxsearch-b200: the thin C ABI between the C11 host library and the
+ * sm_100a CUDA engine.  Plain pointers and sizes only; no CUDA or torch
+ * types.  This is the seam the reference's internals would bind if the GPU
+ * engine were dropped into the reference tree:
+ *
+ *   nxsb_engine_load_shard   <- the in-memory reverse index built by
+ *                               idx_terms_sync / idx_dtmap_sync
+ *                               (ref src/index/terms.c:320-414,
+ *                                src/index/dtmap.c:386-544)
+ *   nxsb_engine_search       <- run_query_logic + nxs_resp_build
+ *                               (ref src/query/search.c:118-278,
+ *                                src/core/results.c:128-220) with the
+ *                               ranking functions of src/algo/ranking.c
+ *   nxsb_engine_fuzzy        <- idxterm_fuzzysearch
+ *                               (ref src/index/idxterm.c:210-249 over
+ *                                src/algo/bktree.c, src/algo/levdist.c)
+ *
+ * All functions return 0 on success and -1 on failure unless stated;
+ * nxsb_engine_errmsg() / nxsb_last_error() describe the failure.  There is
+ * NO CPU fallback: without a usable CUDA device nxsb_engine_create() fails.
+ */
+#ifndef NXSB200_GPU_H
+#define NXSB200_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Everything declared here is exported; the rest of the library is hidden. */
+#pragma GCC visibility push(default)
+
+typedef struct nxsb_engine nxsb_engine_t;
+
+enum { NXSB_ALGO_TFIDF = 0, NXSB_ALGO_BM25 = 1 };	/* ref index.h:30-34 */
+
+/* Postfix boolean program over a query's token slots. */
+enum {
+	NXSB_OP_EMPTY	= -1,	/* push the empty set (unresolved leaf) */
+	NXSB_OP_AND	= -2,
+	NXSB_OP_OR	= -3,
+	NXSB_OP_ANDNOT	= -4,
+	/* >= 0: push the document set of token slot i */
+};
+
+#define NXSB_MAX_QUERY_TOKENS	32	/* resolved tokens per query */
+#define NXSB_MAX_QUERY_PROG	128	/* postfix program length */
+#define NXSB_TILE_DOCS		16384	/* documents per scoring tile */
+
+/* Number of CUDA devices visible; 0 when there is no driver / device. */
+int		nxsb_gpu_device_count(void);
+const char *	nxsb_last_error(void);
+
+nxsb_engine_t *	nxsb_engine_create(int device);
+void		nxsb_engine_destroy(nxsb_engine_t *);
+const char *	nxsb_engine_errmsg(const nxsb_engine_t *);
+
+/*
+ * Run all engine work on an externally owned CUDA stream (a cudaStream_t
+ * passed as void *; NULL restores the engine's own stream).
+ */
+int		nxsb_engine_set_stream(nxsb_engine_t *, void *cuda_stream);
+
+/*
+ * One document shard in document-major form (host memory), documents in
+ * ASCENDING external-id order.  pairs[2j], pairs[2j+1] = (term id 1-based,
+ * count) for j in [doc_off[i], doc_off[i+1]).  doc_count / token_count / df
+ * are WHOLE-INDEX statistics: BM25 and TF-IDF use the global N, df and
+ * average length (ref ranking.c:77-78,149-150,163), so a shard must not
+ * substitute its own.  df may be NULL when the shard is the whole index.
+ */
+typedef struct nxsb_shard_desc {
+	uint32_t		n_docs;
+	uint32_t		n_terms;
+	const uint64_t *	doc_ids;
+	const uint32_t *	doc_len;
+	const uint64_t *	doc_off;
+	const uint32_t *	pairs;
+	uint64_t		token_count;
+	uint32_t		doc_count;
+	const uint32_t *	df;
+} nxsb_shard_desc_t;
+
+/* Build (or rebuild) the HBM-resident CSR image of the shard. */
+int		nxsb_engine_load_shard(nxsb_engine_t *, const nxsb_shard_desc_t *);
+
+/* Shard-local df[t] for t in [0, n_terms) after a load (for the all-reduce). */
+int		nxsb_engine_get_df(nxsb_engine_t *, uint32_t *df, uint32_t n_terms);
+/* Replace the statistics the scores use (after a cross-shard all-reduce). */
+int		nxsb_engine_set_global_stats(nxsb_engine_t *, const uint32_t *df,
+		    uint32_t n_terms, uint64_t token_count, uint32_t doc_count);
+
+typedef struct nxsb_query {
+	uint32_t	tok_off;	/* first token slot in batch.tokens */
+	uint32_t	n_tokens;	/* resolved tokens, token-list order */
+	uint32_t	prog_off;	/* first op in batch.prog */
+	uint32_t	n_prog;
+} nxsb_query_t;
+
+typedef struct nxsb_batch {
+	int			algo;		/* NXSB_ALGO_* */
+	uint32_t		limit;		/* top-N per query, >= 1 */
+	uint32_t		n_queries;
+	const nxsb_query_t *	queries;
+	const uint32_t *	tokens;		/* 1-based term ids */
+	uint32_t		n_tokens;
+	const int32_t *		prog;
+	uint32_t		n_prog;
+} nxsb_batch_t;
+
+/*
+ * Score a batch.  Host buffers: counts[n_queries], ids/scores
+ * [n_queries * limit] (query q's results at [q*limit, q*limit + counts[q]),
+ * descending score, ties by descending document id).  Synchronous.
+ */
+int		nxsb_engine_search(nxsb_engine_t *, const nxsb_batch_t *,
+		    uint32_t *counts, uint64_t *ids, float *scores);
+
+/*
+ * The same in three steps, for callers that keep the batch resident in HBM
+ * (the `value` leg of bench.py) or chain a collective on the device.
+ * upload: copies the batch descriptors to the device, returns a handle >= 0.
+ * run:    enqueues the scoring + top-k kernels on the engine's stream; the
+ *         results stay in device memory: 16-byte records
+ *         { u64 doc_id; f32 score; u32 valid } at recs[q*limit + r].
+ *         If d_recs is NULL an engine-owned buffer is used.
+ * fetch:  copies an engine-owned result buffer to host arrays.
+ */
+int		nxsb_engine_batch_upload(nxsb_engine_t *, const nxsb_batch_t *);
+int		nxsb_engine_batch_run(nxsb_engine_t *, int handle, void *d_recs);
+int		nxsb_engine_batch_fetch(nxsb_engine_t *, int handle,
+		    uint32_t *counts, uint64_t *ids, float *scores);
+int		nxsb_engine_batch_release(nxsb_engine_t *, int handle);
+/* Algorithmic bytes (8 B x sum of df over resolved tokens) of a batch. */
+uint64_t	nxsb_engine_batch_bytes(nxsb_engine_t *, int handle);
+int		nxsb_engine_sync(nxsb_engine_t *);
+
+/*
+ * Merge per-shard top-k record lists (device memory, as produced by
+ * batch_run on each rank and gathered rank-major: d_in[g][q][r]) into the
+ * global top-k per query, same record format, on the engine's stream.
+ */
+int		nxsb_engine_merge_topk(nxsb_engine_t *, const void *d_in,
+		    uint32_t n_shards, uint32_t n_queries, uint32_t limit,
+		    void *d_out);
+
+/*
+ * Vocabulary image for fuzzy matching.  bk_* mirror the reference's BK-tree
+ * (built host-side by replaying bktree_insert in term-id order):
+ * parent term index (UINT32_MAX for the root), edge label to the parent,
+ * and rank in a full breadth-first walk with children by ascending label.
+ */
+int		nxsb_engine_load_vocab(nxsb_engine_t *, uint32_t n_terms,
+		    const char *blob, const uint32_t *term_off,
+		    const uint64_t *term_total, const uint32_t *bk_parent,
+		    const uint8_t *bk_edge, const uint32_t *bk_rank);
+
+/*
+ * Fuzzy-resolve n query strings (NUL-free byte strings q[i] = qblob +
+ * qoff[i] .. qoff[i+1]) against the whole vocabulary: out_term[i] = the term
+ * id the reference's idxterm_fuzzysearch would return (0 = none),
+ * out_dist[i] its edit distance, and -- optionally -- out_true[i] = the
+ * number of vocabulary terms within distance 2 (the true candidate count).
+ */
+int		nxsb_engine_fuzzy(nxsb_engine_t *, uint32_t n, const char *qblob,
+		    const uint32_t *qoff, uint32_t *out_term, uint32_t *out_dist,
+		    uint32_t *out_true);
+
+/* Milliseconds spent by the last batch_run / fuzzy call per kernel family
+ * (CUDA events on the engine's stream); names[i] are static strings.
+ * Returns the number of entries written (<= cap). */
+int		nxsb_engine_last_timings(nxsb_engine_t *, const char **names,
+		    float *ms, int cap);
+/* The same, summed over the last `last_runs` (<= 256) batch_run calls, so a
+ * caller can enqueue many runs back to back and read the per-kernel device
+ * time afterwards without synchronising in between. */
+int		nxsb_engine_timings(nxsb_engine_t *, uint32_t last_runs,
+		    const char **names, float *ms, int cap);
+/* Kernel launches issued by the engine since creation. */
+uint64_t	nxsb_engine_launch_count(const nxsb_engine_t *);
+
+#pragma GCC visibility pop
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

@@ -22,6 +22,9 @@
 extern "C" {
 #endif
 
+/* Everything declared here is exported; the rest of the library is hidden. */
+#pragma GCC visibility push(default)
+
 #define NXSB_CORPUS_SEED	UINT64_C(0x6E78735F42323030)	/* "nxs_B200" */
 
 /*
@@ -94,6 +97,42 @@ int		nxsb_write_dtmap_file(const char *path, const nxsb_corpus_t *);
  */
 nxsb_corpus_t *	nxsb_read_index_files(const char *terms_path,
 		    const char *dtmap_path);
+
+/*
+ * Flat mirror of the BK-tree the reference would build over a vocabulary by
+ * inserting the terms in id order (ref src/algo/bktree.c:160-217): for term
+ * index t, parent[t] (UINT32_MAX for the root), edge[t] = min(distance to
+ * the parent, 63) and rank[t] = position in a full breadth-first walk with
+ * children by ascending edge label.  This is the input of
+ * nxsb_engine_load_vocab().  Returns 0, or -1 on allocation failure.
+ */
+int		nxsb_bkmirror_build(const char *term_blob, const uint32_t *term_off,
+		    uint32_t n_terms, uint32_t *parent, uint8_t *edge,
+		    uint32_t *rank);
+
+/*
+ * Query-language introspection (the parser itself is internal).  Used by the
+ * tests that pin the lexer / grammar to the reference's golden cases
+ * (ref src/tests/t_queryparser.c:27-115).
+ *
+ * nxsb_query_lex:     token kinds in order (1 OR, 2 AND, 3 NOT, 4 '(', 5 ')',
+ *                     6 free-form string, 7 quoted string); returns the count.
+ * nxsb_query_dump:    the parse tree as "(AND (OR `A` `B`) `C`)", malloc'ed;
+ *                     NULL on a syntax error, *errmsg then holds a malloc'ed
+ *                     "syntax error near L:C: ..." message.
+ * nxsb_query_compile: what the search path hands to the GPU engine, without
+ *                     filters or term resolution: the distinct leaf strings in
+ *                     token-list order (NUL-separated into tokens_buf) and the
+ *                     postfix program over their slots.  Returns 0, or -1 on a
+ *                     syntax error / insufficient capacity.
+ */
+size_t		nxsb_query_lex(const char *query, int *kinds, size_t cap);
+char *		nxsb_query_dump(const char *query, char **errmsg);
+int		nxsb_query_compile(const char *query, char *tokens_buf,
+		    size_t buf_len, uint32_t *n_tokens, int32_t *prog,
+		    uint32_t prog_cap, uint32_t *n_prog);
+
+#pragma GCC visibility pop
 
 #ifdef __cplusplus
 }

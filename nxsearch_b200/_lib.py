@@ -1,0 +1,24 @@
+"""Locate and load libnxsearch.so (never silently substitutes anything)."""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+
+_LIB = None
+
+
+def library_path() -> Path:
+    return Path(__file__).resolve().parent / "lib" / "libnxsearch.so"
+
+
+def load_library() -> ctypes.CDLL:
+    """Load the in-tree shared object; raise if it has not been built."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not path.exists():
+            raise RuntimeError(
+                f"{path} is missing: build it with `python -m nxsearch_b200._build` "
+                "(there is no pure-Python or CPU fallback)")
+        _LIB = ctypes.CDLL(str(path))
+    return _LIB

@@ -1,0 +1,61 @@
+/*
+ * Shared device-side definitions of the sm_100a scoring engine.
+ *
+ * HBM layout of one shard image (see DESIGN.md "Data layout"):
+ *
+ *   post[P]        uint2 {doc, tfdl}: postings, term-major, ascending dense
+ *                  doc index within a term.  PACKED mode: tfdl = tf | dl<<16
+ *                  (both < 65535) so one 8-byte load carries everything BM25
+ *                  needs; WIDE mode (a tf or doc length >= 65535 exists):
+ *                  tfdl = tf and the length is gathered from doc_len[].
+ *   term_off[V+1]  u64 CSR offsets into post[]
+ *   df[V]          u32 GLOBAL document frequency (all shards)
+ *   idf_bm25[V], idf_tfidf[V]  f32, computed on the host in double exactly
+ *                  as ref ranking.c:91,172 does
+ *   skip_row[V]    i32: row in skip[] for terms with df_local >= DF_LONG
+ *   skip[R][T+1]   u32: first posting (relative to the term) whose doc lies
+ *                  in tile >= j -- the per-tile slice boundaries
+ *   doc_ids[N]     u64 external ids, ascending;  doc_len[N] u32
+ */
+#ifndef NXSB_GPU_COMMON_CUH
+#define NXSB_GPU_COMMON_CUH
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "nxsb200_gpu.h"
+
+#define TILE_DOCS	NXSB_TILE_DOCS		// 16384
+#define TILE_SHIFT	14
+#define TILE_WORDS	(TILE_DOCS / 32)
+#define DF_LONG		2048u			// permanent skip row threshold
+#define LOGTAB_N	256			// (float)log(c + 1) for c < 256
+#define SMALL_K_MAX	2048u			// optimised top-k path limit
+#define SORT_CAP	4096u			// keys sorted in shared memory
+
+static_assert((1u << TILE_SHIFT) == TILE_DOCS, "tile size");
+
+/* A resolved token instance of a batch: the result of the term lookup. */
+struct DTok {
+	unsigned long long	post_off;	// first posting of the term
+	const uint32_t *	skip;		// [ntiles + 1] slice boundaries
+	uint32_t		df_local;
+	float			idf;
+};
+
+/* 16-byte result record (also the NCCL all-gather payload). */
+struct Rec {
+	unsigned long long	doc_id;
+	float			score;
+	uint32_t		valid;
+};
+
+static_assert(sizeof(Rec) == 16, "record size");
+
+__device__ __forceinline__ unsigned long long
+make_key(float score, uint32_t doc)
+{
+	return ((unsigned long long)__float_as_uint(score) << 32) | doc;
+}
+
+#endif

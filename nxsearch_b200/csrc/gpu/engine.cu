@@ -1,0 +1,1051 @@
+/*
+ * nxsearch-b200 GPU engine: host-side orchestration behind the C ABI of
+ * include/nxsb200_gpu.h.  One engine = one CUDA device = one document shard.
+ *
+ * There is deliberately no CPU path in this file: every entry point either
+ * runs on the device or fails with an error message.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+
+#include "common.cuh"
+#include "build.cuh"
+#include "score.cuh"
+#include "fuzzy.cuh"
+
+#define CAND_ARENA_BYTES	(2ull << 30)	// candidate keys per sub-batch
+#define MAX_HANDLES		64
+#define EV_PER_RUN		8
+#define EV_RING			256
+
+static thread_local char g_last_error[512];
+
+struct Batch {
+	bool		used = false;
+	int		algo = 0;
+	uint32_t	limit = 0, n_q = 0, n_tok = 0, n_prog = 0;
+	uint32_t	max_tokens = 0;
+	uint64_t	bytes = 0;		// algorithmic bytes
+	std::vector<uint32_t> q_or, q_logic;	// host lists
+	QDesc *		d_queries = nullptr;
+	uint32_t *	d_tokens = nullptr;
+	int32_t *	d_prog = nullptr;
+	uint32_t *	d_qlist_or = nullptr, *d_qlist_logic = nullptr;
+	/* scratch + results */
+	DTok *		d_toks = nullptr;
+	uint32_t *	d_tmp_skip = nullptr;
+	unsigned long long *d_thr = nullptr;
+	uint32_t *	d_cand_count = nullptr;
+	uint32_t *	d_work = nullptr;	// [2] work counters
+	Rec *		d_recs = nullptr;
+	uint32_t *	d_counts = nullptr;
+};
+
+struct nxsb_engine {
+	int		device = 0;
+	cudaStream_t	own_stream = nullptr, stream = nullptr;
+	char		err[512] = { 0 };
+	uint64_t	launches = 0;
+	int		n_sms = 148;
+
+	/* shard image */
+	uint32_t	n_docs = 0, n_terms = 0, ntiles = 0, n_long = 0;
+	uint64_t	n_post = 0;
+	bool		wide = false, loaded = false;
+	uint2 *		d_post = nullptr;
+	unsigned long long *d_term_off = nullptr;
+	uint32_t *	d_df_local = nullptr;
+	float *		d_idf_bm25 = nullptr, *d_idf_tfidf = nullptr;
+	int32_t *	d_skip_row = nullptr;
+	uint32_t *	d_skip = nullptr;
+	unsigned long long *d_doc_ids = nullptr;
+	uint32_t *	d_doc_len = nullptr;
+	float *		d_logtab = nullptr;
+	std::vector<uint32_t> h_df_local, h_df;
+	uint64_t	token_count = 0;
+	uint32_t	doc_count = 0;
+	float		K0 = 0, K1 = 0;
+	bool		stats_valid = false;	// N > 0 and adl >= 1
+
+	/* candidate arena (shared by all batches) */
+	unsigned long long *d_cand = nullptr;
+	size_t		cand_bytes = 0;
+	unsigned long long *d_sort_tmp = nullptr;	// large-k path
+	size_t		sort_tmp_bytes = 0;
+	void *		d_cub_tmp = nullptr;
+	size_t		cub_tmp_bytes = 0;
+
+	Batch		batches[MAX_HANDLES];
+
+	/* vocabulary (fuzzy) */
+	FuzzyImage	fz;
+
+	/* timing of the last run */
+	/*
+	 * A ring of per-run event sets, so that a caller can time many
+	 * back-to-back runs without synchronising in between.
+	 */
+	struct RunEvents {
+		cudaEvent_t	ev[EV_PER_RUN] = { nullptr };
+		const char *	names[EV_PER_RUN] = { nullptr };
+		int		n = 0;
+	};
+	RunEvents	runs[EV_RING];
+	uint64_t	n_runs = 0;		// runs started so far
+};
+
+static int
+fail(nxsb_engine_t *e, const char *fmt, ...)
+{
+	va_list ap;
+
+	va_start(ap, fmt);
+	vsnprintf(e->err, sizeof(e->err), fmt, ap);
+	va_end(ap);
+	snprintf(g_last_error, sizeof(g_last_error), "%s", e->err);
+	return -1;
+}
+
+#define CK(e, call) do {						\
+	cudaError_t _rc = (call);					\
+	if (_rc != cudaSuccess)						\
+		return fail((e), "%s: %s (%s:%d)", #call,		\
+		    cudaGetErrorString(_rc), __FILE__, __LINE__);	\
+} while (0)
+
+template <typename T>
+static cudaError_t
+dev_alloc(T **p, size_t n)
+{
+	return cudaMalloc(reinterpret_cast<void **>(p), (n ? n : 1) * sizeof(T));
+}
+
+template <typename T>
+static void
+dev_free(T *&p)
+{
+	if (p)
+		cudaFree(p);
+	p = nullptr;
+}
+
+extern "C" int
+nxsb_gpu_device_count(void)
+{
+	int n = 0;
+
+	if (cudaGetDeviceCount(&n) != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+extern "C" const char *
+nxsb_last_error(void)
+{
+	return g_last_error;
+}
+
+extern "C" const char *
+nxsb_engine_errmsg(const nxsb_engine_t *e)
+{
+	return e ? e->err : g_last_error;
+}
+
+extern "C" uint64_t
+nxsb_engine_launch_count(const nxsb_engine_t *e)
+{
+	return e->launches;
+}
+
+extern "C" nxsb_engine_t *
+nxsb_engine_create(int device)
+{
+	int n = 0;
+	cudaError_t rc = cudaGetDeviceCount(&n);
+
+	if (rc != cudaSuccess || n == 0) {
+		snprintf(g_last_error, sizeof(g_last_error),
+		    "no CUDA device available (%s); the nxsearch-b200 engine has "
+		    "no CPU fallback", rc != cudaSuccess ? cudaGetErrorString(rc) :
+		    "device count is 0");
+		cudaGetLastError();
+		return nullptr;
+	}
+	if (device < 0 || device >= n) {
+		snprintf(g_last_error, sizeof(g_last_error),
+		    "CUDA device %d out of range (have %d)", device, n);
+		return nullptr;
+	}
+	nxsb_engine_t *e = new nxsb_engine();
+	cudaDeviceProp prop;
+
+	e->device = device;
+	if (cudaSetDevice(device) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+	    cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+		snprintf(g_last_error, sizeof(g_last_error), "CUDA init failed: %s",
+		    cudaGetErrorString(cudaGetLastError()));
+		delete e;
+		return nullptr;
+	}
+	e->stream = e->own_stream;
+	e->n_sms = prop.multiProcessorCount;
+	for (auto &r : e->runs)
+		for (int i = 0; i < EV_PER_RUN; i++)
+			cudaEventCreateWithFlags(&r.ev[i], cudaEventDefault);
+
+	/* (float)log(c + 1): the tf weight of ref ranking.c:90,168. */
+	float tab[LOGTAB_N];
+	for (int c = 0; c < LOGTAB_N; c++)
+		tab[c] = (float)log((double)(c + 1));
+	if (dev_alloc(&e->d_logtab, LOGTAB_N) != cudaSuccess ||
+	    cudaMemcpy(e->d_logtab, tab, sizeof(tab), cudaMemcpyHostToDevice) != cudaSuccess) {
+		snprintf(g_last_error, sizeof(g_last_error), "CUDA alloc failed");
+		delete e;
+		return nullptr;
+	}
+	return e;
+}
+
+static void
+free_image(nxsb_engine_t *e)
+{
+	dev_free(e->d_post);
+	dev_free(e->d_term_off);
+	dev_free(e->d_df_local);
+	dev_free(e->d_idf_bm25);
+	dev_free(e->d_idf_tfidf);
+	dev_free(e->d_skip_row);
+	dev_free(e->d_skip);
+	dev_free(e->d_doc_ids);
+	dev_free(e->d_doc_len);
+	e->loaded = false;
+}
+
+static void
+free_batch(Batch &b)
+{
+	dev_free(b.d_queries);
+	dev_free(b.d_tokens);
+	dev_free(b.d_prog);
+	dev_free(b.d_qlist_or);
+	dev_free(b.d_qlist_logic);
+	dev_free(b.d_toks);
+	dev_free(b.d_tmp_skip);
+	dev_free(b.d_thr);
+	dev_free(b.d_cand_count);
+	dev_free(b.d_work);
+	dev_free(b.d_recs);
+	dev_free(b.d_counts);
+	b = Batch();
+}
+
+extern "C" void
+nxsb_engine_destroy(nxsb_engine_t *e)
+{
+	if (!e)
+		return;
+	cudaSetDevice(e->device);
+	cudaStreamSynchronize(e->stream);
+	for (auto &b : e->batches)
+		if (b.used)
+			free_batch(b);
+	free_image(e);
+	fuzzy_free(e->fz);
+	dev_free(e->d_cand);
+	dev_free(e->d_sort_tmp);
+	if (e->d_cub_tmp)
+		cudaFree(e->d_cub_tmp);
+	dev_free(e->d_logtab);
+	for (auto &r : e->runs)
+		for (int i = 0; i < EV_PER_RUN; i++)
+			if (r.ev[i])
+				cudaEventDestroy(r.ev[i]);
+	if (e->own_stream)
+		cudaStreamDestroy(e->own_stream);
+	delete e;
+}
+
+extern "C" int
+nxsb_engine_set_stream(nxsb_engine_t *e, void *s)
+{
+	e->stream = s ? (cudaStream_t)s : e->own_stream;
+	return 0;
+}
+
+extern "C" int
+nxsb_engine_sync(nxsb_engine_t *e)
+{
+	CK(e, cudaSetDevice(e->device));
+	CK(e, cudaStreamSynchronize(e->stream));
+	return 0;
+}
+
+/*
+ * Global statistics -> per-term idf tables and the BM25 constants, in
+ * double on the host with the exact operand types of the reference
+ * (ranking.c:91: float division inside a double log; ranking.c:163: integer
+ * quotient; ranking.c:141-142: float literals widened to double).
+ */
+static int
+upload_stats(nxsb_engine_t *e)
+{
+	const uint32_t V = e->n_terms;
+	const unsigned long doc_count = e->doc_count;
+	std::vector<float> bm(V), tfidf(V);
+
+	e->stats_valid = false;
+	if (doc_count) {
+		const double adl = (double)(e->token_count / doc_count);
+		static const double k = 1.2f, b = 0.75f;
+
+		if (adl >= 1) {
+			e->K0 = (float)(k * (1 - b));
+			e->K1 = (float)(k * b / adl);
+			e->stats_valid = true;
+		}
+	}
+	for (uint32_t t = 0; t < V; t++) {
+		const unsigned long df = e->h_df[t];
+
+		if (!df || !doc_count) {
+			bm[t] = tfidf[t] = 0.f;
+			continue;
+		}
+		bm[t] = (float)log(((doc_count - df + 0.5) / (df + 0.5)) + 1);
+		/*
+		 * C semantics: float quotient, widened, DOUBLE log (in C++ a
+		 * float argument would select logf and lose the last ulp).
+		 */
+		tfidf[t] = (float)(log((double)((float)doc_count / (float)df)) + 1);
+	}
+	CK(e, cudaMemcpyAsync(e->d_idf_bm25, bm.data(), V * sizeof(float),
+	    cudaMemcpyHostToDevice, e->stream));
+	CK(e, cudaMemcpyAsync(e->d_idf_tfidf, tfidf.data(), V * sizeof(float),
+	    cudaMemcpyHostToDevice, e->stream));
+	CK(e, cudaStreamSynchronize(e->stream));
+	return 0;
+}
+
+extern "C" int
+nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
+{
+	const uint32_t N = sd->n_docs, V = sd->n_terms;
+	const uint64_t P = sd->doc_off ? sd->doc_off[N] : 0;
+	uint2 *d_pairs = nullptr, *d_vals_alt = nullptr;
+	unsigned long long *d_doc_off = nullptr;
+	uint32_t *d_keys = nullptr, *d_keys_alt = nullptr, *d_long = nullptr;
+	int rc = -1;
+
+	CK(e, cudaSetDevice(e->device));
+	CK(e, cudaStreamSynchronize(e->stream));
+	for (auto &b : e->batches)
+		if (b.used)
+			free_batch(b);
+	free_image(e);
+
+	e->n_docs = N;
+	e->n_terms = V;
+	e->n_post = P;
+	e->ntiles = (N + TILE_DOCS - 1) / TILE_DOCS;
+	if (e->ntiles == 0)
+		e->ntiles = 1;
+	e->token_count = sd->token_count;
+	e->doc_count = sd->doc_count;
+
+	/* Packed postings need every tf and doc length to fit 16 bits. */
+	e->wide = false;
+	for (uint32_t d = 0; d < N && !e->wide; d++)
+		e->wide = sd->doc_len[d] > 0xffffu;
+	for (uint64_t j = 0; j < P && !e->wide; j++)
+		e->wide = sd->pairs[2 * j + 1] > 0xffffu;
+
+	do {
+		if (dev_alloc(&d_pairs, P) || dev_alloc(&d_doc_off, (size_t)N + 1) ||
+		    dev_alloc(&e->d_doc_len, N) || dev_alloc(&e->d_doc_ids, N) ||
+		    dev_alloc(&d_keys, P) || dev_alloc(&d_keys_alt, P) ||
+		    dev_alloc(&e->d_post, P + 2) || dev_alloc(&d_vals_alt, P + 2) ||
+		    dev_alloc(&e->d_term_off, (size_t)V + 1) ||
+		    dev_alloc(&e->d_df_local, V) || dev_alloc(&e->d_idf_bm25, V) ||
+		    dev_alloc(&e->d_idf_tfidf, V) || dev_alloc(&e->d_skip_row, V)) {
+			fail(e, "device allocation failed while loading a shard of "
+			    "%u docs / %llu postings: %s", N, (unsigned long long)P,
+			    cudaGetErrorString(cudaGetLastError()));
+			break;
+		}
+		cudaStream_t st = e->stream;
+		if (cudaMemcpyAsync(d_pairs, sd->pairs, P * 8, cudaMemcpyHostToDevice, st) ||
+		    cudaMemcpyAsync(d_doc_off, sd->doc_off, ((size_t)N + 1) * 8, cudaMemcpyHostToDevice, st) ||
+		    cudaMemcpyAsync(e->d_doc_len, sd->doc_len, (size_t)N * 4, cudaMemcpyHostToDevice, st) ||
+		    cudaMemcpyAsync(e->d_doc_ids, sd->doc_ids, (size_t)N * 8, cudaMemcpyHostToDevice, st)) {
+			fail(e, "H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+			break;
+		}
+
+		if (N) {
+			const int grid = e->n_sms * 8;
+			if (e->wide)
+				expand_pairs_kernel<true><<<grid, 256, 0, st>>>(d_pairs,
+				    d_doc_off, e->d_doc_len, N, V, d_keys, d_vals_alt);
+			else
+				expand_pairs_kernel<false><<<grid, 256, 0, st>>>(d_pairs,
+				    d_doc_off, e->d_doc_len, N, V, d_keys, d_vals_alt);
+			e->launches++;
+		}
+
+		/* Stable sort by term; document order inside a term survives. */
+		int end_bit = 1;
+		while ((1ull << end_bit) <= V)
+			end_bit++;
+		cub::DoubleBuffer<uint32_t> kb(d_keys, d_keys_alt);
+		cub::DoubleBuffer<unsigned long long> vb(
+		    reinterpret_cast<unsigned long long *>(d_vals_alt),
+		    reinterpret_cast<unsigned long long *>(e->d_post));
+		size_t tmp = 0;
+		if (P) {
+			if (cub::DeviceRadixSort::SortPairs(nullptr, tmp, kb, vb,
+			    (unsigned long long)P, 0, end_bit, st) != cudaSuccess) {
+				fail(e, "cub sort sizing failed");
+				break;
+			}
+			if (tmp > e->cub_tmp_bytes) {
+				if (e->d_cub_tmp)
+					cudaFree(e->d_cub_tmp);
+				e->d_cub_tmp = nullptr;
+				if (cudaMalloc(&e->d_cub_tmp, tmp) != cudaSuccess) {
+					fail(e, "cub temp allocation (%zu bytes) failed", tmp);
+					break;
+				}
+				e->cub_tmp_bytes = tmp;
+			}
+			if (cub::DeviceRadixSort::SortPairs(e->d_cub_tmp, tmp, kb, vb,
+			    (unsigned long long)P, 0, end_bit, st) != cudaSuccess) {
+				fail(e, "cub sort failed: %s",
+				    cudaGetErrorString(cudaGetLastError()));
+				break;
+			}
+			e->launches += 8;
+			if (vb.Current() != reinterpret_cast<unsigned long long *>(e->d_post)) {
+				/* Result landed in the scratch buffer: swap roles. */
+				std::swap(e->d_post, d_vals_alt);
+			}
+		}
+		term_offsets_kernel<<<e->n_sms * 8, 256, 0, st>>>(kb.Current(), P, V,
+		    e->d_term_off);
+		local_df_kernel<<<(V + 255) / 256, 256, 0, st>>>(e->d_term_off, V,
+		    e->d_df_local);
+		e->launches += 2;
+
+		e->h_df_local.resize(V);
+		if (cudaMemcpyAsync(e->h_df_local.data(), e->d_df_local, (size_t)V * 4,
+		    cudaMemcpyDeviceToHost, st) || cudaStreamSynchronize(st)) {
+			fail(e, "image build failed: %s",
+			    cudaGetErrorString(cudaGetLastError()));
+			break;
+		}
+
+		/* Permanent skip rows for the long lists. */
+		std::vector<int32_t> row(V, -1);
+		std::vector<uint32_t> longs;
+		for (uint32_t t = 0; t < V; t++) {
+			if (e->h_df_local[t] >= DF_LONG) {
+				row[t] = (int32_t)longs.size();
+				longs.push_back(t);
+			}
+		}
+		e->n_long = longs.size();
+		if (dev_alloc(&e->d_skip, (size_t)e->n_long * (e->ntiles + 1)) ||
+		    dev_alloc(&d_long, e->n_long)) {
+			fail(e, "skip table allocation failed");
+			break;
+		}
+		cudaMemcpyAsync(e->d_skip_row, row.data(), (size_t)V * 4,
+		    cudaMemcpyHostToDevice, st);
+		if (e->n_long) {
+			cudaMemcpyAsync(d_long, longs.data(), (size_t)e->n_long * 4,
+			    cudaMemcpyHostToDevice, st);
+			build_skip_rows_kernel<<<e->n_long, 256, 0, st>>>(e->d_post,
+			    e->d_term_off, d_long, e->ntiles, e->d_skip);
+			e->launches++;
+		}
+		if (cudaStreamSynchronize(st) != cudaSuccess) {
+			fail(e, "skip table build failed: %s",
+			    cudaGetErrorString(cudaGetLastError()));
+			break;
+		}
+
+		if (sd->df)
+			e->h_df.assign(sd->df, sd->df + V);
+		else
+			e->h_df = e->h_df_local;
+		if (upload_stats(e) == -1)
+			break;
+		e->loaded = true;
+		rc = 0;
+	} while (0);
+
+	dev_free(d_pairs);
+	dev_free(d_doc_off);
+	dev_free(d_keys);
+	dev_free(d_keys_alt);
+	dev_free(d_vals_alt);
+	dev_free(d_long);
+	if (rc != 0)
+		free_image(e);
+	return rc;
+}
+
+extern "C" int
+nxsb_engine_get_df(nxsb_engine_t *e, uint32_t *df, uint32_t n_terms)
+{
+	if (!e->loaded || n_terms != e->n_terms)
+		return fail(e, "get_df: no image or vocabulary size mismatch");
+	memcpy(df, e->h_df_local.data(), (size_t)n_terms * 4);
+	return 0;
+}
+
+extern "C" int
+nxsb_engine_set_global_stats(nxsb_engine_t *e, const uint32_t *df,
+    uint32_t n_terms, uint64_t token_count, uint32_t doc_count)
+{
+	if (!e->loaded || n_terms != e->n_terms)
+		return fail(e, "set_global_stats: no image or vocabulary size mismatch");
+	CK(e, cudaSetDevice(e->device));
+	e->h_df.assign(df, df + n_terms);
+	e->token_count = token_count;
+	e->doc_count = doc_count;
+	return upload_stats(e);
+}
+
+/*
+ * Batches.
+ */
+
+static bool
+is_pure_or(const nxsb_batch_t *b, const nxsb_query_t &q)
+{
+	/* Every token pushed at least once, only OR operators. */
+	uint32_t seen = 0;
+
+	if (q.n_tokens > 32)
+		return false;
+	for (uint32_t i = 0; i < q.n_prog; i++) {
+		const int32_t op = b->prog[q.prog_off + i];
+
+		if (op >= 0)
+			seen |= 1u << op;
+		else if (op != NXSB_OP_OR)
+			return false;
+	}
+	return seen == (q.n_tokens == 32 ? 0xffffffffu : (1u << q.n_tokens) - 1);
+}
+
+static int
+validate_batch(nxsb_engine_t *e, const nxsb_batch_t *b)
+{
+	if (!e->loaded)
+		return fail(e, "no shard image loaded");
+	if (b->limit == 0)
+		return fail(e, "limit must be >= 1");
+	if (b->algo != NXSB_ALGO_BM25 && b->algo != NXSB_ALGO_TFIDF)
+		return fail(e, "unknown ranking algorithm %d", b->algo);
+	for (uint32_t i = 0; i < b->n_queries; i++) {
+		const nxsb_query_t &q = b->queries[i];
+		int depth = 0, maxdepth = 0;
+
+		if (q.n_tokens > NXSB_MAX_QUERY_TOKENS || q.n_prog > NXSB_MAX_QUERY_PROG)
+			return fail(e, "query %u exceeds the engine limits "
+			    "(%u tokens / %u operators)", i, NXSB_MAX_QUERY_TOKENS,
+			    NXSB_MAX_QUERY_PROG);
+		if ((uint64_t)q.tok_off + q.n_tokens > b->n_tokens ||
+		    (uint64_t)q.prog_off + q.n_prog > b->n_prog)
+			return fail(e, "query %u: descriptor out of range", i);
+		for (uint32_t c = 0; c < q.n_prog; c++) {
+			const int32_t op = b->prog[q.prog_off + c];
+
+			if (op >= 0) {
+				if ((uint32_t)op >= q.n_tokens)
+					return fail(e, "query %u: bad token slot", i);
+				depth++;
+			} else if (op == NXSB_OP_EMPTY) {
+				depth++;
+			} else if (op >= NXSB_OP_ANDNOT) {
+				if (depth < 2)
+					return fail(e, "query %u: malformed program", i);
+				depth--;
+			} else {
+				return fail(e, "query %u: unknown operator", i);
+			}
+			maxdepth = std::max(maxdepth, depth);
+		}
+		if (q.n_prog && depth != 1)
+			return fail(e, "query %u: malformed program", i);
+		if (maxdepth > NXSB_MAX_QUERY_TOKENS + 1)
+			return fail(e, "query %u: expression too deep", i);
+	}
+	return 0;
+}
+
+extern "C" int
+nxsb_engine_batch_upload(nxsb_engine_t *e, const nxsb_batch_t *b)
+{
+	int h = -1;
+
+	CK(e, cudaSetDevice(e->device));
+	if (validate_batch(e, b) == -1)
+		return -1;
+	for (int i = 0; i < MAX_HANDLES; i++)
+		if (!e->batches[i].used) {
+			h = i;
+			break;
+		}
+	if (h < 0)
+		return fail(e, "too many resident batches");
+
+	Batch &B = e->batches[h];
+	B.used = true;
+	B.algo = b->algo;
+	B.limit = b->limit;
+	B.n_q = b->n_queries;
+	B.n_tok = b->n_tokens;
+	B.n_prog = b->n_prog;
+	B.max_tokens = 1;
+	B.bytes = 0;
+
+	for (uint32_t i = 0; i < b->n_queries; i++) {
+		const nxsb_query_t &q = b->queries[i];
+
+		/* search.c:224-226: nothing resolved => empty result. */
+		if (q.n_tokens == 0 || q.n_prog == 0)
+			continue;
+		if (is_pure_or(b, q)) {
+			B.q_or.push_back(i);
+		} else {
+			B.q_logic.push_back(i);
+			B.max_tokens = std::max(B.max_tokens, q.n_tokens);
+		}
+		for (uint32_t j = 0; j < q.n_tokens; j++) {
+			const uint32_t id = b->tokens[q.tok_off + j];
+			if (id >= 1 && id <= e->n_terms)
+				B.bytes += 8ull * e->h_df[id - 1];
+		}
+	}
+
+	const uint32_t k = B.limit;
+	const size_t nrec = (size_t)std::max(B.n_q, 1u) * k;
+	static_assert(sizeof(QDesc) == sizeof(nxsb_query_t), "descriptor layout");
+
+	if (dev_alloc(&B.d_queries, B.n_q) || dev_alloc(&B.d_tokens, B.n_tok) ||
+	    dev_alloc(&B.d_prog, B.n_prog) ||
+	    dev_alloc(&B.d_qlist_or, B.q_or.size()) ||
+	    dev_alloc(&B.d_qlist_logic, B.q_logic.size()) ||
+	    dev_alloc(&B.d_toks, B.n_tok) ||
+	    dev_alloc(&B.d_tmp_skip, (size_t)B.n_tok * (e->ntiles + 1)) ||
+	    dev_alloc(&B.d_thr, B.n_q) || dev_alloc(&B.d_cand_count, B.n_q) ||
+	    dev_alloc(&B.d_work, 1) || dev_alloc(&B.d_recs, nrec) ||
+	    dev_alloc(&B.d_counts, B.n_q)) {
+		free_batch(B);
+		return fail(e, "device allocation failed for a batch of %u queries "
+		    "(limit %u): %s", b->n_queries, k,
+		    cudaGetErrorString(cudaGetLastError()));
+	}
+	cudaStream_t st = e->stream;
+	cudaMemcpyAsync(B.d_queries, b->queries, (size_t)B.n_q * sizeof(QDesc),
+	    cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(B.d_tokens, b->tokens, (size_t)B.n_tok * 4,
+	    cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(B.d_prog, b->prog, (size_t)B.n_prog * 4,
+	    cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(B.d_qlist_or, B.q_or.data(), B.q_or.size() * 4,
+	    cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(B.d_qlist_logic, B.q_logic.data(), B.q_logic.size() * 4,
+	    cudaMemcpyHostToDevice, st);
+	if (cudaStreamSynchronize(st) != cudaSuccess) {
+		free_batch(B);
+		return fail(e, "batch upload failed: %s",
+		    cudaGetErrorString(cudaGetLastError()));
+	}
+	return h;
+}
+
+extern "C" int
+nxsb_engine_batch_release(nxsb_engine_t *e, int h)
+{
+	if (h < 0 || h >= MAX_HANDLES || !e->batches[h].used)
+		return fail(e, "bad batch handle %d", h);
+	cudaSetDevice(e->device);
+	cudaStreamSynchronize(e->stream);
+	free_batch(e->batches[h]);
+	return 0;
+}
+
+extern "C" uint64_t
+nxsb_engine_batch_bytes(nxsb_engine_t *e, int h)
+{
+	if (h < 0 || h >= MAX_HANDLES || !e->batches[h].used)
+		return 0;
+	return e->batches[h].bytes;
+}
+
+static void
+begin_run(nxsb_engine_t *e)
+{
+	e->n_runs++;
+	e->runs[(e->n_runs - 1) % EV_RING].n = 0;
+}
+
+static void
+mark(nxsb_engine_t *e, const char *name)
+{
+	nxsb_engine::RunEvents &r = e->runs[(e->n_runs - 1) % EV_RING];
+
+	if (r.n < EV_PER_RUN) {
+		r.names[r.n] = name;
+		cudaEventRecord(r.ev[r.n], e->stream);
+		r.n++;
+	}
+}
+
+template <bool LOGIC>
+static int
+launch_tiles(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
+    uint32_t k_tile, uint64_t cand_cap)
+{
+	ScoreParams p;
+	size_t smem = (size_t)TILE_DOCS * 4;
+
+	p.post = e->d_post;
+	p.toks = B.d_toks;
+	p.queries = B.d_queries;
+	p.prog = B.d_prog;
+	p.qlist = d_qlist;
+	p.n_q = n_q;
+	p.ntiles = e->ntiles;
+	p.k = k_tile;
+	p.thr = B.d_thr;
+	p.cand_count = B.d_cand_count;
+	p.cand = e->d_cand;
+	p.cand_cap = cand_cap;
+	p.work_counter = B.d_work;
+	p.logtab = e->d_logtab;
+	p.doc_len = e->d_doc_len;
+	p.K0 = e->K0;
+	p.K1 = e->K1;
+	p.algo = B.algo;
+	p.max_tokens = B.max_tokens;
+	if (LOGIC)
+		smem += ((size_t)B.max_tokens + 1) * TILE_WORDS * 4;
+
+	auto kern = e->wide ? score_tiles_kernel<LOGIC, true>
+	    : score_tiles_kernel<LOGIC, false>;
+	int per_sm = 0;
+
+	CK(e, cudaFuncSetAttribute(kern,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	CK(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern,
+	    TILE_THREADS, smem));
+	if (per_sm < 1)
+		return fail(e, "scoring kernel does not fit an SM (smem %zu)", smem);
+
+	const unsigned long long items = (unsigned long long)n_q * e->ntiles;
+	unsigned grid = (unsigned)std::min<unsigned long long>(items,
+	    (unsigned long long)e->n_sms * per_sm);
+
+	CK(e, cudaMemsetAsync(B.d_work, 0, 4, e->stream));
+	CK(e, cudaMemsetAsync(B.d_thr, 0, (size_t)n_q * 8, e->stream));
+	CK(e, cudaMemsetAsync(B.d_cand_count, 0, (size_t)n_q * 4, e->stream));
+	mark(e, "score_tiles");
+	kern<<<grid, TILE_THREADS, smem, e->stream>>>(p);
+	e->launches++;
+	CK(e, cudaGetLastError());
+	return 0;
+}
+
+/*
+ * Score one list of queries (pure-OR or boolean) in chunks bounded by the
+ * candidate arena: tiles -> per-query final top-k.
+ */
+template <bool LOGIC>
+static int
+run_list(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list,
+    Rec *d_recs)
+{
+	cudaStream_t st = e->stream;
+	const uint32_t k = B.limit;
+	const bool small_k = k <= SMALL_K_MAX;
+	const uint32_t k_tile = small_k ? k : TILE_DOCS;
+	const uint64_t cand_cap = (uint64_t)e->ntiles * k_tile;
+	const size_t per_q = cand_cap * 8;
+
+	if (n_list == 0)
+		return 0;
+
+	size_t want = std::max(per_q, std::min<size_t>(CAND_ARENA_BYTES, per_q * n_list));
+	if (want > e->cand_bytes) {
+		dev_free(e->d_cand);
+		e->cand_bytes = 0;
+		if (dev_alloc(&e->d_cand, want / 8) != cudaSuccess)
+			return fail(e, "candidate arena allocation (%zu bytes) failed", want);
+		e->cand_bytes = want;
+	}
+	const uint32_t chunk = (uint32_t)std::min<size_t>(n_list, e->cand_bytes / per_q);
+
+	for (uint32_t q0 = 0; q0 < n_list; q0 += chunk) {
+		const uint32_t n = std::min(chunk, n_list - q0);
+
+		if (launch_tiles<LOGIC>(e, B, d_qlist + q0, n, k_tile, cand_cap) == -1)
+			return -1;
+		mark(e, "topk");
+		if (small_k) {
+			finalize_topk_kernel<<<n, 256, 0, st>>>(e->d_cand, cand_cap,
+			    B.d_cand_count, d_qlist + q0, k, e->d_doc_ids, d_recs,
+			    B.d_counts);
+			e->launches++;
+			CK(e, cudaGetLastError());
+			continue;
+		}
+
+		/*
+		 * Large limits: every matching document was emitted; sort each
+		 * query's keys on the device (CUB) and cut at the limit.
+		 */
+		std::vector<uint32_t> cnt(n), qids(n);
+		CK(e, cudaMemcpyAsync(cnt.data(), B.d_cand_count, (size_t)n * 4,
+		    cudaMemcpyDeviceToHost, st));
+		CK(e, cudaMemcpyAsync(qids.data(), d_qlist + q0, (size_t)n * 4,
+		    cudaMemcpyDeviceToHost, st));
+		CK(e, cudaStreamSynchronize(st));
+		if (per_q > e->sort_tmp_bytes) {
+			dev_free(e->d_sort_tmp);
+			e->sort_tmp_bytes = 0;
+			if (dev_alloc(&e->d_sort_tmp, cand_cap) != cudaSuccess)
+				return fail(e, "sort buffer allocation failed");
+			e->sort_tmp_bytes = per_q;
+		}
+		for (uint32_t i = 0; i < n; i++) {
+			const unsigned long long *keys = e->d_cand + (size_t)i * cand_cap;
+			size_t tmp = 0;
+
+			if (cnt[i]) {
+				cub::DeviceRadixSort::SortKeysDescending(nullptr, tmp, keys,
+				    e->d_sort_tmp, (unsigned long long)cnt[i], 0, 64, st);
+				if (tmp > e->cub_tmp_bytes) {
+					if (e->d_cub_tmp)
+						cudaFree(e->d_cub_tmp);
+					e->d_cub_tmp = nullptr;
+					e->cub_tmp_bytes = 0;
+					if (cudaMalloc(&e->d_cub_tmp, tmp) != cudaSuccess)
+						return fail(e, "cub temp allocation failed");
+					e->cub_tmp_bytes = tmp;
+				}
+				cub::DeviceRadixSort::SortKeysDescending(e->d_cub_tmp, tmp,
+				    keys, e->d_sort_tmp, (unsigned long long)cnt[i], 0, 64, st);
+				e->launches += 8;
+			}
+			emit_sorted_kernel<<<std::max(1u, std::min(1024u, (k + 255) / 256)),
+			    256, 0, st>>>(e->d_sort_tmp, cnt[i], k, e->d_doc_ids,
+			    d_recs + (size_t)qids[i] * k, B.d_counts + qids[i]);
+			e->launches++;
+			CK(e, cudaGetLastError());
+		}
+	}
+	return 0;
+}
+
+static int
+run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
+{
+	cudaStream_t st = e->stream;
+	const uint32_t n_active = B.q_or.size() + B.q_logic.size();
+	/* ranking.c:86,156-166: N == 0 (or, BM25, adl < 1) => nothing scores. */
+	const bool can_score = B.algo == NXSB_ALGO_BM25 ? e->stats_valid
+	    : e->doc_count != 0;
+
+	begin_run(e);
+	mark(e, "resolve");
+
+	/* Results start out empty; queries that score nothing stay so. */
+	CK(e, cudaMemsetAsync(d_recs, 0,
+	    (size_t)std::max(B.n_q, 1u) * B.limit * sizeof(Rec), st));
+	CK(e, cudaMemsetAsync(B.d_counts, 0, (size_t)std::max(B.n_q, 1u) * 4, st));
+	if (n_active == 0 || !can_score) {
+		mark(e, "end");
+		return 0;
+	}
+
+	resolve_tokens_kernel<<<(B.n_tok + 255) / 256, 256, 0, st>>>(
+	    B.d_tokens, B.n_tok, e->n_terms, e->d_term_off, e->d_skip_row,
+	    e->d_skip, B.d_tmp_skip,
+	    B.algo == NXSB_ALGO_BM25 ? e->d_idf_bm25 : e->d_idf_tfidf,
+	    e->ntiles, B.d_toks);
+	build_temp_skips_kernel<<<B.n_tok, 128, 0, st>>>(e->d_post, B.d_toks,
+	    B.d_tmp_skip, e->ntiles);
+	e->launches += 2;
+	CK(e, cudaGetLastError());
+
+	if (run_list<false>(e, B, B.d_qlist_or, B.q_or.size(), d_recs) == -1 ||
+	    run_list<true>(e, B, B.d_qlist_logic, B.q_logic.size(), d_recs) == -1)
+		return -1;
+	mark(e, "end");
+	return 0;
+}
+
+extern "C" int
+nxsb_engine_batch_run(nxsb_engine_t *e, int h, void *d_recs)
+{
+	if (h < 0 || h >= MAX_HANDLES || !e->batches[h].used)
+		return fail(e, "bad batch handle %d", h);
+	CK(e, cudaSetDevice(e->device));
+	Batch &B = e->batches[h];
+	return run_batch(e, B, d_recs ? (Rec *)d_recs : B.d_recs);
+}
+
+extern "C" int
+nxsb_engine_batch_fetch(nxsb_engine_t *e, int h, uint32_t *counts,
+    uint64_t *ids, float *scores)
+{
+	if (h < 0 || h >= MAX_HANDLES || !e->batches[h].used)
+		return fail(e, "bad batch handle %d", h);
+	Batch &B = e->batches[h];
+	const size_t nrec = (size_t)B.n_q * B.limit;
+	std::vector<Rec> recs(nrec);
+
+	CK(e, cudaSetDevice(e->device));
+	CK(e, cudaMemcpyAsync(recs.data(), B.d_recs, nrec * sizeof(Rec),
+	    cudaMemcpyDeviceToHost, e->stream));
+	CK(e, cudaMemcpyAsync(counts, B.d_counts, (size_t)B.n_q * 4,
+	    cudaMemcpyDeviceToHost, e->stream));
+	CK(e, cudaStreamSynchronize(e->stream));
+	for (size_t i = 0; i < nrec; i++) {
+		ids[i] = recs[i].doc_id;
+		scores[i] = recs[i].score;
+	}
+	return 0;
+}
+
+extern "C" int
+nxsb_engine_search(nxsb_engine_t *e, const nxsb_batch_t *b, uint32_t *counts,
+    uint64_t *ids, float *scores)
+{
+	const int h = nxsb_engine_batch_upload(e, b);
+	int rc;
+
+	if (h < 0)
+		return -1;
+	rc = nxsb_engine_batch_run(e, h, nullptr);
+	if (rc == 0)
+		rc = nxsb_engine_batch_fetch(e, h, counts, ids, scores);
+	char saved[sizeof(e->err)];
+	memcpy(saved, e->err, sizeof(saved));
+	nxsb_engine_batch_release(e, h);
+	if (rc != 0)
+		memcpy(e->err, saved, sizeof(saved));
+	return rc;
+}
+
+extern "C" int
+nxsb_engine_merge_topk(nxsb_engine_t *e, const void *d_in, uint32_t n_shards,
+    uint32_t n_queries, uint32_t limit, void *d_out)
+{
+	const unsigned long long total = (unsigned long long)n_queries * n_shards * limit;
+
+	CK(e, cudaSetDevice(e->device));
+	CK(e, cudaMemsetAsync(d_out, 0, (size_t)n_queries * limit * sizeof(Rec), e->stream));
+	if (total) {
+		merge_topk_kernel<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(
+		    (const Rec *)d_in, n_shards, n_queries, limit, (Rec *)d_out);
+		e->launches++;
+		CK(e, cudaGetLastError());
+	}
+	return 0;
+}
+
+extern "C" int
+nxsb_engine_timings(nxsb_engine_t *e, uint32_t last_runs, const char **names,
+    float *ms, int cap)
+{
+	int n = 0;
+
+	if (cudaStreamSynchronize(e->stream) != cudaSuccess)
+		return 0;
+	if (last_runs > e->n_runs)
+		last_runs = (uint32_t)e->n_runs;
+	if (last_runs > EV_RING)
+		last_runs = EV_RING;
+	for (uint64_t run = e->n_runs - last_runs; run < e->n_runs; run++) {
+		const nxsb_engine::RunEvents &r = e->runs[run % EV_RING];
+
+		for (int i = 0; i + 1 < r.n; i++) {
+			float t = 0;
+			int k;
+
+			if (cudaEventElapsedTime(&t, r.ev[i], r.ev[i + 1]) != cudaSuccess)
+				continue;
+			for (k = 0; k < n; k++)
+				if (strcmp(names[k], r.names[i]) == 0)
+					break;
+			if (k == n) {
+				if (n == cap)
+					continue;
+				names[n] = r.names[i];
+				ms[n] = 0;
+				n++;
+			}
+			ms[k] += t;
+		}
+	}
+	return n;
+}
+
+extern "C" int
+nxsb_engine_last_timings(nxsb_engine_t *e, const char **names, float *ms, int cap)
+{
+	return nxsb_engine_timings(e, 1, names, ms, cap);
+}
+
+/*
+ * Fuzzy matching entry points (kernels in fuzzy.cuh).
+ */
+
+extern "C" int
+nxsb_engine_load_vocab(nxsb_engine_t *e, uint32_t n_terms, const char *blob,
+    const uint32_t *term_off, const uint64_t *term_total,
+    const uint32_t *bk_parent, const uint8_t *bk_edge, const uint32_t *bk_rank)
+{
+	CK(e, cudaSetDevice(e->device));
+	if (fuzzy_load(e->fz, n_terms, blob, term_off, term_total, bk_parent,
+	    bk_edge, bk_rank, e->stream) != 0)
+		return fail(e, "vocabulary upload failed: %s",
+		    cudaGetErrorString(cudaGetLastError()));
+	return 0;
+}
+
+extern "C" int
+nxsb_engine_fuzzy(nxsb_engine_t *e, uint32_t n, const char *qblob,
+    const uint32_t *qoff, uint32_t *out_term, uint32_t *out_dist,
+    uint32_t *out_true)
+{
+	CK(e, cudaSetDevice(e->device));
+	if (!e->fz.loaded)
+		return fail(e, "no vocabulary image loaded");
+	begin_run(e);
+	mark(e, "fuzzy_scan");
+	int launches = 0;
+	if (fuzzy_run(e->fz, n, qblob, qoff, out_term, out_dist, out_true,
+	    e->stream, e->n_sms, &launches) != 0)
+		return fail(e, "fuzzy scan failed: %s",
+		    cudaGetErrorString(cudaGetLastError()));
+	e->launches += launches;
+	mark(e, "end");
+	return 0;
+}

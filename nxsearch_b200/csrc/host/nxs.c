@@ -1,0 +1,416 @@
+/*
+ * Instance, error slot and index lifecycle: the public entry points of
+ * ref src/core/nxs.c with the same directory layout
+ * ($basedir/data/<index>/{params.db,nxsterms,nxsdtmap}), defaults and error
+ * codes.  The search entry points live in search.c.
+ */
+#define _GNU_SOURCE
+#include <sys/stat.h>
+
+#include <ctype.h>
+#include <errno.h>
+#include <inttypes.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <strings.h>
+#include <unistd.h>
+
+#include "index.h"
+
+static const char *default_filters[] = { "normalizer", "stopwords", "stemmer" };
+
+int
+str_isalnumdu(const char *s)
+{
+	for (; *s; s++) {
+		if (!isalnum((unsigned char)*s) && *s != '-' && *s != '_')
+			return -1;
+	}
+	return 0;
+}
+
+void
+nxs_clear_error(nxs_t *nxs)
+{
+	free(nxs->errmsg);
+	nxs->errmsg = NULL;
+	nxs->errcode = NXS_ERR_SUCCESS;
+}
+
+static void
+set_error_v(nxs_t *nxs, nxs_err_t code, int sys_errno, const char *fmt, va_list ap)
+{
+	char *s = NULL, *msg = NULL;
+
+	if (vasprintf(&s, fmt, ap) == -1)
+		s = NULL;
+	if (sys_errno >= 0 && s) {
+		if (asprintf(&msg, "%s: %s", s, strerror(sys_errno)) == -1)
+			msg = NULL;
+		free(s);
+	} else {
+		msg = s;
+	}
+	if (!nxs) {
+		free(msg);
+		return;
+	}
+	free(nxs->errmsg);
+	nxs->errmsg = msg;
+	nxs->errcode = code;
+}
+
+void
+nxs_set_error(nxs_t *nxs, nxs_err_t code, const char *fmt, ...)
+{
+	va_list ap;
+
+	va_start(ap, fmt);
+	set_error_v(nxs, code, -1, fmt, ap);
+	va_end(ap);
+}
+
+void
+nxs_set_syserror(nxs_t *nxs, nxs_err_t code, const char *fmt, ...)
+{
+	const int e = errno;
+	va_list ap;
+
+	va_start(ap, fmt);
+	set_error_v(nxs, code, e, fmt, ap);
+	va_end(ap);
+}
+
+void
+nxs_error_checkpoint(nxs_t *nxs)
+{
+	/* Error paths that declared nothing get a generic fatal (nxs.c:162). */
+	if (!nxs->errcode)
+		nxs_set_syserror(nxs, NXS_ERR_FATAL, "internal error; last system errno");
+}
+
+NXS_API nxs_err_t
+nxs_get_error(const nxs_t *nxs, const char **msg)
+{
+	if (msg)
+		*msg = nxs->errmsg;
+	return nxs->errcode;
+}
+
+NXS_API nxs_t *
+nxs_open(const char *basedir)
+{
+	nxs_t *nxs = calloc(1, sizeof(*nxs));
+	const char *s;
+	char *path = NULL;
+
+	if (!nxs)
+		return NULL;
+	s = basedir ? basedir : getenv("NXS_BASEDIR");
+	if (!s || (nxs->basedir = realpath(s, NULL)) == NULL)
+		goto err;
+	if (asprintf(&path, "%s/data", nxs->basedir) == -1)
+		goto err;
+	if (mkdir(path, 0755) == -1 && errno != EEXIST)
+		goto err;
+	free(path);
+	if ((s = getenv("NXS_GPU_DEVICE")) != NULL)
+		nxs->device = atoi(s);
+	return nxs;
+err:
+	free(path);
+	free(nxs->basedir);
+	free(nxs);
+	return NULL;
+}
+
+NXS_API void
+nxs_close(nxs_t *nxs)
+{
+	while (nxs->indexes)
+		nxs_index_close(nxs->indexes);
+	free(nxs->basedir);
+	free(nxs->errmsg);
+	free(nxs);
+}
+
+NXS_API int
+nxs_luafilter_load(nxs_t *nxs, const char *name, const char *code)
+{
+	(void)name; (void)code;
+	nxs_clear_error(nxs);
+	nxs_set_error(nxs, NXS_ERR_INVALID,
+	    "Lua filters are not supported by the nxsearch-b200 build");
+	return -1;
+}
+
+static nxs_index_t *
+find_open_index(nxs_t *nxs, const char *name)
+{
+	for (nxs_index_t *i = nxs->indexes; i; i = i->next) {
+		if (strcmp(i->name, name) == 0)
+			return i;
+	}
+	return NULL;
+}
+
+NXS_API nxs_index_t *
+nxs_index_create(nxs_t *nxs, const char *name, nxs_params_t *params)
+{
+	nxs_params_t *def_params = NULL;
+	const char **filters = NULL;
+	nxs_index_t *idx = NULL;
+	size_t nfilters;
+	char *path = NULL;
+
+	nxs_clear_error(nxs);
+	if (str_isalnumdu(name) == -1) {
+		nxs_set_error(nxs, NXS_ERR_INVALID, "invalid characters in index name");
+		return NULL;
+	}
+	if (asprintf(&path, "%s/data/%s", nxs->basedir, name) == -1)
+		return NULL;
+	if (mkdir(path, 0755) == -1) {
+		if (errno == EEXIST)
+			nxs_set_syserror(nxs, NXS_ERR_EXISTS,
+			    "index `%s' already exists", name);
+		else
+			nxs_set_syserror(nxs, NXS_ERR_SYSTEM,
+			    "could not create directory at %s", path);
+		goto out;
+	}
+	free(path);
+	path = NULL;
+
+	/* Defaults (nxs.c:249-268). */
+	if (!params) {
+		if ((def_params = nxs_params_create()) == NULL)
+			goto out;
+		params = def_params;
+	}
+	filters = nxs_params_get_strlist(params, "filters", &nfilters);
+	if (!filters && nxs_params_set_strlist(params, "filters",
+	    default_filters, 3) == -1)
+		goto out;
+	if (!nxs_params_get_str(params, "algo") &&
+	    nxs_params_set_str(params, "algo", NXS_DEFAULT_RANKING_ALGO) == -1)
+		goto out;
+	if (!nxs_params_get_str(params, "lang") &&
+	    nxs_params_set_str(params, "lang", NXS_DEFAULT_LANGUAGE) == -1)
+		goto out;
+
+	if (asprintf(&path, "%s/data/%s/params.db", nxs->basedir, name) == -1)
+		goto out;
+	if (nxs_params_serialize(nxs, params, path) == -1)
+		goto out;
+	idx = nxs_index_open(nxs, name);
+out:
+	if (!idx)
+		nxs_error_checkpoint(nxs);
+	if (def_params)
+		nxs_params_release(def_params);
+	free(filters);
+	free(path);
+	return idx;
+}
+
+NXS_API int
+nxs_index_destroy(nxs_t *nxs, const char *name)
+{
+	static const char *files[] = { "params.db", "nxsterms", "nxsdtmap", "" };
+	int ret = -1;
+
+	nxs_clear_error(nxs);
+	if (str_isalnumdu(name) == -1) {
+		nxs_set_error(nxs, NXS_ERR_INVALID, "invalid characters in index name");
+		return -1;
+	}
+	for (unsigned i = 0; i < 4; i++) {
+		char *path;
+		int rc;
+
+		if (asprintf(&path, "%s/data/%s/%s", nxs->basedir, name, files[i]) == -1)
+			goto out;
+		rc = i < 3 ? unlink(path) : rmdir(path);
+		if (rc == -1) {
+			nxs_set_syserror(nxs, NXS_ERR_SYSTEM, "could not remove `%s'", path);
+			free(path);
+			goto out;
+		}
+		free(path);
+	}
+	ret = 0;
+out:
+	if (ret != 0)
+		nxs_error_checkpoint(nxs);
+	return ret;
+}
+
+static int
+algo_id(const char *name)
+{
+	if (strcasecmp(name, "TF-IDF") == 0)
+		return NXSB_ALGO_TFIDF;
+	if (strcasecmp(name, "BM25") == 0)
+		return NXSB_ALGO_BM25;
+	return -1;
+}
+
+NXS_API nxs_index_t *
+nxs_index_open(nxs_t *nxs, const char *name)
+{
+	nxs_index_t *idx;
+	struct stat sb;
+	const char *algo;
+	char *path = NULL;
+	int ret;
+
+	nxs_clear_error(nxs);
+	if (str_isalnumdu(name) == -1) {
+		nxs_set_error(nxs, NXS_ERR_INVALID, "invalid characters in index name");
+		return NULL;
+	}
+	if (find_open_index(nxs, name)) {
+		nxs_set_error(nxs, NXS_ERR_EXISTS, "index `%s' is already open", name);
+		return NULL;
+	}
+	if ((idx = calloc(1, sizeof(*idx))) == NULL) {
+		nxs_error_checkpoint(nxs);
+		return NULL;
+	}
+	idx->nxs = nxs;
+	idx->algo = -1;
+
+	if (asprintf(&path, "%s/data/%s/params.db", nxs->basedir, name) == -1)
+		goto err;
+	if (stat(path, &sb) == -1 && errno == ENOENT) {
+		nxs_set_error(nxs, NXS_ERR_MISSING, "index `%s' does not exist", name);
+		goto err;
+	}
+	idx->params = nxs_params_unserialize(nxs, path);
+	free(path);
+	path = NULL;
+	if (!idx->params)
+		goto err;
+	if ((algo = nxs_params_get_str(idx->params, "algo")) == NULL) {
+		nxs_set_error(nxs, NXS_ERR_FATAL, "corrupted index params");
+		goto err;
+	}
+	idx->algo = algo_id(algo);
+	if ((idx->fp = filter_pipeline_create(nxs, idx->params)) == NULL)
+		goto err;
+
+	if (asprintf(&path, "%s/data/%s/nxsterms", nxs->basedir, name) == -1)
+		goto err;
+	ret = idx_terms_open(idx, path);
+	free(path);
+	path = NULL;
+	if (ret == -1)
+		goto err;
+	if (asprintf(&path, "%s/data/%s/nxsdtmap", nxs->basedir, name) == -1)
+		goto err;
+	ret = idx_dtmap_open(idx, path);
+	free(path);
+	path = NULL;
+	if (ret == -1)
+		goto err;
+
+	if ((idx->name = strdup(name)) == NULL)
+		goto err;
+	idx->image_dirty = idx->vocab_dirty = true;
+	idx->next = nxs->indexes;
+	nxs->indexes = idx;
+	return idx;
+err:
+	free(path);
+	nxs_error_checkpoint(nxs);
+	nxs_index_close(idx);
+	return NULL;
+}
+
+NXS_API nxs_params_t *
+nxs_index_get_params(nxs_index_t *idx)
+{
+	return idx->params;
+}
+
+NXS_API void
+nxs_index_close(nxs_index_t *idx)
+{
+	nxs_t *nxs = idx->nxs;
+
+	if (idx->name) {
+		for (nxs_index_t **pp = &nxs->indexes; *pp; pp = &(*pp)->next) {
+			if (*pp == idx) {
+				*pp = idx->next;
+				break;
+			}
+		}
+		free(idx->name);
+	}
+	if (idx->engine)
+		nxsb_engine_destroy(idx->engine);
+	bkmirror_free(&idx->bk);
+	if (idx->fp)
+		filter_pipeline_destroy(idx->fp);
+	if (idx->params)
+		nxs_params_release(idx->params);
+	if (idx->doc_map || idx->dfile.base)
+		idx_dtmap_close(idx);
+	if (idx->term_map || idx->tfile.base)
+		idx_terms_close(idx);
+	free(idx);
+}
+
+NXS_API int
+nxs_index_add(nxs_index_t *idx, nxs_params_t *params, nxs_doc_id_t doc_id,
+    const char *text, size_t len)
+{
+	tokenset_t *ts;
+	int ret = -1;
+
+	(void)params;
+	nxs_clear_error(idx->nxs);
+	if (doc_id == 0) {
+		nxs_set_error(idx->nxs, NXS_ERR_INVALID, "document ID must be non-zero");
+		return -1;
+	}
+	if (u64map_get(idx->doc_map, doc_id, NULL)) {
+		nxs_set_error(idx->nxs, NXS_ERR_EXISTS,
+		    "document %" PRIu64 " is already indexed", doc_id);
+		return -1;
+	}
+	if ((ts = tokenize(idx->fp, text, len)) == NULL) {
+		nxs_set_error(idx->nxs, NXS_ERR_FATAL, "tokenizer failed");
+		return -1;
+	}
+	if (ts->count == 0) {
+		nxs_set_error(idx->nxs, NXS_ERR_MISSING,
+		    "the text is empty or no meaningful tokens found");
+		goto out;
+	}
+	for (uint32_t i = 0; i < ts->count; i++)
+		ts->list[i].term_id = idx_term_lookup(idx, ts->list[i].str,
+		    ts->list[i].len);
+	if (idx_terms_add(idx, ts) == -1 || idx_dtmap_add(idx, doc_id, ts) == -1)
+		goto out;
+	ret = 0;
+out:
+	tokenset_destroy(ts);
+	if (ret != 0)
+		nxs_error_checkpoint(idx->nxs);
+	return ret;
+}
+
+NXS_API int
+nxs_index_remove(nxs_index_t *idx, nxs_doc_id_t doc_id)
+{
+	nxs_clear_error(idx->nxs);
+	if (idx_dtmap_remove(idx, doc_id) == -1) {
+		nxs_error_checkpoint(idx->nxs);
+		return -1;
+	}
+	return 0;
+}

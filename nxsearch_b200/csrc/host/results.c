@@ -1,0 +1,101 @@
+/*
+ * Response object: the top-N (doc id, score) list of one query, in the
+ * order the engine produced it (descending score), with the iterator and
+ * JSON rendering of ref src/core/results.c:88-247.
+ *
+ * The reference materialises a yyjson document per result eagerly
+ * (results.c:153-160); at GPU query rates that would dominate, so the JSON
+ * text is rendered only if nxs_resp_tojson() is called.  The
+ * text is what the reference prints: {"results":[{"doc_id":N,"score":X},
+ * ...],"count":K} with X the float score widened to double and printed in
+ * yyjson's shortest round-trip form (golden: ref tests/t_misc.c:115-117).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "nxs_impl.h"
+
+struct nxs_resp {
+	uint32_t	count;
+	uint32_t	iter;
+	uint64_t *	ids;
+	float *		scores;
+};
+
+nxs_resp_t *
+nxs_resp_from_arrays(const uint64_t *ids, const float *scores, uint32_t n)
+{
+	nxs_resp_t *r = calloc(1, sizeof(*r));
+
+	if (!r)
+		return NULL;
+	r->ids = malloc(sizeof(uint64_t) * (n ? n : 1));
+	r->scores = malloc(sizeof(float) * (n ? n : 1));
+	if (!r->ids || !r->scores) {
+		nxs_resp_release(r);
+		return NULL;
+	}
+	if (n) {
+		memcpy(r->ids, ids, sizeof(uint64_t) * n);
+		memcpy(r->scores, scores, sizeof(float) * n);
+	}
+	r->count = n;
+	return r;
+}
+
+NXS_API void
+nxs_resp_release(nxs_resp_t *r)
+{
+	if (r) {
+		free(r->ids);
+		free(r->scores);
+		free(r);
+	}
+}
+
+NXS_API void
+nxs_resp_iter_reset(nxs_resp_t *r)
+{
+	r->iter = 0;
+}
+
+NXS_API bool
+nxs_resp_iter_result(nxs_resp_t *r, nxs_doc_id_t *doc_id, float *score)
+{
+	if (r->iter >= r->count)
+		return false;
+	*doc_id = r->ids[r->iter];
+	*score = r->scores[r->iter];
+	r->iter++;
+	return true;
+}
+
+NXS_API unsigned
+nxs_resp_resultcount(const nxs_resp_t *r)
+{
+	return r->count;
+}
+
+NXS_API char *
+nxs_resp_tojson(nxs_resp_t *r, size_t *len)
+{
+	/* {"doc_id":18446744073709551615,"score":-1.7976931348623157e308}, */
+	const size_t cap = 64 + (size_t)r->count * 80;
+	char *buf = malloc(cap);
+	size_t n = 0;
+
+	if (!buf)
+		return NULL;
+	n += sprintf(buf + n, "{\"results\":[");
+	for (uint32_t i = 0; i < r->count; i++) {
+		n += sprintf(buf + n, "%s{\"doc_id\":%llu,\"score\":", i ? "," : "",
+		    (unsigned long long)r->ids[i]);
+		n += json_format_real((double)r->scores[i], buf + n);
+		buf[n++] = '}';
+	}
+	n += sprintf(buf + n, "],\"count\":%u}", r->count);
+	if (len)
+		*len = n;
+	return buf;
+}

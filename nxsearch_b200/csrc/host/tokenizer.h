@@ -1,0 +1,60 @@
+/*
+ * Text front end: word segmentation, the filter pipeline and token sets.
+ *
+ * OUT OF THE ACCELERATED PATH.  The reference
+ * uses ICU UAX#29 word breaking, ICU NFKC case folding / transliteration and
+ * the Snowball stemmer (ref src/core/tokenizer.c:234-302,
+ * src/core/filters_builtin.c); none of those libraries exist here, so this
+ * front end implements the ASCII subset:
+ *   - a word is a maximal run of [A-Za-z0-9] or bytes >= 0x80;
+ *   - "normalizer" lower-cases ASCII letters;
+ *   - "stopwords" drops words listed in <basedir>/filters/stopwords/<lang>
+ *     (one per line), exactly where the reference looks for them
+ *     (filters_builtin.c:93-127);
+ *   - "stemmer" passes words through unchanged.
+ * Token-set semantics (dedup by string, first-seen order, per-token counts)
+ * are the reference's (tokenizer.c:94-117).
+ */
+#ifndef NXSB_TOKENIZER_H
+#define NXSB_TOKENIZER_H
+
+#include "nxs_impl.h"
+
+typedef enum { FILT_NORMALIZER, FILT_STOPWORDS, FILT_STEMMER } filter_kind_t;
+
+typedef struct {
+	unsigned	count;
+	filter_kind_t	kinds[8];
+	strmap_t *	stopwords;	/* NULL = none for this language */
+} filter_pipeline_t;
+
+typedef struct {
+	char *		str;
+	uint32_t	len;
+	uint32_t	count;		/* occurrences */
+	uint32_t	term_id;	/* 0 = unresolved */
+} token_t;
+
+typedef struct {
+	token_t *	list;
+	uint32_t	count, cap;
+	uint32_t	seen;		/* all occurrences, incl. duplicates */
+	size_t		data_len;
+	strmap_t *	map;		/* string -> list index */
+} tokenset_t;
+
+filter_pipeline_t *filter_pipeline_create(nxs_t *, nxs_params_t *);
+void		filter_pipeline_destroy(filter_pipeline_t *);
+
+tokenset_t *	tokenset_create(void);
+void		tokenset_destroy(tokenset_t *);
+
+/*
+ * Run one value through the pipeline and add it to the set.  *slot gets the
+ * token's index in the set, or -1 if a filter discarded it.  -1 on error.
+ */
+int		tokenize_value(filter_pipeline_t *, tokenset_t *,
+		    const char *val, size_t len, int32_t *slot);
+tokenset_t *	tokenize(filter_pipeline_t *, const char *text, size_t len);
+
+#endif

@@ -1,0 +1,239 @@
+"""ctypes mirror of include/nxsb200_gpu.h: the CUDA engine's C ABI."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from ._lib import load_library
+
+ALGO_TFIDF, ALGO_BM25 = 0, 1
+OP_EMPTY, OP_AND, OP_OR, OP_ANDNOT = -1, -2, -3, -4
+TILE_DOCS = 16384
+
+
+class ShardDesc(C.Structure):
+    _fields_ = [
+        ("n_docs", C.c_uint32), ("n_terms", C.c_uint32),
+        ("doc_ids", C.c_void_p), ("doc_len", C.c_void_p), ("doc_off", C.c_void_p),
+        ("pairs", C.c_void_p), ("token_count", C.c_uint64), ("doc_count", C.c_uint32),
+        ("df", C.c_void_p),
+    ]
+
+
+class QueryDesc(C.Structure):
+    _fields_ = [("tok_off", C.c_uint32), ("n_tokens", C.c_uint32),
+                ("prog_off", C.c_uint32), ("n_prog", C.c_uint32)]
+
+
+class BatchDesc(C.Structure):
+    _fields_ = [
+        ("algo", C.c_int), ("limit", C.c_uint32), ("n_queries", C.c_uint32),
+        ("queries", C.c_void_p), ("tokens", C.c_void_p), ("n_tokens", C.c_uint32),
+        ("prog", C.c_void_p), ("n_prog", C.c_uint32),
+    ]
+
+
+def _bind():
+    lib = load_library()
+    vp, u32, u64, i = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    sig = {
+        "nxsb_gpu_device_count": (i, []),
+        "nxsb_last_error": (C.c_char_p, []),
+        "nxsb_engine_create": (vp, [i]),
+        "nxsb_engine_destroy": (None, [vp]),
+        "nxsb_engine_errmsg": (C.c_char_p, [vp]),
+        "nxsb_engine_set_stream": (i, [vp, vp]),
+        "nxsb_engine_load_shard": (i, [vp, C.POINTER(ShardDesc)]),
+        "nxsb_engine_get_df": (i, [vp, vp, u32]),
+        "nxsb_engine_set_global_stats": (i, [vp, vp, u32, u64, u32]),
+        "nxsb_engine_search": (i, [vp, C.POINTER(BatchDesc), vp, vp, vp]),
+        "nxsb_engine_batch_upload": (i, [vp, C.POINTER(BatchDesc)]),
+        "nxsb_engine_batch_run": (i, [vp, i, vp]),
+        "nxsb_engine_batch_fetch": (i, [vp, i, vp, vp, vp]),
+        "nxsb_engine_batch_release": (i, [vp, i]),
+        "nxsb_engine_batch_bytes": (u64, [vp, i]),
+        "nxsb_engine_sync": (i, [vp]),
+        "nxsb_engine_merge_topk": (i, [vp, vp, u32, u32, u32, vp]),
+        "nxsb_engine_load_vocab": (i, [vp, u32, vp, vp, vp, vp, vp, vp]),
+        "nxsb_engine_fuzzy": (i, [vp, u32, vp, vp, vp, vp, vp]),
+        "nxsb_engine_last_timings": (i, [vp, vp, vp, i]),
+        "nxsb_engine_timings": (i, [vp, u32, vp, vp, i]),
+        "nxsb_engine_launch_count": (u64, [vp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    return lib
+
+
+def device_count() -> int:
+    return _bind().nxsb_gpu_device_count()
+
+
+@dataclass
+class Batch:
+    """Host-side batch: queries as (token term ids, postfix program) pairs."""
+    algo: int
+    limit: int
+    queries: np.ndarray  # structured (n, 4) uint32: tok_off, n_tokens, prog_off, n_prog
+    tokens: np.ndarray   # uint32
+    prog: np.ndarray     # int32
+
+    @classmethod
+    def from_lists(cls, algo: int, limit: int, items) -> "Batch":
+        """items: iterable of (token_term_ids, program) with program=None => OR of all."""
+        q, toks, prog = [], [], []
+        for tk, pr in items:
+            tk = list(tk)
+            if pr is None:
+                pr = []
+                for s in range(len(tk)):
+                    pr.append(s)
+                    if s:
+                        pr.append(OP_OR)
+            q.append((len(toks), len(tk), len(prog), len(pr)))
+            toks.extend(tk)
+            prog.extend(pr)
+        return cls(algo, limit,
+                   np.array(q, dtype=np.uint32).reshape(-1, 4),
+                   np.array(toks, dtype=np.uint32), np.array(prog, dtype=np.int32))
+
+    def desc(self) -> BatchDesc:
+        return BatchDesc(self.algo, self.limit, len(self.queries),
+                         self.queries.ctypes.data, self.tokens.ctypes.data, len(self.tokens),
+                         self.prog.ctypes.data, len(self.prog))
+
+
+class Engine:
+    """One CUDA device / one document shard.  Raises if no GPU is usable."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _bind()
+        self._h = self._lib.nxsb_engine_create(device)
+        if not self._h:
+            raise RuntimeError("nxsb_engine_create failed: " + self._lib.nxsb_last_error().decode())
+
+    def _check(self, rc: int) -> int:
+        if rc < 0:
+            raise RuntimeError(self._lib.nxsb_engine_errmsg(self._h).decode())
+        return rc
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.nxsb_engine_destroy(self._h)
+            self._h = None
+
+    def set_stream(self, cuda_stream: int | None) -> None:
+        self._check(self._lib.nxsb_engine_set_stream(self._h, cuda_stream))
+
+    def load_corpus(self, corpus, *, lo: int = 0, hi: int | None = None, df=None,
+                    token_count: int | None = None, doc_count: int | None = None) -> None:
+        """Load documents [lo, hi) of a tools.Corpus (ids must ascend) as this shard."""
+        hi = corpus.n_docs if hi is None else hi
+        doc_off = np.ascontiguousarray(corpus.doc_off[lo:hi + 1] - corpus.doc_off[lo], dtype=np.uint64)
+        base = int(corpus.doc_off[lo])
+        pairs = corpus.pairs[2 * base: 2 * int(corpus.doc_off[hi])]
+        ids = np.ascontiguousarray(corpus.doc_ids[lo:hi])
+        lens = np.ascontiguousarray(corpus.doc_len[lo:hi])
+        pairs = np.ascontiguousarray(pairs)
+        dfa = None if df is None else np.ascontiguousarray(df, dtype=np.uint32)
+        sd = ShardDesc(hi - lo, corpus.n_terms, ids.ctypes.data, lens.ctypes.data,
+                       doc_off.ctypes.data, pairs.ctypes.data,
+                       corpus.token_count if token_count is None else token_count,
+                       corpus.doc_count if doc_count is None else doc_count,
+                       None if dfa is None else dfa.ctypes.data)
+        self._check(self._lib.nxsb_engine_load_shard(self._h, C.byref(sd)))
+
+    def get_df(self, n_terms: int) -> np.ndarray:
+        df = np.zeros(n_terms, dtype=np.uint32)
+        self._check(self._lib.nxsb_engine_get_df(self._h, df.ctypes.data, n_terms))
+        return df
+
+    def set_global_stats(self, df: np.ndarray, token_count: int, doc_count: int) -> None:
+        df = np.ascontiguousarray(df, dtype=np.uint32)
+        self._check(self._lib.nxsb_engine_set_global_stats(self._h, df.ctypes.data, len(df), token_count, doc_count))
+
+    def search(self, batch: Batch):
+        n, k = len(batch.queries), batch.limit
+        counts = np.zeros(n, dtype=np.uint32)
+        ids = np.zeros(max(n * k, 1), dtype=np.uint64)
+        scores = np.zeros(max(n * k, 1), dtype=np.float32)
+        d = batch.desc()
+        self._check(self._lib.nxsb_engine_search(self._h, C.byref(d), counts.ctypes.data,
+                                                 ids.ctypes.data, scores.ctypes.data))
+        return counts, ids[: n * k].reshape(n, k), scores[: n * k].reshape(n, k)
+
+    def upload(self, batch: Batch) -> int:
+        d = batch.desc()
+        return self._check(self._lib.nxsb_engine_batch_upload(self._h, C.byref(d)))
+
+    def run(self, handle: int, d_recs: int | None = None) -> None:
+        self._check(self._lib.nxsb_engine_batch_run(self._h, handle, d_recs))
+
+    def fetch(self, handle: int, n: int, k: int):
+        counts = np.zeros(n, dtype=np.uint32)
+        ids = np.zeros(max(n * k, 1), dtype=np.uint64)
+        scores = np.zeros(max(n * k, 1), dtype=np.float32)
+        self._check(self._lib.nxsb_engine_batch_fetch(self._h, handle, counts.ctypes.data,
+                                                      ids.ctypes.data, scores.ctypes.data))
+        return counts, ids[: n * k].reshape(n, k), scores[: n * k].reshape(n, k)
+
+    def release(self, handle: int) -> None:
+        self._check(self._lib.nxsb_engine_batch_release(self._h, handle))
+
+    def batch_bytes(self, handle: int) -> int:
+        return self._lib.nxsb_engine_batch_bytes(self._h, handle)
+
+    def sync(self) -> None:
+        self._check(self._lib.nxsb_engine_sync(self._h))
+
+    def merge_topk(self, d_in: int, n_shards: int, n_queries: int, limit: int, d_out: int) -> None:
+        self._check(self._lib.nxsb_engine_merge_topk(self._h, d_in, n_shards, n_queries, limit, d_out))
+
+    def load_vocab(self, blob: bytes, term_off, term_total, parent, edge, rank) -> None:
+        term_off = np.ascontiguousarray(term_off, dtype=np.uint32)
+        n = len(term_off) - 1
+        tt = np.ascontiguousarray(term_total, dtype=np.uint64)
+        pa = np.ascontiguousarray(parent, dtype=np.uint32)
+        ed = np.ascontiguousarray(edge, dtype=np.uint8)
+        rk = np.ascontiguousarray(rank, dtype=np.uint32)
+        buf = C.create_string_buffer(blob, len(blob) + 1)
+        self._check(self._lib.nxsb_engine_load_vocab(self._h, n, C.cast(buf, C.c_void_p), term_off.ctypes.data,
+                                                     tt.ctypes.data, pa.ctypes.data, ed.ctypes.data, rk.ctypes.data))
+
+    def fuzzy(self, queries: list[bytes], want_true: bool = False):
+        n = len(queries)
+        off = np.zeros(n + 1, dtype=np.uint32)
+        off[1:] = np.cumsum([len(q) for q in queries])
+        blob = b"".join(queries)
+        buf = C.create_string_buffer(blob, len(blob) + 1)
+        term = np.zeros(n, dtype=np.uint32)
+        dist = np.zeros(n, dtype=np.uint32)
+        true = np.zeros(n, dtype=np.uint32) if want_true else None
+        self._check(self._lib.nxsb_engine_fuzzy(self._h, n, C.cast(buf, C.c_void_p), off.ctypes.data,
+                                                term.ctypes.data, dist.ctypes.data,
+                                                None if true is None else true.ctypes.data))
+        return term, dist, true
+
+    def timings(self, last_runs: int = 1) -> dict[str, float]:
+        """Device milliseconds per kernel family, summed over the last runs
+        (CUDA events on the engine's stream; synchronises the stream)."""
+        names = (C.c_char_p * 16)()
+        ms = (C.c_float * 16)()
+        n = self._lib.nxsb_engine_timings(self._h, last_runs, names, ms, 16)
+        return {names[i].decode(): float(ms[i]) for i in range(n)}
+
+    def last_timings(self) -> dict[str, float]:
+        return self.timings(1)
+
+    @property
+    def launches(self) -> int:
+        return self._lib.nxsb_engine_launch_count(self._h)
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
