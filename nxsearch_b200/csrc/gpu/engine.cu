@@ -746,8 +746,11 @@ launch_tiles(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
 	if (LOGIC)
 		smem += ((size_t)B.max_tokens + 1) * TILE_WORDS * 4;
 
-	auto kern = e->wide ? score_tiles_kernel<LOGIC, true>
-	    : score_tiles_kernel<LOGIC, false>;
+	auto kern = B.algo == NXSB_ALGO_BM25
+	    ? (e->wide ? score_tiles_kernel<LOGIC, true, NXSB_ALGO_BM25>
+	       : score_tiles_kernel<LOGIC, false, NXSB_ALGO_BM25>)
+	    : (e->wide ? score_tiles_kernel<LOGIC, true, NXSB_ALGO_TFIDF>
+	       : score_tiles_kernel<LOGIC, false, NXSB_ALGO_TFIDF>);
 	int per_sm = 0;
 
 	CK(e, cudaFuncSetAttribute(kern,

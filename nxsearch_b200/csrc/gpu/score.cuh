@@ -108,294 +108,6 @@ build_temp_skips_kernel(const uint2 *__restrict__ post,
 }
 
 /*
- * Per-posting score.  TF-IDF is bit-exact with ref ranking.c:90-96 (float
- * tf times float idf).  BM25 (ranking.c:168-175) is evaluated in fp32 from
- * double-precision host constants; measured error < 5e-7 relative against
- * the reference's fp64 evaluation (budget 1e-5).
- */
-__device__ __forceinline__ float
-log_tf(uint32_t tf, const float *s_logtab)
-{
-	return tf < LOGTAB_N ? s_logtab[tf] : (float)log((double)tf + 1.0);
-}
-
-template <bool WIDE>
-__device__ __forceinline__ float
-score_posting(const ScoreParams &p, const float *s_logtab, uint2 posting,
-    float idf)
-{
-	const uint32_t tf = WIDE ? posting.y : (posting.y & 0xffffu);
-	const float x = log_tf(tf, s_logtab);
-
-	if (p.algo == NXSB_ALGO_TFIDF)
-		return __fmul_rn(x, idf);
-
-	const uint32_t dl = WIDE ? __ldg(p.doc_len + posting.x) : (posting.y >> 16);
-	const float den = __fadd_rn(x, __fmaf_rn(p.K1, (float)(int)dl, p.K0));
-	return __fmul_rn(__fdiv_rn(x, den), idf);
-}
-
-__device__ __forceinline__ uint32_t
-block_sum_u32(uint32_t v, uint32_t *s_scratch)
-{
-	/* s_scratch: one word, zeroed by the caller before a barrier. */
-	for (int o = 16; o; o >>= 1)
-		v += __shfl_xor_sync(0xffffffffu, v, o);
-	if ((threadIdx.x & 31) == 0 && v)
-		atomicAdd(s_scratch, v);
-	__syncthreads();
-	return *s_scratch;
-}
-
-/*
- * Selection key inside a tile: 46 bits, score bits above the 14-bit local
- * document index, so that "greater" means higher score, then higher id.
- */
-__device__ __forceinline__ unsigned long long
-sel_key(float v, uint32_t local)
-{
-	return ((unsigned long long)__float_as_uint(v) << TILE_SHIFT) | local;
-}
-
-template <bool LOGIC, bool WIDE>
-__global__ void __launch_bounds__(TILE_THREADS, LOGIC ? 2 : 3)
-score_tiles_kernel(const ScoreParams p)
-{
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	float *acc = reinterpret_cast<float *>(smem_raw);		// [TILE_DOCS]
-	uint32_t *bits = reinterpret_cast<uint32_t *>(acc + TILE_DOCS);	// LOGIC
-	uint32_t *mask = bits + (LOGIC ? p.max_tokens * TILE_WORDS : 0);	// LOGIC
-
-	__shared__ float s_logtab[LOGTAB_N];
-	__shared__ uint32_t s_lo[NXSB_MAX_QUERY_TOKENS], s_hi[NXSB_MAX_QUERY_TOKENS];
-	__shared__ uint32_t s_hist[256];
-	__shared__ uint32_t s_item, s_any, s_cnt, s_emit, s_base, s_want;
-	__shared__ unsigned long long s_prefix, s_theta;
-
-	const uint32_t tid = threadIdx.x;
-
-	for (uint32_t i = tid; i < LOGTAB_N; i += TILE_THREADS)
-		s_logtab[i] = p.logtab[i];
-
-	const unsigned long long n_items = (unsigned long long)p.n_q * p.ntiles;
-
-	for (;;) {
-		__syncthreads();
-		if (tid == 0) {
-			s_item = atomicAdd(p.work_counter, 1u);
-			s_any = 0;
-			s_cnt = 0;
-			s_emit = 0;
-		}
-		__syncthreads();
-		const unsigned long long item = s_item;
-		if (item >= n_items)
-			break;
-
-		/* Tile-major, highest tile first (ties prefer higher ids). */
-		const uint32_t tile = p.ntiles - 1 - (uint32_t)(item / p.n_q);
-		const uint32_t slot = (uint32_t)(item % p.n_q);
-		const QDesc qd = p.queries[p.qlist[slot]];
-		const uint32_t ntok = qd.n_tokens;
-		const uint32_t tile_lo = tile << TILE_SHIFT;
-
-		if (tid < ntok) {
-			const DTok &t = p.toks[qd.tok_off + tid];
-			const uint32_t lo = __ldg(t.skip + tile);
-			const uint32_t hi = __ldg(t.skip + tile + 1);
-
-			s_lo[tid] = lo;
-			s_hi[tid] = hi;
-			if (hi > lo)
-				s_any = 1;
-		}
-		/* One read of the threshold per item, shared by all threads. */
-		if (tid == 32)
-			s_theta = *(volatile unsigned long long *)(p.thr + slot);
-		__syncthreads();
-		if (!s_any)
-			continue;
-
-		/* Clear the accumulator (and the token bitmaps). */
-		{
-			float4 *a4 = reinterpret_cast<float4 *>(acc);
-			for (uint32_t i = tid; i < TILE_DOCS / 4; i += TILE_THREADS)
-				a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-			if (LOGIC) {
-				for (uint32_t i = tid; i < ntok * TILE_WORDS; i += TILE_THREADS)
-					bits[i] = 0;
-			}
-		}
-		__syncthreads();
-
-		/* Stream each token's slice; token-list order = summation order. */
-		for (uint32_t j = 0; j < ntok; j++) {
-			const DTok &t = p.toks[qd.tok_off + j];
-			const uint2 *list = p.post + t.post_off;
-			const float idf = t.idf;
-			const uint32_t lo = s_lo[j], hi = s_hi[j];
-			uint32_t i = lo + tid;
-
-			/* 4 independent 8-byte loads in flight per thread. */
-			for (; i + 3 * TILE_THREADS < hi; i += 4 * TILE_THREADS) {
-				uint2 v[4];
-#pragma unroll
-				for (int u = 0; u < 4; u++)
-					v[u] = __ldg(list + i + u * TILE_THREADS);
-#pragma unroll
-				for (int u = 0; u < 4; u++) {
-					const uint32_t local = v[u].x - tile_lo;
-					acc[local] += score_posting<WIDE>(p, s_logtab, v[u], idf);
-					if (LOGIC)
-						atomicOr(&bits[j * TILE_WORDS + (local >> 5)],
-						    1u << (local & 31));
-				}
-			}
-			for (; i < hi; i += TILE_THREADS) {
-				const uint2 v = __ldg(list + i);
-				const uint32_t local = v.x - tile_lo;
-
-				acc[local] += score_posting<WIDE>(p, s_logtab, v, idf);
-				if (LOGIC)
-					atomicOr(&bits[j * TILE_WORDS + (local >> 5)],
-					    1u << (local & 31));
-			}
-			__syncthreads();
-		}
-
-		/*
-		 * Boolean logic (ref get_expr_bitmap, search.c:118-174): each
-		 * thread evaluates the postfix program on one 32-document word
-		 * of every token bitmap.
-		 */
-		if (LOGIC) {
-			for (uint32_t w = tid; w < TILE_WORDS; w += TILE_THREADS) {
-				uint32_t st[NXSB_MAX_QUERY_TOKENS + 1];
-				int sp = 0;
-
-				for (uint32_t c = 0; c < qd.n_prog; c++) {
-					const int32_t op = p.prog[qd.prog_off + c];
-
-					if (op >= 0) {
-						st[sp++] = bits[op * TILE_WORDS + w];
-					} else if (op == NXSB_OP_EMPTY) {
-						st[sp++] = 0;
-					} else {
-						const uint32_t b = st[--sp];
-						const uint32_t a = st[sp - 1];
-
-						st[sp - 1] = op == NXSB_OP_AND ? (a & b) :
-						    op == NXSB_OP_OR ? (a | b) : (a & ~b);
-					}
-				}
-				mask[w] = sp ? st[sp - 1] : 0;
-			}
-			__syncthreads();
-		}
-
-		/*
-		 * Top-k of the tile.  A document competes only if its key
-		 * (score, id) beats the query's published threshold -- the
-		 * k-th best key of some already finished tile, hence a lower
-		 * bound of the final k-th best.
-		 */
-		const unsigned long long theta = s_theta;
-		const unsigned long long theta_bits = theta >> 32;
-		const uint32_t theta_doc = (uint32_t)theta;
-		const bool have_theta = theta != 0;
-		uint32_t cnt = 0;
-
-		auto candidate = [&](uint32_t i, unsigned long long &sk) -> bool {
-			const float v = acc[i];
-			const bool valid = LOGIC ? ((mask[i >> 5] >> (i & 31)) & 1u) : (v > 0.f);
-
-			if (!valid)
-				return false;
-			sk = sel_key(v, i);
-			if (!have_theta)
-				return true;
-			/* key(v, tile_lo + i) > theta ? */
-			const unsigned long long sbits = sk >> TILE_SHIFT;
-			return sbits > theta_bits ||
-			    (sbits == theta_bits && tile_lo + i > theta_doc);
-		};
-
-		for (uint32_t i = tid; i < TILE_DOCS; i += TILE_THREADS) {
-			unsigned long long sk;
-			cnt += candidate(i, sk) ? 1u : 0u;
-		}
-		const uint32_t total = block_sum_u32(cnt, &s_cnt);
-		if (total == 0)
-			continue;
-
-		unsigned long long kth = 0;	// emit keys >= kth
-		uint32_t n_emit = total;
-
-		if (total > p.k) {
-			/*
-			 * MSB-first radix select of the k-th largest 46-bit key:
-			 * digits 8,8,8,8 over the score bits, 7,7 over the id.
-			 */
-			const int shifts[6] = { 38, 30, 22, 14, 7, 0 };
-			const int widths[6] = { 8, 8, 8, 8, 7, 7 };
-
-			if (tid == 0) {
-				s_prefix = 0;
-				s_want = p.k;
-			}
-			for (int ps = 0; ps < 6; ps++) {
-				const int sh = shifts[ps], wd = widths[ps];
-
-				if (tid < 256)
-					s_hist[tid] = 0;
-				__syncthreads();
-				const unsigned long long prefix = s_prefix;
-				for (uint32_t i = tid; i < TILE_DOCS; i += TILE_THREADS) {
-					unsigned long long sk;
-					if (candidate(i, sk) && (sk >> (sh + wd)) == prefix)
-						atomicAdd(&s_hist[(uint32_t)(sk >> sh) & ((1u << wd) - 1)], 1u);
-				}
-				__syncthreads();
-				if (tid == 0) {
-					uint32_t want = s_want, cum = 0;
-					int b = (1 << wd) - 1;
-
-					for (; b > 0; b--) {
-						if (cum + s_hist[b] >= want)
-							break;
-						cum += s_hist[b];
-					}
-					s_want = want - cum;
-					s_prefix = (prefix << wd) | (unsigned)b;
-				}
-				__syncthreads();
-			}
-			kth = s_prefix;
-			n_emit = p.k;
-		}
-
-		if (tid == 0)
-			s_base = atomicAdd(p.cand_count + slot, n_emit);
-		__syncthreads();
-		unsigned long long *out = p.cand + (unsigned long long)slot * p.cand_cap + s_base;
-		for (uint32_t i = tid; i < TILE_DOCS; i += TILE_THREADS) {
-			unsigned long long sk;
-			if (candidate(i, sk) && sk >= kth) {
-				const uint32_t slot = atomicAdd(&s_emit, 1u);
-				out[slot] = make_key(acc[i], tile_lo + i);
-			}
-		}
-		if (total > p.k && tid == 0) {
-			/* Publish the tile's k-th best as the new lower bound. */
-			const uint32_t local = (uint32_t)kth & (TILE_DOCS - 1);
-			const unsigned long long key =
-			    ((kth >> TILE_SHIFT) << 32) | (tile_lo + local);
-			atomicMax(p.thr + slot, key);
-		}
-	}
-}
-
-/*
  * Block-wide bitonic sort (descending) of n <= SORT_CAP keys in shared
  * memory; n is padded to a power of two with zeros by the caller.
  */
@@ -420,6 +132,8 @@ bitonic_sort_desc(unsigned long long *s, uint32_t npow2)
 	}
 	__syncthreads();
 }
+
+#include "tiles.cuh"
 
 /*
  * Final per-query top-k: merge the candidates its tiles emitted.  One CTA
