@@ -28,6 +28,65 @@
 
 static thread_local char g_last_error[512];
 
+/* Grow-only device / pinned-host buffers: no allocation in steady state. */
+struct DevBuf {
+	void *	p = nullptr;
+	size_t	cap = 0;
+
+	cudaError_t ensure(size_t bytes)
+	{
+		if (bytes <= cap)
+			return cudaSuccess;
+		release();
+		const size_t want = bytes + bytes / 2 + 256;
+		cudaError_t rc = cudaMalloc(&p, want);
+		if (rc == cudaSuccess)
+			cap = want;
+		else
+			p = nullptr;
+		return rc;
+	}
+	void release()
+	{
+		if (p)
+			cudaFree(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+struct PinnedBuf {
+	void *	p = nullptr;
+	size_t	cap = 0;
+
+	cudaError_t ensure(size_t bytes)
+	{
+		if (bytes <= cap)
+			return cudaSuccess;
+		release();
+		const size_t want = bytes + bytes / 2 + 256;
+		cudaError_t rc = cudaMallocHost(&p, want);
+		if (rc == cudaSuccess)
+			cap = want;
+		else
+			p = nullptr;
+		return rc;
+	}
+	void release()
+	{
+		if (p)
+			cudaFreeHost(p);
+		p = nullptr;
+		cap = 0;
+	}
+};
+
+static inline size_t
+align16(size_t n)
+{
+	return (n + 15) & ~(size_t)15;
+}
+
 struct Batch {
 	bool		used = false;
 	int		algo = 0;
@@ -35,18 +94,28 @@ struct Batch {
 	uint32_t	max_tokens = 0;
 	uint64_t	bytes = 0;		// algorithmic bytes
 	std::vector<uint32_t> q_or, q_logic;	// host lists
+	/* One H2D copy: [queries | tokens | prog | qlist_or | qlist_logic]. */
+	DevBuf		desc;
+	PinnedBuf	h_desc;
+	/* [toks | tmp_skip | thr | cand_count | work]; the tail is re-zeroed per launch. */
+	DevBuf		scratch;
+	/* One D2H copy: [recs | counts]. */
+	DevBuf		results;
+	PinnedBuf	h_results;
+	/* Views into the buffers above. */
 	QDesc *		d_queries = nullptr;
 	uint32_t *	d_tokens = nullptr;
 	int32_t *	d_prog = nullptr;
 	uint32_t *	d_qlist_or = nullptr, *d_qlist_logic = nullptr;
-	/* scratch + results */
 	DTok *		d_toks = nullptr;
 	uint32_t *	d_tmp_skip = nullptr;
 	unsigned long long *d_thr = nullptr;
 	uint32_t *	d_cand_count = nullptr;
-	uint32_t *	d_work = nullptr;	// [2] work counters
+	uint32_t *	d_work = nullptr;
+	size_t		zero_bytes = 0;		// thr .. work
 	Rec *		d_recs = nullptr;
 	uint32_t *	d_counts = nullptr;
+	size_t		results_bytes = 0;
 };
 
 struct nxsb_engine {
@@ -84,6 +153,7 @@ struct nxsb_engine {
 	size_t		cub_tmp_bytes = 0;
 
 	Batch		batches[MAX_HANDLES];
+	Batch		oneshot;	// reused by nxsb_engine_search
 
 	/* vocabulary (fuzzy) */
 	FuzzyImage	fz;
@@ -235,18 +305,11 @@ free_image(nxsb_engine_t *e)
 static void
 free_batch(Batch &b)
 {
-	dev_free(b.d_queries);
-	dev_free(b.d_tokens);
-	dev_free(b.d_prog);
-	dev_free(b.d_qlist_or);
-	dev_free(b.d_qlist_logic);
-	dev_free(b.d_toks);
-	dev_free(b.d_tmp_skip);
-	dev_free(b.d_thr);
-	dev_free(b.d_cand_count);
-	dev_free(b.d_work);
-	dev_free(b.d_recs);
-	dev_free(b.d_counts);
+	b.desc.release();
+	b.h_desc.release();
+	b.scratch.release();
+	b.results.release();
+	b.h_results.release();
 	b = Batch();
 }
 
@@ -260,6 +323,7 @@ nxsb_engine_destroy(nxsb_engine_t *e)
 	for (auto &b : e->batches)
 		if (b.used)
 			free_batch(b);
+	free_batch(e->oneshot);
 	free_image(e);
 	fuzzy_free(e->fz);
 	dev_free(e->d_cand);
@@ -596,23 +660,16 @@ validate_batch(nxsb_engine_t *e, const nxsb_batch_t *b)
 	return 0;
 }
 
-extern "C" int
-nxsb_engine_batch_upload(nxsb_engine_t *e, const nxsb_batch_t *b)
+/*
+ * Stage a batch on the device: classify the queries, size the (grow-only)
+ * buffers, pack all descriptors into one pinned block and copy it with a
+ * single cudaMemcpyAsync.
+ */
+static int
+fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 {
-	int h = -1;
-
-	CK(e, cudaSetDevice(e->device));
 	if (validate_batch(e, b) == -1)
 		return -1;
-	for (int i = 0; i < MAX_HANDLES; i++)
-		if (!e->batches[i].used) {
-			h = i;
-			break;
-		}
-	if (h < 0)
-		return fail(e, "too many resident batches");
-
-	Batch &B = e->batches[h];
 	B.used = true;
 	B.algo = b->algo;
 	B.limit = b->limit;
@@ -621,6 +678,8 @@ nxsb_engine_batch_upload(nxsb_engine_t *e, const nxsb_batch_t *b)
 	B.n_prog = b->n_prog;
 	B.max_tokens = 1;
 	B.bytes = 0;
+	B.q_or.clear();
+	B.q_logic.clear();
 
 	for (uint32_t i = 0; i < b->n_queries; i++) {
 		const nxsb_query_t &q = b->queries[i];
@@ -640,38 +699,76 @@ nxsb_engine_batch_upload(nxsb_engine_t *e, const nxsb_batch_t *b)
 				B.bytes += 8ull * e->h_df[id - 1];
 		}
 	}
-
-	const uint32_t k = B.limit;
-	const size_t nrec = (size_t)std::max(B.n_q, 1u) * k;
 	static_assert(sizeof(QDesc) == sizeof(nxsb_query_t), "descriptor layout");
 
-	if (dev_alloc(&B.d_queries, B.n_q) || dev_alloc(&B.d_tokens, B.n_tok) ||
-	    dev_alloc(&B.d_prog, B.n_prog) ||
-	    dev_alloc(&B.d_qlist_or, B.q_or.size()) ||
-	    dev_alloc(&B.d_qlist_logic, B.q_logic.size()) ||
-	    dev_alloc(&B.d_toks, B.n_tok) ||
-	    dev_alloc(&B.d_tmp_skip, (size_t)B.n_tok * (e->ntiles + 1)) ||
-	    dev_alloc(&B.d_thr, B.n_q) || dev_alloc(&B.d_cand_count, B.n_q) ||
-	    dev_alloc(&B.d_work, 1) || dev_alloc(&B.d_recs, nrec) ||
-	    dev_alloc(&B.d_counts, B.n_q)) {
-		free_batch(B);
+	const size_t nq = std::max(B.n_q, 1u);
+	const size_t o_q = 0;
+	const size_t o_tok = o_q + align16(nq * sizeof(QDesc));
+	const size_t o_prog = o_tok + align16((size_t)B.n_tok * 4);
+	const size_t o_or = o_prog + align16((size_t)B.n_prog * 4);
+	const size_t o_lg = o_or + align16(B.q_or.size() * 4);
+	const size_t desc_bytes = o_lg + align16(B.q_logic.size() * 4);
+
+	const size_t s_toks = 0;
+	const size_t s_skip = s_toks + align16((size_t)B.n_tok * sizeof(DTok));
+	const size_t s_thr = s_skip + align16((size_t)B.n_tok * (e->ntiles + 1) * 4);
+	const size_t s_cnt = s_thr + align16(nq * 8);
+	const size_t s_work = s_cnt + align16(nq * 4);
+	const size_t scratch_bytes = s_work + 16;
+
+	const size_t r_counts = align16(nq * B.limit * sizeof(Rec));
+	B.results_bytes = r_counts + align16(nq * 4);
+
+	if (B.desc.ensure(desc_bytes) || B.h_desc.ensure(desc_bytes) ||
+	    B.scratch.ensure(scratch_bytes) || B.results.ensure(B.results_bytes) ||
+	    B.h_results.ensure(B.results_bytes))
 		return fail(e, "device allocation failed for a batch of %u queries "
-		    "(limit %u): %s", b->n_queries, k,
+		    "(limit %u): %s", b->n_queries, B.limit,
 		    cudaGetErrorString(cudaGetLastError()));
+
+	char *d = (char *)B.desc.p, *h = (char *)B.h_desc.p, *sc = (char *)B.scratch.p;
+	B.d_queries = (QDesc *)(d + o_q);
+	B.d_tokens = (uint32_t *)(d + o_tok);
+	B.d_prog = (int32_t *)(d + o_prog);
+	B.d_qlist_or = (uint32_t *)(d + o_or);
+	B.d_qlist_logic = (uint32_t *)(d + o_lg);
+	B.d_toks = (DTok *)(sc + s_toks);
+	B.d_tmp_skip = (uint32_t *)(sc + s_skip);
+	B.d_thr = (unsigned long long *)(sc + s_thr);
+	B.d_cand_count = (uint32_t *)(sc + s_cnt);
+	B.d_work = (uint32_t *)(sc + s_work);
+	B.zero_bytes = scratch_bytes - s_thr;
+	B.d_recs = (Rec *)B.results.p;
+	B.d_counts = (uint32_t *)((char *)B.results.p + r_counts);
+
+	memcpy(h + o_q, b->queries, (size_t)B.n_q * sizeof(QDesc));
+	memcpy(h + o_tok, b->tokens, (size_t)B.n_tok * 4);
+	memcpy(h + o_prog, b->prog, (size_t)B.n_prog * 4);
+	memcpy(h + o_or, B.q_or.data(), B.q_or.size() * 4);
+	memcpy(h + o_lg, B.q_logic.data(), B.q_logic.size() * 4);
+	CK(e, cudaMemcpyAsync(d, h, desc_bytes, cudaMemcpyHostToDevice, e->stream));
+	return 0;
+}
+
+extern "C" int
+nxsb_engine_batch_upload(nxsb_engine_t *e, const nxsb_batch_t *b)
+{
+	int h = -1;
+
+	CK(e, cudaSetDevice(e->device));
+	for (int i = 0; i < MAX_HANDLES; i++)
+		if (!e->batches[i].used) {
+			h = i;
+			break;
+		}
+	if (h < 0)
+		return fail(e, "too many resident batches");
+	if (fill_batch(e, e->batches[h], b) == -1) {
+		free_batch(e->batches[h]);
+		return -1;
 	}
-	cudaStream_t st = e->stream;
-	cudaMemcpyAsync(B.d_queries, b->queries, (size_t)B.n_q * sizeof(QDesc),
-	    cudaMemcpyHostToDevice, st);
-	cudaMemcpyAsync(B.d_tokens, b->tokens, (size_t)B.n_tok * 4,
-	    cudaMemcpyHostToDevice, st);
-	cudaMemcpyAsync(B.d_prog, b->prog, (size_t)B.n_prog * 4,
-	    cudaMemcpyHostToDevice, st);
-	cudaMemcpyAsync(B.d_qlist_or, B.q_or.data(), B.q_or.size() * 4,
-	    cudaMemcpyHostToDevice, st);
-	cudaMemcpyAsync(B.d_qlist_logic, B.q_logic.data(), B.q_logic.size() * 4,
-	    cudaMemcpyHostToDevice, st);
-	if (cudaStreamSynchronize(st) != cudaSuccess) {
-		free_batch(B);
+	if (cudaStreamSynchronize(e->stream) != cudaSuccess) {
+		free_batch(e->batches[h]);
 		return fail(e, "batch upload failed: %s",
 		    cudaGetErrorString(cudaGetLastError()));
 	}
@@ -764,9 +861,8 @@ launch_tiles(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
 	unsigned grid = (unsigned)std::min<unsigned long long>(items,
 	    (unsigned long long)e->n_sms * per_sm);
 
-	CK(e, cudaMemsetAsync(B.d_work, 0, 4, e->stream));
-	CK(e, cudaMemsetAsync(B.d_thr, 0, (size_t)n_q * 8, e->stream));
-	CK(e, cudaMemsetAsync(B.d_cand_count, 0, (size_t)n_q * 4, e->stream));
+	/* thresholds, candidate counts and the work counter: one memset. */
+	CK(e, cudaMemsetAsync(B.d_thr, 0, B.zero_bytes, e->stream));
 	mark(e, "score_tiles");
 	kern<<<grid, TILE_THREADS, smem, e->stream>>>(p);
 	e->launches++;
@@ -878,9 +974,13 @@ run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
 	mark(e, "resolve");
 
 	/* Results start out empty; queries that score nothing stay so. */
-	CK(e, cudaMemsetAsync(d_recs, 0,
-	    (size_t)std::max(B.n_q, 1u) * B.limit * sizeof(Rec), st));
-	CK(e, cudaMemsetAsync(B.d_counts, 0, (size_t)std::max(B.n_q, 1u) * 4, st));
+	if (d_recs == B.d_recs) {
+		CK(e, cudaMemsetAsync(B.results.p, 0, B.results_bytes, st));
+	} else {
+		CK(e, cudaMemsetAsync(d_recs, 0,
+		    (size_t)std::max(B.n_q, 1u) * B.limit * sizeof(Rec), st));
+		CK(e, cudaMemsetAsync(B.d_counts, 0, (size_t)std::max(B.n_q, 1u) * 4, st));
+	}
 	if (n_active == 0 || !can_score) {
 		mark(e, "end");
 		return 0;
@@ -913,22 +1013,19 @@ nxsb_engine_batch_run(nxsb_engine_t *e, int h, void *d_recs)
 	return run_batch(e, B, d_recs ? (Rec *)d_recs : B.d_recs);
 }
 
-extern "C" int
-nxsb_engine_batch_fetch(nxsb_engine_t *e, int h, uint32_t *counts,
-    uint64_t *ids, float *scores)
+static int
+fetch_results(nxsb_engine_t *e, Batch &B, uint32_t *counts, uint64_t *ids,
+    float *scores)
 {
-	if (h < 0 || h >= MAX_HANDLES || !e->batches[h].used)
-		return fail(e, "bad batch handle %d", h);
-	Batch &B = e->batches[h];
 	const size_t nrec = (size_t)B.n_q * B.limit;
-	std::vector<Rec> recs(nrec);
+	const Rec *recs = (const Rec *)B.h_results.p;
+	const uint32_t *cnt = (const uint32_t *)((const char *)B.h_results.p +
+	    ((const char *)B.d_counts - (const char *)B.results.p));
 
-	CK(e, cudaSetDevice(e->device));
-	CK(e, cudaMemcpyAsync(recs.data(), B.d_recs, nrec * sizeof(Rec),
-	    cudaMemcpyDeviceToHost, e->stream));
-	CK(e, cudaMemcpyAsync(counts, B.d_counts, (size_t)B.n_q * 4,
+	CK(e, cudaMemcpyAsync(B.h_results.p, B.results.p, B.results_bytes,
 	    cudaMemcpyDeviceToHost, e->stream));
 	CK(e, cudaStreamSynchronize(e->stream));
+	memcpy(counts, cnt, (size_t)B.n_q * 4);
 	for (size_t i = 0; i < nrec; i++) {
 		ids[i] = recs[i].doc_id;
 		scores[i] = recs[i].score;
@@ -937,23 +1034,25 @@ nxsb_engine_batch_fetch(nxsb_engine_t *e, int h, uint32_t *counts,
 }
 
 extern "C" int
+nxsb_engine_batch_fetch(nxsb_engine_t *e, int h, uint32_t *counts,
+    uint64_t *ids, float *scores)
+{
+	if (h < 0 || h >= MAX_HANDLES || !e->batches[h].used)
+		return fail(e, "bad batch handle %d", h);
+	CK(e, cudaSetDevice(e->device));
+	return fetch_results(e, e->batches[h], counts, ids, scores);
+}
+
+extern "C" int
 nxsb_engine_search(nxsb_engine_t *e, const nxsb_batch_t *b, uint32_t *counts,
     uint64_t *ids, float *scores)
 {
-	const int h = nxsb_engine_batch_upload(e, b);
-	int rc;
+	Batch &B = e->oneshot;
 
-	if (h < 0)
+	CK(e, cudaSetDevice(e->device));
+	if (fill_batch(e, B, b) == -1 || run_batch(e, B, B.d_recs) == -1)
 		return -1;
-	rc = nxsb_engine_batch_run(e, h, nullptr);
-	if (rc == 0)
-		rc = nxsb_engine_batch_fetch(e, h, counts, ids, scores);
-	char saved[sizeof(e->err)];
-	memcpy(saved, e->err, sizeof(saved));
-	nxsb_engine_batch_release(e, h);
-	if (rc != 0)
-		memcpy(e->err, saved, sizeof(saved));
-	return rc;
+	return fetch_results(e, B, counts, ids, scores);
 }
 
 extern "C" int

@@ -1,0 +1,304 @@
+"""Host-side logic of the product library, CPU only: parser, JSON, params,
+responses, on-disk format, API error behaviour, exported symbols."""
+import ctypes as C
+import json
+import re
+import shutil
+import tempfile
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import _mk
+import _oracle
+from nxsearch_b200 import capi, tools, library_path
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture()
+def nxs():
+    base = tempfile.mkdtemp(prefix="nxsb_t_")
+    n = capi.Nxs(base)
+    n.base = base
+    yield n
+    n.close()
+    shutil.rmtree(base, ignore_errors=True)
+
+
+# ---- query language --------------------------------------------------------
+
+@pytest.mark.parametrize("query,repr_,kinds", _mk.PARSER_CASES)
+def test_parser_goldens(query, repr_, kinds):
+    """ref tests/t_queryparser.c:27-115: token streams and IR s-expressions."""
+    assert tools.query_lex(query) == kinds
+    dump, err = tools.query_dump(query)
+    assert dump == repr_
+    if repr_ is None:
+        assert err and err.startswith("syntax error near ")
+
+
+def test_lexer_longest_match_rules():
+    """re2c semantics (scan.re:64-119): keywords only when followed by a separator."""
+    assert tools.query_lex("ANDROID ORacle NOTary") == ["FF", "FF", "FF"]
+    assert tools.query_lex("a&b a & b") == ["FF", "FF", "AND", "FF"]
+    assert tools.query_lex("'a b' 'ab'c 'unterminated") == ["QS", "FF", "FF"]
+    assert tools.query_lex("a|b | Or oR") == ["FF", "OR", "OR", "OR"]
+    assert tools.query_dump("a AND NOT b AND c")[0] == "(AND (NOT `a` `b`) `c`)"
+    assert tools.query_dump("a b OR c")[0] == "(OR `a` (OR `b` `c`))"
+    assert tools.query_dump("(a b)")[0] is None          # juxtaposition only at top level
+    assert tools.query_dump("NOT a")[0] is None
+    assert tools.query_dump("a OR NOT b")[0] is None
+    assert tools.query_dump("")[0] is None
+    assert tools.query_dump("a AND")[1] == 'syntax error near 1:5: " ..."'
+    assert tools.query_dump("a\n\n) b")[1].startswith("syntax error near ")
+
+
+def test_token_order_is_right_to_left_and_deduplicated():
+    """ref query.c:89-103 (LIFO walk) + tokenizer.c:94-117 (dedup by string)."""
+    assert tools.query_compile("a OR b OR c") == (["c", "b", "a"], [2, 1, -3, 0, -3])
+    toks, prog = tools.query_compile("aa AND NOT (bb AND cc) OR aa")
+    assert toks == ["aa", "cc", "bb"] and prog == [0, 2, 1, -2, -4, 0, -3]
+    deep = " OR ".join(f"t{i}" for i in range(101))      # left-deep chain, depth 100: allowed
+    assert tools.query_compile(deep) is not None
+    assert tools.query_compile(deep + " OR x") is None    # depth 101 > NXS_QUERY_RLIMIT
+
+
+# ---- JSON / params / response ----------------------------------------------
+
+def test_params_roundtrip_and_first_match_semantics(nxs):
+    lib = nxs._lib
+    p = capi.Params(lib, algo="BM25", limit=7, fuzzymatch=False, filters=["normalizer", "stemmer"])
+    doc = json.loads(p.tojson())
+    assert doc == {"algo": "BM25", "limit": 7, "fuzzymatch": False, "filters": ["normalizer", "stemmer"]}
+    p.set("algo", "TF-IDF")                               # yyjson_mut_obj_add appends; get returns the first
+    assert '"algo": "BM25"' in p.tojson() and p.tojson().count('"algo"') == 2
+    p.release()
+    src = b'{"a": [1, -2, 3.5, true, null, "x\\u00e9\\n"], "b": {"c": 18446744073709551615}}'
+    h = lib.nxs_params_fromjson(nxs.h, src, len(src))
+    assert h
+    assert json.loads(capi._take_string(lib.nxs_params_tojson(h, None))) == json.loads(src)
+    lib.nxs_params_release(h)
+    assert not lib.nxs_params_fromjson(nxs.h, b"{bad", 4)
+    assert nxs.error()[0] == capi.ERR_SYSTEM
+
+
+def test_real_number_formatting_matches_yyjson():
+    lib = capi.bind()
+    lib_fmt = C.CDLL(str(library_path()))
+    cases = {1.5: "1.5", 3.0: "3.0", 0.1: "0.1", 1e21: "1e21", 1.25e-7: "1.25e-7", 123456789.0: "123456789.0",
+             float(np.float32(1.1736002)): "1.1736001968383789", 0.000001: "0.000001", 1e-7: "1e-7"}
+    # exercised through a response object: scores are floats widened to double
+    for val in (1.5, 3.0, 0.25378534197807312, 1.1736001968383789, 100.0, 0.0009765625):
+        src = json.dumps({"x": val}).encode()
+        h = lib.nxs_params_fromjson(None, src, len(src))
+        out = capi._take_string(lib.nxs_params_tojson(h, None))
+        assert json.loads(out)["x"] == val
+        lib.nxs_params_release(h)
+    del lib_fmt, cases
+
+
+# ---- on-disk format --------------------------------------------------------
+
+TERMS_GOLDEN = bytes([
+    0x4e, 0x58, 0x53, 0x5f, 0x54, 0x01, 0x00, 0x00, 0x00, 0x00, 0x00, 0x38, 0x00, 0x00, 0x00, 0x00,
+    0x00, 0x0b, 0x73, 0x6f, 0x6d, 0x65, 0x2d, 0x74, 0x65, 0x72, 0x6d, 0x2d, 0x31, 0x00, 0x00, 0x00,
+    0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x01, 0x00, 0x0e, 0x61, 0x6e, 0x6f, 0x74, 0x68, 0x65,
+    0x72, 0x2d, 0x74, 0x65, 0x72, 0x6d, 0x2d, 0x32, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00,
+    0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x02])   # ref tests/t_index_terms.c:23-37
+DTMAP_GOLDEN = bytes([
+    0x4e, 0x58, 0x53, 0x5f, 0x44, 0x01, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x38,
+    0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x04, 0x00, 0x00, 0x00, 0x02, 0x00, 0x00, 0x00, 0x00,
+    0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x03, 0xe9, 0x00, 0x00, 0x00, 0x03, 0x00, 0x00, 0x00, 0x02,
+    0x00, 0x00, 0x00, 0x01, 0x00, 0x00, 0x00, 0x01, 0x00, 0x00, 0x00, 0x02, 0x00, 0x00, 0x00, 0x02,
+    0x00, 0x00, 0x00, 0x00, 0x00, 0x00, 0x03, 0xea, 0x00, 0x00, 0x00, 0x01, 0x00, 0x00, 0x00, 0x01,
+    0x00, 0x00, 0x00, 0x03, 0x00, 0x00, 0x00, 0x01])   # ref tests/t_index_dtmap.c:25-41
+
+
+def _golden_corpus():
+    c = _mk.make_corpus([(1001, ["some-term-1", "another-term-2", "another-term-2"]), (1002, ["term-3"])])
+    return c
+
+
+def test_bulk_writer_reproduces_reference_golden_bytes(tmp_path):
+    c = _golden_corpus()
+    lib = tools._bind()
+    cs = tools.CorpusStruct(
+        c.n_docs, c.n_terms, c.n_pairs, c.token_count, c.doc_count,
+        c.doc_ids.ctypes.data_as(C.POINTER(C.c_uint64)), c.doc_len.ctypes.data_as(C.POINTER(C.c_uint32)),
+        c.doc_off.ctypes.data_as(C.POINTER(C.c_uint64)), c.pairs.ctypes.data_as(C.POINTER(C.c_uint32)),
+        C.cast(C.create_string_buffer(c.term_blob), C.c_void_p), c.term_off.ctypes.data_as(C.POINTER(C.c_uint32)),
+        c.term_total.ctypes.data_as(C.POINTER(C.c_uint64)), c.term_df.ctypes.data_as(C.POINTER(C.c_uint32)))
+    # the terms golden holds only the first two terms (t_index_terms adds one token set)
+    two = tools.CorpusStruct.from_buffer_copy(cs)
+    two.n_terms = 2
+    assert lib.nxsb_write_terms_file(str(tmp_path / "t").encode(), C.byref(two)) == 0
+    assert lib.nxsb_write_dtmap_file(str(tmp_path / "d").encode(), C.byref(cs)) == 0
+    assert (tmp_path / "t").read_bytes()[:len(TERMS_GOLDEN)] == TERMS_GOLDEN
+    assert (tmp_path / "d").read_bytes()[:len(DTMAP_GOLDEN)] == DTMAP_GOLDEN
+    assert (tmp_path / "t").stat().st_size == 32768 and (tmp_path / "d").stat().st_size == 32768
+
+
+def test_reader_roundtrip_and_deletion_markers(tmp_path, c1_corpus):
+    t, d = tmp_path / "nxsterms", tmp_path / "nxsdtmap"
+    c1_corpus.write(t, d)
+    back = tools.Corpus.read(t, d)
+    assert back.n_docs == c1_corpus.n_docs and back.n_terms == c1_corpus.n_terms
+    assert np.array_equal(back.pairs, c1_corpus.pairs) and np.array_equal(back.doc_off, c1_corpus.doc_off)
+    assert np.array_equal(back.doc_len, c1_corpus.doc_len) and back.term_blob == c1_corpus.term_blob
+    assert back.token_count == c1_corpus.token_count and back.doc_count == c1_corpus.doc_count
+    assert np.array_equal(back.term_df, c1_corpus.term_df) and np.array_equal(back.term_total, c1_corpus.term_total)
+    # delete document 3 the way idx_dtmap_remove does: zero the id in place, append {id, 0}
+    raw = bytearray(d.read_bytes())
+    data_len = int.from_bytes(raw[8:16], "big")
+    off = 32
+    for _ in range(2):
+        off += 16 + 8 * int.from_bytes(raw[off + 12: off + 16], "big")
+    assert int.from_bytes(raw[off: off + 8], "big") == 3
+    raw[off: off + 8] = bytes(8)
+    raw[32 + data_len: 32 + data_len + 16] = (3).to_bytes(8, "big") + bytes(8)
+    raw[8:16] = (data_len + 16).to_bytes(8, "big")
+    d.write_bytes(bytes(raw))
+    gone = tools.Corpus.read(t, d)
+    assert gone.n_docs == c1_corpus.n_docs - 1 and 3 not in set(gone.doc_ids[:10].tolist())
+
+
+# ---- API behaviour ---------------------------------------------------------
+
+def test_index_lifecycle_and_error_codes(nxs):
+    idx = nxs.create_index("main")
+    assert idx.params_json() == {"filters": ["normalizer", "stopwords", "stemmer"], "algo": "BM25", "lang": "en"}
+    with pytest.raises(capi.NxsError) as e:
+        nxs.create_index("main")
+    assert e.value.code == capi.ERR_EXISTS
+    with pytest.raises(capi.NxsError) as e:
+        nxs.open_index("main")                             # one handle per name (nxs.c:391-395)
+    assert e.value.code == capi.ERR_EXISTS
+    with pytest.raises(capi.NxsError) as e:
+        nxs.open_index("nope")
+    assert e.value.code == capi.ERR_MISSING
+    with pytest.raises(capi.NxsError) as e:
+        nxs.create_index("bad name!")
+    assert e.value.code == capi.ERR_INVALID
+
+    idx.add(7, "Hello hello WORLD")
+    with pytest.raises(capi.NxsError) as e:
+        idx.add(7, "again")
+    assert e.value.code == capi.ERR_EXISTS
+    with pytest.raises(capi.NxsError) as e:
+        idx.add(0, "zero id")
+    assert e.value.code == capi.ERR_INVALID
+    with pytest.raises(capi.NxsError) as e:
+        idx.add(8, " ... ")
+    assert e.value.code == capi.ERR_MISSING
+    with pytest.raises(capi.NxsError) as e:
+        idx.remove(99)
+    assert e.value.code == capi.ERR_MISSING
+    assert nxs._lib.nxs_luafilter_load(nxs.h, b"f", b"code") == -1 and nxs.error()[0] == capi.ERR_INVALID
+
+    for q, kw, code in (("", {}, capi.ERR_INVALID), ("a AND", {}, capi.ERR_INVALID),
+                        ("hello", {"limit": 0}, capi.ERR_INVALID), ("hello", {"algo": "PageRank"}, capi.ERR_INVALID)):
+        with pytest.raises(capi.NxsError) as e:
+            idx.search(q, **kw)
+        assert e.value.code == code, (q, kw)
+    # nothing resolves => empty result without touching the GPU (search.c:224-226)
+    assert idx.search("unknownterm", fuzzymatch=False) == []
+    idx.close()
+    nxs.destroy_index("main")
+    assert not (Path(nxs.base) / "data" / "main").exists()
+
+
+def test_no_gpu_means_a_loud_error_not_a_fallback(nxs):
+    from nxsearch_b200 import engine
+
+    if engine.device_count() > 0:
+        pytest.skip("a GPU is present")
+    idx = nxs.create_index("x")
+    idx.add(1, "alpha beta")
+    with pytest.raises(capi.NxsError) as e:
+        idx.search("alpha")
+    assert e.value.code == capi.ERR_SYSTEM and "no CPU fallback" in e.value.msg
+    with pytest.raises(RuntimeError):
+        engine.Engine(0)
+
+
+def test_index_files_are_interchangeable_with_the_reference(nxs, c1_corpus):
+    """Files written through nxs_index_add here open in the compiled reference
+    and vice versa, byte-identical for the same sequence of adds."""
+    ref = _oracle.ref()
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    texts = [(5, "the cat sat on the mat"), (9, "a cat and a dog"), (2, "dog eat dog world"), (11, "mat")]
+    ours = nxs.create_index("a")
+    for d, t in texts:
+        ours.add(d, t)
+    ours.remove(9)
+    ours.close()
+    rbase = tempfile.mkdtemp(prefix="nxsb_r_")
+    try:
+        rn = capi.Nxs(rbase, lib=ref)
+        theirs = rn.create_index("a")
+        for d, t in texts:
+            theirs.add(d, t)
+        theirs.remove(9)
+        theirs.close()
+        for f in ("nxsterms", "nxsdtmap"):
+            assert (Path(nxs.base) / "data/a" / f).read_bytes() == (Path(rbase) / "data/a" / f).read_bytes(), f
+        # and the reference searches an index this library wrote
+        shutil.copy(Path(nxs.base) / "data/a/nxsterms", Path(rbase) / "data/a/nxsterms")
+        shutil.copy(Path(nxs.base) / "data/a/nxsdtmap", Path(rbase) / "data/a/nxsdtmap")
+        again = rn.open_index("a")
+        assert sorted(d for d, _ in again.search("dog OR mat")) == [2, 5, 11]
+        again.close()
+        rn.close()
+    finally:
+        shutil.rmtree(rbase, ignore_errors=True)
+
+
+def test_every_declared_symbol_is_exported():
+    lib = C.CDLL(str(library_path()))
+    declared = set()
+    for hdr in (ROOT / "include").glob("*.h"):
+        text = re.sub(r"/\*.*?\*/", "", hdr.read_text(), flags=re.S)
+        declared |= set(re.findall(r"\b(nxsb?_[a-z0-9_]+)\s*\(", text))
+    assert len(declared) >= 55
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    # the reference's 25 public symbols
+    for s in ("nxs_open nxs_close nxs_luafilter_load nxs_get_error nxs_params_create nxs_params_fromjson "
+              "nxs_params_set_strlist nxs_params_set_str nxs_params_set_uint nxs_params_set_bool nxs_params_tojson "
+              "nxs_params_release nxs_index_create nxs_index_destroy nxs_index_get_params nxs_index_open "
+              "nxs_index_close nxs_index_add nxs_index_remove nxs_index_search nxs_resp_iter_reset "
+              "nxs_resp_iter_result nxs_resp_resultcount nxs_resp_tojson nxs_resp_release").split():
+        assert hasattr(lib, s), s
+
+
+def test_bk_mirror_reproduces_the_reference_search(c1_corpus, c1_oracle):
+    """parent/edge/rank arrays + exact distances == the oracle's BK-tree BFS
+    (host-side emulation of what the fuzzy kernel computes)."""
+    parent, edge, rank = c1_corpus.bk_mirror()
+    lev = _oracle.port().ora_levdist
+    terms = [c1_corpus.term(i + 1).encode() for i in range(c1_corpus.n_terms)]
+    by_len = {}
+    for i, t in enumerate(terms):
+        by_len.setdefault(len(t), []).append(i)
+    for q in c1_corpus.fuzzy_terms(60, seed=5):
+        want, cands, _, _ = c1_oracle.fuzzy(q)
+        best = None
+        for L in range(len(q) - 2, len(q) + 3):
+            for t in by_len.get(L, []):
+                # idxterm.c:239: only terms with a non-zero total are picked
+                if c1_corpus.term_total[t] == 0 or lev(q, len(q), terms[t], len(terms[t])) > 2:
+                    continue
+                c, ok = t, True
+                while parent[c] != 0xFFFFFFFF:
+                    p = int(parent[c])
+                    d = lev(q, len(q), terms[p], len(terms[p]))
+                    if not (max(d - 2, 0) <= edge[c] < min(d + 2, 63)):
+                        ok = False
+                        break
+                    c = p
+                if ok and (best is None or rank[t] < rank[best]):
+                    best = t
+        assert (best + 1 if best is not None else 0) == want, q

@@ -1,0 +1,184 @@
+"""The oracle is pinned before it is trusted (CPU only).
+
+1. the CPU restatement (oracle/nxs_oracle.c) against every golden vector the
+   reference's own tests hold for this path;
+2. the restatement against the reference itself -- its own C files compiled
+   with the shims under oracle/shims (oracle/_ref) -- on the synthetic C1
+   index: identical ids, scores and order, ties included.
+"""
+import ctypes as C
+import shutil
+import tempfile
+
+import numpy as np
+import pytest
+
+import _mk
+import _oracle
+from _oracle import BM25, TFIDF, OP_AND, OP_OR, OP_ANDNOT
+
+
+def test_levdist_goldens():
+    lib = _oracle.port()
+    for a, b, d in _mk.LEVDIST_CASES:
+        assert lib.ora_levdist(a.encode(), len(a), b.encode(), len(b)) == d, (a, b)
+        assert lib.ora_levdist(b.encode(), len(b), a.encode(), len(a)) == d, (b, a)
+
+
+def test_bktree_goldens():
+    """ref tests/t_bktree.c: the LAST candidate pushed for each misspelling is the word."""
+    corpus = _mk.make_corpus([(1, " ".join(_mk.BK_WORDS))])
+    ora = _oracle.OracleIndex(corpus)
+    for word, probe in zip(_mk.BK_WORDS, _mk.BK_SEARCH):
+        _, cands, dists, _ = ora.fuzzy(probe.encode())
+        assert len(cands) and corpus.term(int(cands[-1])) == word, (probe, cands)
+        assert all(d <= 2 for d in dists)
+
+
+def test_heap_goldens():
+    """ref tests/t_heap.c:115-129: uncapped -> plain descending sort; capped -> top-N."""
+    lib = _oracle.port()
+    rng = np.random.default_rng(1)
+    for n in range(1, 101):
+        vals = rng.integers(0, 1000, n).astype(np.float32)
+        pay = np.arange(n, dtype=np.uint64)
+        out_p = np.zeros(n, dtype=np.uint64)
+        out_s = np.zeros(n, dtype=np.float32)
+        k = lib.ora_heap_topn(100, n, vals.ctypes.data, pay.ctypes.data, out_p.ctypes.data, out_s.ctypes.data)
+        assert k == n and np.array_equal(out_s, np.sort(vals)[::-1])
+        cap = max(1, n // 3)
+        k = lib.ora_heap_topn(cap, n, vals.ctypes.data, pay.ctypes.data, out_p.ctypes.data, out_s.ctypes.data)
+        assert k == cap and np.array_equal(out_s[:cap], np.sort(vals)[::-1][:cap])
+    # SURVEY 8a F5 [probed]: limit 2 over four tied docs 5..8, fed in descending
+    # id order as nxs_resp_build does, keeps 8 and 7.
+    vals = np.ones(4, dtype=np.float32)
+    pay = np.array([8, 7, 6, 5], dtype=np.uint64)
+    out_p, out_s = np.zeros(4, dtype=np.uint64), np.zeros(4, dtype=np.float32)
+    assert lib.ora_heap_topn(2, 4, vals.ctypes.data, pay.ctypes.data, out_p.ctypes.data, out_s.ctypes.data) == 2
+    assert sorted(out_p[:2].tolist()) == [7, 8]
+
+
+@pytest.mark.parametrize("case", range(len(_mk.SCORING_CASES)))
+def test_scoring_goldens(case):
+    """ref tests/t_scoring.c cases 1,4,5,6,7 at its own tolerance (helpers.c:215)."""
+    docs, query, expected = _mk.SCORING_CASES[case]
+    corpus = _mk.make_corpus(docs)
+    ora = _oracle.OracleIndex(corpus)
+    leaves = [corpus.tid(w) for w in query.split()]
+    toks = []
+    for t in reversed(leaves):
+        if t not in toks:
+            toks.append(t)
+    slot = {t: s for s, t in enumerate(toks)}
+    prog = [slot[leaves[0]]]
+    for t in leaves[1:]:
+        prog += [slot[t], OP_OR]
+    for algo, col in ((TFIDF, 0), (BM25, 1)):
+        ids, sc = ora.search(algo, 1000, toks, prog)
+        got = dict(zip(ids.tolist(), sc.tolist()))
+        assert set(got) == set(expected)
+        for d, vals in expected.items():
+            assert abs(got[d] - vals[col]) < 1e-4, (d, got[d], vals[col])
+
+
+def test_querylogic_goldens():
+    """ref tests/t_querylogic.c:16-52."""
+    from nxsearch_b200 import tools
+
+    corpus = _mk.make_corpus(_mk.LOGIC_DOCS)
+    ora = _oracle.OracleIndex(corpus)
+    for query, expected in _mk.LOGIC_CASES:
+        leaves, prog = tools.query_compile(query)
+        ids = [corpus.tid(w.lower()) for w in leaves]
+        keep = [i for i, t in enumerate(ids) if t]
+        remap = {old: new for new, old in enumerate(keep)}
+        prog = [(remap.get(op, -1) if op >= 0 else op) for op in prog]
+        toks = [ids[i] for i in keep]
+        got, _ = ora.search(BM25, 1000, toks, prog) if toks else (np.array([]), None)
+        assert sorted(got.tolist()) == expected, query
+
+
+# ---------------------------------------------------------------------------
+# against the compiled reference
+
+
+needs_ref = pytest.mark.skipif(not _oracle.REF_SO.exists(), reason="oracle/_ref not built (no /root/reference)")
+
+
+@pytest.fixture(scope="module")
+def ref_c1(c1_corpus):
+    from nxsearch_b200 import capi
+
+    base = tempfile.mkdtemp(prefix="nxsb_ref_")
+    nxs = capi.Nxs(base, lib=_oracle.ref())
+    nxs.create_index("c1").close()
+    c1_corpus.write(f"{base}/data/c1/nxsterms", f"{base}/data/c1/nxsdtmap")
+    idx = nxs.open_index("c1")
+    yield idx
+    idx.close()
+    nxs.close()
+    shutil.rmtree(base, ignore_errors=True)
+
+
+@needs_ref
+@pytest.mark.parametrize("algo,name", [(BM25, "BM25"), (TFIDF, "TF-IDF")])
+def test_port_equals_reference_on_c1(c1_corpus, c1_oracle, ref_c1, algo, name):
+    """BASELINE config 1: 1000 OR queries, 250 each of 1..4 terms, top-10."""
+    qt = c1_corpus.query_terms(2500)
+    pos = 0
+    for qi in range(1000):
+        nt = 1 + qi // 250
+        leaves = [int(t) for t in qt[pos:pos + nt]]
+        pos += nt
+        toks = []
+        for t in reversed(leaves):
+            if t not in toks:
+                toks.append(t)
+        slot = {t: s for s, t in enumerate(toks)}
+        prog = [slot[leaves[0]]]
+        for t in leaves[1:]:
+            prog += [slot[t], OP_OR]
+        ref = ref_c1.search(" OR ".join(c1_corpus.term(t) for t in leaves), limit=10, algo=name, fuzzymatch=False)
+        ids, sc = c1_oracle.search(algo, 10, toks, prog)
+        assert ref == list(zip(ids.tolist(), sc.tolist())), leaves
+
+
+@needs_ref
+def test_port_equals_reference_on_boolean_queries(c1_corpus, c1_oracle, ref_c1):
+    """SURVEY 8d C3 templates through the reference's parser shim and search path."""
+    from nxsearch_b200 import tools
+
+    qt = [int(t) for t in c1_corpus.query_terms(6 * 120, seed=11)]
+    w = c1_corpus.term
+    for i in range(120):
+        a, b, c, d, e, f = qt[6 * i: 6 * i + 6]
+        q = [f"{w(a)} AND {w(b)}", f"({w(a)} OR {w(b)}) AND {w(c)}", f"{w(a)} AND NOT {w(b)}",
+             f"({w(a)} OR {w(b)}) AND ({w(c)} OR {w(d)}) AND NOT ({w(e)} OR {w(f)})"][i % 4]
+        leaves, prog = tools.query_compile(q)
+        toks = [c1_corpus_tid(c1_corpus, s) for s in leaves]
+        for algo, name in ((TFIDF, "TF-IDF"), (BM25, "BM25")):
+            ref = ref_c1.search(q, limit=100, algo=name, fuzzymatch=False)
+            ids, sc = c1_oracle.search(algo, 100, toks, prog)
+            assert ref == list(zip(ids.tolist(), sc.tolist())), q
+
+
+def c1_corpus_tid(corpus, s):
+    if not hasattr(corpus, "_tid"):
+        corpus._tid = {corpus.term(i + 1): i + 1 for i in range(corpus.n_terms)}
+    return corpus._tid[s]
+
+
+@needs_ref
+def test_port_fuzzy_equals_reference(c1_corpus, c1_oracle, ref_c1):
+    """idxterm_fuzzysearch of the compiled reference == the restated BK search."""
+    lib = _oracle.ref()
+    lib.idxterm_fuzzysearch.restype = C.c_void_p
+    lib.idxterm_fuzzysearch.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
+    hits = 0
+    for q in c1_corpus.fuzzy_terms(1500):
+        term = lib.idxterm_fuzzysearch(ref_c1.h, q, len(q))
+        ref_id = C.cast(term, C.POINTER(C.c_uint32))[0] if term else 0   # idxterm_t.id, index.h:43
+        got, _, _, _ = c1_oracle.fuzzy(q)
+        assert got == ref_id, q
+        hits += ref_id != 0
+    assert hits > 700
