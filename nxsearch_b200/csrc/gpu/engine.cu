@@ -91,7 +91,8 @@ struct Batch {
 	bool		used = false;
 	int		algo = 0;
 	uint32_t	limit = 0, n_q = 0, n_tok = 0, n_prog = 0;
-	uint32_t	max_tokens = 0;
+	uint32_t	max_tokens = 0;		// over the boolean queries (bitmap rows)
+	uint32_t	max_tokens_all = 0;	// over every query (plan record stride)
 	uint64_t	bytes = 0;		// algorithmic bytes
 	std::vector<uint32_t> q_or, q_logic;	// host lists
 	/* One H2D copy: [queries | tokens | prog | qlist_or | qlist_logic]. */
@@ -151,6 +152,9 @@ struct nxsb_engine {
 	size_t		sort_tmp_bytes = 0;
 	void *		d_cub_tmp = nullptr;
 	size_t		cub_tmp_bytes = 0;
+	unsigned char *	d_plan = nullptr;		// planned work items (stream kernel)
+	size_t		plan_bytes = 0;
+	bool		force_v2 = false;		// NXSB_KERNEL=v2: A/B against tiles.cuh
 
 	Batch		batches[MAX_HANDLES];
 	Batch		oneshot;	// reused by nxsb_engine_search
@@ -270,6 +274,11 @@ nxsb_engine_create(int device)
 	}
 	e->stream = e->own_stream;
 	e->n_sms = prop.multiProcessorCount;
+	{
+		/* Development switch: score with the older tiles.cuh kernel. */
+		const char *kv = getenv("NXSB_KERNEL");
+		e->force_v2 = kv && strcmp(kv, "v2") == 0;
+	}
 	for (auto &r : e->runs)
 		for (int i = 0; i < EV_PER_RUN; i++)
 			cudaEventCreateWithFlags(&r.ev[i], cudaEventDefault);
@@ -328,6 +337,7 @@ nxsb_engine_destroy(nxsb_engine_t *e)
 	fuzzy_free(e->fz);
 	dev_free(e->d_cand);
 	dev_free(e->d_sort_tmp);
+	dev_free(e->d_plan);
 	if (e->d_cub_tmp)
 		cudaFree(e->d_cub_tmp);
 	dev_free(e->d_logtab);
@@ -677,6 +687,7 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 	B.n_tok = b->n_tokens;
 	B.n_prog = b->n_prog;
 	B.max_tokens = 1;
+	B.max_tokens_all = 1;
 	B.bytes = 0;
 	B.q_or.clear();
 	B.q_logic.clear();
@@ -687,6 +698,7 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 		/* search.c:224-226: nothing resolved => empty result. */
 		if (q.n_tokens == 0 || q.n_prog == 0)
 			continue;
+		B.max_tokens_all = std::max(B.max_tokens_all, q.n_tokens);
 		if (is_pure_or(b, q)) {
 			B.q_or.push_back(i);
 		} else {
@@ -871,6 +883,70 @@ launch_tiles(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
 }
 
 /*
+ * The TMA-fed scorer (stream.cuh): plan the items, then one persistent
+ * launch, two CTAs per SM.
+ */
+static int
+launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
+    uint32_t k_tile, uint64_t cand_cap)
+{
+	const uint64_t items = (uint64_t)n_q * e->ntiles;
+	const uint32_t stride = 16u * (1u + std::max(B.max_tokens_all, 1u));
+	const size_t want = (size_t)items * stride;
+	StreamParams p;
+
+	if (want > e->plan_bytes) {
+		dev_free(e->d_plan);
+		e->plan_bytes = 0;
+		if (dev_alloc(&e->d_plan, want + want / 4) != cudaSuccess)
+			return fail(e, "plan arena allocation (%zu bytes) failed", want);
+		e->plan_bytes = want + want / 4;
+	}
+	p.post = e->d_post;
+	p.plan = e->d_plan;
+	p.plan_stride = stride;
+	p.n_q = n_q;
+	p.ntiles = e->ntiles;
+	p.k = k_tile;
+	p.thr = B.d_thr;
+	p.cand_count = B.d_cand_count;
+	p.cand = e->d_cand;
+	p.cand_cap = cand_cap;
+	p.work_counter = B.d_work;
+	p.logtab = e->d_logtab;
+	p.doc_len = e->d_doc_len;
+	p.K0 = e->K0;
+	p.K1 = e->K1;
+
+	auto kern = B.algo == NXSB_ALGO_BM25
+	    ? (e->wide ? score_stream_kernel<true, NXSB_ALGO_BM25>
+	       : score_stream_kernel<false, NXSB_ALGO_BM25>)
+	    : (e->wide ? score_stream_kernel<true, NXSB_ALGO_TFIDF>
+	       : score_stream_kernel<false, NXSB_ALGO_TFIDF>);
+	const size_t smem = ST_SMEM_BYTES;
+	int per_sm = 0;
+
+	CK(e, cudaFuncSetAttribute(kern,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	CK(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern,
+	    ST_THREADS, smem));
+	if (per_sm < 1)
+		return fail(e, "stream kernel does not fit an SM (smem %zu)", smem);
+	const unsigned grid = (unsigned)std::min<uint64_t>(items,
+	    (uint64_t)e->n_sms * per_sm);
+
+	CK(e, cudaMemsetAsync(B.d_thr, 0, B.zero_bytes, e->stream));
+	mark(e, "plan");
+	plan_items_kernel<<<(unsigned)((items + 255) / 256), 256, 0, e->stream>>>(
+	    B.d_queries, d_qlist, B.d_toks, n_q, e->ntiles, stride, e->d_plan);
+	mark(e, "score_tiles");
+	kern<<<grid, ST_THREADS, smem, e->stream>>>(p);
+	e->launches += 2;
+	CK(e, cudaGetLastError());
+	return 0;
+}
+
+/*
  * Score one list of queries (pure-OR or boolean) in chunks bounded by the
  * candidate arena: tiles -> per-query final top-k.
  */
@@ -897,12 +973,23 @@ run_list(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list,
 			return fail(e, "candidate arena allocation (%zu bytes) failed", want);
 		e->cand_bytes = want;
 	}
-	const uint32_t chunk = (uint32_t)std::min<size_t>(n_list, e->cand_bytes / per_q);
+	uint32_t chunk = (uint32_t)std::min<size_t>(n_list, e->cand_bytes / per_q);
+	const bool stream = !LOGIC && k <= ST_K_MAX && !e->force_v2;
+
+	if (stream) {
+		/* Item numbers are 32-bit; keep the plan arena under 1 GiB. */
+		const uint64_t per_q_plan = (uint64_t)e->ntiles * 16u * (1u + std::max(B.max_tokens_all, 1u));
+		const uint64_t cap = std::min<uint64_t>((1ull << 30) / per_q_plan,
+		    0xfffffff0ull / e->ntiles);
+
+		chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(chunk, cap));
+	}
 
 	for (uint32_t q0 = 0; q0 < n_list; q0 += chunk) {
 		const uint32_t n = std::min(chunk, n_list - q0);
 
-		if (launch_tiles<LOGIC>(e, B, d_qlist + q0, n, k_tile, cand_cap) == -1)
+		if ((stream ? launch_stream(e, B, d_qlist + q0, n, k_tile, cand_cap)
+		    : launch_tiles<LOGIC>(e, B, d_qlist + q0, n, k_tile, cand_cap)) == -1)
 			return -1;
 		mark(e, "topk");
 		if (small_k) {

@@ -134,6 +134,7 @@ bitonic_sort_desc(unsigned long long *s, uint32_t npow2)
 }
 
 #include "tiles.cuh"
+#include "stream.cuh"
 
 /*
  * Final per-query top-k: merge the candidates its tiles emitted.  One CTA

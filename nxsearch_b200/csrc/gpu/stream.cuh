@@ -1,0 +1,634 @@
+/*
+ * score_stream_kernel: the round-1 v3 hot kernel -- a warp-specialised,
+ * TMA-fed version of the tile scorer (score.cuh explains the tiling).
+ *
+ * The v2 kernel (tiles.cuh) was latency bound: every (query, tile) work item
+ * walked a chain of dependent global loads (work counter -> query -> token ->
+ * skip row -> postings) with all 256 threads waiting at barriers in between
+ * (profiles/README.md: issue slots 45 % busy, DRAM idle).  Here the chain is
+ * taken off the scoring threads:
+ *
+ *   plan_items_kernel   one thread per (tile, query): the batched
+ *                       term-to-posting-list lookup.  Writes a fixed-stride
+ *                       record {total, ntok, (first posting, count, idf)...}
+ *                       so the scorer needs ONE load per item, at an address
+ *                       that depends only on the item number.
+ *   producer warp       takes items from the global work counter (two in
+ *                       flight), reads their records and streams the posting
+ *                       slices into a ring of shared-memory stages with 1-D
+ *                       bulk TMA copies (cp.async.bulk -> UBLKCP), signalling
+ *                       "full" mbarriers.  It runs ahead of the consumers
+ *                       across item boundaries, so the ring stays full while
+ *                       they scan / sort / emit.
+ *   consumer warps      wait on a stage, score its postings (one 8-byte LDS
+ *                       per posting, lanes on consecutive postings so that
+ *                       dense lists hit consecutive accumulator banks) and
+ *                       accumulate into the 64 KB shared accumulator in
+ *                       token-list order; a named barrier separates tokens.
+ *
+ * Per-item epilogue:
+ *   - an item that fits one stage (<= 4 postings per consumer thread; 40 %
+ *     of C2 items, 1 % of its postings) never scans the tile: each thread
+ *     remembers the documents it touched and collects/clears them with an
+ *     atomic exchange;
+ *   - otherwise ONE fused pass reads the accumulator, keeps what beats the
+ *     query's threshold in a 1024-entry buffer and writes zeros back.  If the
+ *     buffer overflows, the uncollected survivors stay in the accumulator,
+ *     the buffer is cut to its k best, whose k-th key tightens the
+ *     threshold, and the pass repeats over what is left.
+ *
+ * Arithmetic is identical to tiles.cuh (same tables, same operation order).
+ */
+#ifndef NXSB_GPU_STREAM_CUH
+#define NXSB_GPU_STREAM_CUH
+
+#define ST_CWARPS	8			/* consumer warps */
+#define ST_NCONS	(32 * ST_CWARPS)	/* consumer threads */
+#define ST_THREADS	(ST_NCONS + 32)		/* + the producer warp */
+#define ST_SLOTS	4			/* postings per thread per stage */
+#define ST_STAGE_POST	(ST_SLOTS * ST_NCONS)	/* postings per stage */
+#define ST_NSTAGES	4
+#define ST_MAXSUB	NXSB_MAX_QUERY_TOKENS	/* slices per stage */
+#define ST_CAND		1024u			/* candidate buffer (>= one stage) */
+#define ST_K_MAX	128u			/* limit served by this kernel */
+
+#define ST_F_FIRST	1u	/* first stage of an item */
+#define ST_F_LAST	2u	/* last stage of an item */
+#define ST_F_CONT	4u	/* slice 0 continues the previous stage's token */
+#define ST_F_END	8u	/* no more work */
+
+/* One planned work item: header + one entry per non-empty token slice. */
+struct PlanHdr {
+	uint32_t	total;		/* postings in the item */
+	uint32_t	ntok;		/* non-empty slices */
+	uint32_t	pad[2];
+};
+struct PlanTok {
+	unsigned long long g0;		/* absolute index of the first posting */
+	uint32_t	n;
+	float		idf;
+};
+static_assert(sizeof(PlanHdr) == 16 && sizeof(PlanTok) == 16, "plan record");
+static_assert(ST_CAND >= ST_STAGE_POST, "a one-stage item must fit the candidate buffer");
+static_assert(2 * ST_K_MAX <= ST_CAND, "overflow rounds must make progress");
+
+struct StageSub {		/* a slice of one token inside a stage */
+	uint16_t	b0, b1;		/* buffer slots [b0, b1) */
+	float		idf;
+};
+struct StageMeta {
+	uint32_t	flags, nsub, slot, tile_lo;
+	StageSub	sub[ST_MAXSUB];
+};
+
+struct StreamParams {
+	const uint2 *		post;
+	const unsigned char *	plan;		/* [n_items] records */
+	uint32_t		plan_stride;	/* bytes */
+	uint32_t		n_q, ntiles, k;
+	unsigned long long *	thr;
+	uint32_t *		cand_count;
+	unsigned long long *	cand;
+	unsigned long long	cand_cap;
+	uint32_t *		work_counter;
+	const float *		logtab;
+	const uint32_t *	doc_len;	/* WIDE */
+	float			K0, K1;
+};
+
+#define ST_SMEM_BYTES	(TILE_DOCS * 4 + ST_NSTAGES * ST_STAGE_POST * 8 +	\
+    ST_CAND * 8 + ST_NSTAGES * sizeof(StageMeta) + LOGTAB_N * 4 +		\
+    2 * ST_NSTAGES * 8 + 64)
+
+/* ---- the batched term lookup ------------------------------------------ */
+
+__global__ void __launch_bounds__(256)
+plan_items_kernel(const QDesc *__restrict__ queries,
+    const uint32_t *__restrict__ qlist, const DTok *__restrict__ toks,
+    uint32_t n_q, uint32_t ntiles, uint32_t stride,
+    unsigned char *__restrict__ plan)
+{
+	const unsigned long long item =
+	    (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (item >= (unsigned long long)n_q * ntiles)
+		return;
+	/* Tile-major, highest tile first (ties prefer higher ids). */
+	const uint32_t tile = ntiles - 1 - (uint32_t)(item / n_q);
+	const uint32_t slot = (uint32_t)(item % n_q);
+	const QDesc qd = queries[qlist[slot]];
+	unsigned char *rec = plan + item * stride;
+	PlanTok *out = reinterpret_cast<PlanTok *>(rec + sizeof(PlanHdr));
+	uint32_t total = 0, m = 0;
+
+	for (uint32_t j = 0; j < qd.n_tokens; j++) {
+		const DTok &t = toks[qd.tok_off + j];
+		const uint32_t lo = __ldg(t.skip + tile);
+		const uint32_t hi = __ldg(t.skip + tile + 1);
+
+		if (hi > lo) {
+			PlanTok pt;
+
+			pt.g0 = t.post_off + lo;
+			pt.n = hi - lo;
+			pt.idf = t.idf;
+			out[m++] = pt;
+			total += hi - lo;
+		}
+	}
+	PlanHdr h;
+	h.total = total;
+	h.ntok = m;
+	h.pad[0] = h.pad[1] = 0;
+	*reinterpret_cast<PlanHdr *>(rec) = h;
+}
+
+/* ---- PTX wrappers ------------------------------------------------------ */
+
+__device__ __forceinline__ uint32_t
+smem_addr(const void *p)
+{
+	return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void
+mbar_init(uint32_t bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count));
+}
+
+__device__ __forceinline__ void
+mbar_arrive(uint32_t bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void
+mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+	    :: "r"(bar), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void
+mbar_wait(uint32_t bar, uint32_t parity)
+{
+	uint32_t ok;
+
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\t"
+		    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+		    "selp.u32 %0, 1, 0, p;\n\t}"
+		    : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+	} while (!ok);
+}
+
+/* 1-D bulk TMA copy global -> shared, completion on an mbarrier. */
+__device__ __forceinline__ void
+tma_load_1d(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes"
+	    " [%0], [%1], %2, [%3];"
+	    :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+__device__ __forceinline__ void
+cons_barrier()
+{
+	asm volatile("bar.sync 1, %0;" :: "n"(ST_NCONS) : "memory");
+}
+
+__device__ __forceinline__ float
+rcp_fast(float x)
+{
+	float r;
+
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+
+/* Bitonic sort (descending) by the consumer threads only. */
+__device__ __forceinline__ void
+st_sort_desc(unsigned long long *s, uint32_t npow2, uint32_t ctid)
+{
+	for (uint32_t size = 2; size <= npow2; size <<= 1) {
+		for (uint32_t stride = size >> 1; stride; stride >>= 1) {
+			cons_barrier();
+			for (uint32_t i = ctid; i < npow2 / 2; i += ST_NCONS) {
+				const uint32_t lo = 2 * i - (i & (stride - 1));
+				const uint32_t hi = lo + stride;
+				const bool desc = (lo & size) == 0;
+				const unsigned long long a = s[lo], b = s[hi];
+
+				if ((a < b) == desc) {
+					s[lo] = b;
+					s[hi] = a;
+				}
+			}
+		}
+	}
+	cons_barrier();
+}
+
+/*
+ * Scores of the ST_SLOTS postings a thread holds; same arithmetic as
+ * score_posting() in tiles.cuh, written branch-free so that the postings'
+ * dependency chains interleave.  Invalid slots carry the word 0 (tf = 0 ->
+ * weight 0).  The document length comes out of the packed word with a byte
+ * permute and one subtraction (0x4B000000 | dl is the float 2^23 + dl).
+ * Counts >= 256 (no table entry) are rare and patched in one cold branch.
+ */
+template <bool WIDE, int ALGO>
+__device__ __forceinline__ void
+st_score4(const StreamParams &p, const float *s_logtab, const uint2 (&v)[ST_SLOTS],
+    float idf, float (&sc)[ST_SLOTS])
+{
+	float x[ST_SLOTS];
+	uint32_t any = 0;
+
+#pragma unroll
+	for (int r = 0; r < ST_SLOTS; r++) {
+		const uint32_t tf = WIDE ? v[r].y : (v[r].y & 0xffffu);
+
+		x[r] = s_logtab[tf & (LOGTAB_N - 1)];
+		any |= tf;
+	}
+	if (any >= LOGTAB_N) {
+#pragma unroll
+		for (int r = 0; r < ST_SLOTS; r++) {
+			const uint32_t tf = WIDE ? v[r].y : (v[r].y & 0xffffu);
+
+			if (tf >= LOGTAB_N)
+				x[r] = (float)log((double)tf + 1.0);
+		}
+	}
+#pragma unroll
+	for (int r = 0; r < ST_SLOTS; r++) {
+		if (ALGO == NXSB_ALGO_TFIDF) {
+			sc[r] = __fmul_rn(x[r], idf);
+		} else {
+			const float dl = WIDE ? (float)(int)__ldg(p.doc_len + v[r].x)
+			    : __fsub_rn(__uint_as_float(__byte_perm(v[r].y, 0x4b000000u,
+			      0x7632)), 8388608.f);
+			const float d = __fmaf_rn(p.K1, dl, p.K0);
+
+			sc[r] = __fmul_rn(__fmul_rn(x[r], rcp_fast(__fadd_rn(x[r], d))), idf);
+		}
+	}
+}
+
+template <bool WIDE, int ALGO>
+__global__ void __launch_bounds__(ST_THREADS, 2)
+score_stream_kernel(const StreamParams p)
+{
+	extern __shared__ __align__(128) unsigned char smem_stream[];
+	float *acc = reinterpret_cast<float *>(smem_stream);
+	uint2 *ring = reinterpret_cast<uint2 *>(acc + TILE_DOCS);
+	unsigned long long *s_cand = reinterpret_cast<unsigned long long *>(
+	    ring + ST_NSTAGES * ST_STAGE_POST);
+	StageMeta *meta = reinterpret_cast<StageMeta *>(s_cand + ST_CAND);
+	float *s_logtab = reinterpret_cast<float *>(meta + ST_NSTAGES);
+	unsigned long long *bars = reinterpret_cast<unsigned long long *>(
+	    s_logtab + LOGTAB_N);		/* full[NSTAGES], empty[NSTAGES] */
+	uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 2 * ST_NSTAGES);
+	volatile uint32_t *s_ncand = s_misc;		/* [0] */
+	volatile uint32_t *s_base = s_misc + 1;
+	unsigned long long *s_theta = reinterpret_cast<unsigned long long *>(s_misc + 2);
+
+	const uint32_t tid = threadIdx.x;
+	const uint32_t full0 = smem_addr(bars), empty0 = smem_addr(bars + ST_NSTAGES);
+
+	for (uint32_t i = tid; i < LOGTAB_N; i += ST_THREADS)
+		s_logtab[i] = p.logtab[i];
+	{
+		float4 *a4 = reinterpret_cast<float4 *>(acc);
+		for (uint32_t i = tid; i < TILE_DOCS / 4; i += ST_THREADS)
+			a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+	}
+	if (tid == 0) {
+		for (uint32_t s = 0; s < ST_NSTAGES; s++) {
+			mbar_init(full0 + 8 * s, 1);
+			mbar_init(empty0 + 8 * s, ST_CWARPS);
+		}
+		*s_ncand = 0;
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+	}
+	__syncthreads();
+
+	const uint32_t n_items = p.n_q * p.ntiles;
+
+	if (tid >= ST_NCONS) {
+		/* ================= producer warp ================= */
+		const uint32_t lane = tid & 31;
+		uint32_t ps = 0, pph = 1;	/* stage, parity of its empty barrier */
+		uint32_t it0, it1;
+
+		{
+			uint32_t a = 0, b = 0;
+			if (lane == 0) {
+				a = atomicAdd(p.work_counter, 1u);
+				b = atomicAdd(p.work_counter, 1u);
+			}
+			it0 = __shfl_sync(0xffffffffu, a, 0);
+			it1 = __shfl_sync(0xffffffffu, b, 0);
+		}
+		auto load_hdr = [&](uint32_t it) -> uint2 {
+			if (it >= n_items)
+				return make_uint2(0u, 0u);
+			return __ldg(reinterpret_cast<const uint2 *>(
+			    p.plan + (unsigned long long)it * p.plan_stride));
+		};
+		auto load_tok = [&](uint32_t it, uint32_t ntok) -> uint4 {
+			if (it >= n_items || lane >= ntok)
+				return make_uint4(0u, 0u, 0u, 0u);
+			return __ldg(reinterpret_cast<const uint4 *>(
+			    p.plan + (unsigned long long)it * p.plan_stride + 16) + lane);
+		};
+		uint2 h0 = load_hdr(it0);
+		uint4 t0 = load_tok(it0, h0.y);
+
+		/* Open stage state. */
+		bool open = false;
+		uint32_t used = 0, nsub = 0, bytes = 0, flags = 0;
+
+		auto commit = [&](uint32_t extra_flags, uint32_t slot, uint32_t tile_lo) {
+			if (lane == 0) {
+				StageMeta &m = meta[ps];
+
+				m.flags = flags | extra_flags;
+				m.nsub = nsub;
+				m.slot = slot;
+				m.tile_lo = tile_lo;
+				if (bytes)
+					mbar_arrive_expect_tx(full0 + 8 * ps, bytes);
+				else
+					mbar_arrive(full0 + 8 * ps);
+			}
+			__syncwarp();
+			open = false;
+			if (++ps == ST_NSTAGES) {
+				ps = 0;
+				pph ^= 1;
+			}
+		};
+		auto acquire = [&]() {
+			mbar_wait(empty0 + 8 * ps, pph);
+			open = true;
+			used = nsub = bytes = flags = 0;
+		};
+
+		while (it0 < n_items) {
+			/* Keep the next item's number and record in flight. */
+			uint32_t raw2 = 0;
+			if (lane == 0)
+				raw2 = atomicAdd(p.work_counter, 1u);
+			const uint2 h1 = load_hdr(it1);
+			const uint4 t1 = load_tok(it1, h1.y);
+
+			if (h0.x != 0) {
+				const uint32_t tile = p.ntiles - 1 - it0 / p.n_q;
+				const uint32_t slot = it0 % p.n_q;
+				const uint32_t tile_lo = tile << TILE_SHIFT;
+				const uint32_t ntok = h0.y;
+				uint32_t first = ST_F_FIRST;
+
+				for (uint32_t j = 0; j < ntok; j++) {
+					unsigned long long g =
+					    ((unsigned long long)__shfl_sync(0xffffffffu, t0.y, j) << 32) |
+					    __shfl_sync(0xffffffffu, t0.x, j);
+					uint32_t n = __shfl_sync(0xffffffffu, t0.z, j);
+					const uint32_t idf_bits = __shfl_sync(0xffffffffu, t0.w, j);
+					bool cont = false;
+
+					while (n > 0) {
+						if (!open) {
+							acquire();
+							flags = first | (cont ? ST_F_CONT : 0u);
+							first = 0;
+						}
+						const uint32_t head = (uint32_t)g & 1u;
+						const uint32_t avail = ST_STAGE_POST - used;
+						const uint32_t take = min(n, avail - head);
+						const uint32_t cnt = (head + take + 1u) & ~1u;
+
+						if (lane == 0) {
+							StageSub &sb = meta[ps].sub[nsub];
+
+							sb.b0 = (uint16_t)(used + head);
+							sb.b1 = (uint16_t)(used + head + take);
+							sb.idf = __uint_as_float(idf_bits);
+							tma_load_1d(smem_addr(ring + ps * ST_STAGE_POST + used),
+							    p.post + (g - head), cnt * 8u, full0 + 8 * ps);
+						}
+						nsub++;
+						bytes += cnt * 8u;
+						used += cnt;
+						g += take;
+						n -= take;
+						cont = true;
+						if (n > 0 || used + 2 > ST_STAGE_POST || nsub == ST_MAXSUB) {
+							const bool last = (n == 0 && j + 1 == ntok);
+
+							commit(last ? ST_F_LAST : 0u, slot, tile_lo);
+						}
+					}
+				}
+				if (open)
+					commit(ST_F_LAST, slot, tile_lo);
+			}
+			it0 = it1;
+			h0 = h1;
+			t0 = t1;
+			it1 = __shfl_sync(0xffffffffu, raw2, 0);
+		}
+		/* Tell the consumers there is nothing more. */
+		acquire();
+		flags = ST_F_END;
+		commit(0u, 0u, 0u);
+		return;
+	}
+
+	/* ================= consumer warps ================= */
+	const uint32_t ctid = tid;
+	uint32_t cs = 0, cph = 0;
+	unsigned long long theta_pref = 0;
+
+	for (;;) {
+		mbar_wait(full0 + 8 * cs, cph);
+		const StageMeta &m = meta[cs];
+		const uint32_t flags = m.flags;
+
+		if (flags & ST_F_END)
+			break;
+		const uint32_t nsub = m.nsub, slot = m.slot, tile_lo = m.tile_lo;
+		const uint2 *buf = ring + cs * ST_STAGE_POST;
+		uint32_t mine[ST_SLOTS];
+
+#pragma unroll
+		for (int r = 0; r < ST_SLOTS; r++)
+			mine[r] = 0xffffffffu;
+		if ((flags & ST_F_FIRST) && ctid == 0)
+			theta_pref = *(volatile unsigned long long *)(p.thr + slot);
+
+		for (uint32_t s = 0; s < nsub; s++) {
+			const StageSub sb = m.sub[s];
+			const uint32_t b0 = sb.b0, nb = (uint32_t)sb.b1 - sb.b0;
+			const float idf = sb.idf;
+
+			/* A new token: the previous token's updates must have landed. */
+			if (s != 0 || !(flags & (ST_F_FIRST | ST_F_CONT)))
+				cons_barrier();
+
+			uint2 v[ST_SLOTS];
+			bool ok[ST_SLOTS];
+			uint32_t loc[ST_SLOTS];
+			float sc[ST_SLOTS], a[ST_SLOTS];
+
+#pragma unroll
+			for (int r = 0; r < ST_SLOTS; r++) {
+				const uint32_t i = ctid + r * ST_NCONS;
+
+				ok[r] = (i - b0) < nb;
+				/* WIDE gathers doc_len[doc]: keep the dummy in range. */
+				v[r] = make_uint2(tile_lo, 0u);
+				if (ok[r])
+					v[r] = buf[i];
+			}
+			st_score4<WIDE, ALGO>(p, s_logtab, v, idf, sc);
+			/* Documents of one list are distinct: batch the updates. */
+#pragma unroll
+			for (int r = 0; r < ST_SLOTS; r++) {
+				loc[r] = v[r].x - tile_lo;
+				if (ok[r]) {
+					a[r] = acc[loc[r]];
+					mine[r] = loc[r];
+				}
+			}
+#pragma unroll
+			for (int r = 0; r < ST_SLOTS; r++)
+				if (ok[r])
+					acc[loc[r]] = __fadd_rn(a[r], sc[r]);
+		}
+		/* Stage consumed (its data and meta are in registers now). */
+		__syncwarp();
+		if ((ctid & 31) == 0)
+			mbar_arrive(empty0 + 8 * cs);
+		if (++cs == ST_NSTAGES) {
+			cs = 0;
+			cph ^= 1;
+		}
+		if (!(flags & ST_F_LAST))
+			continue;
+
+		/* ---------------- item epilogue: top-k of the tile ---------------- */
+		if (ctid == 0)
+			*s_theta = theta_pref;
+		cons_barrier();
+		unsigned long long thr_key = *s_theta;
+		const uint32_t k = p.k;
+		bool sorted = false;
+		uint32_t total;
+
+		if (flags & ST_F_FIRST) {
+			/* Sparse item: visit only the documents this thread touched. */
+			const float ths = thr_key ? __uint_as_float((uint32_t)(thr_key >> 32))
+			    : __uint_as_float(1u);
+
+#pragma unroll
+			for (int r = 0; r < ST_SLOTS; r++) {
+				if (mine[r] != 0xffffffffu) {
+					const float val = atomicExch(acc + mine[r], 0.f);
+
+					if (val >= ths) {
+						const unsigned long long key = make_key(val, tile_lo + mine[r]);
+
+						if (key > thr_key) {
+							/* at < ST_STAGE_POST <= ST_CAND */
+							s_cand[atomicAdd((uint32_t *)s_ncand, 1u)] = key;
+						}
+					}
+				}
+			}
+			cons_barrier();
+			total = *s_ncand;
+		} else {
+			for (;;) {
+				const float ths = thr_key ? __uint_as_float((uint32_t)(thr_key >> 32))
+				    : __uint_as_float(1u);
+				float4 *a4 = reinterpret_cast<float4 *>(acc);
+
+				auto visit = [&](float &val, uint32_t i) {
+					if (val >= ths) {
+						const unsigned long long key = make_key(val, tile_lo + i);
+
+						if (key > thr_key) {
+							const uint32_t at = atomicAdd((uint32_t *)s_ncand, 1u);
+
+							if (at < ST_CAND)
+								s_cand[at] = key;
+							else
+								return;	/* stays for the next round */
+						}
+					}
+					val = 0.f;
+				};
+#pragma unroll 4
+				for (uint32_t i4 = ctid; i4 < TILE_DOCS / 4; i4 += ST_NCONS) {
+					float4 q = a4[i4];
+
+					if (q.x >= ths || q.y >= ths || q.z >= ths || q.w >= ths) {
+						visit(q.x, 4 * i4 + 0);
+						visit(q.y, 4 * i4 + 1);
+						visit(q.z, 4 * i4 + 2);
+						visit(q.w, 4 * i4 + 3);
+						a4[i4] = q;
+					} else if (q.x != 0.f || q.y != 0.f || q.z != 0.f || q.w != 0.f) {
+						a4[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+					}
+				}
+				cons_barrier();
+				total = *s_ncand;
+				if (total <= ST_CAND)
+					break;
+				/* Overflow: keep the k best, tighten, rescan what is left. */
+				st_sort_desc(s_cand, ST_CAND, ctid);
+				sorted = true;
+				thr_key = s_cand[k - 1];
+				if (ctid == 0)
+					*s_ncand = k;
+				cons_barrier();
+			}
+		}
+
+		if (total != 0) {
+			uint32_t n_emit = total;
+
+			if (total > k) {
+				uint32_t npow2 = 2;
+
+				while (npow2 < total)
+					npow2 <<= 1;
+				for (uint32_t i = total + ctid; i < npow2; i += ST_NCONS)
+					s_cand[i] = 0;
+				st_sort_desc(s_cand, npow2, ctid);
+				n_emit = k;
+				sorted = true;
+			}
+			if (ctid == 0)
+				*s_base = atomicAdd(p.cand_count + slot, n_emit);
+			cons_barrier();
+			unsigned long long *out = p.cand +
+			    (unsigned long long)slot * p.cand_cap + *s_base;
+			for (uint32_t i = ctid; i < n_emit; i += ST_NCONS)
+				out[i] = s_cand[i];
+			if (sorted && total >= k && ctid == 0)
+				atomicMax(p.thr + slot, s_cand[k - 1]);
+			cons_barrier();
+			if (ctid == 0)
+				*s_ncand = 0;
+		}
+	}
+}
+
+#endif
