@@ -45,9 +45,9 @@
 #define ST_CWARPS	8			/* consumer warps */
 #define ST_NCONS	(32 * ST_CWARPS)	/* consumer threads */
 #define ST_THREADS	(ST_NCONS + 32)		/* + the producer warp */
-#define ST_SLOTS	4			/* postings per thread per stage */
+#define ST_SLOTS	6			/* postings per thread per stage */
 #define ST_STAGE_POST	(ST_SLOTS * ST_NCONS)	/* postings per stage */
-#define ST_NSTAGES	4
+#define ST_NSTAGES	3
 #define ST_MAXSUB	NXSB_MAX_QUERY_TOKENS	/* slices per stage */
 #define ST_CAND		1024u			/* candidate buffer (>= one stage) */
 #define ST_K_MAX	128u			/* limit served by this kernel */
@@ -56,6 +56,9 @@
 #define ST_F_LAST	2u	/* last stage of an item */
 #define ST_F_CONT	4u	/* slice 0 continues the previous stage's token */
 #define ST_F_END	8u	/* no more work */
+#define ST_F_FULL	16u	/* one slice filling every slot of the stage */
+#define ST_F_SPARSE	32u	/* whole item in this stage, <= ST_CAND postings */
+#define ST_F_NSUB_SHIFT	8
 
 /* One planned work item: header + one entry per non-empty token slice. */
 struct PlanHdr {
@@ -69,7 +72,6 @@ struct PlanTok {
 	float		idf;
 };
 static_assert(sizeof(PlanHdr) == 16 && sizeof(PlanTok) == 16, "plan record");
-static_assert(ST_CAND >= ST_STAGE_POST, "a one-stage item must fit the candidate buffer");
 static_assert(2 * ST_K_MAX <= ST_CAND, "overflow rounds must make progress");
 
 struct StageSub {		/* a slice of one token inside a stage */
@@ -77,7 +79,10 @@ struct StageSub {		/* a slice of one token inside a stage */
 	float		idf;
 };
 struct StageMeta {
-	uint32_t	flags, nsub, slot, tile_lo;
+	/* One 16-byte load tells a consumer everything about a FULL stage. */
+	uint32_t	flags;		/* ST_F_* | nsub << ST_F_NSUB_SHIFT */
+	uint32_t	slot, tile_lo;
+	float		idf0;		/* = sub[0].idf */
 	StageSub	sub[ST_MAXSUB];
 };
 
@@ -230,6 +235,29 @@ st_sort_desc(unsigned long long *s, uint32_t npow2, uint32_t ctid)
 	cons_barrier();
 }
 
+/* (float)log(tf + 1) for the counts the table does not hold (cold). */
+static __device__ __noinline__ float
+st_log_slow(uint32_t tf)
+{
+	return (float)log((double)tf + 1.0);
+}
+
+/* Plain shared-memory word access by 32-bit shared address. */
+__device__ __forceinline__ float
+lds_f32(uint32_t addr)
+{
+	float v;
+
+	asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+	return v;
+}
+
+__device__ __forceinline__ void
+sts_f32(uint32_t addr, float v)
+{
+	asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr), "f"(v) : "memory");
+}
+
 /*
  * Scores of the ST_SLOTS postings a thread holds; same arithmetic as
  * score_posting() in tiles.cuh, written branch-free so that the postings'
@@ -248,18 +276,18 @@ st_score4(const StreamParams &p, const float *s_logtab, const uint2 (&v)[ST_SLOT
 
 #pragma unroll
 	for (int r = 0; r < ST_SLOTS; r++) {
-		const uint32_t tf = WIDE ? v[r].y : (v[r].y & 0xffffu);
-
-		x[r] = s_logtab[tf & (LOGTAB_N - 1)];
-		any |= tf;
+		x[r] = s_logtab[__byte_perm(v[r].y, 0u, 0x4440)];	/* count & 255 */
+		any |= v[r].y;
 	}
+	if (!WIDE)
+		any &= 0xffffu;
 	if (any >= LOGTAB_N) {
 #pragma unroll
 		for (int r = 0; r < ST_SLOTS; r++) {
 			const uint32_t tf = WIDE ? v[r].y : (v[r].y & 0xffffu);
 
 			if (tf >= LOGTAB_N)
-				x[r] = (float)log((double)tf + 1.0);
+				x[r] = st_log_slow(tf);
 		}
 	}
 #pragma unroll
@@ -350,16 +378,22 @@ score_stream_kernel(const StreamParams p)
 
 		/* Open stage state. */
 		bool open = false;
-		uint32_t used = 0, nsub = 0, bytes = 0, flags = 0;
+		uint32_t used = 0, nsub = 0, bytes = 0, flags = 0, item_total = 0;
 
 		auto commit = [&](uint32_t extra_flags, uint32_t slot, uint32_t tile_lo) {
 			if (lane == 0) {
 				StageMeta &m = meta[ps];
+				uint32_t f = flags | extra_flags;
 
-				m.flags = flags | extra_flags;
-				m.nsub = nsub;
+				if (nsub == 1 && m.sub[0].b0 == 0 && m.sub[0].b1 == ST_STAGE_POST)
+					f |= ST_F_FULL;
+				if ((f & (ST_F_FIRST | ST_F_LAST)) == (ST_F_FIRST | ST_F_LAST) &&
+				    item_total <= ST_CAND)
+					f |= ST_F_SPARSE;
+				m.flags = f | (nsub << ST_F_NSUB_SHIFT);
 				m.slot = slot;
 				m.tile_lo = tile_lo;
+				m.idf0 = m.sub[0].idf;
 				if (bytes)
 					mbar_arrive_expect_tx(full0 + 8 * ps, bytes);
 				else
@@ -392,6 +426,8 @@ score_stream_kernel(const StreamParams p)
 				const uint32_t tile_lo = tile << TILE_SHIFT;
 				const uint32_t ntok = h0.y;
 				uint32_t first = ST_F_FIRST;
+
+				item_total = h0.x;
 
 				for (uint32_t j = 0; j < ntok; j++) {
 					unsigned long long g =
@@ -457,58 +493,80 @@ score_stream_kernel(const StreamParams p)
 	for (;;) {
 		mbar_wait(full0 + 8 * cs, cph);
 		const StageMeta &m = meta[cs];
-		const uint32_t flags = m.flags;
+		const uint4 hdr = *reinterpret_cast<const uint4 *>(&m);
+		const uint32_t flags = hdr.x;
 
 		if (flags & ST_F_END)
 			break;
-		const uint32_t nsub = m.nsub, slot = m.slot, tile_lo = m.tile_lo;
+		const uint32_t slot = hdr.y, tile_lo = hdr.z;
 		const uint2 *buf = ring + cs * ST_STAGE_POST;
+		/* Shared address of acc[doc - tile_lo] = accb + 4 * doc. */
+		const uint32_t accb = smem_addr(acc) - 4u * tile_lo;
 		uint32_t mine[ST_SLOTS];
 
-#pragma unroll
-		for (int r = 0; r < ST_SLOTS; r++)
-			mine[r] = 0xffffffffu;
 		if ((flags & ST_F_FIRST) && ctid == 0)
 			theta_pref = *(volatile unsigned long long *)(p.thr + slot);
 
-		for (uint32_t s = 0; s < nsub; s++) {
-			const StageSub sb = m.sub[s];
-			const uint32_t b0 = sb.b0, nb = (uint32_t)sb.b1 - sb.b0;
-			const float idf = sb.idf;
-
-			/* A new token: the previous token's updates must have landed. */
-			if (s != 0 || !(flags & (ST_F_FIRST | ST_F_CONT)))
-				cons_barrier();
-
+		if (flags & ST_F_FULL) {
+			/* The common case: every slot valid, one token. */
 			uint2 v[ST_SLOTS];
-			bool ok[ST_SLOTS];
-			uint32_t loc[ST_SLOTS];
 			float sc[ST_SLOTS], a[ST_SLOTS];
 
-#pragma unroll
-			for (int r = 0; r < ST_SLOTS; r++) {
-				const uint32_t i = ctid + r * ST_NCONS;
-
-				ok[r] = (i - b0) < nb;
-				/* WIDE gathers doc_len[doc]: keep the dummy in range. */
-				v[r] = make_uint2(tile_lo, 0u);
-				if (ok[r])
-					v[r] = buf[i];
-			}
-			st_score4<WIDE, ALGO>(p, s_logtab, v, idf, sc);
-			/* Documents of one list are distinct: batch the updates. */
-#pragma unroll
-			for (int r = 0; r < ST_SLOTS; r++) {
-				loc[r] = v[r].x - tile_lo;
-				if (ok[r]) {
-					a[r] = acc[loc[r]];
-					mine[r] = loc[r];
-				}
-			}
+			if (!(flags & (ST_F_FIRST | ST_F_CONT)))
+				cons_barrier();
 #pragma unroll
 			for (int r = 0; r < ST_SLOTS; r++)
-				if (ok[r])
-					acc[loc[r]] = __fadd_rn(a[r], sc[r]);
+				v[r] = buf[ctid + r * ST_NCONS];
+			st_score4<WIDE, ALGO>(p, s_logtab, v, __uint_as_float(hdr.w), sc);
+#pragma unroll
+			for (int r = 0; r < ST_SLOTS; r++)
+				a[r] = lds_f32(accb + 4u * v[r].x);
+#pragma unroll
+			for (int r = 0; r < ST_SLOTS; r++)
+				sts_f32(accb + 4u * v[r].x, __fadd_rn(a[r], sc[r]));
+		} else {
+			const uint32_t nsub = flags >> ST_F_NSUB_SHIFT;
+
+#pragma unroll
+			for (int r = 0; r < ST_SLOTS; r++)
+				mine[r] = 0xffffffffu;
+			for (uint32_t s = 0; s < nsub; s++) {
+				const StageSub sb = m.sub[s];
+				const uint32_t b0 = sb.b0, nb = (uint32_t)sb.b1 - sb.b0;
+				const float idf = sb.idf;
+
+				/* A new token: the previous token's updates must have landed. */
+				if (s != 0 || !(flags & (ST_F_FIRST | ST_F_CONT)))
+					cons_barrier();
+
+				uint2 v[ST_SLOTS];
+				bool ok[ST_SLOTS];
+				float sc[ST_SLOTS], a[ST_SLOTS];
+
+#pragma unroll
+				for (int r = 0; r < ST_SLOTS; r++) {
+					const uint32_t i = ctid + r * ST_NCONS;
+
+					ok[r] = (i - b0) < nb;
+					/* WIDE gathers doc_len[doc]: keep the dummy in range. */
+					v[r] = make_uint2(tile_lo, 0u);
+					if (ok[r])
+						v[r] = buf[i];
+				}
+				st_score4<WIDE, ALGO>(p, s_logtab, v, idf, sc);
+				/* Documents of one list are distinct: batch the updates. */
+#pragma unroll
+				for (int r = 0; r < ST_SLOTS; r++) {
+					if (ok[r]) {
+						a[r] = lds_f32(accb + 4u * v[r].x);
+						mine[r] = v[r].x - tile_lo;
+					}
+				}
+#pragma unroll
+				for (int r = 0; r < ST_SLOTS; r++)
+					if (ok[r])
+						sts_f32(accb + 4u * v[r].x, __fadd_rn(a[r], sc[r]));
+			}
 		}
 		/* Stage consumed (its data and meta are in registers now). */
 		__syncwarp();
@@ -530,7 +588,7 @@ score_stream_kernel(const StreamParams p)
 		bool sorted = false;
 		uint32_t total;
 
-		if (flags & ST_F_FIRST) {
+		if (flags & ST_F_SPARSE) {
 			/* Sparse item: visit only the documents this thread touched. */
 			const float ths = thr_key ? __uint_as_float((uint32_t)(thr_key >> 32))
 			    : __uint_as_float(1u);
@@ -544,7 +602,7 @@ score_stream_kernel(const StreamParams p)
 						const unsigned long long key = make_key(val, tile_lo + mine[r]);
 
 						if (key > thr_key) {
-							/* at < ST_STAGE_POST <= ST_CAND */
+							/* at < item total <= ST_CAND */
 							s_cand[atomicAdd((uint32_t *)s_ncand, 1u)] = key;
 						}
 					}
