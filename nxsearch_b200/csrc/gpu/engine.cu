@@ -154,6 +154,8 @@ struct nxsb_engine {
 	size_t		cub_tmp_bytes = 0;
 	unsigned char *	d_plan = nullptr;		// planned work items (stream kernel)
 	size_t		plan_bytes = 0;
+	uint32_t *	d_tile_cnt = nullptr;		// candidates per (query, tile)
+	size_t		tile_cnt_bytes = 0;
 	bool		force_v2 = false;		// NXSB_KERNEL=v2: A/B against tiles.cuh
 
 	Batch		batches[MAX_HANDLES];
@@ -338,6 +340,7 @@ nxsb_engine_destroy(nxsb_engine_t *e)
 	dev_free(e->d_cand);
 	dev_free(e->d_sort_tmp);
 	dev_free(e->d_plan);
+	dev_free(e->d_tile_cnt);
 	if (e->d_cub_tmp)
 		cudaFree(e->d_cub_tmp);
 	dev_free(e->d_logtab);
@@ -902,6 +905,14 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
 			return fail(e, "plan arena allocation (%zu bytes) failed", want);
 		e->plan_bytes = want + want / 4;
 	}
+	const size_t want_cnt = (size_t)items * 4;
+	if (want_cnt > e->tile_cnt_bytes) {
+		dev_free(e->d_tile_cnt);
+		e->tile_cnt_bytes = 0;
+		if (dev_alloc(&e->d_tile_cnt, items + items / 4) != cudaSuccess)
+			return fail(e, "tile count allocation (%zu bytes) failed", want_cnt);
+		e->tile_cnt_bytes = (items + items / 4) * 4;
+	}
 	p.post = e->d_post;
 	p.plan = e->d_plan;
 	p.plan_stride = stride;
@@ -909,14 +920,14 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
 	p.ntiles = e->ntiles;
 	p.k = k_tile;
 	p.thr = B.d_thr;
-	p.cand_count = B.d_cand_count;
+	p.tile_count = e->d_tile_cnt;
 	p.cand = e->d_cand;
-	p.cand_cap = cand_cap;
 	p.work_counter = B.d_work;
 	p.logtab = e->d_logtab;
 	p.doc_len = e->d_doc_len;
 	p.K0 = e->K0;
 	p.K1 = e->K1;
+	(void)cand_cap;		/* = ntiles * k_tile: one k-cell per (query, tile) */
 
 	auto kern = B.algo == NXSB_ALGO_BM25
 	    ? (e->wide ? score_stream_kernel<true, NXSB_ALGO_BM25>
@@ -936,6 +947,7 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
 	    (uint64_t)e->n_sms * per_sm);
 
 	CK(e, cudaMemsetAsync(B.d_thr, 0, B.zero_bytes, e->stream));
+	CK(e, cudaMemsetAsync(e->d_tile_cnt, 0, want_cnt, e->stream));
 	mark(e, "plan");
 	plan_items_kernel<<<(unsigned)((items + 255) / 256), 256, 0, e->stream>>>(
 	    B.d_queries, d_qlist, B.d_toks, n_q, e->ntiles, stride, e->d_plan);
@@ -992,6 +1004,13 @@ run_list(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list,
 		    : launch_tiles<LOGIC>(e, B, d_qlist + q0, n, k_tile, cand_cap)) == -1)
 			return -1;
 		mark(e, "topk");
+		if (stream) {
+			finalize_cells_kernel<<<n, 256, 0, st>>>(e->d_cand, e->d_tile_cnt,
+			    e->ntiles, d_qlist + q0, k, e->d_doc_ids, d_recs, B.d_counts);
+			e->launches++;
+			CK(e, cudaGetLastError());
+			continue;
+		}
 		if (small_k) {
 			finalize_topk_kernel<<<n, 256, 0, st>>>(e->d_cand, cand_cap,
 			    B.d_cand_count, d_qlist + q0, k, e->d_doc_ids, d_recs,

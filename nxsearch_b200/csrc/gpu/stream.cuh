@@ -51,6 +51,7 @@
 #define ST_MAXSUB	NXSB_MAX_QUERY_TOKENS	/* slices per stage */
 #define ST_CAND		1024u			/* candidate buffer (>= one stage) */
 #define ST_K_MAX	128u			/* limit served by this kernel */
+#define ST_RANK_MAX	256u			/* candidates ranked by counting */
 
 #define ST_F_FIRST	1u	/* first stage of an item */
 #define ST_F_LAST	2u	/* last stage of an item */
@@ -91,10 +92,9 @@ struct StreamParams {
 	const unsigned char *	plan;		/* [n_items] records */
 	uint32_t		plan_stride;	/* bytes */
 	uint32_t		n_q, ntiles, k;
-	unsigned long long *	thr;
-	uint32_t *		cand_count;
-	unsigned long long *	cand;
-	unsigned long long	cand_cap;
+	unsigned long long *	thr;		/* [n_q] pruning thresholds */
+	uint32_t *		tile_count;	/* [n_q][ntiles] candidates emitted */
+	unsigned long long *	cand;		/* [n_q][ntiles][k] */
 	uint32_t *		work_counter;
 	const float *		logtab;
 	const uint32_t *	doc_len;	/* WIDE */
@@ -259,23 +259,23 @@ sts_f32(uint32_t addr, float v)
 }
 
 /*
- * Scores of the ST_SLOTS postings a thread holds; same arithmetic as
+ * Scores of the NP postings a thread holds; same arithmetic as
  * score_posting() in tiles.cuh, written branch-free so that the postings'
  * dependency chains interleave.  Invalid slots carry the word 0 (tf = 0 ->
  * weight 0).  The document length comes out of the packed word with a byte
  * permute and one subtraction (0x4B000000 | dl is the float 2^23 + dl).
  * Counts >= 256 (no table entry) are rare and patched in one cold branch.
  */
-template <bool WIDE, int ALGO>
+template <bool WIDE, int ALGO, int NP>
 __device__ __forceinline__ void
-st_score4(const StreamParams &p, const float *s_logtab, const uint2 (&v)[ST_SLOTS],
-    float idf, float (&sc)[ST_SLOTS])
+st_score(const StreamParams &p, const float *s_logtab, const uint2 (&v)[NP],
+    float idf, float (&sc)[NP])
 {
-	float x[ST_SLOTS];
+	float x[NP];
 	uint32_t any = 0;
 
 #pragma unroll
-	for (int r = 0; r < ST_SLOTS; r++) {
+	for (int r = 0; r < NP; r++) {
 		x[r] = s_logtab[__byte_perm(v[r].y, 0u, 0x4440)];	/* count & 255 */
 		any |= v[r].y;
 	}
@@ -283,7 +283,7 @@ st_score4(const StreamParams &p, const float *s_logtab, const uint2 (&v)[ST_SLOT
 		any &= 0xffffu;
 	if (any >= LOGTAB_N) {
 #pragma unroll
-		for (int r = 0; r < ST_SLOTS; r++) {
+		for (int r = 0; r < NP; r++) {
 			const uint32_t tf = WIDE ? v[r].y : (v[r].y & 0xffffu);
 
 			if (tf >= LOGTAB_N)
@@ -291,7 +291,7 @@ st_score4(const StreamParams &p, const float *s_logtab, const uint2 (&v)[ST_SLOT
 		}
 	}
 #pragma unroll
-	for (int r = 0; r < ST_SLOTS; r++) {
+	for (int r = 0; r < NP; r++) {
 		if (ALGO == NXSB_ALGO_TFIDF) {
 			sc[r] = __fmul_rn(x[r], idf);
 		} else {
@@ -319,8 +319,7 @@ score_stream_kernel(const StreamParams p)
 	unsigned long long *bars = reinterpret_cast<unsigned long long *>(
 	    s_logtab + LOGTAB_N);		/* full[NSTAGES], empty[NSTAGES] */
 	uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 2 * ST_NSTAGES);
-	volatile uint32_t *s_ncand = s_misc;		/* [0] */
-	volatile uint32_t *s_base = s_misc + 1;
+	uint32_t *s_ncand = s_misc;			/* [2], by item parity */
 	unsigned long long *s_theta = reinterpret_cast<unsigned long long *>(s_misc + 2);
 
 	const uint32_t tid = threadIdx.x;
@@ -338,7 +337,7 @@ score_stream_kernel(const StreamParams p)
 			mbar_init(full0 + 8 * s, 1);
 			mbar_init(empty0 + 8 * s, ST_CWARPS);
 		}
-		*s_ncand = 0;
+		s_ncand[0] = s_ncand[1] = 0;
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
@@ -487,7 +486,7 @@ score_stream_kernel(const StreamParams p)
 
 	/* ================= consumer warps ================= */
 	const uint32_t ctid = tid;
-	uint32_t cs = 0, cph = 0;
+	uint32_t cs = 0, cph = 0, par = 0;
 	unsigned long long theta_pref = 0;
 
 	for (;;) {
@@ -502,7 +501,7 @@ score_stream_kernel(const StreamParams p)
 		const uint2 *buf = ring + cs * ST_STAGE_POST;
 		/* Shared address of acc[doc - tile_lo] = accb + 4 * doc. */
 		const uint32_t accb = smem_addr(acc) - 4u * tile_lo;
-		uint32_t mine[ST_SLOTS];
+		const uint32_t my_empty = empty0 + 8 * cs;
 
 		if ((flags & ST_F_FIRST) && ctid == 0)
 			theta_pref = *(volatile unsigned long long *)(p.thr + slot);
@@ -517,7 +516,8 @@ score_stream_kernel(const StreamParams p)
 #pragma unroll
 			for (int r = 0; r < ST_SLOTS; r++)
 				v[r] = buf[ctid + r * ST_NCONS];
-			st_score4<WIDE, ALGO>(p, s_logtab, v, __uint_as_float(hdr.w), sc);
+			st_score<WIDE, ALGO, ST_SLOTS>(p, s_logtab, v, __uint_as_float(hdr.w), sc);
+			/* Documents of one list are distinct: batch the updates. */
 #pragma unroll
 			for (int r = 0; r < ST_SLOTS; r++)
 				a[r] = lds_f32(accb + 4u * v[r].x);
@@ -527,51 +527,52 @@ score_stream_kernel(const StreamParams p)
 		} else {
 			const uint32_t nsub = flags >> ST_F_NSUB_SHIFT;
 
-#pragma unroll
-			for (int r = 0; r < ST_SLOTS; r++)
-				mine[r] = 0xffffffffu;
 			for (uint32_t s = 0; s < nsub; s++) {
 				const StageSub sb = m.sub[s];
-				const uint32_t b0 = sb.b0, nb = (uint32_t)sb.b1 - sb.b0;
+				const uint32_t b0 = sb.b0, b1 = sb.b1, nb = b1 - b0;
 				const float idf = sb.idf;
 
 				/* A new token: the previous token's updates must have landed. */
 				if (s != 0 || !(flags & (ST_F_FIRST | ST_F_CONT)))
 					cons_barrier();
-
-				uint2 v[ST_SLOTS];
-				bool ok[ST_SLOTS];
-				float sc[ST_SLOTS], a[ST_SLOTS];
+				/* Only the slot rows the slice touches, two per round. */
+				for (uint32_t base = b0 & ~(ST_NCONS - 1u); base < b1;
+				    base += 2 * ST_NCONS) {
+					uint2 v[2];
+					bool ok[2];
+					float sc[2], a[2];
 
 #pragma unroll
-				for (int r = 0; r < ST_SLOTS; r++) {
-					const uint32_t i = ctid + r * ST_NCONS;
+					for (int r = 0; r < 2; r++) {
+						const uint32_t i = base + ctid + r * ST_NCONS;
 
-					ok[r] = (i - b0) < nb;
-					/* WIDE gathers doc_len[doc]: keep the dummy in range. */
-					v[r] = make_uint2(tile_lo, 0u);
-					if (ok[r])
-						v[r] = buf[i];
-				}
-				st_score4<WIDE, ALGO>(p, s_logtab, v, idf, sc);
-				/* Documents of one list are distinct: batch the updates. */
-#pragma unroll
-				for (int r = 0; r < ST_SLOTS; r++) {
-					if (ok[r]) {
-						a[r] = lds_f32(accb + 4u * v[r].x);
-						mine[r] = v[r].x - tile_lo;
+						ok[r] = (i - b0) < nb;
+						/* WIDE gathers doc_len[doc]: keep the dummy in range. */
+						v[r] = make_uint2(tile_lo, 0u);
+						if (ok[r])
+							v[r] = buf[i];
 					}
-				}
+					st_score<WIDE, ALGO, 2>(p, s_logtab, v, idf, sc);
 #pragma unroll
-				for (int r = 0; r < ST_SLOTS; r++)
-					if (ok[r])
-						sts_f32(accb + 4u * v[r].x, __fadd_rn(a[r], sc[r]));
+					for (int r = 0; r < 2; r++)
+						if (ok[r])
+							a[r] = lds_f32(accb + 4u * v[r].x);
+#pragma unroll
+					for (int r = 0; r < 2; r++)
+						if (ok[r])
+							sts_f32(accb + 4u * v[r].x, __fadd_rn(a[r], sc[r]));
+				}
 			}
 		}
-		/* Stage consumed (its data and meta are in registers now). */
-		__syncwarp();
-		if ((ctid & 31) == 0)
-			mbar_arrive(empty0 + 8 * cs);
+		/*
+		 * Stage consumed.  A sparse item's epilogue walks the staged
+		 * postings once more, so it releases the stage afterwards.
+		 */
+		if (!(flags & ST_F_SPARSE)) {
+			__syncwarp();
+			if ((ctid & 31) == 0)
+				mbar_arrive(my_empty);
+		}
 		if (++cs == ST_NSTAGES) {
 			cs = 0;
 			cph ^= 1;
@@ -585,31 +586,41 @@ score_stream_kernel(const StreamParams p)
 		cons_barrier();
 		unsigned long long thr_key = *s_theta;
 		const uint32_t k = p.k;
-		bool sorted = false;
+		uint32_t *ncand = s_ncand + par;	/* zero on entry */
 		uint32_t total;
 
+		par ^= 1u;
 		if (flags & ST_F_SPARSE) {
-			/* Sparse item: visit only the documents this thread touched. */
+			/*
+			 * Sparse item: visit only the documents its postings name;
+			 * the first visitor of a document takes its sum and clears it.
+			 */
 			const float ths = thr_key ? __uint_as_float((uint32_t)(thr_key >> 32))
 			    : __uint_as_float(1u);
+			const uint32_t nsub = flags >> ST_F_NSUB_SHIFT;
 
-#pragma unroll
-			for (int r = 0; r < ST_SLOTS; r++) {
-				if (mine[r] != 0xffffffffu) {
-					const float val = atomicExch(acc + mine[r], 0.f);
+			for (uint32_t s = 0; s < nsub; s++) {
+				const uint32_t b1 = m.sub[s].b1;
+
+				for (uint32_t i = m.sub[s].b0 + ctid; i < b1; i += ST_NCONS) {
+					const uint32_t doc = buf[i].x;
+					const float val = atomicExch(acc + (doc - tile_lo), 0.f);
 
 					if (val >= ths) {
-						const unsigned long long key = make_key(val, tile_lo + mine[r]);
+						const unsigned long long key = make_key(val, doc);
 
 						if (key > thr_key) {
 							/* at < item total <= ST_CAND */
-							s_cand[atomicAdd((uint32_t *)s_ncand, 1u)] = key;
+							s_cand[atomicAdd(ncand, 1u)] = key;
 						}
 					}
 				}
 			}
+			__syncwarp();
+			if ((ctid & 31) == 0)
+				mbar_arrive(my_empty);
 			cons_barrier();
-			total = *s_ncand;
+			total = *(volatile uint32_t *)ncand;
 		} else {
 			for (;;) {
 				const float ths = thr_key ? __uint_as_float((uint32_t)(thr_key >> 32))
@@ -621,7 +632,7 @@ score_stream_kernel(const StreamParams p)
 						const unsigned long long key = make_key(val, tile_lo + i);
 
 						if (key > thr_key) {
-							const uint32_t at = atomicAdd((uint32_t *)s_ncand, 1u);
+							const uint32_t at = atomicAdd(ncand, 1u);
 
 							if (at < ST_CAND)
 								s_cand[at] = key;
@@ -631,62 +642,217 @@ score_stream_kernel(const StreamParams p)
 					}
 					val = 0.f;
 				};
-#pragma unroll 4
-				for (uint32_t i4 = ctid; i4 < TILE_DOCS / 4; i4 += ST_NCONS) {
-					float4 q = a4[i4];
+				/*
+				 * Two batches of eight independent 16-byte loads; one
+				 * compare decides for all 32 values of a batch (the
+				 * common case: nothing beats the threshold).
+				 */
+				constexpr int NB = 8;
+				static_assert(TILE_DOCS / 4 == 2 * NB * ST_NCONS, "scan shape");
+#pragma unroll 1
+				for (uint32_t h = 0; h < 2; h++) {
+					float4 q[NB];
+					float mx = 0.f;
 
-					if (q.x >= ths || q.y >= ths || q.z >= ths || q.w >= ths) {
-						visit(q.x, 4 * i4 + 0);
-						visit(q.y, 4 * i4 + 1);
-						visit(q.z, 4 * i4 + 2);
-						visit(q.w, 4 * i4 + 3);
-						a4[i4] = q;
-					} else if (q.x != 0.f || q.y != 0.f || q.z != 0.f || q.w != 0.f) {
-						a4[i4] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+					for (int j = 0; j < NB; j++)
+						q[j] = a4[ctid + (h * NB + j) * ST_NCONS];
+#pragma unroll
+					for (int j = 0; j < NB; j++)
+						mx = fmaxf(fmaxf(mx, fmaxf(q[j].x, q[j].y)),
+						    fmaxf(q[j].z, q[j].w));
+					if (mx >= ths) {
+#pragma unroll
+						for (int j = 0; j < NB; j++) {
+							const uint32_t i4 = ctid + (h * NB + j) * ST_NCONS;
+
+							visit(q[j].x, 4 * i4 + 0);
+							visit(q[j].y, 4 * i4 + 1);
+							visit(q[j].z, 4 * i4 + 2);
+							visit(q[j].w, 4 * i4 + 3);
+							a4[i4] = q[j];
+						}
+					} else {
+#pragma unroll
+						for (int j = 0; j < NB; j++)
+							a4[ctid + (h * NB + j) * ST_NCONS] =
+							    make_float4(0.f, 0.f, 0.f, 0.f);
 					}
 				}
 				cons_barrier();
-				total = *s_ncand;
+				total = *(volatile uint32_t *)ncand;
 				if (total <= ST_CAND)
 					break;
 				/* Overflow: keep the k best, tighten, rescan what is left. */
 				st_sort_desc(s_cand, ST_CAND, ctid);
-				sorted = true;
 				thr_key = s_cand[k - 1];
+				cons_barrier();
 				if (ctid == 0)
-					*s_ncand = k;
+					*ncand = k;
 				cons_barrier();
 			}
 		}
+		/* The other parity's counter was last read an item ago. */
+		if (ctid == 0)
+			s_ncand[par] = 0;
 
 		if (total != 0) {
-			uint32_t n_emit = total;
+			const uint32_t tile = tile_lo >> TILE_SHIFT;
+			const unsigned long long cell = (unsigned long long)slot * p.ntiles + tile;
+			unsigned long long *out = p.cand + cell * k;
 
-			if (total > k) {
-				uint32_t npow2 = 2;
+			if (total <= ST_RANK_MAX) {
+				/*
+				 * Keys are unique: a key's rank is the number of larger
+				 * ones.  No barrier: s_cand is next written after the
+				 * next item's first epilogue barrier.
+				 */
+				if (ctid < total) {
+					const unsigned long long key = s_cand[ctid];
+					uint32_t rank = 0;
+
+					for (uint32_t j = 0; j < total; j++)
+						rank += s_cand[j] > key;
+					if (rank < k)
+						out[rank] = key;
+					if (rank == k - 1)
+						atomicMax(p.thr + slot, key);
+				}
+			} else {
+				uint32_t npow2 = 512;
 
 				while (npow2 < total)
 					npow2 <<= 1;
 				for (uint32_t i = total + ctid; i < npow2; i += ST_NCONS)
 					s_cand[i] = 0;
 				st_sort_desc(s_cand, npow2, ctid);
-				n_emit = k;
-				sorted = true;
+				for (uint32_t i = ctid; i < k; i += ST_NCONS)
+					out[i] = s_cand[i];
+				if (ctid == 0)
+					atomicMax(p.thr + slot, s_cand[k - 1]);
 			}
 			if (ctid == 0)
-				*s_base = atomicAdd(p.cand_count + slot, n_emit);
-			cons_barrier();
-			unsigned long long *out = p.cand +
-			    (unsigned long long)slot * p.cand_cap + *s_base;
-			for (uint32_t i = ctid; i < n_emit; i += ST_NCONS)
-				out[i] = s_cand[i];
-			if (sorted && total >= k && ctid == 0)
-				atomicMax(p.thr + slot, s_cand[k - 1]);
-			cons_barrier();
-			if (ctid == 0)
-				*s_ncand = 0;
+				p.tile_count[cell] = total < k ? total : k;
 		}
 	}
+}
+
+/*
+ * Final per-query top-k from the per-tile candidate cells the stream kernel
+ * wrote: cand[slot][tile][0 .. tile_count[slot][tile]).  One CTA per query;
+ * same selection as finalize_topk_kernel (keys are unique).
+ */
+__global__ void __launch_bounds__(256)
+finalize_cells_kernel(const unsigned long long *__restrict__ cand,
+    const uint32_t *__restrict__ tile_count, uint32_t ntiles,
+    const uint32_t *__restrict__ qlist, uint32_t k,
+    const unsigned long long *__restrict__ doc_ids,
+    Rec *__restrict__ recs, uint32_t *__restrict__ counts)
+{
+	__shared__ unsigned long long s_keys[SORT_CAP];
+	__shared__ uint32_t s_hist[256];
+	__shared__ uint32_t s_want, s_n, s_total;
+	__shared__ unsigned long long s_prefix;
+
+	const uint32_t slot = blockIdx.x, tid = threadIdx.x;
+	const uint32_t q = qlist[slot];
+	const unsigned long long *in = cand + (unsigned long long)slot * ntiles * k;
+	const uint32_t *cnt = tile_count + (size_t)slot * ntiles;
+	const uint32_t cells = ntiles * k;
+
+	if (tid == 0) {
+		s_total = 0;
+		s_n = 0;
+	}
+	__syncthreads();
+	{
+		uint32_t mine = 0;
+
+		for (uint32_t t = tid; t < ntiles; t += blockDim.x)
+			mine += cnt[t];
+		if (mine)
+			atomicAdd(&s_total, mine);
+	}
+	__syncthreads();
+	const uint32_t n = s_total;
+	uint32_t m;		// keys to sort
+
+	if (n <= SORT_CAP) {
+		for (uint32_t i = tid; i < cells; i += blockDim.x)
+			if (i % k < cnt[i / k])
+				s_keys[atomicAdd(&s_n, 1u)] = in[i];
+		__syncthreads();
+		m = n;
+	} else {
+		/* n > SORT_CAP >= 2k: radix-select the k-th largest key. */
+		if (tid == 0) {
+			s_prefix = 0;
+			s_want = k;
+		}
+		for (int sh = 56; sh >= 0; sh -= 8) {
+			if (tid < 256)
+				s_hist[tid] = 0;
+			__syncthreads();
+			const unsigned long long prefix = s_prefix;
+			for (uint32_t i = tid; i < cells; i += blockDim.x) {
+				if (i % k >= cnt[i / k])
+					continue;
+				const unsigned long long key = in[i];
+				if (sh == 56 || (key >> (sh + 8)) == prefix)
+					atomicAdd(&s_hist[(uint32_t)(key >> sh) & 255u], 1u);
+			}
+			__syncthreads();
+			if (tid == 0) {
+				uint32_t want = s_want, cum = 0;
+				int b = 255;
+
+				for (; b > 0; b--) {
+					if (cum + s_hist[b] >= want)
+						break;
+					cum += s_hist[b];
+				}
+				s_want = want - cum;
+				s_prefix = (prefix << 8) | (unsigned)b;
+			}
+			__syncthreads();
+		}
+		const unsigned long long kth = s_prefix;
+		for (uint32_t i = tid; i < cells; i += blockDim.x) {
+			if (i % k >= cnt[i / k])
+				continue;
+			const unsigned long long key = in[i];
+			if (key >= kth)
+				s_keys[atomicAdd(&s_n, 1u)] = key;
+		}
+		__syncthreads();
+		m = s_n;	// == k
+	}
+
+	uint32_t npow2 = 2;
+	while (npow2 < m)
+		npow2 <<= 1;
+	for (uint32_t i = m + tid; i < npow2; i += blockDim.x)
+		s_keys[i] = 0;
+	bitonic_sort_desc(s_keys, npow2);
+
+	const uint32_t cn = m < k ? m : k;
+	Rec *out = recs + (size_t)q * k;
+	for (uint32_t r = tid; r < k; r += blockDim.x) {
+		Rec rec;
+		if (r < cn) {
+			const unsigned long long key = s_keys[r];
+			rec.doc_id = doc_ids[(uint32_t)key];
+			rec.score = __uint_as_float((uint32_t)(key >> 32));
+			rec.valid = 1;
+		} else {
+			rec.doc_id = 0;
+			rec.score = 0.f;
+			rec.valid = 0;
+		}
+		out[r] = rec;
+	}
+	if (tid == 0)
+		counts[q] = cn;
 }
 
 #endif
