@@ -2,12 +2,17 @@
 from __future__ import annotations
 
 import ctypes
+import os
 from pathlib import Path
 
 _LIB = None
 
 
 def library_path() -> Path:
+    # NXSB_LIBRARY: development switch for A/B-ing kernel build variants.
+    override = os.environ.get("NXSB_LIBRARY")
+    if override:
+        return Path(override)
     return Path(__file__).resolve().parent / "lib" / "libnxsearch.so"
 
 

@@ -154,6 +154,7 @@ struct nxsb_engine {
 	size_t		cub_tmp_bytes = 0;
 	unsigned char *	d_plan = nullptr;		// planned work items (stream kernel)
 	size_t		plan_bytes = 0;
+	unsigned long long *d_prof = nullptr;		// -DST_PROF phase counters
 	uint32_t *	d_tile_cnt = nullptr;		// candidates per (query, tile)
 	size_t		tile_cnt_bytes = 0;
 	bool		force_v2 = false;		// NXSB_KERNEL=v2: A/B against tiles.cuh
@@ -237,6 +238,17 @@ nxsb_engine_errmsg(const nxsb_engine_t *e)
 	return e ? e->err : g_last_error;
 }
 
+#ifdef ST_PROF
+extern "C" __attribute__((visibility("default"))) int
+nxsb_engine_prof(nxsb_engine_t *e, unsigned long long *out)
+{
+	cudaStreamSynchronize(e->stream);
+	cudaMemcpy(out, e->d_prof, 32 * 8, cudaMemcpyDeviceToHost);
+	cudaMemset(e->d_prof, 0, 32 * 8);
+	return 0;
+}
+#endif
+
 extern "C" uint64_t
 nxsb_engine_launch_count(const nxsb_engine_t *e)
 {
@@ -276,6 +288,10 @@ nxsb_engine_create(int device)
 	}
 	e->stream = e->own_stream;
 	e->n_sms = prop.multiProcessorCount;
+#ifdef ST_PROF
+	dev_alloc(&e->d_prof, 32);
+	cudaMemset(e->d_prof, 0, 32 * 8);
+#endif
 	{
 		/* Development switch: score with the older tiles.cuh kernel. */
 		const char *kv = getenv("NXSB_KERNEL");
@@ -928,6 +944,7 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
 	p.K0 = e->K0;
 	p.K1 = e->K1;
 	(void)cand_cap;		/* = ntiles * k_tile: one k-cell per (query, tile) */
+	p.prof = e->d_prof;
 
 	auto kern = B.algo == NXSB_ALGO_BM25
 	    ? (e->wide ? score_stream_kernel<true, NXSB_ALGO_BM25>

@@ -42,16 +42,39 @@
 #ifndef NXSB_GPU_STREAM_CUH
 #define NXSB_GPU_STREAM_CUH
 
+#ifndef ST_CWARPS
 #define ST_CWARPS	8			/* consumer warps */
+#endif
 #define ST_NCONS	(32 * ST_CWARPS)	/* consumer threads */
 #define ST_THREADS	(ST_NCONS + 32)		/* + the producer warp */
-#define ST_SLOTS	6			/* postings per thread per stage */
+#ifndef ST_SLOTS
+#define ST_SLOTS	8			/* postings per thread per stage */
+#endif
 #define ST_STAGE_POST	(ST_SLOTS * ST_NCONS)	/* postings per stage */
-#define ST_NSTAGES	3
+#ifndef ST_NSTAGES
+#define ST_NSTAGES	2
+#endif
 #define ST_MAXSUB	NXSB_MAX_QUERY_TOKENS	/* slices per stage */
-#define ST_CAND		1024u			/* candidate buffer (>= one stage) */
+#ifndef ST_CAND
+#define ST_CAND		1024u			/* candidate buffer */
+#endif
 #define ST_K_MAX	128u			/* limit served by this kernel */
 #define ST_RANK_MAX	256u			/* candidates ranked by counting */
+
+/*
+ * -DST_PROF: per-phase cycle counters of the consumer warps (lane 0) and the
+ * producer, summed into StreamParams::prof.  Development only.
+ */
+#ifdef ST_PROF
+#define PROF_DECL	long long prof_t = clock64(); long long prof_acc[12] = { 0 }
+#define PROF(i)		do { const long long _t = clock64(); prof_acc[i] += _t - prof_t; prof_t = _t; } while (0)
+#define PROF_FLUSH(base) do { if ((threadIdx.x & 31) == 0) for (int _i = 0; _i < 12; _i++) \
+	if (prof_acc[_i]) atomicAdd(p.prof + (base) + _i, (unsigned long long)prof_acc[_i]); } while (0)
+#else
+#define PROF_DECL	do { } while (0)
+#define PROF(i)		do { } while (0)
+#define PROF_FLUSH(b)	do { } while (0)
+#endif
 
 #define ST_F_FIRST	1u	/* first stage of an item */
 #define ST_F_LAST	2u	/* last stage of an item */
@@ -99,6 +122,7 @@ struct StreamParams {
 	const float *		logtab;
 	const uint32_t *	doc_len;	/* WIDE */
 	float			K0, K1;
+	unsigned long long *	prof;		/* ST_PROF counters or NULL */
 };
 
 #define ST_SMEM_BYTES	(TILE_DOCS * 4 + ST_NSTAGES * ST_STAGE_POST * 8 +	\
@@ -366,8 +390,10 @@ score_stream_kernel(const StreamParams p)
 			return __ldg(reinterpret_cast<const uint2 *>(
 			    p.plan + (unsigned long long)it * p.plan_stride));
 		};
-		auto load_tok = [&](uint32_t it, uint32_t ntok) -> uint4 {
-			if (it >= n_items || lane >= ntok)
+		/* Independent of the header load: every lane a record has room for. */
+		const uint32_t rec_toks = p.plan_stride / 16u - 1u;
+		auto load_tok = [&](uint32_t it, uint32_t) -> uint4 {
+			if (it >= n_items || lane >= rec_toks)
 				return make_uint4(0u, 0u, 0u, 0u);
 			return __ldg(reinterpret_cast<const uint4 *>(
 			    p.plan + (unsigned long long)it * p.plan_stride + 16) + lane);
@@ -405,8 +431,11 @@ score_stream_kernel(const StreamParams p)
 				pph ^= 1;
 			}
 		};
+		PROF_DECL;
 		auto acquire = [&]() {
+			PROF(0);		/* producer: everything else */
 			mbar_wait(empty0 + 8 * ps, pph);
+			PROF(1);		/* producer: wait for an empty stage */
 			open = true;
 			used = nsub = bytes = flags = 0;
 		};
@@ -481,6 +510,7 @@ score_stream_kernel(const StreamParams p)
 		acquire();
 		flags = ST_F_END;
 		commit(0u, 0u, 0u);
+		PROF_FLUSH(12);
 		return;
 	}
 
@@ -489,14 +519,19 @@ score_stream_kernel(const StreamParams p)
 	uint32_t cs = 0, cph = 0, par = 0;
 	unsigned long long theta_pref = 0;
 
+	PROF_DECL;
 	for (;;) {
+		PROF(0);			/* other */
 		mbar_wait(full0 + 8 * cs, cph);
+		PROF(1);			/* wait for a full stage */
 		const StageMeta &m = meta[cs];
 		const uint4 hdr = *reinterpret_cast<const uint4 *>(&m);
 		const uint32_t flags = hdr.x;
 
-		if (flags & ST_F_END)
+		if (flags & ST_F_END) {
+			PROF_FLUSH(0);
 			break;
+		}
 		const uint32_t slot = hdr.y, tile_lo = hdr.z;
 		const uint2 *buf = ring + cs * ST_STAGE_POST;
 		/* Shared address of acc[doc - tile_lo] = accb + 4 * doc. */
@@ -513,6 +548,7 @@ score_stream_kernel(const StreamParams p)
 
 			if (!(flags & (ST_F_FIRST | ST_F_CONT)))
 				cons_barrier();
+			PROF(2);		/* token barrier */
 #pragma unroll
 			for (int r = 0; r < ST_SLOTS; r++)
 				v[r] = buf[ctid + r * ST_NCONS];
@@ -524,6 +560,7 @@ score_stream_kernel(const StreamParams p)
 #pragma unroll
 			for (int r = 0; r < ST_SLOTS; r++)
 				sts_f32(accb + 4u * v[r].x, __fadd_rn(a[r], sc[r]));
+			PROF(3);		/* full stage */
 		} else {
 			const uint32_t nsub = flags >> ST_F_NSUB_SHIFT;
 
@@ -533,8 +570,10 @@ score_stream_kernel(const StreamParams p)
 				const float idf = sb.idf;
 
 				/* A new token: the previous token's updates must have landed. */
+				PROF(4);	/* partial stage */
 				if (s != 0 || !(flags & (ST_F_FIRST | ST_F_CONT)))
 					cons_barrier();
+				PROF(2);
 				/* Only the slot rows the slice touches, two per round. */
 				for (uint32_t base = b0 & ~(ST_NCONS - 1u); base < b1;
 				    base += 2 * ST_NCONS) {
@@ -577,6 +616,7 @@ score_stream_kernel(const StreamParams p)
 			cs = 0;
 			cph ^= 1;
 		}
+		PROF(4);
 		if (!(flags & ST_F_LAST))
 			continue;
 
@@ -584,6 +624,7 @@ score_stream_kernel(const StreamParams p)
 		if (ctid == 0)
 			*s_theta = theta_pref;
 		cons_barrier();
+		PROF(5);			/* barrier before the epilogue */
 		unsigned long long thr_key = *s_theta;
 		const uint32_t k = p.k;
 		uint32_t *ncand = s_ncand + par;	/* zero on entry */
@@ -619,7 +660,9 @@ score_stream_kernel(const StreamParams p)
 			__syncwarp();
 			if ((ctid & 31) == 0)
 				mbar_arrive(my_empty);
+			PROF(6);		/* sparse collect */
 			cons_barrier();
+			PROF(8);		/* barrier after collect / scan */
 			total = *(volatile uint32_t *)ncand;
 		} else {
 			for (;;) {
@@ -648,15 +691,19 @@ score_stream_kernel(const StreamParams p)
 				 * common case: nothing beats the threshold).
 				 */
 				constexpr int NB = 8;
-				static_assert(TILE_DOCS / 4 == 2 * NB * ST_NCONS, "scan shape");
+				constexpr uint32_t N4 = TILE_DOCS / 4;
+				constexpr bool EXACT = N4 % (NB * ST_NCONS) == 0;
 #pragma unroll 1
-				for (uint32_t h = 0; h < 2; h++) {
+				for (uint32_t base = ctid; base < N4; base += NB * ST_NCONS) {
 					float4 q[NB];
 					float mx = 0.f;
 
 #pragma unroll
-					for (int j = 0; j < NB; j++)
-						q[j] = a4[ctid + (h * NB + j) * ST_NCONS];
+					for (int j = 0; j < NB; j++) {
+						q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+						if (EXACT || base + j * ST_NCONS < N4)
+							q[j] = a4[base + j * ST_NCONS];
+					}
 #pragma unroll
 					for (int j = 0; j < NB; j++)
 						mx = fmaxf(fmaxf(mx, fmaxf(q[j].x, q[j].y)),
@@ -664,22 +711,27 @@ score_stream_kernel(const StreamParams p)
 					if (mx >= ths) {
 #pragma unroll
 						for (int j = 0; j < NB; j++) {
-							const uint32_t i4 = ctid + (h * NB + j) * ST_NCONS;
+							const uint32_t i4 = base + j * ST_NCONS;
 
-							visit(q[j].x, 4 * i4 + 0);
-							visit(q[j].y, 4 * i4 + 1);
-							visit(q[j].z, 4 * i4 + 2);
-							visit(q[j].w, 4 * i4 + 3);
-							a4[i4] = q[j];
+							if (EXACT || i4 < N4) {
+								visit(q[j].x, 4 * i4 + 0);
+								visit(q[j].y, 4 * i4 + 1);
+								visit(q[j].z, 4 * i4 + 2);
+								visit(q[j].w, 4 * i4 + 3);
+								a4[i4] = q[j];
+							}
 						}
 					} else {
 #pragma unroll
 						for (int j = 0; j < NB; j++)
-							a4[ctid + (h * NB + j) * ST_NCONS] =
-							    make_float4(0.f, 0.f, 0.f, 0.f);
+							if (EXACT || base + j * ST_NCONS < N4)
+								a4[base + j * ST_NCONS] =
+								    make_float4(0.f, 0.f, 0.f, 0.f);
 					}
 				}
+				PROF(7);	/* scan + zero */
 				cons_barrier();
+				PROF(8);
 				total = *(volatile uint32_t *)ncand;
 				if (total <= ST_CAND)
 					break;
@@ -734,6 +786,7 @@ score_stream_kernel(const StreamParams p)
 			if (ctid == 0)
 				p.tile_count[cell] = total < k ? total : k;
 		}
+		PROF(9);			/* rank + emit */
 	}
 }
 
