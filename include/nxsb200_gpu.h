@@ -48,7 +48,9 @@ enum {
 
 #define NXSB_MAX_QUERY_TOKENS	32	/* resolved tokens per query */
 #define NXSB_MAX_QUERY_PROG	128	/* postfix program length */
+#ifndef NXSB_TILE_DOCS
 #define NXSB_TILE_DOCS		16384	/* documents per scoring tile */
+#endif
 
 /* Number of CUDA devices visible; 0 when there is no driver / device. */
 int		nxsb_gpu_device_count(void);

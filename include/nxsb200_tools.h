@@ -132,6 +132,16 @@ int		nxsb_query_compile(const char *query, char *tokens_buf,
 		    size_t buf_len, uint32_t *n_tokens, int32_t *prog,
 		    uint32_t prog_cap, uint32_t *n_prog);
 
+/*
+ * Drain n responses of a batch the way a C caller would -- with the public
+ * iterator nxs_resp_iter_reset() / nxs_resp_iter_result() (ref
+ * src/core/results.c:222-247) -- into flat arrays: counts[i] results of
+ * response i at ids/scores[i * stride ...].  NULL responses count as empty.
+ * Returns the total number of results copied.  (Opaque pointers: nxs_resp_t.)
+ */
+uint64_t	nxsb_resp_collect(void *const *resps, size_t n, uint32_t stride,
+		    uint32_t *counts, uint64_t *ids, float *scores);
+
 #pragma GCC visibility pop
 
 #ifdef __cplusplus

@@ -49,6 +49,9 @@ def bind(lib=None):
     if hasattr(lib, "nxs_index_search_batch"):
         lib.nxs_index_search_batch.restype = C.c_int
         lib.nxs_index_search_batch.argtypes = [vp, vp, C.POINTER(cp), sz, C.POINTER(vp)]
+    if hasattr(lib, "nxsb_resp_collect"):
+        lib.nxsb_resp_collect.restype = u64
+        lib.nxsb_resp_collect.argtypes = [C.POINTER(vp), sz, C.c_uint32, vp, vp, vp]
     if hasattr(lib, "nxs_luafilter_load"):
         lib.nxs_luafilter_load.restype = C.c_int
         lib.nxs_luafilter_load.argtypes = [vp, cp, cp]
@@ -172,6 +175,33 @@ class Index:
             res.append(r.results())
             r.release()
         return res
+
+    def search_batch_arrays(self, queries, limit: int, **params):
+        """nxs_index_search_batch, results drained in C through the public
+        iterator (nxsb_resp_collect) into numpy arrays: (counts[n],
+        ids[n, limit], scores[n, limit]).  `queries` may be a prepared
+        (c_char_p * n) array."""
+        import numpy as np
+
+        if isinstance(queries, C.Array):
+            arr, n = queries, len(queries)
+        else:
+            qs = [q.encode() if isinstance(q, str) else q for q in queries]
+            arr, n = (C.c_char_p * len(qs))(*qs), len(qs)
+        out = (C.c_void_p * n)()
+        p = Params(self._lib, limit=limit, **params)
+        rc = self._lib.nxs_index_search_batch(self.h, p.h, arr, n, out)
+        p.release()
+        if rc != 0:
+            self.nxs.raise_error()
+        counts = np.zeros(n, dtype=np.uint32)
+        ids = np.zeros((n, limit), dtype=np.uint64)
+        scores = np.zeros((n, limit), dtype=np.float32)
+        self._lib.nxsb_resp_collect(out, n, limit, counts.ctypes.data, ids.ctypes.data, scores.ctypes.data)
+        for h in out:
+            if h:
+                self._lib.nxs_resp_release(h)
+        return counts, ids, scores
 
     def close(self) -> None:
         if self.h:

@@ -26,7 +26,9 @@
 #include "nxsb200_gpu.h"
 
 #define TILE_DOCS	NXSB_TILE_DOCS		// 16384
+#ifndef TILE_SHIFT
 #define TILE_SHIFT	14
+#endif
 #define TILE_WORDS	(TILE_DOCS / 32)
 #define DF_LONG		2048u			// permanent skip row threshold
 #define LOGTAB_N	256			// (float)log(c + 1) for c < 256

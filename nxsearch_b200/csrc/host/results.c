@@ -15,6 +15,7 @@
 #include <string.h>
 
 #include "nxs_impl.h"
+#include "nxsb200_tools.h"
 
 struct nxs_resp {
 	uint32_t	count;
@@ -98,4 +99,27 @@ nxs_resp_tojson(nxs_resp_t *r, size_t *len)
 	if (len)
 		*len = n;
 	return buf;
+}
+
+/* include/nxsb200_tools.h: drain a batch of responses through the iterator. */
+NXS_API uint64_t
+nxsb_resp_collect(void *const *resps, size_t n, uint32_t stride,
+    uint32_t *counts, uint64_t *ids, float *scores)
+{
+	uint64_t total = 0;
+
+	for (size_t i = 0; i < n; i++) {
+		nxs_resp_t *r = resps[i];
+		uint32_t c = 0;
+
+		if (r) {
+			nxs_resp_iter_reset(r);
+			while (c < stride && nxs_resp_iter_result(r,
+			    &ids[i * (size_t)stride + c], &scores[i * (size_t)stride + c]))
+				c++;
+		}
+		counts[i] = c;
+		total += c;
+	}
+	return total;
 }

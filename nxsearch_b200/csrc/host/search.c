@@ -10,10 +10,13 @@
  */
 #define _GNU_SOURCE
 #include <limits.h>
+#include <pthread.h>
+#include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <strings.h>
+#include <unistd.h>
 
 #include "index.h"
 #include "query.h"
@@ -30,8 +33,16 @@ typedef struct {
 	tokenset_t *	tokens;
 	int32_t *	slot_map;	/* token slot -> compacted slot, -1 = trimmed */
 	uint32_t	n_resolved;
+	uint32_t	n_miss;		/* tokens without an exact term */
 	bool		failed;
+	/* Error of this query, reported in query order after the workers join. */
+	nxs_err_t	err_code;
+	char *		err_msg;
 } prepared_t;
+
+/* Queries per worker below which threads are not worth starting. */
+#define PREP_MIN_PER_THREAD	128
+#define PREP_MAX_THREADS	16
 
 static int
 get_search_params(nxs_index_t *idx, nxs_params_t *params, search_params_t *sp)
@@ -133,6 +144,99 @@ prepared_release(prepared_t *pq)
 	qtree_free(&pq->tree);
 	tokenset_destroy(pq->tokens);
 	free(pq->slot_map);
+	free(pq->err_msg);
+}
+
+static void
+prep_fail(prepared_t *pq, nxs_err_t code, const char *fmt, ...)
+{
+	va_list ap;
+
+	pq->failed = true;
+	pq->err_code = code;
+	va_start(ap, fmt);
+	if (vasprintf(&pq->err_msg, fmt, ap) == -1)
+		pq->err_msg = NULL;
+	va_end(ap);
+}
+
+/* Steps 1-3 of one query: parse, query_prepare, tokenset_resolve (exact). */
+static void
+prepare_one(nxs_index_t *idx, const search_params_t *sp, const char *query,
+    prepared_t *pq)
+{
+	qtree_parse(&pq->tree, query);
+	if (pq->tree.error) {
+		prep_fail(pq, NXS_ERR_INVALID, "query failed with %s",
+		    pq->tree.errmsg ? pq->tree.errmsg : "out of memory");
+		return;
+	}
+	if (prepare_query(idx->fp, pq) == -1) {
+		prep_fail(pq, NXS_ERR_FATAL, "query_prepare() failed");
+		return;
+	}
+	/* tokenset_resolve (tokenizer.c:160-199): exact lookups. */
+	for (uint32_t j = 0; j < pq->tokens->count; j++) {
+		token_t *t = &pq->tokens->list[j];
+
+		t->term_id = idx_term_lookup(idx, t->str, t->len);
+		if (!t->term_id && sp->fuzzymatch)
+			pq->n_miss++;
+	}
+}
+
+typedef struct {
+	nxs_index_t *		idx;
+	const search_params_t *	sp;
+	const char *const *	queries;
+	prepared_t *		pq;
+	size_t			lo, hi;
+} prep_job_t;
+
+static void *
+prepare_worker(void *arg)
+{
+	prep_job_t *j = arg;
+
+	for (size_t i = j->lo; i < j->hi; i++)
+		prepare_one(j->idx, j->sp, j->queries[i], &j->pq[i]);
+	return NULL;
+}
+
+static void
+prepare_all(nxs_index_t *idx, const search_params_t *sp,
+    const char *const *queries, size_t n, prepared_t *pq)
+{
+	pthread_t tid[PREP_MAX_THREADS];
+	prep_job_t job[PREP_MAX_THREADS];
+	long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+	size_t nt = n / PREP_MIN_PER_THREAD;
+
+	if (ncpu < 1)
+		ncpu = 1;
+	if (nt > (size_t)ncpu)
+		nt = ncpu;
+	if (nt > PREP_MAX_THREADS)
+		nt = PREP_MAX_THREADS;
+	if (nt < 2) {
+		prep_job_t all = { idx, sp, queries, pq, 0, n };
+
+		prepare_worker(&all);
+		return;
+	}
+	bool started[PREP_MAX_THREADS] = { false };
+
+	for (size_t t = 0; t < nt; t++) {
+		job[t] = (prep_job_t){ idx, sp, queries, pq, n * t / nt, n * (t + 1) / nt };
+		/* The caller takes the last share, and any share whose thread fails to start. */
+		if (t + 1 < nt)
+			started[t] = pthread_create(&tid[t], NULL, prepare_worker, &job[t]) == 0;
+		if (!started[t])
+			prepare_worker(&job[t]);
+	}
+	for (size_t t = 0; t < nt; t++)
+		if (started[t])
+			pthread_join(tid[t], NULL);
 }
 
 NXS_API int
@@ -168,28 +272,18 @@ nxs_index_search_batch(nxs_index_t *idx, nxs_params_t *params,
 	if ((pq = calloc(n ? n : 1, sizeof(prepared_t))) == NULL)
 		goto out;
 
-	/* Parse and tokenize every query. */
+	/*
+	 * Parse, tokenize and resolve every query (exact lookups).  The
+	 * reference is single-threaded; a batch is independent read-only work
+	 * per query, so it is spread over the host cores here.
+	 */
+	prepare_all(idx, &sp, queries, n, pq);
 	for (size_t i = 0; i < n; i++) {
-		qtree_parse(&pq[i].tree, queries[i]);
-		if (pq[i].tree.error) {
-			nxs_set_error(nxs, NXS_ERR_INVALID, "query failed with %s",
-			    pq[i].tree.errmsg ? pq[i].tree.errmsg : "out of memory");
-			pq[i].failed = true;
-			continue;
+		if (pq[i].failed) {
+			nxs_set_error(nxs, pq[i].err_code, "%s",
+			    pq[i].err_msg ? pq[i].err_msg : "out of memory");
 		}
-		if (prepare_query(idx->fp, &pq[i]) == -1) {
-			nxs_set_error(nxs, NXS_ERR_FATAL, "query_prepare() failed");
-			pq[i].failed = true;
-			continue;
-		}
-		/* tokenset_resolve (tokenizer.c:160-199): exact lookups. */
-		for (uint32_t j = 0; j < pq[i].tokens->count; j++) {
-			token_t *t = &pq[i].tokens->list[j];
-
-			t->term_id = idx_term_lookup(idx, t->str, t->len);
-			if (!t->term_id && sp.fuzzymatch)
-				n_miss++;
-		}
+		n_miss += pq[i].n_miss;
 	}
 
 	/* One batched fuzzy scan for every token that missed. */
