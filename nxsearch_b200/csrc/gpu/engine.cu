@@ -156,6 +156,8 @@ struct nxsb_engine {
 	size_t		plan_bytes = 0;
 	unsigned long long *d_prof = nullptr;		// -DST_PROF phase counters
 	uint32_t *	d_tile_cnt = nullptr;		// candidates per (query, tile)
+	uint32_t *	d_tt = nullptr;			// truth tables of boolean queries
+	size_t		tt_bytes = 0;
 	size_t		tile_cnt_bytes = 0;
 	bool		force_v2 = false;		// NXSB_KERNEL=v2: A/B against tiles.cuh
 
@@ -357,6 +359,7 @@ nxsb_engine_destroy(nxsb_engine_t *e)
 	dev_free(e->d_sort_tmp);
 	dev_free(e->d_plan);
 	dev_free(e->d_tile_cnt);
+	dev_free(e->d_tt);
 	if (e->d_cub_tmp)
 		cudaFree(e->d_cub_tmp);
 	dev_free(e->d_logtab);
@@ -905,6 +908,7 @@ launch_tiles(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
  * The TMA-fed scorer (stream.cuh): plan the items, then one persistent
  * launch, two CTAs per SM.
  */
+template <bool LOGIC>
 static int
 launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
     uint32_t k_tile, uint64_t cand_cap)
@@ -946,12 +950,26 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
 	(void)cand_cap;		/* = ntiles * k_tile: one k-cell per (query, tile) */
 	p.prof = e->d_prof;
 
+	if (LOGIC) {
+		/* Truth tables of the boolean programs: 8 words per query. */
+		const size_t want_tt = (size_t)n_q * 8 * 4;
+
+		if (want_tt > e->tt_bytes) {
+			dev_free(e->d_tt);
+			e->tt_bytes = 0;
+			if (dev_alloc(&e->d_tt, (size_t)n_q * 8 * 2) != cudaSuccess)
+				return fail(e, "truth table allocation failed");
+			e->tt_bytes = want_tt * 2;
+		}
+	}
+	p.tt = e->d_tt;
+
 	auto kern = B.algo == NXSB_ALGO_BM25
-	    ? (e->wide ? score_stream_kernel<true, NXSB_ALGO_BM25>
-	       : score_stream_kernel<false, NXSB_ALGO_BM25>)
-	    : (e->wide ? score_stream_kernel<true, NXSB_ALGO_TFIDF>
-	       : score_stream_kernel<false, NXSB_ALGO_TFIDF>);
-	const size_t smem = ST_SMEM_BYTES;
+	    ? (e->wide ? score_stream_kernel<LOGIC, true, NXSB_ALGO_BM25>
+	       : score_stream_kernel<LOGIC, false, NXSB_ALGO_BM25>)
+	    : (e->wide ? score_stream_kernel<LOGIC, true, NXSB_ALGO_TFIDF>
+	       : score_stream_kernel<LOGIC, false, NXSB_ALGO_TFIDF>);
+	const size_t smem = StCfg<LOGIC>::SMEM;
 	int per_sm = 0;
 
 	CK(e, cudaFuncSetAttribute(kern,
@@ -968,6 +986,11 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
 	mark(e, "plan");
 	plan_items_kernel<<<(unsigned)((items + 255) / 256), 256, 0, e->stream>>>(
 	    B.d_queries, d_qlist, B.d_toks, n_q, e->ntiles, stride, e->d_plan);
+	if (LOGIC) {
+		truth_tables_kernel<<<n_q, 256, 0, e->stream>>>(B.d_queries, d_qlist,
+		    B.d_prog, e->d_tt);
+		e->launches++;
+	}
 	mark(e, "score_tiles");
 	kern<<<grid, ST_THREADS, smem, e->stream>>>(p);
 	e->launches += 2;
@@ -1003,7 +1026,9 @@ run_list(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list,
 		e->cand_bytes = want;
 	}
 	uint32_t chunk = (uint32_t)std::min<size_t>(n_list, e->cand_bytes / per_q);
-	const bool stream = !LOGIC && k <= ST_K_MAX && !e->force_v2;
+	/* Boolean queries fit the stream kernel when a byte holds their tokens. */
+	const bool stream = k <= ST_K_MAX && !e->force_v2 &&
+	    (!LOGIC || B.max_tokens <= ST_LOGIC_TOKENS);
 
 	if (stream) {
 		/* Item numbers are 32-bit; keep the plan arena under 1 GiB. */
@@ -1017,7 +1042,7 @@ run_list(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list,
 	for (uint32_t q0 = 0; q0 < n_list; q0 += chunk) {
 		const uint32_t n = std::min(chunk, n_list - q0);
 
-		if ((stream ? launch_stream(e, B, d_qlist + q0, n, k_tile, cand_cap)
+		if ((stream ? launch_stream<LOGIC>(e, B, d_qlist + q0, n, k_tile, cand_cap)
 		    : launch_tiles<LOGIC>(e, B, d_qlist + q0, n, k_tile, cand_cap)) == -1)
 			return -1;
 		mark(e, "topk");

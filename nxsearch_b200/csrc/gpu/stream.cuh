@@ -58,6 +58,9 @@
 #ifndef ST_CAND
 #define ST_CAND		1024u			/* candidate buffer */
 #endif
+#define ST_SLOTS_LOGIC	6			/* boolean queries: room for the  */
+#define ST_CAND_LOGIC	512u			/* membership bytes (16 KB)       */
+#define ST_LOGIC_TOKENS	8u			/* tokens a membership byte holds */
 #define ST_K_MAX	128u			/* limit served by this kernel */
 #define ST_RANK_MAX	256u			/* candidates ranked by counting */
 
@@ -82,7 +85,9 @@
 #define ST_F_END	8u	/* no more work */
 #define ST_F_FULL	16u	/* one slice filling every slot of the stage */
 #define ST_F_SPARSE	32u	/* whole item in this stage, <= ST_CAND postings */
-#define ST_F_NSUB_SHIFT	8
+#define ST_F_NSUB_SHIFT	8	/* 6 bits */
+#define ST_F_TOK_SHIFT	16	/* token slot of slice 0 (boolean queries) */
+#define ST_SUB_TOK_SHIFT 12	/* StageSub::b0 = first slot | token slot << 12 */
 
 /* One planned work item: header + one entry per non-empty token slice. */
 struct PlanHdr {
@@ -91,15 +96,16 @@ struct PlanHdr {
 	uint32_t	pad[2];
 };
 struct PlanTok {
-	unsigned long long g0;		/* absolute index of the first posting */
+	unsigned long long g0;		/* first posting (absolute) | token slot << 56 */
 	uint32_t	n;
 	float		idf;
 };
 static_assert(sizeof(PlanHdr) == 16 && sizeof(PlanTok) == 16, "plan record");
-static_assert(2 * ST_K_MAX <= ST_CAND, "overflow rounds must make progress");
+static_assert(2 * ST_K_MAX <= ST_CAND && 2 * ST_K_MAX <= ST_CAND_LOGIC,
+    "overflow rounds must make progress");
 
 struct StageSub {		/* a slice of one token inside a stage */
-	uint16_t	b0, b1;		/* buffer slots [b0, b1) */
+	uint16_t	b0, b1;		/* buffer slots [b0 & 0xfff, b1) */
 	float		idf;
 };
 struct StageMeta {
@@ -122,12 +128,27 @@ struct StreamParams {
 	const float *		logtab;
 	const uint32_t *	doc_len;	/* WIDE */
 	float			K0, K1;
+	const uint32_t *	tt;		/* [n_q][8] truth tables (boolean) */
 	unsigned long long *	prof;		/* ST_PROF counters or NULL */
 };
 
-#define ST_SMEM_BYTES	(TILE_DOCS * 4 + ST_NSTAGES * ST_STAGE_POST * 8 +	\
-    ST_CAND * 8 + ST_NSTAGES * sizeof(StageMeta) + LOGTAB_N * 4 +		\
-    2 * ST_NSTAGES * 8 + 64)
+/*
+ * Per-variant shapes.  Boolean queries keep one membership byte per document
+ * (bit j = "token slot j has a posting here") next to the accumulator and pay
+ * for it with a smaller ring and candidate buffer.
+ */
+template <bool LOGIC>
+struct StCfg {
+	static constexpr uint32_t SLOTS = LOGIC ? ST_SLOTS_LOGIC : ST_SLOTS;
+	static constexpr uint32_t STAGE_POST = SLOTS * ST_NCONS;
+	static constexpr uint32_t CAND = LOGIC ? ST_CAND_LOGIC : ST_CAND;
+	static constexpr size_t BASE = TILE_DOCS * 4 + ST_NSTAGES * STAGE_POST * 8 +
+	    CAND * 8 + ST_NSTAGES * sizeof(StageMeta) + LOGTAB_N * 4 +
+	    2 * ST_NSTAGES * 8 + 64;
+	static constexpr size_t SMEM = BASE + (LOGIC ? TILE_DOCS : 0);
+	static_assert(BASE % 16 == 0, "membership bytes are cleared 16 at a time");
+	static_assert(STAGE_POST < (1u << ST_SUB_TOK_SHIFT), "slot bits");
+};
 
 /* ---- the batched term lookup ------------------------------------------ */
 
@@ -158,7 +179,8 @@ plan_items_kernel(const QDesc *__restrict__ queries,
 		if (hi > lo) {
 			PlanTok pt;
 
-			pt.g0 = t.post_off + lo;
+			/* Top byte: the token's slot in the query (boolean programs). */
+			pt.g0 = (t.post_off + lo) | ((unsigned long long)j << 56);
 			pt.n = hi - lo;
 			pt.idf = t.idf;
 			out[m++] = pt;
@@ -170,6 +192,43 @@ plan_items_kernel(const QDesc *__restrict__ queries,
 	h.ntok = m;
 	h.pad[0] = h.pad[1] = 0;
 	*reinterpret_cast<PlanHdr *>(rec) = h;
+}
+
+/*
+ * Boolean queries with at most 8 tokens: the postfix program (ref
+ * get_expr_bitmap, src/query/search.c:118-174) is a function of which tokens
+ * contain the document, i.e. of one membership byte.  Thread m evaluates it
+ * for membership m; a warp vote packs 32 answers into a table word.
+ */
+__global__ void __launch_bounds__(256)
+truth_tables_kernel(const QDesc *__restrict__ queries,
+    const uint32_t *__restrict__ qlist, const int32_t *__restrict__ prog,
+    uint32_t *__restrict__ tt)
+{
+	const QDesc qd = queries[qlist[blockIdx.x]];
+	const uint32_t m = threadIdx.x;
+	bool st[NXSB_MAX_QUERY_PROG / 2 + 2];
+	int sp = 0;
+
+	for (uint32_t c = 0; c < qd.n_prog; c++) {
+		const int32_t op = prog[qd.prog_off + c];
+
+		if (op >= 0) {
+			st[sp++] = (m >> op) & 1u;
+		} else if (op == NXSB_OP_EMPTY) {
+			st[sp++] = false;
+		} else {
+			const bool b = st[--sp];
+			const bool a = st[sp - 1];
+
+			st[sp - 1] = op == NXSB_OP_AND ? (a && b) :
+			    op == NXSB_OP_OR ? (a || b) : (a && !b);
+		}
+	}
+	const uint32_t w = __ballot_sync(0xffffffffu, sp ? st[sp - 1] : false);
+
+	if ((m & 31) == 0)
+		tt[blockIdx.x * 8 + (m >> 5)] = w;
 }
 
 /* ---- PTX wrappers ------------------------------------------------------ */
@@ -329,22 +388,28 @@ st_score(const StreamParams &p, const float *s_logtab, const uint2 (&v)[NP],
 	}
 }
 
-template <bool WIDE, int ALGO>
+template <bool LOGIC, bool WIDE, int ALGO>
 __global__ void __launch_bounds__(ST_THREADS, 2)
 score_stream_kernel(const StreamParams p)
 {
+	using Cfg = StCfg<LOGIC>;
+	constexpr uint32_t SLOTS = Cfg::SLOTS, STAGE_POST = Cfg::STAGE_POST, CAND = Cfg::CAND;
+
 	extern __shared__ __align__(128) unsigned char smem_stream[];
 	float *acc = reinterpret_cast<float *>(smem_stream);
 	uint2 *ring = reinterpret_cast<uint2 *>(acc + TILE_DOCS);
 	unsigned long long *s_cand = reinterpret_cast<unsigned long long *>(
-	    ring + ST_NSTAGES * ST_STAGE_POST);
-	StageMeta *meta = reinterpret_cast<StageMeta *>(s_cand + ST_CAND);
+	    ring + ST_NSTAGES * STAGE_POST);
+	StageMeta *meta = reinterpret_cast<StageMeta *>(s_cand + CAND);
 	float *s_logtab = reinterpret_cast<float *>(meta + ST_NSTAGES);
 	unsigned long long *bars = reinterpret_cast<unsigned long long *>(
 	    s_logtab + LOGTAB_N);		/* full[NSTAGES], empty[NSTAGES] */
 	uint32_t *s_misc = reinterpret_cast<uint32_t *>(bars + 2 * ST_NSTAGES);
 	uint32_t *s_ncand = s_misc;			/* [2], by item parity */
 	unsigned long long *s_theta = reinterpret_cast<unsigned long long *>(s_misc + 2);
+	uint32_t *s_tt = s_misc + 4;			/* [8] truth table (LOGIC) */
+	/* bit j of memb[d]: token slot j has a posting for tile document d */
+	uint8_t *memb = smem_stream + Cfg::BASE;
 
 	const uint32_t tid = threadIdx.x;
 	const uint32_t full0 = smem_addr(bars), empty0 = smem_addr(bars + ST_NSTAGES);
@@ -355,6 +420,11 @@ score_stream_kernel(const StreamParams p)
 		float4 *a4 = reinterpret_cast<float4 *>(acc);
 		for (uint32_t i = tid; i < TILE_DOCS / 4; i += ST_THREADS)
 			a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+		if (LOGIC) {
+			uint4 *m4 = reinterpret_cast<uint4 *>(memb);
+			for (uint32_t i = tid; i < TILE_DOCS / 16; i += ST_THREADS)
+				m4[i] = make_uint4(0u, 0u, 0u, 0u);
+		}
 	}
 	if (tid == 0) {
 		for (uint32_t s = 0; s < ST_NSTAGES; s++) {
@@ -410,10 +480,11 @@ score_stream_kernel(const StreamParams p)
 				StageMeta &m = meta[ps];
 				uint32_t f = flags | extra_flags;
 
-				if (nsub == 1 && m.sub[0].b0 == 0 && m.sub[0].b1 == ST_STAGE_POST)
+				if (nsub == 1 && (m.sub[0].b0 & 0xfffu) == 0 && m.sub[0].b1 == STAGE_POST)
 					f |= ST_F_FULL;
+				f |= (uint32_t)(m.sub[0].b0 >> ST_SUB_TOK_SHIFT) << ST_F_TOK_SHIFT;
 				if ((f & (ST_F_FIRST | ST_F_LAST)) == (ST_F_FIRST | ST_F_LAST) &&
-				    item_total <= ST_CAND)
+				    item_total <= CAND)
 					f |= ST_F_SPARSE;
 				m.flags = f | (nsub << ST_F_NSUB_SHIFT);
 				m.slot = slot;
@@ -458,8 +529,10 @@ score_stream_kernel(const StreamParams p)
 				item_total = h0.x;
 
 				for (uint32_t j = 0; j < ntok; j++) {
+					const uint32_t ghi = __shfl_sync(0xffffffffu, t0.y, j);
+					const uint32_t tokj = ghi >> 24;
 					unsigned long long g =
-					    ((unsigned long long)__shfl_sync(0xffffffffu, t0.y, j) << 32) |
+					    ((unsigned long long)(ghi & 0x00ffffffu) << 32) |
 					    __shfl_sync(0xffffffffu, t0.x, j);
 					uint32_t n = __shfl_sync(0xffffffffu, t0.z, j);
 					const uint32_t idf_bits = __shfl_sync(0xffffffffu, t0.w, j);
@@ -472,17 +545,17 @@ score_stream_kernel(const StreamParams p)
 							first = 0;
 						}
 						const uint32_t head = (uint32_t)g & 1u;
-						const uint32_t avail = ST_STAGE_POST - used;
+						const uint32_t avail = STAGE_POST - used;
 						const uint32_t take = min(n, avail - head);
 						const uint32_t cnt = (head + take + 1u) & ~1u;
 
 						if (lane == 0) {
 							StageSub &sb = meta[ps].sub[nsub];
 
-							sb.b0 = (uint16_t)(used + head);
+							sb.b0 = (uint16_t)((used + head) | (tokj << ST_SUB_TOK_SHIFT));
 							sb.b1 = (uint16_t)(used + head + take);
 							sb.idf = __uint_as_float(idf_bits);
-							tma_load_1d(smem_addr(ring + ps * ST_STAGE_POST + used),
+							tma_load_1d(smem_addr(ring + ps * STAGE_POST + used),
 							    p.post + (g - head), cnt * 8u, full0 + 8 * ps);
 						}
 						nsub++;
@@ -491,7 +564,7 @@ score_stream_kernel(const StreamParams p)
 						g += take;
 						n -= take;
 						cont = true;
-						if (n > 0 || used + 2 > ST_STAGE_POST || nsub == ST_MAXSUB) {
+						if (n > 0 || used + 2 > STAGE_POST || nsub == ST_MAXSUB) {
 							const bool last = (n == 0 && j + 1 == ntok);
 
 							commit(last ? ST_F_LAST : 0u, slot, tile_lo);
@@ -518,6 +591,7 @@ score_stream_kernel(const StreamParams p)
 	const uint32_t ctid = tid;
 	uint32_t cs = 0, cph = 0, par = 0;
 	unsigned long long theta_pref = 0;
+	uint32_t tt_pref = 0;
 
 	PROF_DECL;
 	for (;;) {
@@ -533,40 +607,56 @@ score_stream_kernel(const StreamParams p)
 			break;
 		}
 		const uint32_t slot = hdr.y, tile_lo = hdr.z;
-		const uint2 *buf = ring + cs * ST_STAGE_POST;
+		const uint2 *buf = ring + cs * STAGE_POST;
 		/* Shared address of acc[doc - tile_lo] = accb + 4 * doc. */
 		const uint32_t accb = smem_addr(acc) - 4u * tile_lo;
 		const uint32_t my_empty = empty0 + 8 * cs;
 
-		if ((flags & ST_F_FIRST) && ctid == 0)
-			theta_pref = *(volatile unsigned long long *)(p.thr + slot);
+		if (flags & ST_F_FIRST) {
+			if (ctid == 0)
+				theta_pref = *(volatile unsigned long long *)(p.thr + slot);
+			if (LOGIC && ctid < 8)
+				tt_pref = __ldg(p.tt + slot * 8u + ctid);
+		}
 
 		if (flags & ST_F_FULL) {
 			/* The common case: every slot valid, one token. */
-			uint2 v[ST_SLOTS];
-			float sc[ST_SLOTS], a[ST_SLOTS];
+			uint2 v[SLOTS];
+			float sc[SLOTS], a[SLOTS];
 
 			if (!(flags & (ST_F_FIRST | ST_F_CONT)))
 				cons_barrier();
 			PROF(2);		/* token barrier */
 #pragma unroll
-			for (int r = 0; r < ST_SLOTS; r++)
+			for (int r = 0; r < SLOTS; r++)
 				v[r] = buf[ctid + r * ST_NCONS];
-			st_score<WIDE, ALGO, ST_SLOTS>(p, s_logtab, v, __uint_as_float(hdr.w), sc);
+			st_score<WIDE, ALGO, SLOTS>(p, s_logtab, v, __uint_as_float(hdr.w), sc);
 			/* Documents of one list are distinct: batch the updates. */
 #pragma unroll
-			for (int r = 0; r < ST_SLOTS; r++)
+			for (int r = 0; r < SLOTS; r++)
 				a[r] = lds_f32(accb + 4u * v[r].x);
 #pragma unroll
-			for (int r = 0; r < ST_SLOTS; r++)
+			for (int r = 0; r < SLOTS; r++)
 				sts_f32(accb + 4u * v[r].x, __fadd_rn(a[r], sc[r]));
+			if (LOGIC) {
+				const uint8_t bit = (uint8_t)(1u << ((flags >> ST_F_TOK_SHIFT) & 7u));
+				uint8_t mb[SLOTS];
+
+#pragma unroll
+				for (int r = 0; r < SLOTS; r++)
+					mb[r] = memb[v[r].x - tile_lo];
+#pragma unroll
+				for (int r = 0; r < SLOTS; r++)
+					memb[v[r].x - tile_lo] = mb[r] | bit;
+			}
 			PROF(3);		/* full stage */
 		} else {
-			const uint32_t nsub = flags >> ST_F_NSUB_SHIFT;
+			const uint32_t nsub = (flags >> ST_F_NSUB_SHIFT) & 0x3fu;
 
 			for (uint32_t s = 0; s < nsub; s++) {
 				const StageSub sb = m.sub[s];
-				const uint32_t b0 = sb.b0, b1 = sb.b1, nb = b1 - b0;
+				const uint32_t b0 = sb.b0 & 0xfffu, b1 = sb.b1, nb = b1 - b0;
+				const uint8_t bit = (uint8_t)(1u << ((sb.b0 >> ST_SUB_TOK_SHIFT) & 7u));
 				const float idf = sb.idf;
 
 				/* A new token: the previous token's updates must have landed. */
@@ -600,6 +690,12 @@ score_stream_kernel(const StreamParams p)
 					for (int r = 0; r < 2; r++)
 						if (ok[r])
 							sts_f32(accb + 4u * v[r].x, __fadd_rn(a[r], sc[r]));
+					if (LOGIC) {
+#pragma unroll
+						for (int r = 0; r < 2; r++)
+							if (ok[r])
+								memb[v[r].x - tile_lo] |= bit;
+					}
 				}
 			}
 		}
@@ -623,8 +719,14 @@ score_stream_kernel(const StreamParams p)
 		/* ---------------- item epilogue: top-k of the tile ---------------- */
 		if (ctid == 0)
 			*s_theta = theta_pref;
+		if (LOGIC && ctid < 8)
+			s_tt[ctid] = tt_pref;
 		cons_barrier();
 		PROF(5);			/* barrier before the epilogue */
+		/* Does a document with this membership byte satisfy the query? */
+		auto in_set = [&](uint32_t mb) -> bool {
+			return !LOGIC || ((s_tt[mb >> 5] >> (mb & 31u)) & 1u);
+		};
 		unsigned long long thr_key = *s_theta;
 		const uint32_t k = p.k;
 		uint32_t *ncand = s_ncand + par;	/* zero on entry */
@@ -638,20 +740,26 @@ score_stream_kernel(const StreamParams p)
 			 */
 			const float ths = thr_key ? __uint_as_float((uint32_t)(thr_key >> 32))
 			    : __uint_as_float(1u);
-			const uint32_t nsub = flags >> ST_F_NSUB_SHIFT;
+			const uint32_t nsub = (flags >> ST_F_NSUB_SHIFT) & 0x3fu;
 
 			for (uint32_t s = 0; s < nsub; s++) {
 				const uint32_t b1 = m.sub[s].b1;
 
-				for (uint32_t i = m.sub[s].b0 + ctid; i < b1; i += ST_NCONS) {
+				for (uint32_t i = (m.sub[s].b0 & 0xfffu) + ctid; i < b1; i += ST_NCONS) {
 					const uint32_t doc = buf[i].x;
 					const float val = atomicExch(acc + (doc - tile_lo), 0.f);
+					bool member = true;
 
-					if (val >= ths) {
+					if (LOGIC && val != 0.f) {
+						/* Only a document's first visitor gets here. */
+						member = in_set(memb[doc - tile_lo]);
+						memb[doc - tile_lo] = 0;
+					}
+					if (val >= ths && member) {
 						const unsigned long long key = make_key(val, doc);
 
 						if (key > thr_key) {
-							/* at < item total <= ST_CAND */
+							/* at < item total <= CAND */
 							s_cand[atomicAdd(ncand, 1u)] = key;
 						}
 					}
@@ -670,23 +778,27 @@ score_stream_kernel(const StreamParams p)
 				    : __uint_as_float(1u);
 				float4 *a4 = reinterpret_cast<float4 *>(acc);
 
-				auto visit = [&](float &val, uint32_t i) {
-					if (val >= ths) {
+				uint32_t *memb32 = reinterpret_cast<uint32_t *>(memb);
+
+				/* false: the buffer is full, the document stays for the next round */
+				auto visit = [&](float &val, uint32_t i, uint32_t mb) -> bool {
+					if (val >= ths && in_set(mb)) {
 						const unsigned long long key = make_key(val, tile_lo + i);
 
 						if (key > thr_key) {
 							const uint32_t at = atomicAdd(ncand, 1u);
 
-							if (at < ST_CAND)
+							if (at < CAND)
 								s_cand[at] = key;
 							else
-								return;	/* stays for the next round */
+								return false;
 						}
 					}
 					val = 0.f;
+					return true;
 				};
 				/*
-				 * Two batches of eight independent 16-byte loads; one
+				 * Batches of eight independent 16-byte loads; one
 				 * compare decides for all 32 values of a batch (the
 				 * common case: nothing beats the threshold).
 				 */
@@ -714,29 +826,42 @@ score_stream_kernel(const StreamParams p)
 							const uint32_t i4 = base + j * ST_NCONS;
 
 							if (EXACT || i4 < N4) {
-								visit(q[j].x, 4 * i4 + 0);
-								visit(q[j].y, 4 * i4 + 1);
-								visit(q[j].z, 4 * i4 + 2);
-								visit(q[j].w, 4 * i4 + 3);
+								/* four membership bytes ride along */
+								const uint32_t mb4 = LOGIC ? memb32[i4] : 0u;
+								uint32_t keep = 0;
+
+								if (!visit(q[j].x, 4 * i4 + 0, mb4 & 0xffu))
+									keep |= 0x000000ffu;
+								if (!visit(q[j].y, 4 * i4 + 1, (mb4 >> 8) & 0xffu))
+									keep |= 0x0000ff00u;
+								if (!visit(q[j].z, 4 * i4 + 2, (mb4 >> 16) & 0xffu))
+									keep |= 0x00ff0000u;
+								if (!visit(q[j].w, 4 * i4 + 3, mb4 >> 24))
+									keep |= 0xff000000u;
 								a4[i4] = q[j];
+								if (LOGIC)
+									memb32[i4] = mb4 & keep;
 							}
 						}
 					} else {
 #pragma unroll
 						for (int j = 0; j < NB; j++)
-							if (EXACT || base + j * ST_NCONS < N4)
+							if (EXACT || base + j * ST_NCONS < N4) {
 								a4[base + j * ST_NCONS] =
 								    make_float4(0.f, 0.f, 0.f, 0.f);
+								if (LOGIC)
+									memb32[base + j * ST_NCONS] = 0u;
+							}
 					}
 				}
 				PROF(7);	/* scan + zero */
 				cons_barrier();
 				PROF(8);
 				total = *(volatile uint32_t *)ncand;
-				if (total <= ST_CAND)
+				if (total <= CAND)
 					break;
 				/* Overflow: keep the k best, tighten, rescan what is left. */
-				st_sort_desc(s_cand, ST_CAND, ctid);
+				st_sort_desc(s_cand, CAND, ctid);
 				thr_key = s_cand[k - 1];
 				cons_barrier();
 				if (ctid == 0)
