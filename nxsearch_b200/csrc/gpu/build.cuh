@@ -125,4 +125,26 @@ build_skip_rows_kernel(const uint2 *__restrict__ post,
 	    skip + (size_t)blockIdx.x * (ntiles + 1));
 }
 
+/*
+ * Dense columns: block b scatters the postings of dense term cols[b] into
+ * column b (pre-zeroed): col[doc] = packed word.
+ */
+__global__ void __launch_bounds__(256)
+build_dense_columns_kernel(const uint2 *__restrict__ post,
+    const unsigned long long *__restrict__ term_off,
+    const uint32_t *__restrict__ cols, unsigned long long col_words,
+    uint32_t *__restrict__ dense)
+{
+	const uint32_t t = cols[blockIdx.y];
+	const unsigned long long s = term_off[t], e = term_off[t + 1];
+	uint32_t *col = dense + (unsigned long long)blockIdx.y * col_words;
+
+	for (unsigned long long i = s + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	    i < e; i += (unsigned long long)gridDim.x * blockDim.x) {
+		const uint2 p = post[i];
+
+		col[p.x] = p.y;
+	}
+}
+
 #endif

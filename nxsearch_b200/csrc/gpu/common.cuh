@@ -16,6 +16,15 @@
  *   skip[R][T+1]   u32: first posting (relative to the term) whose doc lies
  *                  in tile >= j -- the per-tile slice boundaries
  *   doc_ids[N]     u64 external ids, ascending;  doc_len[N] u32
+ *   dense[D][T*16384]  u32: for the D terms present in most documents
+ *                  (df_local >= dense_min * N) the same list once more as a
+ *                  column indexed by document -- the packed tf|dl word, 0 where
+ *                  the term is absent.  The dense encoding of a dense list
+ *                  (what roaring's bitmap containers are to the reference):
+ *                  4 bytes per document instead of 8 per posting, and the
+ *                  document index is implicit, so the scorer's accumulator
+ *                  accesses are 16-byte vectors without bank conflicts.
+ *                  PACKED mode only.  dense_col[V] i32 maps term -> column.
  */
 #ifndef NXSB_GPU_COMMON_CUH
 #define NXSB_GPU_COMMON_CUH
@@ -37,12 +46,15 @@
 
 static_assert((1u << TILE_SHIFT) == TILE_DOCS, "tile size");
 
+#define DENSE_NONE	(~0ull)
+
 /* A resolved token instance of a batch: the result of the term lookup. */
 struct DTok {
 	unsigned long long	post_off;	// first posting of the term
 	const uint32_t *	skip;		// [ntiles + 1] slice boundaries
 	uint32_t		df_local;
 	float			idf;
+	unsigned long long	dense_off;	// word offset of its dense column, or DENSE_NONE
 };
 
 /* 16-byte result record (also the NCCL all-gather payload). */

@@ -135,6 +135,10 @@ struct nxsb_engine {
 	uint32_t *	d_df_local = nullptr;
 	float *		d_idf_bm25 = nullptr, *d_idf_tfidf = nullptr;
 	int32_t *	d_skip_row = nullptr;
+	uint32_t *	d_dense = nullptr;		// [n_dense][ntiles * TILE_DOCS] words
+	int32_t *	d_dense_col = nullptr;		// [V] column of a term or -1
+	uint32_t	n_dense = 0;
+	float		dense_min = 0.6f;		// df_local / N at which a list gets a column
 	uint32_t *	d_skip = nullptr;
 	unsigned long long *d_doc_ids = nullptr;
 	uint32_t *	d_doc_len = nullptr;
@@ -298,6 +302,9 @@ nxsb_engine_create(int device)
 		/* Development switch: score with the older tiles.cuh kernel. */
 		const char *kv = getenv("NXSB_KERNEL");
 		e->force_v2 = kv && strcmp(kv, "v2") == 0;
+		/* Development switch: density threshold of the dense columns (> 1: none). */
+		if ((kv = getenv("NXSB_DENSE_MIN")) != NULL)
+			e->dense_min = (float)atof(kv);
 	}
 	for (auto &r : e->runs)
 		for (int i = 0; i < EV_PER_RUN; i++)
@@ -325,6 +332,9 @@ free_image(nxsb_engine_t *e)
 	dev_free(e->d_idf_bm25);
 	dev_free(e->d_idf_tfidf);
 	dev_free(e->d_skip_row);
+	dev_free(e->d_dense);
+	dev_free(e->d_dense_col);
+	e->n_dense = 0;
 	dev_free(e->d_skip);
 	dev_free(e->d_doc_ids);
 	dev_free(e->d_doc_len);
@@ -578,6 +588,48 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 			fail(e, "skip table build failed: %s",
 			    cudaGetErrorString(cudaGetLastError()));
 			break;
+		}
+
+		/* Dense columns for the lists present in most documents. */
+		{
+			std::vector<int32_t> col(V, -1);
+			std::vector<uint32_t> dterms;
+			const unsigned long long col_words =
+			    (unsigned long long)e->ntiles * TILE_DOCS;
+
+			if (!e->wide && N >= TILE_DOCS && e->dense_min <= 1.f) {
+				for (uint32_t t = 0; t < V; t++) {
+					if ((double)e->h_df_local[t] >= (double)e->dense_min * N &&
+					    dterms.size() < 256) {
+						col[t] = (int32_t)dterms.size();
+						dterms.push_back(t);
+					}
+				}
+			}
+			e->n_dense = dterms.size();
+			uint32_t *d_dterms = nullptr;
+			bool ok = dev_alloc(&e->d_dense_col, V) == cudaSuccess &&
+			    dev_alloc(&e->d_dense, (size_t)e->n_dense * col_words) == cudaSuccess &&
+			    dev_alloc(&d_dterms, e->n_dense) == cudaSuccess;
+			if (ok) {
+				cudaMemcpyAsync(e->d_dense_col, col.data(), (size_t)V * 4,
+				    cudaMemcpyHostToDevice, st);
+				if (e->n_dense) {
+					cudaMemsetAsync(e->d_dense, 0, (size_t)e->n_dense * col_words * 4, st);
+					cudaMemcpyAsync(d_dterms, dterms.data(), (size_t)e->n_dense * 4,
+					    cudaMemcpyHostToDevice, st);
+					build_dense_columns_kernel<<<dim3(e->n_sms * 2, e->n_dense), 256, 0, st>>>(
+					    e->d_post, e->d_term_off, d_dterms, col_words, e->d_dense);
+					e->launches++;
+				}
+				ok = cudaStreamSynchronize(st) == cudaSuccess;
+			}
+			dev_free(d_dterms);
+			if (!ok) {
+				fail(e, "dense column build failed: %s",
+				    cudaGetErrorString(cudaGetLastError()));
+				break;
+			}
 		}
 
 		if (sd->df)
@@ -963,6 +1015,7 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
 		}
 	}
 	p.tt = e->d_tt;
+	p.dense = e->d_dense;
 
 	auto kern = B.algo == NXSB_ALGO_BM25
 	    ? (e->wide ? score_stream_kernel<LOGIC, true, NXSB_ALGO_BM25>
@@ -1136,6 +1189,7 @@ run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
 
 	resolve_tokens_kernel<<<(B.n_tok + 255) / 256, 256, 0, st>>>(
 	    B.d_tokens, B.n_tok, e->n_terms, e->d_term_off, e->d_skip_row,
+	    e->d_dense_col, (unsigned long long)e->ntiles * TILE_DOCS,
 	    e->d_skip, B.d_tmp_skip,
 	    B.algo == NXSB_ALGO_BM25 ? e->d_idf_bm25 : e->d_idf_tfidf,
 	    e->ntiles, B.d_toks);

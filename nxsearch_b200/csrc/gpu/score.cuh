@@ -62,7 +62,8 @@ struct ScoreParams {
 __global__ void __launch_bounds__(256)
 resolve_tokens_kernel(const uint32_t *__restrict__ term_ids, uint32_t n,
     uint32_t n_terms, const unsigned long long *__restrict__ term_off,
-    const int32_t *__restrict__ skip_row, const uint32_t *__restrict__ skip,
+    const int32_t *__restrict__ skip_row, const int32_t *__restrict__ dense_col,
+    unsigned long long col_words, const uint32_t *__restrict__ skip,
     uint32_t *__restrict__ tmp_skip, const float *__restrict__ idf,
     uint32_t ntiles, DTok *__restrict__ out)
 {
@@ -78,6 +79,7 @@ resolve_tokens_kernel(const uint32_t *__restrict__ term_ids, uint32_t n,
 		t.post_off = 0;
 		t.df_local = 0;
 		t.idf = 0.f;
+		t.dense_off = DENSE_NONE;
 		t.skip = tmp_skip + (size_t)i * (ntiles + 1);
 	} else {
 		const uint32_t ti = id - 1;
@@ -87,6 +89,8 @@ resolve_tokens_kernel(const uint32_t *__restrict__ term_ids, uint32_t n,
 		t.post_off = s;
 		t.df_local = (uint32_t)(term_off[ti + 1] - s);
 		t.idf = idf[ti];
+		t.dense_off = dense_col[ti] >= 0 ? (unsigned long long)dense_col[ti] * col_words
+		    : DENSE_NONE;
 		t.skip = row >= 0 ? skip + (size_t)row * (ntiles + 1)
 		    : tmp_skip + (size_t)i * (ntiles + 1);
 	}

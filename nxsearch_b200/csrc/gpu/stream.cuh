@@ -85,6 +85,7 @@
 #define ST_F_END	8u	/* no more work */
 #define ST_F_FULL	16u	/* one slice filling every slot of the stage */
 #define ST_F_SPARSE	32u	/* whole item in this stage, <= ST_CAND postings */
+#define ST_F_DENSE	64u	/* a run of a dense column: one word per document */
 #define ST_F_NSUB_SHIFT	8	/* 6 bits */
 #define ST_F_TOK_SHIFT	16	/* token slot of slice 0 (boolean queries) */
 #define ST_SUB_TOK_SHIFT 12	/* StageSub::b0 = first slot | token slot << 12 */
@@ -96,7 +97,11 @@ struct PlanHdr {
 	uint32_t	pad[2];
 };
 struct PlanTok {
-	unsigned long long g0;		/* first posting (absolute) | token slot << 56 */
+	/*
+	 * First posting (absolute index) -- or, with bit 63 set, the first word
+	 * of the tile's run in the term's dense column -- | token slot << 56.
+	 */
+	unsigned long long g0;
 	uint32_t	n;
 	float		idf;
 };
@@ -129,6 +134,7 @@ struct StreamParams {
 	const uint32_t *	doc_len;	/* WIDE */
 	float			K0, K1;
 	const uint32_t *	tt;		/* [n_q][8] truth tables (boolean) */
+	const uint32_t *	dense;		/* dense columns (common.cuh) */
 	unsigned long long *	prof;		/* ST_PROF counters or NULL */
 };
 
@@ -180,7 +186,9 @@ plan_items_kernel(const QDesc *__restrict__ queries,
 			PlanTok pt;
 
 			/* Top byte: the token's slot in the query (boolean programs). */
-			pt.g0 = (t.post_off + lo) | ((unsigned long long)j << 56);
+			pt.g0 = (t.dense_off != DENSE_NONE
+			    ? (t.dense_off + (unsigned long long)tile * TILE_DOCS) | (1ull << 63)
+			    : t.post_off + lo) | ((unsigned long long)j << 56);
 			pt.n = hi - lo;
 			pt.idf = t.idf;
 			out[m++] = pt;
@@ -480,7 +488,8 @@ score_stream_kernel(const StreamParams p)
 				StageMeta &m = meta[ps];
 				uint32_t f = flags | extra_flags;
 
-				if (nsub == 1 && (m.sub[0].b0 & 0xfffu) == 0 && m.sub[0].b1 == STAGE_POST)
+				if (!(f & ST_F_DENSE) && nsub == 1 && (m.sub[0].b0 & 0xfffu) == 0 &&
+				    m.sub[0].b1 == STAGE_POST)
 					f |= ST_F_FULL;
 				f |= (uint32_t)(m.sub[0].b0 >> ST_SUB_TOK_SHIFT) << ST_F_TOK_SHIFT;
 				if ((f & (ST_F_FIRST | ST_F_LAST)) == (ST_F_FIRST | ST_F_LAST) &&
@@ -537,6 +546,38 @@ score_stream_kernel(const StreamParams p)
 					uint32_t n = __shfl_sync(0xffffffffu, t0.z, j);
 					const uint32_t idf_bits = __shfl_sync(0xffffffffu, t0.w, j);
 					bool cont = false;
+
+					if (tokj & 0x80u) {
+						/*
+						 * Dense column: the tile's 16384 words go out in
+						 * runs of DENSE_RUN documents, one stage each.
+						 */
+						constexpr uint32_t DENSE_RUN = 2 * STAGE_POST;
+
+						if (open)
+							commit(0u, slot, tile_lo);
+						for (uint32_t d0 = 0; d0 < TILE_DOCS; d0 += DENSE_RUN) {
+							const uint32_t nd = min(DENSE_RUN, TILE_DOCS - d0);
+							const bool last = d0 + nd == TILE_DOCS && j + 1 == ntok;
+
+							acquire();
+							flags = first | (d0 ? ST_F_CONT : 0u) | ST_F_DENSE;
+							first = 0;
+							if (lane == 0) {
+								StageSub &sb = meta[ps].sub[0];
+
+								sb.b0 = (uint16_t)((d0 / 4u) | ((tokj & 15u) << ST_SUB_TOK_SHIFT));
+								sb.b1 = (uint16_t)nd;
+								sb.idf = __uint_as_float(idf_bits);
+								tma_load_1d(smem_addr(ring + ps * STAGE_POST),
+								    p.dense + g + d0, nd * 4u, full0 + 8 * ps);
+							}
+							nsub = 1;
+							bytes = nd * 4u;
+							commit(last ? ST_F_LAST : 0u, slot, tile_lo);
+						}
+						continue;
+					}
 
 					while (n > 0) {
 						if (!open) {
@@ -619,7 +660,62 @@ score_stream_kernel(const StreamParams p)
 				tt_pref = __ldg(p.tt + slot * 8u + ctid);
 		}
 
-		if (flags & ST_F_FULL) {
+		if (!WIDE && (flags & ST_F_DENSE)) {
+			/*
+			 * A run of a dense column: word i belongs to document
+			 * tile_lo + 4 * doff4 + i, so the accumulator is updated
+			 * with 16-byte vectors at consecutive addresses.  Absent
+			 * documents hold 0 and add +0.0.
+			 */
+			constexpr int DG = SLOTS / 2;	/* 4-document groups per thread */
+			const StageSub sb = m.sub[0];
+			const uint32_t doff4 = sb.b0 & 0xfffu, nd4 = (uint32_t)sb.b1 / 4u;
+			const float idf = __uint_as_float(hdr.w);
+			const uint4 *wb = reinterpret_cast<const uint4 *>(buf);
+			float4 *a4 = reinterpret_cast<float4 *>(acc) + doff4;
+			uint4 w[DG];
+			float sc[DG][4];
+
+			if (!(flags & (ST_F_FIRST | ST_F_CONT)))
+				cons_barrier();
+#pragma unroll
+			for (int g = 0; g < DG; g++) {
+				const uint32_t idx = ctid + g * ST_NCONS;
+
+				w[g] = make_uint4(0u, 0u, 0u, 0u);
+				if (idx < nd4)
+					w[g] = wb[idx];
+			}
+#pragma unroll
+			for (int g = 0; g < DG; g++) {
+				const uint2 v[4] = { make_uint2(0u, w[g].x), make_uint2(0u, w[g].y),
+				    make_uint2(0u, w[g].z), make_uint2(0u, w[g].w) };
+
+				st_score<false, ALGO, 4>(p, s_logtab, v, idf, sc[g]);
+			}
+#pragma unroll
+			for (int g = 0; g < DG; g++) {
+				const uint32_t idx = ctid + g * ST_NCONS;
+
+				if (idx < nd4) {
+					float4 a = a4[idx];
+
+					a.x = __fadd_rn(a.x, sc[g][0]);
+					a.y = __fadd_rn(a.y, sc[g][1]);
+					a.z = __fadd_rn(a.z, sc[g][2]);
+					a.w = __fadd_rn(a.w, sc[g][3]);
+					a4[idx] = a;
+					if (LOGIC) {
+						const uint32_t bit = 1u << ((sb.b0 >> ST_SUB_TOK_SHIFT) & 7u);
+						uint32_t *m32 = reinterpret_cast<uint32_t *>(memb) + doff4 + idx;
+
+						*m32 |= (w[g].x ? bit : 0u) | (w[g].y ? bit << 8 : 0u) |
+						    (w[g].z ? bit << 16 : 0u) | (w[g].w ? bit << 24 : 0u);
+					}
+				}
+			}
+			PROF(3);
+		} else if (flags & ST_F_FULL) {
 			/* The common case: every slot valid, one token. */
 			uint2 v[SLOTS];
 			float sc[SLOTS], a[SLOTS];
