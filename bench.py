@@ -15,7 +15,7 @@ One JSON line on stdout (rank 0): see the contract in the task description.
 `value`  = device-resident throughput (batches already in HBM),
 `e2e`    = the same through the reference-facing C API with host buffers
            (query strings in, result arrays out; N > 1: engine C ABI + merge),
-`roofline` = score_tiles_kernel against the measured HBM peak,
+`roofline` = score_stream_kernel against the measured HBM peak,
 `cpu_baseline` = the oracle port on this box's host cores, bounded sample.
 """
 from __future__ import annotations
@@ -123,7 +123,7 @@ def measured_peak() -> tuple[float, str]:
 
 
 def recorded_traffic():
-    """DRAM bytes per launch of score_tiles_kernel from the committed ncu capture."""
+    """DRAM bytes per launch of the scoring kernel from the committed ncu capture."""
     p = ROOT / "profiles" / "ncu_traffic.json"
     if p.exists():
         try:
@@ -287,7 +287,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     achieved = timed_bytes / (tile_ms / 1000) / 1e9 if tile_ms > 0 else 0.0
     runs_timed = min(args.steps, 256)
     roofline = {
-        "bound": "hbm", "kernel": "score_tiles_kernel<LOGIC=false,WIDE=false,BM25>",
+        "bound": "hbm", "kernel": "score_stream_kernel<LOGIC=false,WIDE=false,BM25>",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": recorded_traffic(), "peak_source": peak_src,
         "algorithmic_bytes_per_launch": timed_bytes / max(runs_timed, 1),
@@ -428,7 +428,7 @@ def cpu_baseline(args, corpus, batch_items, engine, host_batch):
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--docs", type=int, default=10_000_000)
