@@ -138,6 +138,9 @@ struct nxsb_engine {
 	uint32_t *	d_dense = nullptr;		// [n_dense][ntiles * TILE_DOCS] words
 	int32_t *	d_dense_col = nullptr;		// [V] column of a term or -1
 	uint32_t	n_dense = 0;
+	float *		d_dense_sc = nullptr;		// per-batch score columns, same shape
+	uint32_t *	d_dense_terms = nullptr;	// [n_dense] term index of a column
+	uint32_t *	d_dense_used = nullptr;		// [256] column referenced by the batch
 	float		dense_min = 0.6f;		// df_local / N at which a list gets a column
 	uint32_t *	d_skip = nullptr;
 	unsigned long long *d_doc_ids = nullptr;
@@ -334,6 +337,9 @@ free_image(nxsb_engine_t *e)
 	dev_free(e->d_skip_row);
 	dev_free(e->d_dense);
 	dev_free(e->d_dense_col);
+	dev_free(e->d_dense_sc);
+	dev_free(e->d_dense_terms);
+	dev_free(e->d_dense_used);
 	e->n_dense = 0;
 	dev_free(e->d_skip);
 	dev_free(e->d_doc_ids);
@@ -610,6 +616,8 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 			uint32_t *d_dterms = nullptr;
 			bool ok = dev_alloc(&e->d_dense_col, V) == cudaSuccess &&
 			    dev_alloc(&e->d_dense, (size_t)e->n_dense * col_words) == cudaSuccess &&
+			    dev_alloc(&e->d_dense_sc, (size_t)e->n_dense * col_words) == cudaSuccess &&
+			    dev_alloc(&e->d_dense_used, 256) == cudaSuccess &&
 			    dev_alloc(&d_dterms, e->n_dense) == cudaSuccess;
 			if (ok) {
 				cudaMemcpyAsync(e->d_dense_col, col.data(), (size_t)V * 4,
@@ -624,7 +632,7 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 				}
 				ok = cudaStreamSynchronize(st) == cudaSuccess;
 			}
-			dev_free(d_dterms);
+			e->d_dense_terms = d_dterms;
 			if (!ok) {
 				fail(e, "dense column build failed: %s",
 				    cudaGetErrorString(cudaGetLastError()));
@@ -1015,7 +1023,7 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
 		}
 	}
 	p.tt = e->d_tt;
-	p.dense = e->d_dense;
+	p.dense = reinterpret_cast<const uint32_t *>(e->d_dense_sc);
 
 	auto kern = B.algo == NXSB_ALGO_BM25
 	    ? (e->wide ? score_stream_kernel<LOGIC, true, NXSB_ALGO_BM25>
@@ -1187,9 +1195,11 @@ run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
 		return 0;
 	}
 
+	if (e->n_dense)
+		CK(e, cudaMemsetAsync(e->d_dense_used, 0, 256 * 4, st));
 	resolve_tokens_kernel<<<(B.n_tok + 255) / 256, 256, 0, st>>>(
 	    B.d_tokens, B.n_tok, e->n_terms, e->d_term_off, e->d_skip_row,
-	    e->d_dense_col, (unsigned long long)e->ntiles * TILE_DOCS,
+	    e->d_dense_col, e->d_dense_used, (unsigned long long)e->ntiles * TILE_DOCS,
 	    e->d_skip, B.d_tmp_skip,
 	    B.algo == NXSB_ALGO_BM25 ? e->d_idf_bm25 : e->d_idf_tfidf,
 	    e->ntiles, B.d_toks);
@@ -1197,6 +1207,23 @@ run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
 	    B.d_tmp_skip, e->ntiles);
 	e->launches += 2;
 	CK(e, cudaGetLastError());
+	if (e->n_dense) {
+		/* Score columns of the dense terms this batch refers to. */
+		const unsigned long long col_words = (unsigned long long)e->ntiles * TILE_DOCS;
+		const dim3 grid(e->n_sms * 4, e->n_dense);
+
+		mark(e, "dense_scores");
+		if (B.algo == NXSB_ALGO_BM25)
+			dense_scores_kernel<NXSB_ALGO_BM25><<<grid, 256, 0, st>>>(e->d_dense,
+			    e->d_dense_terms, e->d_dense_used, e->d_idf_bm25, e->d_logtab,
+			    e->K0, e->K1, col_words, e->d_dense_sc);
+		else
+			dense_scores_kernel<NXSB_ALGO_TFIDF><<<grid, 256, 0, st>>>(e->d_dense,
+			    e->d_dense_terms, e->d_dense_used, e->d_idf_tfidf, e->d_logtab,
+			    e->K0, e->K1, col_words, e->d_dense_sc);
+		e->launches++;
+		CK(e, cudaGetLastError());
+	}
 
 	if (run_list<false>(e, B, B.d_qlist_or, B.q_or.size(), d_recs) == -1 ||
 	    run_list<true>(e, B, B.d_qlist_logic, B.q_logic.size(), d_recs) == -1)

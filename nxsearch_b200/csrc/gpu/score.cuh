@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256)
 resolve_tokens_kernel(const uint32_t *__restrict__ term_ids, uint32_t n,
     uint32_t n_terms, const unsigned long long *__restrict__ term_off,
     const int32_t *__restrict__ skip_row, const int32_t *__restrict__ dense_col,
-    unsigned long long col_words, const uint32_t *__restrict__ skip,
+    uint32_t *__restrict__ dense_used, unsigned long long col_words, const uint32_t *__restrict__ skip,
     uint32_t *__restrict__ tmp_skip, const float *__restrict__ idf,
     uint32_t ntiles, DTok *__restrict__ out)
 {
@@ -91,6 +91,8 @@ resolve_tokens_kernel(const uint32_t *__restrict__ term_ids, uint32_t n,
 		t.idf = idf[ti];
 		t.dense_off = dense_col[ti] >= 0 ? (unsigned long long)dense_col[ti] * col_words
 		    : DENSE_NONE;
+		if (dense_col[ti] >= 0)
+			dense_used[dense_col[ti]] = 1u;	/* dense_scores_kernel will fill it */
 		t.skip = row >= 0 ? skip + (size_t)row * (ntiles + 1)
 		    : tmp_skip + (size_t)i * (ntiles + 1);
 	}

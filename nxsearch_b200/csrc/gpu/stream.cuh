@@ -63,6 +63,8 @@
 #define ST_LOGIC_TOKENS	8u			/* tokens a membership byte holds */
 #define ST_K_MAX	128u			/* limit served by this kernel */
 #define ST_RANK_MAX	256u			/* candidates ranked by counting */
+#define ST_PUSH		1024u			/* documents noted while accumulating */
+#define ST_PUSH_LOGIC	512u
 
 /*
  * -DST_PROF: per-phase cycle counters of the consumer warps (lane 0) and the
@@ -86,6 +88,7 @@
 #define ST_F_FULL	16u	/* one slice filling every slot of the stage */
 #define ST_F_SPARSE	32u	/* whole item in this stage, <= ST_CAND postings */
 #define ST_F_DENSE	64u	/* a run of a dense column: one word per document */
+#define ST_F_STORE	128u	/* dense run that leads its item: store, do not add */
 #define ST_F_NSUB_SHIFT	8	/* 6 bits */
 #define ST_F_TOK_SHIFT	16	/* token slot of slice 0 (boolean queries) */
 #define ST_SUB_TOK_SHIFT 12	/* StageSub::b0 = first slot | token slot << 12 */
@@ -119,6 +122,10 @@ struct StageMeta {
 	uint32_t	slot, tile_lo;
 	float		idf0;		/* = sub[0].idf */
 	StageSub	sub[ST_MAXSUB];
+	/* First stage of an item: score half of the query's threshold key as
+	 * the producer saw it (0: none yet). */
+	uint32_t	ths_bits;
+	uint32_t	pad[3];
 };
 
 struct StreamParams {
@@ -148,9 +155,11 @@ struct StCfg {
 	static constexpr uint32_t SLOTS = LOGIC ? ST_SLOTS_LOGIC : ST_SLOTS;
 	static constexpr uint32_t STAGE_POST = SLOTS * ST_NCONS;
 	static constexpr uint32_t CAND = LOGIC ? ST_CAND_LOGIC : ST_CAND;
+	static constexpr uint32_t PUSH = LOGIC ? ST_PUSH_LOGIC : ST_PUSH;
 	static constexpr size_t BASE = TILE_DOCS * 4 + ST_NSTAGES * STAGE_POST * 8 +
 	    CAND * 8 + ST_NSTAGES * sizeof(StageMeta) + LOGTAB_N * 4 +
-	    2 * ST_NSTAGES * 8 + 64;
+	    2 * ST_NSTAGES * 8 + 64 + PUSH * 2;
+	static_assert(PUSH <= CAND, "noted documents become candidates");
 	static constexpr size_t SMEM = BASE + (LOGIC ? TILE_DOCS : 0);
 	static_assert(BASE % 16 == 0, "membership bytes are cleared 16 at a time");
 	static_assert(STAGE_POST < (1u << ST_SUB_TOK_SHIFT), "slot bits");
@@ -194,6 +203,18 @@ plan_items_kernel(const QDesc *__restrict__ queries,
 			out[m++] = pt;
 			total += hi - lo;
 		}
+	}
+	/*
+	 * A dense column that leads the item is STORED into the accumulator
+	 * instead of added (no zero-fill, no read).  The first float addition
+	 * of a document's sum is commutative, so a dense slice in second place
+	 * may change places with the first without changing a single bit.
+	 */
+	if (m >= 2 && !(out[0].g0 >> 63) && (out[1].g0 >> 63)) {
+		const PlanTok t0 = out[0];
+
+		out[0] = out[1];
+		out[1] = t0;
 	}
 	PlanHdr h;
 	h.total = total;
@@ -396,12 +417,57 @@ st_score(const StreamParams &p, const float *s_logtab, const uint2 (&v)[NP],
 	}
 }
 
+/*
+ * Score columns of the batch: the weight of (term, document) does not depend
+ * on the query, so for the dense columns a batch refers to it is computed ONCE
+ * per batch here -- same st_score() arithmetic, hence the same bits -- instead
+ * of once per (query, document) in the scorer, which then streams finished
+ * floats.  Absent documents (word 0) score +0.0.  Block (x, c) covers a
+ * grid-strided part of column c; columns no token of the batch uses are skipped.
+ */
+template <int ALGO>
+__global__ void __launch_bounds__(256)
+dense_scores_kernel(const uint32_t *__restrict__ dense,
+    const uint32_t *__restrict__ dterms, const uint32_t *__restrict__ used,
+    const float *__restrict__ idf, const float *__restrict__ logtab,
+    float K0, float K1, unsigned long long col_words, float *__restrict__ out)
+{
+	__shared__ float s_logtab[LOGTAB_N];
+	const uint32_t c = blockIdx.y;
+
+	if (!used[c])
+		return;
+	for (uint32_t i = threadIdx.x; i < LOGTAB_N; i += blockDim.x)
+		s_logtab[i] = logtab[i];
+	__syncthreads();
+
+	StreamParams p;
+	p.K0 = K0;
+	p.K1 = K1;
+	p.doc_len = nullptr;
+	const float w = idf[dterms[c]];
+	const uint4 *in4 = reinterpret_cast<const uint4 *>(dense + c * col_words);
+	float4 *out4 = reinterpret_cast<float4 *>(out + c * col_words);
+
+	for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	    i < col_words / 4; i += (unsigned long long)gridDim.x * blockDim.x) {
+		const uint4 x = in4[i];
+		const uint2 v[4] = { make_uint2(0u, x.x), make_uint2(0u, x.y),
+		    make_uint2(0u, x.z), make_uint2(0u, x.w) };
+		float sc[4];
+
+		st_score<false, ALGO, 4>(p, s_logtab, v, w, sc);
+		out4[i] = make_float4(sc[0], sc[1], sc[2], sc[3]);
+	}
+}
+
 template <bool LOGIC, bool WIDE, int ALGO>
 __global__ void __launch_bounds__(ST_THREADS, 2)
 score_stream_kernel(const StreamParams p)
 {
 	using Cfg = StCfg<LOGIC>;
 	constexpr uint32_t SLOTS = Cfg::SLOTS, STAGE_POST = Cfg::STAGE_POST, CAND = Cfg::CAND;
+	constexpr uint32_t PUSH = Cfg::PUSH;
 
 	extern __shared__ __align__(128) unsigned char smem_stream[];
 	float *acc = reinterpret_cast<float *>(smem_stream);
@@ -416,8 +482,12 @@ score_stream_kernel(const StreamParams p)
 	uint32_t *s_ncand = s_misc;			/* [2], by item parity */
 	unsigned long long *s_theta = reinterpret_cast<unsigned long long *>(s_misc + 2);
 	uint32_t *s_tt = s_misc + 4;			/* [8] truth table (LOGIC) */
+	uint32_t *s_npush = s_misc + 12;		/* [2], by item parity */
+	/* tile-relative documents whose running sum reached the threshold */
+	uint16_t *s_push = reinterpret_cast<uint16_t *>(s_misc + 16);
 	/* bit j of memb[d]: token slot j has a posting for tile document d */
 	uint8_t *memb = smem_stream + Cfg::BASE;
+	static_assert(TILE_DOCS <= 65536, "s_push holds 16-bit document offsets");
 
 	const uint32_t tid = threadIdx.x;
 	const uint32_t full0 = smem_addr(bars), empty0 = smem_addr(bars + ST_NSTAGES);
@@ -440,6 +510,7 @@ score_stream_kernel(const StreamParams p)
 			mbar_init(empty0 + 8 * s, ST_CWARPS);
 		}
 		s_ncand[0] = s_ncand[1] = 0;
+		s_npush[0] = s_npush[1] = 0;
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
@@ -476,8 +547,17 @@ score_stream_kernel(const StreamParams p)
 			return __ldg(reinterpret_cast<const uint4 *>(
 			    p.plan + (unsigned long long)it * p.plan_stride + 16) + lane);
 		};
+		/* The query's threshold as of now: a lower bound of what the
+		 * consumers will find, which is all the inline check needs. */
+		auto load_thr = [&](uint32_t it) -> uint32_t {
+			if (it >= n_items)
+				return 0u;
+			return (uint32_t)(*(volatile const unsigned long long *)
+			    (p.thr + it % p.n_q) >> 32);
+		};
 		uint2 h0 = load_hdr(it0);
 		uint4 t0 = load_tok(it0, h0.y);
+		uint32_t thr0 = load_thr(it0);
 
 		/* Open stage state. */
 		bool open = false;
@@ -499,6 +579,7 @@ score_stream_kernel(const StreamParams p)
 				m.slot = slot;
 				m.tile_lo = tile_lo;
 				m.idf0 = m.sub[0].idf;
+				m.ths_bits = thr0;
 				if (bytes)
 					mbar_arrive_expect_tx(full0 + 8 * ps, bytes);
 				else
@@ -527,6 +608,7 @@ score_stream_kernel(const StreamParams p)
 				raw2 = atomicAdd(p.work_counter, 1u);
 			const uint2 h1 = load_hdr(it1);
 			const uint4 t1 = load_tok(it1, h1.y);
+			const uint32_t thr1 = load_thr(it1);
 
 			if (h0.x != 0) {
 				const uint32_t tile = p.ntiles - 1 - it0 / p.n_q;
@@ -561,7 +643,8 @@ score_stream_kernel(const StreamParams p)
 							const bool last = d0 + nd == TILE_DOCS && j + 1 == ntok;
 
 							acquire();
-							flags = first | (d0 ? ST_F_CONT : 0u) | ST_F_DENSE;
+							flags = first | (d0 ? ST_F_CONT : 0u) | ST_F_DENSE |
+							    (j == 0 ? ST_F_STORE : 0u);
 							first = 0;
 							if (lane == 0) {
 								StageSub &sb = meta[ps].sub[0];
@@ -618,6 +701,7 @@ score_stream_kernel(const StreamParams p)
 			it0 = it1;
 			h0 = h1;
 			t0 = t1;
+			thr0 = thr1;
 			it1 = __shfl_sync(0xffffffffu, raw2, 0);
 		}
 		/* Tell the consumers there is nothing more. */
@@ -633,6 +717,23 @@ score_stream_kernel(const StreamParams p)
 	uint32_t cs = 0, cph = 0, par = 0;
 	unsigned long long theta_pref = 0;
 	uint32_t tt_pref = 0;
+	/*
+	 * Inline selection.  Scores are positive, so a document's running sum
+	 * only grows: one that ends above the query's threshold reaches it at
+	 * some addition, and the thread doing that addition notes the document
+	 * in s_push.  The epilogue then visits the noted documents instead of
+	 * scanning the tile.  ths = +inf switches the noting off (no threshold
+	 * yet, or a sparse item); `dirty` says the accumulator holds leftovers
+	 * of such an item and must be zero-filled before the next addition.
+	 */
+	float ths = __uint_as_float(0x7f800000u);
+	bool dirty = false;
+	auto note = [&](uint32_t rel) {
+		const uint32_t at = atomicAdd(s_npush + par, 1u);
+
+		if (at < PUSH)
+			s_push[at] = (uint16_t)rel;
+	};
 
 	PROF_DECL;
 	for (;;) {
@@ -654,10 +755,31 @@ score_stream_kernel(const StreamParams p)
 		const uint32_t my_empty = empty0 + 8 * cs;
 
 		if (flags & ST_F_FIRST) {
+			const uint32_t tb = m.ths_bits;
+
 			if (ctid == 0)
 				theta_pref = *(volatile unsigned long long *)(p.thr + slot);
 			if (LOGIC && ctid < 8)
 				tt_pref = __ldg(p.tt + slot * 8u + ctid);
+			ths = (tb != 0u && !(flags & ST_F_SPARSE)) ? __uint_as_float(tb)
+			    : __uint_as_float(0x7f800000u);
+			if (dirty && !(flags & ST_F_STORE)) {
+				/* Nobody reads the accumulator past the previous
+				 * item's last epilogue barrier. */
+				float4 *z4 = reinterpret_cast<float4 *>(acc);
+
+#pragma unroll 4
+				for (uint32_t i = ctid; i < TILE_DOCS / 4; i += ST_NCONS)
+					z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (LOGIC) {
+					uint4 *m4 = reinterpret_cast<uint4 *>(memb);
+
+					for (uint32_t i = ctid; i < TILE_DOCS / 16; i += ST_NCONS)
+						m4[i] = make_uint4(0u, 0u, 0u, 0u);
+				}
+				cons_barrier();
+			}
+			dirty = false;
 		}
 
 		if (!WIDE && (flags & ST_F_DENSE)) {
@@ -670,47 +792,62 @@ score_stream_kernel(const StreamParams p)
 			constexpr int DG = SLOTS / 2;	/* 4-document groups per thread */
 			const StageSub sb = m.sub[0];
 			const uint32_t doff4 = sb.b0 & 0xfffu, nd4 = (uint32_t)sb.b1 / 4u;
-			const float idf = __uint_as_float(hdr.w);
-			const uint4 *wb = reinterpret_cast<const uint4 *>(buf);
+			const float4 *wb = reinterpret_cast<const float4 *>(buf);
 			float4 *a4 = reinterpret_cast<float4 *>(acc) + doff4;
-			uint4 w[DG];
-			float sc[DG][4];
+			const bool store = (flags & ST_F_STORE) != 0;
+			float4 w[DG], a[DG];
 
+			/* The words are the finished scores (dense_scores_kernel). */
 			if (!(flags & (ST_F_FIRST | ST_F_CONT)))
 				cons_barrier();
 #pragma unroll
 			for (int g = 0; g < DG; g++) {
 				const uint32_t idx = ctid + g * ST_NCONS;
 
-				w[g] = make_uint4(0u, 0u, 0u, 0u);
+				w[g] = make_float4(0.f, 0.f, 0.f, 0.f);
 				if (idx < nd4)
 					w[g] = wb[idx];
 			}
 #pragma unroll
 			for (int g = 0; g < DG; g++) {
-				const uint2 v[4] = { make_uint2(0u, w[g].x), make_uint2(0u, w[g].y),
-				    make_uint2(0u, w[g].z), make_uint2(0u, w[g].w) };
+				const uint32_t idx = ctid + g * ST_NCONS;
 
-				st_score<false, ALGO, 4>(p, s_logtab, v, idf, sc[g]);
+				a[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+				if (!store && idx < nd4)
+					a[g] = a4[idx];
 			}
 #pragma unroll
 			for (int g = 0; g < DG; g++) {
 				const uint32_t idx = ctid + g * ST_NCONS;
 
 				if (idx < nd4) {
-					float4 a = a4[idx];
+					/* store: 0 + w == w, bit for bit */
+					a[g].x = __fadd_rn(a[g].x, w[g].x);
+					a[g].y = __fadd_rn(a[g].y, w[g].y);
+					a[g].z = __fadd_rn(a[g].z, w[g].z);
+					a[g].w = __fadd_rn(a[g].w, w[g].w);
+					a4[idx] = a[g];
+					if (fmaxf(fmaxf(a[g].x, a[g].y), fmaxf(a[g].z, a[g].w)) >= ths) {
+						const uint32_t rel = 4u * (doff4 + idx);
 
-					a.x = __fadd_rn(a.x, sc[g][0]);
-					a.y = __fadd_rn(a.y, sc[g][1]);
-					a.z = __fadd_rn(a.z, sc[g][2]);
-					a.w = __fadd_rn(a.w, sc[g][3]);
-					a4[idx] = a;
+						if (a[g].x >= ths)
+							note(rel);
+						if (a[g].y >= ths)
+							note(rel + 1u);
+						if (a[g].z >= ths)
+							note(rel + 2u);
+						if (a[g].w >= ths)
+							note(rel + 3u);
+					}
 					if (LOGIC) {
 						const uint32_t bit = 1u << ((sb.b0 >> ST_SUB_TOK_SHIFT) & 7u);
 						uint32_t *m32 = reinterpret_cast<uint32_t *>(memb) + doff4 + idx;
+						const uint32_t bits = (w[g].x != 0.f ? bit : 0u) |
+						    (w[g].y != 0.f ? bit << 8 : 0u) |
+						    (w[g].z != 0.f ? bit << 16 : 0u) |
+						    (w[g].w != 0.f ? bit << 24 : 0u);
 
-						*m32 |= (w[g].x ? bit : 0u) | (w[g].y ? bit << 8 : 0u) |
-						    (w[g].z ? bit << 16 : 0u) | (w[g].w ? bit << 24 : 0u);
+						*m32 = store ? bits : (*m32 | bits);
 					}
 				}
 			}
@@ -731,9 +868,19 @@ score_stream_kernel(const StreamParams p)
 #pragma unroll
 			for (int r = 0; r < SLOTS; r++)
 				a[r] = lds_f32(accb + 4u * v[r].x);
+			float top = 0.f;
 #pragma unroll
-			for (int r = 0; r < SLOTS; r++)
-				sts_f32(accb + 4u * v[r].x, __fadd_rn(a[r], sc[r]));
+			for (int r = 0; r < SLOTS; r++) {
+				a[r] = __fadd_rn(a[r], sc[r]);
+				sts_f32(accb + 4u * v[r].x, a[r]);
+				top = fmaxf(top, a[r]);
+			}
+			if (top >= ths) {
+#pragma unroll
+				for (int r = 0; r < SLOTS; r++)
+					if (a[r] >= ths)
+						note(v[r].x - tile_lo);
+			}
 			if (LOGIC) {
 				const uint8_t bit = (uint8_t)(1u << ((flags >> ST_F_TOK_SHIFT) & 7u));
 				uint8_t mb[SLOTS];
@@ -784,8 +931,12 @@ score_stream_kernel(const StreamParams p)
 							a[r] = lds_f32(accb + 4u * v[r].x);
 #pragma unroll
 					for (int r = 0; r < 2; r++)
-						if (ok[r])
-							sts_f32(accb + 4u * v[r].x, __fadd_rn(a[r], sc[r]));
+						if (ok[r]) {
+							a[r] = __fadd_rn(a[r], sc[r]);
+							sts_f32(accb + 4u * v[r].x, a[r]);
+							if (a[r] >= ths)
+								note(v[r].x - tile_lo);
+						}
 					if (LOGIC) {
 #pragma unroll
 						for (int r = 0; r < 2; r++)
@@ -813,8 +964,12 @@ score_stream_kernel(const StreamParams p)
 			continue;
 
 		/* ---------------- item epilogue: top-k of the tile ---------------- */
-		if (ctid == 0)
+		if (ctid == 0) {
 			*s_theta = theta_pref;
+			/* The next item's counter: last read before the previous
+			 * item's final barrier, next bumped after this item's. */
+			s_npush[par ^ 1u] = 0;
+		}
 		if (LOGIC && ctid < 8)
 			s_tt[ctid] = tt_pref;
 		cons_barrier();
@@ -826,10 +981,34 @@ score_stream_kernel(const StreamParams p)
 		unsigned long long thr_key = *s_theta;
 		const uint32_t k = p.k;
 		uint32_t *ncand = s_ncand + par;	/* zero on entry */
+		const uint32_t npush = s_npush[par];
 		uint32_t total;
 
 		par ^= 1u;
-		if (flags & ST_F_SPARSE) {
+		if (ths != __uint_as_float(0x7f800000u) && npush <= PUSH) {
+			/*
+			 * Every document that can beat the threshold was noted
+			 * (possibly more than once): its first visitor takes the
+			 * final sum.  The rest of the accumulator is left as it is
+			 * and zero-filled when the next item needs it clean.
+			 */
+			for (uint32_t i = ctid; i < npush; i += ST_NCONS) {
+				const uint32_t rel = s_push[i];
+				const float val = atomicExch(acc + rel, 0.f);
+
+				if (val != 0.f && in_set(LOGIC ? memb[rel] : 0u)) {
+					const unsigned long long key = make_key(val, tile_lo + rel);
+
+					if (key > thr_key)
+						s_cand[atomicAdd(ncand, 1u)] = key;	/* < PUSH <= CAND */
+				}
+			}
+			dirty = true;
+			PROF(7);
+			cons_barrier();
+			PROF(8);
+			total = *(volatile uint32_t *)ncand;
+		} else if (flags & ST_F_SPARSE) {
 			/*
 			 * Sparse item: visit only the documents its postings name;
 			 * the first visitor of a document takes its sum and clears it.
