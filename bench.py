@@ -44,6 +44,18 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries loaded later (NCCL's
+# version banner, for one) write to fd 1 directly, so fd 1 is pointed at
+# stderr for the whole run and the line goes out through the saved descriptor.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 # --------------------------------------------------------------------------
 # workload
 
@@ -192,7 +204,7 @@ def run_reference(args, rank: int, world: int) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(args) -> str:
@@ -315,7 +327,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, corpus, batches[args.warmup % n_distinct], engine, host_batches[args.warmup % n_distinct])
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     for h in handles:
         engine.release(h)
     engine.close()
