@@ -358,10 +358,25 @@ def e2e_capi(args, corpus, batches, capi):
         n = len(batches)
         for s in range(args.warmup):
             idx.search_batch_arrays(arrays[s % n], args.limit, **params)
+        # (1) one synchronous nxs_index_search_batch call per step
         t0 = time.perf_counter()
         for s in range(args.steps):
             counts, ids, scores = idx.search_batch_arrays(arrays[(args.warmup + s) % n], args.limit, **params)
+        dt_serial = time.perf_counter() - t0
+        # (2) the same calls split in begin/end, two batches in flight: the
+        # host parses batch s+1 while the GPU scores batch s.  Every step still
+        # takes its strings from host memory, copies its descriptors to the
+        # device and drains its results into host arrays.
+        t0 = time.perf_counter()
+        ticket = idx.search_batch_begin(arrays[args.warmup % n], args.limit, **params)
+        for s in range(args.steps):
+            nxt = (idx.search_batch_begin(arrays[(args.warmup + s + 1) % n], args.limit, **params)
+                   if s + 1 < args.steps else None)
+            counts, ids, scores = idx.search_batch_end_arrays(ticket)
+            ticket = nxt
         dt = time.perf_counter() - t0
+        log(f"[0] e2e: synchronous {args.batch * args.steps / dt_serial:.0f} q/s, "
+            f"pipelined (2 in flight) {args.batch * args.steps / dt:.0f} q/s")
         assert len(counts) == args.batch and int(counts.max()) <= args.limit and int(counts.sum()) > 0
         # the drained arrays are what the list-building wrapper returns
         last = (args.warmup + args.steps - 1) % n
@@ -374,8 +389,10 @@ def e2e_capi(args, corpus, batches, capi):
         d2h = int(args.batch * args.limit * 16 + 4 * args.batch)
         idx.close()
         nxs.close()
-        return args.batch * args.steps / dt, h2d, d2h, ("nxs_index_search_batch (C API: C strings in, "
-                                                        "results drained via nxs_resp_iter_result into host arrays)")
+        return (args.batch * args.steps / dt, h2d, d2h,
+                "nxs_index_search_batch_begin/_end (C API: C strings in, results drained via "
+                "nxs_resp_iter_result into host arrays; two batches in flight); synchronous "
+                "nxs_index_search_batch: %.0f queries/s" % (args.batch * args.steps / dt_serial))
     finally:
         import shutil
         shutil.rmtree(base, ignore_errors=True)

@@ -105,6 +105,21 @@ void		nxs_resp_release(nxs_resp_t *);
 int		nxs_index_search_batch(nxs_index_t *, nxs_params_t *,
 		    const char *const *queries, size_t n, nxs_resp_t **resps);
 
+/*
+ * ADDITIVE: the same batch in two halves, so that the host work of the next
+ * batch (parsing, term lookup) overlaps the GPU work of this one.  _begin
+ * parses, resolves and submits the batch and returns at once; _end waits for
+ * it, fills resps[0..n) as nxs_index_search_batch() does and frees the batch
+ * handle (resps = NULL abandons the results).  Up to 4 batches may be in
+ * flight per index; they complete in submission order.  Every batch must be
+ * ended before nxs_index_close().  nxs_index_search_batch() is _begin
+ * followed by _end.
+ */
+typedef struct nxs_batch nxs_batch_t;
+nxs_batch_t *	nxs_index_search_batch_begin(nxs_index_t *, nxs_params_t *,
+		    const char *const *queries, size_t n);
+int		nxs_index_search_batch_end(nxs_batch_t *, nxs_resp_t **resps);
+
 #pragma GCC visibility pop
 
 #ifdef __cplusplus

@@ -122,6 +122,17 @@ int		nxsb_engine_search(nxsb_engine_t *, const nxsb_batch_t *,
 		    uint32_t *counts, uint64_t *ids, float *scores);
 
 /*
+ * The same search in two halves: begin enqueues the descriptor copy, the
+ * kernels and the result copy and returns a handle >= 0 without waiting; end
+ * waits for that batch only and fills the host arrays (pass counts = NULL to
+ * discard).  Up to 4 searches may be in flight, so a caller can prepare batch
+ * i+1 on the host while batch i is on the device.
+ */
+int		nxsb_engine_search_begin(nxsb_engine_t *, const nxsb_batch_t *);
+int		nxsb_engine_search_end(nxsb_engine_t *, int handle,
+		    uint32_t *counts, uint64_t *ids, float *scores);
+
+/*
  * The same in three steps, for callers that keep the batch resident in HBM
  * (the `value` leg of bench.py) or chain a collective on the device.
  * upload: copies the batch descriptors to the device, returns a handle >= 0.

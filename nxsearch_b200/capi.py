@@ -49,6 +49,11 @@ def bind(lib=None):
     if hasattr(lib, "nxs_index_search_batch"):
         lib.nxs_index_search_batch.restype = C.c_int
         lib.nxs_index_search_batch.argtypes = [vp, vp, C.POINTER(cp), sz, C.POINTER(vp)]
+    if hasattr(lib, "nxs_index_search_batch_begin"):
+        lib.nxs_index_search_batch_begin.restype = vp
+        lib.nxs_index_search_batch_begin.argtypes = [vp, vp, C.POINTER(cp), sz]
+        lib.nxs_index_search_batch_end.restype = C.c_int
+        lib.nxs_index_search_batch_end.argtypes = [vp, C.POINTER(vp)]
     if hasattr(lib, "nxsb_resp_collect"):
         lib.nxsb_resp_collect.restype = u64
         lib.nxsb_resp_collect.argtypes = [C.POINTER(vp), sz, C.c_uint32, vp, vp, vp]
@@ -193,6 +198,38 @@ class Index:
         rc = self._lib.nxs_index_search_batch(self.h, p.h, arr, n, out)
         p.release()
         if rc != 0:
+            self.nxs.raise_error()
+        counts = np.zeros(n, dtype=np.uint32)
+        ids = np.zeros((n, limit), dtype=np.uint64)
+        scores = np.zeros((n, limit), dtype=np.float32)
+        self._lib.nxsb_resp_collect(out, n, limit, counts.ctypes.data, ids.ctypes.data, scores.ctypes.data)
+        for h in out:
+            if h:
+                self._lib.nxs_resp_release(h)
+        return counts, ids, scores
+
+    def search_batch_begin(self, queries, limit: int, **params):
+        """nxs_index_search_batch_begin: parse + resolve + submit, no wait.
+        Returns a ticket for search_batch_end_arrays()."""
+        if isinstance(queries, C.Array):
+            arr, n = queries, len(queries)
+        else:
+            qs = [q.encode() if isinstance(q, str) else q for q in queries]
+            arr, n = (C.c_char_p * len(qs))(*qs), len(qs)
+        p = Params(self._lib, limit=limit, **params)
+        bt = self._lib.nxs_index_search_batch_begin(self.h, p.h, arr, n)
+        p.release()
+        if not bt:
+            self.nxs.raise_error()
+        return (bt, n, limit, arr)
+
+    def search_batch_end_arrays(self, ticket):
+        """nxs_index_search_batch_end + nxsb_resp_collect -> (counts, ids, scores)."""
+        import numpy as np
+
+        bt, n, limit, _ = ticket
+        out = (C.c_void_p * n)()
+        if self._lib.nxs_index_search_batch_end(bt, out) != 0:
             self.nxs.raise_error()
         counts = np.zeros(n, dtype=np.uint32)
         ids = np.zeros((n, limit), dtype=np.uint64)

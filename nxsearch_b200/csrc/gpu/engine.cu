@@ -23,6 +23,7 @@
 
 #define CAND_ARENA_BYTES	(2ull << 30)	// candidate keys per sub-batch
 #define MAX_HANDLES		64
+#define PIPE_DEPTH		4	// searches in flight (search_begin/end)
 #define EV_PER_RUN		8
 #define EV_RING			256
 
@@ -170,6 +171,10 @@ struct nxsb_engine {
 
 	Batch		batches[MAX_HANDLES];
 	Batch		oneshot;	// reused by nxsb_engine_search
+	/* nxsb_engine_search_begin/end: pooled slots, one "done" event each */
+	Batch		pipe[PIPE_DEPTH];
+	cudaEvent_t	pipe_done[PIPE_DEPTH] = { nullptr };
+	bool		pipe_busy[PIPE_DEPTH] = { false };
 
 	/* vocabulary (fuzzy) */
 	FuzzyImage	fz;
@@ -369,6 +374,11 @@ nxsb_engine_destroy(nxsb_engine_t *e)
 		if (b.used)
 			free_batch(b);
 	free_batch(e->oneshot);
+	for (int i = 0; i < PIPE_DEPTH; i++) {
+		free_batch(e->pipe[i]);
+		if (e->pipe_done[i])
+			cudaEventDestroy(e->pipe_done[i]);
+	}
 	free_image(e);
 	fuzzy_free(e->fz);
 	dev_free(e->d_cand);
@@ -1242,23 +1252,38 @@ nxsb_engine_batch_run(nxsb_engine_t *e, int h, void *d_recs)
 	return run_batch(e, B, d_recs ? (Rec *)d_recs : B.d_recs);
 }
 
+/* Results of a batch: one D2H copy into pinned memory, then host arrays. */
 static int
-fetch_results(nxsb_engine_t *e, Batch &B, uint32_t *counts, uint64_t *ids,
-    float *scores)
+enqueue_fetch(nxsb_engine_t *e, Batch &B)
+{
+	CK(e, cudaMemcpyAsync(B.h_results.p, B.results.p, B.results_bytes,
+	    cudaMemcpyDeviceToHost, e->stream));
+	return 0;
+}
+
+static void
+unpack_results(const Batch &B, uint32_t *counts, uint64_t *ids, float *scores)
 {
 	const size_t nrec = (size_t)B.n_q * B.limit;
 	const Rec *recs = (const Rec *)B.h_results.p;
 	const uint32_t *cnt = (const uint32_t *)((const char *)B.h_results.p +
 	    ((const char *)B.d_counts - (const char *)B.results.p));
 
-	CK(e, cudaMemcpyAsync(B.h_results.p, B.results.p, B.results_bytes,
-	    cudaMemcpyDeviceToHost, e->stream));
-	CK(e, cudaStreamSynchronize(e->stream));
 	memcpy(counts, cnt, (size_t)B.n_q * 4);
 	for (size_t i = 0; i < nrec; i++) {
 		ids[i] = recs[i].doc_id;
 		scores[i] = recs[i].score;
 	}
+}
+
+static int
+fetch_results(nxsb_engine_t *e, Batch &B, uint32_t *counts, uint64_t *ids,
+    float *scores)
+{
+	if (enqueue_fetch(e, B) == -1)
+		return -1;
+	CK(e, cudaStreamSynchronize(e->stream));
+	unpack_results(B, counts, ids, scores);
 	return 0;
 }
 
@@ -1282,6 +1307,51 @@ nxsb_engine_search(nxsb_engine_t *e, const nxsb_batch_t *b, uint32_t *counts,
 	if (fill_batch(e, B, b) == -1 || run_batch(e, B, B.d_recs) == -1)
 		return -1;
 	return fetch_results(e, B, counts, ids, scores);
+}
+
+/*
+ * The same search split in two, so that a caller can prepare and submit the
+ * next batch while this one is on the device: begin enqueues the descriptor
+ * copy, every kernel and the result copy on the engine's stream and records
+ * an event; end waits for that event only.
+ */
+extern "C" int
+nxsb_engine_search_begin(nxsb_engine_t *e, const nxsb_batch_t *b)
+{
+	int s = -1;
+
+	CK(e, cudaSetDevice(e->device));
+	for (int i = 0; i < PIPE_DEPTH; i++)
+		if (!e->pipe_busy[i]) {
+			s = i;
+			break;
+		}
+	if (s < 0)
+		return fail(e, "too many searches in flight (%d)", PIPE_DEPTH);
+	if (!e->pipe_done[s])
+		CK(e, cudaEventCreateWithFlags(&e->pipe_done[s], cudaEventDisableTiming));
+	Batch &B = e->pipe[s];
+
+	if (fill_batch(e, B, b) == -1 || run_batch(e, B, B.d_recs) == -1 ||
+	    enqueue_fetch(e, B) == -1)
+		return -1;
+	CK(e, cudaEventRecord(e->pipe_done[s], e->stream));
+	e->pipe_busy[s] = true;
+	return s;
+}
+
+extern "C" int
+nxsb_engine_search_end(nxsb_engine_t *e, int s, uint32_t *counts, uint64_t *ids,
+    float *scores)
+{
+	if (s < 0 || s >= PIPE_DEPTH || !e->pipe_busy[s])
+		return fail(e, "bad search handle %d", s);
+	e->pipe_busy[s] = false;
+	CK(e, cudaSetDevice(e->device));
+	CK(e, cudaEventSynchronize(e->pipe_done[s]));
+	if (counts)
+		unpack_results(e->pipe[s], counts, ids, scores);
+	return 0;
 }
 
 extern "C" int

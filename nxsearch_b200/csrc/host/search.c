@@ -239,36 +239,65 @@ prepare_all(nxs_index_t *idx, const search_params_t *sp,
 			pthread_join(tid[t], NULL);
 }
 
-NXS_API int
-nxs_index_search_batch(nxs_index_t *idx, nxs_params_t *params,
-    const char *const *queries, size_t n, nxs_resp_t **resps)
+/*
+ * A batch between its two halves: what _end needs to turn the engine's
+ * arrays into responses.
+ */
+struct nxs_batch {
+	nxs_index_t *	idx;
+	size_t		n;
+	bool *		failed;		/* per query: no response for it */
+	uint32_t	k;		/* result stride */
+	int		handle;		/* engine search in flight, or -1 */
+};
+
+static void
+batch_free(nxs_batch_t *bt)
+{
+	if (bt) {
+		free(bt->failed);
+		free(bt);
+	}
+}
+
+/*
+ * First half: everything on the host (parameters, index sync, parse, token
+ * resolution) and the submission of the batch to the device.  Returns without
+ * waiting for the GPU.
+ */
+NXS_API nxs_batch_t *
+nxs_index_search_batch_begin(nxs_index_t *idx, nxs_params_t *params,
+    const char *const *queries, size_t n)
 {
 	nxs_t *nxs = idx->nxs;
 	search_params_t sp;
 	prepared_t *pq = NULL;
 	nxsb_query_t *descs = NULL;
-	uint32_t *tokens = NULL, *counts = NULL;
+	uint32_t *tokens = NULL;
 	int32_t *prog = NULL;
-	uint64_t *ids = NULL;
-	float *scores = NULL;
 	size_t n_tok = 0, n_prog = 0, n_miss = 0, n_run = 0;
+	nxs_batch_t *bt = NULL;
 	uint32_t k;
 	int ret = -1;
 
 	nxs_clear_error(nxs);
-	for (size_t i = 0; i < n; i++)
-		resps[i] = NULL;
 	if (get_search_params(idx, params, &sp) == -1)
-		return -1;
+		return NULL;
 	if (sp.algo != NXSB_ALGO_BM25 && sp.algo != NXSB_ALGO_TFIDF) {
 		nxs_set_error(nxs, NXS_ERR_INVALID, "invalid algorithm");
-		return -1;
+		return NULL;
 	}
 
 	/* Pick up what other processes appended (search.c:309-310). */
 	if (idx_terms_sync(idx) == -1 || idx_dtmap_sync(idx, true) == -1)
-		return -1;
+		return NULL;
 
+	if ((bt = calloc(1, sizeof(*bt))) == NULL ||
+	    (bt->failed = calloc(n ? n : 1, sizeof(bool))) == NULL)
+		goto out;
+	bt->idx = idx;
+	bt->n = n;
+	bt->handle = -1;
 	if ((pq = calloc(n ? n : 1, sizeof(prepared_t))) == NULL)
 		goto out;
 
@@ -408,6 +437,8 @@ nxs_index_search_batch(nxs_index_t *idx, nxs_params_t *params,
 	if (k == 0)
 		k = 1;
 
+	bt->k = k;
+
 	if (n_run) {
 		const nxsb_batch_t batch = {
 			.algo = sp.algo, .limit = k, .n_queries = n,
@@ -415,35 +446,22 @@ nxs_index_search_batch(nxs_index_t *idx, nxs_params_t *params,
 			.prog = prog, .n_prog = n_prog,
 		};
 
-		counts = calloc(n, sizeof(uint32_t));
-		ids = malloc(sizeof(uint64_t) * n * k);
-		scores = malloc(sizeof(float) * n * k);
-		if (!counts || !ids || !scores)
-			goto out;
 		if (idx_gpu_prepare(idx, false) == -1)
 			goto out;
-		if (nxsb_engine_search(idx->engine, &batch, counts, ids, scores) == -1) {
+		bt->handle = nxsb_engine_search_begin(idx->engine, &batch);
+		if (bt->handle == -1) {
 			nxs_set_error(nxs, NXS_ERR_SYSTEM, "GPU search failed: %s",
 			    nxsb_engine_errmsg(idx->engine));
 			goto out;
 		}
 	}
-	for (size_t i = 0; i < n; i++) {
-		if (pq[i].failed)
-			continue;
-		resps[i] = nxs_resp_from_arrays(ids ? ids + i * k : NULL,
-		    scores ? scores + i * k : NULL, counts ? counts[i] : 0);
-		if (!resps[i])
-			goto out;
-	}
+	for (size_t i = 0; i < n; i++)
+		bt->failed[i] = pq[i].failed;
 	ret = 0;
 out:
 	if (ret != 0) {
-		for (size_t i = 0; i < n; i++) {
-			if (resps[i])
-				nxs_resp_release(resps[i]);
-			resps[i] = NULL;
-		}
+		batch_free(bt);
+		bt = NULL;
 		nxs_error_checkpoint(nxs);
 	}
 	for (size_t i = 0; pq && i < n; i++)
@@ -452,10 +470,89 @@ out:
 	free(descs);
 	free(tokens);
 	free(prog);
+	return bt;
+}
+
+/*
+ * Second half: wait for the batch, build the responses, release the batch
+ * (also on failure).  resps may be NULL to abandon the results.
+ */
+NXS_API int
+nxs_index_search_batch_end(nxs_batch_t *bt, nxs_resp_t **resps)
+{
+	nxs_index_t *idx;
+	nxs_t *nxs;
+	uint32_t *counts = NULL;
+	uint64_t *ids = NULL;
+	float *scores = NULL;
+	size_t n;
+	uint32_t k;
+	int ret = -1;
+
+	if (!bt)
+		return -1;
+	idx = bt->idx;
+	nxs = idx->nxs;
+	n = bt->n;
+	k = bt->k;
+	for (size_t i = 0; resps && i < n; i++)
+		resps[i] = NULL;
+	if (bt->handle >= 0) {
+		if (resps) {
+			counts = calloc(n, sizeof(uint32_t));
+			ids = malloc(sizeof(uint64_t) * n * k);
+			scores = malloc(sizeof(float) * n * k);
+			if (!counts || !ids || !scores) {
+				nxsb_engine_search_end(idx->engine, bt->handle, NULL, NULL, NULL);
+				nxs_set_error(nxs, NXS_ERR_SYSTEM, "out of memory");
+				goto out;
+			}
+		}
+		if (nxsb_engine_search_end(idx->engine, bt->handle, counts, ids,
+		    scores) == -1) {
+			nxs_set_error(nxs, NXS_ERR_SYSTEM, "GPU search failed: %s",
+			    nxsb_engine_errmsg(idx->engine));
+			goto out;
+		}
+	}
+	for (size_t i = 0; resps && i < n; i++) {
+		if (bt->failed[i])
+			continue;
+		resps[i] = nxs_resp_from_arrays(ids ? ids + i * k : NULL,
+		    scores ? scores + i * k : NULL, counts ? counts[i] : 0);
+		if (!resps[i]) {
+			nxs_set_error(nxs, NXS_ERR_SYSTEM, "out of memory");
+			goto out;
+		}
+	}
+	ret = 0;
+out:
+	if (ret != 0) {
+		for (size_t i = 0; resps && i < n; i++) {
+			if (resps[i])
+				nxs_resp_release(resps[i]);
+			resps[i] = NULL;
+		}
+		nxs_error_checkpoint(nxs);
+	}
 	free(counts);
 	free(ids);
 	free(scores);
+	batch_free(bt);
 	return ret;
+}
+
+NXS_API int
+nxs_index_search_batch(nxs_index_t *idx, nxs_params_t *params,
+    const char *const *queries, size_t n, nxs_resp_t **resps)
+{
+	nxs_batch_t *bt;
+
+	for (size_t i = 0; i < n; i++)
+		resps[i] = NULL;
+	if ((bt = nxs_index_search_batch_begin(idx, params, queries, n)) == NULL)
+		return -1;
+	return nxs_index_search_batch_end(bt, resps);
 }
 
 NXS_API nxs_resp_t *

@@ -36,7 +36,7 @@ if hasattr(e.lib if hasattr(e, "lib") else None, "nxsb_engine_prof") or True:
         lib.nxsb_engine_prof.argtypes = [C.c_void_p, C.c_void_p]
         lib.nxsb_engine_prof(e.h if hasattr(e, "h") else e._h, out)
         names = ["other", "wait_full", "tok_barrier", "full_stage", "partial", "bar_pre_epi", "sparse_collect",
-                 "scan_zero", "bar_post", "rank_emit", "", "", "P_other", "P_wait_empty"]
+                 "scan_zero", "bar_post", "rank_emit", "dense_run", "zero_fill", "P_other", "P_wait_empty"]
         cons = sum(out[i] for i in range(12)); prod = out[12] + out[13]
-        print("consumer:", {names[i]: round(100 * out[i] / cons, 1) for i in range(10)})
+        print("consumer:", {names[i]: round(100 * out[i] / cons, 1) for i in range(12)})
         print("producer:", {names[i]: round(100 * out[i] / prod, 1) for i in (12, 13)})

@@ -264,3 +264,45 @@ def test_ids_limits_and_wide_documents(nxs):
     assert len(idx.search("bulk", limit=5000)) == 1200
     assert len(idx.search("bulk", limit=2**32 - 1)) == 1200
     idx.close()
+
+
+def test_batch_begin_end_pipeline_equals_synchronous_calls(c1_corpus, c1_both):
+    """nxs_index_search_batch_begin/_end: several batches in flight give the
+    arrays the synchronous call gives, in any end order; a fifth begin fails
+    with NXS_ERR_SYSTEM; resps = NULL abandons a batch."""
+    import ctypes as C
+
+    ours, _ = c1_both
+    qt = c1_corpus.query_terms(4 * 3 * 200, seed=77)
+    batches = []
+    for b in range(4):
+        qs = []
+        for i in range(200):
+            leaves = qt[(b * 200 + i) * 3:(b * 200 + i) * 3 + 1 + i % 3]
+            qs.append(" OR ".join(c1_corpus.term(int(t)) for t in leaves))
+        if b == 2:
+            qs[5] = "(("           # a syntax error fails this query only
+        batches.append(qs)
+    params = dict(algo="BM25", fuzzymatch=False)
+    want = []
+    for qs in batches:
+        ok = [q for q in qs if q != "(("]
+        want.append(ours.search_batch_arrays(ok, 10, **params))
+    tickets = [ours.search_batch_begin(qs, 10, **params) for qs in batches]
+    with pytest.raises(capi.NxsError):
+        ours.search_batch_begin(batches[0], 10, **params)
+    for b in (1, 0, 3, 2):
+        counts, ids, scores = ours.search_batch_end_arrays(tickets[b])
+        if b == 2:
+            keep = [i for i in range(200) if i != 5]
+            assert counts[5] == 0
+            counts, ids, scores = counts[keep], ids[keep], scores[keep]
+        assert np.array_equal(counts, want[b][0])
+        assert np.array_equal(ids, want[b][1])
+        assert np.array_equal(scores, want[b][2])
+    # abandoned batch: _end with resps = NULL frees the slot
+    for _ in range(6):
+        bt, n, _, _ = ours.search_batch_begin(batches[0], 10, **params)
+        assert ours._lib.nxs_index_search_batch_end(bt, None) == 0
+    c, i, s = ours.search_batch_arrays(batches[0], 10, **params)
+    assert np.array_equal(i, want[0][1])
