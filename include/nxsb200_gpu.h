@@ -131,6 +131,14 @@ int		nxsb_engine_search(nxsb_engine_t *, const nxsb_batch_t *,
 int		nxsb_engine_search_begin(nxsb_engine_t *, const nxsb_batch_t *);
 int		nxsb_engine_search_end(nxsb_engine_t *, int handle,
 		    uint32_t *counts, uint64_t *ids, float *scores);
+/*
+ * begin for a sharded index: this shard's 16-byte records (see batch_run) are
+ * written to d_recs, device memory owned by the caller -- the send buffer of
+ * the all-gather -- and nothing is copied to the host.  End it with
+ * counts = NULL.
+ */
+int		nxsb_engine_search_begin_dev(nxsb_engine_t *, const nxsb_batch_t *,
+		    void *d_recs);
 
 /*
  * The same in three steps, for callers that keep the batch resident in HBM

@@ -1315,8 +1315,8 @@ nxsb_engine_search(nxsb_engine_t *e, const nxsb_batch_t *b, uint32_t *counts,
  * copy, every kernel and the result copy on the engine's stream and records
  * an event; end waits for that event only.
  */
-extern "C" int
-nxsb_engine_search_begin(nxsb_engine_t *e, const nxsb_batch_t *b)
+static int
+search_begin(nxsb_engine_t *e, const nxsb_batch_t *b, Rec *d_recs)
 {
 	int s = -1;
 
@@ -1332,12 +1332,32 @@ nxsb_engine_search_begin(nxsb_engine_t *e, const nxsb_batch_t *b)
 		CK(e, cudaEventCreateWithFlags(&e->pipe_done[s], cudaEventDisableTiming));
 	Batch &B = e->pipe[s];
 
-	if (fill_batch(e, B, b) == -1 || run_batch(e, B, B.d_recs) == -1 ||
-	    enqueue_fetch(e, B) == -1)
+	if (fill_batch(e, B, b) == -1 ||
+	    run_batch(e, B, d_recs ? d_recs : B.d_recs) == -1 ||
+	    (!d_recs && enqueue_fetch(e, B) == -1))
 		return -1;
 	CK(e, cudaEventRecord(e->pipe_done[s], e->stream));
 	e->pipe_busy[s] = true;
 	return s;
+}
+
+extern "C" int
+nxsb_engine_search_begin(nxsb_engine_t *e, const nxsb_batch_t *b)
+{
+	return search_begin(e, b, nullptr);
+}
+
+/*
+ * As search_begin, but this shard's records stay on the device in d_recs
+ * (the send buffer of the cross-shard all-gather); end the search with
+ * counts = NULL once whatever consumes d_recs has been enqueued.
+ */
+extern "C" int
+nxsb_engine_search_begin_dev(nxsb_engine_t *e, const nxsb_batch_t *b, void *d_recs)
+{
+	if (!d_recs)
+		return fail(e, "search_begin_dev needs a device buffer");
+	return search_begin(e, b, (Rec *)d_recs);
 }
 
 extern "C" int

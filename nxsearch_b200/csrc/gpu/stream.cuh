@@ -778,6 +778,7 @@ score_stream_kernel(const StreamParams p)
 						m4[i] = make_uint4(0u, 0u, 0u, 0u);
 				}
 				cons_barrier();
+				PROF(11);		/* lazy zero-fill */
 			}
 			dirty = false;
 		}
@@ -851,7 +852,7 @@ score_stream_kernel(const StreamParams p)
 					}
 				}
 			}
-			PROF(3);
+			PROF(10);		/* dense run */
 		} else if (flags & ST_F_FULL) {
 			/* The common case: every slot valid, one token. */
 			uint2 v[SLOTS];

@@ -71,6 +71,8 @@ class ShardedSearcher:
         self.engine, self.rank, self.world = engine, rank, world
         self.torch = torch
         self._bufs: dict[tuple[int, int], tuple] = {}
+        self._slots: dict[tuple[int, int, int], list] = {}
+        self._next: dict[tuple[int, int, int], int] = {}
 
     def _buffers(self, n_q: int, k: int):
         torch = self.torch
@@ -98,6 +100,43 @@ class ShardedSearcher:
         dist.all_gather_into_tensor(gathered, local)
         self.engine.merge_topk(gathered.data_ptr(), self.world, n_q, k, merged.data_ptr())
         return merged
+
+    # ---- host batches in, host records out, two batches in flight
+
+    def submit(self, host_batch, depth: int = 2):
+        """Descriptor copy, scoring, all-gather, merge and the copy of the
+        merged records into pinned host memory, all enqueued on the engine's
+        stream; returns a ticket for collect().  Slots rotate, so at most
+        `depth` batches may be outstanding."""
+        import torch.distributed as dist
+
+        torch = self.torch
+        n_q, k = len(host_batch.queries), host_batch.limit
+        key = (n_q, k, depth)
+        if key not in self._slots:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            mk = lambda n: torch.zeros(n * n_q * k * REC_BYTES, dtype=torch.uint8, device=dev)
+            self._slots[key] = [dict(local=mk(1), gathered=mk(self.world), merged=mk(1),
+                                     host=torch.zeros(n_q * k * REC_BYTES, dtype=torch.uint8).pin_memory(),
+                                     done=torch.cuda.Event()) for _ in range(depth)]
+            self._next[key] = 0
+        sl = self._slots[key][self._next[key] % depth]
+        self._next[key] += 1
+        h = self.engine.search_begin(host_batch, sl["local"].data_ptr())
+        out = sl["local"]
+        if self.world > 1:
+            dist.all_gather_into_tensor(sl["gathered"], sl["local"])
+            self.engine.merge_topk(sl["gathered"].data_ptr(), self.world, n_q, k, sl["merged"].data_ptr())
+            out = sl["merged"]
+        sl["host"].copy_(out, non_blocking=True)
+        sl["done"].record()
+        return (h, sl, n_q, k)
+
+    def collect(self, ticket) -> np.ndarray:
+        h, sl, n_q, k = ticket
+        sl["done"].synchronize()
+        self.engine.search_end(h, discard=True)
+        return sl["host"].numpy().view(REC_DTYPE).reshape(n_q, k)
 
     def to_host(self, recs_u8, n_q: int, k: int) -> np.ndarray:
         return recs_u8.cpu().numpy().view(REC_DTYPE).reshape(n_q, k)

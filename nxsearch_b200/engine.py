@@ -57,6 +57,9 @@ def _bind():
         "nxsb_engine_sync": (i, [vp]),
         "nxsb_engine_merge_topk": (i, [vp, vp, u32, u32, u32, vp]),
         "nxsb_engine_load_vocab": (i, [vp, u32, vp, vp, vp, vp, vp, vp]),
+        "nxsb_engine_search_begin": (i, [vp, vp]),
+        "nxsb_engine_search_begin_dev": (i, [vp, vp, vp]),
+        "nxsb_engine_search_end": (i, [vp, i, vp, vp, vp]),
         "nxsb_engine_fuzzy": (i, [vp, u32, vp, vp, vp, vp, vp]),
         "nxsb_engine_last_timings": (i, [vp, vp, vp, i]),
         "nxsb_engine_timings": (i, [vp, u32, vp, vp, i]),
@@ -163,6 +166,26 @@ class Engine:
         d = batch.desc()
         self._check(self._lib.nxsb_engine_search(self._h, C.byref(d), counts.ctypes.data,
                                                  ids.ctypes.data, scores.ctypes.data))
+        return counts, ids[: n * k].reshape(n, k), scores[: n * k].reshape(n, k)
+
+    def search_begin(self, batch: Batch, d_recs: int | None = None) -> int:
+        """Submit a batch without waiting (descriptor copy, kernels and -- unless
+        d_recs names a device buffer for the records -- the result copy)."""
+        d = batch.desc()
+        if d_recs is None:
+            return self._check(self._lib.nxsb_engine_search_begin(self._h, C.byref(d)))
+        return self._check(self._lib.nxsb_engine_search_begin_dev(self._h, C.byref(d), d_recs))
+
+    def search_end(self, handle: int, n: int = 0, k: int = 0, *, discard: bool = False):
+        """Wait for a submitted batch; returns (counts, ids, scores) unless discarded."""
+        if discard:
+            self._check(self._lib.nxsb_engine_search_end(self._h, handle, None, None, None))
+            return None
+        counts = np.zeros(n, dtype=np.uint32)
+        ids = np.zeros(max(n * k, 1), dtype=np.uint64)
+        scores = np.zeros(max(n * k, 1), dtype=np.float32)
+        self._check(self._lib.nxsb_engine_search_end(self._h, handle, counts.ctypes.data,
+                                                     ids.ctypes.data, scores.ctypes.data))
         return counts, ids[: n * k].reshape(n, k), scores[: n * k].reshape(n, k)
 
     def upload(self, batch: Batch) -> int:
