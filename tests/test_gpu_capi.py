@@ -306,3 +306,35 @@ def test_batch_begin_end_pipeline_equals_synchronous_calls(c1_corpus, c1_both):
         assert ours._lib.nxs_index_search_batch_end(bt, None) == 0
     c, i, s = ours.search_batch_arrays(batches[0], 10, **params)
     assert np.array_equal(i, want[0][1])
+
+
+def test_committed_reference_goldens_through_the_c_api(c1_corpus, c1_both):
+    """tests/golden/c1_reference.npz -- outputs of the compiled reference, made by
+    tests/golden/make_golden.py -- against nxs_index_search_batch /
+    nxs_index_search on the same C1 files.  Needs neither oracle/_ref nor
+    /root/reference.  TF-IDF scores are bit-equal; BM25 within 1e-5 relative;
+    documents may differ only inside the score group the limit cuts through."""
+    from _golden import Golden
+
+    ours, _ = c1_both
+    g = Golden()
+    g.check_corpus(c1_corpus)
+    for family, queries, limit in (("or", g.or_queries, 10), ("bool", g.bool_queries, 100)):
+        for name, key in (("BM25", "bm25"), ("TF-IDF", "tfidf")):
+            got = ours.search_batch(queries, limit=limit, algo=name, fuzzymatch=False)
+            same_ids = 0
+            for i, (q, res) in enumerate(zip(queries, got)):
+                ref = g.results(family, key, i)
+                same_results(res, ref)
+                if key == "tfidf":
+                    assert [np.float32(s) for _, s in res] == [np.float32(s) for _, s in ref], q
+                same_ids += sorted(d for d, _ in res) == sorted(d for d, _ in ref)
+            assert same_ids >= 0.9 * len(queries), (family, key, same_ids)
+    # fuzzy: a misspelt term alone must return exactly what the picked term returns
+    probes = [(q, p) for q, p in zip(g.fuzzy_queries, g.fuzzy_pick.tolist()) if p][:120]
+    got = ours.search_batch([q for q, _ in probes], limit=10, algo="TF-IDF", fuzzymatch=True)
+    want = ours.search_batch([c1_corpus.term(p) for _, p in probes], limit=10, algo="TF-IDF", fuzzymatch=False)
+    assert got == want
+    # ... and one the reference found nothing for stays empty
+    misses = [q for q, p in zip(g.fuzzy_queries, g.fuzzy_pick.tolist()) if not p][:20]
+    assert all(r == [] for r in ours.search_batch(misses, limit=10, algo="TF-IDF", fuzzymatch=True))

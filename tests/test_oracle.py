@@ -182,3 +182,28 @@ def test_port_fuzzy_equals_reference(c1_corpus, c1_oracle, ref_c1):
         assert got == ref_id, q
         hits += ref_id != 0
     assert hits > 700
+
+
+# ---------------------------------------------------------------------------
+# against the committed reference-made fixtures (no oracle/_ref needed)
+
+
+def test_port_equals_committed_reference_goldens(c1_corpus, c1_oracle):
+    """tests/golden/c1_reference.npz (made by tests/golden/make_golden.py from the
+    compiled reference): ids, float scores and order -- ties included -- equal."""
+    from _golden import Golden
+    from nxsearch_b200 import tools
+
+    g = Golden()
+    g.check_corpus(c1_corpus)
+    for family, queries, limit in (("or", g.or_queries, 10), ("bool", g.bool_queries, 100)):
+        for i, q in enumerate(queries):
+            leaves, prog = tools.query_compile(q)
+            toks = [c1_corpus_tid(c1_corpus, s) for s in leaves]
+            for algo, key in ((BM25, "bm25"), (TFIDF, "tfidf")):
+                ids, sc = c1_oracle.search(algo, limit, toks, prog)
+                assert list(zip(ids.tolist(), sc.tolist())) == g.results(family, key, i), (q, key)
+    for q, pick in zip(g.fuzzy_queries, g.fuzzy_pick.tolist()):
+        got, _, _, _ = c1_oracle.fuzzy(q)
+        assert got == pick, q
+    assert int((g.fuzzy_pick != 0).sum()) > 300
