@@ -89,6 +89,35 @@ typedef struct nxsb_shard_desc {
 /* Build (or rebuild) the HBM-resident CSR image of the shard. */
 int		nxsb_engine_load_shard(nxsb_engine_t *, const nxsb_shard_desc_t *);
 
+/*
+ * Incremental refresh of the image (the reference applies every
+ * appended dtmap block to its in-memory index on the next search,
+ * ref src/index/dtmap.c:357-441, src/query/search.c:309-310).  The image is
+ * the base shard plus up to NXSB_MAX_SEGMENTS delta segments on the same GPU:
+ *
+ * segment_add   builds the image of the documents appended since the last
+ *               build (same descriptor as load_shard; df[] -- whole-index
+ *               counts -- is required).  Returns the segment number >= 1.
+ * set_dead      ids (strictly ascending) removed from segment `segment`
+ *               (0 = the base shard) after it was built.  Searches ask every
+ *               segment for limit + (longest dead list) results and drop the
+ *               dead ones while merging, so results equal a full rebuild.
+ * segments_drop forgets all delta segments and all dead lists;
+ *               load_shard does the same.
+ * set_global_stats (below) reaches every segment; n_terms may exceed the
+ * vocabulary a segment was built with (term ids only grow).
+ *
+ * Searches on a segmented image go through nxsb_engine_search and
+ * nxsb_engine_search_begin/_begin_dev/_end; resident batches
+ * (batch_upload/_run) are refused.
+ */
+#define NXSB_MAX_SEGMENTS	8
+int		nxsb_engine_segment_add(nxsb_engine_t *, const nxsb_shard_desc_t *);
+int		nxsb_engine_segment_count(const nxsb_engine_t *);
+int		nxsb_engine_segments_drop(nxsb_engine_t *);
+int		nxsb_engine_set_dead(nxsb_engine_t *, uint32_t segment,
+		    const uint64_t *ids, uint32_t n);
+
 /* Shard-local df[t] for t in [0, n_terms) after a load (for the all-reduce). */
 int		nxsb_engine_get_df(nxsb_engine_t *, uint32_t *df, uint32_t n_terms);
 /* Replace the statistics the scores use (after a cross-shard all-reduce). */

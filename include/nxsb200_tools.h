@@ -142,6 +142,17 @@ int		nxsb_query_compile(const char *query, char *tokens_buf,
 uint64_t	nxsb_resp_collect(void *const *resps, size_t n, uint32_t stride,
 		    uint32_t *counts, uint64_t *ids, float *scores);
 
+/*
+ * How the HBM image of an open index (opaque pointer: nxs_index_t) reached its
+ * current state: out[0] full builds, out[1] delta segments added, out[2]
+ * consolidations of the delta segments, out[3] delta segments present now,
+ * out[4] removed documents noted against a segment, out[5] live documents,
+ * out[6] documents appended but not on the GPU yet.  (Incremental refresh,
+ * SURVEY 8f N1; the counterpart of the reference folding appended dtmap
+ * blocks into its in-memory index, ref src/index/dtmap.c:357-441.)
+ */
+void		nxsb_index_image_stats(const void *index, uint64_t out[7]);
+
 #pragma GCC visibility pop
 
 #ifdef __cplusplus

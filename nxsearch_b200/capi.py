@@ -140,6 +140,15 @@ class Index:
         if self._lib.nxs_index_remove(self.h, doc_id) != 0:
             self.nxs.raise_error()
 
+    def image_stats(self) -> dict:
+        """nxsb_index_image_stats: how the HBM image got to its current state."""
+        out = (C.c_uint64 * 7)()
+        self._lib.nxsb_index_image_stats.argtypes = [C.c_void_p, C.c_void_p]
+        self._lib.nxsb_index_image_stats.restype = None
+        self._lib.nxsb_index_image_stats(self.h, out)
+        keys = ("full_builds", "delta_builds", "consolidations", "segments", "dead_noted", "live", "pending")
+        return dict(zip(keys, (int(x) for x in out)))
+
     def params_json(self) -> dict:
         p = self._lib.nxs_index_get_params(self.h)
         return json.loads(_take_string(self._lib.nxs_params_tojson(p, None)))

@@ -179,6 +179,23 @@ struct nxsb_engine {
 	/* vocabulary (fuzzy) */
 	FuzzyImage	fz;
 
+	/*
+	 * Delta segments (incremental refresh): child engines on the same
+	 * device and stream, each holding the image of the documents added
+	 * since the previous build.  dead[g] = ids removed from segment g
+	 * (0 = this engine's own image) after it was built.
+	 */
+	std::vector<nxsb_engine *> segs;
+	std::vector<uint64_t> dead[NXSB_MAX_SEGMENTS + 1];
+	uint32_t	max_dead = 0, n_dead = 0;
+	unsigned long long *d_dead = nullptr;
+	uint32_t *	d_dead_off = nullptr;
+	struct SegRun {
+		Batch	own;		// this engine's image at limit + max_dead
+		DevBuf	gather;		// [segment][query][limit + max_dead] records
+	};
+	SegRun		seg_oneshot, seg_pipe[PIPE_DEPTH];
+
 	/* timing of the last run */
 	/*
 	 * A ring of per-run event sets, so that a caller can time many
@@ -266,7 +283,11 @@ nxsb_engine_prof(nxsb_engine_t *e, unsigned long long *out)
 extern "C" uint64_t
 nxsb_engine_launch_count(const nxsb_engine_t *e)
 {
-	return e->launches;
+	uint64_t n = e->launches;
+
+	for (const nxsb_engine *c : e->segs)
+		n += c->launches;
+	return n;
 }
 
 extern "C" nxsb_engine_t *
@@ -352,6 +373,8 @@ free_image(nxsb_engine_t *e)
 	e->loaded = false;
 }
 
+static void drop_segments(nxsb_engine_t *e);
+
 static void
 free_batch(Batch &b)
 {
@@ -363,6 +386,23 @@ free_batch(Batch &b)
 	b = Batch();
 }
 
+/* Forget the delta segments and every removal note (the stream is idle). */
+static void
+drop_segments(nxsb_engine_t *e)
+{
+	for (nxsb_engine *c : e->segs) {
+		e->launches += c->launches;
+		c->stream = c->own_stream;
+		nxsb_engine_destroy(c);
+	}
+	e->segs.clear();
+	for (auto &d : e->dead)
+		d.clear();
+	e->max_dead = e->n_dead = 0;
+	dev_free(e->d_dead);
+	dev_free(e->d_dead_off);
+}
+
 extern "C" void
 nxsb_engine_destroy(nxsb_engine_t *e)
 {
@@ -370,6 +410,13 @@ nxsb_engine_destroy(nxsb_engine_t *e)
 		return;
 	cudaSetDevice(e->device);
 	cudaStreamSynchronize(e->stream);
+	drop_segments(e);
+	free_batch(e->seg_oneshot.own);
+	e->seg_oneshot.gather.release();
+	for (auto &sr : e->seg_pipe) {
+		free_batch(sr.own);
+		sr.gather.release();
+	}
 	for (auto &b : e->batches)
 		if (b.used)
 			free_batch(b);
@@ -402,6 +449,8 @@ extern "C" int
 nxsb_engine_set_stream(nxsb_engine_t *e, void *s)
 {
 	e->stream = s ? (cudaStream_t)s : e->own_stream;
+	for (nxsb_engine *c : e->segs)
+		c->stream = e->stream;
 	return 0;
 }
 
@@ -471,6 +520,7 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 
 	CK(e, cudaSetDevice(e->device));
 	CK(e, cudaStreamSynchronize(e->stream));
+	drop_segments(e);
 	for (auto &b : e->batches)
 		if (b.used)
 			free_batch(b);
@@ -684,13 +734,101 @@ extern "C" int
 nxsb_engine_set_global_stats(nxsb_engine_t *e, const uint32_t *df,
     uint32_t n_terms, uint64_t token_count, uint32_t doc_count)
 {
-	if (!e->loaded || n_terms != e->n_terms)
+	/*
+	 * The vocabulary only grows: a segment built when it had fewer terms
+	 * takes the leading part of a longer table.
+	 */
+	if (!e->loaded || n_terms < e->n_terms)
 		return fail(e, "set_global_stats: no image or vocabulary size mismatch");
 	CK(e, cudaSetDevice(e->device));
-	e->h_df.assign(df, df + n_terms);
+	e->h_df.assign(df, df + e->n_terms);
 	e->token_count = token_count;
 	e->doc_count = doc_count;
-	return upload_stats(e);
+	if (upload_stats(e) == -1)
+		return -1;
+	for (nxsb_engine *c : e->segs)
+		if (nxsb_engine_set_global_stats(c, df, n_terms, token_count, doc_count) == -1)
+			return fail(e, "%s", c->err);
+	return 0;
+}
+
+/*
+ * Incremental refresh: delta segments and removal notes.
+ */
+
+extern "C" int
+nxsb_engine_segment_add(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
+{
+	if (!e->loaded)
+		return fail(e, "segment_add: no base image loaded");
+	if (e->segs.size() >= NXSB_MAX_SEGMENTS)
+		return fail(e, "segment_add: %d delta segments already", NXSB_MAX_SEGMENTS);
+	if (!sd->df)
+		return fail(e, "segment_add: whole-index df[] is required");
+	CK(e, cudaSetDevice(e->device));
+	CK(e, cudaStreamSynchronize(e->stream));
+
+	nxsb_engine *c = nxsb_engine_create(e->device);
+	if (!c)
+		return fail(e, "segment_add: %s", g_last_error);
+	c->stream = e->stream;
+	c->force_v2 = e->force_v2;
+	if (nxsb_engine_load_shard(c, sd) == -1) {
+		fail(e, "segment_add: %s", c->err);
+		c->stream = c->own_stream;
+		nxsb_engine_destroy(c);
+		return -1;
+	}
+	e->segs.push_back(c);
+	return (int)e->segs.size();
+}
+
+extern "C" int
+nxsb_engine_segment_count(const nxsb_engine_t *e)
+{
+	return (int)e->segs.size();
+}
+
+extern "C" int
+nxsb_engine_segments_drop(nxsb_engine_t *e)
+{
+	CK(e, cudaSetDevice(e->device));
+	CK(e, cudaStreamSynchronize(e->stream));
+	drop_segments(e);
+	return 0;
+}
+
+extern "C" int
+nxsb_engine_set_dead(nxsb_engine_t *e, uint32_t segment, const uint64_t *ids,
+    uint32_t n)
+{
+	if (!e->loaded || segment > e->segs.size())
+		return fail(e, "set_dead: no such segment %u", segment);
+	for (uint32_t i = 1; i < n; i++)
+		if (ids[i - 1] >= ids[i])
+			return fail(e, "set_dead: ids must be strictly ascending");
+	CK(e, cudaSetDevice(e->device));
+	CK(e, cudaStreamSynchronize(e->stream));
+	e->dead[segment].assign(ids, ids + n);
+
+	std::vector<unsigned long long> all;
+	uint32_t off[NXSB_MAX_SEGMENTS + 2] = { 0 };
+
+	e->max_dead = 0;
+	for (uint32_t g = 0; g <= NXSB_MAX_SEGMENTS; g++) {
+		off[g] = all.size();
+		all.insert(all.end(), e->dead[g].begin(), e->dead[g].end());
+		e->max_dead = std::max<uint32_t>(e->max_dead, e->dead[g].size());
+	}
+	off[NXSB_MAX_SEGMENTS + 1] = all.size();
+	e->n_dead = all.size();
+	dev_free(e->d_dead);
+	if (!e->d_dead_off)
+		CK(e, dev_alloc(&e->d_dead_off, NXSB_MAX_SEGMENTS + 2));
+	CK(e, dev_alloc(&e->d_dead, all.size()));
+	CK(e, cudaMemcpy(e->d_dead, all.data(), all.size() * 8, cudaMemcpyHostToDevice));
+	CK(e, cudaMemcpy(e->d_dead_off, off, sizeof(off), cudaMemcpyHostToDevice));
+	return 0;
 }
 
 /*
@@ -1242,11 +1380,86 @@ run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
 	return 0;
 }
 
+
+/*
+ * Search over a segmented image: every segment scores the batch at
+ * k_in = limit + max_dead (so that a segment's list still holds `limit` live
+ * documents after the removed ones are dropped), the lists are merged on the
+ * device.  B receives the final records (or d_out, if given) and counts;
+ * slot selects the children's pooled Batch (-1: the one-shot one).
+ */
+static inline bool
+segmented(const nxsb_engine_t *e)
+{
+	return !e->segs.empty() || e->n_dead != 0;
+}
+
+static int
+run_segmented(nxsb_engine_t *e, Batch &B, nxsb_engine::SegRun &S,
+    const nxsb_batch_t *b, Rec *d_out, int slot)
+{
+	const uint32_t n_segs = 1 + e->segs.size();
+	const uint64_t k_in64 = (uint64_t)b->limit + e->max_dead;
+	const uint32_t k_in = k_in64 > UINT32_MAX ? UINT32_MAX : (uint32_t)k_in64;
+	const size_t nq = std::max(b->n_queries, 1u);
+	const size_t stride = nq * k_in;
+	nxsb_batch_t b2 = *b;
+
+	/* Final buffers (and validation) at the caller's limit. */
+	if (fill_batch(e, B, b) == -1)
+		return -1;
+	b2.limit = k_in;
+	if (S.gather.ensure(stride * n_segs * sizeof(Rec)))
+		return fail(e, "device allocation failed for a %u-segment search "
+		    "(%u queries, limit %u)", n_segs, b->n_queries, k_in);
+	Rec *gather = (Rec *)S.gather.p;
+
+	if (fill_batch(e, S.own, &b2) == -1 || run_batch(e, S.own, gather) == -1)
+		return -1;
+	for (uint32_t i = 0; i < e->segs.size(); i++) {
+		nxsb_engine *c = e->segs[i];
+		Batch &CB = slot < 0 ? c->oneshot : c->pipe[slot];
+
+		c->stream = e->stream;
+		if (fill_batch(c, CB, &b2) == -1 ||
+		    run_batch(c, CB, gather + (size_t)(i + 1) * stride) == -1)
+			return fail(e, "segment %u: %s", i + 1, c->err);
+	}
+
+	cudaStream_t st = e->stream;
+	Rec *out = d_out ? d_out : B.d_recs;
+	const unsigned long long total = (unsigned long long)b->n_queries * n_segs * k_in;
+
+	if (d_out) {
+		CK(e, cudaMemsetAsync(d_out, 0, nq * b->limit * sizeof(Rec), st));
+		CK(e, cudaMemsetAsync(B.d_counts, 0, nq * 4, st));
+	} else {
+		CK(e, cudaMemsetAsync(B.results.p, 0, B.results_bytes, st));
+	}
+	if (total == 0)
+		return 0;
+	if (e->n_dead) {
+		const uint32_t lists = n_segs * b->n_queries;
+
+		drop_dead_kernel<<<(lists + 3) / 4, 128, 0, st>>>(gather, n_segs,
+		    b->n_queries, k_in, e->d_dead, e->d_dead_off);
+		e->launches++;
+	}
+	merge_segments_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gather,
+	    n_segs, b->n_queries, k_in, b->limit, out, B.d_counts);
+	e->launches++;
+	CK(e, cudaGetLastError());
+	return 0;
+}
+
 extern "C" int
 nxsb_engine_batch_run(nxsb_engine_t *e, int h, void *d_recs)
 {
 	if (h < 0 || h >= MAX_HANDLES || !e->batches[h].used)
 		return fail(e, "bad batch handle %d", h);
+	if (segmented(e))
+		return fail(e, "resident batches cannot run on a segmented image; "
+		    "use nxsb_engine_search / _search_begin");
 	CK(e, cudaSetDevice(e->device));
 	Batch &B = e->batches[h];
 	return run_batch(e, B, d_recs ? (Rec *)d_recs : B.d_recs);
@@ -1304,8 +1517,12 @@ nxsb_engine_search(nxsb_engine_t *e, const nxsb_batch_t *b, uint32_t *counts,
 	Batch &B = e->oneshot;
 
 	CK(e, cudaSetDevice(e->device));
-	if (fill_batch(e, B, b) == -1 || run_batch(e, B, B.d_recs) == -1)
+	if (segmented(e)) {
+		if (run_segmented(e, B, e->seg_oneshot, b, nullptr, -1) == -1)
+			return -1;
+	} else if (fill_batch(e, B, b) == -1 || run_batch(e, B, B.d_recs) == -1) {
 		return -1;
+	}
 	return fetch_results(e, B, counts, ids, scores);
 }
 
@@ -1332,9 +1549,14 @@ search_begin(nxsb_engine_t *e, const nxsb_batch_t *b, Rec *d_recs)
 		CK(e, cudaEventCreateWithFlags(&e->pipe_done[s], cudaEventDisableTiming));
 	Batch &B = e->pipe[s];
 
-	if (fill_batch(e, B, b) == -1 ||
-	    run_batch(e, B, d_recs ? d_recs : B.d_recs) == -1 ||
-	    (!d_recs && enqueue_fetch(e, B) == -1))
+	if (segmented(e)) {
+		if (run_segmented(e, B, e->seg_pipe[s], b, d_recs, s) == -1)
+			return -1;
+	} else if (fill_batch(e, B, b) == -1 ||
+	    run_batch(e, B, d_recs ? d_recs : B.d_recs) == -1) {
+		return -1;
+	}
+	if (!d_recs && enqueue_fetch(e, B) == -1)
 		return -1;
 	CK(e, cudaEventRecord(e->pipe_done[s], e->stream));
 	e->pipe_busy[s] = true;

@@ -318,4 +318,139 @@ merge_topk_kernel(const Rec *__restrict__ in, uint32_t n_shards,
 		out[(size_t)q * k + rank] = me;
 }
 
+/*
+ * Segmented image (incremental refresh).  The index image is a
+ * base segment plus a few delta segments on the same GPU; each scores the
+ * batch on its own and writes a list of k_in = limit + (removed documents a
+ * segment may still hold) records per query into in[g][q][.].  Segments do
+ * NOT hold ordered id ranges, so ties are ordered by the external id itself.
+ *
+ * drop_dead_kernel: one warp per (segment, query) list; removes, in place and
+ * keeping the order, the records whose document was deleted after the
+ * segment was built (dead[dead_off[g] .. dead_off[g+1]) ascending ids) and
+ * pads the tail with invalid records.
+ */
+__global__ void __launch_bounds__(128)
+drop_dead_kernel(Rec *__restrict__ recs, uint32_t n_segs, uint32_t n_queries,
+    uint32_t k_in, const unsigned long long *__restrict__ dead,
+    const uint32_t *__restrict__ dead_off)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t list = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+
+	if (list >= n_segs * n_queries)
+		return;
+	const uint32_t g = list / n_queries;
+	const uint32_t d0 = dead_off[g], d1 = dead_off[g + 1];
+
+	if (d0 == d1)
+		return;
+	Rec *lst = recs + (size_t)list * k_in;
+	uint32_t out = 0;
+
+	for (uint32_t base = 0; base < k_in; base += 32) {
+		const uint32_t r = base + lane;
+		Rec me = { 0, 0.f, 0 };
+		bool live = false;
+
+		if (r < k_in) {
+			me = lst[r];
+			live = me.valid != 0;
+		}
+		if (live) {
+			uint32_t lo = d0, hi = d1;
+
+			while (lo < hi) {
+				const uint32_t mid = (lo + hi) >> 1;
+				if (dead[mid] < me.doc_id)
+					lo = mid + 1;
+				else
+					hi = mid;
+			}
+			live = !(lo < d1 && dead[lo] == me.doc_id);
+		}
+		const uint32_t m = __ballot_sync(0xffffffffu, live);
+
+		/* Writes land at or below the chunk just read. */
+		__syncwarp();
+		if (live)
+			lst[out + __popc(m & ((1u << lane) - 1))] = me;
+		out += __popc(m);
+		__syncwarp();
+	}
+	for (uint32_t r = out + lane; r < k_in; r += 32)
+		lst[r] = Rec{ 0, 0.f, 0 };
+}
+
+__device__ __forceinline__ bool
+rec_precedes(const Rec &x, const Rec &me)
+{
+	return x.valid && (x.score > me.score ||
+	    (x.score == me.score && x.doc_id > me.doc_id));
+}
+
+/*
+ * merge_segments_kernel: one thread per (query, segment, position); a record's
+ * global rank is the number of records, in every list, that precede it in
+ * (score desc, id desc) order -- a binary search per list.  The k_out best go
+ * to out[q][rank]; counts[q] = min(k_out, live records).  `out` is
+ * pre-cleared by the caller.
+ */
+__global__ void __launch_bounds__(256)
+merge_segments_kernel(const Rec *__restrict__ in, uint32_t n_segs,
+    uint32_t n_queries, uint32_t k_in, uint32_t k_out, Rec *__restrict__ out,
+    uint32_t *__restrict__ counts)
+{
+	const unsigned long long total = (unsigned long long)n_queries * n_segs * k_in;
+	const unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (idx >= total)
+		return;
+	const uint32_t r = idx % k_in;
+	const uint32_t g = (idx / k_in) % n_segs;
+	const uint32_t q = idx / ((unsigned long long)k_in * n_segs);
+
+	if (r == 0 && g == 0) {
+		/* Live records of the query = valid prefix lengths, summed. */
+		unsigned long long n = 0;
+
+		for (uint32_t o = 0; o < n_segs; o++) {
+			const Rec *lst = in + ((size_t)o * n_queries + q) * k_in;
+			uint32_t lo = 0, hi = k_in;
+
+			while (lo < hi) {
+				const uint32_t mid = (lo + hi) >> 1;
+				if (lst[mid].valid)
+					lo = mid + 1;
+				else
+					hi = mid;
+			}
+			n += lo;
+		}
+		counts[q] = n < k_out ? (uint32_t)n : k_out;
+	}
+	const Rec me = in[((size_t)g * n_queries + q) * k_in + r];
+
+	if (!me.valid)
+		return;
+	uint32_t rank = r;
+	for (uint32_t o = 0; o < n_segs && rank < k_out; o++) {
+		if (o == g)
+			continue;
+		const Rec *lst = in + ((size_t)o * n_queries + q) * k_in;
+		uint32_t lo = 0, hi = k_in;
+
+		while (lo < hi) {
+			const uint32_t mid = (lo + hi) >> 1;
+			if (rec_precedes(lst[mid], me))
+				lo = mid + 1;
+			else
+				hi = mid;
+		}
+		rank += lo;
+	}
+	if (rank < k_out)
+		out[(size_t)q * k_out + rank] = me;
+}
+
 #endif

@@ -438,6 +438,16 @@ idx_dtmap_close(nxs_index_t *idx)
 	free(idx->doc_n);
 	free(idx->doc_blk);
 	free(idx->doc_dead);
+	free(idx->doc_seg);
+	free(idx->df);
+	idx->doc_seg = NULL;
+	idx->df = NULL;
+	idx->df_cap = 0;
+	for (unsigned g = 0; g <= NXSB_MAX_SEGMENTS; g++) {
+		free(idx->seg_dead[g]);
+		idx->seg_dead[g] = NULL;
+		idx->seg_ndead[g] = idx->seg_dead_cap[g] = 0;
+	}
 	idx->doc_ids = NULL;
 	idx->doc_len = idx->doc_n = NULL;
 	idx->doc_blk = NULL;
@@ -455,6 +465,39 @@ uint32_t
 idx_get_doc_count(const nxs_index_t *idx)
 {
 	return load_acquire32(idx->dfile.base + 24);
+}
+
+/* df[] covers every known term (new terms start at zero). */
+static int
+df_reserve(nxs_index_t *idx)
+{
+	if (idx->n_terms > idx->df_cap) {
+		uint32_t ncap = idx->df_cap ? idx->df_cap : 1024;
+		uint32_t *p;
+
+		while (ncap < idx->n_terms)
+			ncap *= 2;
+		if ((p = realloc(idx->df, sizeof(uint32_t) * ncap)) == NULL)
+			return -1;
+		memset(p + idx->df_cap, 0, sizeof(uint32_t) * (ncap - idx->df_cap));
+		idx->df = p;
+		idx->df_cap = ncap;
+	}
+	return 0;
+}
+
+/* Add (+1) or retire (-1) the terms of the block at file offset blk in df[]. */
+static void
+df_apply(nxs_index_t *idx, uint64_t blk, uint32_t n, int sign)
+{
+	const uint8_t *p = idx->dfile.base + blk + 16;
+
+	for (uint32_t j = 0; j < n; j++) {
+		const uint32_t t = be_get32(p + (size_t)j * 8);
+
+		if (t >= 1 && t <= idx->n_terms)
+			idx->df[t - 1] += sign;
+	}
 }
 
 static int
@@ -476,9 +519,12 @@ doc_register(nxs_index_t *idx, uint64_t id, uint32_t len, uint32_t n,
 		GROW(doc_n, uint32_t)
 		GROW(doc_blk, uint64_t)
 		GROW(doc_dead, uint8_t)
+		GROW(doc_seg, uint8_t)
 #undef GROW
 		idx->slots_cap = ncap;
 	}
+	if (df_reserve(idx) == -1)
+		return -1;
 	if (u64map_put(idx->doc_map, id, slot, NULL) != 1) {
 		errno = EEXIST;
 		return -1;
@@ -488,9 +534,13 @@ doc_register(nxs_index_t *idx, uint64_t id, uint32_t len, uint32_t n,
 	idx->doc_n[slot] = n;
 	idx->doc_blk[slot] = blk;
 	idx->doc_dead[slot] = 0;
+	idx->doc_seg[slot] = 0;
 	idx->n_slots++;
 	idx->n_live++;
-	idx->image_dirty = true;
+	df_apply(idx, blk, n, +1);
+	/* Not on the GPU yet: the next search adds a delta segment. */
+	idx->n_pending++;
+	idx->stats_dirty = true;
 	return 0;
 }
 
@@ -499,11 +549,34 @@ doc_unregister(nxs_index_t *idx, uint64_t id)
 {
 	uint32_t slot;
 
-	if (u64map_get(idx->doc_map, id, &slot)) {
-		u64map_del(idx->doc_map, id);
-		idx->doc_dead[slot] = 1;
-		idx->n_live--;
-		idx->image_dirty = true;
+	if (!u64map_get(idx->doc_map, id, &slot))
+		return;
+	u64map_del(idx->doc_map, id);
+	idx->doc_dead[slot] = 1;
+	idx->n_live--;
+	/* Only the id of a removed block is cleared; its terms stay readable. */
+	df_apply(idx, idx->doc_blk[slot], idx->doc_n[slot], -1);
+	idx->stats_dirty = true;
+	if (slot >= idx->built_slots) {
+		idx->n_pending--;
+	} else {
+		/* In the image: note it against the segment that holds it. */
+		const uint32_t g = idx->doc_seg[slot];
+
+		if (idx->seg_ndead[g] == idx->seg_dead_cap[g]) {
+			const uint32_t ncap = idx->seg_dead_cap[g] ? idx->seg_dead_cap[g] * 2 : 16;
+			uint64_t *p = realloc(idx->seg_dead[g], sizeof(uint64_t) * ncap);
+
+			if (p == NULL) {
+				idx->image_dirty = true;	/* fall back to a rebuild */
+				return;
+			}
+			idx->seg_dead[g] = p;
+			idx->seg_dead_cap[g] = ncap;
+		}
+		idx->seg_dead[g][idx->seg_ndead[g]++] = id;
+		idx->seg_dead_dirty[g] = true;
+		idx->seg_live[g]--;
 	}
 }
 
@@ -700,7 +773,27 @@ out:
  * GPU image.  Live documents are handed to the engine in ascending id order
  * -- the order the reference's roaring64 iteration visits them in
  * (search.c:235) and the basis of its tie behaviour.
+ *
+ * The reference folds every appended block into its in-memory index on the
+ * next search (dtmap.c:357-441).  Here the index lives in HBM in term-major
+ * form, which cannot be appended to in place, so the image is kept as a base
+ * segment plus a few small delta segments:
+ *
+ *   - documents appended since the last build become a new delta segment;
+ *   - a removed document stays in its segment and is listed as dead; every
+ *     segment is then asked for limit + (dead documents) results and the
+ *     dead ones are dropped while the per-segment lists are merged;
+ *   - df[], N and the token count are whole-index values held on the host
+ *     and re-sent when they move, so scores equal those of a rebuilt image;
+ *   - when the delta segments run out (NXSB_MAX_SEGMENTS) or one collects
+ *     too many dead documents they are consolidated into one; when the
+ *     deltas outgrow a fraction of the base, or the base collects too many
+ *     dead documents, everything is rebuilt.
  */
+
+#define SEG_DEAD_MAX		64	/* limit + this stays on the fast kernel path */
+#define DELTA_DOCS_MIN		65536	/* deltas smaller than this never force a rebuild */
+#define DELTA_BASE_FRACTION	8	/* ... nor while below base / 8 */
 
 typedef struct { uint64_t id; uint32_t slot; } idslot_t;
 
@@ -711,30 +804,46 @@ idslot_cmp(const void *a, const void *b)
 	return (x->id > y->id) - (x->id < y->id);
 }
 
-static int
-build_image(nxs_index_t *idx)
-{
-	const uint32_t n = idx->n_live;
-	idslot_t *order = malloc(sizeof(idslot_t) * ((size_t)n + 1));
-	uint64_t *ids = malloc(sizeof(uint64_t) * ((size_t)n + 1));
-	uint32_t *lens = malloc(sizeof(uint32_t) * ((size_t)n + 1));
-	uint64_t *offs = malloc(sizeof(uint64_t) * ((size_t)n + 1));
-	uint32_t *pairs = NULL;
-	uint64_t np = 0;
-	uint32_t k = 0;
-	bool sorted = true;
-	int ret = -1;
+enum { PICK_ALL, PICK_DELTAS, PICK_PENDING };
 
+/*
+ * Hand the live documents selected by `pick` to the engine as segment `seg`
+ * (0: nxsb_engine_load_shard, else nxsb_engine_segment_add).  Returns the
+ * number of documents, or -1.
+ */
+static int64_t
+build_segment(nxs_index_t *idx, int pick, uint32_t seg)
+{
+	const uint32_t first = pick == PICK_PENDING ? idx->built_slots : 0;
+	idslot_t *order = NULL;
+	uint64_t *ids = NULL, *offs = NULL;
+	uint32_t *lens = NULL, *pairs = NULL;
+	uint64_t np = 0;
+	uint32_t n = 0, k = 0;
+	bool sorted = true;
+	int64_t ret = -1;
+
+#define PICKED(s) (!idx->doc_dead[s] && (pick != PICK_DELTAS || \
+	(s) >= idx->built_slots || idx->doc_seg[s] != 0))
+	for (uint32_t s = first; s < idx->n_slots; s++)
+		n += PICKED(s);
+	if (n == 0 && seg != 0)
+		return 0;
+	order = malloc(sizeof(idslot_t) * ((size_t)n + 1));
+	ids = malloc(sizeof(uint64_t) * ((size_t)n + 1));
+	lens = malloc(sizeof(uint32_t) * ((size_t)n + 1));
+	offs = malloc(sizeof(uint64_t) * ((size_t)n + 1));
 	if (!order || !ids || !lens || !offs)
 		goto out;
-	for (uint32_t s = 0; s < idx->n_slots; s++) {
-		if (idx->doc_dead[s])
+	for (uint32_t s = first; s < idx->n_slots; s++) {
+		if (!PICKED(s))
 			continue;
 		if (k && idx->doc_ids[s] < order[k - 1].id)
 			sorted = false;
 		order[k++] = (idslot_t){ idx->doc_ids[s], s };
 		np += idx->doc_n[s];
 	}
+#undef PICKED
 	if (!sorted)
 		qsort(order, n, sizeof(idslot_t), idslot_cmp);
 	if ((pairs = malloc(np * 8 + 8)) == NULL)
@@ -761,15 +870,18 @@ build_image(nxs_index_t *idx)
 		/* The header counters are what ranking reads (ranking.c:77,163). */
 		.token_count = idx_get_token_count(idx),
 		.doc_count = idx_get_doc_count(idx),
-		.df = NULL,
+		.df = idx->df,
 	};
-	if (nxsb_engine_load_shard(idx->engine, &sd) == -1) {
+	if ((seg == 0 ? nxsb_engine_load_shard(idx->engine, &sd) :
+	    nxsb_engine_segment_add(idx->engine, &sd)) == -1) {
 		nxs_set_error(idx->nxs, NXS_ERR_SYSTEM, "GPU index image build failed: %s",
 		    nxsb_engine_errmsg(idx->engine));
 		goto out;
 	}
-	idx->image_dirty = false;
-	ret = 0;
+	for (uint32_t i = 0; i < n; i++)
+		idx->doc_seg[order[i].slot] = (uint8_t)seg;
+	idx->seg_live[seg] = n;
+	ret = n;
 out:
 	free(order);
 	free(ids);
@@ -777,6 +889,115 @@ out:
 	free(offs);
 	free(pairs);
 	return ret;
+}
+
+static void
+seg_dead_reset(nxs_index_t *idx, uint32_t from)
+{
+	for (uint32_t g = from; g <= NXSB_MAX_SEGMENTS; g++) {
+		idx->seg_ndead[g] = 0;
+		idx->seg_dead_dirty[g] = false;
+		if (g)
+			idx->seg_live[g] = 0;
+	}
+}
+
+static int
+u64_cmp(const void *a, const void *b)
+{
+	const uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+	return (x > y) - (x < y);
+}
+
+/* Bring the HBM image in line with what the files say now. */
+static int
+refresh_image(nxs_index_t *idx)
+{
+	uint64_t delta_docs = idx->n_pending;
+	bool consolidate = false;
+
+	if (df_reserve(idx) == -1) {
+		nxs_set_syserror(idx->nxs, NXS_ERR_SYSTEM, "out of memory");
+		return -1;
+	}
+	for (uint32_t g = 1; g <= idx->n_segs; g++) {
+		delta_docs += idx->seg_live[g];
+		consolidate |= idx->seg_ndead[g] > SEG_DEAD_MAX;
+	}
+	consolidate |= idx->n_pending && idx->n_segs == NXSB_MAX_SEGMENTS;
+	if (idx->seg_ndead[0] > SEG_DEAD_MAX || (delta_docs > DELTA_DOCS_MIN &&
+	    delta_docs > idx->seg_live[0] / DELTA_BASE_FRACTION) ||
+	    getenv("NXSB_REFRESH_FULL") != NULL)
+		idx->image_dirty |= idx->n_pending || idx->stats_dirty;
+
+	if (idx->image_dirty) {
+		seg_dead_reset(idx, 0);
+		if (build_segment(idx, PICK_ALL, 0) == -1)
+			return -1;
+		idx->n_segs = 0;
+		idx->n_full_builds++;
+		idx->image_dirty = idx->stats_dirty = false;
+	} else if (consolidate) {
+		int64_t n;
+
+		if (nxsb_engine_segments_drop(idx->engine) == -1)
+			goto fail;
+		seg_dead_reset(idx, 1);
+		idx->seg_dead_dirty[0] = idx->seg_ndead[0] != 0;
+		if ((n = build_segment(idx, PICK_DELTAS, 1)) == -1) {
+			idx->image_dirty = true;
+			return -1;
+		}
+		idx->n_segs = n ? 1 : 0;
+		idx->n_consolidations++;
+	} else if (idx->n_pending) {
+		if (build_segment(idx, PICK_PENDING, idx->n_segs + 1) == -1)
+			return -1;
+		idx->n_segs++;
+		idx->n_delta_builds++;
+	}
+	idx->built_slots = idx->n_slots;
+	idx->n_pending = 0;
+
+	for (uint32_t g = 0; g <= idx->n_segs; g++) {
+		if (!idx->seg_dead_dirty[g])
+			continue;
+		qsort(idx->seg_dead[g], idx->seg_ndead[g], sizeof(uint64_t), u64_cmp);
+		if (nxsb_engine_set_dead(idx->engine, g, idx->seg_dead[g],
+		    idx->seg_ndead[g]) == -1)
+			goto fail;
+		idx->seg_dead_dirty[g] = false;
+	}
+	if (idx->stats_dirty) {
+		if (nxsb_engine_set_global_stats(idx->engine, idx->df, idx->n_terms,
+		    idx_get_token_count(idx), idx_get_doc_count(idx)) == -1)
+			goto fail;
+		idx->stats_dirty = false;
+	}
+	return 0;
+fail:
+	nxs_set_error(idx->nxs, NXS_ERR_SYSTEM, "GPU index image refresh failed: %s",
+	    nxsb_engine_errmsg(idx->engine));
+	idx->image_dirty = true;
+	return -1;
+}
+
+/* include/nxsb200_tools.h */
+NXS_API void
+nxsb_index_image_stats(const void *index, uint64_t out[7])
+{
+	const nxs_index_t *idx = index;
+	uint64_t dead = 0;
+
+	for (uint32_t g = 0; g <= idx->n_segs; g++)
+		dead += idx->seg_ndead[g];
+	out[0] = idx->n_full_builds;
+	out[1] = idx->n_delta_builds;
+	out[2] = idx->n_consolidations;
+	out[3] = idx->n_segs;
+	out[4] = dead;
+	out[5] = idx->n_live;
+	out[6] = idx->n_pending;
 }
 
 static int
@@ -821,7 +1042,8 @@ idx_gpu_prepare(nxs_index_t *idx, bool need_vocab)
 		idx->image_dirty = true;
 		idx->vocab_dirty = true;
 	}
-	if (idx->image_dirty && build_image(idx) == -1)
+	if ((idx->image_dirty || idx->n_pending || idx->stats_dirty) &&
+	    refresh_image(idx) == -1)
 		return -1;
 	if (need_vocab && idx->vocab_dirty && idx->n_terms && build_vocab(idx) == -1)
 		return -1;

@@ -61,11 +61,35 @@ struct nxs_index {
 	uint64_t *		doc_blk;	/* file offset of the block */
 	uint8_t *		doc_dead;
 	uint32_t		n_slots, slots_cap, n_live;
+	/*
+	 * Live documents per term -- what the cardinality of a term's roaring
+	 * bitmap is to the reference (ranking.c:78,150) -- kept current as
+	 * blocks and deletion markers are consumed.
+	 */
+	uint32_t *		df;
+	uint32_t		df_cap;
 
-	/* GPU side. */
+	/*
+	 * GPU side.  The image is a base segment (0) plus delta segments
+	 * (1..n_segs) holding what was appended since; documents removed
+	 * after their segment was built are listed per segment and dropped
+	 * when the per-segment results are merged (index.c "GPU image").
+	 */
 	nxsb_engine_t *		engine;
-	bool			image_dirty;
+	bool			image_dirty;	/* nothing usable on the GPU: build it all */
+	bool			stats_dirty;	/* df[] / header counters moved */
 	bool			vocab_dirty;
+	uint8_t *		doc_seg;	/* per slot; valid below built_slots */
+	uint32_t		built_slots;	/* slots the image knows of */
+	uint32_t		n_pending;	/* live slots at or above built_slots */
+	uint32_t		n_segs;
+	uint32_t		seg_live[NXSB_MAX_SEGMENTS + 1];
+	uint64_t *		seg_dead[NXSB_MAX_SEGMENTS + 1];
+	uint32_t		seg_ndead[NXSB_MAX_SEGMENTS + 1];
+	uint32_t		seg_dead_cap[NXSB_MAX_SEGMENTS + 1];
+	bool			seg_dead_dirty[NXSB_MAX_SEGMENTS + 1];
+	/* How the image got to its current state (nxsb_index_image_stats). */
+	uint64_t		n_full_builds, n_delta_builds, n_consolidations;
 	bkmirror_t		bk;
 };
 

@@ -46,6 +46,10 @@ def _bind():
         "nxsb_engine_errmsg": (C.c_char_p, [vp]),
         "nxsb_engine_set_stream": (i, [vp, vp]),
         "nxsb_engine_load_shard": (i, [vp, C.POINTER(ShardDesc)]),
+        "nxsb_engine_segment_add": (i, [vp, C.POINTER(ShardDesc)]),
+        "nxsb_engine_segment_count": (i, [vp]),
+        "nxsb_engine_segments_drop": (i, [vp]),
+        "nxsb_engine_set_dead": (i, [vp, u32, vp, u32]),
         "nxsb_engine_get_df": (i, [vp, vp, u32]),
         "nxsb_engine_set_global_stats": (i, [vp, vp, u32, u64, u32]),
         "nxsb_engine_search": (i, [vp, C.POINTER(BatchDesc), vp, vp, vp]),
@@ -132,22 +136,44 @@ class Engine:
         self._check(self._lib.nxsb_engine_set_stream(self._h, cuda_stream))
 
     def load_corpus(self, corpus, *, lo: int = 0, hi: int | None = None, df=None,
-                    token_count: int | None = None, doc_count: int | None = None) -> None:
-        """Load documents [lo, hi) of a tools.Corpus (ids must ascend) as this shard."""
+                    token_count: int | None = None, doc_count: int | None = None,
+                    segment: bool = False) -> None:
+        """Load documents [lo, hi) of a tools.Corpus (ids must ascend) as this shard,
+        or -- segment=True -- as a delta segment next to the image already loaded."""
         hi = corpus.n_docs if hi is None else hi
-        doc_off = np.ascontiguousarray(corpus.doc_off[lo:hi + 1] - corpus.doc_off[lo], dtype=np.uint64)
+        doc_off = corpus.doc_off[lo:hi + 1] - corpus.doc_off[lo]
         base = int(corpus.doc_off[lo])
         pairs = corpus.pairs[2 * base: 2 * int(corpus.doc_off[hi])]
-        ids = np.ascontiguousarray(corpus.doc_ids[lo:hi])
-        lens = np.ascontiguousarray(corpus.doc_len[lo:hi])
-        pairs = np.ascontiguousarray(pairs)
-        dfa = None if df is None else np.ascontiguousarray(df, dtype=np.uint32)
-        sd = ShardDesc(hi - lo, corpus.n_terms, ids.ctypes.data, lens.ctypes.data,
-                       doc_off.ctypes.data, pairs.ctypes.data,
+        self.load_docs(corpus.doc_ids[lo:hi], corpus.doc_len[lo:hi], doc_off, pairs, corpus.n_terms,
                        corpus.token_count if token_count is None else token_count,
-                       corpus.doc_count if doc_count is None else doc_count,
+                       corpus.doc_count if doc_count is None else doc_count, df, segment=segment)
+
+    def load_docs(self, ids, lens, doc_off, pairs, n_terms: int, token_count: int, doc_count: int,
+                  df=None, *, segment: bool = False) -> None:
+        """Load a document-major shard given as arrays (nxsb_shard_desc_t); ids ascending."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        doc_off = np.ascontiguousarray(doc_off, dtype=np.uint64)
+        pairs = np.ascontiguousarray(pairs, dtype=np.uint32)
+        dfa = None if df is None else np.ascontiguousarray(df, dtype=np.uint32)
+        sd = ShardDesc(len(ids), n_terms, ids.ctypes.data, lens.ctypes.data,
+                       doc_off.ctypes.data, pairs.ctypes.data, token_count, doc_count,
                        None if dfa is None else dfa.ctypes.data)
-        self._check(self._lib.nxsb_engine_load_shard(self._h, C.byref(sd)))
+        if segment:
+            self._check(self._lib.nxsb_engine_segment_add(self._h, C.byref(sd)))
+        else:
+            self._check(self._lib.nxsb_engine_load_shard(self._h, C.byref(sd)))
+
+    def segment_count(self) -> int:
+        return self._lib.nxsb_engine_segment_count(self._h)
+
+    def segments_drop(self) -> None:
+        self._check(self._lib.nxsb_engine_segments_drop(self._h))
+
+    def set_dead(self, segment: int, ids) -> None:
+        """Ids removed from a segment (0 = base) after it was built."""
+        ids = np.ascontiguousarray(sorted(int(x) for x in ids), dtype=np.uint64)
+        self._check(self._lib.nxsb_engine_set_dead(self._h, segment, ids.ctypes.data, len(ids)))
 
     def get_df(self, n_terms: int) -> np.ndarray:
         df = np.zeros(n_terms, dtype=np.uint32)
