@@ -73,6 +73,13 @@ int		nxsb_engine_set_stream(nxsb_engine_t *, void *cuda_stream);
  * are WHOLE-INDEX statistics: BM25 and TF-IDF use the global N, df and
  * average length (ref ranking.c:77-78,149-150,163), so a shard must not
  * substitute its own.  df may be NULL when the shard is the whole index.
+ *
+ * Instead of pairs/doc_off the shard may be given as the bytes of the
+ * `nxsdtmap` file itself: raw points at host memory holding
+ * the file (or any part of it), and document i's raw_n[i] big-endian
+ * (term id u32, count u32) pairs start at raw + raw_off[i] (ref
+ * src/index/storage.h:80-84; raw_off[i] is a multiple of 8).  The bytes are
+ * copied to the device as they are and decoded there.
  */
 typedef struct nxsb_shard_desc {
 	uint32_t		n_docs;
@@ -84,6 +91,9 @@ typedef struct nxsb_shard_desc {
 	uint64_t		token_count;
 	uint32_t		doc_count;
 	const uint32_t *	df;
+	const void *		raw;		/* NULL: use pairs / doc_off */
+	const uint64_t *	raw_off;
+	const uint32_t *	raw_n;
 } nxsb_shard_desc_t;
 
 /* Build (or rebuild) the HBM-resident CSR image of the shard. */

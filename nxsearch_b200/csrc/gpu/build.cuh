@@ -45,6 +45,71 @@ expand_pairs_kernel(const uint2 *__restrict__ pairs,
 }
 
 /*
+ * The same straight from the bytes of an `nxsdtmap` file: the
+ * (term id, count) pairs of document d are doc_off[d+1] - doc_off[d]
+ * big-endian u32 pairs at raw + raw_off[d] (ref src/index/storage.h:80-84,
+ * 8-byte aligned: 32-byte header, 16-byte block header, 8-byte pairs), so the
+ * host never converts or copies a posting.
+ */
+__device__ __forceinline__ uint32_t
+be32(uint32_t v)
+{
+	return __byte_perm(v, 0, 0x0123);
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(256)
+expand_raw_kernel(const unsigned char *__restrict__ raw,
+    const unsigned long long *__restrict__ raw_off,
+    const unsigned long long *__restrict__ doc_off,
+    const uint32_t *__restrict__ doc_len, uint32_t n_docs, uint32_t n_terms,
+    uint32_t *__restrict__ keys, uint2 *__restrict__ vals)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+	uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+
+	for (; d < n_docs; d += warps_per_grid) {
+		const unsigned long long s = doc_off[d];
+		const uint32_t n = (uint32_t)(doc_off[d + 1] - s);
+		const uint2 *src = reinterpret_cast<const uint2 *>(raw + raw_off[d]);
+		const uint32_t dl = doc_len[d];
+
+		for (uint32_t i = lane; i < n; i += 32) {
+			const uint2 p = src[i];
+			const uint32_t t = be32(p.x) - 1, c = be32(p.y);
+
+			keys[s + i] = t < n_terms ? t : n_terms;
+			vals[s + i] = make_uint2(d, WIDE ? c : (c | (dl << 16)));
+		}
+	}
+}
+
+/* Largest count in the raw blocks (decides packed vs wide postings). */
+__global__ void __launch_bounds__(256)
+raw_max_count_kernel(const unsigned char *__restrict__ raw,
+    const unsigned long long *__restrict__ raw_off,
+    const unsigned long long *__restrict__ doc_off, uint32_t n_docs,
+    uint32_t *__restrict__ max_count)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t warps_per_grid = (gridDim.x * blockDim.x) >> 5;
+	uint32_t d = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	uint32_t m = 0;
+
+	for (; d < n_docs; d += warps_per_grid) {
+		const uint32_t n = (uint32_t)(doc_off[d + 1] - doc_off[d]);
+		const uint2 *src = reinterpret_cast<const uint2 *>(raw + raw_off[d]);
+
+		for (uint32_t i = lane; i < n; i += 32)
+			m = max(m, be32(src[i].y));
+	}
+	m = __reduce_max_sync(0xffffffffu, m);
+	if (lane == 0 && m > 0xffffu)
+		atomicMax(max_count, m);
+}
+
+/*
  * CSR offsets from the sorted keys: off[t] = first j with keys[j] >= t.
  * Thread j owns the (possibly empty) run of terms (keys[j-1], keys[j]].
  */

@@ -512,11 +512,38 @@ extern "C" int
 nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 {
 	const uint32_t N = sd->n_docs, V = sd->n_terms;
-	const uint64_t P = sd->doc_off ? sd->doc_off[N] : 0;
+	const bool raw = sd->raw != nullptr;
+	std::vector<uint64_t> raw_doc_off, raw_rel;
+	uint64_t raw_lo = 0, raw_hi = 0;
 	uint2 *d_pairs = nullptr, *d_vals_alt = nullptr;
-	unsigned long long *d_doc_off = nullptr;
+	unsigned char *d_raw = nullptr;
+	unsigned long long *d_doc_off = nullptr, *d_raw_off = nullptr;
 	uint32_t *d_keys = nullptr, *d_keys_alt = nullptr, *d_long = nullptr;
+	uint32_t *d_maxc = nullptr;
 	int rc = -1;
+
+	if (raw) {
+		/* Offsets of the decoded pairs, and the byte range to copy. */
+		raw_doc_off.resize((size_t)N + 1);
+		raw_rel.resize((size_t)N + 1);
+		raw_lo = N ? UINT64_MAX : 0;
+		uint64_t acc = 0;
+		for (uint32_t d = 0; d < N; d++) {
+			raw_doc_off[d] = acc;
+			acc += sd->raw_n[d];
+			if (sd->raw_off[d] & 7)
+				return fail(e, "load_shard: raw_off[%u] is not 8-byte aligned", d);
+			raw_lo = std::min<uint64_t>(raw_lo, sd->raw_off[d]);
+			raw_hi = std::max<uint64_t>(raw_hi, sd->raw_off[d] + 8ull * sd->raw_n[d]);
+		}
+		raw_doc_off[N] = acc;
+		if (raw_hi < raw_lo)
+			raw_hi = raw_lo;
+		for (uint32_t d = 0; d < N; d++)
+			raw_rel[d] = sd->raw_off[d] - raw_lo;
+	}
+	const uint64_t P = raw ? raw_doc_off[N] : (sd->doc_off ? sd->doc_off[N] : 0);
+	const uint64_t *h_doc_off = raw ? raw_doc_off.data() : sd->doc_off;
 
 	CK(e, cudaSetDevice(e->device));
 	CK(e, cudaStreamSynchronize(e->stream));
@@ -539,11 +566,13 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 	e->wide = false;
 	for (uint32_t d = 0; d < N && !e->wide; d++)
 		e->wide = sd->doc_len[d] > 0xffffu;
-	for (uint64_t j = 0; j < P && !e->wide; j++)
+	for (uint64_t j = 0; !raw && j < P && !e->wide; j++)
 		e->wide = sd->pairs[2 * j + 1] > 0xffffu;
 
 	do {
-		if (dev_alloc(&d_pairs, P) || dev_alloc(&d_doc_off, (size_t)N + 1) ||
+		if ((raw ? (dev_alloc(&d_raw, raw_hi - raw_lo + 8) ||
+		    dev_alloc(&d_raw_off, (size_t)N + 1) || dev_alloc(&d_maxc, 1))
+		    : dev_alloc(&d_pairs, P)) || dev_alloc(&d_doc_off, (size_t)N + 1) ||
 		    dev_alloc(&e->d_doc_len, N) || dev_alloc(&e->d_doc_ids, N) ||
 		    dev_alloc(&d_keys, P) || dev_alloc(&d_keys_alt, P) ||
 		    dev_alloc(&e->d_post, P + 2) || dev_alloc(&d_vals_alt, P + 2) ||
@@ -556,8 +585,11 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 			break;
 		}
 		cudaStream_t st = e->stream;
-		if (cudaMemcpyAsync(d_pairs, sd->pairs, P * 8, cudaMemcpyHostToDevice, st) ||
-		    cudaMemcpyAsync(d_doc_off, sd->doc_off, ((size_t)N + 1) * 8, cudaMemcpyHostToDevice, st) ||
+		if ((raw ? (cudaMemcpyAsync(d_raw, (const char *)sd->raw + raw_lo, raw_hi - raw_lo, cudaMemcpyHostToDevice, st) ||
+		    cudaMemcpyAsync(d_raw_off, raw_rel.data(), (size_t)N * 8, cudaMemcpyHostToDevice, st) ||
+		    cudaMemsetAsync(d_maxc, 0, 4, st))
+		    : cudaMemcpyAsync(d_pairs, sd->pairs, P * 8, cudaMemcpyHostToDevice, st)) ||
+		    cudaMemcpyAsync(d_doc_off, h_doc_off, ((size_t)N + 1) * 8, cudaMemcpyHostToDevice, st) ||
 		    cudaMemcpyAsync(e->d_doc_len, sd->doc_len, (size_t)N * 4, cudaMemcpyHostToDevice, st) ||
 		    cudaMemcpyAsync(e->d_doc_ids, sd->doc_ids, (size_t)N * 8, cudaMemcpyHostToDevice, st)) {
 			fail(e, "H2D copy failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -566,7 +598,27 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 
 		if (N) {
 			const int grid = e->n_sms * 8;
-			if (e->wide)
+			if (raw && !e->wide) {
+				uint32_t maxc = 0;
+
+				raw_max_count_kernel<<<grid, 256, 0, st>>>(d_raw, d_raw_off,
+				    d_doc_off, N, d_maxc);
+				e->launches++;
+				if (cudaMemcpyAsync(&maxc, d_maxc, 4, cudaMemcpyDeviceToHost, st) ||
+				    cudaStreamSynchronize(st)) {
+					fail(e, "raw block scan failed: %s",
+					    cudaGetErrorString(cudaGetLastError()));
+					break;
+				}
+				e->wide = maxc > 0xffffu;
+			}
+			if (raw && e->wide)
+				expand_raw_kernel<true><<<grid, 256, 0, st>>>(d_raw, d_raw_off,
+				    d_doc_off, e->d_doc_len, N, V, d_keys, d_vals_alt);
+			else if (raw)
+				expand_raw_kernel<false><<<grid, 256, 0, st>>>(d_raw, d_raw_off,
+				    d_doc_off, e->d_doc_len, N, V, d_keys, d_vals_alt);
+			else if (e->wide)
 				expand_pairs_kernel<true><<<grid, 256, 0, st>>>(d_pairs,
 				    d_doc_off, e->d_doc_len, N, V, d_keys, d_vals_alt);
 			else
@@ -711,6 +763,9 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 	} while (0);
 
 	dev_free(d_pairs);
+	dev_free(d_raw);
+	dev_free(d_raw_off);
+	dev_free(d_maxc);
 	dev_free(d_doc_off);
 	dev_free(d_keys);
 	dev_free(d_keys_alt);

@@ -817,7 +817,8 @@ build_segment(nxs_index_t *idx, int pick, uint32_t seg)
 	const uint32_t first = pick == PICK_PENDING ? idx->built_slots : 0;
 	idslot_t *order = NULL;
 	uint64_t *ids = NULL, *offs = NULL;
-	uint32_t *lens = NULL, *pairs = NULL;
+	uint32_t *lens = NULL, *pairs = NULL, *raw_n = NULL;
+	const bool host_pairs = getenv("NXSB_IMAGE_HOST_PAIRS") != NULL;
 	uint64_t np = 0;
 	uint32_t n = 0, k = 0;
 	bool sorted = true;
@@ -846,8 +847,18 @@ build_segment(nxs_index_t *idx, int pick, uint32_t seg)
 #undef PICKED
 	if (!sorted)
 		qsort(order, n, sizeof(idslot_t), idslot_cmp);
-	if ((pairs = malloc(np * 8 + 8)) == NULL)
+	/*
+	 * The postings go to the device as the file holds them (big-endian
+	 * blocks, decoded there: SURVEY 8f N2); offs[] / lens[] double as
+	 * raw_off[] / raw_n[].  NXSB_IMAGE_HOST_PAIRS=1 keeps the older
+	 * host-side conversion for A/B timing.
+	 */
+	if (host_pairs) {
+		if ((pairs = malloc(np * 8 + 8)) == NULL)
+			goto out;
+	} else if ((raw_n = malloc(sizeof(uint32_t) * ((size_t)n + 1))) == NULL) {
 		goto out;
+	}
 	np = 0;
 	for (uint32_t i = 0; i < n; i++) {
 		const uint32_t s = order[i].slot;
@@ -855,6 +866,11 @@ build_segment(nxs_index_t *idx, int pick, uint32_t seg)
 
 		ids[i] = order[i].id;
 		lens[i] = idx->doc_len[s];
+		if (!host_pairs) {
+			offs[i] = idx->doc_blk[s] + 16;
+			raw_n[i] = idx->doc_n[s];
+			continue;
+		}
 		offs[i] = np;
 		for (uint32_t j = 0; j < idx->doc_n[s]; j++) {
 			pairs[2 * np] = be_get32(p + (size_t)j * 8);
@@ -866,11 +882,15 @@ build_segment(nxs_index_t *idx, int pick, uint32_t seg)
 
 	const nxsb_shard_desc_t sd = {
 		.n_docs = n, .n_terms = idx->n_terms,
-		.doc_ids = ids, .doc_len = lens, .doc_off = offs, .pairs = pairs,
+		.doc_ids = ids, .doc_len = lens,
+		.doc_off = host_pairs ? offs : NULL, .pairs = pairs,
 		/* The header counters are what ranking reads (ranking.c:77,163). */
 		.token_count = idx_get_token_count(idx),
 		.doc_count = idx_get_doc_count(idx),
 		.df = idx->df,
+		.raw = host_pairs ? NULL : idx->dfile.base,
+		.raw_off = host_pairs ? NULL : offs,
+		.raw_n = raw_n,
 	};
 	if ((seg == 0 ? nxsb_engine_load_shard(idx->engine, &sd) :
 	    nxsb_engine_segment_add(idx->engine, &sd)) == -1) {
@@ -888,6 +908,7 @@ out:
 	free(lens);
 	free(offs);
 	free(pairs);
+	free(raw_n);
 	return ret;
 }
 

@@ -19,6 +19,7 @@ class ShardDesc(C.Structure):
         ("doc_ids", C.c_void_p), ("doc_len", C.c_void_p), ("doc_off", C.c_void_p),
         ("pairs", C.c_void_p), ("token_count", C.c_uint64), ("doc_count", C.c_uint32),
         ("df", C.c_void_p),
+        ("raw", C.c_void_p), ("raw_off", C.c_void_p), ("raw_n", C.c_void_p),
     ]
 
 
@@ -158,7 +159,25 @@ class Engine:
         dfa = None if df is None else np.ascontiguousarray(df, dtype=np.uint32)
         sd = ShardDesc(len(ids), n_terms, ids.ctypes.data, lens.ctypes.data,
                        doc_off.ctypes.data, pairs.ctypes.data, token_count, doc_count,
-                       None if dfa is None else dfa.ctypes.data)
+                       None if dfa is None else dfa.ctypes.data, None, None, None)
+        if segment:
+            self._check(self._lib.nxsb_engine_segment_add(self._h, C.byref(sd)))
+        else:
+            self._check(self._lib.nxsb_engine_load_shard(self._h, C.byref(sd)))
+
+    def load_dtmap(self, raw: np.ndarray, ids, lens, raw_off, raw_n, n_terms: int, token_count: int,
+                   doc_count: int, df=None, *, segment: bool = False) -> None:
+        """Load a shard straight from `nxsdtmap` bytes (nxsb_shard_desc_t.raw): document i's
+        raw_n[i] big-endian (term, count) pairs start at raw[raw_off[i]]; decoded on the device."""
+        raw = np.ascontiguousarray(raw, dtype=np.uint8)
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        lens = np.ascontiguousarray(lens, dtype=np.uint32)
+        raw_off = np.ascontiguousarray(raw_off, dtype=np.uint64)
+        raw_n = np.ascontiguousarray(raw_n, dtype=np.uint32)
+        dfa = None if df is None else np.ascontiguousarray(df, dtype=np.uint32)
+        sd = ShardDesc(len(ids), n_terms, ids.ctypes.data, lens.ctypes.data, None, None,
+                       token_count, doc_count, None if dfa is None else dfa.ctypes.data,
+                       raw.ctypes.data, raw_off.ctypes.data, raw_n.ctypes.data)
         if segment:
             self._check(self._lib.nxsb_engine_segment_add(self._h, C.byref(sd)))
         else:
