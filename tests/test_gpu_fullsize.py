@@ -1,0 +1,177 @@
+"""BASELINE.json's full size -- 10M synthetic documents, 1M-term vocabulary
+(configs C2 / C3) -- checked through properties that do not need a ground
+truth for every query: shard invariance (G shards + merge == one image, bit
+for bit), agreement of the two scoring kernels, order and count invariants,
+incremental refresh == rebuild; plus a sample of queries against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import _oracle
+from _oracle import BM25, TFIDF, check_topk
+
+pytestmark = pytest.mark.gpu
+
+N_DOCS = int(os.environ.get("NXSB_FULLSIZE_DOCS", 10_000_000))
+N_TERMS = 1_000_000
+
+
+@pytest.fixture(scope="module")
+def corpus():
+    from nxsearch_b200 import tools
+
+    return tools.Corpus.generate(N_DOCS, N_TERMS)
+
+
+@pytest.fixture(scope="module")
+def whole(corpus):
+    from nxsearch_b200 import engine
+
+    e = engine.Engine(0)
+    e.load_corpus(corpus)
+    yield e
+    e.close()
+
+
+def queries(corpus):
+    from test_gpu_stream import or_queries, bool_queries
+    return or_queries(corpus, 256), bool_queries(corpus, 96)
+
+
+def same(a, b):
+    (ca, ia, sa), (cb, ib, sb) = a, b
+    assert np.array_equal(ca, cb)
+    for q in range(len(ca)):
+        n = int(ca[q])
+        assert np.array_equal(ia[q, :n], ib[q, :n]), q
+        assert np.array_equal(sa[q, :n], sb[q, :n]), q
+
+
+def test_order_and_count_invariants(corpus, whole):
+    from nxsearch_b200 import engine
+
+    ors, bools = queries(corpus)
+    for algo, k, qs in ((BM25, 10, ors), (TFIDF, 100, bools), (BM25, 100, ors[:64])):
+        counts, ids, scores = whole.search(engine.Batch.from_lists(algo, k, qs))
+        for i, (toks, prog) in enumerate(qs):
+            n = int(counts[i])
+            s, d = scores[i, :n], ids[i, :n].astype(np.int64)
+            assert np.all(s > 0) and len(set(d.tolist())) == n
+            # descending score, ties by descending id
+            assert np.all((s[:-1] > s[1:]) | ((s[:-1] == s[1:]) & (d[:-1] > d[1:])))
+            if len(toks) == 1:
+                assert n == min(k, int(corpus.term_df[toks[0] - 1]))
+            elif qs is ors:
+                # an OR matches at least the documents of its most frequent term
+                assert n >= min(k, max(int(corpus.term_df[t - 1]) for t in toks))
+
+
+def test_shards_plus_merge_equal_the_whole_index(corpus, whole):
+    import torch
+    from nxsearch_b200 import dist as nxdist, engine
+
+    ors, bools = queries(corpus)
+    G = 4
+    shards = []
+    for g in range(G):
+        lo, hi = nxdist.shard_range(corpus.n_docs, g, G)
+        e = engine.Engine(0)
+        e.load_corpus(corpus, lo=lo, hi=hi, df=corpus.term_df,
+                      token_count=corpus.token_count, doc_count=corpus.doc_count)
+        shards.append(e)
+    for algo, k, qs in ((BM25, 10, ors), (TFIDF, 100, bools)):
+        batch = engine.Batch.from_lists(algo, k, qs)
+        want = whole.search(batch)
+        per = len(qs) * k * nxdist.REC_BYTES
+        gathered = torch.zeros(G * per, dtype=torch.uint8, device="cuda")
+        for g, e in enumerate(shards):
+            h = e.upload(batch)
+            e.run(h, gathered.data_ptr() + g * per)
+            e.sync()
+            e.release(h)
+        merged = torch.zeros(per, dtype=torch.uint8, device="cuda")
+        shards[0].merge_topk(gathered.data_ptr(), G, len(qs), k, merged.data_ptr())
+        shards[0].sync()
+        recs = merged.cpu().numpy().view(nxdist.REC_DTYPE).reshape(len(qs), k)
+        for i in range(len(qs)):
+            n = int(recs[i]["valid"].sum())
+            assert n == want[0][i]
+            assert np.array_equal(recs[i]["doc_id"][:n], want[1][i, :n])
+            assert np.array_equal(recs[i]["score"][:n], want[2][i, :n])
+    for e in shards:
+        e.close()
+
+
+def test_both_kernels_agree(corpus, whole):
+    from nxsearch_b200 import engine
+
+    ors, bools = queries(corpus)
+    os.environ["NXSB_KERNEL"] = "v2"
+    try:
+        old = engine.Engine(0)
+    finally:
+        del os.environ["NXSB_KERNEL"]
+    old.load_corpus(corpus)
+    for algo, k, qs in ((BM25, 10, ors[:128]), (TFIDF, 100, bools[:48])):
+        batch = engine.Batch.from_lists(algo, k, qs)
+        same(whole.search(batch), old.search(batch))
+    old.close()
+
+
+def test_delta_segment_and_removals_equal_the_whole_index(corpus, whole):
+    """The last 5000 documents as a delta segment, 30 documents removed."""
+    from nxsearch_b200 import engine
+
+    ors, bools = queries(corpus)
+    cut = corpus.n_docs - 5000
+    rng = np.random.default_rng(11)
+    dead_base = np.sort(rng.choice(cut, 24, replace=False))
+    dead_delta = np.sort(cut + rng.choice(5000, 6, replace=False))
+    dead = np.concatenate([dead_base, dead_delta])
+    # statistics without the removed documents
+    df = np.array(corpus.term_df, dtype=np.int64)
+    tokens = int(corpus.token_count)
+    for i in dead:
+        lo, hi = int(corpus.doc_off[i]), int(corpus.doc_off[i + 1])
+        df[corpus.pairs[2 * lo:2 * hi:2].astype(np.int64) - 1] -= 1
+        tokens -= int(corpus.doc_len[i])
+    ndocs = corpus.n_docs - len(dead)
+
+    seg = engine.Engine(0)
+    seg.load_corpus(corpus, lo=0, hi=cut, df=corpus.term_df)
+    seg.load_corpus(corpus, lo=cut, hi=corpus.n_docs, df=corpus.term_df, segment=True)
+    seg.set_dead(0, corpus.doc_ids[dead_base])
+    seg.set_dead(1, corpus.doc_ids[dead_delta])
+    seg.set_global_stats(df.astype(np.uint32), tokens, ndocs)
+    # the whole image with the same statistics, over-fetched and filtered on the host
+    whole.set_global_stats(df.astype(np.uint32), tokens, ndocs)
+    try:
+        dead_ids = set(int(x) for x in corpus.doc_ids[dead])
+        for algo, k, qs in ((BM25, 10, ors), (TFIDF, 100, bools)):
+            got = seg.search(engine.Batch.from_lists(algo, k, qs))
+            wc, wi, ws = whole.search(engine.Batch.from_lists(algo, k + len(dead), qs))
+            for q in range(len(qs)):
+                keep = [j for j in range(int(wc[q])) if int(wi[q, j]) not in dead_ids][:k]
+                assert int(got[0][q]) == len(keep), q
+                assert np.array_equal(got[1][q, :len(keep)], wi[q, keep]), q
+                assert np.array_equal(got[2][q, :len(keep)], ws[q, keep]), q
+    finally:
+        whole.set_global_stats(np.asarray(corpus.term_df), corpus.token_count, corpus.doc_count)
+        seg.close()
+
+
+def test_sample_against_the_oracle(corpus, whole):
+    from nxsearch_b200 import engine
+
+    ors, bools = queries(corpus)
+    ora = _oracle.OracleIndex(corpus)
+    try:
+        for algo, k, qs in ((BM25, 10, ors[:12]), (TFIDF, 100, bools[:6])):
+            counts, ids, scores = whole.search(engine.Batch.from_lists(algo, k, qs))
+            for i, (toks, prog) in enumerate(qs):
+                all_ids, all_sc = ora.search_all(algo, toks, prog)
+                check_topk(ids[i, :counts[i]], scores[i, :counts[i]], all_ids, all_sc, k,
+                           exact_scores=(algo == TFIDF))
+    finally:
+        ora.close()
