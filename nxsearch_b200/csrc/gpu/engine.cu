@@ -96,6 +96,18 @@ struct Batch {
 	uint32_t	max_tokens_all = 0;	// over every query (plan record stride)
 	uint64_t	bytes = 0;		// algorithmic bytes
 	std::vector<uint32_t> q_or, q_logic;	// host lists
+	/*
+	 * Shared dense prefixes (stream.cuh "base columns"): the distinct ordered
+	 * sets of dense terms that lead the OR queries of the batch become
+	 * n_virtual extra queries at the head of q_or (query index >= n_q,
+	 * tokens appended after the batch's); q_base[i] = {columns, count |
+	 * prefix number << 8} of q_or[i], count 0 = the query streams its own.
+	 */
+	uint32_t	n_virtual = 0, n_tok_all = 0;
+	std::vector<uint2> q_base;
+	uint2 *		d_qbase = nullptr;
+	unsigned long long *d_prefix_keys = nullptr;	// [n_virtual][limit] top-k keys
+	uint32_t *	d_prefix_cnt = nullptr;		// [n_virtual]
 	/* One H2D copy: [queries | tokens | prog | qlist_or | qlist_logic]. */
 	DevBuf		desc;
 	PinnedBuf	h_desc;
@@ -148,6 +160,8 @@ struct nxsb_engine {
 	uint32_t *	d_doc_len = nullptr;
 	float *		d_logtab = nullptr;
 	std::vector<uint32_t> h_df_local, h_df;
+	std::vector<int32_t> h_dense_col;		// [V] as d_dense_col
+	bool		share_dense = true;		// NXSB_SHARE_DENSE=0: development switch
 	uint64_t	token_count = 0;
 	uint32_t	doc_count = 0;
 	float		K0 = 0, K1 = 0;
@@ -334,6 +348,9 @@ nxsb_engine_create(int device)
 		/* Development switch: density threshold of the dense columns (> 1: none). */
 		if ((kv = getenv("NXSB_DENSE_MIN")) != NULL)
 			e->dense_min = (float)atof(kv);
+		/* Development switch: every query streams its own dense columns. */
+		if ((kv = getenv("NXSB_SHARE_DENSE")) != NULL)
+			e->share_dense = atoi(kv) != 0;
 	}
 	for (auto &r : e->runs)
 		for (int i = 0; i < EV_PER_RUN; i++)
@@ -734,6 +751,7 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 			if (ok) {
 				cudaMemcpyAsync(e->d_dense_col, col.data(), (size_t)V * 4,
 				    cudaMemcpyHostToDevice, st);
+				e->h_dense_col = col;
 				if (e->n_dense) {
 					cudaMemsetAsync(e->d_dense, 0, (size_t)e->n_dense * col_words * 4, st);
 					cudaMemcpyAsync(d_dterms, dterms.data(), (size_t)e->n_dense * 4,
@@ -998,19 +1016,118 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 	}
 	static_assert(sizeof(QDesc) == sizeof(nxsb_query_t), "descriptor layout");
 
+	/*
+	 * Shared dense prefixes.  The dense terms of an OR query contribute
+	 * the same column values to whatever query names them, so when they
+	 * LEAD the token list their sum is computed once per distinct ordered
+	 * prefix of the batch (a "virtual" query of just those terms) instead
+	 * of once per query: the query itself then scores only the documents
+	 * its other terms name, starting each from the prefix sum (a gather
+	 * from the score columns), and takes the rest of its top-k from the
+	 * prefix's own top-k.  Float sums keep the token-list order: a single
+	 * non-dense token ahead of a single dense one also qualifies, because
+	 * the first addition of a sum is commutative.
+	 */
+	std::vector<QDesc> vq;			// virtual queries
+	std::vector<uint32_t> vtok;		// their tokens
+	std::vector<uint2> qbase(B.q_or.size(), make_uint2(0u, 0u));
+	if (e->share_dense && e->n_dense && !e->wide && !e->force_v2 &&
+	    B.limit <= ST_K_MAX && !e->h_dense_col.empty()) {
+		std::vector<std::pair<uint64_t, uint32_t>> seen;	// (terms packed, prefix number)
+
+		for (size_t i = 0; i < B.q_or.size(); i++) {
+			const nxsb_query_t &q = b->queries[B.q_or[i]];
+			uint32_t terms[4], nd = 0, first_sparse = q.n_tokens, last_dense = 0;
+			bool ok = true;
+
+			for (uint32_t j = 0; j < q.n_tokens; j++) {
+				const uint32_t id = b->tokens[q.tok_off + j];
+				const bool dense = id >= 1 && id <= e->n_terms &&
+				    e->h_dense_col[id - 1] >= 0;
+
+				if (dense) {
+					if (nd == 4) {
+						ok = false;
+						break;
+					}
+					/* A term listed twice would be added twice: leave it. */
+					for (uint32_t x = 0; x < nd; x++)
+						ok &= terms[x] != id;
+					terms[nd++] = id;
+					last_dense = j;
+				} else if (first_sparse == q.n_tokens) {
+					first_sparse = j;
+				}
+			}
+			if (!ok || nd == 0)
+				continue;
+			/* All dense tokens lead, or the list is [sparse, dense, sparse...]. */
+			if (!(last_dense < first_sparse ||
+			    (nd == 1 && last_dense == 1 && first_sparse == 0)))
+				continue;
+			uint64_t key = nd;
+			uint32_t cols = 0;
+			for (uint32_t x = 0; x < nd; x++) {
+				key = key * 0x100000001b3ull + terms[x];
+				cols |= (uint32_t)e->h_dense_col[terms[x] - 1] << (8 * x);
+			}
+			uint32_t pn = UINT32_MAX;
+			for (auto &sp : seen)
+				if (sp.first == key) {
+					const QDesc &v = vq[sp.second];
+					bool same = v.n_tokens == nd;
+					for (uint32_t x = 0; same && x < nd; x++)
+						same = vtok[v.tok_off - B.n_tok + x] == terms[x];
+					if (same) {
+						pn = sp.second;
+						break;
+					}
+				}
+			if (pn == UINT32_MAX) {
+				QDesc v;
+
+				pn = vq.size();
+				v.tok_off = B.n_tok + vtok.size();
+				v.n_tokens = nd;
+				v.prog_off = 0;
+				v.n_prog = 0;
+				vq.push_back(v);
+				vtok.insert(vtok.end(), terms, terms + nd);
+				seen.emplace_back(key, pn);
+			}
+			qbase[i] = make_uint2(cols, nd | (pn << 8));
+		}
+	}
+	B.n_virtual = vq.size();
+	B.n_tok_all = B.n_tok + vtok.size();
+	/* q_or = [virtual queries | the batch's OR queries]; q_base likewise. */
+	B.q_base.assign(B.n_virtual, make_uint2(0u, 0u));
+	B.q_base.insert(B.q_base.end(), qbase.begin(), qbase.end());
+	{
+		std::vector<uint32_t> lst(B.n_virtual);
+
+		for (uint32_t v = 0; v < B.n_virtual; v++)
+			lst[v] = B.n_q + v;
+		B.q_or.insert(B.q_or.begin(), lst.begin(), lst.end());
+	}
+
 	const size_t nq = std::max(B.n_q, 1u);
+	const size_t nslots = nq + B.n_virtual;
 	const size_t o_q = 0;
-	const size_t o_tok = o_q + align16(nq * sizeof(QDesc));
-	const size_t o_prog = o_tok + align16((size_t)B.n_tok * 4);
+	const size_t o_tok = o_q + align16(nslots * sizeof(QDesc));
+	const size_t o_prog = o_tok + align16((size_t)B.n_tok_all * 4);
 	const size_t o_or = o_prog + align16((size_t)B.n_prog * 4);
-	const size_t o_lg = o_or + align16(B.q_or.size() * 4);
+	const size_t o_base = o_or + align16(B.q_or.size() * 4);
+	const size_t o_lg = o_base + align16(B.q_or.size() * sizeof(uint2));
 	const size_t desc_bytes = o_lg + align16(B.q_logic.size() * 4);
 
 	const size_t s_toks = 0;
-	const size_t s_skip = s_toks + align16((size_t)B.n_tok * sizeof(DTok));
-	const size_t s_thr = s_skip + align16((size_t)B.n_tok * (e->ntiles + 1) * 4);
-	const size_t s_cnt = s_thr + align16(nq * 8);
-	const size_t s_work = s_cnt + align16(nq * 4);
+	const size_t s_skip = s_toks + align16((size_t)B.n_tok_all * sizeof(DTok));
+	const size_t s_pkey = s_skip + align16((size_t)B.n_tok_all * (e->ntiles + 1) * 4);
+	const size_t s_pcnt = s_pkey + align16((size_t)B.n_virtual * B.limit * 8);
+	const size_t s_thr = s_pcnt + align16((size_t)B.n_virtual * 4);
+	const size_t s_cnt = s_thr + align16(nslots * 8);
+	const size_t s_work = s_cnt + align16(nslots * 4);
 	const size_t scratch_bytes = s_work + 16;
 
 	const size_t r_counts = align16(nq * B.limit * sizeof(Rec));
@@ -1028,9 +1145,12 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 	B.d_tokens = (uint32_t *)(d + o_tok);
 	B.d_prog = (int32_t *)(d + o_prog);
 	B.d_qlist_or = (uint32_t *)(d + o_or);
+	B.d_qbase = (uint2 *)(d + o_base);
 	B.d_qlist_logic = (uint32_t *)(d + o_lg);
 	B.d_toks = (DTok *)(sc + s_toks);
 	B.d_tmp_skip = (uint32_t *)(sc + s_skip);
+	B.d_prefix_keys = (unsigned long long *)(sc + s_pkey);
+	B.d_prefix_cnt = (uint32_t *)(sc + s_pcnt);
 	B.d_thr = (unsigned long long *)(sc + s_thr);
 	B.d_cand_count = (uint32_t *)(sc + s_cnt);
 	B.d_work = (uint32_t *)(sc + s_work);
@@ -1039,9 +1159,12 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 	B.d_counts = (uint32_t *)((char *)B.results.p + r_counts);
 
 	memcpy(h + o_q, b->queries, (size_t)B.n_q * sizeof(QDesc));
+	memcpy(h + o_q + (size_t)B.n_q * sizeof(QDesc), vq.data(), vq.size() * sizeof(QDesc));
 	memcpy(h + o_tok, b->tokens, (size_t)B.n_tok * 4);
+	memcpy(h + o_tok + (size_t)B.n_tok * 4, vtok.data(), vtok.size() * 4);
 	memcpy(h + o_prog, b->prog, (size_t)B.n_prog * 4);
 	memcpy(h + o_or, B.q_or.data(), B.q_or.size() * 4);
+	memcpy(h + o_base, B.q_base.data(), B.q_base.size() * sizeof(uint2));
 	memcpy(h + o_lg, B.q_logic.data(), B.q_logic.size() * 4);
 	CK(e, cudaMemcpyAsync(d, h, desc_bytes, cudaMemcpyHostToDevice, e->stream));
 	return 0;
@@ -1173,8 +1296,8 @@ launch_tiles(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
  */
 template <bool LOGIC>
 static int
-launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
-    uint32_t k_tile, uint64_t cand_cap)
+launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist,
+    const uint2 *d_qbase, uint32_t n_q, uint32_t k_tile, uint64_t cand_cap)
 {
 	const uint64_t items = (uint64_t)n_q * e->ntiles;
 	const uint32_t stride = 16u * (1u + std::max(B.max_tokens_all, 1u));
@@ -1227,6 +1350,7 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
 	}
 	p.tt = e->d_tt;
 	p.dense = reinterpret_cast<const uint32_t *>(e->d_dense_sc);
+	p.col_words = (unsigned long long)e->ntiles * TILE_DOCS;
 
 	auto kern = B.algo == NXSB_ALGO_BM25
 	    ? (e->wide ? score_stream_kernel<LOGIC, true, NXSB_ALGO_BM25>
@@ -1249,7 +1373,7 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
 	CK(e, cudaMemsetAsync(e->d_tile_cnt, 0, want_cnt, e->stream));
 	mark(e, "plan");
 	plan_items_kernel<<<(unsigned)((items + 255) / 256), 256, 0, e->stream>>>(
-	    B.d_queries, d_qlist, B.d_toks, n_q, e->ntiles, stride, e->d_plan);
+	    B.d_queries, d_qlist, d_qbase, B.d_toks, n_q, e->ntiles, stride, e->d_plan);
 	if (LOGIC) {
 		truth_tables_kernel<<<n_q, 256, 0, e->stream>>>(B.d_queries, d_qlist,
 		    B.d_prog, e->d_tt);
@@ -1303,17 +1427,54 @@ run_list(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list,
 		chunk = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(chunk, cap));
 	}
 
+	/*
+	 * Shared dense prefixes need the virtual queries (the head of the
+	 * list) finalized before the queries that merge with them: possible
+	 * when the list goes through in one chunk, else every query streams
+	 * its own dense columns as before.
+	 */
+	const uint32_t n_virtual = LOGIC ? 0 : B.n_virtual;
+	const uint2 *d_qbase = (!LOGIC && stream && n_virtual && chunk >= n_list)
+	    ? B.d_qbase : nullptr;
+
 	for (uint32_t q0 = 0; q0 < n_list; q0 += chunk) {
 		const uint32_t n = std::min(chunk, n_list - q0);
 
-		if ((stream ? launch_stream<LOGIC>(e, B, d_qlist + q0, n, k_tile, cand_cap)
+		if ((stream ? launch_stream<LOGIC>(e, B, d_qlist + q0,
+		    d_qbase ? d_qbase + q0 : nullptr, n, k_tile, cand_cap)
 		    : launch_tiles<LOGIC>(e, B, d_qlist + q0, n, k_tile, cand_cap)) == -1)
 			return -1;
 		mark(e, "topk");
 		if (stream) {
-			finalize_cells_kernel<<<n, 256, 0, st>>>(e->d_cand, e->d_tile_cnt,
-			    e->ntiles, d_qlist + q0, k, e->d_doc_ids, d_recs, B.d_counts);
-			e->launches++;
+			FinalizeShared fs;
+
+			fs.queries = B.d_queries;
+			fs.toks = B.d_toks;
+			fs.post = e->d_post;
+			fs.qbase = d_qbase ? d_qbase + q0 : nullptr;
+			fs.prefix_keys = B.d_prefix_keys;
+			fs.prefix_cnt = B.d_prefix_cnt;
+			fs.n_real = B.n_q;
+			/* Virtual queries lead the list: [q0, q0 + nv) of this chunk. */
+			const uint32_t nv = q0 < n_virtual ? std::min(n, n_virtual - q0) : 0;
+
+			if (nv) {
+				finalize_cells_kernel<<<nv, 256, 0, st>>>(e->d_cand, e->d_tile_cnt,
+				    e->ntiles, d_qlist + q0, k, e->d_doc_ids, d_recs, B.d_counts, fs);
+				e->launches++;
+			}
+			if (n > nv) {
+				/* Slot numbers stay relative to the chunk: shift the views. */
+				FinalizeShared fr = fs;
+
+				if (fr.qbase)
+					fr.qbase += nv;
+				finalize_cells_kernel<<<n - nv, 256, 0, st>>>(
+				    e->d_cand + (size_t)nv * cand_cap,
+				    e->d_tile_cnt + (size_t)nv * e->ntiles, e->ntiles,
+				    d_qlist + q0 + nv, k, e->d_doc_ids, d_recs, B.d_counts, fr);
+				e->launches++;
+			}
 			CK(e, cudaGetLastError());
 			continue;
 		}
@@ -1400,13 +1561,13 @@ run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
 
 	if (e->n_dense)
 		CK(e, cudaMemsetAsync(e->d_dense_used, 0, 256 * 4, st));
-	resolve_tokens_kernel<<<(B.n_tok + 255) / 256, 256, 0, st>>>(
-	    B.d_tokens, B.n_tok, e->n_terms, e->d_term_off, e->d_skip_row,
+	resolve_tokens_kernel<<<(B.n_tok_all + 255) / 256, 256, 0, st>>>(
+	    B.d_tokens, B.n_tok_all, e->n_terms, e->d_term_off, e->d_skip_row,
 	    e->d_dense_col, e->d_dense_used, (unsigned long long)e->ntiles * TILE_DOCS,
 	    e->d_skip, B.d_tmp_skip,
 	    B.algo == NXSB_ALGO_BM25 ? e->d_idf_bm25 : e->d_idf_tfidf,
 	    e->ntiles, B.d_toks);
-	build_temp_skips_kernel<<<B.n_tok, 128, 0, st>>>(e->d_post, B.d_toks,
+	build_temp_skips_kernel<<<B.n_tok_all, 128, 0, st>>>(e->d_post, B.d_toks,
 	    B.d_tmp_skip, e->ntiles);
 	e->launches += 2;
 	CK(e, cudaGetLastError());

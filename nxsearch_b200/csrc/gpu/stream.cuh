@@ -97,7 +97,13 @@
 struct PlanHdr {
 	uint32_t	total;		/* postings in the item */
 	uint32_t	ntok;		/* non-empty slices */
-	uint32_t	pad[2];
+	/*
+	 * Base columns (shared dense prefix): the query's leading dense terms
+	 * are not streamed; a document's sum starts, at its first posting,
+	 * from the fold of score columns base_cols[8x .. 8x+7], x < nbase.
+	 */
+	uint32_t	base_cols;
+	uint32_t	nbase;
 };
 struct PlanTok {
 	/*
@@ -125,7 +131,8 @@ struct StageMeta {
 	/* First stage of an item: score half of the query's threshold key as
 	 * the producer saw it (0: none yet). */
 	uint32_t	ths_bits;
-	uint32_t	pad[3];
+	uint32_t	base_cols, nbase;	/* first stage of an item: PlanHdr's */
+	uint32_t	pad;
 };
 
 struct StreamParams {
@@ -142,6 +149,7 @@ struct StreamParams {
 	float			K0, K1;
 	const uint32_t *	tt;		/* [n_q][8] truth tables (boolean) */
 	const uint32_t *	dense;		/* dense columns (common.cuh) */
+	unsigned long long	col_words;	/* words per column */
 	unsigned long long *	prof;		/* ST_PROF counters or NULL */
 };
 
@@ -169,7 +177,8 @@ struct StCfg {
 
 __global__ void __launch_bounds__(256)
 plan_items_kernel(const QDesc *__restrict__ queries,
-    const uint32_t *__restrict__ qlist, const DTok *__restrict__ toks,
+    const uint32_t *__restrict__ qlist, const uint2 *__restrict__ qbase,
+    const DTok *__restrict__ toks,
     uint32_t n_q, uint32_t ntiles, uint32_t stride,
     unsigned char *__restrict__ plan)
 {
@@ -182,6 +191,8 @@ plan_items_kernel(const QDesc *__restrict__ queries,
 	const uint32_t tile = ntiles - 1 - (uint32_t)(item / n_q);
 	const uint32_t slot = (uint32_t)(item % n_q);
 	const QDesc qd = queries[qlist[slot]];
+	const uint2 qb = qbase ? qbase[slot] : make_uint2(0u, 0u);
+	const uint32_t nbase = qb.y & 0xffu;
 	unsigned char *rec = plan + item * stride;
 	PlanTok *out = reinterpret_cast<PlanTok *>(rec + sizeof(PlanHdr));
 	uint32_t total = 0, m = 0;
@@ -191,6 +202,9 @@ plan_items_kernel(const QDesc *__restrict__ queries,
 		const uint32_t lo = __ldg(t.skip + tile);
 		const uint32_t hi = __ldg(t.skip + tile + 1);
 
+		/* The query's dense terms come in through its base columns. */
+		if (nbase && t.dense_off != DENSE_NONE)
+			continue;
 		if (hi > lo) {
 			PlanTok pt;
 
@@ -219,7 +233,8 @@ plan_items_kernel(const QDesc *__restrict__ queries,
 	PlanHdr h;
 	h.total = total;
 	h.ntok = m;
-	h.pad[0] = h.pad[1] = 0;
+	h.base_cols = qb.x;
+	h.nbase = nbase;
 	*reinterpret_cast<PlanHdr *>(rec) = h;
 }
 
@@ -533,10 +548,10 @@ score_stream_kernel(const StreamParams p)
 			it0 = __shfl_sync(0xffffffffu, a, 0);
 			it1 = __shfl_sync(0xffffffffu, b, 0);
 		}
-		auto load_hdr = [&](uint32_t it) -> uint2 {
+		auto load_hdr = [&](uint32_t it) -> uint4 {
 			if (it >= n_items)
-				return make_uint2(0u, 0u);
-			return __ldg(reinterpret_cast<const uint2 *>(
+				return make_uint4(0u, 0u, 0u, 0u);
+			return __ldg(reinterpret_cast<const uint4 *>(
 			    p.plan + (unsigned long long)it * p.plan_stride));
 		};
 		/* Independent of the header load: every lane a record has room for. */
@@ -555,7 +570,7 @@ score_stream_kernel(const StreamParams p)
 			return (uint32_t)(*(volatile const unsigned long long *)
 			    (p.thr + it % p.n_q) >> 32);
 		};
-		uint2 h0 = load_hdr(it0);
+		uint4 h0 = load_hdr(it0);
 		uint4 t0 = load_tok(it0, h0.y);
 		uint32_t thr0 = load_thr(it0);
 
@@ -580,6 +595,8 @@ score_stream_kernel(const StreamParams p)
 				m.tile_lo = tile_lo;
 				m.idf0 = m.sub[0].idf;
 				m.ths_bits = thr0;
+				m.base_cols = h0.z;
+				m.nbase = h0.w;
 				if (bytes)
 					mbar_arrive_expect_tx(full0 + 8 * ps, bytes);
 				else
@@ -606,7 +623,7 @@ score_stream_kernel(const StreamParams p)
 			uint32_t raw2 = 0;
 			if (lane == 0)
 				raw2 = atomicAdd(p.work_counter, 1u);
-			const uint2 h1 = load_hdr(it1);
+			const uint4 h1 = load_hdr(it1);
 			const uint4 t1 = load_tok(it1, h1.y);
 			const uint32_t thr1 = load_thr(it1);
 
@@ -728,6 +745,22 @@ score_stream_kernel(const StreamParams p)
 	 */
 	float ths = __uint_as_float(0x7f800000u);
 	bool dirty = false;
+	/*
+	 * Base columns of the current item (PlanHdr): a document's sum starts,
+	 * at its first posting (accumulator still 0 -- scores are positive),
+	 * from the fold of the query's leading dense score columns, which is
+	 * what streaming those columns first would have left there.
+	 */
+	constexpr bool BASE = !LOGIC && !WIDE;
+	uint32_t nbase = 0, base_cols = 0;
+	const float *colf = reinterpret_cast<const float *>(p.dense);
+	auto base_of = [&](uint32_t doc) -> float {
+		float b = __ldg(colf + (base_cols & 0xffu) * p.col_words + doc);
+
+		for (uint32_t x = 1; x < nbase; x++)
+			b = __fadd_rn(b, __ldg(colf + ((base_cols >> (8u * x)) & 0xffu) * p.col_words + doc));
+		return b;
+	};
 	auto note = [&](uint32_t rel) {
 		const uint32_t at = atomicAdd(s_npush + par, 1u);
 
@@ -756,6 +789,11 @@ score_stream_kernel(const StreamParams p)
 
 		if (flags & ST_F_FIRST) {
 			const uint32_t tb = m.ths_bits;
+
+			if (BASE) {
+				nbase = m.nbase;
+				base_cols = m.base_cols;
+			}
 
 			if (ctid == 0)
 				theta_pref = *(volatile unsigned long long *)(p.thr + slot);
@@ -864,11 +902,23 @@ score_stream_kernel(const StreamParams p)
 #pragma unroll
 			for (int r = 0; r < SLOTS; r++)
 				v[r] = buf[ctid + r * ST_NCONS];
+			float bs[SLOTS];
+			if (BASE && nbase) {
+				/* In flight while the postings are scored. */
+#pragma unroll
+				for (int r = 0; r < SLOTS; r++)
+					bs[r] = base_of(v[r].x);
+			}
 			st_score<WIDE, ALGO, SLOTS>(p, s_logtab, v, __uint_as_float(hdr.w), sc);
 			/* Documents of one list are distinct: batch the updates. */
 #pragma unroll
 			for (int r = 0; r < SLOTS; r++)
 				a[r] = lds_f32(accb + 4u * v[r].x);
+			if (BASE && nbase) {
+#pragma unroll
+				for (int r = 0; r < SLOTS; r++)
+					a[r] = a[r] == 0.f ? bs[r] : a[r];
+			}
 			float top = 0.f;
 #pragma unroll
 			for (int r = 0; r < SLOTS; r++) {
@@ -925,11 +975,24 @@ score_stream_kernel(const StreamParams p)
 						if (ok[r])
 							v[r] = buf[i];
 					}
+					float bs[2];
+					if (BASE && nbase) {
+#pragma unroll
+						for (int r = 0; r < 2; r++)
+							if (ok[r])
+								bs[r] = base_of(v[r].x);
+					}
 					st_score<WIDE, ALGO, 2>(p, s_logtab, v, idf, sc);
 #pragma unroll
 					for (int r = 0; r < 2; r++)
 						if (ok[r])
 							a[r] = lds_f32(accb + 4u * v[r].x);
+					if (BASE && nbase) {
+#pragma unroll
+						for (int r = 0; r < 2; r++)
+							if (ok[r])
+								a[r] = a[r] == 0.f ? bs[r] : a[r];
+					}
 #pragma unroll
 					for (int r = 0; r < 2; r++)
 						if (ok[r]) {
@@ -1196,12 +1259,34 @@ score_stream_kernel(const StreamParams p)
  * wrote: cand[slot][tile][0 .. tile_count[slot][tile]).  One CTA per query;
  * same selection as finalize_topk_kernel (keys are unique).
  */
+/*
+ * Shared dense prefixes (engine.cu fill_batch): a query with index >= n_real
+ * is a virtual one -- the leading dense terms of some queries on their own --
+ * and leaves its top-k as KEYS in prefix_keys[q - n_real][k].  A real query
+ * with base columns (qbase[slot].y != 0) scored only the documents its other
+ * terms name; the rest of its top-k are the prefix's best documents that none
+ * of those terms names (a binary search per list), so the two are merged.  The
+ * prefix's k best suffice: a document of that list that IS named scores at
+ * least its prefix sum in the query's own candidates, so the list always
+ * accounts for k documents at or above anything the prefix ranks lower.
+ */
+struct FinalizeShared {
+	const QDesc *		queries;
+	const DTok *		toks;
+	const uint2 *		post;
+	const uint2 *		qbase;		/* per slot, or NULL */
+	unsigned long long *	prefix_keys;
+	uint32_t *		prefix_cnt;
+	uint32_t		n_real;
+};
+
 __global__ void __launch_bounds__(256)
 finalize_cells_kernel(const unsigned long long *__restrict__ cand,
     const uint32_t *__restrict__ tile_count, uint32_t ntiles,
     const uint32_t *__restrict__ qlist, uint32_t k,
     const unsigned long long *__restrict__ doc_ids,
-    Rec *__restrict__ recs, uint32_t *__restrict__ counts)
+    Rec *__restrict__ recs, uint32_t *__restrict__ counts,
+    const FinalizeShared fs)
 {
 	__shared__ unsigned long long s_keys[SORT_CAP];
 	__shared__ uint32_t s_hist[256];
@@ -1288,6 +1373,62 @@ finalize_cells_kernel(const unsigned long long *__restrict__ cand,
 	for (uint32_t i = m + tid; i < npow2; i += blockDim.x)
 		s_keys[i] = 0;
 	bitonic_sort_desc(s_keys, npow2);
+
+	if (q >= fs.n_real) {
+		/* A virtual query: its keys are what the real ones merge with. */
+		const uint32_t vn = m < k ? m : k;
+
+		for (uint32_t r = tid; r < vn; r += blockDim.x)
+			fs.prefix_keys[(size_t)(q - fs.n_real) * k + r] = s_keys[r];
+		if (tid == 0)
+			fs.prefix_cnt[q - fs.n_real] = vn;
+		return;
+	}
+	const uint2 qb = fs.qbase ? fs.qbase[slot] : make_uint2(0u, 0u);
+	if (qb.y & 0xffu) {
+		const uint32_t pn = qb.y >> 8;
+		const uint32_t pc = fs.prefix_cnt[pn];
+		const QDesc qd = fs.queries[q];
+		const uint32_t own = m < k ? m : k;	/* own keys beyond k cannot win */
+
+		__syncthreads();
+		if (tid == 0)
+			s_n = own;
+		__syncthreads();
+		for (uint32_t r = tid; r < pc; r += blockDim.x) {
+			const unsigned long long key = fs.prefix_keys[(size_t)pn * k + r];
+			const uint32_t doc = (uint32_t)key;
+			bool named = false;
+
+			for (uint32_t j = 0; j < qd.n_tokens && !named; j++) {
+				const DTok t = fs.toks[qd.tok_off + j];
+
+				if (t.dense_off != DENSE_NONE)
+					continue;
+				const uint2 *lst = fs.post + t.post_off;
+				uint32_t lo = 0, hi = t.df_local;
+
+				while (lo < hi) {
+					const uint32_t mid = (lo + hi) >> 1;
+					if (lst[mid].x < doc)
+						lo = mid + 1;
+					else
+						hi = mid;
+				}
+				named = lo < t.df_local && lst[lo].x == doc;
+			}
+			if (!named)
+				s_keys[atomicAdd(&s_n, 1u)] = key;	/* own + pc <= 2k <= SORT_CAP */
+		}
+		__syncthreads();
+		m = s_n;
+		npow2 = 2;
+		while (npow2 < m)
+			npow2 <<= 1;
+		for (uint32_t i = m + tid; i < npow2; i += blockDim.x)
+			s_keys[i] = 0;
+		bitonic_sort_desc(s_keys, npow2);
+	}
 
 	const uint32_t cn = m < k ? m : k;
 	Rec *out = recs + (size_t)q * k;
