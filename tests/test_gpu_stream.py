@@ -165,3 +165,62 @@ def test_limit_above_the_stream_kernel_falls_back(corpus, oracle, eng):
         n = min(int(c_a[q]), 128)
         assert np.array_equal(i_a[q, :n], i_b[q, :n])
         assert np.array_equal(s_a[q, :n], s_b[q, :n])
+
+
+def test_shared_dense_prefixes_every_token_order(corpus, oracle, eng):
+    """Shared dense prefixes (engine.cu fill_batch): queries whose dense terms
+    lead the token list take their sum from a virtual query; the other orders
+    stream their own columns.  Every shape must equal the tile kernel bit for
+    bit (which adds token by token) and the oracle."""
+    from nxsearch_b200 import engine
+
+    df = np.asarray(corpus.term_df)
+    dense = [int(t) + 1 for t in np.flatnonzero(df >= 0.6 * corpus.n_docs)][:5]
+    assert len(dense) >= 3
+    d1, d2, d3 = dense[:3]
+    sp = [int(t) for t in corpus.query_terms(64, seed=4242) if int(t) not in dense][:12]
+    s1, s2, s3, s4 = sp[:4]
+    OR = OP_OR
+
+    def q(*toks):
+        prog = [0]
+        for i in range(1, len(toks)):
+            prog += [i, OR]
+        return (list(toks), prog)
+
+    shapes = [q(d1), q(d2), q(d1, d2), q(d2, d1), q(d1, d2, d3), q(*dense[:4]),
+              q(d1, s1), q(s1, d1), q(s1, d1, s2), q(s1, d1, s2, s3), q(d1, d2, s1, s2), q(d1, s1, s2, s3),
+              # not eligible: a dense term after two others, dense terms apart, one named twice
+              q(s1, s2, d1), q(s1, s2, s3, d1), q(d1, s1, d2), q(s1, d1, d2), q(s1, d1, s2, d2), q(d1, d1, s1),
+              q(s1), q(s1, s2, s3, s4)]
+    if len(dense) == 5:
+        shapes.append(q(*dense))                 # five dense terms: more than a prefix holds
+    qs = shapes * 3 + or_queries(corpus, 64, 5)
+    os.environ["NXSB_KERNEL"] = "v2"
+    try:
+        e2 = engine.Engine(0)
+    finally:
+        del os.environ["NXSB_KERNEL"]
+    e2.load_corpus(corpus)
+    try:
+        for algo in (BM25, TFIDF):
+            for limit in (1, 10, 128):
+                b = engine.Batch.from_lists(algo, limit, qs)
+                c1, i1, s1_ = eng.search(b)
+                c2, i2, s2_ = e2.search(b)
+                assert np.array_equal(c1, c2), (algo, limit)
+                assert np.array_equal(i1, i2), (algo, limit)
+                assert np.array_equal(s1_.view(np.uint32), s2_.view(np.uint32)), (algo, limit)
+            # one-query batches: the prefix serves a single user
+            for sh in shapes[:12]:
+                b = engine.Batch.from_lists(algo, 10, [sh])
+                r1, r2 = eng.search(b), e2.search(b)
+                assert np.array_equal(r1[1], r2[1]) and np.array_equal(r1[2], r2[2])
+        counts, ids, scores = eng.search(engine.Batch.from_lists(TFIDF, 10, shapes))
+        for i, (toks, prog) in enumerate(shapes):
+            if len(set(toks)) != len(toks):
+                continue                          # the oracle merges a repeated term
+            all_ids, all_sc = oracle.search_all(TFIDF, toks, prog)
+            check_topk(ids[i, :counts[i]], scores[i, :counts[i]], all_ids, all_sc, 10, exact_scores=True)
+    finally:
+        e2.close()
