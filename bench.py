@@ -40,6 +40,14 @@ METRIC = "BM25 top-10 queries/s, 10M-doc synthetic index"
 UNIT = "queries/s"
 
 
+def metric_name(args) -> str:
+    """BASELINE.json's metric; a run at another size (--docs, --limit) says so."""
+    if args.docs == 10_000_000 and args.limit == 10:
+        return METRIC
+    docs = f"{args.docs // 1_000_000}M" if args.docs % 1_000_000 == 0 else str(args.docs)
+    return f"BM25 top-{args.limit} queries/s, {docs}-doc synthetic index"
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -194,7 +202,7 @@ def run_reference(args, rank: int, world: int) -> None:
     value = per_step * steps_done / total
     sample = f"{per_step} queries/step x {steps_done} steps of the same query stream, full {args.docs}-doc index"
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps_done,
+        "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps_done,
         "warmup": args.warmup, "ms_per_step": 1000 * total / steps_done, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "impl": "reference",
@@ -311,7 +319,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     }
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "docs": args.docs, "vocab": args.vocab,
