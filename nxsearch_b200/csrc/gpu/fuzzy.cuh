@@ -13,6 +13,20 @@
  * so a lane's term arrives as one coalesced 16-byte load and only the
  * buckets with |len(term) - len(query)| <= 2 are scanned at all.
  *
+ * Before Myers runs, a 64-bit SIGNATURE of each term (bit h(byte) set for
+ * every byte it contains) is tested against the query's: an edit changes at
+ * most one byte occurrence on either side, so d(q,t) <= 2 needs
+ * popc(sig_q & ~sig_t) <= 2 and popc(sig_t & ~sig_q) <= 2 -- a necessary
+ * condition, whatever h is, so no candidate is lost.  POPC issues on the
+ * quarter-rate XU pipe, so the bulk test is ONE of them per pair: the
+ * signatures folded to 32 bits (another valid h) must differ in at most 4
+ * bits; the two-sided 64-bit test runs only for what passes.  The folded
+ * signatures of a bucket are staged in shared memory once per CTA and tested
+ * by all its warps (query terms, sorted by length on the host so that a CTA's
+ * share buckets); the few survivors queue up per warp and go through Myers 32
+ * at a time, one per lane.  Candidate sets, distances and the chosen term are
+ * unchanged.
+ *
  * The reference's answer is NOT "nearest" or "most popular" (SURVEY 8a F3):
  * its child range is half-open and its selection loop never updates the
  * running maximum, so it returns the first candidate in BFS order that the
@@ -24,6 +38,7 @@
 #ifndef NXSB_GPU_FUZZY_CUH
 #define NXSB_GPU_FUZZY_CUH
 
+#include <algorithm>
 #include <vector>
 #include <cstring>
 
@@ -31,7 +46,9 @@
 
 #define FZ_TOLERANCE	2	/* ref index/index.h:26 */
 #define FZ_EDGE_MAX	63	/* ref algo/bktree.h:11 */
-#define FZ_WARPS	8	/* query terms per CTA */
+#define FZ_WARPS	8	/* query terms per CTA, 64-bit patterns */
+#define FZ_WARPS32	16	/* ... 32-bit patterns */
+#define FZ_CHUNK	2048	/* signatures staged per round */
 #define FZ_MAX_QLEN	64	/* pattern bits */
 #define FZ_ROOT		0xffffffffu
 
@@ -48,6 +65,8 @@ struct FuzzyImage {
 	/* scan order: 16-byte slots bucketed by length 1..16 */
 	uint4 *		d_slot16 = nullptr;
 	uint32_t *	d_slot16_term = nullptr;
+	unsigned long long *d_sig16 = nullptr;	// [n16] byte-presence signatures
+	uint32_t *	d_sig32 = nullptr;	// [n16 + pad] the same folded to 32 bits
 	uint32_t	n16 = 0;
 	uint32_t	len16_start[18] = { 0 };	// bucket L = [start[L], start[L+1])
 	/* terms longer than 16 bytes, any length (generic path) */
@@ -56,12 +75,20 @@ struct FuzzyImage {
 	uint32_t	max_len = 0;
 };
 
+/* Signature bit of a byte: collision-free on [a-z0-9], any map is valid. */
+__host__ __device__ __forceinline__ unsigned long long
+fz_sig_bit(unsigned char b)
+{
+	return 1ull << ((((uint32_t)b * 225u) >> 5) & 63u);
+}
+
 static void
 fuzzy_free(FuzzyImage &f)
 {
 	cudaFree(f.d_blob); cudaFree(f.d_off); cudaFree(f.d_live);
 	cudaFree(f.d_parent); cudaFree(f.d_edge); cudaFree(f.d_rank);
 	cudaFree(f.d_slot16); cudaFree(f.d_slot16_term); cudaFree(f.d_long_term);
+	cudaFree(f.d_sig16); cudaFree(f.d_sig32);
 	f = FuzzyImage();
 }
 
@@ -91,6 +118,8 @@ fuzzy_load(FuzzyImage &f, uint32_t V, const char *blob, const uint32_t *off,
 	f.n_long = longs.size();
 
 	std::vector<uint4> slots(f.n16 ? f.n16 : 1);
+	std::vector<unsigned long long> sigs(f.n16 ? f.n16 : 1);
+	std::vector<uint32_t> sigs32((size_t)f.n16 + 8, 0u);
 	std::vector<uint32_t> slot_term(f.n16 ? f.n16 : 1), cur(f.len16_start, f.len16_start + 18);
 	for (uint32_t t = 0; t < V; t++) {
 		const uint32_t len = off[t + 1] - off[t];
@@ -100,6 +129,11 @@ fuzzy_load(FuzzyImage &f, uint32_t V, const char *blob, const uint32_t *off,
 		unsigned char b[16] = { 0 };
 		memcpy(b, blob + off[t], len);
 		memcpy(&slots[cur[len]], b, 16);
+		unsigned long long sg = 0;
+		for (uint32_t i = 0; i < len; i++)
+			sg |= fz_sig_bit(b[i]);
+		sigs[cur[len]] = sg;
+		sigs32[cur[len]] = (uint32_t)(sg | (sg >> 32));
 		slot_term[cur[len]] = t;
 		cur[len]++;
 	}
@@ -110,6 +144,8 @@ fuzzy_load(FuzzyImage &f, uint32_t V, const char *blob, const uint32_t *off,
 	    cudaMalloc(&f.d_edge, V ? V : 1) || cudaMalloc(&f.d_rank, (size_t)(V ? V : 1) * 4) ||
 	    cudaMalloc(&f.d_slot16, slots.size() * 16) ||
 	    cudaMalloc(&f.d_slot16_term, slot_term.size() * 4) ||
+	    cudaMalloc(&f.d_sig16, sigs.size() * 8) ||
+	    cudaMalloc(&f.d_sig32, sigs32.size() * 4) ||
 	    cudaMalloc(&f.d_long_term, (longs.size() ? longs.size() : 1) * 4))
 		return -1;
 	cudaMemcpyAsync(f.d_blob, blob, blob_len, cudaMemcpyHostToDevice, st);
@@ -120,6 +156,8 @@ fuzzy_load(FuzzyImage &f, uint32_t V, const char *blob, const uint32_t *off,
 	cudaMemcpyAsync(f.d_rank, rank, (size_t)V * 4, cudaMemcpyHostToDevice, st);
 	cudaMemcpyAsync(f.d_slot16, slots.data(), (size_t)f.n16 * 16, cudaMemcpyHostToDevice, st);
 	cudaMemcpyAsync(f.d_slot16_term, slot_term.data(), (size_t)f.n16 * 4, cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(f.d_sig16, sigs.data(), (size_t)f.n16 * 8, cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(f.d_sig32, sigs32.data(), sigs32.size() * 4, cudaMemcpyHostToDevice, st);
 	cudaMemcpyAsync(f.d_long_term, longs.data(), longs.size() * 4, cudaMemcpyHostToDevice, st);
 	if (cudaStreamSynchronize(st) != cudaSuccess)
 		return -1;
@@ -225,51 +263,75 @@ fuzzy_consider(const FuzzyImage &f, const W *peq, int m, uint32_t t, int d,
 
 /*
  * One warp per query term.  W = uint32_t for queries of <= 32 bytes,
- * unsigned long long for <= 64.
+ * unsigned long long for <= 64; NW query terms per CTA.
  */
-template <typename W>
-__global__ void __launch_bounds__(FZ_WARPS * 32)
+template <typename W, int NW>
+__global__ void __launch_bounds__(NW * 32)
 fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
     const uint32_t *__restrict__ qoff, const uint32_t *__restrict__ qsel,
     uint32_t n_sel, uint32_t *__restrict__ out_term,
     uint32_t *__restrict__ out_dist, uint32_t *__restrict__ out_true)
 {
-	__shared__ W s_peq[FZ_WARPS][256];
+	__shared__ W s_peq[NW][256];
+	__shared__ __align__(16) uint32_t s_sig[2][FZ_CHUNK];
+	__shared__ uint32_t s_queue[NW][64];	/* slots that passed the signature test */
+	__shared__ int s_lo, s_hi;
 
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const uint32_t wi = blockIdx.x * FZ_WARPS + warp;
+	const uint32_t wi = blockIdx.x * NW + warp;
+	const bool active = wi < n_sel;
 	W *peq = s_peq[warp];
+	uint32_t *queue = s_queue[warp];
+	uint32_t qi = 0;
+	int m = 0, l_lo = 1, l_hi = 0;
+	unsigned long long qsig = 0;
 
-	if (wi >= n_sel)
-		return;
-	const uint32_t qi = qsel[wi];
-	const unsigned char *q = qblob + qoff[qi];
-	const int m = (int)(qoff[qi + 1] - qoff[qi]);
-
-	for (int c = lane; c < 256; c += 32)
-		peq[c] = 0;
-	__syncwarp();
-	for (int i = lane; i < m; i += 32) {
-		/* Distinct lanes may share a byte value: OR atomically. */
-		if (sizeof(W) == 4)
-			atomicOr(reinterpret_cast<unsigned int *>(&peq[q[i]]), 1u << i);
-		else
-			atomicOr(reinterpret_cast<unsigned long long *>(&peq[q[i]]), 1ull << i);
+	if (threadIdx.x == 0) {
+		s_lo = 17;
+		s_hi = 0;
 	}
-	__syncwarp();
+	__syncthreads();
+	if (active) {
+		qi = qsel[wi];
+		const unsigned char *q = qblob + qoff[qi];
+
+		m = (int)(qoff[qi + 1] - qoff[qi]);
+		for (int c = lane; c < 256; c += 32)
+			peq[c] = 0;
+		__syncwarp();
+		for (int i = lane; i < m; i += 32) {
+			/* Distinct lanes may share a byte value: OR atomically. */
+			if (sizeof(W) == 4)
+				atomicOr(reinterpret_cast<unsigned int *>(&peq[q[i]]), 1u << i);
+			else
+				atomicOr(reinterpret_cast<unsigned long long *>(&peq[q[i]]), 1ull << i);
+			qsig |= fz_sig_bit(q[i]);
+		}
+		for (int o = 16; o; o >>= 1)
+			qsig |= __shfl_xor_sync(0xffffffffu, qsig, o);
+		/* 16-byte slots, only the length buckets within the tolerance. */
+		l_lo = m - FZ_TOLERANCE < 1 ? 1 : m - FZ_TOLERANCE;
+		l_hi = m + FZ_TOLERANCE > 16 ? 16 : m + FZ_TOLERANCE;
+		if (lane == 0 && l_lo <= l_hi) {
+			atomicMin(&s_lo, l_lo);
+			atomicMax(&s_hi, l_hi);
+		}
+	}
+	__syncthreads();
+	const int cta_lo = s_lo, cta_hi = s_hi;
 
 	FuzzyBest best = { 0xffffffffu, 0xffffffffu, 0 };
-	uint32_t n_true = 0;
+	uint32_t n_true = 0, nq = 0;
 
-	/* 16-byte slots, only the length buckets within the tolerance. */
-	const int l_lo = m - FZ_TOLERANCE < 1 ? 1 : m - FZ_TOLERANCE;
-	const int l_hi = m + FZ_TOLERANCE > 16 ? 16 : m + FZ_TOLERANCE;
-
-	for (int L = l_lo; L <= l_hi; L++) {
-		const uint32_t s0 = f.len16_start[L], s1 = f.len16_start[L + 1];
-
-		for (uint32_t s = s0 + lane; s < s1; s += 32) {
+	/* Myers over the first cnt queued survivors, one per lane. */
+	auto drain = [&](uint32_t cnt) {
+		if (lane < cnt) {
+			const uint32_t s = queue[lane];
+			int L = l_lo;
 			const uint4 w = __ldg(f.d_slot16 + s);
+
+			while (s >= f.len16_start[L + 1])	/* the slot's length bucket */
+				L++;
 			const uint32_t ww[4] = { w.x, w.y, w.z, w.w };
 			MyersState<W> st;
 
@@ -283,7 +345,109 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 				fuzzy_consider<W>(f, peq, m, __ldg(f.d_slot16_term + s),
 				    st.score, best, n_true);
 		}
+		__syncwarp();
+	};
+
+	/*
+	 * The folded signatures of the CTA's buckets, FZ_CHUNK at a time through
+	 * two shared buffers: the next chunk is fetched into registers before
+	 * the current one is scanned and stored after, so that the loads'
+	 * latency hides behind the scan.  A warp tests 128 signatures per round
+	 * (one 16-byte load of four per lane).  Buckets ascend by length, so the
+	 * slots of THIS query's buckets are one range [my0, my1).
+	 */
+	static_assert(FZ_CHUNK % (NW * 32 * 4) == 0, "one or more uint4 per thread");
+	constexpr int PER_T = FZ_CHUNK / (NW * 32 * 4);
+	/* Chunks start at multiples of 4 slots: 16-byte loads of d_sig32 (padded). */
+	const uint32_t g0 = cta_lo <= cta_hi ? f.len16_start[cta_lo] & ~3u : 0u;
+	const uint32_t g1 = cta_lo <= cta_hi ? f.len16_start[cta_hi + 1] : 0u;
+	const uint32_t my0 = l_lo <= l_hi ? f.len16_start[l_lo] : 0u;
+	const uint32_t my1 = l_lo <= l_hi ? f.len16_start[l_hi + 1] : 0u;
+	const uint32_t q32 = (uint32_t)(qsig | (qsig >> 32));
+	uint4 pre[PER_T];
+	uint32_t buf = 0;
+
+	auto fetch = [&](uint32_t c0) {
+#pragma unroll
+		for (int u = 0; u < PER_T; u++) {
+			const uint32_t j = 4u * (threadIdx.x + u * NW * 32);
+
+			pre[u] = c0 + j < g1 ? __ldg(reinterpret_cast<const uint4 *>(f.d_sig32 + c0 + j))
+			    : make_uint4(0u, 0u, 0u, 0u);
+		}
+	};
+	auto stash = [&](uint32_t b) {
+#pragma unroll
+		for (int u = 0; u < PER_T; u++)
+			reinterpret_cast<uint4 *>(s_sig[b])[threadIdx.x + u * NW * 32] = pre[u];
+	};
+	if (g0 < g1) {
+		fetch(g0);
+		stash(0);
 	}
+	__syncthreads();
+	for (uint32_t c0 = g0; c0 < g1; c0 += FZ_CHUNK, buf ^= 1u) {
+		const uint32_t n = g1 - c0 < FZ_CHUNK ? g1 - c0 : FZ_CHUNK;
+		const bool more = c0 + FZ_CHUNK < g1;
+
+		if (more)
+			fetch(c0 + FZ_CHUNK);
+		if (active && c0 < my1 && c0 + n > my0) {
+			const uint4 *sg4 = reinterpret_cast<const uint4 *>(s_sig[buf]);
+
+			for (uint32_t base = 0; base < n; base += 128) {
+				const uint4 t4 = sg4[(base >> 2) + lane];
+				const uint32_t ts[4] = { t4.x, t4.y, t4.z, t4.w };
+				const uint32_t slot0 = c0 + base + 4u * lane;
+				uint32_t hit = 0;
+
+#pragma unroll
+				for (int u = 0; u < 4; u++)
+					hit |= (__popc(q32 ^ ts[u]) <= 2 * FZ_TOLERANCE &&
+					    slot0 + u >= my0 && slot0 + u < my1) ? 1u << u : 0u;
+				if (!__any_sync(0xffffffffu, hit != 0))
+					continue;
+#pragma unroll
+				for (int u = 0; u < 4; u++) {
+					bool pass = false;
+
+					if (hit & (1u << u)) {
+						/* The two-sided test on the full signature. */
+						const unsigned long long tl = __ldg(f.d_sig16 + slot0 + u);
+
+						pass = __popcll(qsig & ~tl) <= FZ_TOLERANCE &&
+						    __popcll(tl & ~qsig) <= FZ_TOLERANCE;
+					}
+					const uint32_t pm = __ballot_sync(0xffffffffu, pass);
+
+					if (pm == 0)
+						continue;
+					if (pass)
+						queue[nq + __popc(pm & ((1u << lane) - 1u))] = slot0 + u;
+					nq += __popc(pm);
+					__syncwarp();
+					if (nq >= 32) {
+						drain(32);
+						/* The leftovers (< 32) move to the front. */
+						const uint32_t left = nq - 32;
+						const uint32_t e = lane < left ? queue[32 + lane] : 0u;
+
+						__syncwarp();
+						if (lane < left)
+							queue[lane] = e;
+						nq = left;
+						__syncwarp();
+					}
+				}
+			}
+		}
+		if (more)
+			stash(buf ^ 1u);
+		__syncthreads();
+	}
+	if (!active)
+		return;
+	drain(nq);
 
 	/* Terms longer than 16 bytes: byte-wise from the blob. */
 	for (uint32_t i = lane; i < f.n_long; i += 32) {
@@ -348,6 +512,12 @@ fuzzy_run(FuzzyImage &f, uint32_t n, const char *qblob, const uint32_t *qoff,
 		else if (m >= 33 && m <= FZ_MAX_QLEN)
 			sel64.push_back(i);
 	}
+	/* Query terms of like length share a CTA, hence its staged buckets. */
+	auto by_len = [&](uint32_t a, uint32_t b) {
+		return qoff[a + 1] - qoff[a] < qoff[b + 1] - qoff[b];
+	};
+	std::stable_sort(sel32.begin(), sel32.end(), by_len);
+	std::stable_sort(sel64.begin(), sel64.end(), by_len);
 	do {
 		if (cudaMalloc(&d_qblob, qoff[n] + 16) || cudaMalloc(&d_qoff, ((size_t)n + 1) * 4) ||
 		    cudaMalloc(&d_sel32, (sel32.size() + 1) * 4) ||
@@ -363,13 +533,13 @@ fuzzy_run(FuzzyImage &f, uint32_t n, const char *qblob, const uint32_t *qoff,
 		cudaMemsetAsync(d_dist, 0, (size_t)n * 4, st);
 		cudaMemsetAsync(d_true, 0, (size_t)n * 4, st);
 		if (!sel32.empty()) {
-			fuzzy_scan_kernel<uint32_t><<<(sel32.size() + FZ_WARPS - 1) / FZ_WARPS,
-			    FZ_WARPS * 32, 0, st>>>(f, d_qblob, d_qoff, d_sel32,
+			fuzzy_scan_kernel<uint32_t, FZ_WARPS32><<<(sel32.size() + FZ_WARPS32 - 1) / FZ_WARPS32,
+			    FZ_WARPS32 * 32, 0, st>>>(f, d_qblob, d_qoff, d_sel32,
 			    sel32.size(), d_term, d_dist, d_true);
 			(*launches)++;
 		}
 		if (!sel64.empty()) {
-			fuzzy_scan_kernel<unsigned long long><<<(sel64.size() + FZ_WARPS - 1) / FZ_WARPS,
+			fuzzy_scan_kernel<unsigned long long, FZ_WARPS><<<(sel64.size() + FZ_WARPS - 1) / FZ_WARPS,
 			    FZ_WARPS * 32, 0, st>>>(f, d_qblob, d_qoff, d_sel64,
 			    sel64.size(), d_term, d_dist, d_true);
 			(*launches)++;
