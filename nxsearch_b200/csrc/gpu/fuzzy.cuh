@@ -274,14 +274,15 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 {
 	__shared__ W s_peq[NW][256];
 	__shared__ __align__(16) uint32_t s_sig[2][FZ_CHUNK];
-	__shared__ uint32_t s_queue[NW][64];	/* slots that passed the signature test */
+	__shared__ uint32_t s_queue[NW][64];	/* slots that passed the 64-bit signature test */
+	__shared__ uint32_t s_first[NW][160];	/* ... the folded one (up to 128 join per round) */
 	__shared__ int s_lo, s_hi;
 
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t wi = blockIdx.x * NW + warp;
 	const bool active = wi < n_sel;
 	W *peq = s_peq[warp];
-	uint32_t *queue = s_queue[warp];
+	uint32_t *queue = s_queue[warp], *first = s_first[warp];
 	uint32_t qi = 0;
 	int m = 0, l_lo = 1, l_hi = 0;
 	unsigned long long qsig = 0;
@@ -386,6 +387,47 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 		stash(0);
 	}
 	__syncthreads();
+	/*
+	 * The two-sided test on the full signatures of 32 queued slots (the last
+	 * 32), one per lane: 32 independent loads in flight instead of a
+	 * divergent one per hit.  What passes joins the Myers queue.
+	 */
+	uint32_t nf = 0;
+	auto sift = [&]() {
+		const uint32_t cnt = nf < 32 ? nf : 32;
+		const uint32_t at = nf - cnt;
+		bool pass = false;
+		uint32_t slot = 0;
+
+		if (lane < cnt) {
+			slot = first[at + lane];
+			const unsigned long long tl = __ldg(f.d_sig16 + slot);
+
+			pass = __popcll(qsig & ~tl) <= FZ_TOLERANCE &&
+			    __popcll(tl & ~qsig) <= FZ_TOLERANCE;
+		}
+		const uint32_t pm = __ballot_sync(0xffffffffu, pass);
+
+		nf = at;
+		if (pm) {
+			if (pass)
+				queue[nq + __popc(pm & ((1u << lane) - 1u))] = slot;
+			nq += __popc(pm);
+			__syncwarp();
+			if (nq >= 32) {
+				drain(32);
+				/* The leftovers (< 32) move to the front. */
+				const uint32_t left = nq - 32;
+				const uint32_t e = lane < left ? queue[32 + lane] : 0u;
+
+				__syncwarp();
+				if (lane < left)
+					queue[lane] = e;
+				nq = left;
+			}
+		}
+		__syncwarp();
+	};
 	for (uint32_t c0 = g0; c0 < g1; c0 += FZ_CHUNK, buf ^= 1u) {
 		const uint32_t n = g1 - c0 < FZ_CHUNK ? g1 - c0 : FZ_CHUNK;
 		const bool more = c0 + FZ_CHUNK < g1;
@@ -407,38 +449,19 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 					    slot0 + u >= my0 && slot0 + u < my1) ? 1u << u : 0u;
 				if (!__any_sync(0xffffffffu, hit != 0))
 					continue;
+				/* Queue what passed (slot order is irrelevant to the answer). */
 #pragma unroll
 				for (int u = 0; u < 4; u++) {
-					bool pass = false;
+					const bool h = (hit >> u) & 1u;
+					const uint32_t hm = __ballot_sync(0xffffffffu, h);
 
-					if (hit & (1u << u)) {
-						/* The two-sided test on the full signature. */
-						const unsigned long long tl = __ldg(f.d_sig16 + slot0 + u);
-
-						pass = __popcll(qsig & ~tl) <= FZ_TOLERANCE &&
-						    __popcll(tl & ~qsig) <= FZ_TOLERANCE;
-					}
-					const uint32_t pm = __ballot_sync(0xffffffffu, pass);
-
-					if (pm == 0)
-						continue;
-					if (pass)
-						queue[nq + __popc(pm & ((1u << lane) - 1u))] = slot0 + u;
-					nq += __popc(pm);
-					__syncwarp();
-					if (nq >= 32) {
-						drain(32);
-						/* The leftovers (< 32) move to the front. */
-						const uint32_t left = nq - 32;
-						const uint32_t e = lane < left ? queue[32 + lane] : 0u;
-
-						__syncwarp();
-						if (lane < left)
-							queue[lane] = e;
-						nq = left;
-						__syncwarp();
-					}
+					if (h)
+						first[nf + __popc(hm & ((1u << lane) - 1u))] = slot0 + u;
+					nf += __popc(hm);
 				}
+				__syncwarp();
+				while (nf >= 32)
+					sift();
 			}
 		}
 		if (more)
@@ -447,6 +470,8 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 	}
 	if (!active)
 		return;
+	while (nf)
+		sift();
 	drain(nq);
 
 	/* Terms longer than 16 bytes: byte-wise from the blob. */
