@@ -106,6 +106,9 @@ struct Batch {
 	uint32_t	n_virtual = 0, n_tok_all = 0;
 	std::vector<uint2> q_base;
 	uint2 *		d_qbase = nullptr;
+	/* Boolean queries: {columns, count | token slots << 8}, no virtual queries. */
+	std::vector<uint2> q_base_logic;
+	uint2 *		d_qbase_logic = nullptr;
 	unsigned long long *d_prefix_keys = nullptr;	// [n_virtual][limit] top-k keys
 	uint32_t *	d_prefix_cnt = nullptr;		// [n_virtual]
 	/* One H2D copy: [queries | tokens | prog | qlist_or | qlist_logic]. */
@@ -908,6 +911,31 @@ nxsb_engine_set_dead(nxsb_engine_t *e, uint32_t segment, const uint64_t *ids,
  * Batches.
  */
 
+/* The query's postfix program for a document held by exactly the token slots in m. */
+static bool
+eval_program(const nxsb_batch_t *b, const nxsb_query_t &q, uint32_t m)
+{
+	bool st[NXSB_MAX_QUERY_PROG / 2 + 2];
+	int sp = 0;
+
+	for (uint32_t c = 0; c < q.n_prog; c++) {
+		const int32_t op = b->prog[q.prog_off + c];
+
+		if (op >= 0) {
+			st[sp++] = (m >> op) & 1u;
+		} else if (op == NXSB_OP_EMPTY) {
+			st[sp++] = false;
+		} else {
+			const bool y = st[--sp];
+			const bool x = st[sp - 1];
+
+			st[sp - 1] = op == NXSB_OP_AND ? (x && y) :
+			    op == NXSB_OP_OR ? (x || y) : (x && !y);
+		}
+	}
+	return sp ? st[sp - 1] : false;
+}
+
 static bool
 is_pure_or(const nxsb_batch_t *b, const nxsb_query_t &q)
 {
@@ -1098,6 +1126,66 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 			qbase[i] = make_uint2(cols, nd | (pn << 8));
 		}
 	}
+	/*
+	 * Boolean queries: the same base columns when the dense terms lead AND no
+	 * document can satisfy the query through dense terms alone -- then only
+	 * the documents the other terms name can match, the dense terms' scores
+	 * and membership bits are gathered for those, and nothing else is needed
+	 * (no virtual query).
+	 */
+	B.q_base_logic.assign(B.q_logic.size(), make_uint2(0u, 0u));
+	if (e->share_dense && e->n_dense && !e->wide && !e->force_v2 &&
+	    B.limit <= ST_K_MAX && B.max_tokens <= ST_LOGIC_TOKENS && !e->h_dense_col.empty()) {
+		for (size_t i = 0; i < B.q_logic.size(); i++) {
+			const nxsb_query_t &q = b->queries[B.q_logic[i]];
+			uint32_t terms[4], slots[4], nd = 0, first_sparse = q.n_tokens, last_dense = 0;
+			uint32_t dmask = 0;
+			bool ok = true;
+
+			for (uint32_t j = 0; j < q.n_tokens && ok; j++) {
+				const uint32_t id = b->tokens[q.tok_off + j];
+				const bool dense = id >= 1 && id <= e->n_terms &&
+				    e->h_dense_col[id - 1] >= 0;
+
+				if (dense) {
+					if (nd == 4) {
+						ok = false;
+						break;
+					}
+					for (uint32_t x = 0; x < nd; x++)
+						ok &= terms[x] != id;
+					terms[nd] = id;
+					slots[nd++] = j;
+					dmask |= 1u << j;
+					last_dense = j;
+				} else if (first_sparse == q.n_tokens) {
+					first_sparse = j;
+				}
+			}
+			if (!ok || nd == 0 || first_sparse == q.n_tokens)
+				continue;
+			if (!(last_dense < first_sparse ||
+			    (nd == 1 && last_dense == 1 && first_sparse == 0)))
+				continue;
+			/* Every subset of the dense terms, the empty one included. */
+			for (uint32_t m = dmask;; m = (m - 1) & dmask) {
+				if (eval_program(b, q, m)) {
+					ok = false;
+					break;
+				}
+				if (m == 0)
+					break;
+			}
+			if (!ok)
+				continue;
+			uint32_t cols = 0, y = nd;
+			for (uint32_t x = 0; x < nd; x++) {
+				cols |= (uint32_t)e->h_dense_col[terms[x] - 1] << (8 * x);
+				y |= slots[x] << (8 + 3 * x);
+			}
+			B.q_base_logic[i] = make_uint2(cols, y);
+		}
+	}
 	B.n_virtual = vq.size();
 	B.n_tok_all = B.n_tok + vtok.size();
 	/* q_or = [virtual queries | the batch's OR queries]; q_base likewise. */
@@ -1119,7 +1207,8 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 	const size_t o_or = o_prog + align16((size_t)B.n_prog * 4);
 	const size_t o_base = o_or + align16(B.q_or.size() * 4);
 	const size_t o_lg = o_base + align16(B.q_or.size() * sizeof(uint2));
-	const size_t desc_bytes = o_lg + align16(B.q_logic.size() * 4);
+	const size_t o_lgb = o_lg + align16(B.q_logic.size() * 4);
+	const size_t desc_bytes = o_lgb + align16(B.q_logic.size() * sizeof(uint2));
 
 	const size_t s_toks = 0;
 	const size_t s_skip = s_toks + align16((size_t)B.n_tok_all * sizeof(DTok));
@@ -1147,6 +1236,7 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 	B.d_qlist_or = (uint32_t *)(d + o_or);
 	B.d_qbase = (uint2 *)(d + o_base);
 	B.d_qlist_logic = (uint32_t *)(d + o_lg);
+	B.d_qbase_logic = (uint2 *)(d + o_lgb);
 	B.d_toks = (DTok *)(sc + s_toks);
 	B.d_tmp_skip = (uint32_t *)(sc + s_skip);
 	B.d_prefix_keys = (unsigned long long *)(sc + s_pkey);
@@ -1166,6 +1256,7 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 	memcpy(h + o_or, B.q_or.data(), B.q_or.size() * 4);
 	memcpy(h + o_base, B.q_base.data(), B.q_base.size() * sizeof(uint2));
 	memcpy(h + o_lg, B.q_logic.data(), B.q_logic.size() * 4);
+	memcpy(h + o_lgb, B.q_base_logic.data(), B.q_base_logic.size() * sizeof(uint2));
 	CK(e, cudaMemcpyAsync(d, h, desc_bytes, cudaMemcpyHostToDevice, e->stream));
 	return 0;
 }
@@ -1434,8 +1525,9 @@ run_list(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list,
 	 * its own dense columns as before.
 	 */
 	const uint32_t n_virtual = LOGIC ? 0 : B.n_virtual;
-	const uint2 *d_qbase = (!LOGIC && stream && n_virtual && chunk >= n_list)
-	    ? B.d_qbase : nullptr;
+	const uint2 *d_qbase = !stream ? nullptr
+	    : LOGIC ? B.d_qbase_logic		/* no virtual queries: any chunking */
+	    : (n_virtual && chunk >= n_list) ? B.d_qbase : nullptr;
 
 	for (uint32_t q0 = 0; q0 < n_list; q0 += chunk) {
 		const uint32_t n = std::min(chunk, n_list - q0);
@@ -1451,7 +1543,7 @@ run_list(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list,
 			fs.queries = B.d_queries;
 			fs.toks = B.d_toks;
 			fs.post = e->d_post;
-			fs.qbase = d_qbase ? d_qbase + q0 : nullptr;
+			fs.qbase = (!LOGIC && d_qbase) ? d_qbase + q0 : nullptr;
 			fs.prefix_keys = B.d_prefix_keys;
 			fs.prefix_cnt = B.d_prefix_cnt;
 			fs.n_real = B.n_q;

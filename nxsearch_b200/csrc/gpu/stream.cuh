@@ -234,7 +234,7 @@ plan_items_kernel(const QDesc *__restrict__ queries,
 	h.total = total;
 	h.ntok = m;
 	h.base_cols = qb.x;
-	h.nbase = nbase;
+	h.nbase = qb.y;		/* count | (boolean) token slots or (OR) prefix number */
 	*reinterpret_cast<PlanHdr *>(rec) = h;
 }
 
@@ -751,14 +751,26 @@ score_stream_kernel(const StreamParams p)
 	 * from the fold of the query's leading dense score columns, which is
 	 * what streaming those columns first would have left there.
 	 */
-	constexpr bool BASE = !LOGIC && !WIDE;
-	uint32_t nbase = 0, base_cols = 0;
+	constexpr bool BASE = !WIDE;
+	uint32_t nbase = 0, base_cols = 0, base_slots = 0;
 	const float *colf = reinterpret_cast<const float *>(p.dense);
-	auto base_of = [&](uint32_t doc) -> float {
+	/*
+	 * Boolean queries also need the membership bits of the base terms: a
+	 * document is in a dense term's list iff its column value is not 0.
+	 * base_slots holds the terms' token slots, 3 bits each.
+	 */
+	auto base_of = [&](uint32_t doc, uint32_t &bits) -> float {
 		float b = __ldg(colf + (base_cols & 0xffu) * p.col_words + doc);
 
-		for (uint32_t x = 1; x < nbase; x++)
-			b = __fadd_rn(b, __ldg(colf + ((base_cols >> (8u * x)) & 0xffu) * p.col_words + doc));
+		if (LOGIC)
+			bits = b != 0.f ? 1u << (base_slots & 7u) : 0u;
+		for (uint32_t x = 1; x < nbase; x++) {
+			const float v = __ldg(colf + ((base_cols >> (8u * x)) & 0xffu) * p.col_words + doc);
+
+			b = __fadd_rn(b, v);
+			if (LOGIC)
+				bits |= v != 0.f ? 1u << ((base_slots >> (3u * x)) & 7u) : 0u;
+		}
 		return b;
 	};
 	auto note = [&](uint32_t rel) {
@@ -791,7 +803,8 @@ score_stream_kernel(const StreamParams p)
 			const uint32_t tb = m.ths_bits;
 
 			if (BASE) {
-				nbase = m.nbase;
+				nbase = m.nbase & 0xffu;
+				base_slots = m.nbase >> 8;	/* boolean queries (OR: prefix number, unused here) */
 				base_cols = m.base_cols;
 			}
 
@@ -903,11 +916,12 @@ score_stream_kernel(const StreamParams p)
 			for (int r = 0; r < SLOTS; r++)
 				v[r] = buf[ctid + r * ST_NCONS];
 			float bs[SLOTS];
+			uint32_t bb[SLOTS];
 			if (BASE && nbase) {
 				/* In flight while the postings are scored. */
 #pragma unroll
 				for (int r = 0; r < SLOTS; r++)
-					bs[r] = base_of(v[r].x);
+					bs[r] = base_of(v[r].x, bb[r]);
 			}
 			st_score<WIDE, ALGO, SLOTS>(p, s_logtab, v, __uint_as_float(hdr.w), sc);
 			/* Documents of one list are distinct: batch the updates. */
@@ -916,8 +930,12 @@ score_stream_kernel(const StreamParams p)
 				a[r] = lds_f32(accb + 4u * v[r].x);
 			if (BASE && nbase) {
 #pragma unroll
-				for (int r = 0; r < SLOTS; r++)
+				for (int r = 0; r < SLOTS; r++) {
+					/* Later touches keep the bits the first one set. */
+					if (LOGIC)
+						bb[r] = a[r] == 0.f ? bb[r] : 0u;
 					a[r] = a[r] == 0.f ? bs[r] : a[r];
+				}
 			}
 			float top = 0.f;
 #pragma unroll
@@ -941,7 +959,8 @@ score_stream_kernel(const StreamParams p)
 					mb[r] = memb[v[r].x - tile_lo];
 #pragma unroll
 				for (int r = 0; r < SLOTS; r++)
-					memb[v[r].x - tile_lo] = mb[r] | bit;
+					memb[v[r].x - tile_lo] = mb[r] | bit |
+					    (uint8_t)((BASE && nbase) ? bb[r] : 0u);
 			}
 			PROF(3);		/* full stage */
 		} else {
@@ -976,11 +995,12 @@ score_stream_kernel(const StreamParams p)
 							v[r] = buf[i];
 					}
 					float bs[2];
+					uint32_t bb[2] = { 0u, 0u };
 					if (BASE && nbase) {
 #pragma unroll
 						for (int r = 0; r < 2; r++)
 							if (ok[r])
-								bs[r] = base_of(v[r].x);
+								bs[r] = base_of(v[r].x, bb[r]);
 					}
 					st_score<WIDE, ALGO, 2>(p, s_logtab, v, idf, sc);
 #pragma unroll
@@ -990,8 +1010,11 @@ score_stream_kernel(const StreamParams p)
 					if (BASE && nbase) {
 #pragma unroll
 						for (int r = 0; r < 2; r++)
-							if (ok[r])
+							if (ok[r]) {
+								if (LOGIC)
+									bb[r] = a[r] == 0.f ? bb[r] : 0u;
 								a[r] = a[r] == 0.f ? bs[r] : a[r];
+							}
 					}
 #pragma unroll
 					for (int r = 0; r < 2; r++)
@@ -1005,7 +1028,7 @@ score_stream_kernel(const StreamParams p)
 #pragma unroll
 						for (int r = 0; r < 2; r++)
 							if (ok[r])
-								memb[v[r].x - tile_lo] |= bit;
+								memb[v[r].x - tile_lo] |= bit | (uint8_t)bb[r];
 					}
 				}
 			}

@@ -224,3 +224,58 @@ def test_shared_dense_prefixes_every_token_order(corpus, oracle, eng):
             check_topk(ids[i, :counts[i]], scores[i, :counts[i]], all_ids, all_sc, 10, exact_scores=True)
     finally:
         e2.close()
+
+
+def test_boolean_queries_with_base_columns(corpus, oracle, eng):
+    """Boolean queries whose dense terms lead and cannot match on their own take
+    those terms' scores and membership from the score columns; the others
+    stream them.  All shapes against the tile kernel (bit-equal) and the oracle."""
+    from nxsearch_b200 import engine
+
+    df = np.asarray(corpus.term_df)
+    dense = [int(t) + 1 for t in np.flatnonzero(df >= 0.6 * corpus.n_docs)][:5]
+    d1, d2, d3 = dense[:3]
+    sp = [int(t) for t in corpus.query_terms(64, seed=777) if int(t) not in dense][:8]
+    s1, s2, s3, s4 = sp[:4]
+    A, O, N = OP_AND, OP_OR, OP_ANDNOT
+    shapes = [
+        ([d1, s1], [0, 1, A]),                      # d AND s
+        ([d1, s1], [1, 0, N]),                      # s AND NOT d
+        ([d1, s1], [0, 1, N]),                      # d AND NOT s: dense alone matches -> streams
+        ([d1, d2, s1], [0, 1, A, 2, A]),            # d AND d AND s
+        ([d1, d2, s1], [0, 1, O, 2, A]),            # (d OR d) AND s
+        ([d1, s1, s2], [0, 1, O, 2, A]),            # (d OR s) AND s
+        ([s1, d1, s2], [0, 1, A, 2, O]),            # [s, d, s]: (s AND d) OR s
+        ([s1, d1, s2], [0, 2, O, 1, A]),            # (s OR s) AND d  -- sparse required
+        ([s1, s2, d1], [0, 1, A, 2, A]),            # dense last -> streams
+        ([d1, s1, d2], [0, 1, A, 2, A]),            # dense apart -> streams
+        ([d1, d2, d3, s1, s2], [0, 1, O, 2, O, 3, 4, O, A]),   # (d|d|d) AND (s|s)
+        ([d1, s1, s2, s3], [1, 2, O, 3, O, 0, N]),  # (s|s|s) AND NOT d
+        ([d1, s1], [0, 1, O]),                      # pure OR goes the other way (prefix)
+        ([s1, s2], [0, 1, A]),
+    ]
+    qs = shapes * 4 + bool_queries(corpus, 60)
+    os.environ["NXSB_KERNEL"] = "v2"
+    try:
+        e2 = engine.Engine(0)
+    finally:
+        del os.environ["NXSB_KERNEL"]
+    e2.load_corpus(corpus)
+    try:
+        for algo in (TFIDF, BM25):
+            for limit in (1, 10, 100):
+                b = engine.Batch.from_lists(algo, limit, qs)
+                c1, i1, sc1 = eng.search(b)
+                c2, i2, sc2 = e2.search(b)
+                assert np.array_equal(c1, c2), (algo, limit)
+                assert np.array_equal(i1, i2), (algo, limit)
+                assert np.array_equal(sc1.view(np.uint32), sc2.view(np.uint32)), (algo, limit)
+        counts, ids, scores = eng.search(engine.Batch.from_lists(TFIDF, 100, shapes))
+        matched = 0
+        for i, (toks, prog) in enumerate(shapes):
+            all_ids, all_sc = oracle.search_all(TFIDF, toks, prog)
+            matched += len(all_ids) > 0
+            check_topk(ids[i, :counts[i]], scores[i, :counts[i]], all_ids, all_sc, 100, exact_scores=True)
+        assert matched >= 10
+    finally:
+        e2.close()
