@@ -1428,13 +1428,14 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist,
 	p.prof = e->d_prof;
 
 	if (LOGIC) {
-		/* Truth tables of the boolean programs: 8 words per query. */
-		const size_t want_tt = (size_t)n_q * 8 * 4;
+		/* Truth tables of the boolean programs and their subset closures:
+		 * 8 + 8 words per query. */
+		const size_t want_tt = (size_t)n_q * 16 * 4;
 
 		if (want_tt > e->tt_bytes) {
 			dev_free(e->d_tt);
 			e->tt_bytes = 0;
-			if (dev_alloc(&e->d_tt, (size_t)n_q * 8 * 2) != cudaSuccess)
+			if (dev_alloc(&e->d_tt, (size_t)n_q * 16 * 2) != cudaSuccess)
 				return fail(e, "truth table allocation failed");
 			e->tt_bytes = want_tt * 2;
 		}
@@ -1463,13 +1464,15 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist,
 	CK(e, cudaMemsetAsync(B.d_thr, 0, B.zero_bytes, e->stream));
 	CK(e, cudaMemsetAsync(e->d_tile_cnt, 0, want_cnt, e->stream));
 	mark(e, "plan");
-	plan_items_kernel<<<(unsigned)((items + 255) / 256), 256, 0, e->stream>>>(
-	    B.d_queries, d_qlist, d_qbase, B.d_toks, n_q, e->ntiles, stride, e->d_plan);
 	if (LOGIC) {
+		/* tt[n_q][8] truth tables, then tu[n_q][8] their subset closures. */
 		truth_tables_kernel<<<n_q, 256, 0, e->stream>>>(B.d_queries, d_qlist,
-		    B.d_prog, e->d_tt);
+		    B.d_prog, e->d_tt, e->d_tt + (size_t)n_q * 8);
 		e->launches++;
 	}
+	plan_items_kernel<<<(unsigned)((items + 255) / 256), 256, 0, e->stream>>>(
+	    B.d_queries, d_qlist, d_qbase, LOGIC ? e->d_tt + (size_t)n_q * 8 : nullptr,
+	    B.d_toks, n_q, e->ntiles, stride, e->d_plan);
 	mark(e, "score_tiles");
 	kern<<<grid, ST_THREADS, smem, e->stream>>>(p);
 	e->launches += 2;

@@ -178,7 +178,7 @@ struct StCfg {
 __global__ void __launch_bounds__(256)
 plan_items_kernel(const QDesc *__restrict__ queries,
     const uint32_t *__restrict__ qlist, const uint2 *__restrict__ qbase,
-    const DTok *__restrict__ toks,
+    const uint32_t *__restrict__ tu, const DTok *__restrict__ toks,
     uint32_t n_q, uint32_t ntiles, uint32_t stride,
     unsigned char *__restrict__ plan)
 {
@@ -195,13 +195,14 @@ plan_items_kernel(const QDesc *__restrict__ queries,
 	const uint32_t nbase = qb.y & 0xffu;
 	unsigned char *rec = plan + item * stride;
 	PlanTok *out = reinterpret_cast<PlanTok *>(rec + sizeof(PlanHdr));
-	uint32_t total = 0, m = 0;
+	uint32_t total = 0, m = 0, present = 0;
 
 	for (uint32_t j = 0; j < qd.n_tokens; j++) {
 		const DTok &t = toks[qd.tok_off + j];
 		const uint32_t lo = __ldg(t.skip + tile);
 		const uint32_t hi = __ldg(t.skip + tile + 1);
 
+		present |= hi > lo ? 1u << (j & 31u) : 0u;
 		/* The query's dense terms come in through its base columns. */
 		if (nbase && t.dense_off != DENSE_NONE)
 			continue;
@@ -230,6 +231,9 @@ plan_items_kernel(const QDesc *__restrict__ queries,
 		out[0] = out[1];
 		out[1] = t0;
 	}
+	/* Boolean query: can the tokens present in this tile satisfy it at all? */
+	if (tu && !((tu[slot * 8u + ((present & 255u) >> 5)] >> (present & 31u)) & 1u))
+		total = m = 0;
 	PlanHdr h;
 	h.total = total;
 	h.ntok = m;
@@ -247,8 +251,9 @@ plan_items_kernel(const QDesc *__restrict__ queries,
 __global__ void __launch_bounds__(256)
 truth_tables_kernel(const QDesc *__restrict__ queries,
     const uint32_t *__restrict__ qlist, const int32_t *__restrict__ prog,
-    uint32_t *__restrict__ tt)
+    uint32_t *__restrict__ tt, uint32_t *__restrict__ tu)
 {
+	__shared__ unsigned char s_any[256];
 	const QDesc qd = queries[qlist[blockIdx.x]];
 	const uint32_t m = threadIdx.x;
 	bool st[NXSB_MAX_QUERY_PROG / 2 + 2];
@@ -269,10 +274,28 @@ truth_tables_kernel(const QDesc *__restrict__ queries,
 			    op == NXSB_OP_OR ? (a || b) : (a && !b);
 		}
 	}
-	const uint32_t w = __ballot_sync(0xffffffffu, sp ? st[sp - 1] : false);
+	const bool sat = sp ? st[sp - 1] : false;
+	const uint32_t w = __ballot_sync(0xffffffffu, sat);
 
 	if ((m & 31) == 0)
 		tt[blockIdx.x * 8 + (m >> 5)] = w;
+	/*
+	 * tu[p] = "some document whose tokens are a subset of p satisfies the
+	 * query" (sum over subsets, one token at a time): a tile in which only
+	 * the tokens p have postings cannot hold a match when tu[p] is 0, and
+	 * plan_items_kernel leaves it out.
+	 */
+	s_any[m] = sat;
+	for (uint32_t bit = 1; bit < 256; bit <<= 1) {
+		__syncthreads();
+		const unsigned char below = (m & bit) ? s_any[m ^ bit] : 0;
+		__syncthreads();
+		s_any[m] |= below;
+	}
+	const uint32_t u = __ballot_sync(0xffffffffu, s_any[m] != 0);
+
+	if ((m & 31) == 0)
+		tu[blockIdx.x * 8 + (m >> 5)] = u;
 }
 
 /* ---- PTX wrappers ------------------------------------------------------ */
