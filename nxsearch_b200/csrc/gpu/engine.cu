@@ -749,7 +749,7 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 			bool ok = dev_alloc(&e->d_dense_col, V) == cudaSuccess &&
 			    dev_alloc(&e->d_dense, (size_t)e->n_dense * col_words) == cudaSuccess &&
 			    dev_alloc(&e->d_dense_sc, (size_t)e->n_dense * col_words) == cudaSuccess &&
-			    dev_alloc(&e->d_dense_used, 256) == cudaSuccess &&
+			    dev_alloc(&e->d_dense_used, 512) == cudaSuccess &&	/* used[256] | max score bits[256] */
 			    dev_alloc(&d_dterms, e->n_dense) == cudaSuccess;
 			if (ok) {
 				cudaMemcpyAsync(e->d_dense_col, col.data(), (size_t)V * 4,
@@ -1089,10 +1089,29 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 			}
 			if (!ok || nd == 0)
 				continue;
-			/* All dense tokens lead, or the list is [sparse, dense, sparse...]. */
+			/*
+			 * All dense tokens lead, or the list is [sparse, dense,
+			 * sparse...] (the first addition commutes): the sum starts
+			 * from them.  All dense tokens LAST: they are added to the
+			 * finished sums in the epilogue (0x80).  Anything else streams.
+			 */
+			uint32_t trailing = 0;
 			if (!(last_dense < first_sparse ||
-			    (nd == 1 && last_dense == 1 && first_sparse == 0)))
-				continue;
+			    (nd == 1 && last_dense == 1 && first_sparse == 0))) {
+				uint32_t first_dense = q.n_tokens, last_sparse = 0;
+
+				for (uint32_t j = 0; j < q.n_tokens; j++) {
+					const uint32_t id = b->tokens[q.tok_off + j];
+
+					if (id >= 1 && id <= e->n_terms && e->h_dense_col[id - 1] >= 0)
+						first_dense = std::min(first_dense, j);
+					else
+						last_sparse = j;
+				}
+				if (first_dense < last_sparse)
+					continue;
+				trailing = 0x80u;
+			}
 			uint64_t key = nd;
 			uint32_t cols = 0;
 			for (uint32_t x = 0; x < nd; x++) {
@@ -1123,7 +1142,7 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 				vtok.insert(vtok.end(), terms, terms + nd);
 				seen.emplace_back(key, pn);
 			}
-			qbase[i] = make_uint2(cols, nd | (pn << 8));
+			qbase[i] = make_uint2(cols, nd | trailing | (pn << 8));
 		}
 	}
 	/*
@@ -1443,6 +1462,7 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist,
 	p.tt = e->d_tt;
 	p.dense = reinterpret_cast<const uint32_t *>(e->d_dense_sc);
 	p.col_words = (unsigned long long)e->ntiles * TILE_DOCS;
+	p.dense_max = e->d_dense_used ? e->d_dense_used + 256 : nullptr;
 
 	auto kern = B.algo == NXSB_ALGO_BM25
 	    ? (e->wide ? score_stream_kernel<LOGIC, true, NXSB_ALGO_BM25>
@@ -1655,7 +1675,7 @@ run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
 	}
 
 	if (e->n_dense)
-		CK(e, cudaMemsetAsync(e->d_dense_used, 0, 256 * 4, st));
+		CK(e, cudaMemsetAsync(e->d_dense_used, 0, 512 * 4, st));
 	resolve_tokens_kernel<<<(B.n_tok_all + 255) / 256, 256, 0, st>>>(
 	    B.d_tokens, B.n_tok_all, e->n_terms, e->d_term_off, e->d_skip_row,
 	    e->d_dense_col, e->d_dense_used, (unsigned long long)e->ntiles * TILE_DOCS,
@@ -1675,11 +1695,11 @@ run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
 		if (B.algo == NXSB_ALGO_BM25)
 			dense_scores_kernel<NXSB_ALGO_BM25><<<grid, 256, 0, st>>>(e->d_dense,
 			    e->d_dense_terms, e->d_dense_used, e->d_idf_bm25, e->d_logtab,
-			    e->K0, e->K1, col_words, e->d_dense_sc);
+			    e->K0, e->K1, col_words, e->d_dense_sc, e->d_dense_used + 256);
 		else
 			dense_scores_kernel<NXSB_ALGO_TFIDF><<<grid, 256, 0, st>>>(e->d_dense,
 			    e->d_dense_terms, e->d_dense_used, e->d_idf_tfidf, e->d_logtab,
-			    e->K0, e->K1, col_words, e->d_dense_sc);
+			    e->K0, e->K1, col_words, e->d_dense_sc, e->d_dense_used + 256);
 		e->launches++;
 		CK(e, cudaGetLastError());
 	}

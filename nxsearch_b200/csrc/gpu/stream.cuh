@@ -150,6 +150,7 @@ struct StreamParams {
 	const uint32_t *	tt;		/* [n_q][8] truth tables (boolean) */
 	const uint32_t *	dense;		/* dense columns (common.cuh) */
 	unsigned long long	col_words;	/* words per column */
+	const uint32_t *	dense_max;	/* [256] largest score of a column (bits) */
 	unsigned long long *	prof;		/* ST_PROF counters or NULL */
 };
 
@@ -192,7 +193,7 @@ plan_items_kernel(const QDesc *__restrict__ queries,
 	const uint32_t slot = (uint32_t)(item % n_q);
 	const QDesc qd = queries[qlist[slot]];
 	const uint2 qb = qbase ? qbase[slot] : make_uint2(0u, 0u);
-	const uint32_t nbase = qb.y & 0xffu;
+	const uint32_t nbase = qb.y & 0x0fu;	/* 0x80: trailing (the epilogue adds them) */
 	unsigned char *rec = plan + item * stride;
 	PlanTok *out = reinterpret_cast<PlanTok *>(rec + sizeof(PlanHdr));
 	uint32_t total = 0, m = 0, present = 0;
@@ -468,10 +469,12 @@ __global__ void __launch_bounds__(256)
 dense_scores_kernel(const uint32_t *__restrict__ dense,
     const uint32_t *__restrict__ dterms, const uint32_t *__restrict__ used,
     const float *__restrict__ idf, const float *__restrict__ logtab,
-    float K0, float K1, unsigned long long col_words, float *__restrict__ out)
+    float K0, float K1, unsigned long long col_words, float *__restrict__ out,
+    uint32_t *__restrict__ col_max)
 {
 	__shared__ float s_logtab[LOGTAB_N];
 	const uint32_t c = blockIdx.y;
+	float mx = 0.f;
 
 	if (!used[c])
 		return;
@@ -496,7 +499,23 @@ dense_scores_kernel(const uint32_t *__restrict__ dense,
 
 		st_score<false, ALGO, 4>(p, s_logtab, v, w, sc);
 		out4[i] = make_float4(sc[0], sc[1], sc[2], sc[3]);
+		mx = fmaxf(fmaxf(mx, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
 	}
+	/* The column's largest score (scores are >= 0: bit order = value order). */
+	for (int o = 16; o; o >>= 1)
+		mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+	if ((threadIdx.x & 31) == 0 && mx > 0.f)
+		atomicMax(col_max + c, __float_as_uint(mx));
+}
+
+/* val + the trailing score columns of doc, in token order (cold: epilogues only). */
+static __device__ __noinline__ float
+st_trail_of(const float *colf, unsigned long long col_words, uint32_t cols,
+    uint32_t n, float val, uint32_t doc)
+{
+	for (uint32_t x = 0; x < n; x++)
+		val = __fadd_rn(val, __ldg(colf + ((cols >> (8u * x)) & 0xffu) * col_words + doc));
+	return val;
 }
 
 template <bool LOGIC, bool WIDE, int ALGO>
@@ -775,7 +794,29 @@ score_stream_kernel(const StreamParams p)
 	 * what streaming those columns first would have left there.
 	 */
 	constexpr bool BASE = !WIDE;
-	uint32_t nbase = 0, base_cols = 0, base_slots = 0;
+	uint32_t nbm = 0, base_cols = 0, base_slots = 0;	/* nbm: count | 0x80 if trailing */
+#define NLEAD	((nbm & 0x80u) ? 0u : nbm)
+#define NTRAIL	((nbm & 0x80u) ? (nbm & 0x0fu) : 0u)
+	/*
+	 * OR queries whose dense terms come LAST: the accumulator holds the sum
+	 * of the other terms, and the epilogue adds the columns to whatever it
+	 * looks at (trail_of), in token order.  Until then a sum can still grow
+	 * by at most trail_ub (the columns' largest scores, rounded up), so the
+	 * inline threshold is lowered by that much.
+	 */
+	/* The bound is recomputed where it is needed (cold paths): one register less. */
+	auto trail_bound = [&]() -> float {
+		float ub = 0.f;
+
+		for (uint32_t x = 0; x < NTRAIL; x++)
+			ub = __fadd_ru(ub, __uint_as_float(
+			    __ldg(p.dense_max + ((base_cols >> (8u * x)) & 0xffu))));
+		return ub;
+	};
+	auto trail_of = [&](float val, uint32_t doc) -> float {
+		return st_trail_of(reinterpret_cast<const float *>(p.dense), p.col_words,
+		    base_cols, NTRAIL, val, doc);
+	};
 	const float *colf = reinterpret_cast<const float *>(p.dense);
 	/*
 	 * Boolean queries also need the membership bits of the base terms: a
@@ -787,7 +828,7 @@ score_stream_kernel(const StreamParams p)
 
 		if (LOGIC)
 			bits = b != 0.f ? 1u << (base_slots & 7u) : 0u;
-		for (uint32_t x = 1; x < nbase; x++) {
+		for (uint32_t x = 1; x < NLEAD; x++) {
 			const float v = __ldg(colf + ((base_cols >> (8u * x)) & 0xffu) * p.col_words + doc);
 
 			b = __fadd_rn(b, v);
@@ -826,7 +867,7 @@ score_stream_kernel(const StreamParams p)
 			const uint32_t tb = m.ths_bits;
 
 			if (BASE) {
-				nbase = m.nbase & 0xffu;
+				nbm = m.nbase & (LOGIC ? 0x0fu : 0x8fu);
 				base_slots = m.nbase >> 8;	/* boolean queries (OR: prefix number, unused here) */
 				base_cols = m.base_cols;
 			}
@@ -837,6 +878,8 @@ score_stream_kernel(const StreamParams p)
 				tt_pref = __ldg(p.tt + slot * 8u + ctid);
 			ths = (tb != 0u && !(flags & ST_F_SPARSE)) ? __uint_as_float(tb)
 			    : __uint_as_float(0x7f800000u);
+			if (BASE && NTRAIL && ths != __uint_as_float(0x7f800000u))
+				ths = __fsub_rd(ths, trail_bound());
 			if (dirty && !(flags & ST_F_STORE)) {
 				/* Nobody reads the accumulator past the previous
 				 * item's last epilogue barrier. */
@@ -940,7 +983,7 @@ score_stream_kernel(const StreamParams p)
 				v[r] = buf[ctid + r * ST_NCONS];
 			float bs[SLOTS];
 			uint32_t bb[SLOTS];
-			if (BASE && nbase) {
+			if (BASE && NLEAD) {
 				/* In flight while the postings are scored. */
 #pragma unroll
 				for (int r = 0; r < SLOTS; r++)
@@ -951,7 +994,7 @@ score_stream_kernel(const StreamParams p)
 #pragma unroll
 			for (int r = 0; r < SLOTS; r++)
 				a[r] = lds_f32(accb + 4u * v[r].x);
-			if (BASE && nbase) {
+			if (BASE && NLEAD) {
 #pragma unroll
 				for (int r = 0; r < SLOTS; r++) {
 					/* Later touches keep the bits the first one set. */
@@ -983,7 +1026,7 @@ score_stream_kernel(const StreamParams p)
 #pragma unroll
 				for (int r = 0; r < SLOTS; r++)
 					memb[v[r].x - tile_lo] = mb[r] | bit |
-					    (uint8_t)((BASE && nbase) ? bb[r] : 0u);
+					    (uint8_t)((BASE && NLEAD) ? bb[r] : 0u);
 			}
 			PROF(3);		/* full stage */
 		} else {
@@ -1019,7 +1062,7 @@ score_stream_kernel(const StreamParams p)
 					}
 					float bs[2];
 					uint32_t bb[2] = { 0u, 0u };
-					if (BASE && nbase) {
+					if (BASE && NLEAD) {
 #pragma unroll
 						for (int r = 0; r < 2; r++)
 							if (ok[r])
@@ -1030,7 +1073,7 @@ score_stream_kernel(const StreamParams p)
 					for (int r = 0; r < 2; r++)
 						if (ok[r])
 							a[r] = lds_f32(accb + 4u * v[r].x);
-					if (BASE && nbase) {
+					if (BASE && NLEAD) {
 #pragma unroll
 						for (int r = 0; r < 2; r++)
 							if (ok[r]) {
@@ -1104,9 +1147,11 @@ score_stream_kernel(const StreamParams p)
 			 */
 			for (uint32_t i = ctid; i < npush; i += ST_NCONS) {
 				const uint32_t rel = s_push[i];
-				const float val = atomicExch(acc + rel, 0.f);
+				float val = atomicExch(acc + rel, 0.f);
 
 				if (val != 0.f && in_set(LOGIC ? memb[rel] : 0u)) {
+					if (BASE && NTRAIL)
+						val = trail_of(val, tile_lo + rel);
 					const unsigned long long key = make_key(val, tile_lo + rel);
 
 					if (key > thr_key)
@@ -1132,7 +1177,7 @@ score_stream_kernel(const StreamParams p)
 
 				for (uint32_t i = (m.sub[s].b0 & 0xfffu) + ctid; i < b1; i += ST_NCONS) {
 					const uint32_t doc = buf[i].x;
-					const float val = atomicExch(acc + (doc - tile_lo), 0.f);
+					float val = atomicExch(acc + (doc - tile_lo), 0.f);
 					bool member = true;
 
 					if (LOGIC && val != 0.f) {
@@ -1140,6 +1185,8 @@ score_stream_kernel(const StreamParams p)
 						member = in_set(memb[doc - tile_lo]);
 						memb[doc - tile_lo] = 0;
 					}
+					if (BASE && NTRAIL && val != 0.f)
+						val = trail_of(val, doc);
 					if (val >= ths && member) {
 						const unsigned long long key = make_key(val, doc);
 
@@ -1162,13 +1209,17 @@ score_stream_kernel(const StreamParams p)
 				const float ths = thr_key ? __uint_as_float((uint32_t)(thr_key >> 32))
 				    : __uint_as_float(1u);
 				float4 *a4 = reinterpret_cast<float4 *>(acc);
+				/* Trailing columns: what a raw sum must reach to be looked at. */
+				const bool trl = BASE && NTRAIL;
+				const float ths_raw = trl ? __fsub_rd(ths, trail_bound()) : ths;
 
 				uint32_t *memb32 = reinterpret_cast<uint32_t *>(memb);
 
 				/* false: the buffer is full, the document stays for the next round */
 				auto visit = [&](float &val, uint32_t i, uint32_t mb) -> bool {
-					if (val >= ths && in_set(mb)) {
-						const unsigned long long key = make_key(val, tile_lo + i);
+					if ((trl ? (val != 0.f && val >= ths_raw) : val >= ths) && in_set(mb)) {
+						const unsigned long long key = make_key(
+						    trl ? trail_of(val, tile_lo + i) : val, tile_lo + i);
 
 						if (key > thr_key) {
 							const uint32_t at = atomicAdd(ncand, 1u);
@@ -1205,7 +1256,7 @@ score_stream_kernel(const StreamParams p)
 					for (int j = 0; j < NB; j++)
 						mx = fmaxf(fmaxf(mx, fmaxf(q[j].x, q[j].y)),
 						    fmaxf(q[j].z, q[j].w));
-					if (mx >= ths) {
+					if (mx >= ths_raw) {
 #pragma unroll
 						for (int j = 0; j < NB; j++) {
 							const uint32_t i4 = base + j * ST_NCONS;
@@ -1299,6 +1350,9 @@ score_stream_kernel(const StreamParams p)
 		PROF(9);			/* rank + emit */
 	}
 }
+
+#undef NLEAD
+#undef NTRAIL
 
 /*
  * Final per-query top-k from the per-tile candidate cells the stream kernel
