@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -506,19 +507,35 @@ upload_stats(nxsb_engine_t *e)
 			e->stats_valid = true;
 		}
 	}
-	for (uint32_t t = 0; t < V; t++) {
-		const unsigned long df = e->h_df[t];
+	/* Two libm log() calls per term: spread over host threads (an index
+	 * refresh re-derives every term's idf because N moved). */
+	auto fill = [&](uint32_t t0, uint32_t t1) {
+		for (uint32_t t = t0; t < t1; t++) {
+			const unsigned long df = e->h_df[t];
 
-		if (!df || !doc_count) {
-			bm[t] = tfidf[t] = 0.f;
-			continue;
+			if (!df || !doc_count) {
+				bm[t] = tfidf[t] = 0.f;
+				continue;
+			}
+			bm[t] = (float)log(((doc_count - df + 0.5) / (df + 0.5)) + 1);
+			/*
+			 * C semantics: float quotient, widened, DOUBLE log (in C++ a
+			 * float argument would select logf and lose the last ulp).
+			 */
+			tfidf[t] = (float)(log((double)((float)doc_count / (float)df)) + 1);
 		}
-		bm[t] = (float)log(((doc_count - df + 0.5) / (df + 0.5)) + 1);
-		/*
-		 * C semantics: float quotient, widened, DOUBLE log (in C++ a
-		 * float argument would select logf and lose the last ulp).
-		 */
-		tfidf[t] = (float)(log((double)((float)doc_count / (float)df)) + 1);
+	};
+	{
+		const unsigned hw = std::thread::hardware_concurrency();
+		const uint32_t nthr = V < 65536 ? 1 : std::min(8u, hw ? hw : 1u);
+		std::vector<std::thread> pool;
+
+		for (uint32_t i = 1; i < nthr; i++)
+			pool.emplace_back(fill, (uint32_t)((uint64_t)V * i / nthr),
+			    (uint32_t)((uint64_t)V * (i + 1) / nthr));
+		fill(0, (uint32_t)((uint64_t)V / nthr));
+		for (auto &th : pool)
+			th.join();
 	}
 	CK(e, cudaMemcpyAsync(e->d_idf_bm25, bm.data(), V * sizeof(float),
 	    cudaMemcpyHostToDevice, e->stream));
