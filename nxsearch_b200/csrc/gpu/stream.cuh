@@ -501,11 +501,20 @@ dense_scores_kernel(const uint32_t *__restrict__ dense,
 		out4[i] = make_float4(sc[0], sc[1], sc[2], sc[3]);
 		mx = fmaxf(fmaxf(mx, fmaxf(sc[0], sc[1])), fmaxf(sc[2], sc[3]));
 	}
-	/* The column's largest score (scores are >= 0: bit order = value order). */
+	/* The column's largest score (scores are >= 0: bit order = value order);
+	 * one atomic per block, they all land on the same word. */
+	__shared__ float s_mx[8];
 	for (int o = 16; o; o >>= 1)
 		mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-	if ((threadIdx.x & 31) == 0 && mx > 0.f)
-		atomicMax(col_max + c, __float_as_uint(mx));
+	if ((threadIdx.x & 31) == 0)
+		s_mx[threadIdx.x >> 5] = mx;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int w = 1; w < 8; w++)
+			mx = fmaxf(mx, s_mx[w]);
+		if (mx > 0.f)
+			atomicMax(col_max + c, __float_as_uint(mx));
+	}
 }
 
 /* val + the trailing score columns of doc, in token order (cold: epilogues only). */
