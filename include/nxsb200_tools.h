@@ -153,6 +153,13 @@ uint64_t	nxsb_resp_collect(void *const *resps, size_t n, uint32_t stride,
  */
 void		nxsb_index_image_stats(const void *index, uint64_t out[7]);
 
+/*
+ * Live documents containing term_id as the open index (opaque pointer:
+ * nxs_index_t) counts them -- the cardinality of the term's document set in
+ * the reference (ref src/algo/ranking.c:78,150).  0 for an unknown id.
+ */
+uint32_t	nxsb_index_term_df(const void *index, uint32_t term_id);
+
 #pragma GCC visibility pop
 
 #ifdef __cplusplus

@@ -149,6 +149,11 @@ class Index:
         keys = ("full_builds", "delta_builds", "consolidations", "segments", "dead_noted", "live", "pending")
         return dict(zip(keys, (int(x) for x in out)))
 
+    def term_df(self, term_id: int) -> int:
+        self._lib.nxsb_index_term_df.argtypes = [C.c_void_p, C.c_uint32]
+        self._lib.nxsb_index_term_df.restype = C.c_uint32
+        return int(self._lib.nxsb_index_term_df(self.h, term_id))
+
     def params_json(self) -> dict:
         p = self._lib.nxs_index_get_params(self.h)
         return json.loads(_take_string(self._lib.nxs_params_tojson(p, None)))

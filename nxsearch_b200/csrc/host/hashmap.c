@@ -255,6 +255,23 @@ u64map_grow(u64map_t *m)
 	return 0;
 }
 
+/* Room for n keys without growing on the way (bulk loads). */
+int
+u64map_reserve(u64map_t *m, size_t n)
+{
+	while (n * 10 > m->nslots * 7)
+		if (u64map_grow(m) == -1)
+			return -1;
+	return 0;
+}
+
+/* Start fetching the home slot of a key that is about to be looked up. */
+void
+u64map_prefetch(const u64map_t *m, uint64_t key)
+{
+	__builtin_prefetch(&m->slots[mix64(key) & (m->nslots - 1)], 1, 0);
+}
+
 int
 u64map_put(u64map_t *m, uint64_t key, uint32_t val, uint32_t *cur)
 {

@@ -30,6 +30,8 @@ typedef struct u64map u64map_t;
 u64map_t *	u64map_create(size_t hint);
 void		u64map_destroy(u64map_t *);
 size_t		u64map_count(const u64map_t *);
+int		u64map_reserve(u64map_t *, size_t n);
+void		u64map_prefetch(const u64map_t *, uint64_t key);
 int		u64map_put(u64map_t *, uint64_t key, uint32_t val, uint32_t *cur);
 bool		u64map_get(const u64map_t *, uint64_t key, uint32_t *val);
 bool		u64map_del(u64map_t *, uint64_t key);

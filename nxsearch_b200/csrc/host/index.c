@@ -9,9 +9,11 @@
 #include <errno.h>
 #include <fcntl.h>
 #include <inttypes.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 
 #include "index.h"
@@ -501,13 +503,14 @@ df_apply(nxs_index_t *idx, uint64_t blk, uint32_t n, int sign)
 }
 
 static int
-doc_register(nxs_index_t *idx, uint64_t id, uint32_t len, uint32_t n,
-    uint64_t blk)
+doc_register_opt(nxs_index_t *idx, uint64_t id, uint32_t len, uint32_t n,
+    uint64_t blk, bool count_df)
 {
 	uint32_t slot = idx->n_slots;
 
 	if (slot == idx->slots_cap) {
-		const uint32_t ncap = idx->slots_cap ? idx->slots_cap * 2 : 1024;
+		const uint32_t ncap = idx->slots_want > slot ? idx->slots_want :
+		    idx->slots_cap ? idx->slots_cap * 2 : 1024;
 		void *p;
 
 #define GROW(field, type) \
@@ -537,11 +540,19 @@ doc_register(nxs_index_t *idx, uint64_t id, uint32_t len, uint32_t n,
 	idx->doc_seg[slot] = 0;
 	idx->n_slots++;
 	idx->n_live++;
-	df_apply(idx, blk, n, +1);
+	if (count_df)
+		df_apply(idx, blk, n, +1);
 	/* Not on the GPU yet: the next search adds a delta segment. */
 	idx->n_pending++;
 	idx->stats_dirty = true;
 	return 0;
+}
+
+static int
+doc_register(nxs_index_t *idx, uint64_t id, uint32_t len, uint32_t n,
+    uint64_t blk)
+{
+	return doc_register_opt(idx, id, len, n, blk, true);
 }
 
 static void
@@ -580,6 +591,196 @@ doc_unregister(nxs_index_t *idx, uint64_t id)
 	}
 }
 
+/*
+ * Bulk catch-up (opening a large index): the per-posting work of a sync --
+ * checking every term id and counting df[] -- is spread over host threads.
+ * The block chain itself (each block's length is in its header) is walked
+ * once, serially; documents are then registered in file order as always.
+ * Returns 1 when the range was consumed, 0 when the caller should take the
+ * block-by-block path instead (small range, unknown term, no memory), -1 on
+ * a corrupt file.
+ */
+#define BULK_MIN_BYTES	(64u << 20)
+#define BULK_MAX_THREADS 8
+
+typedef struct { uint64_t id; uint32_t dl, n; } bulk_hdr_t;
+
+typedef struct {
+	const nxs_index_t *	idx;
+	const uint64_t *	blk;		/* block offsets */
+	bulk_hdr_t *		hdr;		/* decoded block headers (filled here) */
+	size_t			lo, hi;		/* blocks [lo, hi) */
+	uint32_t *		df;		/* private counts */
+	bool			bad;		/* a term id outside the vocabulary */
+} bulk_job_t;
+
+static void *
+bulk_worker(void *arg)
+{
+	bulk_job_t *job = arg;
+	const uint8_t *base = job->idx->dfile.base;
+	const uint32_t n_terms = job->idx->n_terms;
+
+	for (size_t i = job->lo; i < job->hi; i++) {
+		const uint8_t *p = base + job->blk[i];
+		const uint32_t n = be_get32(p + 12);
+
+		job->hdr[i] = (bulk_hdr_t){ be_get64(p), be_get32(p + 8), n };
+		if (job->hdr[i].id == 0 || job->hdr[i].dl == 0)
+			continue;		/* deleted in place / deletion marker */
+		for (uint32_t j = 0; j < n; j++) {
+			const uint32_t t = be_get32(p + 16 + (size_t)j * 8);
+
+			if (t == 0 || t > n_terms) {
+				job->bad = true;
+				return NULL;
+			}
+			job->df[t - 1]++;
+		}
+	}
+	return NULL;
+}
+
+static int
+dtmap_sync_bulk(nxs_index_t *idx, size_t off, size_t end)
+{
+	idxfile_t *f = &idx->dfile;
+	long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+	unsigned nthr = ncpu < 1 ? 1 : ncpu > BULK_MAX_THREADS ? BULK_MAX_THREADS : (unsigned)ncpu;
+	bulk_job_t jobs[BULK_MAX_THREADS] = { { 0 } };
+	pthread_t tids[BULK_MAX_THREADS];
+	/* Test hook: the size from which a sync takes this path. */
+	const char *min_env = getenv("NXSB_BULK_MIN_BYTES");
+	const size_t min_bytes = min_env ? (size_t)strtoull(min_env, NULL, 10) : BULK_MIN_BYTES;
+	uint64_t *blk = NULL;
+	bulk_hdr_t *hdr = NULL;
+	size_t nblk = 0, cap = (end - off) / 256 + 1024;
+	int ret = 0;
+
+	if (end - off < min_bytes || nthr < 2 || df_reserve(idx) == -1)
+		return 0;
+#ifdef MADV_POPULATE_READ
+	/* Fault the range in with one call instead of once per page. */
+	(void)madvise(f->base + (off & ~(size_t)4095), end - (off & ~(size_t)4095),
+	    MADV_POPULATE_READ);
+#endif
+	struct timespec ts0, ts1, ts2, ts3;
+	const bool prof = getenv("NXSB_OPEN_PROF") != NULL;
+
+	clock_gettime(CLOCK_MONOTONIC, &ts0);
+	if ((blk = malloc(sizeof(uint64_t) * cap)) == NULL)
+		return 0;
+	for (size_t o = off; o < end;) {
+		uint32_t n;
+
+		if (o + 16 > end)
+			goto corrupt;
+		n = be_get32(f->base + o + 12);
+		if (o + 16 + (size_t)n * 8 > end)
+			goto corrupt;
+		if (nblk == cap) {
+			uint64_t *nb = realloc(blk, sizeof(uint64_t) * cap * 2);
+
+			if (nb == NULL)
+				goto out;
+			blk = nb;
+			cap *= 2;
+		}
+		blk[nblk++] = o;
+		o += 16 + (size_t)n * 8;
+	}
+
+	clock_gettime(CLOCK_MONOTONIC, &ts1);
+	if ((hdr = malloc(sizeof(bulk_hdr_t) * (nblk + 1))) == NULL)
+		goto out;
+	for (unsigned t = 0; t < nthr; t++) {
+		jobs[t].idx = idx;
+		jobs[t].hdr = hdr;
+		jobs[t].blk = blk;
+		jobs[t].lo = nblk * t / nthr;
+		jobs[t].hi = nblk * (t + 1) / nthr;
+		if ((jobs[t].df = calloc(idx->n_terms ? idx->n_terms : 1, sizeof(uint32_t))) == NULL)
+			nthr = t;		/* fewer workers: re-split below */
+	}
+	if (nthr < 2)
+		goto out;
+	for (unsigned t = 0; t < nthr; t++) {
+		jobs[t].lo = nblk * t / nthr;
+		jobs[t].hi = nblk * (t + 1) / nthr;
+	}
+	{
+		unsigned started = 0;
+		bool bad = false;
+
+		for (; started < nthr; started++)
+			if (pthread_create(&tids[started], NULL, bulk_worker, &jobs[started]) != 0)
+				break;
+		for (unsigned t = started; t < nthr; t++)
+			bulk_worker(&jobs[t]);		/* could not start: do it here */
+		for (unsigned t = 0; t < started; t++)
+			pthread_join(tids[t], NULL);
+		for (unsigned t = 0; t < nthr; t++)
+			bad |= jobs[t].bad;
+		if (bad)
+			goto out;	/* the serial path reports or defers it */
+	}
+	for (unsigned t = 0; t < nthr; t++)
+		for (uint32_t i = 0; i < idx->n_terms; i++)
+			idx->df[i] += jobs[t].df[i];
+	clock_gettime(CLOCK_MONOTONIC, &ts2);
+
+	/* The tables grow once, and the document map's slots are fetched ahead. */
+	if ((uint64_t)idx->n_slots + nblk < UINT32_MAX) {
+		idx->slots_want = idx->n_slots + (uint32_t)nblk;
+		(void)u64map_reserve(idx->doc_map, u64map_count(idx->doc_map) + nblk);
+	}
+	for (size_t i = 0; i < nblk; i++) {
+		const uint64_t id = hdr[i].id;
+		const uint32_t dl = hdr[i].dl, n = hdr[i].n;
+
+		if (i + 16 < nblk)
+			u64map_prefetch(idx->doc_map, hdr[i + 16].id);
+		if (id == 0) {
+			/* Deleted in place (dtmap.c:360-368): skip. */
+		} else if (dl == 0) {
+			doc_unregister(idx, id);
+		} else if (doc_register_opt(idx, id, dl, n, blk[i], false) == -1) {
+			/*
+			 * df[] already holds the rest of the range: undo what
+			 * was not registered, then fail as the serial path does.
+			 */
+			for (size_t k = i; k < nblk; k++)
+				if (hdr[k].id != 0 && hdr[k].dl != 0)
+					df_apply(idx, blk[k], hdr[k].n, -1);
+			nxs_set_syserror(idx->nxs, NXS_ERR_SYSTEM,
+			    "document registration failed");
+			ret = -1;
+			goto out;
+		}
+		idx->dt_consumed = blk[i] + 16 + (size_t)n * 8 - DTMAP_HDR_LEN;
+	}
+	ret = 1;
+	idx->slots_want = 0;
+	if (prof) {
+		clock_gettime(CLOCK_MONOTONIC, &ts3);
+#define DT(a, b) ((b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec))
+		fprintf(stderr, "dtmap_sync_bulk: %zu blocks, %u threads: chain %.2fs, "
+		    "terms+df %.2fs, register %.2fs\n", nblk, nthr, DT(ts0, ts1),
+		    DT(ts1, ts2), DT(ts2, ts3));
+#undef DT
+	}
+out:
+	for (unsigned t = 0; t < BULK_MAX_THREADS; t++)
+		free(jobs[t].df);
+	free(blk);
+	free(hdr);
+	return ret;
+corrupt:
+	free(blk);
+	nxs_set_error(idx->nxs, NXS_ERR_FATAL, "corrupted dtmap index");
+	return -1;
+}
+
 int
 idx_dtmap_sync(nxs_index_t *idx, bool partial)
 {
@@ -595,6 +796,12 @@ idx_dtmap_sync(nxs_index_t *idx, bool partial)
 	}
 	off = DTMAP_HDR_LEN + idx->dt_consumed;
 	end = DTMAP_HDR_LEN + seen;
+	{
+		const int rc = dtmap_sync_bulk(idx, off, end);
+
+		if (rc != 0)
+			return rc == 1 ? 0 : -1;
+	}
 	while (off < end) {
 		uint64_t id;
 		uint32_t dl, n;
@@ -1001,6 +1208,16 @@ fail:
 	    nxsb_engine_errmsg(idx->engine));
 	idx->image_dirty = true;
 	return -1;
+}
+
+/* include/nxsb200_tools.h */
+NXS_API uint32_t
+nxsb_index_term_df(const void *index, uint32_t term_id)
+{
+	const nxs_index_t *idx = index;
+
+	return term_id >= 1 && term_id <= idx->n_terms && term_id <= idx->df_cap
+	    ? idx->df[term_id - 1] : 0;
 }
 
 /* include/nxsb200_tools.h */

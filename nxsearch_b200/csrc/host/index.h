@@ -61,6 +61,7 @@ struct nxs_index {
 	uint64_t *		doc_blk;	/* file offset of the block */
 	uint8_t *		doc_dead;
 	uint32_t		n_slots, slots_cap, n_live;
+	uint32_t		slots_want;	/* bulk sync: capacity to grow to at once */
 	/*
 	 * Live documents per term -- what the cardinality of a term's roaring
 	 * bitmap is to the reference (ranking.c:78,150) -- kept current as

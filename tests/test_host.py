@@ -302,3 +302,51 @@ def test_bk_mirror_reproduces_the_reference_search(c1_corpus, c1_oracle):
                 if ok and (best is None or rank[t] < rank[best]):
                     best = t
         assert (best + 1 if best is not None else 0) == want, q
+
+
+def test_bulk_threaded_sync_equals_block_by_block(tmp_path, c1_corpus, monkeypatch):
+    """Opening a large index checks term ids and counts df[] on host threads
+    (index.c dtmap_sync_bulk); the state must equal the block-by-block sync,
+    with deleted blocks, deletion markers and an unknown term id in the way."""
+    base = tmp_path / "base"
+    base.mkdir()
+    nxs = capi.Nxs(str(base))
+    nxs.create_index("b", filters=["normalizer"]).close()
+    c1_corpus.write(base / "data/b/nxsterms", base / "data/b/nxsdtmap")
+    w = nxs.open_index("b")
+    for d in (3, 77, 4000, 9999):
+        w.remove(int(c1_corpus.doc_ids[d]))
+    w.add(2**40, " ".join(c1_corpus.term(t) for t in (5, 5, 9, 1234)))
+    w.add(int(c1_corpus.doc_ids[77]), c1_corpus.term(42))          # an id comes back
+    w.close()
+
+    def state(min_bytes):
+        monkeypatch.setenv("NXSB_BULK_MIN_BYTES", str(min_bytes))
+        n = capi.Nxs(str(base))
+        i = n.open_index("b")
+        st = i.image_stats()
+        df = np.array([i.term_df(t) for t in range(1, c1_corpus.n_terms + 1)], dtype=np.int64)
+        i.close()
+        n.close()
+        return st, df
+
+    serial, df_serial = state(1 << 60)
+    bulk, df_bulk = state(1)
+    assert serial == bulk and serial["live"] == c1_corpus.n_docs - 4 + 2
+    assert np.array_equal(df_serial, df_bulk) and df_bulk.sum() > 0
+    # against the file reader's own recount
+    back = tools.Corpus.read(base / "data/b/nxsterms", base / "data/b/nxsdtmap")
+    assert np.array_equal(df_bulk, np.asarray(back.term_df, dtype=np.int64))
+
+    # a block naming a term the vocabulary does not have yet: both paths refuse it the same way
+    raw = bytearray((base / "data/b/nxsdtmap").read_bytes())
+    raw[32 + 16: 32 + 20] = (c1_corpus.n_terms + 7).to_bytes(4, "big")
+    (base / "data/b/nxsdtmap").write_bytes(bytes(raw))
+    for mb in (1 << 60, 1):
+        monkeypatch.setenv("NXSB_BULK_MIN_BYTES", str(mb))
+        n = capi.Nxs(str(base))
+        i = n.open_index("b")          # partial sync at open: stops at the block, no error
+        assert i.image_stats()["live"] == 0
+        i.close()
+        n.close()
+    nxs.close()
