@@ -21,9 +21,10 @@
  * quarter-rate XU pipe, so the bulk test is ONE of them per pair: the
  * signatures folded to 32 bits (another valid h) must differ in at most 4
  * bits; the two-sided 64-bit test runs only for what passes.  The folded
- * signatures of a bucket are staged in shared memory once per CTA and tested
- * by all its warps (query terms, sorted by length on the host so that a CTA's
- * share buckets); the few survivors queue up per warp and go through Myers 32
+ * signatures of a bucket are staged in shared memory once per CTA (a ring of
+ * stages filled by a producer warp with bulk TMA copies) and tested by all
+ * its warps (query terms, sorted by length on the host so that a CTA's share
+ * buckets); the few survivors queue up per warp and go through Myers 32
  * at a time, one per lane.  Candidate sets, distances and the chosen term are
  * unchanged.
  *
@@ -48,7 +49,8 @@
 #define FZ_EDGE_MAX	63	/* ref algo/bktree.h:11 */
 #define FZ_WARPS	8	/* query terms per CTA, 64-bit patterns */
 #define FZ_WARPS32	16	/* ... 32-bit patterns */
-#define FZ_CHUNK	2048	/* signatures staged per round */
+#define FZ_CHUNK	1024	/* signatures per ring stage */
+#define FZ_STAGES	4	/* ring depth */
 #define FZ_MAX_QLEN	64	/* pattern bits */
 #define FZ_ROOT		0xffffffffu
 
@@ -266,23 +268,26 @@ fuzzy_consider(const FuzzyImage &f, const W *peq, int m, uint32_t t, int d,
  * unsigned long long for <= 64; NW query terms per CTA.
  */
 template <typename W, int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__((NW + 1) * 32)
 fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
     const uint32_t *__restrict__ qoff, const uint32_t *__restrict__ qsel,
     uint32_t n_sel, uint32_t *__restrict__ out_term,
     uint32_t *__restrict__ out_dist, uint32_t *__restrict__ out_true)
 {
 	__shared__ W s_peq[NW][256];
-	__shared__ __align__(16) uint32_t s_sig[2][FZ_CHUNK];
+	__shared__ __align__(128) uint32_t s_sig[FZ_STAGES][FZ_CHUNK];
+	__shared__ __align__(8) unsigned long long s_bar[2 * FZ_STAGES];	/* full[], empty[] */
 	__shared__ uint32_t s_queue[NW][64];	/* slots that passed the 64-bit signature test */
 	__shared__ uint32_t s_first[NW][160];	/* ... the folded one (up to 128 join per round) */
 	__shared__ int s_lo, s_hi;
 
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const uint32_t wi = blockIdx.x * NW + warp;
-	const bool active = wi < n_sel;
-	W *peq = s_peq[warp];
-	uint32_t *queue = s_queue[warp], *first = s_first[warp];
+	const bool producer = warp == NW;	/* the extra warp feeds the ring */
+	const bool active = !producer && wi < n_sel;
+	const uint32_t full0 = smem_addr(s_bar), empty0 = smem_addr(s_bar + FZ_STAGES);
+	W *peq = s_peq[producer ? 0 : warp];
+	uint32_t *queue = s_queue[producer ? 0 : warp], *first = s_first[producer ? 0 : warp];
 	uint32_t qi = 0;
 	int m = 0, l_lo = 1, l_hi = 0;
 	unsigned long long qsig = 0;
@@ -290,6 +295,12 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 	if (threadIdx.x == 0) {
 		s_lo = 17;
 		s_hi = 0;
+		for (uint32_t st = 0; st < FZ_STAGES; st++) {
+			mbar_init(full0 + 8 * st, 1);
+			mbar_init(empty0 + 8 * st, NW);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
 	__syncthreads();
 	if (active) {
@@ -350,43 +361,42 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 	};
 
 	/*
-	 * The folded signatures of the CTA's buckets, FZ_CHUNK at a time through
-	 * two shared buffers: the next chunk is fetched into registers before
-	 * the current one is scanned and stored after, so that the loads'
-	 * latency hides behind the scan.  A warp tests 128 signatures per round
-	 * (one 16-byte load of four per lane).  Buckets ascend by length, so the
-	 * slots of THIS query's buckets are one range [my0, my1).
+	 * The folded signatures of the CTA's buckets go through a ring of
+	 * FZ_STAGES shared-memory stages, FZ_CHUNK at a time: the extra warp
+	 * issues one 1-D bulk TMA copy per chunk (contiguous in d_sig32) as soon
+	 * as every consumer warp has released the stage, the consumers wait on
+	 * the stage's "full" mbarrier -- so a warp that queues and verifies many
+	 * survivors may fall a few chunks behind the others without stopping
+	 * them.  A warp tests 128 signatures per round (one 16-byte load of four
+	 * per lane).  Buckets ascend by length, so the slots of THIS query's
+	 * buckets are one range [my0, my1).
 	 */
-	static_assert(FZ_CHUNK % (NW * 32 * 4) == 0, "one or more uint4 per thread");
-	constexpr int PER_T = FZ_CHUNK / (NW * 32 * 4);
-	/* Chunks start at multiples of 4 slots: 16-byte loads of d_sig32 (padded). */
+	/* Chunks start at multiples of 4 slots: 16-byte aligned copies of d_sig32 (padded). */
 	const uint32_t g0 = cta_lo <= cta_hi ? f.len16_start[cta_lo] & ~3u : 0u;
 	const uint32_t g1 = cta_lo <= cta_hi ? f.len16_start[cta_hi + 1] : 0u;
 	const uint32_t my0 = l_lo <= l_hi ? f.len16_start[l_lo] : 0u;
 	const uint32_t my1 = l_lo <= l_hi ? f.len16_start[l_hi + 1] : 0u;
 	const uint32_t q32 = (uint32_t)(qsig | (qsig >> 32));
-	uint4 pre[PER_T];
-	uint32_t buf = 0;
 
-	auto fetch = [&](uint32_t c0) {
-#pragma unroll
-		for (int u = 0; u < PER_T; u++) {
-			const uint32_t j = 4u * (threadIdx.x + u * NW * 32);
+	if (producer) {
+		if (lane == 0) {
+			uint32_t ps = 0, pph = 1;
 
-			pre[u] = c0 + j < g1 ? __ldg(reinterpret_cast<const uint4 *>(f.d_sig32 + c0 + j))
-			    : make_uint4(0u, 0u, 0u, 0u);
+			for (uint32_t c0 = g0; c0 < g1; c0 += FZ_CHUNK) {
+				const uint32_t n = g1 - c0 < FZ_CHUNK ? g1 - c0 : FZ_CHUNK;
+				const uint32_t bytes = ((n + 3u) & ~3u) * 4u;
+
+				mbar_wait(empty0 + 8 * ps, pph);
+				mbar_arrive_expect_tx(full0 + 8 * ps, bytes);
+				tma_load_1d(smem_addr(s_sig[ps]), f.d_sig32 + c0, bytes, full0 + 8 * ps);
+				if (++ps == FZ_STAGES) {
+					ps = 0;
+					pph ^= 1u;
+				}
+			}
 		}
-	};
-	auto stash = [&](uint32_t b) {
-#pragma unroll
-		for (int u = 0; u < PER_T; u++)
-			reinterpret_cast<uint4 *>(s_sig[b])[threadIdx.x + u * NW * 32] = pre[u];
-	};
-	if (g0 < g1) {
-		fetch(g0);
-		stash(0);
+		return;
 	}
-	__syncthreads();
 	/*
 	 * The two-sided test on the full signatures of 32 queued slots (the last
 	 * 32), one per lane: 32 independent loads in flight instead of a
@@ -428,14 +438,13 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 		}
 		__syncwarp();
 	};
-	for (uint32_t c0 = g0; c0 < g1; c0 += FZ_CHUNK, buf ^= 1u) {
+	uint32_t cs = 0, cph = 0;
+	for (uint32_t c0 = g0; c0 < g1; c0 += FZ_CHUNK) {
 		const uint32_t n = g1 - c0 < FZ_CHUNK ? g1 - c0 : FZ_CHUNK;
-		const bool more = c0 + FZ_CHUNK < g1;
 
-		if (more)
-			fetch(c0 + FZ_CHUNK);
+		mbar_wait(full0 + 8 * cs, cph);
 		if (active && c0 < my1 && c0 + n > my0) {
-			const uint4 *sg4 = reinterpret_cast<const uint4 *>(s_sig[buf]);
+			const uint4 *sg4 = reinterpret_cast<const uint4 *>(s_sig[cs]);
 
 			for (uint32_t base = 0; base < n; base += 128) {
 				const uint4 t4 = sg4[(base >> 2) + lane];
@@ -464,9 +473,14 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 					sift();
 			}
 		}
-		if (more)
-			stash(buf ^ 1u);
-		__syncthreads();
+		/* Done with the stage (idle warps included: the count is NW). */
+		__syncwarp();
+		if (lane == 0)
+			mbar_arrive(empty0 + 8 * cs);
+		if (++cs == FZ_STAGES) {
+			cs = 0;
+			cph ^= 1u;
+		}
 	}
 	if (!active)
 		return;
@@ -559,13 +573,13 @@ fuzzy_run(FuzzyImage &f, uint32_t n, const char *qblob, const uint32_t *qoff,
 		cudaMemsetAsync(d_true, 0, (size_t)n * 4, st);
 		if (!sel32.empty()) {
 			fuzzy_scan_kernel<uint32_t, FZ_WARPS32><<<(sel32.size() + FZ_WARPS32 - 1) / FZ_WARPS32,
-			    FZ_WARPS32 * 32, 0, st>>>(f, d_qblob, d_qoff, d_sel32,
+			    (FZ_WARPS32 + 1) * 32, 0, st>>>(f, d_qblob, d_qoff, d_sel32,
 			    sel32.size(), d_term, d_dist, d_true);
 			(*launches)++;
 		}
 		if (!sel64.empty()) {
 			fuzzy_scan_kernel<unsigned long long, FZ_WARPS><<<(sel64.size() + FZ_WARPS - 1) / FZ_WARPS,
-			    FZ_WARPS * 32, 0, st>>>(f, d_qblob, d_qoff, d_sel64,
+			    (FZ_WARPS + 1) * 32, 0, st>>>(f, d_qblob, d_qoff, d_sel64,
 			    sel64.size(), d_term, d_dist, d_true);
 			(*launches)++;
 		}
