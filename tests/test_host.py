@@ -350,3 +350,50 @@ def test_bulk_threaded_sync_equals_block_by_block(tmp_path, c1_corpus, monkeypat
         i.close()
         n.close()
     nxs.close()
+
+
+def test_df_stays_current_through_adds_removes_and_a_second_writer(tmp_path):
+    """The whole-index df[] the GPU segments score with is kept on the
+    host as blocks and deletion markers are consumed; after any mix of
+    nxs_index_add / nxs_index_remove from two handles it must equal a recount of
+    the files (what the reference's per-term bitmap cardinality would be)."""
+    rng = np.random.default_rng(17)
+    words = [f"w{i}" for i in range(60)]
+    base = tmp_path / "b"
+    base.mkdir()
+    a, b = capi.Nxs(str(base)), capi.Nxs(str(base))
+    ia = a.create_index("x", filters=["normalizer"])
+    ib = b.open_index("x")
+    live, next_id = set(), 1
+
+    def check(idx):
+        back = tools.Corpus.read(base / "data/x/nxsterms", base / "data/x/nxsdtmap")
+        # a handle learns of foreign changes when it syncs: adding/removing does that
+        got = np.array([idx.term_df(t) for t in range(1, back.n_terms + 1)], dtype=np.int64)
+        assert np.array_equal(got, np.asarray(back.term_df, dtype=np.int64))
+        assert idx.image_stats()["live"] == len(live) == back.n_docs
+
+    for step in range(120):
+        idx = ia if rng.random() < 0.5 else ib
+        if live and rng.random() < 0.35:
+            d = int(rng.choice(sorted(live)))
+            idx.remove(d)
+            live.discard(d)
+        else:
+            n = int(rng.integers(1, 12))
+            idx.add(next_id, " ".join(rng.choice(words, n)))
+            live.add(next_id)
+            next_id += 1
+        if step % 10 == 9:
+            check(idx)              # the handle that wrote last is in sync
+    # the other handle catches up on its next write
+    ia.add(next_id, "w1 w2")
+    live.add(next_id)
+    check(ia)
+    ib.add(next_id + 1, "w3")
+    live.add(next_id + 1)
+    check(ib)
+    for h in (ia, ib):
+        h.close()
+    a.close()
+    b.close()
