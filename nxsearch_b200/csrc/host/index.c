@@ -421,6 +421,7 @@ idx_dtmap_open(nxs_index_t *idx, const char *path)
 	}
 	if ((idx->doc_map = u64map_create(1024)) == NULL)
 		goto err;
+	idx->doc_map_ready = true;
 	idx->dt_consumed = 0;
 	flock(idx->dfile.fd, LOCK_UN);
 	return idx_dtmap_sync(idx, true);
@@ -528,7 +529,7 @@ doc_register_opt(nxs_index_t *idx, uint64_t id, uint32_t len, uint32_t n,
 	}
 	if (df_reserve(idx) == -1)
 		return -1;
-	if (u64map_put(idx->doc_map, id, slot, NULL) != 1) {
+	if (idx->doc_map_ready && u64map_put(idx->doc_map, id, slot, NULL) != 1) {
 		errno = EEXIST;
 		return -1;
 	}
@@ -555,11 +556,41 @@ doc_register(nxs_index_t *idx, uint64_t id, uint32_t len, uint32_t n,
 	return doc_register_opt(idx, id, len, n, blk, true);
 }
 
+/*
+ * A search-only process never looks a document up by id, so a bulk open
+ * (dtmap_sync_bulk) does not fill the map; the first add / remove / deletion
+ * marker does, from the per-slot arrays.
+ */
+int
+idx_docmap_ensure(nxs_index_t *idx)
+{
+	if (idx->doc_map_ready)
+		return 0;
+	if (u64map_reserve(idx->doc_map, idx->n_live) == -1)
+		return -1;
+	for (uint32_t s = 0; s < idx->n_slots; s++) {
+		if (idx->doc_dead[s])
+			continue;
+		if (s + 16 < idx->n_slots)
+			u64map_prefetch(idx->doc_map, idx->doc_ids[s + 16]);
+		if (u64map_put(idx->doc_map, idx->doc_ids[s], s, NULL) != 1) {
+			errno = EEXIST;		/* one id in two live blocks */
+			return -1;
+		}
+	}
+	idx->doc_map_ready = true;
+	return 0;
+}
+
 static void
 doc_unregister(nxs_index_t *idx, uint64_t id)
 {
 	uint32_t slot;
 
+	if (idx_docmap_ensure(idx) == -1) {
+		idx->image_dirty = true;	/* cannot tell which slot: rebuild from the files' view */
+		return;
+	}
 	if (!u64map_get(idx->doc_map, id, &slot))
 		return;
 	u64map_del(idx->doc_map, id);
@@ -730,15 +761,17 @@ dtmap_sync_bulk(nxs_index_t *idx, size_t off, size_t end)
 	clock_gettime(CLOCK_MONOTONIC, &ts2);
 
 	/* The tables grow once, and the document map's slots are fetched ahead. */
-	if ((uint64_t)idx->n_slots + nblk < UINT32_MAX) {
+	if ((uint64_t)idx->n_slots + nblk < UINT32_MAX)
 		idx->slots_want = idx->n_slots + (uint32_t)nblk;
+	if (idx->n_slots == 0)
+		idx->doc_map_ready = false;	/* a fresh open: left to idx_docmap_ensure */
+	else if (idx->doc_map_ready)
 		(void)u64map_reserve(idx->doc_map, u64map_count(idx->doc_map) + nblk);
-	}
 	for (size_t i = 0; i < nblk; i++) {
 		const uint64_t id = hdr[i].id;
 		const uint32_t dl = hdr[i].dl, n = hdr[i].n;
 
-		if (i + 16 < nblk)
+		if (idx->doc_map_ready && i + 16 < nblk)
 			u64map_prefetch(idx->doc_map, hdr[i + 16].id);
 		if (id == 0) {
 			/* Deleted in place (dtmap.c:360-368): skip. */
@@ -883,6 +916,10 @@ idx_dtmap_add(nxs_index_t *idx, nxs_doc_id_t doc_id, tokenset_t *ts)
 		if (idx_terms_sync(idx) == -1 || idx_dtmap_sync(idx, false) == -1)
 			goto unlock;
 	}
+	if (idx_docmap_ensure(idx) == -1) {
+		nxs_set_syserror(idx->nxs, NXS_ERR_SYSTEM, "document map build failed");
+		goto unlock;
+	}
 	if (u64map_get(idx->doc_map, doc_id, NULL)) {
 		nxs_set_error(idx->nxs, NXS_ERR_EXISTS,
 		    "document %" PRIu64 " is already indexed", doc_id);
@@ -937,6 +974,10 @@ idx_dtmap_remove(nxs_index_t *idx, nxs_doc_id_t doc_id)
 		return -1;
 	if (idx_terms_sync(idx) == -1 || idx_dtmap_sync(idx, false) == -1)
 		goto out;
+	if (idx_docmap_ensure(idx) == -1) {
+		nxs_set_syserror(idx->nxs, NXS_ERR_SYSTEM, "document map build failed");
+		goto out;
+	}
 	if (!u64map_get(idx->doc_map, doc_id, &slot)) {
 		nxs_set_error(idx->nxs, NXS_ERR_MISSING,
 		    "document %" PRIu64 " not found", doc_id);

@@ -55,6 +55,7 @@ struct nxs_index {
 	idxfile_t		dfile;
 	size_t			dt_consumed;
 	u64map_t *		doc_map;	/* doc id -> slot */
+	bool			doc_map_ready;	/* false: a bulk open left it for the first writer */
 	uint64_t *		doc_ids;	/* per slot, file order */
 	uint32_t *		doc_len;
 	uint32_t *		doc_n;
@@ -105,6 +106,8 @@ int		idx_dtmap_sync(nxs_index_t *, bool partial);
 int		idx_dtmap_add(nxs_index_t *, nxs_doc_id_t, tokenset_t *);
 int		idx_dtmap_remove(nxs_index_t *, nxs_doc_id_t);
 void		idx_dtmap_close(nxs_index_t *);
+/* The id -> slot map is only needed to add / remove: built on first use. */
+int		idx_docmap_ensure(nxs_index_t *);
 uint64_t	idx_get_token_count(const nxs_index_t *);
 uint32_t	idx_get_doc_count(const nxs_index_t *);
 

@@ -377,6 +377,10 @@ nxs_index_add(nxs_index_t *idx, nxs_params_t *params, nxs_doc_id_t doc_id,
 		nxs_set_error(idx->nxs, NXS_ERR_INVALID, "document ID must be non-zero");
 		return -1;
 	}
+	if (idx_docmap_ensure(idx) == -1) {
+		nxs_set_syserror(idx->nxs, NXS_ERR_SYSTEM, "document map build failed");
+		return -1;
+	}
 	if (u64map_get(idx->doc_map, doc_id, NULL)) {
 		nxs_set_error(idx->nxs, NXS_ERR_EXISTS,
 		    "document %" PRIu64 " is already indexed", doc_id);

@@ -304,6 +304,11 @@ def test_bk_mirror_reproduces_the_reference_search(c1_corpus, c1_oracle):
         assert (best + 1 if best is not None else 0) == want, q
 
 
+def _doc_terms(corpus, i):
+    lo, hi = int(corpus.doc_off[i]), int(corpus.doc_off[i + 1])
+    return set(int(t) for t in corpus.pairs[2 * lo: 2 * hi: 2])
+
+
 def test_bulk_threaded_sync_equals_block_by_block(tmp_path, c1_corpus, monkeypatch):
     """Opening a large index checks term ids and counts df[] on host threads
     (index.c dtmap_sync_bulk); the state must equal the block-by-block sync,
@@ -337,6 +342,23 @@ def test_bulk_threaded_sync_equals_block_by_block(tmp_path, c1_corpus, monkeypat
     # against the file reader's own recount
     back = tools.Corpus.read(base / "data/b/nxsterms", base / "data/b/nxsdtmap")
     assert np.array_equal(df_bulk, np.asarray(back.term_df, dtype=np.int64))
+
+    # a bulk open leaves the id -> slot map to the first writer: it must still know every document
+    monkeypatch.setenv("NXSB_BULK_MIN_BYTES", "1")
+    n = capi.Nxs(str(base))
+    i = n.open_index("b")
+    with pytest.raises(capi.NxsError) as ei:
+        i.add(int(c1_corpus.doc_ids[10]), "anything")
+    assert ei.value.code == 4                      # NXS_ERR_EXISTS
+    with pytest.raises(capi.NxsError) as ei:
+        i.remove(int(c1_corpus.doc_ids[3]))         # removed before
+    assert ei.value.code == 5                      # NXS_ERR_MISSING
+    i.remove(int(c1_corpus.doc_ids[10]))
+    i.add(int(c1_corpus.doc_ids[10]), c1_corpus.term(7))
+    assert i.image_stats()["live"] == serial["live"]
+    assert i.term_df(7) == df_serial[6] + 1 - (1 if 7 in _doc_terms(c1_corpus, 10) else 0)
+    i.close()
+    n.close()
 
     # a block naming a term the vocabulary does not have yet: both paths refuse it the same way
     raw = bytearray((base / "data/b/nxsdtmap").read_bytes())
