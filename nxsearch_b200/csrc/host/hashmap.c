@@ -123,6 +123,16 @@ strmap_grow(strmap_t *m)
 	return 0;
 }
 
+/* Room for n keys without rehashing on the way (bulk loads). */
+int
+strmap_reserve(strmap_t *m, size_t n)
+{
+	while (n * 10 > m->nslots * 7)
+		if (strmap_grow(m) == -1)
+			return -1;
+	return 0;
+}
+
 int
 strmap_put(strmap_t *m, const void *key, size_t len, uint32_t val,
     uint32_t *cur)

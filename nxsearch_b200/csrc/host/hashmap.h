@@ -16,6 +16,7 @@ typedef struct strmap strmap_t;
 strmap_t *	strmap_create(size_t hint);
 void		strmap_destroy(strmap_t *);
 size_t		strmap_count(const strmap_t *);
+int		strmap_reserve(strmap_t *, size_t n);
 /*
  * Insert key -> val unless present.  Returns 1 if inserted, 0 if the key was
  * already there (*cur gets its value), -1 on OOM.  The key bytes are copied.
