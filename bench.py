@@ -204,6 +204,7 @@ def run_reference(args, rank: int, world: int) -> None:
     total = sum(times)
     value = per_step * steps_done / total
     sample = f"{per_step} queries/step x {steps_done} steps of the same query stream, full {args.docs}-doc index"
+    compiled = compiled_reference_check(args) if args.ref_real_docs > 0 else None
     line = {
         "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps_done,
         "warmup": args.warmup, "ms_per_step": 1000 * total / steps_done, "higher_is_better": True,
@@ -215,7 +216,58 @@ def run_reference(args, rank: int, world: int) -> None:
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if compiled:
+        line["compiled_reference"] = compiled
     emit(line)
+
+
+def compiled_reference_check(args):
+    """How the port relates to the real thing: the reference's own C files
+    (oracle/_ref) and the port on the SAME reduced index -- the compiled
+    reference needs about a minute per million documents to open one, so it
+    cannot serve the 10M-document config inside a benchmark run -- one core
+    each, the same queries.  Supplementary; not the line's value."""
+    import shutil
+    import _oracle
+    from nxsearch_b200 import capi, tools
+
+    ref = _oracle.ref()
+    if ref is None:
+        return {"unavailable": "oracle/_ref was not built (no /root/reference at build time)"}
+    base = tempfile.mkdtemp(prefix="nxsb_ref_", dir=args.tmpdir)
+    try:
+        corpus = tools.Corpus.generate(args.ref_real_docs, args.vocab)
+        boot = capi.Nxs(base)                      # index directory + params.db
+        boot.create_index("r").close()
+        boot.close()
+        corpus.write(f"{base}/data/r/nxsterms", f"{base}/data/r/nxsdtmap")
+        t0 = time.perf_counter()
+        rn = capi.Nxs(base, lib=ref)
+        ridx = rn.open_index("r")
+        open_s = time.perf_counter() - t0
+        qt = corpus.query_terms(4 * 64)
+        queries = make_queries(qt, 64)
+        strings = [" OR ".join(corpus.term(t) for t in leaves) for _, _, leaves in queries]
+        done, t0 = 0, time.perf_counter()
+        for q in strings:
+            ridx.search(q, limit=args.limit, algo="BM25")
+            done += 1
+            if time.perf_counter() - t0 > 20:
+                break
+        ref_qps = done / (time.perf_counter() - t0)
+        ridx.close()
+        rn.close()
+        ora = _oracle.OracleIndex(corpus)
+        t0 = time.perf_counter()
+        for toks, prog, _ in queries[:done]:
+            ora.search(_oracle.BM25, args.limit, toks, prog)
+        port_qps = done / (time.perf_counter() - t0)
+        ora.close()
+        return {"docs": args.ref_real_docs, "index_open_s": round(open_s, 1), "queries": done,
+                "reference_queries_per_s_1core": ref_qps, "port_queries_per_s_1core": port_qps,
+                "note": "same reduced index and queries for both; the line's value is the port on the full index"}
+    finally:
+        shutil.rmtree(base, ignore_errors=True)
 
 
 def workload_name(args) -> str:
@@ -485,6 +537,8 @@ def main() -> None:
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-sample", type=int, default=64, help="queries per step of the reference arm")
     ap.add_argument("--ref-budget", type=float, default=60.0, help="seconds of timed CPU work, reference arm")
+    ap.add_argument("--ref-real-docs", type=int, default=1_000_000,
+                    help="reference arm: also time the compiled reference on an index of this many documents (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tmpdir", default=None)
     args = ap.parse_args()
