@@ -252,7 +252,7 @@ def compiled_reference_check(args):
         for q in strings:
             ridx.search(q, limit=args.limit, algo="BM25")
             done += 1
-            if time.perf_counter() - t0 > 20:
+            if time.perf_counter() - t0 > 10:
                 break
         ref_qps = done / (time.perf_counter() - t0)
         ridx.close()
@@ -537,7 +537,7 @@ def main() -> None:
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-sample", type=int, default=64, help="queries per step of the reference arm")
     ap.add_argument("--ref-budget", type=float, default=60.0, help="seconds of timed CPU work, reference arm")
-    ap.add_argument("--ref-real-docs", type=int, default=1_000_000,
+    ap.add_argument("--ref-real-docs", type=int, default=500_000,
                     help="reference arm: also time the compiled reference on an index of this many documents (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--tmpdir", default=None)
