@@ -241,6 +241,26 @@ int		nxsb_engine_timings(nxsb_engine_t *, uint32_t last_runs,
 		    const char **names, float *ms, int cap);
 /* Kernel launches issued by the engine since creation. */
 uint64_t	nxsb_engine_launch_count(const nxsb_engine_t *);
+/*
+ * Device / pinned-host allocations and frees made by the library since it
+ * was loaded.  cudaFree synchronises the device, so the count must not move
+ * while batches of one shape are searched (tests/test_gpu_engine.py).
+ */
+uint64_t	nxsb_alloc_events(void);
+
+/*
+ * Exact top-k pruning (bmw.cuh).  OR queries with limit <= 128 skip the
+ * blocks of documents whose score bound -- the sum of the per-(term, block)
+ * score maxima kept in the image -- cannot enter the query's current top-k;
+ * results are bit-identical to scoring everything, which is what the
+ * reference does (ref src/query/search.c:235-272).  On by default
+ * (environment NXSB_BMW=0 turns it off at engine creation); set_pruning
+ * switches it for the batches staged afterwards and returns the old setting.
+ * pruning_stats: out = { (query, chunk) items, blocks scored, postings
+ * scored, selection rounds } since creation or the last reset.
+ */
+int		nxsb_engine_set_pruning(nxsb_engine_t *, int on);
+int		nxsb_engine_pruning_stats(nxsb_engine_t *, uint64_t out[4], int reset);
 
 #pragma GCC visibility pop
 

@@ -1,0 +1,707 @@
+/*
+ * score_bmw_kernel: exact top-k for OR queries with block-max pruning.
+ *
+ * The reference scores every document a query matches and keeps the best
+ * `limit` in a heap (ref src/query/search.c:235-272, src/core/results.c:
+ * 128-220).  The answer only needs the documents that can still enter the
+ * heap, so this kernel never touches most postings (the dynamic pruning of
+ * block-max WAND, done tile-at-a-time instead of with posting cursors):
+ *
+ *   The dense document space is cut into BLOCKS of 2^bshift documents.  For
+ *   every "column term" -- a list long enough to average two postings per
+ *   block -- the image holds, per block, the offset of its first posting
+ *   (boff) and the largest query-independent weight any of its postings has
+ *   (bmax: BM25 tf-normalisation, or the TF-IDF tf weight; recomputed when
+ *   the index statistics move).  A score is weight x idf, both roundings
+ *   monotonic, so  sum_t bmax[t][b] * idf[t]  bounds every score in block b
+ *   from above, bit for bit (float addition is monotonic, absent terms add
+ *   +0).  Short lists have no arrays: their exact per-block maxima are folded
+ *   in from the postings themselves (a few per block).
+ *
+ *   work item = (query, CHUNK of 8192 blocks), handed out chunk-major from
+ *   the highest ids down so that a query's threshold (its k-th best key so
+ *   far, shared through global memory) is known before most of its items
+ *   start.  Per item:
+ *     1. ub[b] for the chunk's blocks in shared memory;
+ *     2. blocks whose bound cannot beat the threshold are dropped; of the
+ *        rest the most promising are scored first (a histogram over the
+ *        bounds picks them) so that the threshold settles after a handful;
+ *     3. a warp scores one block: the block's slice of every token's list,
+ *        in TOKEN-LIST ORDER (the reference's float summation order), into a
+ *        per-warp accumulator of 2^bshift sums; survivors join the item's
+ *        candidate buffer, which is cut back to the k best whenever a round
+ *        ends (that k-th key is the new threshold).
+ *   The item's <= k keys go to the same per-(query, chunk) cells
+ *   finalize_cells_kernel merges for the stream kernel.
+ *
+ * Arithmetic is st_score() of stream.cuh, hence identical bits; ties still
+ * fall to the higher document id because a bound is compared as the key
+ * (bound, last document of the block).
+ */
+#ifndef NXSB_GPU_BMW_CUH
+#define NXSB_GPU_BMW_CUH
+
+#define BMW_THREADS	256
+#define BMW_WARPS	(BMW_THREADS / 32)
+#define BMW_CH_BLOCKS	8192u			/* blocks per chunk (ub[] in shared memory) */
+#define BMW_CAND	1024u			/* candidate keys per item */
+#define BMW_SEL		512u			/* blocks selected per round */
+#define BMW_K_MAX	128u			/* limit served by this kernel */
+#define BMW_HIST	64u
+#define BMW_SEED_BLOCKS	BMW_WARPS		/* first round without a threshold */
+#define BMW_ROUND_BLOCKS 64u			/* later partial rounds */
+#define BMW_BCOL_NONE	0xffffffffu
+#define BMW_SHIFT_MIN	5
+#define BMW_SHIFT_MAX	8
+#define BMW_TOK_GROUP	4			/* tokens whose postings are in flight together */
+
+static_assert((BMW_CH_BLOCKS << BMW_SHIFT_MIN) % TILE_DOCS == 0, "chunks start at tile boundaries");
+static_assert(BMW_K_MAX + (1u << BMW_SHIFT_MAX) <= BMW_CAND, "a block always fits after a cut");
+
+struct BmwParams {
+	const uint2 *		post;
+	const DTok *		toks;
+	const QDesc *		queries;
+	const uint32_t *	qlist;
+	uint32_t		n_q, nchunks, nblocks, n_docs, ntiles, k;
+	const uint32_t *	boff;		/* [n_bcol][nblocks + 1] */
+	const float *		bmax;		/* [n_bcol][nblocks], the batch's algorithm */
+	unsigned long long *	thr;		/* [n_q] */
+	uint32_t *		tile_count;	/* [n_q][nchunks] */
+	unsigned long long *	cand;		/* [n_q][nchunks][k] */
+	uint32_t *		work_counter;
+	const float *		logtab;
+	float			K0, K1;
+	unsigned long long *	stats;		/* [4] items, blocks scored, postings scored, rounds */
+};
+
+struct BmwTok {
+	unsigned long long	post_off;
+	const uint32_t *	fine;		/* slice boundaries per 2^fine_shift documents */
+	uint32_t		clo, chi;	/* the chunk's slice of the list */
+	float			idf;
+	uint32_t		col;
+	uint32_t		fine_shift;
+	uint32_t		pad;
+};
+
+template <uint32_t BSHIFT>
+struct BmwCfg {
+	static constexpr uint32_t BS = 1u << BSHIFT;
+	static constexpr uint32_t NP = BS / 32;
+	static constexpr size_t SMEM = BMW_CH_BLOCKS * 4 + BMW_CAND * 8 + BMW_K_MAX * 8 +
+	    BMW_WARPS * BS * 4 + BMW_SEL * 2 + LOGTAB_N * 4 +
+	    NXSB_MAX_QUERY_TOKENS * sizeof(BmwTok);
+};
+
+/* ---- image side: block offsets and block maxima of the column terms ---- */
+
+/* row[j] = first posting of the list whose document lies in block >= j. */
+__global__ void __launch_bounds__(256)
+build_block_offsets_kernel(const uint2 *__restrict__ post,
+    const unsigned long long *__restrict__ term_off,
+    const uint32_t *__restrict__ col_terms, uint32_t nblocks, uint32_t bshift,
+    uint32_t *__restrict__ boff)
+{
+	const uint32_t t = col_terms[blockIdx.x];
+	const unsigned long long s = term_off[t];
+	const uint32_t df = (uint32_t)(term_off[t + 1] - s);
+	const uint2 *list = post + s;
+	uint32_t *row = boff + (size_t)blockIdx.x * (nblocks + 1);
+
+	if (df == 0) {
+		for (uint32_t j = threadIdx.x; j <= nblocks; j += blockDim.x)
+			row[j] = 0;
+		return;
+	}
+	for (uint32_t i = threadIdx.x; i < df; i += blockDim.x) {
+		const uint32_t b = list[i].x >> bshift;
+		const uint32_t lo = i ? (list[i - 1].x >> bshift) + 1 : 0;
+
+		for (uint32_t j = lo; j <= b; j++)
+			row[j] = i;
+		if (i == df - 1) {
+			for (uint32_t j = b + 1; j <= nblocks; j++)
+				row[j] = df;
+		}
+	}
+}
+
+/*
+ * bmax_bm25[c][b], bmax_tfidf[c][b] = the largest weight (st_score with
+ * idf = 1: the same roundings as the scorer, so weight * idf reproduces the
+ * largest score exactly) of column c's postings in block b.  Block (x, c)
+ * strides over the list; postings of one block are neighbours, so a thread
+ * folds its run before touching memory.  Pre-zeroed by the caller; weights
+ * are positive, so unsigned order is value order.
+ */
+__global__ void __launch_bounds__(256)
+block_max_kernel(const uint2 *__restrict__ post,
+    const unsigned long long *__restrict__ term_off,
+    const uint32_t *__restrict__ col_terms, uint32_t nblocks, uint32_t bshift,
+    const float *__restrict__ logtab, float K0, float K1,
+    float *__restrict__ bmax_bm25, float *__restrict__ bmax_tfidf)
+{
+	__shared__ float s_logtab[LOGTAB_N];
+	const uint32_t t = col_terms[blockIdx.y];
+	const unsigned long long s = term_off[t], e = term_off[t + 1];
+	uint32_t *o_bm = reinterpret_cast<uint32_t *>(bmax_bm25) + (size_t)blockIdx.y * nblocks;
+	uint32_t *o_tf = reinterpret_cast<uint32_t *>(bmax_tfidf) + (size_t)blockIdx.y * nblocks;
+
+	for (uint32_t i = threadIdx.x; i < LOGTAB_N; i += blockDim.x)
+		s_logtab[i] = logtab[i];
+	__syncthreads();
+
+	StreamParams sp;
+	sp.K0 = K0;
+	sp.K1 = K1;
+	sp.doc_len = nullptr;
+	/* Each thread takes 4 consecutive postings. */
+	for (unsigned long long i = s + 4ull * ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x);
+	    i < e; i += 4ull * gridDim.x * blockDim.x) {
+		uint2 v[4];
+		float wb[4], wt[4];
+
+#pragma unroll
+		for (int r = 0; r < 4; r++)
+			v[r] = i + r < e ? post[i + r] : make_uint2(0u, 0u);
+		st_score<false, NXSB_ALGO_BM25, 4>(sp, s_logtab, v, 1.f, wb);
+		st_score<false, NXSB_ALGO_TFIDF, 4>(sp, s_logtab, v, 1.f, wt);
+		uint32_t b = v[0].x >> bshift;
+		float mb = wb[0], mt = wt[0];
+#pragma unroll
+		for (int r = 1; r < 4; r++) {
+			if (i + r >= e)
+				break;
+			const uint32_t br = v[r].x >> bshift;
+
+			if (br != b) {
+				atomicMax(o_bm + b, __float_as_uint(mb));
+				atomicMax(o_tf + b, __float_as_uint(mt));
+				b = br;
+				mb = wb[r];
+				mt = wt[r];
+			} else {
+				mb = fmaxf(mb, wb[r]);
+				mt = fmaxf(mt, wt[r]);
+			}
+		}
+		atomicMax(o_bm + b, __float_as_uint(mb));
+		atomicMax(o_tf + b, __float_as_uint(mt));
+	}
+}
+
+/* ---- the scorer --------------------------------------------------------- */
+
+template <int ALGO, uint32_t BSHIFT>
+__global__ void __launch_bounds__(BMW_THREADS, 3)
+score_bmw_kernel(const BmwParams p)
+{
+	using Cfg = BmwCfg<BSHIFT>;
+	constexpr uint32_t BS = Cfg::BS, NP = Cfg::NP;
+
+	extern __shared__ __align__(16) unsigned char smem_bmw[];
+	float *ub = reinterpret_cast<float *>(smem_bmw);
+	unsigned long long *s_cand = reinterpret_cast<unsigned long long *>(ub + BMW_CH_BLOCKS);
+	unsigned long long *s_top = s_cand + BMW_CAND;			/* [K_MAX] cut buffer */
+	float *s_acc = reinterpret_cast<float *>(s_top + BMW_K_MAX);	/* [WARPS][BS] */
+	BmwTok *s_tok = reinterpret_cast<BmwTok *>(s_acc + BMW_WARPS * BS);
+	float *s_logtab = reinterpret_cast<float *>(s_tok + NXSB_MAX_QUERY_TOKENS);
+	uint16_t *s_sel = reinterpret_cast<uint16_t *>(s_logtab + LOGTAB_N);
+
+	__shared__ uint32_t s_item, s_nsel, s_selw, s_next, s_ncand, s_overflow, s_umax, s_cut;
+	__shared__ uint32_t s_hist[BMW_HIST];
+	__shared__ unsigned long long s_theta;
+
+	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const uint32_t n_items = p.n_q * p.nchunks;
+	const uint32_t k = p.k;
+	unsigned long long st_blocks = 0, st_post = 0, st_rounds = 0, st_items = 0;
+
+	for (uint32_t i = tid; i < LOGTAB_N; i += BMW_THREADS)
+		s_logtab[i] = p.logtab[i];
+
+	StreamParams sp;
+	sp.K0 = p.K0;
+	sp.K1 = p.K1;
+	sp.doc_len = nullptr;
+
+	for (;;) {
+		__syncthreads();
+		if (tid == 0) {
+			s_item = atomicAdd(p.work_counter, 1u);
+			s_ncand = 0;
+		}
+		__syncthreads();
+		const uint32_t item = s_item;
+
+		if (item >= n_items)
+			break;
+		const uint32_t chunk = p.nchunks - 1 - item / p.n_q;
+		const uint32_t slot = item % p.n_q;
+		const QDesc qd = p.queries[p.qlist[slot]];
+		const uint32_t ntok = qd.n_tokens;
+		const uint32_t cb0 = chunk * BMW_CH_BLOCKS;
+		const uint32_t nb = min(BMW_CH_BLOCKS, p.nblocks - cb0);
+		const uint32_t doc0 = cb0 << BSHIFT;
+		const uint32_t tile0 = doc0 >> TILE_SHIFT;
+		const uint32_t tile1 = min(p.ntiles,
+		    (uint32_t)((((unsigned long long)(cb0 + nb) << BSHIFT) + TILE_DOCS - 1) >> TILE_SHIFT));
+
+		if (tid < ntok) {
+			const DTok t = p.toks[qd.tok_off + tid];
+			BmwTok bt;
+
+			bt.post_off = t.post_off;
+			bt.clo = __ldg(t.skip + tile0);
+			bt.chi = __ldg(t.skip + tile1);
+			bt.idf = t.idf;
+			bt.col = t.bcol;
+			bt.fine = t.fine;
+			bt.fine_shift = t.fine_shift;
+			bt.pad = 0;
+			s_tok[tid] = bt;
+		}
+		if (tid == 0)
+			s_theta = *(volatile unsigned long long *)(p.thr + slot);
+		__syncthreads();
+		if (tid == 0)
+			st_items++;
+
+		/* ---- 1. upper bounds ---- */
+		bool any_list = false;
+		for (uint32_t j = 0; j < ntok; j++)
+			any_list |= s_tok[j].col == BMW_BCOL_NONE;
+		{
+			constexpr uint32_t U = 4;
+
+			for (uint32_t b0 = tid; b0 < nb; b0 += U * BMW_THREADS) {
+				float u[U];
+
+#pragma unroll
+				for (uint32_t x = 0; x < U; x++)
+					u[x] = 0.f;
+				for (uint32_t j = 0; j < ntok; j++) {
+					const BmwTok &bt = s_tok[j];
+
+					if (bt.col == BMW_BCOL_NONE)
+						continue;
+					const float *row = p.bmax + (size_t)bt.col * p.nblocks + cb0;
+					float m[U];
+
+#pragma unroll
+					for (uint32_t x = 0; x < U; x++) {
+						const uint32_t b = b0 + x * BMW_THREADS;
+
+						m[x] = b < nb ? __ldg(row + b) : 0.f;
+					}
+#pragma unroll
+					for (uint32_t x = 0; x < U; x++)
+						u[x] = __fadd_rn(u[x], __fmul_rn(m[x], bt.idf));
+				}
+#pragma unroll
+				for (uint32_t x = 0; x < U; x++) {
+					const uint32_t b = b0 + x * BMW_THREADS;
+
+					if (b < nb)
+						ub[b] = u[x];
+				}
+			}
+		}
+		if (any_list) {
+			__syncthreads();
+			for (uint32_t j = 0; j < ntok; j++) {
+				const BmwTok bt = s_tok[j];
+
+				if (bt.col != BMW_BCOL_NONE)
+					continue;
+				const uint2 *list = p.post + bt.post_off;
+
+				for (uint32_t i = bt.clo + tid; i < bt.chi; i += BMW_THREADS) {
+					uint2 v[1] = { __ldg(list + i) };
+					const uint32_t b = (v[0].x - doc0) >> BSHIFT;
+
+					/* The head of a block's run folds the run. */
+					if (i != bt.clo && ((__ldg(list + i - 1).x - doc0) >> BSHIFT) == b)
+						continue;
+					float sc[1], m;
+
+					st_score<false, ALGO, 1>(sp, s_logtab, v, bt.idf, sc);
+					m = sc[0];
+					for (uint32_t i2 = i + 1; i2 < bt.chi; i2++) {
+						v[0] = __ldg(list + i2);
+						if (((v[0].x - doc0) >> BSHIFT) != b)
+							break;
+						st_score<false, ALGO, 1>(sp, s_logtab, v, bt.idf, sc);
+						m = fmaxf(m, sc[0]);
+					}
+					atomicAdd(ub + b, m);
+				}
+			}
+		}
+		/*
+		 * The bound was summed columns first, short lists after: another
+		 * order than the token list's, which can round a few ulp lower once
+		 * three or more terms are involved.  2^-16 covers 32 terms.
+		 */
+		const float infl = (any_list && ntok >= 3) ? 1.0000152587890625f : 1.f;
+
+		/* ---- 2./3. rounds: select, score, cut ---- */
+		for (;;) {
+			__syncthreads();
+			if (tid == 0) {
+				const unsigned long long g = *(volatile unsigned long long *)(p.thr + slot);
+
+				if (g > s_theta)
+					s_theta = g;
+				s_nsel = s_selw = s_next = s_overflow = s_umax = 0;
+			}
+			if (tid < BMW_HIST)
+				s_hist[tid] = 0;
+			__syncthreads();
+			const unsigned long long theta = s_theta;
+			uint32_t cnt = 0, mxb = 0;
+
+			/* (bound, last document of the block) must beat the threshold key. */
+			auto alive = [&](uint32_t b, float u) -> bool {
+				return u != 0.f && make_key(u, ((cb0 + b + 1u) << BSHIFT) - 1u) > theta;
+			};
+			for (uint32_t b = tid; b < nb; b += BMW_THREADS) {
+				const float u = __fmul_ru(ub[b], infl);
+
+				if (alive(b, u)) {
+					cnt++;
+					mxb = max(mxb, __float_as_uint(u));
+				}
+			}
+			cnt = __reduce_add_sync(0xffffffffu, cnt);
+			mxb = __reduce_max_sync(0xffffffffu, mxb);
+			if (lane == 0 && cnt) {
+				atomicAdd(&s_nsel, cnt);
+				atomicMax(&s_umax, mxb);
+			}
+			__syncthreads();
+			const uint32_t nsel = s_nsel;
+
+			if (nsel == 0)
+				break;
+			/* Everything alive, or only the blocks with the highest bounds? */
+			const uint32_t target = theta == 0 ? BMW_SEED_BLOCKS : BMW_ROUND_BLOCKS;
+			const bool subset = nsel > (theta == 0 ? BMW_SEED_BLOCKS : BMW_SEL / 2);
+			const float lo = __uint_as_float((uint32_t)(theta >> 32));
+			const float hi = __uint_as_float(s_umax);
+			const float scale = subset && hi > lo ? (float)BMW_HIST / (hi - lo) : 0.f;
+			auto bin_of = [&](float u) -> uint32_t {
+				const float x = (u - lo) * scale;
+
+				return x <= 0.f ? 0u : min(BMW_HIST - 1u, (uint32_t)x);
+			};
+
+			if (subset) {
+				for (uint32_t b = tid; b < nb; b += BMW_THREADS) {
+					const float u = __fmul_ru(ub[b], infl);
+
+					if (alive(b, u))
+						atomicAdd(&s_hist[bin_of(u)], 1u);
+				}
+				__syncthreads();
+				if (tid == 0) {
+					uint32_t cum = 0;
+					int bin = BMW_HIST - 1;
+
+					for (; bin > 0; bin--) {
+						cum += s_hist[bin];
+						if (cum >= target)
+							break;
+					}
+					s_cut = (uint32_t)bin;
+				}
+				__syncthreads();
+			}
+			const uint32_t cut = subset ? s_cut : 0u;
+
+			for (uint32_t b = tid; b < nb; b += BMW_THREADS) {
+				const float u = __fmul_ru(ub[b], infl);
+
+				if (alive(b, u) && (!subset || bin_of(u) >= cut)) {
+					const uint32_t at = atomicAdd(&s_selw, 1u);
+
+					if (at < BMW_SEL)
+						s_sel[at] = (uint16_t)b;
+				}
+			}
+			__syncthreads();
+			const uint32_t n_round = min(s_selw, BMW_SEL);
+			/* Did this round take every live block? */
+			const bool partial = subset || s_selw > BMW_SEL;
+
+			if (tid == 0)
+				st_rounds++;
+
+			/* ---- score the selected blocks, one per warp at a time ---- */
+			float *wacc = s_acc + warp * BS;
+
+			for (;;) {
+				uint32_t si = 0;
+
+				if (lane == 0)
+					si = *(volatile uint32_t *)&s_overflow ? n_round : atomicAdd(&s_next, 1u);
+				si = __shfl_sync(0xffffffffu, si, 0);
+				if (si >= n_round)
+					break;
+				const uint32_t b = s_sel[si];
+				const uint32_t gb = cb0 + b;
+				const uint32_t base = gb << BSHIFT;
+
+#pragma unroll
+				for (uint32_t r = 0; r < NP; r++)
+					wacc[lane + 32 * r] = 0.f;
+				/* Lane j finds token j's slice of the block. */
+				uint32_t my_lo = 0, my_hi = 0;
+				if (lane < ntok) {
+					const BmwTok &bt = s_tok[lane];
+
+					if (bt.col != BMW_BCOL_NONE) {
+						const uint32_t *row = p.boff + (size_t)bt.col * (p.nblocks + 1) + gb;
+
+						my_lo = __ldg(row);
+						my_hi = __ldg(row + 1);
+					} else {
+						/*
+						 * A short list: the slice of the block's mini-tile
+						 * (or tile) is a handful of postings; the warp
+						 * loads all of it and keeps the block's.  Longer
+						 * than the warp's registers: narrow it first.
+						 */
+						const uint32_t idx = base >> bt.fine_shift;
+
+						my_lo = __ldg(bt.fine + idx);
+						my_hi = __ldg(bt.fine + idx + 1);
+						if (my_hi - my_lo > 32 * NP) {
+							const uint2 *list = p.post + bt.post_off;
+							uint32_t l = my_lo, h = my_hi;
+
+							while (l < h) {
+								const uint32_t mid = (l + h) >> 1;
+
+								if (__ldg(list + mid).x < base)
+									l = mid + 1;
+								else
+									h = mid;
+							}
+							my_lo = l;
+							h = min(my_hi, l + BS);
+							while (l < h) {
+								const uint32_t mid = (l + h) >> 1;
+
+								if (__ldg(list + mid).x < base + BS)
+									l = mid + 1;
+								else
+									h = mid;
+							}
+							my_hi = l;
+						}
+					}
+				}
+				__syncwarp();
+				for (uint32_t j0 = 0; j0 < ntok; j0 += BMW_TOK_GROUP) {
+					uint2 v[BMW_TOK_GROUP][NP];
+
+					/* Every load of the group is in flight before the first sum. */
+#pragma unroll
+					for (uint32_t g = 0; g < BMW_TOK_GROUP; g++) {
+						const uint32_t j = j0 + g;
+						const uint32_t lo_j = __shfl_sync(0xffffffffu, my_lo, j & 31u);
+						const uint32_t hi_j = __shfl_sync(0xffffffffu, my_hi, j & 31u);
+
+#pragma unroll
+						for (uint32_t r = 0; r < NP; r++) {
+							const uint32_t i = lo_j + lane + 32 * r;
+
+							v[g][r] = make_uint2(base, 0u);
+							if (j < ntok && i < hi_j)
+								v[g][r] = __ldg(p.post + s_tok[j].post_off + i);
+							/* A short list's slice may reach past the block. */
+							if (v[g][r].x - base >= BS)
+								v[g][r] = make_uint2(base, 0u);
+						}
+					}
+#pragma unroll
+					for (uint32_t g = 0; g < BMW_TOK_GROUP; g++) {
+						const uint32_t j = j0 + g;
+
+						if (j >= ntok)
+							break;
+						float sc[NP];
+
+						st_score<false, ALGO, NP>(sp, s_logtab, v[g], s_tok[j].idf, sc);
+#pragma unroll
+						for (uint32_t r = 0; r < NP; r++) {
+							if (v[g][r].y != 0u) {
+								float *a = wacc + (v[g][r].x - base);
+
+								*a = __fadd_rn(*a, sc[r]);
+								st_post++;
+							}
+						}
+						__syncwarp();
+					}
+				}
+				/* Candidates: sums that beat the current threshold key. */
+				const unsigned long long th = *(volatile unsigned long long *)&s_theta;
+				unsigned long long keys[NP];
+				uint32_t mine = 0;
+
+#pragma unroll
+				for (uint32_t r = 0; r < NP; r++) {
+					const float val = wacc[lane + 32 * r];
+
+					keys[r] = make_key(val, base + lane + 32 * r);
+					if (val == 0.f || keys[r] <= th)
+						keys[r] = 0;
+					mine += keys[r] != 0;
+				}
+				/* exclusive prefix over the lanes */
+				uint32_t incl = mine;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) {
+					const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
+
+					if ((int)lane >= o)
+						incl += x;
+				}
+				const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+				uint32_t at = 0;
+				bool fits = true;
+
+				if (total) {
+					if (lane == 0) {
+						at = atomicAdd(&s_ncand, total);
+						if (at + total > BMW_CAND) {
+							atomicSub(&s_ncand, total);
+							s_overflow = 1;
+							at = 0xffffffffu;
+						}
+					}
+					at = __shfl_sync(0xffffffffu, at, 0);
+					fits = at != 0xffffffffu;
+					if (fits) {
+						uint32_t w = at + incl - mine;
+
+#pragma unroll
+						for (uint32_t r = 0; r < NP; r++)
+							if (keys[r])
+								s_cand[w++] = keys[r];
+					}
+				}
+				if (fits && lane == 0) {
+					ub[b] = 0.f;		/* done */
+					st_blocks++;
+				}
+				__syncwarp();
+			}
+			__syncthreads();
+
+			/* ---- cut the candidates back to the k best ---- */
+			const uint32_t nc = s_ncand;
+
+			if (nc >= k) {
+				for (uint32_t i = tid; i < nc; i += BMW_THREADS) {
+					const unsigned long long key = s_cand[i];
+					uint32_t rank = 0;
+
+					for (uint32_t j = 0; j < nc; j++)
+						rank += s_cand[j] > key;
+					if (rank < k)
+						s_top[rank] = key;
+				}
+				__syncthreads();
+				for (uint32_t i = tid; i < k; i += BMW_THREADS)
+					s_cand[i] = s_top[i];
+				if (tid == 0) {
+					const unsigned long long kth = s_top[k - 1];
+
+					s_ncand = k;
+					if (kth > s_theta) {
+						s_theta = kth;
+						atomicMax(p.thr + slot, kth);
+					}
+				}
+			}
+			if (!partial && !s_overflow)
+				break;		/* every live block was scored */
+		}
+
+		/* ---- the item's cell ---- */
+		__syncthreads();
+		const uint32_t nc = s_ncand;		/* <= k */
+
+		if (nc) {
+			const unsigned long long cell0 = (unsigned long long)slot * p.nchunks;
+			unsigned long long *out = p.cand + (cell0 + chunk) * k;
+
+			for (uint32_t i = tid; i < nc; i += BMW_THREADS)
+				out[i] = s_cand[i];
+			__threadfence();
+			__syncthreads();
+			if (tid == 0)
+				*(volatile uint32_t *)(p.tile_count + cell0 + chunk) = nc;
+			/*
+			 * The query's exact k-th best so far: this cell merged with
+			 * the cells its other chunks have published (keys first, then
+			 * the count, fenced).  Later items of the query start from it.
+			 */
+			const unsigned long long cur = s_theta;
+
+			for (uint32_t idx = tid; idx < p.nchunks * k; idx += BMW_THREADS) {
+				const uint32_t c2 = idx / k, r = idx % k;
+
+				if (c2 == chunk)
+					continue;
+				const uint32_t cnt = *(volatile uint32_t *)(p.tile_count + cell0 + c2);
+
+				if (r < cnt) {
+					__threadfence();
+					const unsigned long long key =
+					    *(volatile unsigned long long *)(p.cand + (cell0 + c2) * k + r);
+
+					if (key >= cur) {
+						const uint32_t at = atomicAdd(&s_ncand, 1u);
+
+						if (at < BMW_CAND)
+							s_cand[at] = key;
+					}
+				}
+			}
+			__syncthreads();
+			const uint32_t np = s_ncand;
+
+			if (np > nc && np >= k && np <= BMW_CAND) {
+				for (uint32_t i = tid; i < np; i += BMW_THREADS) {
+					const unsigned long long key = s_cand[i];
+					uint32_t rank = 0;
+
+					for (uint32_t j = 0; j < np; j++)
+						rank += s_cand[j] > key;
+					if (rank == k - 1 && key > cur)
+						atomicMax(p.thr + slot, key);
+				}
+			}
+		}
+	}
+	if (p.stats && lane == 0) {
+		if (st_items)
+			atomicAdd(p.stats + 0, st_items);
+		if (st_blocks)
+			atomicAdd(p.stats + 1, st_blocks);
+		if (st_rounds)
+			atomicAdd(p.stats + 3, st_rounds);
+	}
+	if (p.stats) {
+		st_post = __reduce_add_sync(0xffffffffu, (unsigned)st_post);
+		if (lane == 0 && st_post)
+			atomicAdd(p.stats + 2, st_post);
+	}
+}
+
+#endif

@@ -156,7 +156,7 @@ local_df_kernel(const unsigned long long *__restrict__ off, uint32_t n_terms,
  */
 __device__ __forceinline__ void
 fill_skip_row(const uint2 *__restrict__ list, uint32_t df, uint32_t ntiles,
-    uint32_t *__restrict__ row)
+    uint32_t *__restrict__ row, uint32_t shift = TILE_SHIFT)
 {
 	if (df == 0) {
 		for (uint32_t j = threadIdx.x; j <= ntiles; j += blockDim.x)
@@ -164,8 +164,8 @@ fill_skip_row(const uint2 *__restrict__ list, uint32_t df, uint32_t ntiles,
 		return;
 	}
 	for (uint32_t i = threadIdx.x; i < df; i += blockDim.x) {
-		const uint32_t tile = list[i].x >> TILE_SHIFT;
-		const uint32_t lo = i ? (list[i - 1].x >> TILE_SHIFT) + 1 : 0;
+		const uint32_t tile = list[i].x >> shift;
+		const uint32_t lo = i ? (list[i - 1].x >> shift) + 1 : 0;
 
 		for (uint32_t j = lo; j <= tile; j++)
 			row[j] = i;
@@ -176,18 +176,22 @@ fill_skip_row(const uint2 *__restrict__ list, uint32_t df, uint32_t ntiles,
 	}
 }
 
-/* Permanent rows: one block per long term (rows[r] = term index). */
+/*
+ * Permanent rows: one block per long term (rows[r] = term index); tiles of
+ * 2^shift documents (TILE_SHIFT for the scorers' tiles, MT_SHIFT for the
+ * mini-tiles of the block scorer).
+ */
 __global__ void __launch_bounds__(256)
 build_skip_rows_kernel(const uint2 *__restrict__ post,
     const unsigned long long *__restrict__ term_off,
     const uint32_t *__restrict__ long_terms, uint32_t ntiles,
-    uint32_t *__restrict__ skip)
+    uint32_t *__restrict__ skip, uint32_t shift)
 {
 	const uint32_t t = long_terms[blockIdx.x];
 	const unsigned long long s = term_off[t];
 
 	fill_skip_row(post + s, (uint32_t)(term_off[t + 1] - s), ntiles,
-	    skip + (size_t)blockIdx.x * (ntiles + 1));
+	    skip + (size_t)blockIdx.x * (ntiles + 1), shift);
 }
 
 /*

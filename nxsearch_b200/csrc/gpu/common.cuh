@@ -40,6 +40,7 @@
 #endif
 #define TILE_WORDS	(TILE_DOCS / 32)
 #define DF_LONG		2048u			// permanent skip row threshold
+#define MT_SHIFT	10			// mini-tiles: finer rows of the long lists
 #define LOGTAB_N	256			// (float)log(c + 1) for c < 256
 #define SMALL_K_MAX	2048u			// optimised top-k path limit
 #define SORT_CAP	4096u			// keys sorted in shared memory
@@ -55,6 +56,13 @@ struct DTok {
 	uint32_t		df_local;
 	float			idf;
 	unsigned long long	dense_off;	// word offset of its dense column, or DENSE_NONE
+	/*
+	 * Finer slice boundaries for the block scorer (bmw.cuh): per mini-tile of
+	 * 2^MT_SHIFT documents for the long lists, else `skip` again (tiles).
+	 */
+	const uint32_t *	fine;
+	uint32_t		fine_shift;
+	uint32_t		bcol;		// row of its block arrays (bmw.cuh), or 0xffffffff
 };
 
 /* 16-byte result record (also the NCCL all-gather payload). */

@@ -6,11 +6,13 @@
  * runs on the device or fails with an error message.
  */
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <thread>
 #include <vector>
 
@@ -30,6 +32,36 @@
 
 static thread_local char g_last_error[512];
 
+/*
+ * Device / pinned allocations and frees since the library was loaded
+ * (nxsb_alloc_events): cudaFree is a device-wide synchronisation, so none of
+ * them belongs on the steady-state search path.  Every allocation in this
+ * file goes through the counted wrappers below.
+ */
+static std::atomic<uint64_t> g_alloc_events{0};
+
+static cudaError_t
+counted_malloc(void **p, size_t bytes)
+{
+	g_alloc_events++;
+	return cudaMalloc(p, bytes);
+}
+
+static void
+counted_free(void *p)
+{
+	if (p) {
+		g_alloc_events++;
+		cudaFree(p);
+	}
+}
+
+extern "C" uint64_t
+nxsb_alloc_events(void)
+{
+	return g_alloc_events.load();
+}
+
 /* Grow-only device / pinned-host buffers: no allocation in steady state. */
 struct DevBuf {
 	void *	p = nullptr;
@@ -41,7 +73,7 @@ struct DevBuf {
 			return cudaSuccess;
 		release();
 		const size_t want = bytes + bytes / 2 + 256;
-		cudaError_t rc = cudaMalloc(&p, want);
+		cudaError_t rc = counted_malloc(&p, want);
 		if (rc == cudaSuccess)
 			cap = want;
 		else
@@ -50,8 +82,7 @@ struct DevBuf {
 	}
 	void release()
 	{
-		if (p)
-			cudaFree(p);
+		counted_free(p);
 		p = nullptr;
 		cap = 0;
 	}
@@ -67,6 +98,7 @@ struct PinnedBuf {
 			return cudaSuccess;
 		release();
 		const size_t want = bytes + bytes / 2 + 256;
+		g_alloc_events++;
 		cudaError_t rc = cudaMallocHost(&p, want);
 		if (rc == cudaSuccess)
 			cap = want;
@@ -76,8 +108,10 @@ struct PinnedBuf {
 	}
 	void release()
 	{
-		if (p)
+		if (p) {
+			g_alloc_events++;
 			cudaFreeHost(p);
+		}
 		p = nullptr;
 		cap = 0;
 	}
@@ -96,6 +130,7 @@ struct Batch {
 	uint32_t	max_tokens = 0;		// over the boolean queries (bitmap rows)
 	uint32_t	max_tokens_all = 0;	// over every query (plan record stride)
 	uint64_t	bytes = 0;		// algorithmic bytes
+	bool		bmw = false;		// OR queries go through score_bmw_kernel
 	std::vector<uint32_t> q_or, q_logic;	// host lists
 	/*
 	 * Shared dense prefixes (stream.cuh "base columns"): the distinct ordered
@@ -160,12 +195,25 @@ struct nxsb_engine {
 	uint32_t *	d_dense_used = nullptr;		// [256] column referenced by the batch
 	float		dense_min = 0.6f;		// df_local / N at which a list gets a column
 	uint32_t *	d_skip = nullptr;
+	uint32_t *	d_skip_mt = nullptr;		// [n_long][n_mt + 1] mini-tile rows
+	uint32_t	n_mt = 0;
 	unsigned long long *d_doc_ids = nullptr;
 	uint32_t *	d_doc_len = nullptr;
 	float *		d_logtab = nullptr;
 	std::vector<uint32_t> h_df_local, h_df;
 	std::vector<int32_t> h_dense_col;		// [V] as d_dense_col
 	bool		share_dense = true;		// NXSB_SHARE_DENSE=0: development switch
+	/*
+	 * Block arrays of the column terms (bmw.cuh): lists averaging at least
+	 * two postings per block of 2^bshift documents.
+	 */
+	bool		bmw_enabled = true;		// NXSB_BMW=0: every query streams
+	uint32_t	bshift = 6, nblocks = 0, nchunks = 0, n_bcol = 0;
+	uint32_t *	d_bcol = nullptr;		// [V] row of a term or BMW_BCOL_NONE
+	uint32_t *	d_bcol_terms = nullptr;		// [n_bcol] term index of a row
+	uint32_t *	d_boff = nullptr;		// [n_bcol][nblocks + 1]
+	float *		d_bmax_bm25 = nullptr, *d_bmax_tfidf = nullptr;	// [n_bcol][nblocks]
+	unsigned long long *d_bmw_stats = nullptr;	// [4] counters of the BMW launches
 	uint64_t	token_count = 0;
 	uint32_t	doc_count = 0;
 	float		K0 = 0, K1 = 0;
@@ -186,6 +234,10 @@ struct nxsb_engine {
 	size_t		tt_bytes = 0;
 	size_t		tile_cnt_bytes = 0;
 	bool		force_v2 = false;		// NXSB_KERNEL=v2: A/B against tiles.cuh
+
+	/* cudaFuncSetAttribute / occupancy results, once per kernel variant. */
+	struct KernFit { size_t smem; int per_sm; };
+	std::map<const void *, KernFit> kfit;
 
 	Batch		batches[MAX_HANDLES];
 	Batch		oneshot;	// reused by nxsb_engine_search
@@ -251,16 +303,69 @@ template <typename T>
 static cudaError_t
 dev_alloc(T **p, size_t n)
 {
-	return cudaMalloc(reinterpret_cast<void **>(p), (n ? n : 1) * sizeof(T));
+	return counted_malloc(reinterpret_cast<void **>(p), (n ? n : 1) * sizeof(T));
 }
 
 template <typename T>
 static void
 dev_free(T *&p)
 {
-	if (p)
-		cudaFree(p);
+	counted_free(p);
 	p = nullptr;
+}
+
+/*
+ * Engine-wide arenas grow with headroom and are sized from the batch's
+ * capacity (slots_for), not from what one batch happens to need, so that a
+ * stream of batches of one shape never reallocates (cudaFree synchronises
+ * the whole device).
+ */
+template <typename T>
+static int
+ensure_arena(nxsb_engine_t *e, T *&p, size_t &cap_bytes, size_t want, const char *what)
+{
+	if (want <= cap_bytes)
+		return 0;
+	dev_free(p);
+	cap_bytes = 0;
+	const size_t sz = want + want / 4 + 4096;
+
+	if (counted_malloc(reinterpret_cast<void **>(&p), sz) != cudaSuccess) {
+		p = nullptr;
+		return fail(e, "%s allocation (%zu bytes) failed: %s", what, sz,
+		    cudaGetErrorString(cudaGetLastError()));
+	}
+	cap_bytes = sz;
+	return 0;
+}
+
+/* Query slots (real + virtual) the arenas are sized for. */
+static inline uint32_t
+virtual_cap(uint32_t n_q)
+{
+	return std::max(64u, n_q / 4);
+}
+
+static inline size_t
+slots_for(uint32_t n_q)
+{
+	return (size_t)n_q + virtual_cap(n_q);
+}
+
+/* Dynamic shared memory opt-in and CTAs per SM of a kernel, cached. */
+static int
+kernel_fit(nxsb_engine_t *e, const void *fn, int threads, size_t smem, int *per_sm)
+{
+	auto it = e->kfit.find(fn);
+
+	if (it != e->kfit.end() && it->second.smem == smem) {
+		*per_sm = it->second.per_sm;
+		return 0;
+	}
+	CK(e, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	CK(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, fn, threads, smem));
+	e->kfit[fn] = { smem, *per_sm };
+	return 0;
 }
 
 extern "C" int
@@ -306,6 +411,40 @@ nxsb_engine_launch_count(const nxsb_engine_t *e)
 	for (const nxsb_engine *c : e->segs)
 		n += c->launches;
 	return n;
+}
+
+extern "C" int
+nxsb_engine_set_pruning(nxsb_engine_t *e, int on)
+{
+	const int was = e->bmw_enabled;
+
+	e->bmw_enabled = on != 0;
+	for (nxsb_engine *c : e->segs)
+		c->bmw_enabled = e->bmw_enabled;
+	return was;
+}
+
+extern "C" int
+nxsb_engine_pruning_stats(nxsb_engine_t *e, uint64_t out[4], int reset)
+{
+	unsigned long long v[4];
+
+	CK(e, cudaSetDevice(e->device));
+	CK(e, cudaStreamSynchronize(e->stream));
+	CK(e, cudaMemcpy(v, e->d_bmw_stats, sizeof(v), cudaMemcpyDeviceToHost));
+	for (int i = 0; i < 4; i++)
+		out[i] = v[i];
+	for (nxsb_engine *c : e->segs) {
+		uint64_t sub[4];
+
+		if (nxsb_engine_pruning_stats(c, sub, reset) == -1)
+			return fail(e, "%s", c->err);
+		for (int i = 0; i < 4; i++)
+			out[i] += sub[i];
+	}
+	if (reset)
+		CK(e, cudaMemset(e->d_bmw_stats, 0, sizeof(v)));
+	return 0;
 }
 
 extern "C" nxsb_engine_t *
@@ -355,6 +494,18 @@ nxsb_engine_create(int device)
 		/* Development switch: every query streams its own dense columns. */
 		if ((kv = getenv("NXSB_SHARE_DENSE")) != NULL)
 			e->share_dense = atoi(kv) != 0;
+		/* NXSB_BMW=0: no block-max pruning, every query streams all its postings. */
+		if ((kv = getenv("NXSB_BMW")) != NULL)
+			e->bmw_enabled = atoi(kv) != 0;
+		/* Development switch: documents per block = 2^NXSB_BMW_SHIFT. */
+		if ((kv = getenv("NXSB_BMW_SHIFT")) != NULL)
+			e->bshift = (uint32_t)std::min(BMW_SHIFT_MAX, std::max(BMW_SHIFT_MIN, atoi(kv)));
+	}
+	if (dev_alloc(&e->d_bmw_stats, 4) != cudaSuccess ||
+	    cudaMemset(e->d_bmw_stats, 0, 32) != cudaSuccess) {
+		snprintf(g_last_error, sizeof(g_last_error), "CUDA alloc failed");
+		delete e;
+		return nullptr;
 	}
 	for (auto &r : e->runs)
 		for (int i = 0; i < EV_PER_RUN; i++)
@@ -388,7 +539,14 @@ free_image(nxsb_engine_t *e)
 	dev_free(e->d_dense_terms);
 	dev_free(e->d_dense_used);
 	e->n_dense = 0;
+	dev_free(e->d_bcol);
+	dev_free(e->d_bcol_terms);
+	dev_free(e->d_boff);
+	dev_free(e->d_bmax_bm25);
+	dev_free(e->d_bmax_tfidf);
+	e->n_bcol = 0;
 	dev_free(e->d_skip);
+	dev_free(e->d_skip_mt);
 	dev_free(e->d_doc_ids);
 	dev_free(e->d_doc_len);
 	e->loaded = false;
@@ -457,6 +615,7 @@ nxsb_engine_destroy(nxsb_engine_t *e)
 	if (e->d_cub_tmp)
 		cudaFree(e->d_cub_tmp);
 	dev_free(e->d_logtab);
+	dev_free(e->d_bmw_stats);
 	for (auto &r : e->runs)
 		for (int i = 0; i < EV_PER_RUN; i++)
 			if (r.ev[i])
@@ -541,6 +700,18 @@ upload_stats(nxsb_engine_t *e)
 	    cudaMemcpyHostToDevice, e->stream));
 	CK(e, cudaMemcpyAsync(e->d_idf_tfidf, tfidf.data(), V * sizeof(float),
 	    cudaMemcpyHostToDevice, e->stream));
+	if (e->n_bcol) {
+		/* The BM25 weight depends on K0 / K1: the block maxima follow the statistics. */
+		const size_t words = (size_t)e->n_bcol * e->nblocks;
+
+		CK(e, cudaMemsetAsync(e->d_bmax_bm25, 0, words * 4, e->stream));
+		CK(e, cudaMemsetAsync(e->d_bmax_tfidf, 0, words * 4, e->stream));
+		block_max_kernel<<<dim3(16, e->n_bcol), 256, 0, e->stream>>>(e->d_post,
+		    e->d_term_off, e->d_bcol_terms, e->nblocks, e->bshift, e->d_logtab,
+		    e->K0, e->K1, e->d_bmax_bm25, e->d_bmax_tfidf);
+		e->launches++;
+		CK(e, cudaGetLastError());
+	}
 	CK(e, cudaStreamSynchronize(e->stream));
 	return 0;
 }
@@ -725,7 +896,9 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 			}
 		}
 		e->n_long = longs.size();
+		e->n_mt = std::max(1u, (N + (1u << MT_SHIFT) - 1) >> MT_SHIFT);
 		if (dev_alloc(&e->d_skip, (size_t)e->n_long * (e->ntiles + 1)) ||
+		    dev_alloc(&e->d_skip_mt, (size_t)e->n_long * (e->n_mt + 1)) ||
 		    dev_alloc(&d_long, e->n_long)) {
 			fail(e, "skip table allocation failed");
 			break;
@@ -736,8 +909,10 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 			cudaMemcpyAsync(d_long, longs.data(), (size_t)e->n_long * 4,
 			    cudaMemcpyHostToDevice, st);
 			build_skip_rows_kernel<<<e->n_long, 256, 0, st>>>(e->d_post,
-			    e->d_term_off, d_long, e->ntiles, e->d_skip);
-			e->launches++;
+			    e->d_term_off, d_long, e->ntiles, e->d_skip, TILE_SHIFT);
+			build_skip_rows_kernel<<<e->n_long, 256, 0, st>>>(e->d_post,
+			    e->d_term_off, d_long, e->n_mt, e->d_skip_mt, MT_SHIFT);
+			e->launches += 2;
 		}
 		if (cudaStreamSynchronize(st) != cudaSuccess) {
 			fail(e, "skip table build failed: %s",
@@ -785,6 +960,56 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 			e->d_dense_terms = d_dterms;
 			if (!ok) {
 				fail(e, "dense column build failed: %s",
+				    cudaGetErrorString(cudaGetLastError()));
+				break;
+			}
+		}
+
+		/* Block arrays of the column terms (bmw.cuh). */
+		{
+			e->nblocks = std::max(1u, (N + (1u << e->bshift) - 1) >> e->bshift);
+			e->nchunks = (e->nblocks + BMW_CH_BLOCKS - 1) / BMW_CH_BLOCKS;
+			std::vector<uint32_t> bcol(V, BMW_BCOL_NONE), bterms;
+
+			if (!e->wide && e->bmw_enabled) {
+				/* At least two postings per block on average; 1 GiB of arrays at most. */
+				const uint64_t min_df = std::max<uint64_t>(2ull * e->nblocks, 64);
+				const size_t cap = std::max<size_t>(1, (1ull << 30) / (12ull * (e->nblocks + 1)));
+
+				for (uint32_t t = 0; t < V; t++)
+					if (e->h_df_local[t] >= min_df)
+						bterms.push_back(t);
+				if (bterms.size() > cap) {
+					std::nth_element(bterms.begin(), bterms.begin() + cap, bterms.end(),
+					    [&](uint32_t a, uint32_t b) {
+						return e->h_df_local[a] > e->h_df_local[b];
+					    });
+					bterms.resize(cap);
+					std::sort(bterms.begin(), bterms.end());
+				}
+				for (size_t c = 0; c < bterms.size(); c++)
+					bcol[bterms[c]] = (uint32_t)c;
+			}
+			e->n_bcol = bterms.size();
+			bool ok = dev_alloc(&e->d_bcol, V) == cudaSuccess &&
+			    dev_alloc(&e->d_bcol_terms, e->n_bcol) == cudaSuccess &&
+			    dev_alloc(&e->d_boff, (size_t)e->n_bcol * (e->nblocks + 1)) == cudaSuccess &&
+			    dev_alloc(&e->d_bmax_bm25, (size_t)e->n_bcol * e->nblocks) == cudaSuccess &&
+			    dev_alloc(&e->d_bmax_tfidf, (size_t)e->n_bcol * e->nblocks) == cudaSuccess;
+			if (ok) {
+				cudaMemcpyAsync(e->d_bcol, bcol.data(), (size_t)V * 4,
+				    cudaMemcpyHostToDevice, st);
+				if (e->n_bcol) {
+					cudaMemcpyAsync(e->d_bcol_terms, bterms.data(), (size_t)e->n_bcol * 4,
+					    cudaMemcpyHostToDevice, st);
+					build_block_offsets_kernel<<<e->n_bcol, 256, 0, st>>>(e->d_post,
+					    e->d_term_off, e->d_bcol_terms, e->nblocks, e->bshift, e->d_boff);
+					e->launches++;
+				}
+				ok = cudaStreamSynchronize(st) == cudaSuccess;
+			}
+			if (!ok) {
+				fail(e, "block array build failed: %s",
 				    cudaGetErrorString(cudaGetLastError()));
 				break;
 			}
@@ -866,6 +1091,8 @@ nxsb_engine_segment_add(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 		return fail(e, "segment_add: %s", g_last_error);
 	c->stream = e->stream;
 	c->force_v2 = e->force_v2;
+	c->bmw_enabled = e->bmw_enabled;
+	c->bshift = e->bshift;
 	if (nxsb_engine_load_shard(c, sd) == -1) {
 		fail(e, "segment_add: %s", c->err);
 		c->stream = c->own_stream;
@@ -1039,6 +1266,9 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 	B.bytes = 0;
 	B.q_or.clear();
 	B.q_logic.clear();
+	/* OR queries with a small limit are pruned (bmw.cuh); the rest stream. */
+	B.bmw = e->bmw_enabled && !e->wide && !e->force_v2 && b->limit <= BMW_K_MAX &&
+	    e->d_bcol != nullptr;
 
 	for (uint32_t i = 0; i < b->n_queries; i++) {
 		const nxsb_query_t &q = b->queries[i];
@@ -1076,9 +1306,10 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 	std::vector<QDesc> vq;			// virtual queries
 	std::vector<uint32_t> vtok;		// their tokens
 	std::vector<uint2> qbase(B.q_or.size(), make_uint2(0u, 0u));
-	if (e->share_dense && e->n_dense && !e->wide && !e->force_v2 &&
+	if (e->share_dense && e->n_dense && !e->wide && !e->force_v2 && !B.bmw &&
 	    B.limit <= ST_K_MAX && !e->h_dense_col.empty()) {
 		std::vector<std::pair<uint64_t, uint32_t>> seen;	// (terms packed, prefix number)
+		const uint32_t vcap = virtual_cap(B.n_q);	/* the arenas' headroom */
 
 		for (size_t i = 0; i < B.q_or.size(); i++) {
 			const nxsb_query_t &q = b->queries[B.q_or[i]];
@@ -1147,6 +1378,8 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 						break;
 					}
 				}
+			if (pn == UINT32_MAX && vq.size() >= vcap)
+				continue;	/* out of virtual slots: the query streams its columns */
 			if (pn == UINT32_MAX) {
 				QDesc v;
 
@@ -1397,10 +1630,8 @@ launch_tiles(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
 	       : score_tiles_kernel<LOGIC, false, NXSB_ALGO_TFIDF>);
 	int per_sm = 0;
 
-	CK(e, cudaFuncSetAttribute(kern,
-	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	CK(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern,
-	    TILE_THREADS, smem));
+	if (kernel_fit(e, (const void *)kern, TILE_THREADS, smem, &per_sm) == -1)
+		return -1;
 	if (per_sm < 1)
 		return fail(e, "scoring kernel does not fit an SM (smem %zu)", smem);
 
@@ -1424,27 +1655,24 @@ launch_tiles(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_q,
 template <bool LOGIC>
 static int
 launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist,
-    const uint2 *d_qbase, uint32_t n_q, uint32_t k_tile, uint64_t cand_cap)
+    const uint2 *d_qbase, uint32_t n_q, uint32_t k_tile, uint64_t cand_cap,
+    size_t chunk_cap)
 {
 	const uint64_t items = (uint64_t)n_q * e->ntiles;
 	const uint32_t stride = 16u * (1u + std::max(B.max_tokens_all, 1u));
-	const size_t want = (size_t)items * stride;
+	const size_t want_cnt = (size_t)items * 4;
 	StreamParams p;
 
-	if (want > e->plan_bytes) {
-		dev_free(e->d_plan);
-		e->plan_bytes = 0;
-		if (dev_alloc(&e->d_plan, want + want / 4) != cudaSuccess)
-			return fail(e, "plan arena allocation (%zu bytes) failed", want);
-		e->plan_bytes = want + want / 4;
-	}
-	const size_t want_cnt = (size_t)items * 4;
-	if (want_cnt > e->tile_cnt_bytes) {
-		dev_free(e->d_tile_cnt);
-		e->tile_cnt_bytes = 0;
-		if (dev_alloc(&e->d_tile_cnt, items + items / 4) != cudaSuccess)
-			return fail(e, "tile count allocation (%zu bytes) failed", want_cnt);
-		e->tile_cnt_bytes = (items + items / 4) * 4;
+	/* Sized for the chunk capacity run_list works with, and 4-token records at least. */
+	{
+		const size_t cap_q = std::max<size_t>(n_q, std::min<size_t>(slots_for(B.n_q), chunk_cap));
+		const size_t cap_items = cap_q * e->ntiles;
+
+		if (ensure_arena(e, e->d_plan, e->plan_bytes,
+		    cap_items * std::max(stride, 16u * 5u), "plan arena") == -1 ||
+		    ensure_arena(e, e->d_tile_cnt, e->tile_cnt_bytes, cap_items * 4,
+		    "tile count") == -1)
+			return -1;
 	}
 	p.post = e->d_post;
 	p.plan = e->d_plan;
@@ -1466,15 +1694,9 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist,
 	if (LOGIC) {
 		/* Truth tables of the boolean programs and their subset closures:
 		 * 8 + 8 words per query. */
-		const size_t want_tt = (size_t)n_q * 16 * 4;
-
-		if (want_tt > e->tt_bytes) {
-			dev_free(e->d_tt);
-			e->tt_bytes = 0;
-			if (dev_alloc(&e->d_tt, (size_t)n_q * 16 * 2) != cudaSuccess)
-				return fail(e, "truth table allocation failed");
-			e->tt_bytes = want_tt * 2;
-		}
+		if (ensure_arena(e, e->d_tt, e->tt_bytes,
+		    std::max<size_t>(n_q, B.n_q) * 16 * 4, "truth table") == -1)
+			return -1;
 	}
 	p.tt = e->d_tt;
 	p.dense = reinterpret_cast<const uint32_t *>(e->d_dense_sc);
@@ -1489,10 +1711,8 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist,
 	const size_t smem = StCfg<LOGIC>::SMEM;
 	int per_sm = 0;
 
-	CK(e, cudaFuncSetAttribute(kern,
-	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-	CK(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern,
-	    ST_THREADS, smem));
+	if (kernel_fit(e, (const void *)kern, ST_THREADS, smem, &per_sm) == -1)
+		return -1;
 	if (per_sm < 1)
 		return fail(e, "stream kernel does not fit an SM (smem %zu)", smem);
 	const unsigned grid = (unsigned)std::min<uint64_t>(items,
@@ -1518,6 +1738,98 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist,
 }
 
 /*
+ * OR queries through the block-max scorer (bmw.cuh): one persistent launch
+ * over (query, chunk) items, then the same per-query merge of the cells.
+ */
+static int
+run_bmw(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list, Rec *d_recs)
+{
+	cudaStream_t st = e->stream;
+	const uint32_t k = B.limit;
+	const size_t cells = (size_t)e->nchunks * k;
+	/* Item numbers are 32-bit. */
+	const uint32_t chunk = (uint32_t)std::min<uint64_t>(n_list, 0xfffffff0ull / e->nchunks);
+	const size_t slots = std::max<size_t>(chunk, std::min<size_t>(slots_for(B.n_q), chunk));
+
+	if (ensure_arena(e, e->d_cand, e->cand_bytes, slots * cells * 8, "candidate arena") == -1 ||
+	    ensure_arena(e, e->d_tile_cnt, e->tile_cnt_bytes, slots * e->nchunks * 4,
+	    "tile count") == -1)
+		return -1;
+
+	for (uint32_t q0 = 0; q0 < n_list; q0 += chunk) {
+		const uint32_t n = std::min(chunk, n_list - q0);
+		BmwParams p;
+
+		p.post = e->d_post;
+		p.toks = B.d_toks;
+		p.queries = B.d_queries;
+		p.qlist = d_qlist + q0;
+		p.n_q = n;
+		p.nchunks = e->nchunks;
+		p.nblocks = e->nblocks;
+		p.n_docs = e->n_docs;
+		p.ntiles = e->ntiles;
+		p.k = k;
+		p.boff = e->d_boff;
+		p.bmax = B.algo == NXSB_ALGO_BM25 ? e->d_bmax_bm25 : e->d_bmax_tfidf;
+		p.thr = B.d_thr;
+		p.tile_count = e->d_tile_cnt;
+		p.cand = e->d_cand;
+		p.work_counter = B.d_work;
+		p.logtab = e->d_logtab;
+		p.K0 = e->K0;
+		p.K1 = e->K1;
+		p.stats = e->d_bmw_stats;
+
+		const void *kern = nullptr;
+		size_t smem = 0;
+#define BMW_PICK(S) do {								\
+		kern = B.algo == NXSB_ALGO_BM25						\
+		    ? (const void *)score_bmw_kernel<NXSB_ALGO_BM25, S>			\
+		    : (const void *)score_bmw_kernel<NXSB_ALGO_TFIDF, S>;		\
+		smem = BmwCfg<S>::SMEM;							\
+	} while (0)
+		switch (e->bshift) {
+		case 5: BMW_PICK(5); break;
+		case 6: BMW_PICK(6); break;
+		case 7: BMW_PICK(7); break;
+		default: BMW_PICK(8); break;
+		}
+#undef BMW_PICK
+		int per_sm = 0;
+
+		if (kernel_fit(e, kern, BMW_THREADS, smem, &per_sm) == -1)
+			return -1;
+		if (per_sm < 1)
+			return fail(e, "block-max kernel does not fit an SM (smem %zu)", smem);
+		const uint64_t items = (uint64_t)n * e->nchunks;
+		const unsigned grid = (unsigned)std::min<uint64_t>(items, (uint64_t)e->n_sms * per_sm);
+
+		CK(e, cudaMemsetAsync(B.d_thr, 0, B.zero_bytes, st));
+		CK(e, cudaMemsetAsync(e->d_tile_cnt, 0, (size_t)items * 4, st));
+		mark(e, "score_tiles");
+		void *args[] = { &p };
+		CK(e, cudaLaunchKernel(kern, dim3(grid), dim3(BMW_THREADS), args, smem, st));
+		e->launches++;
+		mark(e, "topk");
+
+		FinalizeShared fs;
+		fs.queries = B.d_queries;
+		fs.toks = B.d_toks;
+		fs.post = e->d_post;
+		fs.qbase = nullptr;
+		fs.prefix_keys = B.d_prefix_keys;
+		fs.prefix_cnt = B.d_prefix_cnt;
+		fs.n_real = B.n_q;
+		finalize_cells_kernel<<<n, 256, 0, st>>>(e->d_cand, e->d_tile_cnt, e->nchunks,
+		    d_qlist + q0, k, e->d_doc_ids, d_recs, B.d_counts, fs);
+		e->launches++;
+		CK(e, cudaGetLastError());
+	}
+	return 0;
+}
+
+/*
  * Score one list of queries (pure-OR or boolean) in chunks bounded by the
  * candidate arena: tiles -> per-query final top-k.
  */
@@ -1536,14 +1848,14 @@ run_list(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list,
 	if (n_list == 0)
 		return 0;
 
-	size_t want = std::max(per_q, std::min<size_t>(CAND_ARENA_BYTES, per_q * n_list));
-	if (want > e->cand_bytes) {
-		dev_free(e->d_cand);
-		e->cand_bytes = 0;
-		if (dev_alloc(&e->d_cand, want / 8) != cudaSuccess)
-			return fail(e, "candidate arena allocation (%zu bytes) failed", want);
-		e->cand_bytes = want;
-	}
+	if (!LOGIC && B.bmw)
+		return run_bmw(e, B, d_qlist, n_list, d_recs);
+
+	const size_t slots = std::max<size_t>(n_list, slots_for(B.n_q));
+	if (ensure_arena(e, e->d_cand, e->cand_bytes,
+	    std::max(per_q, std::min<size_t>(CAND_ARENA_BYTES, per_q * slots)),
+	    "candidate arena") == -1)
+		return -1;
 	uint32_t chunk = (uint32_t)std::min<size_t>(n_list, e->cand_bytes / per_q);
 	/* Boolean queries fit the stream kernel when a byte holds their tokens. */
 	const bool stream = k <= ST_K_MAX && !e->force_v2 &&
@@ -1573,7 +1885,7 @@ run_list(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list,
 		const uint32_t n = std::min(chunk, n_list - q0);
 
 		if ((stream ? launch_stream<LOGIC>(e, B, d_qlist + q0,
-		    d_qbase ? d_qbase + q0 : nullptr, n, k_tile, cand_cap)
+		    d_qbase ? d_qbase + q0 : nullptr, n, k_tile, cand_cap, chunk)
 		    : launch_tiles<LOGIC>(e, B, d_qlist + q0, n, k_tile, cand_cap)) == -1)
 			return -1;
 		mark(e, "topk");
@@ -1695,15 +2007,15 @@ run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
 		CK(e, cudaMemsetAsync(e->d_dense_used, 0, 512 * 4, st));
 	resolve_tokens_kernel<<<(B.n_tok_all + 255) / 256, 256, 0, st>>>(
 	    B.d_tokens, B.n_tok_all, e->n_terms, e->d_term_off, e->d_skip_row,
-	    e->d_dense_col, e->d_dense_used, (unsigned long long)e->ntiles * TILE_DOCS,
-	    e->d_skip, B.d_tmp_skip,
+	    e->d_dense_col, e->d_bcol, e->d_dense_used, (unsigned long long)e->ntiles * TILE_DOCS,
+	    e->d_skip, e->d_skip_mt, e->n_mt, B.d_tmp_skip,
 	    B.algo == NXSB_ALGO_BM25 ? e->d_idf_bm25 : e->d_idf_tfidf,
 	    e->ntiles, B.d_toks);
 	build_temp_skips_kernel<<<B.n_tok_all, 128, 0, st>>>(e->d_post, B.d_toks,
 	    B.d_tmp_skip, e->ntiles);
 	e->launches += 2;
 	CK(e, cudaGetLastError());
-	if (e->n_dense) {
+	if (e->n_dense && !(B.bmw && B.q_logic.empty())) {
 		/* Score columns of the dense terms this batch refers to. */
 		const unsigned long long col_words = (unsigned long long)e->ntiles * TILE_DOCS;
 		const dim3 grid(e->n_sms * 4, e->n_dense);

@@ -63,7 +63,8 @@ __global__ void __launch_bounds__(256)
 resolve_tokens_kernel(const uint32_t *__restrict__ term_ids, uint32_t n,
     uint32_t n_terms, const unsigned long long *__restrict__ term_off,
     const int32_t *__restrict__ skip_row, const int32_t *__restrict__ dense_col,
-    uint32_t *__restrict__ dense_used, unsigned long long col_words, const uint32_t *__restrict__ skip,
+    const uint32_t *__restrict__ bcol, uint32_t *__restrict__ dense_used, unsigned long long col_words, const uint32_t *__restrict__ skip,
+    const uint32_t *__restrict__ skip_mt, uint32_t n_mt,
     uint32_t *__restrict__ tmp_skip, const float *__restrict__ idf,
     uint32_t ntiles, DTok *__restrict__ out)
 {
@@ -80,7 +81,10 @@ resolve_tokens_kernel(const uint32_t *__restrict__ term_ids, uint32_t n,
 		t.df_local = 0;
 		t.idf = 0.f;
 		t.dense_off = DENSE_NONE;
+		t.bcol = 0xffffffffu;
 		t.skip = tmp_skip + (size_t)i * (ntiles + 1);
+		t.fine = t.skip;
+		t.fine_shift = TILE_SHIFT;
 	} else {
 		const uint32_t ti = id - 1;
 		const unsigned long long s = term_off[ti];
@@ -91,10 +95,13 @@ resolve_tokens_kernel(const uint32_t *__restrict__ term_ids, uint32_t n,
 		t.idf = idf[ti];
 		t.dense_off = dense_col[ti] >= 0 ? (unsigned long long)dense_col[ti] * col_words
 		    : DENSE_NONE;
+		t.bcol = bcol ? bcol[ti] : 0xffffffffu;
 		if (dense_col[ti] >= 0)
 			dense_used[dense_col[ti]] = 1u;	/* dense_scores_kernel will fill it */
 		t.skip = row >= 0 ? skip + (size_t)row * (ntiles + 1)
 		    : tmp_skip + (size_t)i * (ntiles + 1);
+		t.fine = row >= 0 && skip_mt ? skip_mt + (size_t)row * (n_mt + 1) : t.skip;
+		t.fine_shift = row >= 0 && skip_mt ? MT_SHIFT : TILE_SHIFT;
 	}
 	out[i] = t;
 }
@@ -141,6 +148,7 @@ bitonic_sort_desc(unsigned long long *s, uint32_t npow2)
 
 #include "tiles.cuh"
 #include "stream.cuh"
+#include "bmw.cuh"
 
 /*
  * Final per-query top-k: merge the candidates its tiles emitted.  One CTA

@@ -69,6 +69,9 @@ def _bind():
         "nxsb_engine_last_timings": (i, [vp, vp, vp, i]),
         "nxsb_engine_timings": (i, [vp, u32, vp, vp, i]),
         "nxsb_engine_launch_count": (u64, [vp]),
+        "nxsb_alloc_events": (u64, []),
+        "nxsb_engine_set_pruning": (i, [vp, i]),
+        "nxsb_engine_pruning_stats": (i, [vp, vp, i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -78,6 +81,11 @@ def _bind():
 
 def device_count() -> int:
     return _bind().nxsb_gpu_device_count()
+
+
+def alloc_events() -> int:
+    """Device / pinned allocations and frees made by the library so far."""
+    return _bind().nxsb_alloc_events()
 
 
 @dataclass
@@ -299,6 +307,15 @@ class Engine:
     @property
     def launches(self) -> int:
         return self._lib.nxsb_engine_launch_count(self._h)
+
+    def set_pruning(self, on: bool) -> bool:
+        """Exact block-max pruning of OR queries on/off (batches staged afterwards)."""
+        return bool(self._lib.nxsb_engine_set_pruning(self._h, int(on)))
+
+    def pruning_stats(self, reset: bool = False) -> dict[str, int]:
+        out = (C.c_uint64 * 4)()
+        self._check(self._lib.nxsb_engine_pruning_stats(self._h, out, int(reset)))
+        return {"items": out[0], "blocks_scored": out[1], "postings_scored": out[2], "rounds": out[3]}
 
     def __del__(self):  # pragma: no cover - best effort
         try:
