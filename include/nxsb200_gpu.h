@@ -256,11 +256,12 @@ uint64_t	nxsb_alloc_events(void);
  * reference does (ref src/query/search.c:235-272).  On by default
  * (environment NXSB_BMW=0 turns it off at engine creation); set_pruning
  * switches it for the batches staged afterwards and returns the old setting.
- * pruning_stats: out = { (query, chunk) items, blocks scored, postings
- * scored, selection rounds } since creation or the last reset.
+ * pruning_stats: out[0..3] = { (query, chunk) items, blocks scored, postings
+ * scored, selection rounds } since creation or the last reset; out[4..15] are
+ * per-phase cycle counters of a -DBMW_PROF build, else 0.
  */
 int		nxsb_engine_set_pruning(nxsb_engine_t *, int on);
-int		nxsb_engine_pruning_stats(nxsb_engine_t *, uint64_t out[4], int reset);
+int		nxsb_engine_pruning_stats(nxsb_engine_t *, uint64_t out[16], int reset);
 
 #pragma GCC visibility pop
 

@@ -5,34 +5,39 @@
  * `limit` in a heap (ref src/query/search.c:235-272, src/core/results.c:
  * 128-220).  The answer only needs the documents that can still enter the
  * heap, so this kernel never touches most postings (the dynamic pruning of
- * block-max WAND, done tile-at-a-time instead of with posting cursors):
+ * block-max WAND, done block-at-a-time instead of with posting cursors):
  *
- *   The dense document space is cut into BLOCKS of 2^bshift documents.  For
- *   every "column term" -- a list long enough to average two postings per
- *   block -- the image holds, per block, the offset of its first posting
- *   (boff) and the largest query-independent weight any of its postings has
- *   (bmax: BM25 tf-normalisation, or the TF-IDF tf weight; recomputed when
- *   the index statistics move).  A score is weight x idf, both roundings
- *   monotonic, so  sum_t bmax[t][b] * idf[t]  bounds every score in block b
- *   from above, bit for bit (float addition is monotonic, absent terms add
- *   +0).  Short lists have no arrays: their exact per-block maxima are folded
- *   in from the postings themselves (a few per block).
+ *   The dense document space is cut into BLOCKS of 2^bshift documents, 32
+ *   blocks make a SUPERBLOCK, 256 superblocks a CHUNK.  For every "column
+ *   term" -- a list long enough to average a posting per two blocks -- the
+ *   image holds, per block, the offset of its first posting (boff) and the
+ *   largest query-independent weight any of its postings has (bmax: BM25
+ *   tf-normalisation, or the TF-IDF tf weight; recomputed when the index
+ *   statistics move), and the same maxima per superblock (bmax1).  A score is
+ *   weight x idf, both roundings monotonic, so  sum_t bmax[t][b] * idf[t]
+ *   bounds every score in block b from above, bit for bit (float addition is
+ *   monotonic, absent terms add +0).  Shorter lists have no arrays: a
+ *   superblock they touch is charged their best score anywhere (wmax x idf),
+ *   a block their exact maximum in it, folded in from the postings.
  *
- *   work item = (query, CHUNK of 8192 blocks), handed out chunk-major from
- *   the highest ids down so that a query's threshold (its k-th best key so
- *   far, shared through global memory) is known before most of its items
- *   start.  Per item:
- *     1. ub[b] for the chunk's blocks in shared memory;
- *     2. blocks whose bound cannot beat the threshold are dropped; of the
- *        rest the most promising are scored first (a histogram over the
- *        bounds picks them) so that the threshold settles after a handful;
- *     3. a warp scores one block: the block's slice of every token's list,
- *        in TOKEN-LIST ORDER (the reference's float summation order), into a
- *        per-warp accumulator of 2^bshift sums; survivors join the item's
- *        candidate buffer, which is cut back to the k best whenever a round
- *        ends (that k-th key is the new threshold).
- *   The item's <= k keys go to the same per-(query, chunk) cells
- *   finalize_cells_kernel merges for the stream kernel.
+ *   work item = (query, chunk), handed out chunk-major from the highest ids
+ *   down, after one SEED item per query: the seed looks at the superblock
+ *   bounds of the whole shard, scores the best blocks of the best superblocks
+ *   and publishes the k-th best key it saw as the query's first threshold.
+ *   Per item:
+ *     A. one thread per superblock: bound against the threshold;
+ *     B. the blocks of the surviving superblocks: bound against the
+ *        threshold (a thread per block, rows read 128 bytes per warp);
+ *     C. the surviving blocks are scored, the most promising first when there
+ *        are many (a histogram over the bounds picks them): a warp scores one
+ *        block -- the block's slice of every token's list, in TOKEN-LIST ORDER
+ *        (the reference's float summation order), into a per-warp accumulator
+ *        of 2^bshift sums; what beats the threshold joins the item's candidate
+ *        buffer, which is cut back to the k best whenever a round ends (that
+ *        k-th key is the new threshold);
+ *     D. the item's <= k keys go to the same per-(query, chunk) cells
+ *        finalize_cells_kernel merges for the stream kernel, and the query's
+ *        threshold becomes the exact k-th best of all its cells so far.
  *
  * Arithmetic is st_score() of stream.cuh, hence identical bits; ties still
  * fall to the higher document id because a bound is compared as the key
@@ -43,13 +48,15 @@
 
 #define BMW_THREADS	256
 #define BMW_WARPS	(BMW_THREADS / 32)
-#define BMW_CH_BLOCKS	8192u			/* blocks per chunk (ub[] in shared memory) */
+#define BMW_SB_BLOCKS	32u			/* blocks per superblock */
+#define BMW_CH_SB	BMW_THREADS		/* superblocks per chunk */
+#define BMW_CH_BLOCKS	(BMW_CH_SB * BMW_SB_BLOCKS)	/* ub[] in shared memory */
 #define BMW_CAND	1024u			/* candidate keys per item */
 #define BMW_SEL		512u			/* blocks selected per round */
 #define BMW_K_MAX	128u			/* limit served by this kernel */
 #define BMW_HIST	64u
-#define BMW_SEED_BLOCKS	BMW_WARPS		/* first round without a threshold */
-#define BMW_ROUND_BLOCKS 64u			/* later partial rounds */
+#define BMW_ROUND_BLOCKS 64u			/* blocks of a partial round */
+#define BMW_SEED_MAX	4u			/* blocks a warp scores for a seed */
 #define BMW_BCOL_NONE	0xffffffffu
 #define BMW_SHIFT_MIN	5
 #define BMW_SHIFT_MAX	8
@@ -57,15 +64,34 @@
 
 static_assert((BMW_CH_BLOCKS << BMW_SHIFT_MIN) % TILE_DOCS == 0, "chunks start at tile boundaries");
 static_assert(BMW_K_MAX + (1u << BMW_SHIFT_MAX) <= BMW_CAND, "a block always fits after a cut");
+static_assert(BMW_SHIFT_MIN + 5 >= MT_SHIFT, "a superblock is whole mini-tiles");
+
+/*
+ * -DBMW_PROF: cycles thread 0 of every CTA spends per phase, summed into
+ * stats[4..]: bounds, short-list bounds, select, score, cut, emit + merge,
+ * item setup, seed.
+ */
+#ifdef BMW_PROF
+#define BPROF_DECL	long long bp_t = clock64(); unsigned long long bp_acc[8] = { 0 }
+#define BPROF(i)	do { if (tid == 0) { const long long _t = clock64(); bp_acc[i] += _t - bp_t; bp_t = _t; } } while (0)
+#define BPROF_FLUSH()	do { if (tid == 0 && p.stats) for (int _i = 0; _i < 8; _i++) \
+	if (bp_acc[_i]) atomicAdd(p.stats + 4 + _i, bp_acc[_i]); } while (0)
+#else
+#define BPROF_DECL	do { } while (0)
+#define BPROF(i)	do { } while (0)
+#define BPROF_FLUSH()	do { } while (0)
+#endif
 
 struct BmwParams {
 	const uint2 *		post;
 	const DTok *		toks;
 	const QDesc *		queries;
 	const uint32_t *	qlist;
-	uint32_t		n_q, nchunks, nblocks, n_docs, ntiles, k;
+	uint32_t		n_q, nchunks, nblocks, nsb, n_docs, ntiles, k;
+	uint32_t		n_seed;		/* seed items ahead of the (query, chunk) items */
 	const uint32_t *	boff;		/* [n_bcol][nblocks + 1] */
-	const float *		bmax;		/* [n_bcol][nblocks], the batch's algorithm */
+	const float *		bmax;		/* [n_bcol][nsb * 32], the batch's algorithm */
+	const float *		bmax1;		/* [n_bcol][nsb] */
 	unsigned long long *	thr;		/* [n_q] */
 	uint32_t *		tile_count;	/* [n_q][nchunks] */
 	unsigned long long *	cand;		/* [n_q][nchunks][k] */
@@ -82,7 +108,7 @@ struct BmwTok {
 	float			idf;
 	uint32_t		col;
 	uint32_t		fine_shift;
-	uint32_t		pad;
+	float			best;		/* short list: its largest score anywhere */
 };
 
 template <uint32_t BSHIFT>
@@ -91,7 +117,7 @@ struct BmwCfg {
 	static constexpr uint32_t NP = BS / 32;
 	static constexpr size_t SMEM = BMW_CH_BLOCKS * 4 + BMW_CAND * 8 + BMW_K_MAX * 8 +
 	    BMW_WARPS * BS * 4 + BMW_SEL * 2 + LOGTAB_N * 4 +
-	    NXSB_MAX_QUERY_TOKENS * sizeof(BmwTok);
+	    NXSB_MAX_QUERY_TOKENS * sizeof(BmwTok) + BMW_CH_SB * 2;
 };
 
 /* ---- image side: block offsets and block maxima of the column terms ---- */
@@ -145,6 +171,7 @@ block_max_kernel(const uint2 *__restrict__ post,
 	__shared__ float s_logtab[LOGTAB_N];
 	const uint32_t t = col_terms[blockIdx.y];
 	const unsigned long long s = term_off[t], e = term_off[t + 1];
+	/* Rows are padded to whole superblocks (nblocks here = the row stride). */
 	uint32_t *o_bm = reinterpret_cast<uint32_t *>(bmax_bm25) + (size_t)blockIdx.y * nblocks;
 	uint32_t *o_tf = reinterpret_cast<uint32_t *>(bmax_tfidf) + (size_t)blockIdx.y * nblocks;
 
@@ -191,6 +218,78 @@ block_max_kernel(const uint2 *__restrict__ post,
 	}
 }
 
+/* Superblock maxima: bmax1[c][sb] = max of the 32 block maxima (a warp per superblock). */
+__global__ void __launch_bounds__(256)
+superblock_max_kernel(const float *__restrict__ bmax_a, const float *__restrict__ bmax_b,
+    unsigned long long n_sb_total, float *__restrict__ out_a, float *__restrict__ out_b)
+{
+	const uint32_t lane = threadIdx.x & 31;
+	unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+
+	for (; w < n_sb_total; w += nw) {
+		float a = bmax_a[w * 32 + lane], b = bmax_b[w * 32 + lane];
+
+		for (int o = 16; o; o >>= 1) {
+			a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+			b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+		}
+		if (lane == 0) {
+			out_a[w] = a;
+			out_b[w] = b;
+		}
+	}
+}
+
+/*
+ * wmax_*[t] = the largest weight of any posting of term t, for the terms
+ * without block arrays (a warp per term; those lists are short).
+ */
+__global__ void __launch_bounds__(256)
+term_wmax_kernel(const uint2 *__restrict__ post,
+    const unsigned long long *__restrict__ term_off, const uint32_t *__restrict__ bcol,
+    uint32_t n_terms, const float *__restrict__ logtab, float K0, float K1,
+    float *__restrict__ wmax_bm25, float *__restrict__ wmax_tfidf)
+{
+	__shared__ float s_logtab[LOGTAB_N];
+	const uint32_t lane = threadIdx.x & 31;
+	const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+
+	for (uint32_t i = threadIdx.x; i < LOGTAB_N; i += blockDim.x)
+		s_logtab[i] = logtab[i];
+	__syncthreads();
+
+	StreamParams sp;
+	sp.K0 = K0;
+	sp.K1 = K1;
+	sp.doc_len = nullptr;
+	for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_terms; t += nw) {
+		float mb = 0.f, mt = 0.f;
+
+		if (bcol[t] == BMW_BCOL_NONE) {
+			const unsigned long long s = term_off[t], e = term_off[t + 1];
+
+			for (unsigned long long i = s + lane; i < e; i += 32) {
+				const uint2 v[1] = { post[i] };
+				float wb[1], wt[1];
+
+				st_score<false, NXSB_ALGO_BM25, 1>(sp, s_logtab, v, 1.f, wb);
+				st_score<false, NXSB_ALGO_TFIDF, 1>(sp, s_logtab, v, 1.f, wt);
+				mb = fmaxf(mb, wb[0]);
+				mt = fmaxf(mt, wt[0]);
+			}
+			for (int o = 16; o; o >>= 1) {
+				mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+				mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+			}
+		}
+		if (lane == 0) {
+			wmax_bm25[t] = mb;
+			wmax_tfidf[t] = mt;
+		}
+	}
+}
+
 /* ---- the scorer --------------------------------------------------------- */
 
 template <int ALGO, uint32_t BSHIFT>
@@ -199,6 +298,8 @@ score_bmw_kernel(const BmwParams p)
 {
 	using Cfg = BmwCfg<BSHIFT>;
 	constexpr uint32_t BS = Cfg::BS, NP = Cfg::NP;
+	constexpr uint32_t SBSHIFT = BSHIFT + 5;	/* log2 documents per superblock */
+	constexpr uint32_t FULL = 0xffffffffu;
 
 	extern __shared__ __align__(16) unsigned char smem_bmw[];
 	float *ub = reinterpret_cast<float *>(smem_bmw);
@@ -208,14 +309,18 @@ score_bmw_kernel(const BmwParams p)
 	BmwTok *s_tok = reinterpret_cast<BmwTok *>(s_acc + BMW_WARPS * BS);
 	float *s_logtab = reinterpret_cast<float *>(s_tok + NXSB_MAX_QUERY_TOKENS);
 	uint16_t *s_sel = reinterpret_cast<uint16_t *>(s_logtab + LOGTAB_N);
+	uint16_t *s_alive = s_sel + BMW_SEL;				/* [CH_SB] live superblocks */
 
-	__shared__ uint32_t s_item, s_nsel, s_selw, s_next, s_ncand, s_overflow, s_umax, s_cut;
+	__shared__ uint32_t s_item, s_nsel, s_selw, s_next, s_ncand, s_overflow, s_umax, s_cut, s_nalive;
 	__shared__ uint32_t s_hist[BMW_HIST];
-	__shared__ unsigned long long s_theta;
+	__shared__ unsigned long long s_theta, s_kth;
+	__shared__ uint8_t s_live1[BMW_CH_SB];
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t n_items = p.n_q * p.nchunks;
+	const uint32_t n_items = p.n_seed + p.n_q * p.nchunks;
 	const uint32_t k = p.k;
+	const uint32_t row_stride = p.nsb * BMW_SB_BLOCKS;	/* bmax rows are whole superblocks */
+	float *wacc = s_acc + warp * BS;
 	unsigned long long st_blocks = 0, st_post = 0, st_rounds = 0, st_items = 0;
 
 	for (uint32_t i = tid; i < LOGTAB_N; i += BMW_THREADS)
@@ -226,27 +331,34 @@ score_bmw_kernel(const BmwParams p)
 	sp.K1 = p.K1;
 	sp.doc_len = nullptr;
 
+	BPROF_DECL;
 	for (;;) {
 		__syncthreads();
+		BPROF(5);
 		if (tid == 0) {
 			s_item = atomicAdd(p.work_counter, 1u);
 			s_ncand = 0;
+			s_nalive = 0;
+			s_overflow = 0;
 		}
 		__syncthreads();
 		const uint32_t item = s_item;
 
 		if (item >= n_items)
 			break;
-		const uint32_t chunk = p.nchunks - 1 - item / p.n_q;
-		const uint32_t slot = item % p.n_q;
+		const bool seed_item = item < p.n_seed;
+		const uint32_t it = seed_item ? 0u : item - p.n_seed;
+		const uint32_t chunk = seed_item ? 0u : p.nchunks - 1 - it / p.n_q;
+		const uint32_t slot = seed_item ? item : it % p.n_q;
 		const QDesc qd = p.queries[p.qlist[slot]];
 		const uint32_t ntok = qd.n_tokens;
 		const uint32_t cb0 = chunk * BMW_CH_BLOCKS;
-		const uint32_t nb = min(BMW_CH_BLOCKS, p.nblocks - cb0);
 		const uint32_t doc0 = cb0 << BSHIFT;
+		const uint32_t sb_lo = chunk * BMW_CH_SB;
+		const uint32_t sb_hi = min(p.nsb, sb_lo + BMW_CH_SB);
 		const uint32_t tile0 = doc0 >> TILE_SHIFT;
 		const uint32_t tile1 = min(p.ntiles,
-		    (uint32_t)((((unsigned long long)(cb0 + nb) << BSHIFT) + TILE_DOCS - 1) >> TILE_SHIFT));
+		    (uint32_t)((((unsigned long long)sb_hi << SBSHIFT) + TILE_DOCS - 1) >> TILE_SHIFT));
 
 		if (tid < ntok) {
 			const DTok t = p.toks[qd.tok_off + tid];
@@ -259,7 +371,7 @@ score_bmw_kernel(const BmwParams p)
 			bt.col = t.bcol;
 			bt.fine = t.fine;
 			bt.fine_shift = t.fine_shift;
-			bt.pad = 0;
+			bt.best = __fmul_rn(t.wmax, t.idf);
 			s_tok[tid] = bt;
 		}
 		if (tid == 0)
@@ -268,47 +380,397 @@ score_bmw_kernel(const BmwParams p)
 		if (tid == 0)
 			st_items++;
 
-		/* ---- 1. upper bounds ---- */
 		bool any_list = false;
 		for (uint32_t j = 0; j < ntok; j++)
 			any_list |= s_tok[j].col == BMW_BCOL_NONE;
-		{
-			constexpr uint32_t U = 4;
+		/*
+		 * A block's bound is summed columns first, short lists after:
+		 * another order than the token list's, which can round a few ulp
+		 * lower once three or more terms are involved.  2^-16 covers 32.
+		 */
+		const float infl = (any_list && ntok >= 3) ? 1.0000152587890625f : 1.f;
 
-			for (uint32_t b0 = tid; b0 < nb; b0 += U * BMW_THREADS) {
-				float u[U];
+		/* Token j's postings that may lie in superblock sb: [lo, hi). */
+		auto sb_slice = [&](const BmwTok &bt, uint32_t sb, uint32_t &lo, uint32_t &hi) {
+			uint32_t i0, i1;
 
-#pragma unroll
-				for (uint32_t x = 0; x < U; x++)
-					u[x] = 0.f;
-				for (uint32_t j = 0; j < ntok; j++) {
-					const BmwTok &bt = s_tok[j];
+			if (bt.fine_shift <= SBSHIFT) {
+				i0 = sb << (SBSHIFT - bt.fine_shift);
+				i1 = (sb + 1) << (SBSHIFT - bt.fine_shift);
+				i1 = min(i1, (p.n_docs + (1u << bt.fine_shift) - 1) >> bt.fine_shift);
+			} else {
+				i0 = (sb << SBSHIFT) >> bt.fine_shift;
+				i1 = i0 + 1;
+			}
+			lo = __ldg(bt.fine + i0);
+			hi = __ldg(bt.fine + i1);
+		};
+		/* Bound of a superblock, summed in token order (no slack needed). */
+		auto coarse = [&](uint32_t sb) -> float {
+			float u = 0.f;
 
-					if (bt.col == BMW_BCOL_NONE)
-						continue;
-					const float *row = p.bmax + (size_t)bt.col * p.nblocks + cb0;
-					float m[U];
+			for (uint32_t j = 0; j < ntok; j++) {
+				const BmwTok &bt = s_tok[j];
 
-#pragma unroll
-					for (uint32_t x = 0; x < U; x++) {
-						const uint32_t b = b0 + x * BMW_THREADS;
+				if (bt.col != BMW_BCOL_NONE) {
+					u = __fadd_rn(u, __fmul_rn(__ldg(p.bmax1 + (size_t)bt.col * p.nsb + sb), bt.idf));
+				} else {
+					uint32_t lo, hi;
 
-						m[x] = b < nb ? __ldg(row + b) : 0.f;
-					}
-#pragma unroll
-					for (uint32_t x = 0; x < U; x++)
-						u[x] = __fadd_rn(u[x], __fmul_rn(m[x], bt.idf));
-				}
-#pragma unroll
-				for (uint32_t x = 0; x < U; x++) {
-					const uint32_t b = b0 + x * BMW_THREADS;
-
-					if (b < nb)
-						ub[b] = u[x];
+					sb_slice(bt, sb, lo, hi);
+					if (hi > lo)
+						u = __fadd_rn(u, bt.best);
 				}
 			}
+			return u;
+		};
+		/* Column part of a block's bound, token order. */
+		auto fine_cols = [&](uint32_t gb) -> float {
+			float u = 0.f;
+
+			for (uint32_t j = 0; j < ntok; j++) {
+				const BmwTok &bt = s_tok[j];
+
+				if (bt.col != BMW_BCOL_NONE)
+					u = __fadd_rn(u, __fmul_rn(__ldg(p.bmax + (size_t)bt.col * row_stride + gb), bt.idf));
+			}
+			return u;
+		};
+
+		/*
+		 * A warp scores block gb: every token's slice of the block, token
+		 * order, into wacc; sums beating the threshold key join s_cand.
+		 * False: the candidate buffer is full, nothing was recorded.
+		 */
+		auto score_block = [&](uint32_t gb) -> bool {
+			const uint32_t base = gb << BSHIFT;
+
+#pragma unroll
+			for (uint32_t r = 0; r < NP; r++)
+				wacc[lane + 32 * r] = 0.f;
+			/* Lane j finds token j's slice of the block. */
+			uint32_t my_lo = 0, my_hi = 0;
+			if (lane < ntok) {
+				const BmwTok &bt = s_tok[lane];
+
+				if (bt.col != BMW_BCOL_NONE) {
+					const uint32_t *row = p.boff + (size_t)bt.col * (p.nblocks + 1) + gb;
+
+					my_lo = __ldg(row);
+					my_hi = __ldg(row + 1);
+				} else {
+					/*
+					 * A short list: the slice of the block's mini-tile
+					 * (or tile) is a handful of postings; the warp
+					 * loads all of it and keeps the block's.  Longer
+					 * than the warp's registers: narrow it first.
+					 */
+					const uint32_t idx = base >> bt.fine_shift;
+
+					my_lo = __ldg(bt.fine + idx);
+					my_hi = __ldg(bt.fine + idx + 1);
+					if (my_hi - my_lo > 32 * NP) {
+						const uint2 *list = p.post + bt.post_off;
+						uint32_t l = my_lo, h = my_hi;
+
+						while (l < h) {
+							const uint32_t mid = (l + h) >> 1;
+
+							if (__ldg(list + mid).x < base)
+								l = mid + 1;
+							else
+								h = mid;
+						}
+						my_lo = l;
+						h = min(my_hi, l + BS);
+						while (l < h) {
+							const uint32_t mid = (l + h) >> 1;
+
+							if (__ldg(list + mid).x < base + BS)
+								l = mid + 1;
+							else
+								h = mid;
+						}
+						my_hi = l;
+					}
+				}
+			}
+			__syncwarp();
+			for (uint32_t j0 = 0; j0 < ntok; j0 += BMW_TOK_GROUP) {
+				uint2 v[BMW_TOK_GROUP][NP];
+
+				/* Every load of the group is in flight before the first sum. */
+#pragma unroll
+				for (uint32_t g = 0; g < BMW_TOK_GROUP; g++) {
+					const uint32_t j = j0 + g;
+					const uint32_t lo_j = __shfl_sync(FULL, my_lo, j & 31u);
+					const uint32_t hi_j = __shfl_sync(FULL, my_hi, j & 31u);
+
+#pragma unroll
+					for (uint32_t r = 0; r < NP; r++) {
+						const uint32_t i = lo_j + lane + 32 * r;
+
+						v[g][r] = make_uint2(base, 0u);
+						if (j < ntok && i < hi_j)
+							v[g][r] = __ldg(p.post + s_tok[j].post_off + i);
+						/* A short list's slice may reach past the block. */
+						if (v[g][r].x - base >= BS)
+							v[g][r] = make_uint2(base, 0u);
+					}
+				}
+#pragma unroll
+				for (uint32_t g = 0; g < BMW_TOK_GROUP; g++) {
+					const uint32_t j = j0 + g;
+
+					if (j >= ntok)
+						break;
+					float sc[NP];
+
+					st_score<false, ALGO, NP>(sp, s_logtab, v[g], s_tok[j].idf, sc);
+#pragma unroll
+					for (uint32_t r = 0; r < NP; r++) {
+						if (v[g][r].y != 0u) {
+							float *a = wacc + (v[g][r].x - base);
+
+							*a = __fadd_rn(*a, sc[r]);
+							st_post++;
+						}
+					}
+					__syncwarp();
+				}
+			}
+			/* Candidates: sums that beat the current threshold key. */
+			const unsigned long long th = *(volatile unsigned long long *)&s_theta;
+			unsigned long long keys[NP];
+			uint32_t mine = 0;
+
+#pragma unroll
+			for (uint32_t r = 0; r < NP; r++) {
+				const float val = wacc[lane + 32 * r];
+
+				keys[r] = make_key(val, base + lane + 32 * r);
+				if (val == 0.f || keys[r] <= th)
+					keys[r] = 0;
+				mine += keys[r] != 0;
+			}
+			/* inclusive prefix over the lanes */
+			uint32_t incl = mine;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const uint32_t x = __shfl_up_sync(FULL, incl, o);
+
+				if ((int)lane >= o)
+					incl += x;
+			}
+			const uint32_t total = __shfl_sync(FULL, incl, 31);
+			uint32_t at = 0;
+
+			if (total) {
+				if (lane == 0) {
+					at = atomicAdd(&s_ncand, total);
+					if (at + total > BMW_CAND) {
+						atomicSub(&s_ncand, total);
+						s_overflow = 1;
+						at = 0xffffffffu;
+					}
+				}
+				at = __shfl_sync(FULL, at, 0);
+				if (at == 0xffffffffu)
+					return false;
+				uint32_t w = at + incl - mine;
+
+#pragma unroll
+				for (uint32_t r = 0; r < NP; r++)
+					if (keys[r])
+						s_cand[w++] = keys[r];
+			}
+			if (lane == 0)
+				st_blocks++;
+			__syncwarp();
+			return true;
+		};
+
+		/*
+		 * Cut s_cand back to its k best (if it holds that many); the k-th
+		 * key lands in s_kth (else 0).  Block-wide, ends on a barrier.
+		 */
+		auto cut = [&]() {
+			const uint32_t nc = s_ncand;
+
+			if (tid == 0)
+				s_kth = 0;
+			if (nc >= k) {
+				for (uint32_t i = tid; i < nc; i += BMW_THREADS) {
+					const unsigned long long key = s_cand[i];
+					uint32_t rank = 0;
+
+					for (uint32_t j = 0; j < nc; j++)
+						rank += s_cand[j] > key;
+					if (rank < k)
+						s_top[rank] = key;
+				}
+				__syncthreads();
+				for (uint32_t i = tid; i < k; i += BMW_THREADS)
+					s_cand[i] = s_top[i];
+				if (tid == 0) {
+					s_ncand = k;
+					s_kth = s_top[k - 1];
+				}
+			}
+			__syncthreads();
+		};
+
+		/*
+		 * Seed: score the best block of the best superblocks of
+		 * [lo, hi) -- a few per warp -- and take the k-th best key seen,
+		 * less one (the documents themselves are scored again by the item
+		 * that owns them and must pass `key > threshold` there).
+		 */
+		auto seed = [&](uint32_t lo, uint32_t hi) {
+			float bu = 0.f;
+			uint32_t bsb = 0;
+
+			for (uint32_t sb = lo + tid; sb < hi; sb += BMW_THREADS) {
+				const float u1 = coarse(sb);
+
+				if (u1 > bu) {
+					bu = u1;
+					bsb = sb;
+				}
+			}
+			const uint32_t rounds = min(BMW_SEED_MAX, (k + BMW_WARPS - 1) / BMW_WARPS + 1);
+
+			for (uint32_t r = 0; r < rounds; r++) {
+				float m = bu;
+				uint32_t ml = lane;
+
+				for (int o = 16; o; o >>= 1) {
+					const float om = __shfl_xor_sync(FULL, m, o);
+					const uint32_t ol = __shfl_xor_sync(FULL, ml, o);
+
+					if (om > m || (om == m && ol < ml)) {
+						m = om;
+						ml = ol;
+					}
+				}
+				if (m == 0.f || *(volatile uint32_t *)&s_overflow)
+					break;
+				const uint32_t wsb = __shfl_sync(FULL, bsb, ml);
+
+				if (lane == ml)
+					bu = 0.f;
+				/* lane = block of the superblock */
+				const uint32_t gb = wsb * BMW_SB_BLOCKS + lane;
+				float u = fine_cols(gb);
+
+				for (uint32_t j = 0; j < ntok; j++) {
+					const BmwTok bt = s_tok[j];
+
+					if (bt.col != BMW_BCOL_NONE)
+						continue;
+					uint32_t slo, shi;
+					uint32_t *wmax = reinterpret_cast<uint32_t *>(wacc);
+
+					sb_slice(bt, wsb, slo, shi);
+					wmax[lane] = 0u;
+					__syncwarp();
+					for (uint32_t i = slo + lane; i < shi; i += 32) {
+						const uint2 v[1] = { __ldg(p.post + bt.post_off + i) };
+
+						if ((v[0].x >> SBSHIFT) == wsb) {
+							float sc[1];
+
+							st_score<false, ALGO, 1>(sp, s_logtab, v, bt.idf, sc);
+							atomicMax(wmax + ((v[0].x >> BSHIFT) & 31u), __float_as_uint(sc[0]));
+						}
+					}
+					__syncwarp();
+					u = __fadd_rn(u, __uint_as_float(wmax[lane]));
+					__syncwarp();
+				}
+				/* the warp's best block */
+				float fm = gb < p.nblocks ? u : 0.f;
+				uint32_t fl = lane;
+
+				for (int o = 16; o; o >>= 1) {
+					const float om = __shfl_xor_sync(FULL, fm, o);
+					const uint32_t ol = __shfl_xor_sync(FULL, fl, o);
+
+					if (om > fm || (om == fm && ol < fl)) {
+						fm = om;
+						fl = ol;
+					}
+				}
+				if (fm != 0.f)
+					score_block(wsb * BMW_SB_BLOCKS + fl);
+			}
+			__syncthreads();
+			cut();
+			if (tid == 0) {
+				const unsigned long long kth = s_kth;
+
+				if (kth > 1 && kth - 1 > s_theta) {
+					s_theta = kth - 1;
+					atomicMax(p.thr + slot, kth - 1);
+				}
+				s_ncand = 0;		/* nothing is kept */
+				s_overflow = 0;
+			}
+			__syncthreads();
+		};
+
+		BPROF(6);
+		if (seed_item) {
+			if (s_theta == 0)
+				seed(0, p.nsb);
+			BPROF(7);
+			continue;
 		}
+		if (s_theta == 0) {
+			/* No seed reached this item (a lone query, a late seed): a local one. */
+			if (tid == 0)
+				s_overflow = 0;
+			__syncthreads();
+			seed(sb_lo, sb_hi);
+			BPROF(7);
+		}
+
+		/* ---- A. superblocks ---- */
+		{
+			const unsigned long long theta = s_theta;
+			const uint32_t sb = sb_lo + tid;
+			const float u1 = sb < sb_hi ? coarse(sb) : 0.f;
+			const bool a1 = u1 != 0.f && make_key(u1, ((sb + 1u) << SBSHIFT) - 1u) > theta;
+			const uint32_t m = __ballot_sync(FULL, a1);
+			uint32_t at = 0;
+
+			s_live1[tid] = a1;
+			if (m) {
+				if (lane == 0)
+					at = atomicAdd(&s_nalive, __popc(m));
+				at = __shfl_sync(FULL, at, 0);
+				if (a1)
+					s_alive[at + __popc(m & ((1u << lane) - 1u))] = (uint16_t)tid;
+			}
+		}
+		__syncthreads();
+		const uint32_t nfine = s_nalive * BMW_SB_BLOCKS;
+
+#ifdef BMW_PROF
+		if (tid == 0 && p.stats) {
+			atomicAdd(p.stats + 12, (unsigned long long)s_nalive);
+			if (nfine == 0)
+				atomicAdd(p.stats + 13, 1ull);
+		}
+#endif
+		BPROF(0);
+		if (nfine == 0)
+			continue;
+
+		/* ---- B. blocks of the live superblocks ---- */
 		if (any_list) {
+			for (uint32_t idx = tid; idx < nfine; idx += BMW_THREADS)
+				ub[s_alive[idx >> 5] * BMW_SB_BLOCKS + (idx & 31u)] = 0.f;
 			__syncthreads();
 			for (uint32_t j = 0; j < ntok; j++) {
 				const BmwTok bt = s_tok[j];
@@ -317,12 +779,19 @@ score_bmw_kernel(const BmwParams p)
 					continue;
 				const uint2 *list = p.post + bt.post_off;
 
-				for (uint32_t i = bt.clo + tid; i < bt.chi; i += BMW_THREADS) {
-					uint2 v[1] = { __ldg(list + i) };
+				for (uint32_t i0 = bt.clo; i0 < bt.chi; i0 += BMW_THREADS) {
+					const uint32_t i = i0 + tid;
+					const bool valid = i < bt.chi;
+					uint2 v[1] = { valid ? __ldg(list + i) : make_uint2(0xffffffffu, 0u) };
+					uint32_t xp = __shfl_up_sync(FULL, v[0].x, 1);
+
+					if (lane == 0)
+						xp = (valid && i > bt.clo) ? __ldg(list + i - 1).x : 0xffffffffu;
 					const uint32_t b = (v[0].x - doc0) >> BSHIFT;
 
 					/* The head of a block's run folds the run. */
-					if (i != bt.clo && ((__ldg(list + i - 1).x - doc0) >> BSHIFT) == b)
+					if (!valid || (i != bt.clo && ((xp - doc0) >> BSHIFT) == b) ||
+					    !s_live1[b >> 5])
 						continue;
 					float sc[1], m;
 
@@ -338,15 +807,20 @@ score_bmw_kernel(const BmwParams p)
 					atomicAdd(ub + b, m);
 				}
 			}
+			__syncthreads();
+			BPROF(1);
 		}
-		/*
-		 * The bound was summed columns first, short lists after: another
-		 * order than the token list's, which can round a few ulp lower once
-		 * three or more terms are involved.  2^-16 covers 32 terms.
-		 */
-		const float infl = (any_list && ntok >= 3) ? 1.0000152587890625f : 1.f;
+		for (uint32_t idx = tid; idx < nfine; idx += BMW_THREADS) {
+			const uint32_t b = s_alive[idx >> 5] * BMW_SB_BLOCKS + (idx & 31u);
+			float u = fine_cols(cb0 + b);
 
-		/* ---- 2./3. rounds: select, score, cut ---- */
+			if (any_list)
+				u = __fadd_rn(u, ub[b]);
+			ub[b] = u;
+		}
+		BPROF(0);
+
+		/* ---- C. rounds: select, score, cut ---- */
 		for (;;) {
 			__syncthreads();
 			if (tid == 0) {
@@ -366,7 +840,8 @@ score_bmw_kernel(const BmwParams p)
 			auto alive = [&](uint32_t b, float u) -> bool {
 				return u != 0.f && make_key(u, ((cb0 + b + 1u) << BSHIFT) - 1u) > theta;
 			};
-			for (uint32_t b = tid; b < nb; b += BMW_THREADS) {
+			for (uint32_t idx = tid; idx < nfine; idx += BMW_THREADS) {
+				const uint32_t b = s_alive[idx >> 5] * BMW_SB_BLOCKS + (idx & 31u);
 				const float u = __fmul_ru(ub[b], infl);
 
 				if (alive(b, u)) {
@@ -374,8 +849,8 @@ score_bmw_kernel(const BmwParams p)
 					mxb = max(mxb, __float_as_uint(u));
 				}
 			}
-			cnt = __reduce_add_sync(0xffffffffu, cnt);
-			mxb = __reduce_max_sync(0xffffffffu, mxb);
+			cnt = __reduce_add_sync(FULL, cnt);
+			mxb = __reduce_max_sync(FULL, mxb);
 			if (lane == 0 && cnt) {
 				atomicAdd(&s_nsel, cnt);
 				atomicMax(&s_umax, mxb);
@@ -383,11 +858,14 @@ score_bmw_kernel(const BmwParams p)
 			__syncthreads();
 			const uint32_t nsel = s_nsel;
 
+#ifdef BMW_PROF
+			if (tid == 0 && p.stats)
+				atomicAdd(p.stats + 14, (unsigned long long)nsel);
+#endif
 			if (nsel == 0)
 				break;
 			/* Everything alive, or only the blocks with the highest bounds? */
-			const uint32_t target = theta == 0 ? BMW_SEED_BLOCKS : BMW_ROUND_BLOCKS;
-			const bool subset = nsel > (theta == 0 ? BMW_SEED_BLOCKS : BMW_SEL / 2);
+			const bool subset = nsel > BMW_SEL / 2;
 			const float lo = __uint_as_float((uint32_t)(theta >> 32));
 			const float hi = __uint_as_float(s_umax);
 			const float scale = subset && hi > lo ? (float)BMW_HIST / (hi - lo) : 0.f;
@@ -398,11 +876,20 @@ score_bmw_kernel(const BmwParams p)
 			};
 
 			if (subset) {
-				for (uint32_t b = tid; b < nb; b += BMW_THREADS) {
+				for (uint32_t idx = tid; idx < nfine; idx += BMW_THREADS) {
+					const uint32_t b = s_alive[idx >> 5] * BMW_SB_BLOCKS + (idx & 31u);
 					const float u = __fmul_ru(ub[b], infl);
+					const bool a = alive(b, u);
+					const uint32_t am = __ballot_sync(FULL, a);
 
-					if (alive(b, u))
-						atomicAdd(&s_hist[bin_of(u)], 1u);
+					if (a) {
+						/* one atomic per distinct bin of the warp */
+						const uint32_t bin = bin_of(u);
+						const uint32_t same = __match_any_sync(am, bin);
+
+						if (lane == (uint32_t)__ffs(same) - 1u)
+							atomicAdd(&s_hist[bin], __popc(same));
+					}
 				}
 				__syncthreads();
 				if (tid == 0) {
@@ -411,22 +898,28 @@ score_bmw_kernel(const BmwParams p)
 
 					for (; bin > 0; bin--) {
 						cum += s_hist[bin];
-						if (cum >= target)
+						if (cum >= BMW_ROUND_BLOCKS)
 							break;
 					}
 					s_cut = (uint32_t)bin;
 				}
 				__syncthreads();
 			}
-			const uint32_t cut = subset ? s_cut : 0u;
+			const uint32_t cutbin = subset ? s_cut : 0u;
 
-			for (uint32_t b = tid; b < nb; b += BMW_THREADS) {
+			for (uint32_t idx = tid; idx < nfine; idx += BMW_THREADS) {
+				const uint32_t b = s_alive[idx >> 5] * BMW_SB_BLOCKS + (idx & 31u);
 				const float u = __fmul_ru(ub[b], infl);
+				const bool take = alive(b, u) && (!subset || bin_of(u) >= cutbin);
+				const uint32_t tm = __ballot_sync(FULL, take);
 
-				if (alive(b, u) && (!subset || bin_of(u) >= cut)) {
-					const uint32_t at = atomicAdd(&s_selw, 1u);
+				if (tm) {
+					uint32_t at = 0;
 
-					if (at < BMW_SEL)
+					if (lane == 0)
+						at = atomicAdd(&s_selw, __popc(tm));
+					at = __shfl_sync(FULL, at, 0) + __popc(tm & ((1u << lane) - 1u));
+					if (take && at < BMW_SEL)
 						s_sel[at] = (uint16_t)b;
 				}
 			}
@@ -437,202 +930,42 @@ score_bmw_kernel(const BmwParams p)
 
 			if (tid == 0)
 				st_rounds++;
+			BPROF(2);
 
 			/* ---- score the selected blocks, one per warp at a time ---- */
-			float *wacc = s_acc + warp * BS;
-
 			for (;;) {
 				uint32_t si = 0;
 
 				if (lane == 0)
 					si = *(volatile uint32_t *)&s_overflow ? n_round : atomicAdd(&s_next, 1u);
-				si = __shfl_sync(0xffffffffu, si, 0);
+				si = __shfl_sync(FULL, si, 0);
 				if (si >= n_round)
 					break;
 				const uint32_t b = s_sel[si];
-				const uint32_t gb = cb0 + b;
-				const uint32_t base = gb << BSHIFT;
 
-#pragma unroll
-				for (uint32_t r = 0; r < NP; r++)
-					wacc[lane + 32 * r] = 0.f;
-				/* Lane j finds token j's slice of the block. */
-				uint32_t my_lo = 0, my_hi = 0;
-				if (lane < ntok) {
-					const BmwTok &bt = s_tok[lane];
-
-					if (bt.col != BMW_BCOL_NONE) {
-						const uint32_t *row = p.boff + (size_t)bt.col * (p.nblocks + 1) + gb;
-
-						my_lo = __ldg(row);
-						my_hi = __ldg(row + 1);
-					} else {
-						/*
-						 * A short list: the slice of the block's mini-tile
-						 * (or tile) is a handful of postings; the warp
-						 * loads all of it and keeps the block's.  Longer
-						 * than the warp's registers: narrow it first.
-						 */
-						const uint32_t idx = base >> bt.fine_shift;
-
-						my_lo = __ldg(bt.fine + idx);
-						my_hi = __ldg(bt.fine + idx + 1);
-						if (my_hi - my_lo > 32 * NP) {
-							const uint2 *list = p.post + bt.post_off;
-							uint32_t l = my_lo, h = my_hi;
-
-							while (l < h) {
-								const uint32_t mid = (l + h) >> 1;
-
-								if (__ldg(list + mid).x < base)
-									l = mid + 1;
-								else
-									h = mid;
-							}
-							my_lo = l;
-							h = min(my_hi, l + BS);
-							while (l < h) {
-								const uint32_t mid = (l + h) >> 1;
-
-								if (__ldg(list + mid).x < base + BS)
-									l = mid + 1;
-								else
-									h = mid;
-							}
-							my_hi = l;
-						}
-					}
-				}
-				__syncwarp();
-				for (uint32_t j0 = 0; j0 < ntok; j0 += BMW_TOK_GROUP) {
-					uint2 v[BMW_TOK_GROUP][NP];
-
-					/* Every load of the group is in flight before the first sum. */
-#pragma unroll
-					for (uint32_t g = 0; g < BMW_TOK_GROUP; g++) {
-						const uint32_t j = j0 + g;
-						const uint32_t lo_j = __shfl_sync(0xffffffffu, my_lo, j & 31u);
-						const uint32_t hi_j = __shfl_sync(0xffffffffu, my_hi, j & 31u);
-
-#pragma unroll
-						for (uint32_t r = 0; r < NP; r++) {
-							const uint32_t i = lo_j + lane + 32 * r;
-
-							v[g][r] = make_uint2(base, 0u);
-							if (j < ntok && i < hi_j)
-								v[g][r] = __ldg(p.post + s_tok[j].post_off + i);
-							/* A short list's slice may reach past the block. */
-							if (v[g][r].x - base >= BS)
-								v[g][r] = make_uint2(base, 0u);
-						}
-					}
-#pragma unroll
-					for (uint32_t g = 0; g < BMW_TOK_GROUP; g++) {
-						const uint32_t j = j0 + g;
-
-						if (j >= ntok)
-							break;
-						float sc[NP];
-
-						st_score<false, ALGO, NP>(sp, s_logtab, v[g], s_tok[j].idf, sc);
-#pragma unroll
-						for (uint32_t r = 0; r < NP; r++) {
-							if (v[g][r].y != 0u) {
-								float *a = wacc + (v[g][r].x - base);
-
-								*a = __fadd_rn(*a, sc[r]);
-								st_post++;
-							}
-						}
-						__syncwarp();
-					}
-				}
-				/* Candidates: sums that beat the current threshold key. */
-				const unsigned long long th = *(volatile unsigned long long *)&s_theta;
-				unsigned long long keys[NP];
-				uint32_t mine = 0;
-
-#pragma unroll
-				for (uint32_t r = 0; r < NP; r++) {
-					const float val = wacc[lane + 32 * r];
-
-					keys[r] = make_key(val, base + lane + 32 * r);
-					if (val == 0.f || keys[r] <= th)
-						keys[r] = 0;
-					mine += keys[r] != 0;
-				}
-				/* exclusive prefix over the lanes */
-				uint32_t incl = mine;
-#pragma unroll
-				for (int o = 1; o < 32; o <<= 1) {
-					const uint32_t x = __shfl_up_sync(0xffffffffu, incl, o);
-
-					if ((int)lane >= o)
-						incl += x;
-				}
-				const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-				uint32_t at = 0;
-				bool fits = true;
-
-				if (total) {
-					if (lane == 0) {
-						at = atomicAdd(&s_ncand, total);
-						if (at + total > BMW_CAND) {
-							atomicSub(&s_ncand, total);
-							s_overflow = 1;
-							at = 0xffffffffu;
-						}
-					}
-					at = __shfl_sync(0xffffffffu, at, 0);
-					fits = at != 0xffffffffu;
-					if (fits) {
-						uint32_t w = at + incl - mine;
-
-#pragma unroll
-						for (uint32_t r = 0; r < NP; r++)
-							if (keys[r])
-								s_cand[w++] = keys[r];
-					}
-				}
-				if (fits && lane == 0) {
+				if (score_block(cb0 + b) && lane == 0)
 					ub[b] = 0.f;		/* done */
-					st_blocks++;
-				}
-				__syncwarp();
 			}
 			__syncthreads();
+			BPROF(3);
 
 			/* ---- cut the candidates back to the k best ---- */
-			const uint32_t nc = s_ncand;
+			cut();
+			if (tid == 0) {
+				const unsigned long long kth = s_kth;
 
-			if (nc >= k) {
-				for (uint32_t i = tid; i < nc; i += BMW_THREADS) {
-					const unsigned long long key = s_cand[i];
-					uint32_t rank = 0;
-
-					for (uint32_t j = 0; j < nc; j++)
-						rank += s_cand[j] > key;
-					if (rank < k)
-						s_top[rank] = key;
-				}
-				__syncthreads();
-				for (uint32_t i = tid; i < k; i += BMW_THREADS)
-					s_cand[i] = s_top[i];
-				if (tid == 0) {
-					const unsigned long long kth = s_top[k - 1];
-
-					s_ncand = k;
-					if (kth > s_theta) {
-						s_theta = kth;
-						atomicMax(p.thr + slot, kth);
-					}
+				if (kth > s_theta) {
+					s_theta = kth;
+					atomicMax(p.thr + slot, kth);
 				}
 			}
+			BPROF(4);
 			if (!partial && !s_overflow)
 				break;		/* every live block was scored */
 		}
+		BPROF(2);
 
-		/* ---- the item's cell ---- */
+		/* ---- D. the item's cell ---- */
 		__syncthreads();
 		const uint32_t nc = s_ncand;		/* <= k */
 
@@ -689,6 +1022,7 @@ score_bmw_kernel(const BmwParams p)
 			}
 		}
 	}
+	BPROF_FLUSH();
 	if (p.stats && lane == 0) {
 		if (st_items)
 			atomicAdd(p.stats + 0, st_items);
@@ -698,7 +1032,8 @@ score_bmw_kernel(const BmwParams p)
 			atomicAdd(p.stats + 3, st_rounds);
 	}
 	if (p.stats) {
-		st_post = __reduce_add_sync(0xffffffffu, (unsigned)st_post);
+		for (int o = 16; o; o >>= 1)
+			st_post += __shfl_xor_sync(FULL, st_post, o);
 		if (lane == 0 && st_post)
 			atomicAdd(p.stats + 2, st_post);
 	}

@@ -63,6 +63,8 @@ struct DTok {
 	const uint32_t *	fine;
 	uint32_t		fine_shift;
 	uint32_t		bcol;		// row of its block arrays (bmw.cuh), or 0xffffffff
+	float			wmax;		// no block arrays: the list's largest weight
+	uint32_t		pad;
 };
 
 /* 16-byte result record (also the NCCL all-gather payload). */

@@ -208,11 +208,13 @@ struct nxsb_engine {
 	 * two postings per block of 2^bshift documents.
 	 */
 	bool		bmw_enabled = true;		// NXSB_BMW=0: every query streams
-	uint32_t	bshift = 6, nblocks = 0, nchunks = 0, n_bcol = 0;
+	uint32_t	bshift = 6, nblocks = 0, nsb = 0, nchunks = 0, n_bcol = 0;
 	uint32_t *	d_bcol = nullptr;		// [V] row of a term or BMW_BCOL_NONE
 	uint32_t *	d_bcol_terms = nullptr;		// [n_bcol] term index of a row
 	uint32_t *	d_boff = nullptr;		// [n_bcol][nblocks + 1]
-	float *		d_bmax_bm25 = nullptr, *d_bmax_tfidf = nullptr;	// [n_bcol][nblocks]
+	float *		d_bmax_bm25 = nullptr, *d_bmax_tfidf = nullptr;	// [n_bcol][nsb * 32]
+	float *		d_bmax1_bm25 = nullptr, *d_bmax1_tfidf = nullptr;	// [n_bcol][nsb]
+	float *		d_wmax_bm25 = nullptr, *d_wmax_tfidf = nullptr;	// [V] terms without block arrays
 	unsigned long long *d_bmw_stats = nullptr;	// [4] counters of the BMW launches
 	uint64_t	token_count = 0;
 	uint32_t	doc_count = 0;
@@ -425,21 +427,21 @@ nxsb_engine_set_pruning(nxsb_engine_t *e, int on)
 }
 
 extern "C" int
-nxsb_engine_pruning_stats(nxsb_engine_t *e, uint64_t out[4], int reset)
+nxsb_engine_pruning_stats(nxsb_engine_t *e, uint64_t out[16], int reset)
 {
-	unsigned long long v[4];
+	unsigned long long v[16];
 
 	CK(e, cudaSetDevice(e->device));
 	CK(e, cudaStreamSynchronize(e->stream));
 	CK(e, cudaMemcpy(v, e->d_bmw_stats, sizeof(v), cudaMemcpyDeviceToHost));
-	for (int i = 0; i < 4; i++)
+	for (int i = 0; i < 16; i++)
 		out[i] = v[i];
 	for (nxsb_engine *c : e->segs) {
-		uint64_t sub[4];
+		uint64_t sub[16];
 
 		if (nxsb_engine_pruning_stats(c, sub, reset) == -1)
 			return fail(e, "%s", c->err);
-		for (int i = 0; i < 4; i++)
+		for (int i = 0; i < 16; i++)
 			out[i] += sub[i];
 	}
 	if (reset)
@@ -501,8 +503,8 @@ nxsb_engine_create(int device)
 		if ((kv = getenv("NXSB_BMW_SHIFT")) != NULL)
 			e->bshift = (uint32_t)std::min(BMW_SHIFT_MAX, std::max(BMW_SHIFT_MIN, atoi(kv)));
 	}
-	if (dev_alloc(&e->d_bmw_stats, 4) != cudaSuccess ||
-	    cudaMemset(e->d_bmw_stats, 0, 32) != cudaSuccess) {
+	if (dev_alloc(&e->d_bmw_stats, 16) != cudaSuccess ||
+	    cudaMemset(e->d_bmw_stats, 0, 128) != cudaSuccess) {
 		snprintf(g_last_error, sizeof(g_last_error), "CUDA alloc failed");
 		delete e;
 		return nullptr;
@@ -544,6 +546,10 @@ free_image(nxsb_engine_t *e)
 	dev_free(e->d_boff);
 	dev_free(e->d_bmax_bm25);
 	dev_free(e->d_bmax_tfidf);
+	dev_free(e->d_bmax1_bm25);
+	dev_free(e->d_bmax1_tfidf);
+	dev_free(e->d_wmax_bm25);
+	dev_free(e->d_wmax_tfidf);
 	e->n_bcol = 0;
 	dev_free(e->d_skip);
 	dev_free(e->d_skip_mt);
@@ -700,15 +706,24 @@ upload_stats(nxsb_engine_t *e)
 	    cudaMemcpyHostToDevice, e->stream));
 	CK(e, cudaMemcpyAsync(e->d_idf_tfidf, tfidf.data(), V * sizeof(float),
 	    cudaMemcpyHostToDevice, e->stream));
-	if (e->n_bcol) {
-		/* The BM25 weight depends on K0 / K1: the block maxima follow the statistics. */
-		const size_t words = (size_t)e->n_bcol * e->nblocks;
+	if (e->d_wmax_bm25) {
+		/* The BM25 weight depends on K0 / K1: the maxima follow the statistics. */
+		const size_t stride = (size_t)e->nsb * BMW_SB_BLOCKS;
+		const size_t words = (size_t)e->n_bcol * stride;
 
-		CK(e, cudaMemsetAsync(e->d_bmax_bm25, 0, words * 4, e->stream));
-		CK(e, cudaMemsetAsync(e->d_bmax_tfidf, 0, words * 4, e->stream));
-		block_max_kernel<<<dim3(16, e->n_bcol), 256, 0, e->stream>>>(e->d_post,
-		    e->d_term_off, e->d_bcol_terms, e->nblocks, e->bshift, e->d_logtab,
-		    e->K0, e->K1, e->d_bmax_bm25, e->d_bmax_tfidf);
+		if (e->n_bcol) {
+			CK(e, cudaMemsetAsync(e->d_bmax_bm25, 0, words * 4, e->stream));
+			CK(e, cudaMemsetAsync(e->d_bmax_tfidf, 0, words * 4, e->stream));
+			block_max_kernel<<<dim3(16, e->n_bcol), 256, 0, e->stream>>>(e->d_post,
+			    e->d_term_off, e->d_bcol_terms, (uint32_t)stride, e->bshift, e->d_logtab,
+			    e->K0, e->K1, e->d_bmax_bm25, e->d_bmax_tfidf);
+			superblock_max_kernel<<<e->n_sms * 8, 256, 0, e->stream>>>(e->d_bmax_bm25,
+			    e->d_bmax_tfidf, (unsigned long long)e->n_bcol * e->nsb,
+			    e->d_bmax1_bm25, e->d_bmax1_tfidf);
+			e->launches += 2;
+		}
+		term_wmax_kernel<<<e->n_sms * 8, 256, 0, e->stream>>>(e->d_post, e->d_term_off,
+		    e->d_bcol, V, e->d_logtab, e->K0, e->K1, e->d_wmax_bm25, e->d_wmax_tfidf);
 		e->launches++;
 		CK(e, cudaGetLastError());
 	}
@@ -968,13 +983,16 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 		/* Block arrays of the column terms (bmw.cuh). */
 		{
 			e->nblocks = std::max(1u, (N + (1u << e->bshift) - 1) >> e->bshift);
-			e->nchunks = (e->nblocks + BMW_CH_BLOCKS - 1) / BMW_CH_BLOCKS;
+			e->nsb = (e->nblocks + BMW_SB_BLOCKS - 1) / BMW_SB_BLOCKS;
+			e->nchunks = (e->nsb + BMW_CH_SB - 1) / BMW_CH_SB;
 			std::vector<uint32_t> bcol(V, BMW_BCOL_NONE), bterms;
+			const size_t stride = (size_t)e->nsb * BMW_SB_BLOCKS;
 
 			if (!e->wide && e->bmw_enabled) {
-				/* At least two postings per block on average; 1 GiB of arrays at most. */
-				const uint64_t min_df = std::max<uint64_t>(2ull * e->nblocks, 64);
-				const size_t cap = std::max<size_t>(1, (1ull << 30) / (12ull * (e->nblocks + 1)));
+				/* A posting per two blocks on average at least; 2 GiB of arrays at most. */
+				const uint64_t min_df = std::max<uint64_t>(e->nblocks / 2, 64);
+				const size_t cap = std::max<size_t>(1, (2ull << 30) /
+				    (4ull * (e->nblocks + 1) + 8ull * stride + 8ull * e->nsb));
 
 				for (uint32_t t = 0; t < V; t++)
 					if (e->h_df_local[t] >= min_df)
@@ -994,8 +1012,12 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 			bool ok = dev_alloc(&e->d_bcol, V) == cudaSuccess &&
 			    dev_alloc(&e->d_bcol_terms, e->n_bcol) == cudaSuccess &&
 			    dev_alloc(&e->d_boff, (size_t)e->n_bcol * (e->nblocks + 1)) == cudaSuccess &&
-			    dev_alloc(&e->d_bmax_bm25, (size_t)e->n_bcol * e->nblocks) == cudaSuccess &&
-			    dev_alloc(&e->d_bmax_tfidf, (size_t)e->n_bcol * e->nblocks) == cudaSuccess;
+			    dev_alloc(&e->d_bmax_bm25, (size_t)e->n_bcol * stride) == cudaSuccess &&
+			    dev_alloc(&e->d_bmax_tfidf, (size_t)e->n_bcol * stride) == cudaSuccess &&
+			    dev_alloc(&e->d_bmax1_bm25, (size_t)e->n_bcol * e->nsb) == cudaSuccess &&
+			    dev_alloc(&e->d_bmax1_tfidf, (size_t)e->n_bcol * e->nsb) == cudaSuccess &&
+			    (e->wide || (dev_alloc(&e->d_wmax_bm25, V) == cudaSuccess &&
+			    dev_alloc(&e->d_wmax_tfidf, V) == cudaSuccess));
 			if (ok) {
 				cudaMemcpyAsync(e->d_bcol, bcol.data(), (size_t)V * 4,
 				    cudaMemcpyHostToDevice, st);
@@ -1268,7 +1290,7 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 	B.q_logic.clear();
 	/* OR queries with a small limit are pruned (bmw.cuh); the rest stream. */
 	B.bmw = e->bmw_enabled && !e->wide && !e->force_v2 && b->limit <= BMW_K_MAX &&
-	    e->d_bcol != nullptr;
+	    e->d_wmax_bm25 != nullptr;
 
 	for (uint32_t i = 0; i < b->n_queries; i++) {
 		const nxsb_query_t &q = b->queries[i];
@@ -1748,7 +1770,7 @@ run_bmw(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list, Re
 	const uint32_t k = B.limit;
 	const size_t cells = (size_t)e->nchunks * k;
 	/* Item numbers are 32-bit. */
-	const uint32_t chunk = (uint32_t)std::min<uint64_t>(n_list, 0xfffffff0ull / e->nchunks);
+	const uint32_t chunk = (uint32_t)std::min<uint64_t>(n_list, 0xfffffff0ull / (e->nchunks + 1));
 	const size_t slots = std::max<size_t>(chunk, std::min<size_t>(slots_for(B.n_q), chunk));
 
 	if (ensure_arena(e, e->d_cand, e->cand_bytes, slots * cells * 8, "candidate arena") == -1 ||
@@ -1767,11 +1789,14 @@ run_bmw(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list, Re
 		p.n_q = n;
 		p.nchunks = e->nchunks;
 		p.nblocks = e->nblocks;
+		p.nsb = e->nsb;
+		p.n_seed = e->nchunks > 1 ? n : 0;
 		p.n_docs = e->n_docs;
 		p.ntiles = e->ntiles;
 		p.k = k;
 		p.boff = e->d_boff;
 		p.bmax = B.algo == NXSB_ALGO_BM25 ? e->d_bmax_bm25 : e->d_bmax_tfidf;
+		p.bmax1 = B.algo == NXSB_ALGO_BM25 ? e->d_bmax1_bm25 : e->d_bmax1_tfidf;
 		p.thr = B.d_thr;
 		p.tile_count = e->d_tile_cnt;
 		p.cand = e->d_cand;
@@ -1803,7 +1828,8 @@ run_bmw(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list, Re
 		if (per_sm < 1)
 			return fail(e, "block-max kernel does not fit an SM (smem %zu)", smem);
 		const uint64_t items = (uint64_t)n * e->nchunks;
-		const unsigned grid = (unsigned)std::min<uint64_t>(items, (uint64_t)e->n_sms * per_sm);
+		const unsigned grid = (unsigned)std::min<uint64_t>(items + p.n_seed,
+		    (uint64_t)e->n_sms * per_sm);
 
 		CK(e, cudaMemsetAsync(B.d_thr, 0, B.zero_bytes, st));
 		CK(e, cudaMemsetAsync(e->d_tile_cnt, 0, (size_t)items * 4, st));
@@ -2010,6 +2036,7 @@ run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
 	    e->d_dense_col, e->d_bcol, e->d_dense_used, (unsigned long long)e->ntiles * TILE_DOCS,
 	    e->d_skip, e->d_skip_mt, e->n_mt, B.d_tmp_skip,
 	    B.algo == NXSB_ALGO_BM25 ? e->d_idf_bm25 : e->d_idf_tfidf,
+	    B.algo == NXSB_ALGO_BM25 ? e->d_wmax_bm25 : e->d_wmax_tfidf,
 	    e->ntiles, B.d_toks);
 	build_temp_skips_kernel<<<B.n_tok_all, 128, 0, st>>>(e->d_post, B.d_toks,
 	    B.d_tmp_skip, e->ntiles);

@@ -66,13 +66,15 @@ resolve_tokens_kernel(const uint32_t *__restrict__ term_ids, uint32_t n,
     const uint32_t *__restrict__ bcol, uint32_t *__restrict__ dense_used, unsigned long long col_words, const uint32_t *__restrict__ skip,
     const uint32_t *__restrict__ skip_mt, uint32_t n_mt,
     uint32_t *__restrict__ tmp_skip, const float *__restrict__ idf,
-    uint32_t ntiles, DTok *__restrict__ out)
+    const float *__restrict__ wmax, uint32_t ntiles, DTok *__restrict__ out)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	DTok t;
 
 	if (i >= n)
 		return;
+	t.pad = 0;
+	t.wmax = 0.f;
 	const uint32_t id = term_ids[i];
 
 	if (id == 0 || id > n_terms) {
@@ -96,6 +98,7 @@ resolve_tokens_kernel(const uint32_t *__restrict__ term_ids, uint32_t n,
 		t.dense_off = dense_col[ti] >= 0 ? (unsigned long long)dense_col[ti] * col_words
 		    : DENSE_NONE;
 		t.bcol = bcol ? bcol[ti] : 0xffffffffu;
+		t.wmax = wmax ? wmax[ti] : 0.f;
 		if (dense_col[ti] >= 0)
 			dense_used[dense_col[ti]] = 1u;	/* dense_scores_kernel will fill it */
 		t.skip = row >= 0 ? skip + (size_t)row * (ntiles + 1)

@@ -313,9 +313,14 @@ class Engine:
         return bool(self._lib.nxsb_engine_set_pruning(self._h, int(on)))
 
     def pruning_stats(self, reset: bool = False) -> dict[str, int]:
-        out = (C.c_uint64 * 4)()
+        out = (C.c_uint64 * 16)()
         self._check(self._lib.nxsb_engine_pruning_stats(self._h, out, int(reset)))
-        return {"items": out[0], "blocks_scored": out[1], "postings_scored": out[2], "rounds": out[3]}
+        st = {"items": out[0], "blocks_scored": out[1], "postings_scored": out[2], "rounds": out[3]}
+        if any(out[4:12]):      # -DBMW_PROF build: cycles of thread 0 per phase
+            names = ["bounds", "bounds_short_lists", "select", "score", "cut", "emit_merge", "item_setup", "seed"]
+            st["phase_cycles"] = {n: out[4 + i] for i, n in enumerate(names)}
+            st["live_superblocks"], st["items_all_pruned"], st["live_blocks_seen"] = out[12], out[13], out[14]
+        return st
 
     def __del__(self):  # pragma: no cover - best effort
         try:

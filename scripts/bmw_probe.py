@@ -30,6 +30,10 @@ for shift in shifts:
     e.sync()
     t = e.timings(steps)
     st = e.pruning_stats()
+    ph = st.pop("phase_cycles", None)
+    if ph:
+        tot = sum(ph.values()) or 1
+        print("   phases:", {k: f"{100 * v / tot:.1f}%" for k, v in ph.items()})
     print(f"shift {shift}:", {k: round(v / steps, 3) for k, v in t.items()},
           {k: round(v / steps) for k, v in st.items()},
           f"postings named per batch {named:.3g}, scored {st['postings_scored'] / steps / named:.4%}", flush=True)
