@@ -7,35 +7,32 @@
  * heap, so this kernel never touches most postings (the dynamic pruning of
  * block-max WAND, done block-at-a-time instead of with posting cursors):
  *
- *   The dense document space is cut into BLOCKS of 2^bshift documents, 32
- *   blocks make a SUPERBLOCK, 256 superblocks a CHUNK.  For every "column
- *   term" -- a list long enough to average a posting per two blocks -- the
- *   image holds, per block, the offset of its first posting (boff) and the
- *   largest query-independent weight any of its postings has (bmax: BM25
- *   tf-normalisation, or the TF-IDF tf weight; recomputed when the index
- *   statistics move), and the same maxima per superblock (bmax1).  A score is
+ *   The dense document space is cut into BLOCKS of 2^bshift documents, 8192
+ *   blocks make a CHUNK.  For every "column term" -- a list long enough to
+ *   average a posting per two blocks -- the image holds, per block, the
+ *   offset of its first posting (boff) and the largest query-independent
+ *   weight any of its postings has (bmax: BM25 tf-normalisation, or the
+ *   TF-IDF tf weight; recomputed when the index statistics move).  A score is
  *   weight x idf, both roundings monotonic, so  sum_t bmax[t][b] * idf[t]
  *   bounds every score in block b from above, bit for bit (float addition is
- *   monotonic, absent terms add +0).  Shorter lists have no arrays: a
- *   superblock they touch is charged their best score anywhere (wmax x idf),
- *   a block their exact maximum in it, folded in from the postings.
+ *   monotonic, absent terms add +0).  Shorter lists have no arrays: their
+ *   exact per-block maxima are folded in from the postings themselves.
  *
  *   work item = (query, chunk), handed out chunk-major from the highest ids
- *   down, after one SEED item per query: the seed looks at the superblock
- *   bounds of the whole shard, scores the best blocks of the best superblocks
- *   and publishes the k-th best key it saw as the query's first threshold.
+ *   down, so that a query's threshold (the k-th best key of everything its
+ *   earlier items found, kept in global memory) is known when an item starts.
  *   Per item:
- *     A. one thread per superblock: bound against the threshold;
- *     B. the blocks of the surviving superblocks: bound against the
- *        threshold (a thread per block, rows read 128 bytes per warp);
- *     C. the surviving blocks are scored, the most promising first when there
- *        are many (a histogram over the bounds picks them): a warp scores one
- *        block -- the block's slice of every token's list, in TOKEN-LIST ORDER
- *        (the reference's float summation order), into a per-warp accumulator
- *        of 2^bshift sums; what beats the threshold joins the item's candidate
- *        buffer, which is cut back to the k best whenever a round ends (that
- *        k-th key is the new threshold);
- *     D. the item's <= k keys go to the same per-(query, chunk) cells
+ *     1. one pass, a thread per block: bound against the threshold; what
+ *        survives is compacted into a list (and counted per bound bucket);
+ *     2. the surviving blocks are scored -- only the most promising when
+ *        there are many (the buckets pick them; the pass is then repeated
+ *        with the better threshold): a warp scores one block, the block's
+ *        slice of every token's list, in TOKEN-LIST ORDER (the reference's
+ *        float summation order), into a per-warp accumulator of 2^bshift
+ *        sums; what beats the threshold joins the item's candidate buffer,
+ *        which is cut back to the k best whenever a round ends (that k-th
+ *        key is the new threshold);
+ *     3. the item's <= k keys go to the same per-(query, chunk) cells
  *        finalize_cells_kernel merges for the stream kernel, and the query's
  *        threshold becomes the exact k-th best of all its cells so far.
  *
@@ -48,15 +45,13 @@
 
 #define BMW_THREADS	256
 #define BMW_WARPS	(BMW_THREADS / 32)
-#define BMW_SB_BLOCKS	32u			/* blocks per superblock */
-#define BMW_CH_SB	BMW_THREADS		/* superblocks per chunk */
-#define BMW_CH_BLOCKS	(BMW_CH_SB * BMW_SB_BLOCKS)	/* ub[] in shared memory */
+#define BMW_CH_BLOCKS	8192u			/* blocks per chunk */
+#define BMW_PER_THREAD	(BMW_CH_BLOCKS / BMW_THREADS)
 #define BMW_CAND	1024u			/* candidate keys per item */
 #define BMW_SEL		512u			/* blocks selected per round */
 #define BMW_K_MAX	128u			/* limit served by this kernel */
 #define BMW_HIST	64u
 #define BMW_ROUND_BLOCKS 64u			/* blocks of a partial round */
-#define BMW_SEED_MAX	4u			/* blocks a warp scores for a seed */
 #define BMW_BCOL_NONE	0xffffffffu
 #define BMW_SHIFT_MIN	5
 #define BMW_SHIFT_MAX	8
@@ -64,12 +59,11 @@
 
 static_assert((BMW_CH_BLOCKS << BMW_SHIFT_MIN) % TILE_DOCS == 0, "chunks start at tile boundaries");
 static_assert(BMW_K_MAX + (1u << BMW_SHIFT_MAX) <= BMW_CAND, "a block always fits after a cut");
-static_assert(BMW_SHIFT_MIN + 5 >= MT_SHIFT, "a superblock is whole mini-tiles");
 
 /*
  * -DBMW_PROF: cycles thread 0 of every CTA spends per phase, summed into
- * stats[4..]: bounds, short-list bounds, select, score, cut, emit + merge,
- * item setup, seed.
+ * stats[4..]: bounds + select, short-list bounds, pick, score, cut,
+ * emit + merge, item setup.
  */
 #ifdef BMW_PROF
 #define BPROF_DECL	long long bp_t = clock64(); unsigned long long bp_acc[8] = { 0 }
@@ -87,11 +81,9 @@ struct BmwParams {
 	const DTok *		toks;
 	const QDesc *		queries;
 	const uint32_t *	qlist;
-	uint32_t		n_q, nchunks, nblocks, nsb, n_docs, ntiles, k;
-	uint32_t		n_seed;		/* seed items ahead of the (query, chunk) items */
+	uint32_t		n_q, nchunks, nblocks, row_stride, n_docs, ntiles, k;
 	const uint32_t *	boff;		/* [n_bcol][nblocks + 1] */
-	const float *		bmax;		/* [n_bcol][nsb * 32], the batch's algorithm */
-	const float *		bmax1;		/* [n_bcol][nsb] */
+	const float *		bmax;		/* [n_bcol][row_stride], the batch's algorithm */
 	unsigned long long *	thr;		/* [n_q] */
 	uint32_t *		tile_count;	/* [n_q][nchunks] */
 	unsigned long long *	cand;		/* [n_q][nchunks][k] */
@@ -108,7 +100,7 @@ struct BmwTok {
 	float			idf;
 	uint32_t		col;
 	uint32_t		fine_shift;
-	float			best;		/* short list: its largest score anywhere */
+	float			best;		/* the list's largest score anywhere */
 };
 
 template <uint32_t BSHIFT>
@@ -117,7 +109,7 @@ struct BmwCfg {
 	static constexpr uint32_t NP = BS / 32;
 	static constexpr size_t SMEM = BMW_CH_BLOCKS * 4 + BMW_CAND * 8 + BMW_K_MAX * 8 +
 	    BMW_WARPS * BS * 4 + BMW_SEL * 2 + LOGTAB_N * 4 +
-	    NXSB_MAX_QUERY_TOKENS * sizeof(BmwTok) + BMW_CH_SB * 2;
+	    NXSB_MAX_QUERY_TOKENS * sizeof(BmwTok);
 };
 
 /* ---- image side: block offsets and block maxima of the column terms ---- */
@@ -218,38 +210,17 @@ block_max_kernel(const uint2 *__restrict__ post,
 	}
 }
 
-/* Superblock maxima: bmax1[c][sb] = max of the 32 block maxima (a warp per superblock). */
-__global__ void __launch_bounds__(256)
-superblock_max_kernel(const float *__restrict__ bmax_a, const float *__restrict__ bmax_b,
-    unsigned long long n_sb_total, float *__restrict__ out_a, float *__restrict__ out_b)
-{
-	const uint32_t lane = threadIdx.x & 31;
-	unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-	const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-
-	for (; w < n_sb_total; w += nw) {
-		float a = bmax_a[w * 32 + lane], b = bmax_b[w * 32 + lane];
-
-		for (int o = 16; o; o >>= 1) {
-			a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
-			b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
-		}
-		if (lane == 0) {
-			out_a[w] = a;
-			out_b[w] = b;
-		}
-	}
-}
-
 /*
- * wmax_*[t] = the largest weight of any posting of term t, for the terms
- * without block arrays (a warp per term; those lists are short).
+ * wmax_*[t] = the largest weight of any posting of term t (a warp per term):
+ * from the block maxima where the term has them, else from its postings
+ * (those lists are short).
  */
 __global__ void __launch_bounds__(256)
 term_wmax_kernel(const uint2 *__restrict__ post,
     const unsigned long long *__restrict__ term_off, const uint32_t *__restrict__ bcol,
     uint32_t n_terms, const float *__restrict__ logtab, float K0, float K1,
-    float *__restrict__ wmax_bm25, float *__restrict__ wmax_tfidf)
+    const float *__restrict__ bmax_bm25, const float *__restrict__ bmax_tfidf,
+    uint32_t row_stride, float *__restrict__ wmax_bm25, float *__restrict__ wmax_tfidf)
 {
 	__shared__ float s_logtab[LOGTAB_N];
 	const uint32_t lane = threadIdx.x & 31;
@@ -266,7 +237,14 @@ term_wmax_kernel(const uint2 *__restrict__ post,
 	for (uint32_t t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_terms; t += nw) {
 		float mb = 0.f, mt = 0.f;
 
-		if (bcol[t] == BMW_BCOL_NONE) {
+		if (bcol[t] != BMW_BCOL_NONE) {
+			const size_t r0 = (size_t)bcol[t] * row_stride;
+
+			for (uint32_t b = lane; b < row_stride; b += 32) {
+				mb = fmaxf(mb, bmax_bm25[r0 + b]);
+				mt = fmaxf(mt, bmax_tfidf[r0 + b]);
+			}
+		} else {
 			const unsigned long long s = term_off[t], e = term_off[t + 1];
 
 			for (unsigned long long i = s + lane; i < e; i += 32) {
@@ -278,10 +256,10 @@ term_wmax_kernel(const uint2 *__restrict__ post,
 				mb = fmaxf(mb, wb[0]);
 				mt = fmaxf(mt, wt[0]);
 			}
-			for (int o = 16; o; o >>= 1) {
-				mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
-				mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
-			}
+		}
+		for (int o = 16; o; o >>= 1) {
+			mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o));
+			mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
 		}
 		if (lane == 0) {
 			wmax_bm25[t] = mb;
@@ -293,33 +271,29 @@ term_wmax_kernel(const uint2 *__restrict__ post,
 /* ---- the scorer --------------------------------------------------------- */
 
 template <int ALGO, uint32_t BSHIFT>
-__global__ void __launch_bounds__(BMW_THREADS, 3)
+__global__ void __launch_bounds__(BMW_THREADS, 4)
 score_bmw_kernel(const BmwParams p)
 {
 	using Cfg = BmwCfg<BSHIFT>;
 	constexpr uint32_t BS = Cfg::BS, NP = Cfg::NP;
-	constexpr uint32_t SBSHIFT = BSHIFT + 5;	/* log2 documents per superblock */
 	constexpr uint32_t FULL = 0xffffffffu;
 
 	extern __shared__ __align__(16) unsigned char smem_bmw[];
-	float *ub = reinterpret_cast<float *>(smem_bmw);
+	float *ub = reinterpret_cast<float *>(smem_bmw);		/* [CH_BLOCKS] bounds; 0 = scored */
 	unsigned long long *s_cand = reinterpret_cast<unsigned long long *>(ub + BMW_CH_BLOCKS);
 	unsigned long long *s_top = s_cand + BMW_CAND;			/* [K_MAX] cut buffer */
 	float *s_acc = reinterpret_cast<float *>(s_top + BMW_K_MAX);	/* [WARPS][BS] */
 	BmwTok *s_tok = reinterpret_cast<BmwTok *>(s_acc + BMW_WARPS * BS);
 	float *s_logtab = reinterpret_cast<float *>(s_tok + NXSB_MAX_QUERY_TOKENS);
 	uint16_t *s_sel = reinterpret_cast<uint16_t *>(s_logtab + LOGTAB_N);
-	uint16_t *s_alive = s_sel + BMW_SEL;				/* [CH_SB] live superblocks */
 
-	__shared__ uint32_t s_item, s_nsel, s_selw, s_next, s_ncand, s_overflow, s_umax, s_cut, s_nalive;
+	__shared__ uint32_t s_item, s_selw[2], s_next, s_ncand, s_overflow, s_cut;
 	__shared__ uint32_t s_hist[BMW_HIST];
 	__shared__ unsigned long long s_theta, s_kth;
-	__shared__ uint8_t s_live1[BMW_CH_SB];
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const uint32_t n_items = p.n_seed + p.n_q * p.nchunks;
+	const uint32_t n_items = p.n_q * p.nchunks;
 	const uint32_t k = p.k;
-	const uint32_t row_stride = p.nsb * BMW_SB_BLOCKS;	/* bmax rows are whole superblocks */
 	float *wacc = s_acc + warp * BS;
 	unsigned long long st_blocks = 0, st_post = 0, st_rounds = 0, st_items = 0;
 
@@ -338,27 +312,22 @@ score_bmw_kernel(const BmwParams p)
 		if (tid == 0) {
 			s_item = atomicAdd(p.work_counter, 1u);
 			s_ncand = 0;
-			s_nalive = 0;
-			s_overflow = 0;
 		}
 		__syncthreads();
 		const uint32_t item = s_item;
 
 		if (item >= n_items)
 			break;
-		const bool seed_item = item < p.n_seed;
-		const uint32_t it = seed_item ? 0u : item - p.n_seed;
-		const uint32_t chunk = seed_item ? 0u : p.nchunks - 1 - it / p.n_q;
-		const uint32_t slot = seed_item ? item : it % p.n_q;
+		const uint32_t chunk = p.nchunks - 1 - item / p.n_q;
+		const uint32_t slot = item % p.n_q;
 		const QDesc qd = p.queries[p.qlist[slot]];
 		const uint32_t ntok = qd.n_tokens;
 		const uint32_t cb0 = chunk * BMW_CH_BLOCKS;
+		const uint32_t nb = min(BMW_CH_BLOCKS, p.nblocks - cb0);
 		const uint32_t doc0 = cb0 << BSHIFT;
-		const uint32_t sb_lo = chunk * BMW_CH_SB;
-		const uint32_t sb_hi = min(p.nsb, sb_lo + BMW_CH_SB);
 		const uint32_t tile0 = doc0 >> TILE_SHIFT;
 		const uint32_t tile1 = min(p.ntiles,
-		    (uint32_t)((((unsigned long long)sb_hi << SBSHIFT) + TILE_DOCS - 1) >> TILE_SHIFT));
+		    (uint32_t)((((unsigned long long)(cb0 + nb) << BSHIFT) + TILE_DOCS - 1) >> TILE_SHIFT));
 
 		if (tid < ntok) {
 			const DTok t = p.toks[qd.tok_off + tid];
@@ -381,8 +350,11 @@ score_bmw_kernel(const BmwParams p)
 			st_items++;
 
 		bool any_list = false;
-		for (uint32_t j = 0; j < ntok; j++)
+		float best_sum = 0.f;		/* no score of the query exceeds it */
+		for (uint32_t j = 0; j < ntok; j++) {
 			any_list |= s_tok[j].col == BMW_BCOL_NONE;
+			best_sum = __fadd_ru(best_sum, s_tok[j].best);
+		}
 		/*
 		 * A block's bound is summed columns first, short lists after:
 		 * another order than the token list's, which can round a few ulp
@@ -390,52 +362,50 @@ score_bmw_kernel(const BmwParams p)
 		 */
 		const float infl = (any_list && ntok >= 3) ? 1.0000152587890625f : 1.f;
 
-		/* Token j's postings that may lie in superblock sb: [lo, hi). */
-		auto sb_slice = [&](const BmwTok &bt, uint32_t sb, uint32_t &lo, uint32_t &hi) {
-			uint32_t i0, i1;
-
-			if (bt.fine_shift <= SBSHIFT) {
-				i0 = sb << (SBSHIFT - bt.fine_shift);
-				i1 = (sb + 1) << (SBSHIFT - bt.fine_shift);
-				i1 = min(i1, (p.n_docs + (1u << bt.fine_shift) - 1) >> bt.fine_shift);
-			} else {
-				i0 = (sb << SBSHIFT) >> bt.fine_shift;
-				i1 = i0 + 1;
-			}
-			lo = __ldg(bt.fine + i0);
-			hi = __ldg(bt.fine + i1);
-		};
-		/* Bound of a superblock, summed in token order (no slack needed). */
-		auto coarse = [&](uint32_t sb) -> float {
-			float u = 0.f;
-
+		BPROF(6);
+		/* ---- short lists: their exact block maxima, from the postings ---- */
+		if (any_list) {
+#pragma unroll 8
+			for (uint32_t b = tid; b < BMW_CH_BLOCKS; b += BMW_THREADS)
+				ub[b] = 0.f;
+			__syncthreads();
 			for (uint32_t j = 0; j < ntok; j++) {
-				const BmwTok &bt = s_tok[j];
-
-				if (bt.col != BMW_BCOL_NONE) {
-					u = __fadd_rn(u, __fmul_rn(__ldg(p.bmax1 + (size_t)bt.col * p.nsb + sb), bt.idf));
-				} else {
-					uint32_t lo, hi;
-
-					sb_slice(bt, sb, lo, hi);
-					if (hi > lo)
-						u = __fadd_rn(u, bt.best);
-				}
-			}
-			return u;
-		};
-		/* Column part of a block's bound, token order. */
-		auto fine_cols = [&](uint32_t gb) -> float {
-			float u = 0.f;
-
-			for (uint32_t j = 0; j < ntok; j++) {
-				const BmwTok &bt = s_tok[j];
+				const BmwTok bt = s_tok[j];
 
 				if (bt.col != BMW_BCOL_NONE)
-					u = __fadd_rn(u, __fmul_rn(__ldg(p.bmax + (size_t)bt.col * row_stride + gb), bt.idf));
+					continue;
+				const uint2 *list = p.post + bt.post_off;
+
+				for (uint32_t i0 = bt.clo; i0 < bt.chi; i0 += BMW_THREADS) {
+					const uint32_t i = i0 + tid;
+					const bool valid = i < bt.chi;
+					uint2 v[1] = { valid ? __ldg(list + i) : make_uint2(0xffffffffu, 0u) };
+					uint32_t xp = __shfl_up_sync(FULL, v[0].x, 1);
+
+					if (lane == 0)
+						xp = (valid && i > bt.clo) ? __ldg(list + i - 1).x : 0xffffffffu;
+					const uint32_t b = (v[0].x - doc0) >> BSHIFT;
+
+					/* The head of a block's run folds the run. */
+					if (!valid || (i != bt.clo && ((xp - doc0) >> BSHIFT) == b))
+						continue;
+					float sc[1], m;
+
+					st_score<false, ALGO, 1>(sp, s_logtab, v, bt.idf, sc);
+					m = sc[0];
+					for (uint32_t i2 = i + 1; i2 < bt.chi; i2++) {
+						v[0] = __ldg(list + i2);
+						if (((v[0].x - doc0) >> BSHIFT) != b)
+							break;
+						st_score<false, ALGO, 1>(sp, s_logtab, v, bt.idf, sc);
+						m = fmaxf(m, sc[0]);
+					}
+					atomicAdd(ub + b, m);
+				}
 			}
-			return u;
-		};
+			__syncthreads();
+			BPROF(1);
+		}
 
 		/*
 		 * A warp scores block gb: every token's slice of the block, token
@@ -620,278 +590,123 @@ score_bmw_kernel(const BmwParams p)
 			__syncthreads();
 		};
 
-		/*
-		 * Seed: score the best block of the best superblocks of
-		 * [lo, hi) -- a few per warp -- and take the k-th best key seen,
-		 * less one (the documents themselves are scored again by the item
-		 * that owns them and must pass `key > threshold` there).
-		 */
-		auto seed = [&](uint32_t lo, uint32_t hi) {
-			float bu = 0.f;
-			uint32_t bsb = 0;
-
-			for (uint32_t sb = lo + tid; sb < hi; sb += BMW_THREADS) {
-				const float u1 = coarse(sb);
-
-				if (u1 > bu) {
-					bu = u1;
-					bsb = sb;
-				}
-			}
-			const uint32_t rounds = min(BMW_SEED_MAX, (k + BMW_WARPS - 1) / BMW_WARPS + 1);
-
-			for (uint32_t r = 0; r < rounds; r++) {
-				float m = bu;
-				uint32_t ml = lane;
-
-				for (int o = 16; o; o >>= 1) {
-					const float om = __shfl_xor_sync(FULL, m, o);
-					const uint32_t ol = __shfl_xor_sync(FULL, ml, o);
-
-					if (om > m || (om == m && ol < ml)) {
-						m = om;
-						ml = ol;
-					}
-				}
-				if (m == 0.f || *(volatile uint32_t *)&s_overflow)
-					break;
-				const uint32_t wsb = __shfl_sync(FULL, bsb, ml);
-
-				if (lane == ml)
-					bu = 0.f;
-				/* lane = block of the superblock */
-				const uint32_t gb = wsb * BMW_SB_BLOCKS + lane;
-				float u = fine_cols(gb);
-
-				for (uint32_t j = 0; j < ntok; j++) {
-					const BmwTok bt = s_tok[j];
-
-					if (bt.col != BMW_BCOL_NONE)
-						continue;
-					uint32_t slo, shi;
-					uint32_t *wmax = reinterpret_cast<uint32_t *>(wacc);
-
-					sb_slice(bt, wsb, slo, shi);
-					wmax[lane] = 0u;
-					__syncwarp();
-					for (uint32_t i = slo + lane; i < shi; i += 32) {
-						const uint2 v[1] = { __ldg(p.post + bt.post_off + i) };
-
-						if ((v[0].x >> SBSHIFT) == wsb) {
-							float sc[1];
-
-							st_score<false, ALGO, 1>(sp, s_logtab, v, bt.idf, sc);
-							atomicMax(wmax + ((v[0].x >> BSHIFT) & 31u), __float_as_uint(sc[0]));
-						}
-					}
-					__syncwarp();
-					u = __fadd_rn(u, __uint_as_float(wmax[lane]));
-					__syncwarp();
-				}
-				/* the warp's best block */
-				float fm = gb < p.nblocks ? u : 0.f;
-				uint32_t fl = lane;
-
-				for (int o = 16; o; o >>= 1) {
-					const float om = __shfl_xor_sync(FULL, fm, o);
-					const uint32_t ol = __shfl_xor_sync(FULL, fl, o);
-
-					if (om > fm || (om == fm && ol < fl)) {
-						fm = om;
-						fl = ol;
-					}
-				}
-				if (fm != 0.f)
-					score_block(wsb * BMW_SB_BLOCKS + fl);
-			}
-			__syncthreads();
-			cut();
-			if (tid == 0) {
-				const unsigned long long kth = s_kth;
-
-				if (kth > 1 && kth - 1 > s_theta) {
-					s_theta = kth - 1;
-					atomicMax(p.thr + slot, kth - 1);
-				}
-				s_ncand = 0;		/* nothing is kept */
-				s_overflow = 0;
-			}
-			__syncthreads();
-		};
-
-		BPROF(6);
-		if (seed_item) {
-			if (s_theta == 0)
-				seed(0, p.nsb);
-			BPROF(7);
-			continue;
-		}
-		if (s_theta == 0) {
-			/* No seed reached this item (a lone query, a late seed): a local one. */
-			if (tid == 0)
-				s_overflow = 0;
-			__syncthreads();
-			seed(sb_lo, sb_hi);
-			BPROF(7);
-		}
-
-		/* ---- A. superblocks ---- */
-		{
-			const unsigned long long theta = s_theta;
-			const uint32_t sb = sb_lo + tid;
-			const float u1 = sb < sb_hi ? coarse(sb) : 0.f;
-			const bool a1 = u1 != 0.f && make_key(u1, ((sb + 1u) << SBSHIFT) - 1u) > theta;
-			const uint32_t m = __ballot_sync(FULL, a1);
-			uint32_t at = 0;
-
-			s_live1[tid] = a1;
-			if (m) {
-				if (lane == 0)
-					at = atomicAdd(&s_nalive, __popc(m));
-				at = __shfl_sync(FULL, at, 0);
-				if (a1)
-					s_alive[at + __popc(m & ((1u << lane) - 1u))] = (uint16_t)tid;
-			}
-		}
-		__syncthreads();
-		const uint32_t nfine = s_nalive * BMW_SB_BLOCKS;
-
-#ifdef BMW_PROF
-		if (tid == 0 && p.stats) {
-			atomicAdd(p.stats + 12, (unsigned long long)s_nalive);
-			if (nfine == 0)
-				atomicAdd(p.stats + 13, 1ull);
-		}
-#endif
-		BPROF(0);
-		if (nfine == 0)
-			continue;
-
-		/* ---- B. blocks of the live superblocks ---- */
-		if (any_list) {
-			for (uint32_t idx = tid; idx < nfine; idx += BMW_THREADS)
-				ub[s_alive[idx >> 5] * BMW_SB_BLOCKS + (idx & 31u)] = 0.f;
-			__syncthreads();
-			for (uint32_t j = 0; j < ntok; j++) {
-				const BmwTok bt = s_tok[j];
-
-				if (bt.col != BMW_BCOL_NONE)
-					continue;
-				const uint2 *list = p.post + bt.post_off;
-
-				for (uint32_t i0 = bt.clo; i0 < bt.chi; i0 += BMW_THREADS) {
-					const uint32_t i = i0 + tid;
-					const bool valid = i < bt.chi;
-					uint2 v[1] = { valid ? __ldg(list + i) : make_uint2(0xffffffffu, 0u) };
-					uint32_t xp = __shfl_up_sync(FULL, v[0].x, 1);
-
-					if (lane == 0)
-						xp = (valid && i > bt.clo) ? __ldg(list + i - 1).x : 0xffffffffu;
-					const uint32_t b = (v[0].x - doc0) >> BSHIFT;
-
-					/* The head of a block's run folds the run. */
-					if (!valid || (i != bt.clo && ((xp - doc0) >> BSHIFT) == b) ||
-					    !s_live1[b >> 5])
-						continue;
-					float sc[1], m;
-
-					st_score<false, ALGO, 1>(sp, s_logtab, v, bt.idf, sc);
-					m = sc[0];
-					for (uint32_t i2 = i + 1; i2 < bt.chi; i2++) {
-						v[0] = __ldg(list + i2);
-						if (((v[0].x - doc0) >> BSHIFT) != b)
-							break;
-						st_score<false, ALGO, 1>(sp, s_logtab, v, bt.idf, sc);
-						m = fmaxf(m, sc[0]);
-					}
-					atomicAdd(ub + b, m);
-				}
-			}
-			__syncthreads();
-			BPROF(1);
-		}
-		for (uint32_t idx = tid; idx < nfine; idx += BMW_THREADS) {
-			const uint32_t b = s_alive[idx >> 5] * BMW_SB_BLOCKS + (idx & 31u);
-			float u = fine_cols(cb0 + b);
-
-			if (any_list)
-				u = __fadd_rn(u, ub[b]);
-			ub[b] = u;
-		}
-		BPROF(0);
-
-		/* ---- C. rounds: select, score, cut ---- */
+		/* ---- rounds: bound + select, score, cut ---- */
+		bool first = true;
 		for (;;) {
-			__syncthreads();
 			if (tid == 0) {
 				const unsigned long long g = *(volatile unsigned long long *)(p.thr + slot);
 
 				if (g > s_theta)
 					s_theta = g;
-				s_nsel = s_selw = s_next = s_overflow = s_umax = 0;
+				s_selw[0] = s_selw[1] = s_next = s_overflow = 0;
 			}
 			if (tid < BMW_HIST)
 				s_hist[tid] = 0;
 			__syncthreads();
 			const unsigned long long theta = s_theta;
-			uint32_t cnt = 0, mxb = 0;
-
-			/* (bound, last document of the block) must beat the threshold key. */
-			auto alive = [&](uint32_t b, float u) -> bool {
-				return u != 0.f && make_key(u, ((cb0 + b + 1u) << BSHIFT) - 1u) > theta;
-			};
-			for (uint32_t idx = tid; idx < nfine; idx += BMW_THREADS) {
-				const uint32_t b = s_alive[idx >> 5] * BMW_SB_BLOCKS + (idx & 31u);
-				const float u = __fmul_ru(ub[b], infl);
-
-				if (alive(b, u)) {
-					cnt++;
-					mxb = max(mxb, __float_as_uint(u));
-				}
-			}
-			cnt = __reduce_add_sync(FULL, cnt);
-			mxb = __reduce_max_sync(FULL, mxb);
-			if (lane == 0 && cnt) {
-				atomicAdd(&s_nsel, cnt);
-				atomicMax(&s_umax, mxb);
-			}
-			__syncthreads();
-			const uint32_t nsel = s_nsel;
-
-#ifdef BMW_PROF
-			if (tid == 0 && p.stats)
-				atomicAdd(p.stats + 14, (unsigned long long)nsel);
-#endif
-			if (nsel == 0)
-				break;
-			/* Everything alive, or only the blocks with the highest bounds? */
-			const bool subset = nsel > BMW_SEL / 2;
+			/* Buckets between the threshold's score and the query's best. */
 			const float lo = __uint_as_float((uint32_t)(theta >> 32));
-			const float hi = __uint_as_float(s_umax);
-			const float scale = subset && hi > lo ? (float)BMW_HIST / (hi - lo) : 0.f;
+			const float hi = __fmul_ru(best_sum, infl);
+			const float scale = hi > lo ? (float)BMW_HIST / (hi - lo) : 0.f;
 			auto bin_of = [&](float u) -> uint32_t {
 				const float x = (u - lo) * scale;
 
 				return x <= 0.f ? 0u : min(BMW_HIST - 1u, (uint32_t)x);
 			};
+			/* (bound, last document of the block) must beat the threshold key. */
+			auto alive = [&](uint32_t b, float u) -> bool {
+				return u != 0.f && make_key(u, ((cb0 + b + 1u) << BSHIFT) - 1u) > theta;
+			};
 
-			if (subset) {
-				for (uint32_t idx = tid; idx < nfine; idx += BMW_THREADS) {
-					const uint32_t b = s_alive[idx >> 5] * BMW_SB_BLOCKS + (idx & 31u);
-					const float u = __fmul_ru(ub[b], infl);
-					const bool a = alive(b, u);
-					const uint32_t am = __ballot_sync(FULL, a);
+			/* Live blocks are compacted into s_sel while there is room, and
+			 * counted per bucket; cutbin > 0: only the buckets from there up. */
+			auto select = [&](uint32_t b, float u, uint32_t cutbin, bool count, uint32_t *selw) {
+				const bool a = alive(b, u);
+				const uint32_t bin = a ? bin_of(u) : 0u;
+				const bool take = a && bin >= cutbin;
+				const uint32_t tm = __ballot_sync(FULL, take);
 
-					if (a) {
-						/* one atomic per distinct bin of the warp */
-						const uint32_t bin = bin_of(u);
-						const uint32_t same = __match_any_sync(am, bin);
+				if (!tm)
+					return;
+				uint32_t at = 0;
 
-						if (lane == (uint32_t)__ffs(same) - 1u)
-							atomicAdd(&s_hist[bin], __popc(same));
-					}
+				if (lane == 0)
+					at = atomicAdd(selw, __popc(tm));
+				at = __shfl_sync(FULL, at, 0) + __popc(tm & ((1u << lane) - 1u));
+				if (take && at < BMW_SEL)
+					s_sel[at] = (uint16_t)b;
+				if (count && take) {
+					/* one atomic per distinct bucket of the warp */
+					const uint32_t same = __match_any_sync(tm, bin);
+
+					if (lane == (uint32_t)__ffs(same) - 1u)
+						atomicAdd(&s_hist[bin], __popc(same));
 				}
-				__syncthreads();
+			};
+			if (first) {
+				/*
+				 * The bounds themselves, a thread per block, eight
+				 * blocks at a time so that every load of a token's row
+				 * is in flight before the first sum: ub[b] = (columns
+				 * in token order + what the short lists left) * slack.
+				 */
+				constexpr uint32_t U = 8;
+
+				for (uint32_t i0 = 0; i0 < BMW_PER_THREAD; i0 += U) {
+					float u[U];
+
+#pragma unroll
+					for (uint32_t x = 0; x < U; x++)
+						u[x] = 0.f;
+					for (uint32_t j = 0; j < ntok; j++) {
+						const BmwTok &bt = s_tok[j];
+
+						if (bt.col == BMW_BCOL_NONE)
+							continue;
+						const float *row = p.bmax + (size_t)bt.col * p.row_stride + cb0;
+						float m[U];
+
+#pragma unroll
+						for (uint32_t x = 0; x < U; x++) {
+							const uint32_t b = tid + (i0 + x) * BMW_THREADS;
+
+							m[x] = b < nb ? __ldg(row + b) : 0.f;
+						}
+#pragma unroll
+						for (uint32_t x = 0; x < U; x++)
+							u[x] = __fadd_rn(u[x], __fmul_rn(m[x], bt.idf));
+					}
+#pragma unroll
+					for (uint32_t x = 0; x < U; x++) {
+						const uint32_t b = tid + (i0 + x) * BMW_THREADS;
+
+						if (any_list)
+							u[x] = __fadd_rn(u[x], ub[b]);
+						u[x] = b < nb ? __fmul_ru(u[x], infl) : 0.f;
+						ub[b] = u[x];
+					}
+#pragma unroll
+					for (uint32_t x = 0; x < U; x++)
+						select(tid + (i0 + x) * BMW_THREADS, u[x], 0u, true, &s_selw[0]);
+				}
+			} else {
+#pragma unroll 4
+				for (uint32_t i = 0; i < BMW_PER_THREAD; i++) {
+					const uint32_t b = tid + i * BMW_THREADS;
+
+					select(b, ub[b], 0u, true, &s_selw[0]);
+				}
+			}
+			first = false;
+			__syncthreads();
+			uint32_t found = s_selw[0];
+
+			if (found == 0)
+				break;
+			/* Too many: only the blocks with the highest bounds this round. */
+			const bool partial = found > BMW_SEL / 2;
+
+			if (partial) {
 				if (tid == 0) {
 					uint32_t cum = 0;
 					int bin = BMW_HIST - 1;
@@ -904,33 +719,25 @@ score_bmw_kernel(const BmwParams p)
 					s_cut = (uint32_t)bin;
 				}
 				__syncthreads();
-			}
-			const uint32_t cutbin = subset ? s_cut : 0u;
+				const uint32_t cutbin = s_cut;
 
-			for (uint32_t idx = tid; idx < nfine; idx += BMW_THREADS) {
-				const uint32_t b = s_alive[idx >> 5] * BMW_SB_BLOCKS + (idx & 31u);
-				const float u = __fmul_ru(ub[b], infl);
-				const bool take = alive(b, u) && (!subset || bin_of(u) >= cutbin);
-				const uint32_t tm = __ballot_sync(FULL, take);
+				if (cutbin > 0) {
+					/* its own counter: s_selw[0] is still being read */
+#pragma unroll 4
+					for (uint32_t i = 0; i < BMW_PER_THREAD; i++) {
+						const uint32_t b = tid + i * BMW_THREADS;
 
-				if (tm) {
-					uint32_t at = 0;
-
-					if (lane == 0)
-						at = atomicAdd(&s_selw, __popc(tm));
-					at = __shfl_sync(FULL, at, 0) + __popc(tm & ((1u << lane) - 1u));
-					if (take && at < BMW_SEL)
-						s_sel[at] = (uint16_t)b;
+						select(b, ub[b], cutbin, false, &s_selw[1]);
+					}
+					__syncthreads();
+					found = s_selw[1];
 				}
 			}
-			__syncthreads();
-			const uint32_t n_round = min(s_selw, BMW_SEL);
-			/* Did this round take every live block? */
-			const bool partial = subset || s_selw > BMW_SEL;
+			const uint32_t n_round = min(found, BMW_SEL);
 
 			if (tid == 0)
 				st_rounds++;
-			BPROF(2);
+			BPROF(partial ? 2 : 0);
 
 			/* ---- score the selected blocks, one per warp at a time ---- */
 			for (;;) {
@@ -962,10 +769,11 @@ score_bmw_kernel(const BmwParams p)
 			BPROF(4);
 			if (!partial && !s_overflow)
 				break;		/* every live block was scored */
+			__syncthreads();
 		}
-		BPROF(2);
+		BPROF(0);
 
-		/* ---- D. the item's cell ---- */
+		/* ---- the item's cell ---- */
 		__syncthreads();
 		const uint32_t nc = s_ncand;		/* <= k */
 

@@ -208,13 +208,12 @@ struct nxsb_engine {
 	 * two postings per block of 2^bshift documents.
 	 */
 	bool		bmw_enabled = true;		// NXSB_BMW=0: every query streams
-	uint32_t	bshift = 6, nblocks = 0, nsb = 0, nchunks = 0, n_bcol = 0;
+	uint32_t	bshift = 5, nblocks = 0, row_stride = 0, nchunks = 0, n_bcol = 0;
 	uint32_t *	d_bcol = nullptr;		// [V] row of a term or BMW_BCOL_NONE
 	uint32_t *	d_bcol_terms = nullptr;		// [n_bcol] term index of a row
 	uint32_t *	d_boff = nullptr;		// [n_bcol][nblocks + 1]
-	float *		d_bmax_bm25 = nullptr, *d_bmax_tfidf = nullptr;	// [n_bcol][nsb * 32]
-	float *		d_bmax1_bm25 = nullptr, *d_bmax1_tfidf = nullptr;	// [n_bcol][nsb]
-	float *		d_wmax_bm25 = nullptr, *d_wmax_tfidf = nullptr;	// [V] terms without block arrays
+	float *		d_bmax_bm25 = nullptr, *d_bmax_tfidf = nullptr;	// [n_bcol][row_stride]
+	float *		d_wmax_bm25 = nullptr, *d_wmax_tfidf = nullptr;	// [V] largest weight of a term
 	unsigned long long *d_bmw_stats = nullptr;	// [4] counters of the BMW launches
 	uint64_t	token_count = 0;
 	uint32_t	doc_count = 0;
@@ -546,8 +545,6 @@ free_image(nxsb_engine_t *e)
 	dev_free(e->d_boff);
 	dev_free(e->d_bmax_bm25);
 	dev_free(e->d_bmax_tfidf);
-	dev_free(e->d_bmax1_bm25);
-	dev_free(e->d_bmax1_tfidf);
 	dev_free(e->d_wmax_bm25);
 	dev_free(e->d_wmax_tfidf);
 	e->n_bcol = 0;
@@ -708,22 +705,19 @@ upload_stats(nxsb_engine_t *e)
 	    cudaMemcpyHostToDevice, e->stream));
 	if (e->d_wmax_bm25) {
 		/* The BM25 weight depends on K0 / K1: the maxima follow the statistics. */
-		const size_t stride = (size_t)e->nsb * BMW_SB_BLOCKS;
-		const size_t words = (size_t)e->n_bcol * stride;
+		const size_t words = (size_t)e->n_bcol * e->row_stride;
 
 		if (e->n_bcol) {
 			CK(e, cudaMemsetAsync(e->d_bmax_bm25, 0, words * 4, e->stream));
 			CK(e, cudaMemsetAsync(e->d_bmax_tfidf, 0, words * 4, e->stream));
 			block_max_kernel<<<dim3(16, e->n_bcol), 256, 0, e->stream>>>(e->d_post,
-			    e->d_term_off, e->d_bcol_terms, (uint32_t)stride, e->bshift, e->d_logtab,
+			    e->d_term_off, e->d_bcol_terms, e->row_stride, e->bshift, e->d_logtab,
 			    e->K0, e->K1, e->d_bmax_bm25, e->d_bmax_tfidf);
-			superblock_max_kernel<<<e->n_sms * 8, 256, 0, e->stream>>>(e->d_bmax_bm25,
-			    e->d_bmax_tfidf, (unsigned long long)e->n_bcol * e->nsb,
-			    e->d_bmax1_bm25, e->d_bmax1_tfidf);
-			e->launches += 2;
+			e->launches++;
 		}
 		term_wmax_kernel<<<e->n_sms * 8, 256, 0, e->stream>>>(e->d_post, e->d_term_off,
-		    e->d_bcol, V, e->d_logtab, e->K0, e->K1, e->d_wmax_bm25, e->d_wmax_tfidf);
+		    e->d_bcol, V, e->d_logtab, e->K0, e->K1, e->d_bmax_bm25, e->d_bmax_tfidf,
+		    e->row_stride, e->d_wmax_bm25, e->d_wmax_tfidf);
 		e->launches++;
 		CK(e, cudaGetLastError());
 	}
@@ -983,16 +977,16 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 		/* Block arrays of the column terms (bmw.cuh). */
 		{
 			e->nblocks = std::max(1u, (N + (1u << e->bshift) - 1) >> e->bshift);
-			e->nsb = (e->nblocks + BMW_SB_BLOCKS - 1) / BMW_SB_BLOCKS;
-			e->nchunks = (e->nsb + BMW_CH_SB - 1) / BMW_CH_SB;
+			e->row_stride = (e->nblocks + 31u) & ~31u;
+			e->nchunks = (e->nblocks + BMW_CH_BLOCKS - 1) / BMW_CH_BLOCKS;
 			std::vector<uint32_t> bcol(V, BMW_BCOL_NONE), bterms;
-			const size_t stride = (size_t)e->nsb * BMW_SB_BLOCKS;
+			const size_t stride = e->row_stride;
 
 			if (!e->wide && e->bmw_enabled) {
 				/* A posting per two blocks on average at least; 2 GiB of arrays at most. */
 				const uint64_t min_df = std::max<uint64_t>(e->nblocks / 2, 64);
 				const size_t cap = std::max<size_t>(1, (2ull << 30) /
-				    (4ull * (e->nblocks + 1) + 8ull * stride + 8ull * e->nsb));
+				    (4ull * (e->nblocks + 1) + 8ull * stride));
 
 				for (uint32_t t = 0; t < V; t++)
 					if (e->h_df_local[t] >= min_df)
@@ -1014,8 +1008,6 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 			    dev_alloc(&e->d_boff, (size_t)e->n_bcol * (e->nblocks + 1)) == cudaSuccess &&
 			    dev_alloc(&e->d_bmax_bm25, (size_t)e->n_bcol * stride) == cudaSuccess &&
 			    dev_alloc(&e->d_bmax_tfidf, (size_t)e->n_bcol * stride) == cudaSuccess &&
-			    dev_alloc(&e->d_bmax1_bm25, (size_t)e->n_bcol * e->nsb) == cudaSuccess &&
-			    dev_alloc(&e->d_bmax1_tfidf, (size_t)e->n_bcol * e->nsb) == cudaSuccess &&
 			    (e->wide || (dev_alloc(&e->d_wmax_bm25, V) == cudaSuccess &&
 			    dev_alloc(&e->d_wmax_tfidf, V) == cudaSuccess));
 			if (ok) {
@@ -1789,14 +1781,12 @@ run_bmw(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list, Re
 		p.n_q = n;
 		p.nchunks = e->nchunks;
 		p.nblocks = e->nblocks;
-		p.nsb = e->nsb;
-		p.n_seed = e->nchunks > 1 ? n : 0;
+		p.row_stride = e->row_stride;
 		p.n_docs = e->n_docs;
 		p.ntiles = e->ntiles;
 		p.k = k;
 		p.boff = e->d_boff;
 		p.bmax = B.algo == NXSB_ALGO_BM25 ? e->d_bmax_bm25 : e->d_bmax_tfidf;
-		p.bmax1 = B.algo == NXSB_ALGO_BM25 ? e->d_bmax1_bm25 : e->d_bmax1_tfidf;
 		p.thr = B.d_thr;
 		p.tile_count = e->d_tile_cnt;
 		p.cand = e->d_cand;
@@ -1828,8 +1818,7 @@ run_bmw(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list, Re
 		if (per_sm < 1)
 			return fail(e, "block-max kernel does not fit an SM (smem %zu)", smem);
 		const uint64_t items = (uint64_t)n * e->nchunks;
-		const unsigned grid = (unsigned)std::min<uint64_t>(items + p.n_seed,
-		    (uint64_t)e->n_sms * per_sm);
+		const unsigned grid = (unsigned)std::min<uint64_t>(items, (uint64_t)e->n_sms * per_sm);
 
 		CK(e, cudaMemsetAsync(B.d_thr, 0, B.zero_bytes, st));
 		CK(e, cudaMemsetAsync(e->d_tile_cnt, 0, (size_t)items * 4, st));

@@ -317,9 +317,8 @@ class Engine:
         self._check(self._lib.nxsb_engine_pruning_stats(self._h, out, int(reset)))
         st = {"items": out[0], "blocks_scored": out[1], "postings_scored": out[2], "rounds": out[3]}
         if any(out[4:12]):      # -DBMW_PROF build: cycles of thread 0 per phase
-            names = ["bounds", "bounds_short_lists", "select", "score", "cut", "emit_merge", "item_setup", "seed"]
+            names = ["bound_select", "bounds_short_lists", "pick", "score", "cut", "emit_merge", "item_setup"]
             st["phase_cycles"] = {n: out[4 + i] for i, n in enumerate(names)}
-            st["live_superblocks"], st["items_all_pruned"], st["live_blocks_seen"] = out[12], out[13], out[14]
         return st
 
     def __del__(self):  # pragma: no cover - best effort

@@ -14,7 +14,7 @@ from _oracle import BM25, TFIDF, OP_OR, check_topk
 
 pytestmark = pytest.mark.gpu
 
-N_DOCS = 300_000      # 19 tiles, 4688 blocks of 64 documents
+N_DOCS = 300_000      # 19 tiles, 9375 blocks of 32 documents (two chunks)
 N_TERMS = 50_000
 
 
@@ -131,7 +131,7 @@ def test_many_terms_rare_terms_and_odd_ids(corpus, oracle, eng):
                            exact_scores=(algo == TFIDF))
 
 
-@pytest.mark.parametrize("shift", [5, 7, 8])
+@pytest.mark.parametrize("shift", [6, 7, 8])
 def test_other_block_sizes(corpus, eng, shift):
     from nxsearch_b200 import engine
 
