@@ -219,6 +219,15 @@ int		nxsb_engine_load_vocab(nxsb_engine_t *, uint32_t n_terms,
 		    const uint8_t *bk_edge, const uint32_t *bk_rank);
 
 /*
+ * The per-term occurrence totals moved (documents added or removed; the
+ * vocabulary is the one of the last load_vocab): fuzzy matching only picks
+ * terms whose total is non-zero (ref src/index/idxterm.c:239, which reads the
+ * mapped counter at search time).
+ */
+int		nxsb_engine_update_term_totals(nxsb_engine_t *, uint32_t n_terms,
+		    const uint64_t *term_total);
+
+/*
  * Fuzzy-resolve n query strings (NUL-free byte strings q[i] = qblob +
  * qoff[i] .. qoff[i+1]) against the whole vocabulary: out_term[i] = the term
  * id the reference's idxterm_fuzzysearch would return (0 = none),

@@ -47,7 +47,9 @@
 #define BMW_WARPS	(BMW_THREADS / 32)
 #define BMW_CH_BLOCKS	8192u			/* blocks per chunk */
 #define BMW_PER_THREAD	(BMW_CH_BLOCKS / BMW_THREADS)
+#ifndef BMW_CAND
 #define BMW_CAND	1024u			/* candidate keys per item */
+#endif
 #define BMW_SEL		512u			/* blocks selected per round */
 #define BMW_K_MAX	128u			/* limit served by this kernel */
 #define BMW_HIST	64u
@@ -537,11 +539,23 @@ score_bmw_kernel(const BmwParams p)
 
 			if (total) {
 				if (lane == 0) {
-					at = atomicAdd(&s_ncand, total);
-					if (at + total > BMW_CAND) {
-						atomicSub(&s_ncand, total);
-						s_overflow = 1;
-						at = 0xffffffffu;
+					/*
+					 * Compare-and-swap, not add-then-undo: a failed
+					 * reservation must never be visible, or a later
+					 * one lands past the keys that end up counted.
+					 */
+					uint32_t seen = *(volatile uint32_t *)&s_ncand;
+
+					for (;;) {
+						if (seen + total > BMW_CAND) {
+							s_overflow = 1;
+							at = 0xffffffffu;
+							break;
+						}
+						at = atomicCAS(&s_ncand, seen, seen + total);
+						if (at == seen)
+							break;
+						seen = at;
 					}
 				}
 				at = __shfl_sync(FULL, at, 0);
@@ -743,6 +757,10 @@ score_bmw_kernel(const BmwParams p)
 			for (;;) {
 				uint32_t si = 0;
 
+#ifdef BMW_SERIAL
+				if (warp != 0)
+					break;
+#endif
 				if (lane == 0)
 					si = *(volatile uint32_t *)&s_overflow ? n_round : atomicAdd(&s_next, 1u);
 				si = __shfl_sync(FULL, si, 0);

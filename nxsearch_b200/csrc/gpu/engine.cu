@@ -2350,6 +2350,15 @@ nxsb_engine_load_vocab(nxsb_engine_t *e, uint32_t n_terms, const char *blob,
 }
 
 extern "C" int
+nxsb_engine_update_term_totals(nxsb_engine_t *e, uint32_t n_terms, const uint64_t *term_total)
+{
+	CK(e, cudaSetDevice(e->device));
+	if (fuzzy_update_live(e->fz, n_terms, term_total, e->stream) != 0)
+		return fail(e, "term totals do not match the vocabulary image (%u terms)", n_terms);
+	return 0;
+}
+
+extern "C" int
 nxsb_engine_fuzzy(nxsb_engine_t *e, uint32_t n, const char *qblob,
     const uint32_t *qoff, uint32_t *out_term, uint32_t *out_dist,
     uint32_t *out_true)

@@ -169,6 +169,26 @@ fuzzy_load(FuzzyImage &f, uint32_t V, const char *blob, const uint32_t *off,
 }
 
 /*
+ * The per-term "total > 0" flags again (ref idxterm.c:239 reads the totals
+ * from the mapped file at search time: they move with every add / remove,
+ * also of documents that bring no new term).
+ */
+static int
+fuzzy_update_live(FuzzyImage &f, uint32_t V, const uint64_t *total, cudaStream_t st)
+{
+	if (!f.loaded || V != f.n_terms)
+		return -1;
+	std::vector<unsigned char> live(V ? V : 1);
+
+	for (uint32_t t = 0; t < V; t++)
+		live[t] = total[t] > 0;
+	if (cudaMemcpyAsync(f.d_live, live.data(), V, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+	    cudaStreamSynchronize(st) != cudaSuccess)
+		return -1;
+	return 0;
+}
+
+/*
  * Myers / Hyyro bit-parallel Levenshtein distance: pattern (the query) in
  * the low m bits of a W-bit word, one column update per text byte.
  * peq[c] = bitmask of pattern positions holding byte c.

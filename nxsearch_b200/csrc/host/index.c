@@ -308,6 +308,7 @@ term_total_add(nxs_index_t *idx, uint32_t term_id, int64_t delta)
 		nv = htobe64(cur + delta);
 	} while (!__atomic_compare_exchange_n(tc, &old, nv, true,
 	    __ATOMIC_RELAXED, __ATOMIC_RELAXED));
+	idx->totals_dirty = true;
 }
 
 /*
@@ -549,6 +550,7 @@ doc_register_opt(nxs_index_t *idx, uint64_t id, uint32_t len, uint32_t n,
 	/* Not on the GPU yet: the next search adds a delta segment. */
 	idx->n_pending++;
 	idx->stats_dirty = true;
+	idx->totals_dirty = true;
 	return 0;
 }
 
@@ -602,6 +604,7 @@ doc_unregister(nxs_index_t *idx, uint64_t id)
 	/* Only the id of a removed block is cleared; its terms stay readable. */
 	df_apply(idx, idx->doc_blk[slot], idx->doc_n[slot], -1);
 	idx->stats_dirty = true;
+	idx->totals_dirty = true;
 	if (slot >= idx->built_slots) {
 		idx->n_pending--;
 	} else {
@@ -1312,9 +1315,37 @@ build_vocab(nxs_index_t *idx)
 		    nxsb_engine_errmsg(idx->engine));
 		goto out;
 	}
-	idx->vocab_dirty = false;
+	idx->vocab_dirty = idx->totals_dirty = false;
 	ret = 0;
 out:
+	free(totals);
+	return ret;
+}
+
+/*
+ * The vocabulary on the GPU is current but documents came or went: the
+ * "total > 0" flags of the fuzzy matcher follow the counters in nxsterms
+ * (ref idxterm.c:239 reads them at search time).
+ */
+static int
+refresh_term_totals(nxs_index_t *idx)
+{
+	uint64_t *totals = malloc(sizeof(uint64_t) * ((size_t)idx->n_terms + 1));
+	int ret = -1;
+
+	if (!totals) {
+		nxs_set_syserror(idx->nxs, NXS_ERR_SYSTEM, "out of memory");
+		return -1;
+	}
+	for (uint32_t t = 1; t <= idx->n_terms; t++)
+		totals[t - 1] = idx_term_total(idx, t);
+	if (nxsb_engine_update_term_totals(idx->engine, idx->n_terms, totals) == -1) {
+		nxs_set_error(idx->nxs, NXS_ERR_SYSTEM, "GPU vocabulary refresh failed: %s",
+		    nxsb_engine_errmsg(idx->engine));
+	} else {
+		idx->totals_dirty = false;
+		ret = 0;
+	}
 	free(totals);
 	return ret;
 }
@@ -1336,6 +1367,8 @@ idx_gpu_prepare(nxs_index_t *idx, bool need_vocab)
 	    refresh_image(idx) == -1)
 		return -1;
 	if (need_vocab && idx->vocab_dirty && idx->n_terms && build_vocab(idx) == -1)
+		return -1;
+	if (need_vocab && idx->totals_dirty && idx->n_terms && refresh_term_totals(idx) == -1)
 		return -1;
 	return 0;
 }

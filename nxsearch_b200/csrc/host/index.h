@@ -81,6 +81,7 @@ struct nxs_index {
 	bool			image_dirty;	/* nothing usable on the GPU: build it all */
 	bool			stats_dirty;	/* df[] / header counters moved */
 	bool			vocab_dirty;
+	bool			totals_dirty;	/* term totals moved since the vocabulary upload */
 	uint8_t *		doc_seg;	/* per slot; valid below built_slots */
 	uint32_t		built_slots;	/* slots the image knows of */
 	uint32_t		n_pending;	/* live slots at or above built_slots */

@@ -19,7 +19,11 @@
 
 #include "index.h"
 
-static const char *default_filters[] = { "normalizer", "stopwords", "stemmer" };
+/*
+ * ref nxs.c:249-268 adds "stemmer" as well; this build has no Snowball and
+ * refuses the filter rather than pass terms through silently (tokenizer.c).
+ */
+static const char *default_filters[] = { "normalizer", "stopwords" };
 
 int
 str_isalnumdu(const char *s)
@@ -192,7 +196,7 @@ nxs_index_create(nxs_t *nxs, const char *name, nxs_params_t *params)
 	}
 	filters = nxs_params_get_strlist(params, "filters", &nfilters);
 	if (!filters && nxs_params_set_strlist(params, "filters",
-	    default_filters, 3) == -1)
+	    default_filters, sizeof(default_filters) / sizeof(default_filters[0])) == -1)
 		goto out;
 	if (!nxs_params_get_str(params, "algo") &&
 	    nxs_params_set_str(params, "algo", NXS_DEFAULT_RANKING_ALGO) == -1)

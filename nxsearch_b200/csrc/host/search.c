@@ -138,6 +138,24 @@ emit_program(const prepared_t *pq, int32_t node, int32_t *prog, uint32_t *n)
 	    nd->type == QN_OR ? NXSB_OP_OR : NXSB_OP_ANDNOT;
 }
 
+/*
+ * Operand stack the postfix program of emit_program() needs: the engine
+ * evaluates it with a fixed stack (engine.cu validate_batch), and a query that
+ * does not fit must fail on its own, not take the batch down.
+ */
+static uint32_t
+program_stack_depth(const prepared_t *pq, int32_t node)
+{
+	const qnode_t *nd = &pq->tree.nodes[node];
+
+	if (nd->type == QN_VALUE)
+		return 1;
+	const uint32_t l = program_stack_depth(pq, nd->left);
+	const uint32_t r = program_stack_depth(pq, nd->right) + 1;
+
+	return l > r ? l : r;
+}
+
 static void
 prepared_release(prepared_t *pq)
 {
@@ -395,7 +413,8 @@ nxs_index_search_batch_begin(nxs_index_t *idx, nxs_params_t *params,
 			continue;
 		}
 		if (pq[i].n_resolved > NXSB_MAX_QUERY_TOKENS ||
-		    (uint32_t)pq[i].tree.n_nodes > NXSB_MAX_QUERY_PROG) {
+		    (uint32_t)pq[i].tree.n_nodes > NXSB_MAX_QUERY_PROG ||
+		    program_stack_depth(&pq[i], pq[i].tree.root) > NXSB_MAX_QUERY_TOKENS + 1) {
 			nxs_set_error(nxs, NXS_ERR_LIMIT, "query too large for the GPU "
 			    "engine (%u terms, %d nodes; limits %u / %u)",
 			    pq[i].n_resolved, pq[i].tree.n_nodes,

@@ -2,6 +2,7 @@
  * Text front end; see tokenizer.h.
  */
 #define _GNU_SOURCE
+#include <stdbool.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -66,6 +67,34 @@ filter_pipeline_create(nxs_t *nxs, nxs_params_t *params)
 			free(names);
 			free(fp);
 			return NULL;
+		}
+		/*
+		 * No Snowball in this build: a pipeline that names the stemmer
+		 * would index and query UNSTEMMED terms under parameters that
+		 * promise stemmed ones (and miss the terms of an index the
+		 * reference built).  That is an error, not a silent pass-through;
+		 * NXSB_STEMMER_PASSTHROUGH=1 accepts it knowingly (identity
+		 * stemmer -- what the tests' compiled reference is built with).
+		 */
+		if (kind == FILT_STEMMER) {
+			const char *ok = getenv("NXSB_STEMMER_PASSTHROUGH");
+			static bool warned;
+
+			if (!ok || strcmp(ok, "1") != 0) {
+				nxs_set_error(nxs, NXS_ERR_INVALID,
+				    "filter `stemmer' is not available in this build (no "
+				    "Snowball); drop it from `filters' or set "
+				    "NXSB_STEMMER_PASSTHROUGH=1 to index unstemmed terms");
+				free(names);
+				strmap_destroy(fp->stopwords);
+				free(fp);
+				return NULL;
+			}
+			if (!warned) {
+				warned = true;
+				fprintf(stderr, "nxsearch-b200: warning: the `stemmer' filter "
+				    "passes terms through unchanged (NXSB_STEMMER_PASSTHROUGH=1)\n");
+			}
 		}
 		fp->kinds[fp->count++] = kind;
 		if (kind == FILT_STOPWORDS && !fp->stopwords)

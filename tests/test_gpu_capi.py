@@ -338,3 +338,57 @@ def test_committed_reference_goldens_through_the_c_api(c1_corpus, c1_both):
     # ... and one the reference found nothing for stays empty
     misses = [q for q, p in zip(g.fuzzy_queries, g.fuzzy_pick.tolist()) if not p][:20]
     assert all(r == [] for r in ours.search_batch(misses, limit=10, algo="TF-IDF", fuzzymatch=True))
+
+
+def test_fuzzy_follows_term_totals_after_remove_and_readd(nxs):
+    """The fuzzy pick skips terms whose total count is 0 (ref idxterm.c:239 reads
+    the counter at search time).  Totals move with every add / remove, also when
+    no new term appears: after the only document of a term is removed a
+    misspelling must resolve to another candidate (or to nothing), and a term
+    that is used again must be picked again.  Same files through the reference."""
+    idx = nxs.create_index("fz")
+    idx.add(1, "alpha betas gamma")
+    idx.add(2, "alpha betaz delta")
+    idx.add(3, "alpha omega")
+    ref = _oracle.ref()
+
+    def agree(q):
+        got = idx.search(q, limit=10, algo="BM25")
+        if ref is not None:
+            rn = capi.Nxs(nxs.base, lib=ref)
+            ridx = rn.open_index("fz")
+            same_results(got, ridx.search(q, limit=10, algo="BM25"))
+            ridx.close()
+            rn.close()
+        return [d for d, _ in got]
+
+    first = agree("betax")                  # distance 1 from both betas and betaz
+    assert first in ([1], [2])
+    idx.remove(first[0])                    # its term's total drops to 0, no term is added
+    second = agree("betax")
+    assert second == [3 - first[0]], "the fuzzy pick still names a term without documents"
+    idx.remove(second[0])
+    assert agree("betax") == []             # both candidates are dead now
+    idx.add(7, "betas again")               # an EXISTING term gets a document back
+    assert agree("betax") == [7]
+    idx.close()
+
+
+def test_one_oversized_query_does_not_take_the_batch_down(nxs):
+    """a right-nested query whose postfix program needs a deeper
+    operand stack than the engine has (one repeated term: 1 token, ~80 nodes)
+    passes the token and node limits; it must fail alone with NXS_ERR_LIMIT."""
+    idx = nxs.create_index("deep")
+    for d in range(1, 30):
+        idx.add(d, f"aa bb{d % 3} cc")
+    deep = "aa" + "".join(" AND (aa" for _ in range(40)) + ")" * 40
+    res = idx.search_batch(["aa", deep, "bb1 OR cc"], limit=50)
+    assert res[1] is None and nxs.error()[0] == capi.ERR_LIMIT
+    assert len(res[0]) == 29 and len(res[2]) == 29
+    with pytest.raises(capi.NxsError) as e:
+        idx.search(deep)
+    assert e.value.code == capi.ERR_LIMIT
+    # nesting the engine does hold still works
+    ok = "aa" + "".join(" AND (aa" for _ in range(20)) + ")" * 20
+    assert len(idx.search(ok, limit=50)) == 29
+    idx.close()

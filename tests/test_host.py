@@ -168,7 +168,8 @@ def test_reader_roundtrip_and_deletion_markers(tmp_path, c1_corpus):
 
 def test_index_lifecycle_and_error_codes(nxs):
     idx = nxs.create_index("main")
-    assert idx.params_json() == {"filters": ["normalizer", "stopwords", "stemmer"], "algo": "BM25", "lang": "en"}
+    # the reference's defaults minus the stemmer, which this build does not have
+    assert idx.params_json() == {"filters": ["normalizer", "stopwords"], "algo": "BM25", "lang": "en"}
     with pytest.raises(capi.NxsError) as e:
         nxs.create_index("main")
     assert e.value.code == capi.ERR_EXISTS
@@ -254,6 +255,26 @@ def test_index_files_are_interchangeable_with_the_reference(nxs, c1_corpus):
         rn.close()
     finally:
         shutil.rmtree(rbase, ignore_errors=True)
+
+
+def test_stemmer_is_refused_loudly_not_passed_through(nxs, monkeypatch):
+    """a pipeline naming `stemmer' must not silently index unstemmed
+    terms.  Creating or opening such an index fails with NXS_ERR_INVALID unless
+    the caller opts in to the identity stemmer."""
+    monkeypatch.delenv("NXSB_STEMMER_PASSTHROUGH", raising=False)
+    with pytest.raises(capi.NxsError) as e:
+        nxs.create_index("s", filters=["normalizer", "stemmer"])
+    assert e.value.code == capi.ERR_INVALID and "stemmer" in str(e.value)
+    # an index the reference created with ITS defaults names the stemmer too
+    (Path(nxs.base) / "data/s/params.db").write_text(
+        json.dumps({"filters": ["normalizer", "stopwords", "stemmer"], "algo": "BM25", "lang": "en"}))
+    with pytest.raises(capi.NxsError) as e:
+        nxs.open_index("s")
+    assert e.value.code == capi.ERR_INVALID
+    monkeypatch.setenv("NXSB_STEMMER_PASSTHROUGH", "1")
+    idx = nxs.open_index("s")
+    assert idx.params_json()["filters"] == ["normalizer", "stopwords", "stemmer"]
+    idx.close()
 
 
 def test_every_declared_symbol_is_exported():
