@@ -157,14 +157,17 @@ static int32_t
 new_node(qtree_t *t, qnode_type_t type, int32_t l, int32_t r, char *value)
 {
 	if (t->n_nodes == t->cap) {
-		const int32_t ncap = t->cap ? t->cap * 2 : 16;
-		qnode_t *nn = realloc(t->nodes, sizeof(qnode_t) * ncap);
+		const int32_t ncap = t->cap * 2;
+		qnode_t *nn = t->nodes == t->inl ? malloc(sizeof(qnode_t) * ncap)
+		    : realloc(t->nodes, sizeof(qnode_t) * ncap);
 
 		if (!nn) {
 			free(value);
 			t->error = true;
 			return -1;
 		}
+		if (t->nodes == t->inl)
+			memcpy(nn, t->inl, sizeof(qnode_t) * t->n_nodes);
 		t->nodes = nn;
 		t->cap = ncap;
 	}
@@ -242,7 +245,9 @@ static unsigned
 tree_depth(const qtree_t *t)
 {
 	/* Children always precede their parent in the node array. */
-	unsigned *d = calloc(t->n_nodes ? t->n_nodes : 1, sizeof(unsigned));
+	unsigned small[QTREE_INLINE_NODES] = { 0 };
+	unsigned *d = t->n_nodes <= QTREE_INLINE_NODES ? small
+	    : calloc(t->n_nodes, sizeof(unsigned));
 	unsigned max = 0;
 
 	if (!d)
@@ -256,7 +261,8 @@ tree_depth(const qtree_t *t)
 			d[n->left] = d[n->right] = d[i] + 1;
 		}
 	}
-	free(d);
+	if (d != small)
+		free(d);
 	return max;
 }
 
@@ -266,7 +272,12 @@ qtree_parse(qtree_t *t, const char *query)
 	qparser_t ps = { .tree = t };
 	int32_t root, r;
 
-	memset(t, 0, sizeof(*t));
+	t->nodes = t->inl;
+	t->n_nodes = 0;
+	t->cap = QTREE_INLINE_NODES;
+	t->depth = 0;
+	t->error = false;
+	t->errmsg = NULL;
 	t->root = -1;
 	qlex_init(&ps.lx, query);
 	parser_advance(&ps);
@@ -299,9 +310,12 @@ qtree_free(qtree_t *t)
 {
 	for (int32_t i = 0; i < t->n_nodes; i++)
 		free(t->nodes[i].value);
-	free(t->nodes);
+	if (t->nodes != t->inl)
+		free(t->nodes);
 	free(t->errmsg);
-	memset(t, 0, sizeof(*t));
+	t->nodes = NULL;
+	t->n_nodes = t->cap = 0;
+	t->errmsg = NULL;
 	t->root = -1;
 }
 

@@ -48,8 +48,11 @@ typedef struct {
 	size_t		len;		/* its source length incl. quotes */
 } qlexer_t;
 
+#define QTREE_INLINE_NODES	12	/* a typical query never allocates its node array */
+
 typedef struct {
 	qnode_t *	nodes;
+	qnode_t		inl[QTREE_INLINE_NODES];
 	int32_t		n_nodes, cap;
 	int32_t		root;		/* -1 when empty / failed */
 	unsigned	depth;		/* deepest node, root = 0 */

@@ -20,39 +20,33 @@
 struct nxs_resp {
 	uint32_t	count;
 	uint32_t	iter;
-	uint64_t *	ids;
+	uint64_t *	ids;		/* both arrays live behind the header */
 	float *		scores;
 };
 
 nxs_resp_t *
 nxs_resp_from_arrays(const uint64_t *ids, const float *scores, uint32_t n)
 {
-	nxs_resp_t *r = calloc(1, sizeof(*r));
+	/* One allocation per response: header | ids[n] | scores[n]. */
+	nxs_resp_t *r = malloc(sizeof(*r) + (size_t)n * (sizeof(uint64_t) + sizeof(float)));
 
 	if (!r)
 		return NULL;
-	r->ids = malloc(sizeof(uint64_t) * (n ? n : 1));
-	r->scores = malloc(sizeof(float) * (n ? n : 1));
-	if (!r->ids || !r->scores) {
-		nxs_resp_release(r);
-		return NULL;
-	}
+	r->ids = (uint64_t *)(r + 1);
+	r->scores = (float *)(r->ids + n);
 	if (n) {
 		memcpy(r->ids, ids, sizeof(uint64_t) * n);
 		memcpy(r->scores, scores, sizeof(float) * n);
 	}
 	r->count = n;
+	r->iter = 0;
 	return r;
 }
 
 NXS_API void
 nxs_resp_release(nxs_resp_t *r)
 {
-	if (r) {
-		free(r->ids);
-		free(r->scores);
-		free(r);
-	}
+	free(r);
 }
 
 NXS_API void

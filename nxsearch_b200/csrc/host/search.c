@@ -28,22 +28,6 @@ typedef struct {
 	bool		fuzzymatch;
 } search_params_t;
 
-typedef struct {
-	qtree_t		tree;
-	tokenset_t *	tokens;
-	int32_t *	slot_map;	/* token slot -> compacted slot, -1 = trimmed */
-	uint32_t	n_resolved;
-	uint32_t	n_miss;		/* tokens without an exact term */
-	bool		failed;
-	/* Error of this query, reported in query order after the workers join. */
-	nxs_err_t	err_code;
-	char *		err_msg;
-} prepared_t;
-
-/* Queries per worker below which threads are not worth starting. */
-#define PREP_MIN_PER_THREAD	128
-#define PREP_MAX_THREADS	16
-
 static int
 get_search_params(nxs_index_t *idx, nxs_params_t *params, search_params_t *sp)
 {
@@ -78,22 +62,145 @@ get_search_params(nxs_index_t *idx, nxs_params_t *params, search_params_t *sp)
 }
 
 /*
+ * The host half of a batch is parse + tokenize + exact term lookup per query,
+ * independent read-only work: it is spread over a persistent pool of worker
+ * threads, each building the descriptors, token ids and programs of its share
+ * of the queries in its own buffers; the shares are then laid end to end.
+ * A typical query allocates nothing but its leaf strings.
+ */
+
+/* The distinct tokens of one query, in token-list order (<= the engine's limit). */
+typedef struct {
+	struct {
+		const char *	str;
+		uint32_t	len;
+		uint32_t	term_id;	/* 0 = no exact term */
+	} tok[NXSB_MAX_QUERY_TOKENS];
+	uint32_t	count;
+	bool		overflow;	/* more distinct tokens than the engine takes */
+	char		buf[640];	/* filtered strings; longer ones go to the heap */
+	uint32_t	used;
+	char *		heap[NXSB_MAX_QUERY_TOKENS];
+	uint32_t	n_heap;
+} qtokens_t;
+
+typedef struct {
+	nxs_err_t	code;
+	char *		msg;
+} qerror_t;
+
+/* One worker's share of a batch: queries [lo, hi). */
+typedef struct {
+	size_t		lo, hi;
+	uint32_t *	tokens;
+	int32_t *	prog;
+	uint32_t	n_tok, cap_tok, n_prog, cap_prog;
+	/* tokens without an exact term (fuzzymatch): position in tokens[] + string */
+	uint32_t *	miss_pos;
+	uint32_t *	miss_off;	/* [n_miss + 1] into miss_blob */
+	char *		miss_blob;
+	uint32_t	n_miss, cap_miss, blob_len, blob_cap;
+	size_t		n_run;
+	bool		oom;
+} share_t;
+
+typedef struct {
+	nxs_index_t *		idx;
+	const search_params_t *	sp;
+	const char *const *	queries;
+	size_t			n;
+	nxsb_query_t *		descs;		/* [n], offsets relative to the share */
+	qerror_t *		errs;		/* [n], code 0 = fine */
+	share_t *		shares;
+} prep_job_t;
+
+/* Queries per worker below which threads are not worth waking. */
+#define PREP_MIN_PER_THREAD	64
+#define PREP_MAX_THREADS	16
+
+static void
+query_fail(qerror_t *e, nxs_err_t code, const char *fmt, ...)
+{
+	va_list ap;
+
+	e->code = code;
+	va_start(ap, fmt);
+	if (vasprintf(&e->msg, fmt, ap) == -1)
+		e->msg = NULL;
+	va_end(ap);
+}
+
+/*
+ * One leaf through the filter pipeline into the query's token list
+ * (tokenizer.c tokenize_value without the allocations): *slot = its index, or
+ * -1 if a filter discarded it.
+ */
+static int
+leaf_token(const filter_pipeline_t *fp, qtokens_t *qt, const char *val,
+    size_t len, int32_t *slot)
+{
+	char *buf;
+	bool on_heap = false;
+
+	*slot = -1;
+	if (qt->used + len + 1 <= sizeof(qt->buf)) {
+		buf = qt->buf + qt->used;
+	} else {
+		if ((buf = malloc(len + 1)) == NULL)
+			return -1;
+		on_heap = true;
+	}
+	memcpy(buf, val, len);
+	buf[len] = '\0';
+	if (!filter_apply(fp, buf, &len)) {
+		if (on_heap)
+			free(buf);
+		return 0;
+	}
+	/* Same string, same token: scored once (ref tokenizer.c:94-117). */
+	for (uint32_t i = 0; i < qt->count; i++) {
+		if (qt->tok[i].len == len && memcmp(qt->tok[i].str, buf, len) == 0) {
+			if (on_heap)
+				free(buf);
+			*slot = (int32_t)i;
+			return 0;
+		}
+	}
+	if (qt->count == NXSB_MAX_QUERY_TOKENS) {
+		if (on_heap)
+			free(buf);
+		qt->overflow = true;
+		return 0;
+	}
+	if (on_heap)
+		qt->heap[qt->n_heap++] = buf;
+	else
+		qt->used += len + 1;
+	qt->tok[qt->count].str = buf;
+	qt->tok[qt->count].len = len;
+	qt->tok[qt->count].term_id = 0;
+	*slot = (int32_t)qt->count++;
+	return 0;
+}
+
+/*
  * query_prepare (ref query.c:75-115): walk the tree with a LIFO so that the
  * RIGHT-most leaf is tokenized first; the order of first appearance in that
  * walk is the token-list order, i.e. the score summation order.
  */
 static int
-prepare_query(filter_pipeline_t *fp, prepared_t *pq)
+prepare_query(const filter_pipeline_t *fp, qtree_t *t, qtokens_t *qt)
 {
-	qtree_t *t = &pq->tree;
-	int32_t *stack;
+	int32_t small[2 * QTREE_INLINE_NODES + 2], *stack = small;
 	int32_t sp = 0;
+	int ret = 0;
 
-	if ((pq->tokens = tokenset_create()) == NULL)
-		return -1;
+	qt->count = qt->used = qt->n_heap = 0;
+	qt->overflow = false;
 	if (t->root < 0)
 		return 0;
-	if ((stack = malloc(sizeof(int32_t) * (t->n_nodes + 1))) == NULL)
+	if (t->n_nodes > 2 * QTREE_INLINE_NODES &&
+	    (stack = malloc(sizeof(int32_t) * (t->n_nodes + 1))) == NULL)
 		return -1;
 	stack[sp++] = t->root;
 	while (sp) {
@@ -104,36 +211,35 @@ prepare_query(filter_pipeline_t *fp, prepared_t *pq)
 			stack[sp++] = n->right;
 			continue;
 		}
-		if (tokenize_value(fp, pq->tokens, n->value, strlen(n->value),
-		    &n->token) == -1) {
-			free(stack);
-			return -1;
+		if (leaf_token(fp, qt, n->value, strlen(n->value), &n->token) == -1) {
+			ret = -1;
+			break;
 		}
 	}
-	free(stack);
-	return 0;
+	if (stack != small)
+		free(stack);
+	return ret;
 }
 
 /* Post-order emission of the boolean program (depth is bounded by then). */
 static void
-emit_program(const prepared_t *pq, int32_t node, int32_t *prog, uint32_t *n)
+emit_program(const qtree_t *t, int32_t node, int32_t *prog, uint32_t *n)
 {
-	const qnode_t *nd = &pq->tree.nodes[node];
+	const qnode_t *nd = &t->nodes[node];
 
 	if (nd->type == QN_VALUE) {
-		const int32_t slot = nd->token >= 0 ? pq->slot_map[nd->token] : -1;
-
 		/*
-		 * A leaf without a usable term is the empty set.  The reference
-		 * does this for filter-discarded leaves (search.c:133-141); for
-		 * unresolved ones it reads freed memory -- the
-		 * empty set is the defined behaviour here.
+		 * A leaf a filter discarded is the empty set (ref search.c:
+		 * 133-141).  A leaf without a term keeps its slot with term id
+		 * 0, which the engine treats as an empty list -- the reference
+		 * reads freed memory there; the empty set is the
+		 * defined behaviour here.
 		 */
-		prog[(*n)++] = slot >= 0 ? slot : NXSB_OP_EMPTY;
+		prog[(*n)++] = nd->token >= 0 ? nd->token : NXSB_OP_EMPTY;
 		return;
 	}
-	emit_program(pq, nd->left, prog, n);
-	emit_program(pq, nd->right, prog, n);
+	emit_program(t, nd->left, prog, n);
+	emit_program(t, nd->right, prog, n);
 	prog[(*n)++] = nd->type == QN_AND ? NXSB_OP_AND :
 	    nd->type == QN_OR ? NXSB_OP_OR : NXSB_OP_ANDNOT;
 }
@@ -144,117 +250,239 @@ emit_program(const prepared_t *pq, int32_t node, int32_t *prog, uint32_t *n)
  * does not fit must fail on its own, not take the batch down.
  */
 static uint32_t
-program_stack_depth(const prepared_t *pq, int32_t node)
+program_stack_depth(const qtree_t *t, int32_t node)
 {
-	const qnode_t *nd = &pq->tree.nodes[node];
+	const qnode_t *nd = &t->nodes[node];
 
 	if (nd->type == QN_VALUE)
 		return 1;
-	const uint32_t l = program_stack_depth(pq, nd->left);
-	const uint32_t r = program_stack_depth(pq, nd->right) + 1;
+	const uint32_t l = program_stack_depth(t, nd->left);
+	const uint32_t r = program_stack_depth(t, nd->right) + 1;
 
 	return l > r ? l : r;
 }
 
-static void
-prepared_release(prepared_t *pq)
+static int
+share_reserve(share_t *sh, uint32_t ntok, uint32_t nprog, uint32_t nmiss, uint32_t nblob)
 {
-	qtree_free(&pq->tree);
-	tokenset_destroy(pq->tokens);
-	free(pq->slot_map);
-	free(pq->err_msg);
-}
+#define GROW(ptr, cap, need, type) do {						\
+	if ((need) > (cap)) {							\
+		const uint32_t _nc = (need) + (need) / 2 + 64;			\
+		type *_p = realloc((ptr), sizeof(type) * _nc);			\
+		if (!_p)							\
+			return -1;						\
+		(ptr) = _p;							\
+		(cap) = _nc;							\
+	}									\
+} while (0)
+	GROW(sh->tokens, sh->cap_tok, sh->n_tok + ntok, uint32_t);
+	GROW(sh->prog, sh->cap_prog, sh->n_prog + nprog, int32_t);
+	if (nmiss) {
+		const uint32_t need = sh->n_miss + nmiss + 1;
 
-static void
-prep_fail(prepared_t *pq, nxs_err_t code, const char *fmt, ...)
-{
-	va_list ap;
+		if (need > sh->cap_miss) {
+			const uint32_t nc = need + need / 2 + 16;
+			uint32_t *a = realloc(sh->miss_pos, sizeof(uint32_t) * nc);
+			uint32_t *b = a ? realloc(sh->miss_off, sizeof(uint32_t) * nc) : NULL;
 
-	pq->failed = true;
-	pq->err_code = code;
-	va_start(ap, fmt);
-	if (vasprintf(&pq->err_msg, fmt, ap) == -1)
-		pq->err_msg = NULL;
-	va_end(ap);
-}
-
-/* Steps 1-3 of one query: parse, query_prepare, tokenset_resolve (exact). */
-static void
-prepare_one(nxs_index_t *idx, const search_params_t *sp, const char *query,
-    prepared_t *pq)
-{
-	qtree_parse(&pq->tree, query);
-	if (pq->tree.error) {
-		prep_fail(pq, NXS_ERR_INVALID, "query failed with %s",
-		    pq->tree.errmsg ? pq->tree.errmsg : "out of memory");
-		return;
+			if (a)
+				sh->miss_pos = a;
+			if (b)
+				sh->miss_off = b;
+			if (!a || !b)
+				return -1;
+			sh->cap_miss = nc;
+		}
+		GROW(sh->miss_blob, sh->blob_cap, sh->blob_len + nblob, char);
 	}
-	if (prepare_query(idx->fp, pq) == -1) {
-		prep_fail(pq, NXS_ERR_FATAL, "query_prepare() failed");
-		return;
+#undef GROW
+	return 0;
+}
+
+/*
+ * Everything the host does for one query (ref search.c:285-342 up to
+ * run_query_logic): parse, query_prepare, exact tokenset_resolve, the limits,
+ * and its part of the batch arrays.
+ */
+static void
+prepare_one(const prep_job_t *job, share_t *sh, size_t i)
+{
+	const nxs_index_t *idx = job->idx;
+	nxsb_query_t *d = &job->descs[i];
+	qerror_t *err = &job->errs[i];
+	qtree_t tree;
+	qtokens_t qt;
+	uint32_t n_resolved = 0, n_miss = 0, miss_bytes = 0, np = 0;
+
+	qt.n_heap = 0;
+	qtree_parse(&tree, job->queries[i]);
+	if (tree.error) {
+		query_fail(err, NXS_ERR_INVALID, "query failed with %s",
+		    tree.errmsg ? tree.errmsg : "out of memory");
+		goto out;
+	}
+	if (prepare_query(idx->fp, &tree, &qt) == -1) {
+		query_fail(err, NXS_ERR_FATAL, "query_prepare() failed");
+		goto out;
 	}
 	/* tokenset_resolve (tokenizer.c:160-199): exact lookups. */
-	for (uint32_t j = 0; j < pq->tokens->count; j++) {
-		token_t *t = &pq->tokens->list[j];
-
-		t->term_id = idx_term_lookup(idx, t->str, t->len);
-		if (!t->term_id && sp->fuzzymatch)
-			pq->n_miss++;
+	for (uint32_t j = 0; j < qt.count; j++) {
+		qt.tok[j].term_id = idx_term_lookup(idx, qt.tok[j].str, qt.tok[j].len);
+		if (qt.tok[j].term_id) {
+			n_resolved++;
+		} else if (job->sp->fuzzymatch) {
+			n_miss++;
+			miss_bytes += qt.tok[j].len;
+		}
 	}
+	/* search.c:224-226: nothing usable => empty result, no error. */
+	if (tree.root < 0 || (n_resolved == 0 && n_miss == 0))
+		goto out;
+	/* search.c:126-131 (the recursion guard of get_expr_bitmap). */
+	if (tree.depth > NXS_QUERY_RLIMIT) {
+		query_fail(err, NXS_ERR_LIMIT, "query nesting limit reached (%u levels)",
+		    NXS_QUERY_RLIMIT);
+		goto out;
+	}
+	if (qt.overflow || (uint32_t)tree.n_nodes > NXSB_MAX_QUERY_PROG ||
+	    program_stack_depth(&tree, tree.root) > NXSB_MAX_QUERY_TOKENS + 1) {
+		query_fail(err, NXS_ERR_LIMIT, "query too large for the GPU engine "
+		    "(%s%d nodes; limits %u terms / %u nodes)",
+		    qt.overflow ? "too many terms, " : "", tree.n_nodes,
+		    NXSB_MAX_QUERY_TOKENS, NXSB_MAX_QUERY_PROG);
+		goto out;
+	}
+	if (share_reserve(sh, qt.count, (uint32_t)tree.n_nodes, n_miss, miss_bytes) == -1) {
+		sh->oom = true;
+		goto out;
+	}
+	d->tok_off = sh->n_tok;
+	d->n_tokens = qt.count;
+	for (uint32_t j = 0; j < qt.count; j++) {
+		if (!qt.tok[j].term_id && job->sp->fuzzymatch) {
+			sh->miss_pos[sh->n_miss] = sh->n_tok;
+			sh->miss_off[sh->n_miss++] = sh->blob_len;
+			memcpy(sh->miss_blob + sh->blob_len, qt.tok[j].str, qt.tok[j].len);
+			sh->blob_len += qt.tok[j].len;
+		}
+		sh->tokens[sh->n_tok++] = qt.tok[j].term_id;
+	}
+	d->prog_off = sh->n_prog;
+	emit_program(&tree, tree.root, sh->prog + sh->n_prog, &np);
+	d->n_prog = np;
+	sh->n_prog += np;
+	sh->n_run++;
+out:
+	for (uint32_t j = 0; j < qt.n_heap; j++)
+		free(qt.heap[j]);
+	qtree_free(&tree);
 }
 
-typedef struct {
-	nxs_index_t *		idx;
-	const search_params_t *	sp;
-	const char *const *	queries;
-	prepared_t *		pq;
-	size_t			lo, hi;
-} prep_job_t;
+static void
+prepare_share(void *arg, unsigned w, unsigned nw)
+{
+	prep_job_t *job = arg;
+	share_t *sh = &job->shares[w];
+
+	sh->lo = job->n * w / nw;
+	sh->hi = job->n * (w + 1) / nw;
+	for (size_t i = sh->lo; i < sh->hi; i++)
+		prepare_one(job, sh, i);
+}
+
+/*
+ * A small persistent pool: the reference is single-threaded, and so is this
+ * API (one nxs_t per thread); the pool only ever serves one batch at a time
+ * -- a second caller finding it busy does its work itself.
+ */
+typedef void (*pool_fn_t)(void *, unsigned worker, unsigned nworkers);
+
+static struct {
+	pthread_mutex_t	user;		/* one batch at a time */
+	pthread_mutex_t	lock;
+	pthread_cond_t	wake, done;
+	pthread_t	threads[PREP_MAX_THREADS];
+	unsigned	n_threads;	/* started so far */
+	unsigned	generation, helpers, pending;
+	pool_fn_t	fn;
+	void *		arg;
+} g_pool = {
+	.user = PTHREAD_MUTEX_INITIALIZER, .lock = PTHREAD_MUTEX_INITIALIZER,
+	.wake = PTHREAD_COND_INITIALIZER, .done = PTHREAD_COND_INITIALIZER,
+};
 
 static void *
-prepare_worker(void *arg)
+pool_worker(void *arg)
 {
-	prep_job_t *j = arg;
+	const unsigned me = (unsigned)(uintptr_t)arg;
+	unsigned seen = 0;
 
-	for (size_t i = j->lo; i < j->hi; i++)
-		prepare_one(j->idx, j->sp, j->queries[i], &j->pq[i]);
+	pthread_mutex_lock(&g_pool.lock);
+	for (;;) {
+		while (g_pool.generation == seen)
+			pthread_cond_wait(&g_pool.wake, &g_pool.lock);
+		seen = g_pool.generation;
+		if (me >= g_pool.helpers)
+			continue;
+		pool_fn_t fn = g_pool.fn;
+		void *a = g_pool.arg;
+		const unsigned nw = g_pool.helpers + 1;
+
+		pthread_mutex_unlock(&g_pool.lock);
+		fn(a, me + 1, nw);
+		pthread_mutex_lock(&g_pool.lock);
+		if (--g_pool.pending == 0)
+			pthread_cond_signal(&g_pool.done);
+	}
 	return NULL;
 }
 
-static void
-prepare_all(nxs_index_t *idx, const search_params_t *sp,
-    const char *const *queries, size_t n, prepared_t *pq)
+/* Run fn(arg, w, nw) for w in [0, nw) with nw <= want; returns nw. */
+static unsigned
+pool_run(unsigned want, pool_fn_t fn, void *arg, unsigned (*plan)(void *, unsigned))
 {
-	pthread_t tid[PREP_MAX_THREADS];
-	prep_job_t job[PREP_MAX_THREADS];
-	long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
-	size_t nt = n / PREP_MIN_PER_THREAD;
+	unsigned helpers;
 
-	if (ncpu < 1)
-		ncpu = 1;
-	if (nt > (size_t)ncpu)
-		nt = ncpu;
-	if (nt > PREP_MAX_THREADS)
-		nt = PREP_MAX_THREADS;
-	if (nt < 2) {
-		prep_job_t all = { idx, sp, queries, pq, 0, n };
-
-		prepare_worker(&all);
-		return;
+	if (want < 2 || pthread_mutex_trylock(&g_pool.user) != 0) {
+		plan(arg, 1);
+		fn(arg, 0, 1);
+		return 1;
 	}
-	bool started[PREP_MAX_THREADS] = { false };
-
-	for (size_t t = 0; t < nt; t++) {
-		job[t] = (prep_job_t){ idx, sp, queries, pq, n * t / nt, n * (t + 1) / nt };
-		/* The caller takes the last share, and any share whose thread fails to start. */
-		if (t + 1 < nt)
-			started[t] = pthread_create(&tid[t], NULL, prepare_worker, &job[t]) == 0;
-		if (!started[t])
-			prepare_worker(&job[t]);
+	pthread_mutex_lock(&g_pool.lock);
+	while (g_pool.n_threads < want - 1 && g_pool.n_threads < PREP_MAX_THREADS) {
+		if (pthread_create(&g_pool.threads[g_pool.n_threads], NULL, pool_worker,
+		    (void *)(uintptr_t)g_pool.n_threads) != 0)
+			break;
+		pthread_detach(g_pool.threads[g_pool.n_threads]);
+		g_pool.n_threads++;
 	}
-	for (size_t t = 0; t < nt; t++)
-		if (started[t])
-			pthread_join(tid[t], NULL);
+	helpers = want - 1 < g_pool.n_threads ? want - 1 : g_pool.n_threads;
+	plan(arg, helpers + 1);
+	g_pool.fn = fn;
+	g_pool.arg = arg;
+	g_pool.helpers = helpers;
+	g_pool.pending = helpers;
+	g_pool.generation++;
+	pthread_cond_broadcast(&g_pool.wake);
+	pthread_mutex_unlock(&g_pool.lock);
+
+	fn(arg, 0, helpers + 1);
+
+	pthread_mutex_lock(&g_pool.lock);
+	while (g_pool.pending)
+		pthread_cond_wait(&g_pool.done, &g_pool.lock);
+	pthread_mutex_unlock(&g_pool.lock);
+	pthread_mutex_unlock(&g_pool.user);
+	return helpers + 1;
+}
+
+static unsigned
+prepare_plan(void *arg, unsigned nw)
+{
+	prep_job_t *job = arg;
+
+	job->shares = calloc(nw, sizeof(share_t));
+	return nw;
 }
 
 /*
@@ -289,11 +517,12 @@ nxs_index_search_batch_begin(nxs_index_t *idx, nxs_params_t *params,
 {
 	nxs_t *nxs = idx->nxs;
 	search_params_t sp;
-	prepared_t *pq = NULL;
-	nxsb_query_t *descs = NULL;
-	uint32_t *tokens = NULL;
+	prep_job_t job = { 0 };
+	uint32_t *tokens = NULL, *miss_pos = NULL, *miss_off = NULL;
 	int32_t *prog = NULL;
-	size_t n_tok = 0, n_prog = 0, n_miss = 0, n_run = 0;
+	char *miss_blob = NULL;
+	size_t n_tok = 0, n_prog = 0, n_miss = 0, n_run = 0, blob_len = 0;
+	unsigned nw = 0;
 	nxs_batch_t *bt = NULL;
 	uint32_t k;
 	int ret = -1;
@@ -312,156 +541,124 @@ nxs_index_search_batch_begin(nxs_index_t *idx, nxs_params_t *params,
 
 	if ((bt = calloc(1, sizeof(*bt))) == NULL ||
 	    (bt->failed = calloc(n ? n : 1, sizeof(bool))) == NULL)
-		goto out;
+		goto oom;
 	bt->idx = idx;
 	bt->n = n;
 	bt->handle = -1;
-	if ((pq = calloc(n ? n : 1, sizeof(prepared_t))) == NULL)
-		goto out;
 
-	/*
-	 * Parse, tokenize and resolve every query (exact lookups).  The
-	 * reference is single-threaded; a batch is independent read-only work
-	 * per query, so it is spread over the host cores here.
-	 */
-	prepare_all(idx, &sp, queries, n, pq);
+	job.idx = idx;
+	job.sp = &sp;
+	job.queries = queries;
+	job.n = n;
+	job.descs = calloc(n ? n : 1, sizeof(nxsb_query_t));
+	job.errs = calloc(n ? n : 1, sizeof(qerror_t));
+	if (!job.descs || !job.errs)
+		goto oom;
+	{
+		long ncpu = sysconf(_SC_NPROCESSORS_ONLN);
+		size_t want = n / PREP_MIN_PER_THREAD;
+
+		if (ncpu < 1)
+			ncpu = 1;
+		if (want > (size_t)ncpu)
+			want = ncpu;
+		if (want > PREP_MAX_THREADS)
+			want = PREP_MAX_THREADS;
+		nw = pool_run((unsigned)want, prepare_share, &job, prepare_plan);
+		if (!job.shares)
+			goto oom;
+	}
+
+	/* Errors in query order (the slot keeps the last one, as a loop of single searches would). */
 	for (size_t i = 0; i < n; i++) {
-		if (pq[i].failed) {
-			nxs_set_error(nxs, pq[i].err_code, "%s",
-			    pq[i].err_msg ? pq[i].err_msg : "out of memory");
+		if (job.errs[i].code) {
+			nxs_set_error(nxs, job.errs[i].code, "%s",
+			    job.errs[i].msg ? job.errs[i].msg : "out of memory");
+			bt->failed[i] = true;
 		}
-		n_miss += pq[i].n_miss;
+	}
+	/* Lay the shares end to end. */
+	for (unsigned w = 0; w < nw; w++) {
+		const share_t *sh = &job.shares[w];
+
+		if (sh->oom)
+			goto oom;
+		n_tok += sh->n_tok;
+		n_prog += sh->n_prog;
+		n_miss += sh->n_miss;
+		blob_len += sh->blob_len;
+		n_run += sh->n_run;
+	}
+	tokens = malloc(sizeof(uint32_t) * (n_tok + 1));
+	prog = malloc(sizeof(int32_t) * (n_prog + 1));
+	if (!tokens || !prog)
+		goto oom;
+	if (n_miss) {
+		miss_pos = malloc(sizeof(uint32_t) * n_miss);
+		miss_off = malloc(sizeof(uint32_t) * (n_miss + 1));
+		miss_blob = malloc(blob_len + 1);
+		if (!miss_pos || !miss_off || !miss_blob)
+			goto oom;
+	}
+	n_tok = n_prog = n_miss = blob_len = 0;
+	for (unsigned w = 0; w < nw; w++) {
+		const share_t *sh = &job.shares[w];
+
+		memcpy(tokens + n_tok, sh->tokens, sizeof(uint32_t) * sh->n_tok);
+		memcpy(prog + n_prog, sh->prog, sizeof(int32_t) * sh->n_prog);
+		for (size_t i = sh->lo; i < sh->hi; i++) {
+			if (job.descs[i].n_tokens) {
+				job.descs[i].tok_off += n_tok;
+				job.descs[i].prog_off += n_prog;
+			}
+		}
+		for (uint32_t m = 0; m < sh->n_miss; m++) {
+			miss_pos[n_miss + m] = sh->miss_pos[m] + n_tok;
+			miss_off[n_miss + m] = sh->miss_off[m] + blob_len;
+		}
+		if (sh->n_miss)
+			memcpy(miss_blob + blob_len, sh->miss_blob, sh->blob_len);
+		n_tok += sh->n_tok;
+		n_prog += sh->n_prog;
+		n_miss += sh->n_miss;
+		blob_len += sh->blob_len;
 	}
 
 	/* One batched fuzzy scan for every token that missed. */
 	if (n_miss && idx->n_terms) {
-		uint32_t *qoff = malloc(sizeof(uint32_t) * (n_miss + 1));
 		uint32_t *oterm = malloc(sizeof(uint32_t) * n_miss);
 		uint32_t *odist = malloc(sizeof(uint32_t) * n_miss);
-		size_t blob_len = 0, m = 0;
-		char *blob;
 		int rc = -1;
 
-		for (size_t i = 0; i < n; i++) {
-			for (uint32_t j = 0; !pq[i].failed && j < pq[i].tokens->count; j++) {
-				if (!pq[i].tokens->list[j].term_id)
-					blob_len += pq[i].tokens->list[j].len;
-			}
+		miss_off[n_miss] = blob_len;
+		if (!oterm || !odist) {
+			nxs_set_error(nxs, NXS_ERR_SYSTEM, "out of memory");
+		} else if (idx_gpu_prepare(idx, true) == 0) {
+			rc = nxsb_engine_fuzzy(idx->engine, n_miss, miss_blob, miss_off,
+			    oterm, odist, NULL);
+			if (rc == -1)
+				nxs_set_error(nxs, NXS_ERR_SYSTEM, "GPU fuzzy match "
+				    "failed: %s", nxsb_engine_errmsg(idx->engine));
 		}
-		blob = malloc(blob_len + 1);
-		if (qoff && oterm && odist && blob) {
-			blob_len = 0;
-			for (size_t i = 0; i < n; i++) {
-				for (uint32_t j = 0; !pq[i].failed && j < pq[i].tokens->count; j++) {
-					const token_t *t = &pq[i].tokens->list[j];
-
-					if (t->term_id)
-						continue;
-					qoff[m++] = blob_len;
-					memcpy(blob + blob_len, t->str, t->len);
-					blob_len += t->len;
-				}
-			}
-			qoff[m] = blob_len;
-			if (idx_gpu_prepare(idx, true) == 0) {
-				rc = nxsb_engine_fuzzy(idx->engine, m, blob, qoff, oterm,
-				    odist, NULL);
-				if (rc == -1)
-					nxs_set_error(nxs, NXS_ERR_SYSTEM, "GPU fuzzy match "
-					    "failed: %s", nxsb_engine_errmsg(idx->engine));
-			}
-		}
-		if (rc == 0) {
-			m = 0;
-			for (size_t i = 0; i < n; i++) {
-				for (uint32_t j = 0; !pq[i].failed && j < pq[i].tokens->count; j++) {
-					token_t *t = &pq[i].tokens->list[j];
-
-					if (!t->term_id)
-						t->term_id = oterm[m++];
-				}
-			}
-		}
-		free(qoff); free(oterm); free(odist); free(blob);
+		/* A token nothing matched keeps id 0: an empty list. */
+		for (size_t m = 0; rc == 0 && m < n_miss; m++)
+			tokens[miss_pos[m]] = oterm[m];
+		free(oterm);
+		free(odist);
 		if (rc != 0)
 			goto out;
-	}
-
-	/*
-	 * TOKENSET_TRIM: unresolved tokens leave the list; the rest keep
-	 * their order.  Size the batch arrays.
-	 */
-	for (size_t i = 0; i < n; i++) {
-		tokenset_t *ts = pq[i].tokens;
-
-		if (pq[i].failed)
-			continue;
-		if ((pq[i].slot_map = malloc(sizeof(int32_t) * (ts->count + 1))) == NULL)
-			goto out;
-		for (uint32_t j = 0; j < ts->count; j++)
-			pq[i].slot_map[j] = ts->list[j].term_id ?
-			    (int32_t)pq[i].n_resolved++ : -1;
-
-		/* search.c:224-226: nothing usable => empty result, no error. */
-		if (pq[i].tree.root < 0 || pq[i].n_resolved == 0)
-			continue;
-		/* search.c:126-131 (the recursion guard of get_expr_bitmap). */
-		if (pq[i].tree.depth > NXS_QUERY_RLIMIT) {
-			nxs_set_error(nxs, NXS_ERR_LIMIT,
-			    "query nesting limit reached (%u levels)", NXS_QUERY_RLIMIT);
-			pq[i].failed = true;
-			continue;
-		}
-		if (pq[i].n_resolved > NXSB_MAX_QUERY_TOKENS ||
-		    (uint32_t)pq[i].tree.n_nodes > NXSB_MAX_QUERY_PROG ||
-		    program_stack_depth(&pq[i], pq[i].tree.root) > NXSB_MAX_QUERY_TOKENS + 1) {
-			nxs_set_error(nxs, NXS_ERR_LIMIT, "query too large for the GPU "
-			    "engine (%u terms, %d nodes; limits %u / %u)",
-			    pq[i].n_resolved, pq[i].tree.n_nodes,
-			    NXSB_MAX_QUERY_TOKENS, NXSB_MAX_QUERY_PROG);
-			pq[i].failed = true;
-			continue;
-		}
-		n_tok += pq[i].n_resolved;
-		n_prog += pq[i].tree.n_nodes;
-		n_run++;
-	}
-
-	descs = calloc(n ? n : 1, sizeof(nxsb_query_t));
-	tokens = malloc(sizeof(uint32_t) * (n_tok + 1));
-	prog = malloc(sizeof(int32_t) * (n_prog + 1));
-	if (!descs || !tokens || !prog)
-		goto out;
-	n_tok = n_prog = 0;
-	for (size_t i = 0; i < n; i++) {
-		const tokenset_t *ts = pq[i].tokens;
-		uint32_t np = 0;
-
-		if (pq[i].failed || pq[i].tree.root < 0 || pq[i].n_resolved == 0)
-			continue;	/* descriptor stays all-zero: empty result */
-		descs[i].tok_off = n_tok;
-		descs[i].n_tokens = pq[i].n_resolved;
-		for (uint32_t j = 0; j < ts->count; j++) {
-			if (ts->list[j].term_id)
-				tokens[n_tok++] = ts->list[j].term_id;
-		}
-		descs[i].prog_off = n_prog;
-		emit_program(&pq[i], pq[i].tree.root, prog + n_prog, &np);
-		descs[i].n_prog = np;
-		n_prog += np;
 	}
 
 	/* More results than live documents cannot exist: clamp the limit. */
 	k = sp.limit > idx->n_live ? idx->n_live : (uint32_t)sp.limit;
 	if (k == 0)
 		k = 1;
-
 	bt->k = k;
 
 	if (n_run) {
 		const nxsb_batch_t batch = {
 			.algo = sp.algo, .limit = k, .n_queries = n,
-			.queries = descs, .tokens = tokens, .n_tokens = n_tok,
+			.queries = job.descs, .tokens = tokens, .n_tokens = n_tok,
 			.prog = prog, .n_prog = n_prog,
 		};
 
@@ -474,21 +671,35 @@ nxs_index_search_batch_begin(nxs_index_t *idx, nxs_params_t *params,
 			goto out;
 		}
 	}
-	for (size_t i = 0; i < n; i++)
-		bt->failed[i] = pq[i].failed;
 	ret = 0;
+	goto out;
+oom:
+	nxs_set_error(nxs, NXS_ERR_SYSTEM, "out of memory");
 out:
 	if (ret != 0) {
 		batch_free(bt);
 		bt = NULL;
 		nxs_error_checkpoint(nxs);
 	}
-	for (size_t i = 0; pq && i < n; i++)
-		prepared_release(&pq[i]);
-	free(pq);
-	free(descs);
+	for (unsigned w = 0; job.shares && w < nw; w++) {
+		share_t *sh = &job.shares[w];
+
+		free(sh->tokens);
+		free(sh->prog);
+		free(sh->miss_pos);
+		free(sh->miss_off);
+		free(sh->miss_blob);
+	}
+	free(job.shares);
+	for (size_t i = 0; job.errs && i < n; i++)
+		free(job.errs[i].msg);
+	free(job.errs);
+	free(job.descs);
 	free(tokens);
 	free(prog);
+	free(miss_pos);
+	free(miss_off);
+	free(miss_blob);
 	return bt;
 }
 
@@ -634,34 +845,50 @@ nxsb_query_compile(const char *query, char *tokens_buf, size_t buf_len,
     uint32_t *n_tokens, int32_t *prog, uint32_t prog_cap, uint32_t *n_prog)
 {
 	filter_pipeline_t nofilters = { 0 };
-	prepared_t pq = { 0 };
+	tokenset_t *ts = NULL;
+	int32_t *stack = NULL;
+	qtree_t tree;
 	size_t off = 0;
+	int32_t sp = 0;
 	int ret = -1;
 
+	/* No engine limits here: the general token set, same walk as prepare_query(). */
 	*n_tokens = *n_prog = 0;
-	qtree_parse(&pq.tree, query);
-	if (pq.tree.error || prepare_query(&nofilters, &pq) == -1)
+	qtree_parse(&tree, query);
+	if (tree.error || (ts = tokenset_create()) == NULL ||
+	    (stack = malloc(sizeof(int32_t) * (tree.n_nodes + 2))) == NULL)
 		goto out;
-	if ((pq.slot_map = malloc(sizeof(int32_t) * (pq.tokens->count + 1))) == NULL)
-		goto out;
-	for (uint32_t j = 0; j < pq.tokens->count; j++) {
-		const token_t *t = &pq.tokens->list[j];
+	if (tree.root >= 0)
+		stack[sp++] = tree.root;
+	while (sp) {
+		qnode_t *n = &tree.nodes[stack[--sp]];
 
-		pq.slot_map[j] = j;
+		if (n->type != QN_VALUE) {
+			stack[sp++] = n->left;
+			stack[sp++] = n->right;
+		} else if (tokenize_value(&nofilters, ts, n->value, strlen(n->value),
+		    &n->token) == -1) {
+			goto out;
+		}
+	}
+	for (uint32_t j = 0; j < ts->count; j++) {
+		const token_t *t = &ts->list[j];
+
 		if (off + t->len + 1 > buf_len)
 			goto out;
 		memcpy(tokens_buf + off, t->str, t->len + 1);
 		off += t->len + 1;
 	}
-	if (pq.tree.root >= 0) {
-		if ((uint32_t)pq.tree.n_nodes > prog_cap ||
-		    pq.tree.depth > NXS_QUERY_RLIMIT)
+	if (tree.root >= 0) {
+		if ((uint32_t)tree.n_nodes > prog_cap || tree.depth > NXS_QUERY_RLIMIT)
 			goto out;
-		emit_program(&pq, pq.tree.root, prog, n_prog);
+		emit_program(&tree, tree.root, prog, n_prog);
 	}
-	*n_tokens = pq.tokens->count;
+	*n_tokens = ts->count;
 	ret = 0;
 out:
-	prepared_release(&pq);
+	free(stack);
+	tokenset_destroy(ts);
+	qtree_free(&tree);
 	return ret;
 }

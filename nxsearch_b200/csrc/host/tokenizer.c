@@ -138,6 +138,36 @@ tokenset_destroy(tokenset_t *ts)
 	free(ts);
 }
 
+/*
+ * The filter pipeline over one word, in place.  Returns 1 to keep the token,
+ * 0 if a filter discarded it (or left it empty: ref filters.c:206-208).
+ */
+int
+filter_apply(const filter_pipeline_t *fp, char *buf, size_t *lenp)
+{
+	const size_t len = *lenp;
+
+	for (unsigned i = 0; i < fp->count; i++) {
+		switch (fp->kinds[i]) {
+		case FILT_NORMALIZER:
+			for (size_t k = 0; k < len; k++) {
+				if (buf[k] >= 'A' && buf[k] <= 'Z')
+					buf[k] += 'a' - 'A';
+			}
+			break;
+		case FILT_STOPWORDS:
+			if (fp->stopwords && strmap_get(fp->stopwords, buf, len, NULL))
+				return 0;
+			break;
+		case FILT_STEMMER:
+			break;	/* identity: only with NXSB_STEMMER_PASSTHROUGH=1 */
+		}
+		if (len == 0)
+			return 0;
+	}
+	return len != 0;
+}
+
 int
 tokenize_value(filter_pipeline_t *fp, tokenset_t *ts, const char *val,
     size_t len, int32_t *slot)
@@ -152,31 +182,8 @@ tokenize_value(filter_pipeline_t *fp, tokenset_t *ts, const char *val,
 	memcpy(buf, val, len);
 	buf[len] = '\0';
 
-	for (unsigned i = 0; i < fp->count; i++) {
-		switch (fp->kinds[i]) {
-		case FILT_NORMALIZER:
-			for (size_t k = 0; k < len; k++) {
-				if (buf[k] >= 'A' && buf[k] <= 'Z')
-					buf[k] += 'a' - 'A';
-			}
-			break;
-		case FILT_STOPWORDS:
-			if (fp->stopwords && strmap_get(fp->stopwords, buf, len, NULL)) {
-				ret = 0;	/* discarded */
-				goto out;
-			}
-			break;
-		case FILT_STEMMER:
-			break;
-		}
-		/* An empty token is discarded (ref filters.c:206-208). */
-		if (len == 0) {
-			ret = 0;
-			goto out;
-		}
-	}
-	if (len == 0) {
-		ret = 0;
+	if (!filter_apply(fp, buf, &len)) {
+		ret = 0;	/* discarded */
 		goto out;
 	}
 

@@ -49,6 +49,9 @@ void		filter_pipeline_destroy(filter_pipeline_t *);
 tokenset_t *	tokenset_create(void);
 void		tokenset_destroy(tokenset_t *);
 
+/* The pipeline over one word in place: 1 = keep, 0 = discarded. */
+int		filter_apply(const filter_pipeline_t *, char *buf, size_t *len);
+
 /*
  * Run one value through the pipeline and add it to the set.  *slot gets the
  * token's index in the set, or -1 if a filter discarded it.  -1 on error.
