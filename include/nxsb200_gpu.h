@@ -270,6 +270,18 @@ uint64_t	nxsb_alloc_events(void);
  * per-phase cycle counters of a -DBMW_PROF build, else 0.
  */
 int		nxsb_engine_set_pruning(nxsb_engine_t *, int on);
+/*
+ * Threshold priming: the image keeps, per term, the k-th largest
+ * query-independent weight (BM25 tf-normalisation or the TF-IDF tf weight)
+ * for k = 1, 2, 4, 10, 20, 50, 100, 128; a query's pruning threshold starts
+ * at the largest (k-th weight x idf) over its terms instead of zero -- at
+ * least k documents score that much.  term_kth copies the NXSB_KTH_STEPS
+ * values of n terms (1-based ids) to out[n][NXSB_KTH_STEPS]; 0 = the list has
+ * fewer postings than that step (or the id is not a term).
+ */
+#define NXSB_KTH_STEPS	8
+int		nxsb_engine_term_kth(nxsb_engine_t *, int algo, const uint32_t *term_ids,
+		    uint32_t n, float *out);
 int		nxsb_engine_pruning_stats(nxsb_engine_t *, uint64_t out[16], int reset);
 
 #pragma GCC visibility pop

@@ -103,6 +103,7 @@ struct BmwTok {
 	uint32_t		col;
 	uint32_t		fine_shift;
 	float			best;		/* the list's largest score anywhere */
+	float			prime;		/* its k-th largest score (0: fewer postings) */
 };
 
 template <uint32_t BSHIFT>
@@ -270,6 +271,235 @@ term_wmax_kernel(const uint2 *__restrict__ post,
 	}
 }
 
+/* ---- threshold priming: the k-th largest weight of every term ----------- */
+
+/*
+ * A query's threshold need not start at zero.  A document's score is a sum of
+ * non-negative terms, and float addition never rounds a sum below an operand,
+ * so at least k documents score >= (k-th largest weight of term t) * idf(t)
+ * for every term t of the query: the largest of those products is a lower
+ * bound of the query's k-th best score before a single posting is read
+ * ("threshold priming" of the WAND family).  The image keeps, per term and
+ * algorithm, the k-th largest weight for the k of a short ladder; a query
+ * with limit k uses the first step >= k (fewer documents can only score
+ * higher).  Exact, duplicates counted: weights tie all the time.
+ *
+ * One warp per term streams the list and keeps the 128 largest weights seen
+ * in a shared-memory buffer: a weight joins only if it beats the current
+ * 128th, and the buffer is sorted and cut when it fills.  Lists longer than
+ * BMW_KTH_PART postings are cut in parts whose 128 best are merged by a second
+ * launch of the same code over the parts' lists.
+ */
+#define BMW_LADDER	8u
+#define BMW_KTH_BUF	256u
+#define BMW_KTH_KEEP	128u
+#define BMW_KTH_PART	32768u
+
+__host__ __device__ __forceinline__ uint32_t
+bmw_ladder_k(uint32_t j)
+{
+	return (uint32_t)(0x806432140a040201ull >> (8u * j)) & 0xffu;	/* 1 2 4 10 20 50 100 128 */
+}
+
+/* The first step of the ladder that covers limit k (k <= BMW_K_MAX). */
+static inline uint32_t
+bmw_ladder_step(uint32_t k)
+{
+	uint32_t j = 0;
+
+	while (j + 1 < BMW_LADDER && bmw_ladder_k(j) < k)
+		j++;
+	return j;
+}
+
+static_assert(BMW_KTH_KEEP >= BMW_K_MAX, "the ladder reaches the kernel's largest limit");
+
+/* Descending bitonic sort of n words (a power of two >= 64) by one warp. */
+__device__ __forceinline__ void
+warp_sort_desc(uint32_t *s, uint32_t n, uint32_t lane)
+{
+	for (uint32_t size = 2; size <= n; size <<= 1) {
+		for (uint32_t stride = size >> 1; stride; stride >>= 1) {
+			__syncwarp();
+			for (uint32_t p = lane; p < n / 2; p += 32) {
+				const uint32_t i = 2 * p - (p & (stride - 1));
+				const uint32_t a = s[i], b = s[i + stride];
+
+				if ((a < b) == ((i & size) == 0)) {
+					s[i] = b;
+					s[i + stride] = a;
+				}
+			}
+		}
+	}
+	__syncwarp();
+}
+
+struct KthBuf {
+	uint32_t *	buf;	/* [BMW_KTH_BUF] float bits (weights are positive) */
+	uint32_t	cnt, tau;
+};
+
+__device__ __forceinline__ void
+kth_cut(KthBuf &k, uint32_t lane)
+{
+	for (uint32_t i = k.cnt + lane; i < BMW_KTH_BUF; i += 32)
+		k.buf[i] = 0;
+	warp_sort_desc(k.buf, BMW_KTH_BUF, lane);
+	k.cnt = min(k.cnt, BMW_KTH_KEEP);
+	k.tau = k.cnt >= BMW_KTH_KEEP ? k.buf[BMW_KTH_KEEP - 1] : 0u;
+}
+
+/* One value per lane (0 = none) joins the buffer if it can still matter. */
+__device__ __forceinline__ void
+kth_push(KthBuf &k, uint32_t w, uint32_t lane)
+{
+	bool pass = w > k.tau;
+	uint32_t m = __ballot_sync(0xffffffffu, pass);
+
+	if (!m)
+		return;
+	if (k.cnt + __popc(m) > BMW_KTH_BUF) {
+		kth_cut(k, lane);
+		pass = w > k.tau;
+		m = __ballot_sync(0xffffffffu, pass);
+		if (!m)
+			return;
+	}
+	if (pass)
+		k.buf[k.cnt + __popc(m & ((1u << lane) - 1u))] = w;
+	k.cnt += __popc(m);
+}
+
+/* Sort what is left; the buffer then holds min(cnt, 128) weights, descending. */
+__device__ __forceinline__ void
+kth_finish(KthBuf &k, uint32_t lane)
+{
+	uint32_t n = 64;
+
+	__syncwarp();
+	while (n < k.cnt)
+		n <<= 1;
+	for (uint32_t i = k.cnt + lane; i < n; i += 32)
+		k.buf[i] = 0;
+	warp_sort_desc(k.buf, n, lane);
+	k.cnt = min(k.cnt, BMW_KTH_KEEP);
+}
+
+/*
+ * PARTS = false: a warp per term with at most BMW_KTH_PART postings, ladder
+ * written.  PARTS = true: a warp per unit = {term, part} of a longer list,
+ * the part's 128 best (zero padded) written to scratch[unit][algorithm][128].
+ */
+template <bool PARTS>
+__global__ void __launch_bounds__(256)
+term_kth_kernel(const uint2 *__restrict__ post,
+    const unsigned long long *__restrict__ term_off, uint32_t n_terms,
+    const uint2 *__restrict__ units, uint32_t n_units,
+    const float *__restrict__ logtab, float K0, float K1,
+    float *__restrict__ kth_bm25, float *__restrict__ kth_tfidf,
+    uint32_t *__restrict__ scratch)
+{
+	__shared__ float s_logtab[LOGTAB_N];
+	__shared__ uint32_t s_buf[8][2][BMW_KTH_BUF];
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+	const uint32_t n_work = PARTS ? n_units : n_terms;
+
+	for (uint32_t i = threadIdx.x; i < LOGTAB_N; i += blockDim.x)
+		s_logtab[i] = logtab[i];
+	__syncthreads();
+
+	StreamParams sp;
+	sp.K0 = K0;
+	sp.K1 = K1;
+	sp.doc_len = nullptr;
+	for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_work; w += nw) {
+		const uint32_t t = PARTS ? units[w].x : w;
+		unsigned long long s = term_off[t], e = term_off[t + 1];
+
+		if (PARTS) {
+			s += (unsigned long long)units[w].y * BMW_KTH_PART;
+			e = min(e, s + BMW_KTH_PART);
+		} else if (e - s > BMW_KTH_PART || e == s) {
+			continue;	/* a long list (its parts are merged), or none */
+		}
+		KthBuf kb = { s_buf[warp][0], 0u, 0u }, kt = { s_buf[warp][1], 0u, 0u };
+
+		for (unsigned long long i0 = s; i0 < e; i0 += 128) {
+			uint2 v[4];
+			float wb[4], wt[4];
+
+#pragma unroll
+			for (int r = 0; r < 4; r++) {
+				const unsigned long long i = i0 + 32u * r + lane;
+
+				v[r] = i < e ? __ldg(post + i) : make_uint2(0u, 0u);
+			}
+			st_score<false, NXSB_ALGO_BM25, 4>(sp, s_logtab, v, 1.f, wb);
+			st_score<false, NXSB_ALGO_TFIDF, 4>(sp, s_logtab, v, 1.f, wt);
+#pragma unroll
+			for (int r = 0; r < 4; r++) {
+				const bool valid = v[r].y != 0u;
+
+				kth_push(kb, valid ? __float_as_uint(wb[r]) : 0u, lane);
+				kth_push(kt, valid ? __float_as_uint(wt[r]) : 0u, lane);
+			}
+		}
+		kth_finish(kb, lane);
+		kth_finish(kt, lane);
+		if (PARTS) {
+			uint32_t *o = scratch + (size_t)w * 2 * BMW_KTH_KEEP;
+
+			for (uint32_t i = lane; i < BMW_KTH_KEEP; i += 32) {
+				o[i] = i < kb.cnt ? kb.buf[i] : 0u;
+				o[BMW_KTH_KEEP + i] = i < kt.cnt ? kt.buf[i] : 0u;
+			}
+		} else if (lane < BMW_LADDER) {
+			const uint32_t L = bmw_ladder_k(lane);
+
+			kth_bm25[(size_t)t * BMW_LADDER + lane] = kb.cnt >= L ? __uint_as_float(kb.buf[L - 1]) : 0.f;
+			kth_tfidf[(size_t)t * BMW_LADDER + lane] = kt.cnt >= L ? __uint_as_float(kt.buf[L - 1]) : 0.f;
+		}
+		__syncwarp();
+	}
+}
+
+/* A warp per long term: longs[i] = {term, first unit}, units of a term adjoin. */
+__global__ void __launch_bounds__(256)
+term_kth_merge_kernel(const uint2 *__restrict__ longs, uint32_t n_long,
+    const uint2 *__restrict__ units, uint32_t n_units,
+    const uint32_t *__restrict__ scratch,
+    float *__restrict__ kth_bm25, float *__restrict__ kth_tfidf)
+{
+	__shared__ uint32_t s_buf[8][2][BMW_KTH_BUF];
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const uint32_t nw = (gridDim.x * blockDim.x) >> 5;
+
+	for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < n_long; w += nw) {
+		const uint32_t t = longs[w].x, u0 = longs[w].y;
+		KthBuf kb = { s_buf[warp][0], 0u, 0u }, kt = { s_buf[warp][1], 0u, 0u };
+
+		for (uint32_t u = u0; u < n_units && units[u].x == t; u++) {
+			const uint32_t *in = scratch + (size_t)u * 2 * BMW_KTH_KEEP;
+
+			for (uint32_t i = lane; i < BMW_KTH_KEEP; i += 32) {
+				kth_push(kb, in[i], lane);
+				kth_push(kt, in[BMW_KTH_KEEP + i], lane);
+			}
+		}
+		kth_finish(kb, lane);
+		kth_finish(kt, lane);
+		if (lane < BMW_LADDER) {
+			const uint32_t L = bmw_ladder_k(lane);
+
+			kth_bm25[(size_t)t * BMW_LADDER + lane] = kb.cnt >= L ? __uint_as_float(kb.buf[L - 1]) : 0.f;
+			kth_tfidf[(size_t)t * BMW_LADDER + lane] = kt.cnt >= L ? __uint_as_float(kt.buf[L - 1]) : 0.f;
+		}
+		__syncwarp();
+	}
+}
+
 /* ---- the scorer --------------------------------------------------------- */
 
 template <int ALGO, uint32_t BSHIFT>
@@ -343,6 +573,7 @@ score_bmw_kernel(const BmwParams p)
 			bt.fine = t.fine;
 			bt.fine_shift = t.fine_shift;
 			bt.best = __fmul_rn(t.wmax, t.idf);
+			bt.prime = __fmul_rn(t.wk, t.idf);
 			s_tok[tid] = bt;
 		}
 		if (tid == 0)
@@ -353,10 +584,14 @@ score_bmw_kernel(const BmwParams p)
 
 		bool any_list = false;
 		float best_sum = 0.f;		/* no score of the query exceeds it */
+		float prime = 0.f;		/* at least k documents score this much */
 		for (uint32_t j = 0; j < ntok; j++) {
 			any_list |= s_tok[j].col == BMW_BCOL_NONE;
 			best_sum = __fadd_ru(best_sum, s_tok[j].best);
+			prime = fmaxf(prime, s_tok[j].prime);
 		}
+		/* As a key: every document scoring >= prime stays above it. */
+		const unsigned long long prime_key = prime > 0.f ? make_key(prime, 0u) - 1ull : 0ull;
 		/*
 		 * A block's bound is summed columns first, short lists after:
 		 * another order than the token list's, which can round a few ulp
@@ -608,7 +843,8 @@ score_bmw_kernel(const BmwParams p)
 		bool first = true;
 		for (;;) {
 			if (tid == 0) {
-				const unsigned long long g = *(volatile unsigned long long *)(p.thr + slot);
+				const unsigned long long g = max(prime_key,
+				    *(volatile unsigned long long *)(p.thr + slot));
 
 				if (g > s_theta)
 					s_theta = g;

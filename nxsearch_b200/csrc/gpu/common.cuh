@@ -63,8 +63,8 @@ struct DTok {
 	const uint32_t *	fine;
 	uint32_t		fine_shift;
 	uint32_t		bcol;		// row of its block arrays (bmw.cuh), or 0xffffffff
-	float			wmax;		// no block arrays: the list's largest weight
-	uint32_t		pad;
+	float			wmax;		// the list's largest weight
+	float			wk;		// its k-th largest, k = the batch's ladder step (bmw.cuh); 0 = none
 };
 
 /* 16-byte result record (also the NCCL all-gather payload). */

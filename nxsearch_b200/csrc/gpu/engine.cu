@@ -214,6 +214,15 @@ struct nxsb_engine {
 	uint32_t *	d_boff = nullptr;		// [n_bcol][nblocks + 1]
 	float *		d_bmax_bm25 = nullptr, *d_bmax_tfidf = nullptr;	// [n_bcol][row_stride]
 	float *		d_wmax_bm25 = nullptr, *d_wmax_tfidf = nullptr;	// [V] largest weight of a term
+	/* Threshold priming: [V][BMW_LADDER] k-th largest weight of a term. */
+	float *		d_kth_bm25 = nullptr, *d_kth_tfidf = nullptr;
+	uint2 *		d_kth_units = nullptr, *d_kth_longs = nullptr;	// parts of the long lists
+	uint32_t *	d_kth_scratch = nullptr;
+	uint32_t	n_kth_units = 0, n_kth_longs = 0;
+	bool		prime_enabled = true;		// NXSB_PRIME=0: thresholds start at zero
+	/* The weight tables (bmax, wmax, kth) were computed with these constants. */
+	bool		tables_valid = false;
+	float		tables_K0 = 0, tables_K1 = 0;
 	unsigned long long *d_bmw_stats = nullptr;	// [4] counters of the BMW launches
 	uint64_t	token_count = 0;
 	uint32_t	doc_count = 0;
@@ -425,6 +434,30 @@ nxsb_engine_set_pruning(nxsb_engine_t *e, int on)
 	return was;
 }
 
+static_assert(NXSB_KTH_STEPS == BMW_LADDER, "header and kernel agree on the ladder");
+
+extern "C" int
+nxsb_engine_term_kth(nxsb_engine_t *e, int algo, const uint32_t *term_ids, uint32_t n, float *out)
+{
+	const float *tab = algo == NXSB_ALGO_BM25 ? e->d_kth_bm25 : e->d_kth_tfidf;
+
+	if (!e->loaded || !tab)
+		return fail(e, "no k-th weight tables (no image, a wide image, or pruning off)");
+	CK(e, cudaSetDevice(e->device));
+	CK(e, cudaStreamSynchronize(e->stream));
+	for (uint32_t i = 0; i < n; i++) {
+		float *o = out + (size_t)i * BMW_LADDER;
+
+		if (term_ids[i] == 0 || term_ids[i] > e->n_terms) {
+			memset(o, 0, BMW_LADDER * sizeof(float));
+			continue;
+		}
+		CK(e, cudaMemcpy(o, tab + (size_t)(term_ids[i] - 1) * BMW_LADDER,
+		    BMW_LADDER * sizeof(float), cudaMemcpyDeviceToHost));
+	}
+	return 0;
+}
+
 extern "C" int
 nxsb_engine_pruning_stats(nxsb_engine_t *e, uint64_t out[16], int reset)
 {
@@ -498,6 +531,9 @@ nxsb_engine_create(int device)
 		/* NXSB_BMW=0: no block-max pruning, every query streams all its postings. */
 		if ((kv = getenv("NXSB_BMW")) != NULL)
 			e->bmw_enabled = atoi(kv) != 0;
+		/* NXSB_PRIME=0: pruning thresholds start at zero (A/B of the priming). */
+		if ((kv = getenv("NXSB_PRIME")) != NULL)
+			e->prime_enabled = atoi(kv) != 0;
 		/* Development switch: documents per block = 2^NXSB_BMW_SHIFT. */
 		if ((kv = getenv("NXSB_BMW_SHIFT")) != NULL)
 			e->bshift = (uint32_t)std::min(BMW_SHIFT_MAX, std::max(BMW_SHIFT_MIN, atoi(kv)));
@@ -547,6 +583,13 @@ free_image(nxsb_engine_t *e)
 	dev_free(e->d_bmax_tfidf);
 	dev_free(e->d_wmax_bm25);
 	dev_free(e->d_wmax_tfidf);
+	dev_free(e->d_kth_bm25);
+	dev_free(e->d_kth_tfidf);
+	dev_free(e->d_kth_units);
+	dev_free(e->d_kth_longs);
+	dev_free(e->d_kth_scratch);
+	e->n_kth_units = e->n_kth_longs = 0;
+	e->tables_valid = false;
 	e->n_bcol = 0;
 	dev_free(e->d_skip);
 	dev_free(e->d_skip_mt);
@@ -703,8 +746,12 @@ upload_stats(nxsb_engine_t *e)
 	    cudaMemcpyHostToDevice, e->stream));
 	CK(e, cudaMemcpyAsync(e->d_idf_tfidf, tfidf.data(), V * sizeof(float),
 	    cudaMemcpyHostToDevice, e->stream));
-	if (e->d_wmax_bm25) {
-		/* The BM25 weight depends on K0 / K1: the maxima follow the statistics. */
+	if (e->d_wmax_bm25 && !(e->tables_valid && e->tables_K0 == e->K0 && e->tables_K1 == e->K1)) {
+		/*
+		 * The BM25 weight depends on K0 / K1: the maxima follow the
+		 * statistics.  K1 moves only when the integer average length does
+		 * (ref ranking.c:163), so most refreshes keep the tables.
+		 */
 		const size_t words = (size_t)e->n_bcol * e->row_stride;
 
 		if (e->n_bcol) {
@@ -719,7 +766,30 @@ upload_stats(nxsb_engine_t *e)
 		    e->d_bcol, V, e->d_logtab, e->K0, e->K1, e->d_bmax_bm25, e->d_bmax_tfidf,
 		    e->row_stride, e->d_wmax_bm25, e->d_wmax_tfidf);
 		e->launches++;
+		if (e->d_kth_bm25) {
+			const size_t lad = (size_t)V * BMW_LADDER * 4;
+
+			CK(e, cudaMemsetAsync(e->d_kth_bm25, 0, lad, e->stream));
+			CK(e, cudaMemsetAsync(e->d_kth_tfidf, 0, lad, e->stream));
+			term_kth_kernel<false><<<e->n_sms * 8, 256, 0, e->stream>>>(e->d_post,
+			    e->d_term_off, V, nullptr, 0, e->d_logtab, e->K0, e->K1,
+			    e->d_kth_bm25, e->d_kth_tfidf, nullptr);
+			e->launches++;
+			if (e->n_kth_units) {
+				term_kth_kernel<true><<<std::min(e->n_sms * 8u, (e->n_kth_units + 7) / 8),
+				    256, 0, e->stream>>>(e->d_post, e->d_term_off, V, e->d_kth_units,
+				    e->n_kth_units, e->d_logtab, e->K0, e->K1, nullptr, nullptr,
+				    e->d_kth_scratch);
+				term_kth_merge_kernel<<<std::min(e->n_sms * 8u, (e->n_kth_longs + 7) / 8),
+				    256, 0, e->stream>>>(e->d_kth_longs, e->n_kth_longs, e->d_kth_units,
+				    e->n_kth_units, e->d_kth_scratch, e->d_kth_bm25, e->d_kth_tfidf);
+				e->launches += 2;
+			}
+		}
 		CK(e, cudaGetLastError());
+		e->tables_valid = true;
+		e->tables_K0 = e->K0;
+		e->tables_K1 = e->K1;
 	}
 	CK(e, cudaStreamSynchronize(e->stream));
 	return 0;
@@ -1010,6 +1080,33 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 			    dev_alloc(&e->d_bmax_tfidf, (size_t)e->n_bcol * stride) == cudaSuccess &&
 			    (e->wide || (dev_alloc(&e->d_wmax_bm25, V) == cudaSuccess &&
 			    dev_alloc(&e->d_wmax_tfidf, V) == cudaSuccess));
+			/* Threshold priming (bmw.cuh): the ladder tables and, for the
+			 * lists longer than one part, the units of the two-level pass. */
+			std::vector<uint2> units, longs;
+			if (ok && !e->wide && e->bmw_enabled && e->prime_enabled) {
+				for (uint32_t t = 0; t < V; t++) {
+					const uint32_t df = e->h_df_local[t];
+
+					if (df <= BMW_KTH_PART)
+						continue;
+					longs.push_back(make_uint2(t, (uint32_t)units.size()));
+					for (uint32_t part = 0; part * BMW_KTH_PART < df; part++)
+						units.push_back(make_uint2(t, part));
+				}
+				e->n_kth_units = units.size();
+				e->n_kth_longs = longs.size();
+				ok = dev_alloc(&e->d_kth_bm25, (size_t)V * BMW_LADDER) == cudaSuccess &&
+				    dev_alloc(&e->d_kth_tfidf, (size_t)V * BMW_LADDER) == cudaSuccess &&
+				    dev_alloc(&e->d_kth_units, units.size()) == cudaSuccess &&
+				    dev_alloc(&e->d_kth_longs, longs.size()) == cudaSuccess &&
+				    dev_alloc(&e->d_kth_scratch, units.size() * 2 * BMW_KTH_KEEP) == cudaSuccess;
+				if (ok && !units.empty()) {
+					cudaMemcpyAsync(e->d_kth_units, units.data(), units.size() * sizeof(uint2),
+					    cudaMemcpyHostToDevice, st);
+					cudaMemcpyAsync(e->d_kth_longs, longs.data(), longs.size() * sizeof(uint2),
+					    cudaMemcpyHostToDevice, st);
+				}
+			}
 			if (ok) {
 				cudaMemcpyAsync(e->d_bcol, bcol.data(), (size_t)V * 4,
 				    cudaMemcpyHostToDevice, st);
@@ -2026,7 +2123,8 @@ run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
 	    e->d_skip, e->d_skip_mt, e->n_mt, B.d_tmp_skip,
 	    B.algo == NXSB_ALGO_BM25 ? e->d_idf_bm25 : e->d_idf_tfidf,
 	    B.algo == NXSB_ALGO_BM25 ? e->d_wmax_bm25 : e->d_wmax_tfidf,
-	    e->ntiles, B.d_toks);
+	    B.bmw ? (B.algo == NXSB_ALGO_BM25 ? e->d_kth_bm25 : e->d_kth_tfidf) : nullptr,
+	    bmw_ladder_step(B.limit), e->ntiles, B.d_toks);
 	build_temp_skips_kernel<<<B.n_tok_all, 128, 0, st>>>(e->d_post, B.d_toks,
 	    B.d_tmp_skip, e->ntiles);
 	e->launches += 2;

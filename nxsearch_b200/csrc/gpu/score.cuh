@@ -66,14 +66,15 @@ resolve_tokens_kernel(const uint32_t *__restrict__ term_ids, uint32_t n,
     const uint32_t *__restrict__ bcol, uint32_t *__restrict__ dense_used, unsigned long long col_words, const uint32_t *__restrict__ skip,
     const uint32_t *__restrict__ skip_mt, uint32_t n_mt,
     uint32_t *__restrict__ tmp_skip, const float *__restrict__ idf,
-    const float *__restrict__ wmax, uint32_t ntiles, DTok *__restrict__ out)
+    const float *__restrict__ wmax, const float *__restrict__ kth, uint32_t kth_step,
+    uint32_t ntiles, DTok *__restrict__ out)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	DTok t;
 
 	if (i >= n)
 		return;
-	t.pad = 0;
+	t.wk = 0.f;
 	t.wmax = 0.f;
 	const uint32_t id = term_ids[i];
 
@@ -99,6 +100,7 @@ resolve_tokens_kernel(const uint32_t *__restrict__ term_ids, uint32_t n,
 		    : DENSE_NONE;
 		t.bcol = bcol ? bcol[ti] : 0xffffffffu;
 		t.wmax = wmax ? wmax[ti] : 0.f;
+		t.wk = kth ? kth[(size_t)ti * 8u + kth_step] : 0.f;
 		if (dense_col[ti] >= 0)
 			dense_used[dense_col[ti]] = 1u;	/* dense_scores_kernel will fill it */
 		t.skip = row >= 0 ? skip + (size_t)row * (ntiles + 1)

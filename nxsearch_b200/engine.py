@@ -72,6 +72,7 @@ def _bind():
         "nxsb_alloc_events": (u64, []),
         "nxsb_engine_set_pruning": (i, [vp, i]),
         "nxsb_engine_pruning_stats": (i, [vp, vp, i]),
+        "nxsb_engine_term_kth": (i, [vp, i, vp, C.c_uint32, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -311,6 +312,15 @@ class Engine:
     def set_pruning(self, on: bool) -> bool:
         """Exact block-max pruning of OR queries on/off (batches staged afterwards)."""
         return bool(self._lib.nxsb_engine_set_pruning(self._h, int(on)))
+
+    KTH_STEPS = (1, 2, 4, 10, 20, 50, 100, 128)
+
+    def term_kth(self, algo: int, term_ids) -> np.ndarray:
+        """[n, 8] k-th largest weight of each term for k in KTH_STEPS (0: fewer postings)."""
+        ids = np.ascontiguousarray(term_ids, dtype=np.uint32)
+        out = np.zeros((len(ids), len(self.KTH_STEPS)), dtype=np.float32)
+        self._check(self._lib.nxsb_engine_term_kth(self._h, algo, ids.ctypes.data, len(ids), out.ctypes.data))
+        return out
 
     def pruning_stats(self, reset: bool = False) -> dict[str, int]:
         out = (C.c_uint64 * 16)()

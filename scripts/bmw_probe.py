@@ -19,9 +19,14 @@ qt = c.query_terms(4 * 1024 * nb)
 qs = bench.make_queries(qt, 1024 * nb)
 hb = [eng.Batch.from_lists(eng.ALGO_BM25, 10, [(t, p) for t, p, _ in qs[i * 1024:(i + 1) * 1024]]) for i in range(nb)]
 named = sum(int(c.term_df[t - 1]) for t, _, _ in qs for t in t) / nb
-for shift in shifts:
+import time
+primes = [int(x) for x in os.environ.get("PROBE_PRIME", "1").split(",")]
+for shift, prime in [(s, p) for s in shifts for p in primes]:
     os.environ["NXSB_BMW_SHIFT"] = str(shift)
+    os.environ["NXSB_PRIME"] = str(prime)
+    t0 = time.time()
     e = eng.Engine(0); e.load_corpus(c)
+    print(f"prime {prime}: image built in {time.time() - t0:.2f}s")
     hs = [e.upload(b) for b in hb]
     for i in range(3): e.run(hs[i % nb])
     e.sync()

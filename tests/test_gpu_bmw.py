@@ -226,3 +226,61 @@ def test_no_allocation_in_steady_state(corpus, eng):
             eng.search_end(eng.search_begin(b), len(b.queries), b.limit)
         assert engine.alloc_events() == before, "device memory was (re)allocated on the search path"
     eng.set_pruning(True)
+
+
+def test_kth_weight_ladder(corpus, eng):
+    """Threshold priming: the image's k-th largest weight per term (one warp
+    per list, long lists in parts) against a sort of the list on the host --
+    TF-IDF weights bit for bit, BM25 weights within the kernel's 1e-6."""
+    df = np.asarray(corpus.term_df)
+    terms = np.asarray(corpus.pairs[0::2])
+    counts = np.asarray(corpus.pairs[1::2]).astype(np.int64)
+    doc_of = np.repeat(np.arange(corpus.n_docs), np.diff(np.asarray(corpus.doc_off)).astype(np.int64))
+    dl = np.asarray(corpus.doc_len).astype(np.float64)
+    by_df = np.argsort(-df.astype(np.int64), kind="stable")
+    picks = [int(by_df[0]) + 1, int(by_df[1]) + 1, int(by_df[7]) + 1]               # several parts each
+    picks += [int(t) + 1 for t in np.nonzero((df > 300) & (df < 5000))[0][:4]]       # one buffer cut or more
+    picks += [int(t) + 1 for t in np.nonzero((df >= 1) & (df < 128))[0][:4]]         # shorter than the ladder
+    picks += [int(np.nonzero(df == 0)[0][0]) + 1] if (df == 0).any() else []
+    assert df[picks[0] - 1] > 32768 * 2
+    kth_t = eng.term_kth(TFIDF, picks)
+    kth_b = eng.term_kth(BM25, picks)
+    k = np.float64(np.float32(1.2))
+    adl = float(corpus.token_count // corpus.doc_count)
+    K0, K1 = np.float64(np.float32(k * 0.25)), np.float64(np.float32(k * 0.75 / adl))
+    for row, t in enumerate(picks):
+        sel = terms == t
+        tf = counts[sel]
+        T = np.log(tf.astype(np.float64) + 1).astype(np.float32)
+        wt = np.sort(T)[::-1]
+        Tb = T.astype(np.float64)
+        wb = np.sort(Tb / (Tb + K0 + K1 * dl[doc_of[sel]]))[::-1]
+        assert len(tf) == df[t - 1]
+        for j, step in enumerate(eng.KTH_STEPS):
+            if step > len(tf):
+                assert kth_t[row, j] == 0 and kth_b[row, j] == 0, (t, step)
+                continue
+            assert kth_t[row, j].view(np.uint32) == wt[step - 1].view(np.uint32), (t, step)
+            assert abs(float(kth_b[row, j]) - wb[step - 1]) <= 2e-6 * wb[step - 1], (t, step, kth_b[row, j], wb[step - 1])
+
+
+def test_priming_only_raises_the_start(corpus, eng, monkeypatch):
+    """An engine without priming (NXSB_PRIME=0) gives the same answers and
+    scores more blocks."""
+    from nxsearch_b200 import engine
+
+    qs = or_queries(corpus, 512, seed_off=3)
+    batch = engine.Batch.from_lists(BM25, 10, qs)
+    eng.pruning_stats(reset=True)
+    primed = eng.search(batch)
+    s1 = eng.pruning_stats()
+    monkeypatch.setenv("NXSB_PRIME", "0")
+    plain = engine.Engine(0)
+    try:
+        plain.load_corpus(corpus)
+        unprimed = plain.search(batch)
+        s0 = plain.pruning_stats()
+    finally:
+        plain.close()
+    assert_identical(primed, unprimed)
+    assert s1["blocks_scored"] < s0["blocks_scored"], (s1, s0)
