@@ -46,7 +46,10 @@
 #define BMW_THREADS	256
 #define BMW_WARPS	(BMW_THREADS / 32)
 #define BMW_CH_BLOCKS	8192u			/* blocks per chunk */
-#define BMW_PER_THREAD	(BMW_CH_BLOCKS / BMW_THREADS)
+#define BMW_CH_SB	(BMW_CH_BLOCKS / 32u)		/* superblocks (32 blocks) per chunk */
+#ifndef BMW_DENSE_SB
+#define BMW_DENSE_SB	32u			/* more live superblocks than this: dense block bounds */
+#endif
 #ifndef BMW_CAND
 #define BMW_CAND	1024u			/* candidate keys per item */
 #endif
@@ -86,6 +89,8 @@ struct BmwParams {
 	uint32_t		n_q, nchunks, nblocks, row_stride, n_docs, ntiles, k;
 	const uint32_t *	boff;		/* [n_bcol][nblocks + 1] */
 	const float *		bmax;		/* [n_bcol][row_stride], the batch's algorithm */
+	const float *		smax;		/* [n_bcol][sb_stride]: maxima per superblock of 32 blocks */
+	uint32_t		sb_stride, n_mt;
 	unsigned long long *	thr;		/* [n_q] */
 	uint32_t *		tile_count;	/* [n_q][nchunks] */
 	unsigned long long *	cand;		/* [n_q][nchunks][k] */
@@ -104,6 +109,8 @@ struct BmwTok {
 	uint32_t		fine_shift;
 	float			best;		/* the list's largest score anywhere */
 	float			prime;		/* its k-th largest score (0: fewer postings) */
+	const uint8_t *		mtmax;		/* mini-tile maxima bytes, or NULL */
+	float			step;		/* what one unit of those bytes is worth */
 };
 
 template <uint32_t BSHIFT>
@@ -213,6 +220,28 @@ block_max_kernel(const uint2 *__restrict__ post,
 	}
 }
 
+/* smax[c][s] = the largest of bmax[c][32 s .. 32 s + 31] (rows zero padded). */
+__global__ void __launch_bounds__(256)
+superblock_max_kernel(const float *__restrict__ bmax_bm25, const float *__restrict__ bmax_tfidf,
+    uint32_t n_bcol, uint32_t row_stride, uint32_t sb_stride,
+    float *__restrict__ smax_bm25, float *__restrict__ smax_tfidf)
+{
+	const size_t n = (size_t)n_bcol * sb_stride;
+
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+	    i += (size_t)gridDim.x * blockDim.x) {
+		const uint32_t c = (uint32_t)(i / sb_stride), sb = (uint32_t)(i % sb_stride);
+		float mb = 0.f, mt = 0.f;
+
+		for (uint32_t b = sb * 32u; b < min(row_stride, sb * 32u + 32u); b++) {
+			mb = fmaxf(mb, bmax_bm25[(size_t)c * row_stride + b]);
+			mt = fmaxf(mt, bmax_tfidf[(size_t)c * row_stride + b]);
+		}
+		smax_bm25[i] = mb;
+		smax_tfidf[i] = mt;
+	}
+}
+
 /*
  * wmax_*[t] = the largest weight of any posting of term t (a warp per term):
  * from the block maxima where the term has them, else from its postings
@@ -268,6 +297,84 @@ term_wmax_kernel(const uint2 *__restrict__ post,
 			wmax_bm25[t] = mb;
 			wmax_tfidf[t] = mt;
 		}
+	}
+}
+
+/*
+ * Long lists without block arrays (DF_LONG <= df < a posting per two blocks)
+ * get one BYTE per mini-tile of 2^MT_SHIFT documents: the largest weight of
+ * the list's postings there, as a fraction of the list's largest weight,
+ * rounded UP to a multiple of 1/255 -- a bound, never below the true maximum.
+ * The scorer's superblock pass reads it instead of walking the postings.
+ */
+__device__ __forceinline__ float
+mt_step(float wmax)
+{
+	return __fmul_ru(wmax, 0.003921569f);	/* 1/255 rounded up */
+}
+
+__device__ __forceinline__ float
+mt_bound(uint32_t q, float step)
+{
+	return __fmul_ru((float)q, step);
+}
+
+/* A thread per (long list, mini-tile); rows of the column terms stay zero. */
+__global__ void __launch_bounds__(256)
+minitile_max_kernel(const uint2 *__restrict__ post,
+    const unsigned long long *__restrict__ term_off, const uint32_t *__restrict__ long_terms,
+    const uint32_t *__restrict__ bcol, const uint32_t *__restrict__ skip_mt,
+    uint32_t n_long, uint32_t n_mt, uint32_t mt_stride,
+    const float *__restrict__ logtab, float K0, float K1,
+    const float *__restrict__ wmax_bm25, const float *__restrict__ wmax_tfidf,
+    uint8_t *__restrict__ mt_bm25, uint8_t *__restrict__ mt_tfidf)
+{
+	__shared__ float s_logtab[LOGTAB_N];
+	const size_t n = (size_t)n_long * n_mt;
+
+	for (uint32_t i = threadIdx.x; i < LOGTAB_N; i += blockDim.x)
+		s_logtab[i] = logtab[i];
+	__syncthreads();
+
+	StreamParams sp;
+	sp.K0 = K0;
+	sp.K1 = K1;
+	sp.doc_len = nullptr;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+	    i += (size_t)gridDim.x * blockDim.x) {
+		const uint32_t r = (uint32_t)(i / n_mt), m = (uint32_t)(i % n_mt);
+		const uint32_t t = long_terms[r];
+
+		if (bcol[t] != BMW_BCOL_NONE)
+			continue;
+		const uint32_t *row = skip_mt + (size_t)r * (n_mt + 1);
+		const uint32_t lo = row[m], hi = row[m + 1];
+
+		if (lo == hi)
+			continue;	/* pre-zeroed */
+		const uint2 *list = post + term_off[t];
+		float mb = 0.f, mt = 0.f;
+
+		for (uint32_t x = lo; x < hi; x++) {
+			const uint2 v[1] = { list[x] };
+			float wb[1], wt[1];
+
+			st_score<false, NXSB_ALGO_BM25, 1>(sp, s_logtab, v, 1.f, wb);
+			st_score<false, NXSB_ALGO_TFIDF, 1>(sp, s_logtab, v, 1.f, wt);
+			mb = fmaxf(mb, wb[0]);
+			mt = fmaxf(mt, wt[0]);
+		}
+		const float sb = mt_step(wmax_bm25[t]), st = mt_step(wmax_tfidf[t]);
+		uint32_t qb = min(255u, (uint32_t)ceilf(__fdiv_ru(mb, sb)));
+		uint32_t qt = min(255u, (uint32_t)ceilf(__fdiv_ru(mt, st)));
+
+		/* Belt and braces: the byte's bound is at least the maximum. */
+		while (qb < 255u && mt_bound(qb, sb) < mb)
+			qb++;
+		while (qt < 255u && mt_bound(qt, st) < mt)
+			qt++;
+		mt_bm25[(size_t)r * mt_stride + m] = (uint8_t)qb;
+		mt_tfidf[(size_t)r * mt_stride + m] = (uint8_t)qt;
 	}
 }
 
@@ -509,6 +616,8 @@ score_bmw_kernel(const BmwParams p)
 	using Cfg = BmwCfg<BSHIFT>;
 	constexpr uint32_t BS = Cfg::BS, NP = Cfg::NP;
 	constexpr uint32_t FULL = 0xffffffffu;
+	constexpr uint32_t SBB = 32u, SB_SHIFT = BSHIFT + 5u;
+	static_assert(BMW_CH_SB == BMW_THREADS, "a thread per superblock of the chunk");
 
 	extern __shared__ __align__(16) unsigned char smem_bmw[];
 	float *ub = reinterpret_cast<float *>(smem_bmw);		/* [CH_BLOCKS] bounds; 0 = scored */
@@ -522,6 +631,15 @@ score_bmw_kernel(const BmwParams p)
 	__shared__ uint32_t s_item, s_selw[2], s_next, s_ncand, s_overflow, s_cut;
 	__shared__ uint32_t s_hist[BMW_HIST];
 	__shared__ unsigned long long s_theta, s_kth;
+	/*
+	 * Scratch of the bound passes, in buffers that are idle until the first
+	 * block is scored (4 CTAs per SM must stay within the 196 KB carve-out:
+	 * the next step up costs the L1 half of its capacity).
+	 */
+	float *s_sbs = reinterpret_cast<float *>(s_cand);		/* [CH_SB] short lists' part of a superblock's bound */
+	uint32_t *s_tmp = reinterpret_cast<uint32_t *>(s_cand) + BMW_CH_SB;	/* [CH_SB] one list's superblock maxima */
+	uint32_t *s_wtmp = reinterpret_cast<uint32_t *>(s_top);		/* [WARPS * 32] one list's block maxima, per warp */
+	static_assert(BMW_CAND * 8 >= 2 * BMW_CH_SB * 4 && BMW_K_MAX * 8 >= BMW_WARPS * 32 * 4, "scratch fits");
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t n_items = p.n_q * p.nchunks;
@@ -537,13 +655,19 @@ score_bmw_kernel(const BmwParams p)
 	sp.K1 = p.K1;
 	sp.doc_len = nullptr;
 
+	/* Thread 0 takes the item after this one while this one runs. */
+	uint32_t next_item = 0;
+	if (tid == 0)
+		next_item = atomicAdd(p.work_counter, 1u);
+
 	BPROF_DECL;
 	for (;;) {
 		__syncthreads();
 		BPROF(5);
 		if (tid == 0) {
-			s_item = atomicAdd(p.work_counter, 1u);
+			s_item = next_item;
 			s_ncand = 0;
+			next_item = atomicAdd(p.work_counter, 1u);
 		}
 		__syncthreads();
 		const uint32_t item = s_item;
@@ -574,10 +698,10 @@ score_bmw_kernel(const BmwParams p)
 			bt.fine_shift = t.fine_shift;
 			bt.best = __fmul_rn(t.wmax, t.idf);
 			bt.prime = __fmul_rn(t.wk, t.idf);
+			bt.mtmax = t.mtmax;
+			bt.step = mt_step(t.wmax);
 			s_tok[tid] = bt;
 		}
-		if (tid == 0)
-			s_theta = *(volatile unsigned long long *)(p.thr + slot);
 		__syncthreads();
 		if (tid == 0)
 			st_items++;
@@ -599,9 +723,89 @@ score_bmw_kernel(const BmwParams p)
 		 */
 		const float infl = (any_list && ntok >= 3) ? 1.0000152587890625f : 1.f;
 
+		if (tid == 0)
+			s_theta = max(prime_key, *(volatile unsigned long long *)(p.thr + slot));
+		s_wtmp[tid] = 0u;
+		__syncthreads();
+
 		BPROF(6);
-		/* ---- short lists: their exact block maxima, from the postings ---- */
+		/*
+		 * ---- superblocks first: a thread per superblock of 32 blocks ----
+		 * bound = the columns' superblock maxima (smax rows) + the short
+		 * lists' exact maxima, folded in from the chunk's postings at this
+		 * coarse grain.  Only the superblocks that can still beat the
+		 * threshold get block bounds at all.
+		 */
+		const uint32_t nsb = (nb + SBB - 1) / SBB;
 		if (any_list) {
+			s_sbs[tid] = 0.f;
+			for (uint32_t j = 0; j < ntok; j++) {
+				const BmwTok bt = s_tok[j];
+
+				if (bt.col != BMW_BCOL_NONE || bt.mtmax || bt.clo == bt.chi)
+					continue;
+				const uint2 *list = p.post + bt.post_off;
+
+				s_tmp[tid] = 0u;
+				__syncthreads();
+				for (uint32_t i = bt.clo + tid; i < bt.chi; i += BMW_THREADS) {
+					const uint2 v[1] = { __ldg(list + i) };
+					float sc[1];
+
+					st_score<false, ALGO, 1>(sp, s_logtab, v, bt.idf, sc);
+					atomicMax(&s_tmp[(v[0].x - doc0) >> SB_SHIFT], __float_as_uint(sc[0]));
+				}
+				__syncthreads();
+				s_sbs[tid] = __fadd_rn(s_sbs[tid], __uint_as_float(s_tmp[tid]));
+			}
+			BPROF(1);
+		}
+		uint32_t live_mask, n_live;
+		{
+			float u = 0.f;
+
+			for (uint32_t j = 0; j < ntok; j++) {
+				const BmwTok &bt = s_tok[j];
+
+				if (bt.col == BMW_BCOL_NONE)
+					continue;
+				const float m = tid < nsb ? __ldg(p.smax + (size_t)bt.col * p.sb_stride +
+				    chunk * BMW_CH_SB + tid) : 0.f;
+
+				u = __fadd_rn(u, __fmul_rn(m, bt.idf));
+			}
+			if (any_list) {
+				/* Long lists: the bytes of the superblock's mini-tiles. */
+				for (uint32_t j = 0; j < ntok; j++) {
+					const BmwTok &bt = s_tok[j];
+
+					if (bt.col != BMW_BCOL_NONE || !bt.mtmax || tid >= nsb)
+						continue;
+					constexpr uint32_t MPS = 1u << (SB_SHIFT - MT_SHIFT);
+					const uint8_t *q = bt.mtmax + (size_t)(chunk * BMW_CH_SB + tid) * MPS;
+					uint32_t qm = 0;
+
+#pragma unroll
+					for (uint32_t m = 0; m < MPS; m++)
+						qm = max(qm, (uint32_t)__ldg(q + m));
+					u = __fadd_rn(u, __fmul_ru(mt_bound(qm, bt.step), bt.idf));
+				}
+				u = __fadd_rn(u, s_sbs[tid]);
+			}
+			u = tid < nsb ? __fmul_ru(u, infl) : 0.f;
+			const bool a = u != 0.f &&
+			    make_key(u, doc0 + ((tid + 1u) << SB_SHIFT) - 1u) > s_theta;
+			/* Warp w owns superblocks [32 w, 32 w + 32): its live ones are a mask. */
+			live_mask = __ballot_sync(FULL, a);
+			n_live = (uint32_t)__syncthreads_count(a);
+		}
+		BPROF(0);
+
+		/*
+		 * The dense way, for chunks where most superblocks are live: every short
+		 * list's exact block maxima, summed into ub[] from the chunk's postings.
+		 */
+		auto short_lists_dense = [&]() {
 #pragma unroll 8
 			for (uint32_t b = tid; b < BMW_CH_BLOCKS; b += BMW_THREADS)
 				ub[b] = 0.f;
@@ -641,8 +845,7 @@ score_bmw_kernel(const BmwParams p)
 				}
 			}
 			__syncthreads();
-			BPROF(1);
-		}
+		};
 
 		/*
 		 * A warp scores block gb: every token's slice of the block, token
@@ -839,12 +1042,20 @@ score_bmw_kernel(const BmwParams p)
 			__syncthreads();
 		};
 
+		/* Most of the chunk is live: block bounds the dense way (throughput, not latency). */
+		const bool dense = n_live > BMW_DENSE_SB;
+		if (dense && any_list) {
+			short_lists_dense();
+			BPROF(1);
+		}
+
 		/* ---- rounds: bound + select, score, cut ---- */
 		bool first = true;
 		for (;;) {
+			if (n_live == 0)
+				break;		/* nothing of this chunk can enter the top k */
 			if (tid == 0) {
-				const unsigned long long g = max(prime_key,
-				    *(volatile unsigned long long *)(p.thr + slot));
+				const unsigned long long g = *(volatile unsigned long long *)(p.thr + slot);
 
 				if (g > s_theta)
 					s_theta = g;
@@ -893,7 +1104,44 @@ score_bmw_kernel(const BmwParams p)
 						atomicAdd(&s_hist[bin], __popc(same));
 				}
 			};
-			if (first) {
+			/*
+			 * The bounds of a warp's live superblocks against the current
+			 * threshold, four superblocks in flight; `nm` collects the
+			 * superblocks that still have a live block.
+			 */
+			auto sweep = [&](uint32_t mask, uint32_t cutbin, bool count, uint32_t *selw, uint32_t &nm) {
+				while (mask) {
+					uint32_t sbi[4], bb[4];
+					float u[4];
+
+#pragma unroll
+					for (int x = 0; x < 4; x++) {
+						sbi[x] = mask ? (uint32_t)__ffs(mask) - 1u : 0xffffffffu;
+						mask &= mask - 1u;
+					}
+#pragma unroll
+					for (int x = 0; x < 4; x++) {
+						bb[x] = (warp * 32u + (sbi[x] & 31u)) * SBB + lane;
+						u[x] = sbi[x] != 0xffffffffu ? ub[bb[x]] : 0.f;
+					}
+#pragma unroll
+					for (int x = 0; x < 4; x++) {
+						if (count && __any_sync(FULL, alive(bb[x], u[x])))
+							nm |= 1u << (sbi[x] & 31u);
+						select(bb[x], u[x], cutbin, count, selw);
+					}
+				}
+			};
+			/*
+			 * A warp per live superblock, a lane per block.  The first
+			 * pass computes the block bounds: ub[b] = (columns in token
+			 * order + the short lists' block maxima, from the superblock's
+			 * slice of each) * slack.  Superblocks with a live block make
+			 * the next pass's list.
+			 */
+			uint32_t next_mask = 0;
+
+			if (first && dense) {
 				/*
 				 * The bounds themselves, a thread per block, eight
 				 * blocks at a time so that every load of a token's row
@@ -902,7 +1150,8 @@ score_bmw_kernel(const BmwParams p)
 				 */
 				constexpr uint32_t U = 8;
 
-				for (uint32_t i0 = 0; i0 < BMW_PER_THREAD; i0 += U) {
+				/* Block of (warp, i, lane) = 32 (32 warp + i) + lane: superblock 32 warp + i. */
+				for (uint32_t i0 = 0; i0 < (BMW_CH_BLOCKS / BMW_THREADS); i0 += U) {
 					float u[U];
 
 #pragma unroll
@@ -918,7 +1167,7 @@ score_bmw_kernel(const BmwParams p)
 
 #pragma unroll
 						for (uint32_t x = 0; x < U; x++) {
-							const uint32_t b = tid + (i0 + x) * BMW_THREADS;
+							const uint32_t b = warp * (BMW_CH_BLOCKS / BMW_WARPS) + (i0 + x) * 32u + lane;
 
 							m[x] = b < nb ? __ldg(row + b) : 0.f;
 						}
@@ -928,7 +1177,7 @@ score_bmw_kernel(const BmwParams p)
 					}
 #pragma unroll
 					for (uint32_t x = 0; x < U; x++) {
-						const uint32_t b = tid + (i0 + x) * BMW_THREADS;
+						const uint32_t b = warp * (BMW_CH_BLOCKS / BMW_WARPS) + (i0 + x) * 32u + lane;
 
 						if (any_list)
 							u[x] = __fadd_rn(u[x], ub[b]);
@@ -936,17 +1185,82 @@ score_bmw_kernel(const BmwParams p)
 						ub[b] = u[x];
 					}
 #pragma unroll
-					for (uint32_t x = 0; x < U; x++)
-						select(tid + (i0 + x) * BMW_THREADS, u[x], 0u, true, &s_selw[0]);
-				}
-			} else {
-#pragma unroll 4
-				for (uint32_t i = 0; i < BMW_PER_THREAD; i++) {
-					const uint32_t b = tid + i * BMW_THREADS;
+					for (uint32_t x = 0; x < U; x++) {
+						const uint32_t b = warp * (BMW_CH_BLOCKS / BMW_WARPS) + (i0 + x) * 32u + lane;
 
-					select(b, ub[b], 0u, true, &s_selw[0]);
+						/* The warp's 32 blocks are one superblock. */
+						if (__any_sync(FULL, alive(b, u[x])))
+							next_mask |= 1u << (i0 + x);
+						select(b, u[x], 0u, true, &s_selw[0]);
+					}
 				}
+			} else if (!first) {
+				sweep(live_mask, 0u, true, &s_selw[0], next_mask);
+			} else
+			for (uint32_t lm = live_mask; lm; lm &= lm - 1u) {
+				const uint32_t sbi = (uint32_t)__ffs(lm) - 1u, sb = warp * 32u + sbi;
+				const uint32_t b = sb * SBB + lane;
+				const bool vb = b < nb;
+				float u = 0.f;
+
+				if (first) {
+					for (uint32_t j = 0; j < ntok; j++) {
+						const BmwTok &bt = s_tok[j];
+
+						if (bt.col == BMW_BCOL_NONE)
+							continue;
+						const float m = vb ? __ldg(p.bmax + (size_t)bt.col * p.row_stride + cb0 + b) : 0.f;
+
+						u = __fadd_rn(u, __fmul_rn(m, bt.idf));
+					}
+					if (any_list) {
+						const uint32_t sbdoc0 = doc0 + (sb << SB_SHIFT);
+
+						for (uint32_t j = 0; j < ntok; j++) {
+							const BmwTok &bt = s_tok[j];
+
+							if (bt.col != BMW_BCOL_NONE || bt.clo == bt.chi)
+								continue;
+							/* The superblock's mini-tiles, or the tile around it. */
+							const uint32_t i_lo = sbdoc0 >> bt.fine_shift;
+							const uint32_t i_hi = bt.fine_shift > SB_SHIFT ? i_lo + 1u
+							    : min((sbdoc0 + (1u << SB_SHIFT)) >> bt.fine_shift,
+							      bt.fine_shift == MT_SHIFT ? p.n_mt : p.ntiles);
+							const uint32_t lo = max(bt.clo, __ldg(bt.fine + i_lo));
+							const uint32_t hi = min(bt.chi, __ldg(bt.fine + i_hi));
+							const uint2 *list = p.post + bt.post_off;
+
+							for (uint32_t i0 = lo; i0 < hi; i0 += 32) {
+								const uint32_t i = i0 + lane;
+
+								if (i < hi) {
+									const uint2 v[1] = { __ldg(list + i) };
+									const uint32_t rel = v[0].x - sbdoc0;
+
+									if (rel < (1u << SB_SHIFT)) {
+										float sc[1];
+
+										st_score<false, ALGO, 1>(sp, s_logtab, v, bt.idf, sc);
+										atomicMax(&s_wtmp[warp * 32 + (rel >> BSHIFT)],
+										    __float_as_uint(sc[0]));
+									}
+								}
+							}
+							__syncwarp();
+							u = __fadd_rn(u, __uint_as_float(s_wtmp[warp * 32 + lane]));
+							__syncwarp();
+							s_wtmp[warp * 32 + lane] = 0u;
+							__syncwarp();
+						}
+					}
+					u = vb ? __fmul_ru(u, infl) : 0.f;
+					ub[b] = u;
+				}
+				if (__any_sync(FULL, alive(b, u)))
+					next_mask |= 1u << sbi;
+				select(b, u, 0u, true, &s_selw[0]);
 			}
+			live_mask = next_mask;
 			first = false;
 			__syncthreads();
 			uint32_t found = s_selw[0];
@@ -973,12 +1287,9 @@ score_bmw_kernel(const BmwParams p)
 
 				if (cutbin > 0) {
 					/* its own counter: s_selw[0] is still being read */
-#pragma unroll 4
-					for (uint32_t i = 0; i < BMW_PER_THREAD; i++) {
-						const uint32_t b = tid + i * BMW_THREADS;
+					uint32_t unused = 0;
 
-						select(b, ub[b], cutbin, false, &s_selw[1]);
-					}
+					sweep(live_mask, cutbin, false, &s_selw[1], unused);
 					__syncthreads();
 					found = s_selw[1];
 				}

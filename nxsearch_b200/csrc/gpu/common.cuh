@@ -65,6 +65,7 @@ struct DTok {
 	uint32_t		bcol;		// row of its block arrays (bmw.cuh), or 0xffffffff
 	float			wmax;		// the list's largest weight
 	float			wk;		// its k-th largest, k = the batch's ladder step (bmw.cuh); 0 = none
+	const uint8_t *		mtmax;		// long list without block arrays: bytes per mini-tile (bmw.cuh)
 };
 
 /* 16-byte result record (also the NCCL all-gather payload). */

@@ -213,6 +213,12 @@ struct nxsb_engine {
 	uint32_t *	d_bcol_terms = nullptr;		// [n_bcol] term index of a row
 	uint32_t *	d_boff = nullptr;		// [n_bcol][nblocks + 1]
 	float *		d_bmax_bm25 = nullptr, *d_bmax_tfidf = nullptr;	// [n_bcol][row_stride]
+	float *		d_smax_bm25 = nullptr, *d_smax_tfidf = nullptr;	// [n_bcol][sb_stride]
+	uint32_t	sb_stride = 0;
+	/* Long lists without block arrays: a byte per mini-tile (bmw.cuh). */
+	uint8_t *	d_mt_bm25 = nullptr, *d_mt_tfidf = nullptr;	// [n_long][mt_stride]
+	uint32_t *	d_long_terms = nullptr;				// [n_long] term index of a row
+	uint32_t	mt_stride = 0;
 	float *		d_wmax_bm25 = nullptr, *d_wmax_tfidf = nullptr;	// [V] largest weight of a term
 	/* Threshold priming: [V][BMW_LADDER] k-th largest weight of a term. */
 	float *		d_kth_bm25 = nullptr, *d_kth_tfidf = nullptr;
@@ -581,6 +587,11 @@ free_image(nxsb_engine_t *e)
 	dev_free(e->d_boff);
 	dev_free(e->d_bmax_bm25);
 	dev_free(e->d_bmax_tfidf);
+	dev_free(e->d_smax_bm25);
+	dev_free(e->d_smax_tfidf);
+	dev_free(e->d_mt_bm25);
+	dev_free(e->d_mt_tfidf);
+	dev_free(e->d_long_terms);
 	dev_free(e->d_wmax_bm25);
 	dev_free(e->d_wmax_tfidf);
 	dev_free(e->d_kth_bm25);
@@ -760,12 +771,26 @@ upload_stats(nxsb_engine_t *e)
 			block_max_kernel<<<dim3(16, e->n_bcol), 256, 0, e->stream>>>(e->d_post,
 			    e->d_term_off, e->d_bcol_terms, e->row_stride, e->bshift, e->d_logtab,
 			    e->K0, e->K1, e->d_bmax_bm25, e->d_bmax_tfidf);
-			e->launches++;
+			superblock_max_kernel<<<e->n_sms * 4, 256, 0, e->stream>>>(e->d_bmax_bm25,
+			    e->d_bmax_tfidf, e->n_bcol, e->row_stride, e->sb_stride,
+			    e->d_smax_bm25, e->d_smax_tfidf);
+			e->launches += 2;
 		}
 		term_wmax_kernel<<<e->n_sms * 8, 256, 0, e->stream>>>(e->d_post, e->d_term_off,
 		    e->d_bcol, V, e->d_logtab, e->K0, e->K1, e->d_bmax_bm25, e->d_bmax_tfidf,
 		    e->row_stride, e->d_wmax_bm25, e->d_wmax_tfidf);
 		e->launches++;
+		if (e->d_mt_bm25) {
+			const size_t bytes = (size_t)e->n_long * e->mt_stride;
+
+			CK(e, cudaMemsetAsync(e->d_mt_bm25, 0, bytes, e->stream));
+			CK(e, cudaMemsetAsync(e->d_mt_tfidf, 0, bytes, e->stream));
+			minitile_max_kernel<<<e->n_sms * 16, 256, 0, e->stream>>>(e->d_post, e->d_term_off,
+			    e->d_long_terms, e->d_bcol, e->d_skip_mt, e->n_long, e->n_mt, e->mt_stride,
+			    e->d_logtab, e->K0, e->K1, e->d_wmax_bm25, e->d_wmax_tfidf,
+			    e->d_mt_bm25, e->d_mt_tfidf);
+			e->launches++;
+		}
 		if (e->d_kth_bm25) {
 			const size_t lad = (size_t)V * BMW_LADDER * 4;
 
@@ -987,6 +1012,12 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 		if (e->n_long) {
 			cudaMemcpyAsync(d_long, longs.data(), (size_t)e->n_long * 4,
 			    cudaMemcpyHostToDevice, st);
+			if (dev_alloc(&e->d_long_terms, e->n_long) != cudaSuccess) {
+				fail(e, "skip table allocation failed");
+				break;
+			}
+			cudaMemcpyAsync(e->d_long_terms, longs.data(), (size_t)e->n_long * 4,
+			    cudaMemcpyHostToDevice, st);
 			build_skip_rows_kernel<<<e->n_long, 256, 0, st>>>(e->d_post,
 			    e->d_term_off, d_long, e->ntiles, e->d_skip, TILE_SHIFT);
 			build_skip_rows_kernel<<<e->n_long, 256, 0, st>>>(e->d_post,
@@ -1049,6 +1080,9 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 			e->nblocks = std::max(1u, (N + (1u << e->bshift) - 1) >> e->bshift);
 			e->row_stride = (e->nblocks + 31u) & ~31u;
 			e->nchunks = (e->nblocks + BMW_CH_BLOCKS - 1) / BMW_CH_BLOCKS;
+			e->sb_stride = e->nchunks * BMW_CH_SB;
+			/* Whole superblocks of mini-tiles per row, zero padded. */
+			e->mt_stride = e->sb_stride << (e->bshift + 5 - MT_SHIFT);
 			std::vector<uint32_t> bcol(V, BMW_BCOL_NONE), bterms;
 			const size_t stride = e->row_stride;
 
@@ -1078,8 +1112,13 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 			    dev_alloc(&e->d_boff, (size_t)e->n_bcol * (e->nblocks + 1)) == cudaSuccess &&
 			    dev_alloc(&e->d_bmax_bm25, (size_t)e->n_bcol * stride) == cudaSuccess &&
 			    dev_alloc(&e->d_bmax_tfidf, (size_t)e->n_bcol * stride) == cudaSuccess &&
+			    dev_alloc(&e->d_smax_bm25, (size_t)e->n_bcol * e->sb_stride) == cudaSuccess &&
+			    dev_alloc(&e->d_smax_tfidf, (size_t)e->n_bcol * e->sb_stride) == cudaSuccess &&
 			    (e->wide || (dev_alloc(&e->d_wmax_bm25, V) == cudaSuccess &&
 			    dev_alloc(&e->d_wmax_tfidf, V) == cudaSuccess));
+			if (ok && !e->wide && e->bmw_enabled && e->n_long)
+				ok = dev_alloc(&e->d_mt_bm25, (size_t)e->n_long * e->mt_stride) == cudaSuccess &&
+				    dev_alloc(&e->d_mt_tfidf, (size_t)e->n_long * e->mt_stride) == cudaSuccess;
 			/* Threshold priming (bmw.cuh): the ladder tables and, for the
 			 * lists longer than one part, the units of the two-level pass. */
 			std::vector<uint2> units, longs;
@@ -1884,6 +1923,9 @@ run_bmw(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list, Re
 		p.k = k;
 		p.boff = e->d_boff;
 		p.bmax = B.algo == NXSB_ALGO_BM25 ? e->d_bmax_bm25 : e->d_bmax_tfidf;
+		p.smax = B.algo == NXSB_ALGO_BM25 ? e->d_smax_bm25 : e->d_smax_tfidf;
+		p.sb_stride = e->sb_stride;
+		p.n_mt = e->n_mt;
 		p.thr = B.d_thr;
 		p.tile_count = e->d_tile_cnt;
 		p.cand = e->d_cand;
@@ -1917,7 +1959,12 @@ run_bmw(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list, Re
 		const uint64_t items = (uint64_t)n * e->nchunks;
 		const unsigned grid = (unsigned)std::min<uint64_t>(items, (uint64_t)e->n_sms * per_sm);
 
+#ifdef BMW_EXP_KEEP_THR
+		/* Experiment: a rerun of the batch starts from its final thresholds. */
+		CK(e, cudaMemsetAsync(B.d_cand_count, 0, B.zero_bytes - ((char *)B.d_cand_count - (char *)B.d_thr), st));
+#else
 		CK(e, cudaMemsetAsync(B.d_thr, 0, B.zero_bytes, st));
+#endif
 		CK(e, cudaMemsetAsync(e->d_tile_cnt, 0, (size_t)items * 4, st));
 		mark(e, "score_tiles");
 		void *args[] = { &p };
@@ -2124,7 +2171,9 @@ run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
 	    B.algo == NXSB_ALGO_BM25 ? e->d_idf_bm25 : e->d_idf_tfidf,
 	    B.algo == NXSB_ALGO_BM25 ? e->d_wmax_bm25 : e->d_wmax_tfidf,
 	    B.bmw ? (B.algo == NXSB_ALGO_BM25 ? e->d_kth_bm25 : e->d_kth_tfidf) : nullptr,
-	    bmw_ladder_step(B.limit), e->ntiles, B.d_toks);
+	    bmw_ladder_step(B.limit),
+	    B.bmw ? (B.algo == NXSB_ALGO_BM25 ? e->d_mt_bm25 : e->d_mt_tfidf) : nullptr, e->mt_stride,
+	    e->ntiles, B.d_toks);
 	build_temp_skips_kernel<<<B.n_tok_all, 128, 0, st>>>(e->d_post, B.d_toks,
 	    B.d_tmp_skip, e->ntiles);
 	e->launches += 2;

@@ -26,7 +26,10 @@ def run(name, qs):
     n = 8
     for _ in range(n): e.run(h)
     e.sync()
-    t = e.timings(n); st = e.pruning_stats(); st.pop("phase_cycles", None)
+    t = e.timings(n); st = e.pruning_stats(); ph = st.pop("phase_cycles", None)
+    if ph and sum(ph.values()):
+        tot = sum(ph.values())
+        print("     ", {k: f"{100 * v / tot:.0f}%" for k, v in ph.items()})
     named = sum(int(df[t - 1]) for toks, _ in qs for t in toks)
     print(f"{name:28s} {t['score_tiles'] / n:7.3f} ms  blocks/q {st['blocks_scored'] / n / len(qs):8.1f}  "
           f"postings/q {st['postings_scored'] / n / len(qs):9.0f}  rounds/q {st['rounds'] / n / len(qs):6.1f}  named/q {named / len(qs):.3g}", flush=True)
