@@ -5,17 +5,26 @@
     python bench.py --impl reference --gpus N --steps K ...  (CPU reference arm)
 
 A step is one batch of 1024 synthetic OR-queries (1-4 Zipf terms each, SURVEY
-section 8d "C2") scored against the whole index, top-10 per query.  With N > 1
-the SAME 10M-document index is document-sharded over the N GPUs (strong
-scaling, as BASELINE.json's metric is quoted), each rank scores its shard with
-global statistics and the per-shard top-k lists are merged after an NCCL
-all-gather.
+section 8d "C2") PER GPU, scored against the whole index, top-10 per query.
+
+Layouts for N > 1 (--layout, default auto):
+  replica  the 10M-document image is 4.4 GB and fits one B200 forty times
+           over, so every GPU holds the whole index and takes its own stream
+           of query batches -- the reference's own concurrency model, one
+           process with a private index per worker (ref docs/c-api.md:5-8).
+           No data-path collective; weak scaling (N batches per step).
+  shard    the index is document-sharded, every rank scores every query on
+           its shard with global statistics, per-shard top-k lists are merged
+           after an NCCL all-gather (strong scaling).  What a 100M-document
+           index needs (--docs 100000000), and measured beside the replica
+           line as `doc_sharded`: exact top-k pruning does not strong-scale,
+           because each shard pays the threshold warm-up of a whole index.
 
 One JSON line on stdout (rank 0): see the contract in the task description.
 `value`  = device-resident throughput (batches already in HBM),
 `e2e`    = the same through the reference-facing C API with host buffers
-           (query strings in, result arrays out; N > 1: engine C ABI + merge),
-`roofline` = score_stream_kernel against the measured HBM peak,
+           (query strings in, result arrays out) on every rank,
+`roofline` = the scoring kernel against the measured HBM peak,
 `cpu_baseline` = the oracle port on this box's host cores, bounded sample.
 """
 from __future__ import annotations
@@ -145,14 +154,17 @@ def measured_peak() -> tuple[float, str]:
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def recorded_traffic():
-    """DRAM bytes per launch of the scoring kernel from the committed ncu capture."""
+def recorded_traffic(args, per_gpu_docs: int):
+    """DRAM bytes per launch of the scoring kernel from the committed ncu
+    capture (profiles/ncu_traffic.json) -- only when that capture is of this
+    workload (same documents per GPU, batch, limit); else None."""
     p = ROOT / "profiles" / "ncu_traffic.json"
-    if p.exists():
-        try:
-            return json.loads(p.read_text()).get("score_tiles_dram_bytes_per_launch")
-        except Exception:
-            return None
+    try:
+        rec = json.loads(p.read_text())
+        if (rec.get("docs_per_gpu"), rec.get("batch"), rec.get("limit")) == (per_gpu_docs, args.batch, args.limit):
+            return rec
+    except Exception:
+        pass
     return None
 
 
@@ -208,7 +220,7 @@ def run_reference(args, rank: int, world: int) -> None:
     line = {
         "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": steps_done,
         "warmup": args.warmup, "ms_per_step": 1000 * total / steps_done, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "impl": "reference",
         "config": {"workload": workload_name(args), "docs": args.docs, "vocab": args.vocab,
                    "batch": per_step, "limit": args.limit},
@@ -279,6 +291,43 @@ def workload_name(args) -> str:
 # our arm
 
 
+def pick_layout(args, world: int) -> str:
+    """replica while the whole image fits one GPU with room to spare, else shard."""
+    if world == 1:
+        return "replica"
+    if args.layout != "auto":
+        return args.layout
+    image_gb = args.docs * 64 * 8 / 1e9 * 1.6       # postings + block arrays + tables, generous
+    return "replica" if image_gb < 90 else "shard"
+
+
+def timed_value_leg(args, torch, dist, world, dev, stream, engine, searcher, handles, bytes_local, barrier):
+    """W warm-up steps, then K timed steps bracketed by barrier + synchronize,
+    device time from CUDA events on the engine's stream, max over ranks."""
+    n_distinct = len(handles)
+    for s in range(args.warmup):
+        searcher.run(handles[s % n_distinct], args.batch, args.limit)
+    barrier()
+    launches0 = engine.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for s in range(args.steps):
+        searcher.run(handles[(args.warmup + s) % n_distinct], args.batch, args.limit)
+    ev1.record(stream)
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = engine.launches - launches0
+    runs_timed = min(args.steps, 256)
+    kern = engine.timings(runs_timed)
+    timed_bytes = sum(bytes_local[(args.warmup + s) % n_distinct] for s in range(max(0, args.steps - 256), args.steps))
+    if world > 1:
+        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    return elapsed_ms, launches, kern, timed_bytes, runs_timed
+
+
 def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     import torch
     import torch.distributed as dist
@@ -290,108 +339,130 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    # ---- corpus shard + global statistics
-    lo, hi = nxdist.shard_range(args.docs, rank, world)
-    t0 = time.time()
-    corpus = tools.Corpus.generate(hi - lo, args.vocab, first_doc=lo)
-    log(f"[{rank}] shard docs [{lo},{hi}) {corpus.n_pairs} postings generated in {time.time() - t0:.1f}s")
-    df, tokens, ndocs = nxdist.allreduce_stats(np.asarray(corpus.term_df), corpus.token_count, corpus.n_docs, device=dev)
-
-    t0 = time.time()
-    engine = eng_mod.Engine(local_rank)
-    engine.load_corpus(corpus, df=df, token_count=tokens, doc_count=ndocs)
-    log(f"[{rank}] HBM image built in {time.time() - t0:.1f}s")
+    layout = pick_layout(args, world)
     # A dedicated (non-default) stream shared by the engine's kernels, the NCCL
     # collectives and the timing events.
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    engine.set_stream(stream.cuda_stream)
-    searcher = nxdist.ShardedSearcher(engine, rank, world)
-
-    # ---- queries: identical on every rank (deterministic in the global df)
-    n_steps = args.warmup + args.steps
-    n_distinct = min(n_steps, 48)
-    qt = tools.query_terms(corpus.n_terms, df, 4 * args.batch * n_distinct)
-    queries = make_queries(qt, args.batch * n_distinct)
-    batches = [queries[i * args.batch:(i + 1) * args.batch] for i in range(n_distinct)]
-    local_df = np.asarray(corpus.term_df)
-    bytes_local = [batch_bytes(b, local_df) for b in batches]
-    host_batches = [eng_mod.Batch.from_lists(eng_mod.ALGO_BM25, args.limit, [(t, p) for t, p, _ in b]) for b in batches]
-    handles = [engine.upload(hb) for hb in host_batches]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: batches resident in HBM
-    for s in range(args.warmup):
-        searcher.run(handles[s % n_distinct], args.batch, args.limit)
-    barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = engine.launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for s in range(args.steps):
-        searcher.run(handles[(args.warmup + s) % n_distinct], args.batch, args.limit)
-    ev1.record(stream)
-    barrier()
-    elapsed_ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
-    launches = engine.launches - launches0
-    kern = engine.timings(min(args.steps, 256))
-    timed_bytes = sum(bytes_local[(args.warmup + s) % n_distinct] for s in range(max(0, args.steps - 256), args.steps))
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    value = args.batch * args.steps / (elapsed_ms / 1000)
+    def load(lo, hi):
+        t0 = time.time()
+        corpus = tools.Corpus.generate(hi - lo, args.vocab, first_doc=lo)
+        log(f"[{rank}] docs [{lo},{hi}) {corpus.n_pairs} postings generated in {time.time() - t0:.1f}s")
+        if hi - lo == args.docs:
+            df, tokens, ndocs = np.asarray(corpus.term_df).astype(np.uint32), corpus.token_count, corpus.n_docs
+        else:
+            df, tokens, ndocs = nxdist.allreduce_stats(np.asarray(corpus.term_df), corpus.token_count,
+                                                       corpus.n_docs, device=dev)
+        t0 = time.time()
+        engine = eng_mod.Engine(local_rank)
+        engine.load_corpus(corpus, df=df, token_count=tokens, doc_count=ndocs)
+        engine.set_stream(stream.cuda_stream)
+        log(f"[{rank}] HBM image built in {time.time() - t0:.1f}s")
+        return corpus, engine, df
 
-    # ---- e2e: host buffers in, host results out, every step
-    if world == 1:
-        e2e, h2d, d2h, e2e_note = e2e_capi(args, corpus, batches, capi)
+    def stage(corpus, engine, df, seed):
+        """The batches of the run: queries, their algorithmic bytes on this GPU, resident handles."""
+        n_distinct = min(args.warmup + args.steps, 48)
+        qt = tools.query_terms(corpus.n_terms, df, 4 * args.batch * n_distinct, seed=seed)
+        queries = make_queries(qt, args.batch * n_distinct)
+        batches = [queries[i * args.batch:(i + 1) * args.batch] for i in range(n_distinct)]
+        local_df = np.asarray(corpus.term_df)
+        bytes_local = [batch_bytes(b, local_df) for b in batches]
+        host_batches = [eng_mod.Batch.from_lists(eng_mod.ALGO_BM25, args.limit, [(t, p) for t, p, _ in b]) for b in batches]
+        handles = [engine.upload(hb) for hb in host_batches]
+        return batches, bytes_local, host_batches, handles
+
+    doc_sharded = None
+    if layout == "replica":
+        # ---- every GPU holds the whole index and takes its own query stream
+        corpus, engine, df = load(0, args.docs)
+        batches, bytes_local, host_batches, handles = stage(corpus, engine, df, tools.SEED + 1 + 7919 * rank)
+        searcher = nxdist.ShardedSearcher(engine, 0, 1)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        elapsed_ms, launches, kern, timed_bytes, runs_timed = timed_value_leg(
+            args, torch, dist, world, dev, stream, engine, searcher, handles, bytes_local, barrier)
+        clocks = sampler.stop()
+        value = world * args.batch * args.steps / (elapsed_ms / 1000)
+        e2e, h2d, d2h, e2e_note = e2e_capi(args, corpus, batches, capi, rank, world, local_rank, dist, barrier, dev)
+        if world > 1 and not args.no_shard_leg:
+            doc_sharded = shard_leg(args, rank, world, torch, dist, dev, stream, barrier, load, stage, nxdist, tools)
+        parallelism = f"replica x{world}: whole index on every GPU, {world} batches of {args.batch} per step"
+        scaling = "weak"
     else:
+        # ---- document shards + NCCL all-gather merge
+        lo, hi = nxdist.shard_range(args.docs, rank, world)
+        corpus, engine, df = load(lo, hi)
+        batches, bytes_local, host_batches, handles = stage(corpus, engine, df, tools.SEED + 1)
+        searcher = nxdist.ShardedSearcher(engine, rank, world)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        elapsed_ms, launches, kern, timed_bytes, runs_timed = timed_value_leg(
+            args, torch, dist, world, dev, stream, engine, searcher, handles, bytes_local, barrier)
+        clocks = sampler.stop()
+        value = args.batch * args.steps / (elapsed_ms / 1000)
         e2e, h2d, d2h, e2e_note = e2e_sharded(args, engine, searcher, host_batches, barrier, dist, dev)
+        parallelism = f"doc-shard x{world}: every query on every shard, NCCL all-gather + merge"
+        scaling = "strong"
 
-    # ---- roofline of the dominant kernel
+    # ---- roofline of the dominant kernel (this rank's GPU)
     peak, peak_src = measured_peak()
     tile_ms = kern.get("score_tiles", 0.0)
     achieved = timed_bytes / (tile_ms / 1000) / 1e9 if tile_ms > 0 else 0.0
-    runs_timed = min(args.steps, 256)
+    rec = recorded_traffic(args, corpus.n_docs)
     roofline = {
-        "bound": "hbm", "kernel": "score_stream_kernel<LOGIC=false,WIDE=false,BM25>",
+        "bound": "hbm", "kernel": "score_bmw_kernel<BM25, 32-document blocks> (exact top-k with block-max pruning)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-        "traffic": recorded_traffic(), "peak_source": peak_src,
+        "traffic": rec["dram_bytes_per_launch"] if rec else None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": timed_bytes / max(runs_timed, 1),
         "kernel_ms_per_launch": tile_ms / max(runs_timed, 1),
         "kernel_share_of_step": (tile_ms / runs_timed) / (elapsed_ms / args.steps) if tile_ms else None,
         "other_kernels_ms_per_step": {k: v / runs_timed for k, v in kern.items() if k != "score_tiles"},
-        "note": "algorithmic bytes = 8 B x sum of df over query tokens (SURVEY 8d); popular posting "
-                "slices are re-read from L2 across the queries of a batch, so DRAM traffic is lower",
+        "note": "achieved = SURVEY 8d's algorithmic bytes (8 B x sum of df over query tokens: what the reference's "
+                "exhaustive loop and the round-1 streaming kernel touch) / kernel time, so frac > 1 measures work "
+                "AVOIDED by pruning, not HBM utilisation; see `physical` for what the kernel really moves",
     }
+    if rec and tile_ms > 0:
+        ms = tile_ms / max(runs_timed, 1)
+        roofline["physical"] = {
+            "dram_bytes_per_launch": rec["dram_bytes_per_launch"],
+            "dram_gbs": rec["dram_bytes_per_launch"] / (ms / 1000) / 1e9,
+            "hbm_frac": rec["dram_bytes_per_launch"] / (ms / 1000) / 1e9 / peak,
+            "issue_slots_busy_pct": rec.get("issue_slots_busy_pct"),
+            "l2_hit_pct": rec.get("l2_hit_pct"),
+            "limiter": rec.get("limiter"),
+            "source": rec.get("source"),
+        }
 
     line = {
         "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "docs": args.docs, "vocab": args.vocab,
-                   "batch": args.batch, "limit": args.limit, "parallelism": f"doc-shard x{world}",
-                   "distinct_batches": n_distinct,
+                   "batch": args.batch, "global_batch": args.batch * (world if layout == "replica" else 1),
+                   "limit": args.limit, "layout": layout, "parallelism": parallelism,
+                   "distinct_batches": len(handles),
                    "l2": "inputs larger than L2: %.1f GB of postings per GPU, a different batch every step"
                          % (corpus.n_pairs * 8 / 1e9)},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "path": e2e_note},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches) * (world if layout == "replica" else 1),
         "roofline": roofline,
     }
+    if doc_sharded:
+        line["doc_sharded"] = doc_sharded
     if AUX:
         line["index_load"] = dict(AUX, note="10M-document index through the public C API: nxs_index_open of the "
                                             "reference-format files, then the HBM image build inside the first search")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args, corpus, batches[args.warmup % n_distinct], engine, host_batches[args.warmup % n_distinct])
+        i = args.warmup % len(handles)
+        line["cpu_baseline"] = cpu_baseline(args, corpus, batches[i], engine, host_batches[i])
     if rank == 0:
         emit(line)
     for h in handles:
@@ -401,19 +472,59 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         dist.destroy_process_group()
 
 
-def e2e_capi(args, corpus, batches, capi):
-    """N = 1: the public C API, query strings in -> result arrays out."""
-    base = tempfile.mkdtemp(prefix="nxsb_bench_", dir=args.tmpdir)
+def shard_leg(args, rank, world, torch, dist, dev, stream, barrier, load, stage, nxdist, tools):
+    """The same index document-sharded over the ranks (strong scaling): every
+    rank scores every query of a 1024-query batch on its shard, NCCL
+    all-gather, merge.  Reported beside the replica line."""
+    lo, hi = nxdist.shard_range(args.docs, rank, world)
+    corpus, engine, df = load(lo, hi)
+    batches, bytes_local, host_batches, handles = stage(corpus, engine, df, tools.SEED + 1)
+    searcher = nxdist.ShardedSearcher(engine, rank, world)
+    elapsed_ms, launches, kern, timed_bytes, runs_timed = timed_value_leg(
+        args, torch, dist, world, dev, stream, engine, searcher, handles, bytes_local, barrier)
+    out = {"value": args.batch * args.steps / (elapsed_ms / 1000), "unit": UNIT, "scaling": "strong",
+           "ms_per_step": elapsed_ms / args.steps,
+           "kernel_ms_per_launch": kern.get("score_tiles", 0.0) / max(runs_timed, 1),
+           "parallelism": f"doc-shard x{world}: {hi - lo} documents per GPU, every query on every shard, "
+                          "NCCL all-gather of the per-shard top-k + merge_topk_kernel",
+           "note": "device-resident batches, same protocol as `value`"}
+    for h in handles:
+        engine.release(h)
+    engine.close()
+    corpus.close()
+    return out
+
+
+def e2e_capi(args, corpus, batches, capi, rank=0, world=1, local_rank=0, dist=None, barrier=None, dev=None):
+    """The public C API on every rank, query strings in -> result arrays out.
+    One process per GPU, each with its own nxs_t on the SAME index files
+    (rank 0 writes them), the reference's multi-process model."""
+    import shutil
+
+    if rank == 0:
+        base = tempfile.mkdtemp(prefix="nxsb_bench_", dir=args.tmpdir)
+    else:
+        base = None
+    if world > 1:
+        box = [base]
+        dist.broadcast_object_list(box, src=0)
+        base = box[0]
+    os.environ["NXS_GPU_DEVICE"] = str(local_rank)
     try:
-        nxs = capi.Nxs(base)
-        nxs.create_index("bench").close()
-        t0 = time.time()
-        corpus.write(f"{base}/data/bench/nxsterms", f"{base}/data/bench/nxsdtmap")
+        if rank == 0:
+            boot = capi.Nxs(base)
+            boot.create_index("bench").close()
+            boot.close()
+            t0 = time.time()
+            corpus.write(f"{base}/data/bench/nxsterms", f"{base}/data/bench/nxsdtmap")
+            AUX["index_files_write_s"] = round(time.time() - t0, 2)
+        if world > 1:
+            barrier()
         t1 = time.time()
+        nxs = capi.Nxs(base)
         idx = nxs.open_index("bench")
-        AUX["index_files_write_s"] = round(t1 - t0, 2)
         AUX["nxs_index_open_s"] = round(time.time() - t1, 2)
-        log(f"[0] index files written in {t1 - t0:.1f}s, opened through nxs_index_open in {time.time() - t1:.1f}s")
+        log(f"[{rank}] index opened through nxs_index_open in {time.time() - t1:.1f}s")
         import ctypes as C
         strings = [[" OR ".join(corpus.term(t) for t in leaves).encode() for _, _, leaves in b] for b in batches]
         # Host buffers as a C caller holds them: an array of C strings in, and
@@ -424,11 +535,13 @@ def e2e_capi(args, corpus, batches, capi):
         t0 = time.time()
         idx.search_batch(strings[0][:8], limit=args.limit, **params)          # builds the HBM image
         AUX["first_search_image_build_s"] = round(time.time() - t0, 2)
-        log(f"[0] first search (image build) {time.time() - t0:.1f}s")
+        log(f"[{rank}] first search (image build) {time.time() - t0:.1f}s")
         n = len(batches)
         for s in range(args.warmup):
             idx.search_batch_arrays(arrays[s % n], args.limit, **params)
         # (1) one synchronous nxs_index_search_batch call per step
+        if barrier:
+            barrier()
         t0 = time.perf_counter()
         for s in range(args.steps):
             counts, ids, scores = idx.search_batch_arrays(arrays[(args.warmup + s) % n], args.limit, **params)
@@ -437,6 +550,8 @@ def e2e_capi(args, corpus, batches, capi):
         # host parses batch s+1 while the GPU scores batch s.  Every step still
         # takes its strings from host memory, copies its descriptors to the
         # device and drains its results into host arrays.
+        if barrier:
+            barrier()
         t0 = time.perf_counter()
         ticket = idx.search_batch_begin(arrays[args.warmup % n], args.limit, **params)
         for s in range(args.steps):
@@ -445,8 +560,13 @@ def e2e_capi(args, corpus, batches, capi):
             counts, ids, scores = idx.search_batch_end_arrays(ticket)
             ticket = nxt
         dt = time.perf_counter() - t0
-        log(f"[0] e2e: synchronous {args.batch * args.steps / dt_serial:.0f} q/s, "
-            f"pipelined (2 in flight) {args.batch * args.steps / dt:.0f} q/s")
+        if world > 1:
+            import torch
+            t = torch.tensor([dt, dt_serial], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt, dt_serial = float(t[0].item()), float(t[1].item())
+        log(f"[{rank}] e2e: synchronous {world * args.batch * args.steps / dt_serial:.0f} q/s, "
+            f"pipelined (2 in flight) {world * args.batch * args.steps / dt:.0f} q/s")
         assert len(counts) == args.batch and int(counts.max()) <= args.limit and int(counts.sum()) > 0
         # the drained arrays are what the list-building wrapper returns
         last = (args.warmup + args.steps - 1) % n
@@ -455,17 +575,21 @@ def e2e_capi(args, corpus, batches, capi):
             assert [d for d, _ in r] == [int(x) for x in ids[i, :counts[i]]]
         ntok = np.mean([sum(len(t) for t, _, _ in b) for b in batches])
         nprog = np.mean([sum(len(p) for _, p, _ in b) for b in batches])
-        h2d = int(args.batch * 16 + 4 * ntok + 4 * nprog + 8 * args.batch)
-        d2h = int(args.batch * args.limit * 16 + 4 * args.batch)
+        h2d = int(args.batch * 16 + 4 * ntok + 4 * nprog + 8 * args.batch) * world
+        d2h = int(args.batch * args.limit * 16 + 4 * args.batch) * world
         idx.close()
         nxs.close()
-        return (args.batch * args.steps / dt, h2d, d2h,
+        if world > 1:
+            barrier()
+        return (world * args.batch * args.steps / dt, h2d, d2h,
                 "nxs_index_search_batch_begin/_end (C API: C strings in, results drained via "
-                "nxs_resp_iter_result into host arrays; two batches in flight); synchronous "
-                "nxs_index_search_batch: %.0f queries/s" % (args.batch * args.steps / dt_serial))
+                "nxs_resp_iter_result into host arrays; two batches in flight)%s; synchronous "
+                "nxs_index_search_batch: %.0f queries/s"
+                % (f" on each of {world} processes, one GPU each, sharing the index files" if world > 1 else "",
+                   world * args.batch * args.steps / dt_serial))
     finally:
-        import shutil
-        shutil.rmtree(base, ignore_errors=True)
+        if rank == 0:
+            shutil.rmtree(base, ignore_errors=True)
 
 
 def e2e_sharded(args, engine, searcher, host_batches, barrier, dist, dev):
@@ -540,6 +664,9 @@ def main() -> None:
     ap.add_argument("--ref-real-docs", type=int, default=500_000,
                     help="reference arm: also time the compiled reference on an index of this many documents (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layout", default="auto", choices=["auto", "replica", "shard"],
+                    help="N > 1: whole index on every GPU with its own query stream, or document shards + NCCL merge")
+    ap.add_argument("--no-shard-leg", action="store_true", help="replica layout: skip the doc_sharded side measurement")
     ap.add_argument("--tmpdir", default=None)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
