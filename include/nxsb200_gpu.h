@@ -238,6 +238,23 @@ int		nxsb_engine_fuzzy(nxsb_engine_t *, uint32_t n, const char *qblob,
 		    const uint32_t *qoff, uint32_t *out_term, uint32_t *out_dist,
 		    uint32_t *out_true);
 
+/*
+ * The same lookups with the candidate sets laid open ("report
+ * both the reference-compatible candidate set and the true <= 2 set").  For
+ * query i, out_n[i] = the number of vocabulary terms within distance 2, and
+ * the first min(out_n[i], cap) of them, in the BK-tree's breadth-first order,
+ * are at [i * cap ...]: cand_term (1-based id), cand_dist, and cand_flags --
+ * bit 0: the reference's pruned walk visits the term, i.e. it is in the list
+ * bktree_search returns (ref src/algo/bktree.c:219-275; the flagged entries,
+ * in this order, ARE that list); bit 1: the term's total is non-zero (ref
+ * src/index/idxterm.c:239).  out_term / out_dist (may be NULL) as in
+ * nxsb_engine_fuzzy.  A diagnostic call: it allocates and sorts on the host.
+ */
+int		nxsb_engine_fuzzy_candidates(nxsb_engine_t *, uint32_t n,
+		    const char *qblob, const uint32_t *qoff, uint32_t cap,
+		    uint32_t *out_term, uint32_t *out_dist, uint32_t *out_n,
+		    uint32_t *cand_term, uint8_t *cand_dist, uint8_t *cand_flags);
+
 /* Milliseconds spent by the last batch_run / fuzzy call per kernel family
  * (CUDA events on the engine's stream); names[i] are static strings.
  * Returns the number of entries written (<= cap). */

@@ -264,6 +264,7 @@ struct nxsb_engine {
 
 	/* vocabulary (fuzzy) */
 	FuzzyImage	fz;
+	FuzzyScratch	fz_scratch;
 
 	/*
 	 * Delta segments (incremental refresh): child engines on the same
@@ -664,6 +665,7 @@ nxsb_engine_destroy(nxsb_engine_t *e)
 	}
 	free_image(e);
 	fuzzy_free(e->fz);
+	fuzzy_scratch_free(e->fz_scratch);
 	dev_free(e->d_cand);
 	dev_free(e->d_sort_tmp);
 	dev_free(e->d_plan);
@@ -2516,11 +2518,49 @@ nxsb_engine_fuzzy(nxsb_engine_t *e, uint32_t n, const char *qblob,
 	begin_run(e);
 	mark(e, "fuzzy_scan");
 	int launches = 0;
-	if (fuzzy_run(e->fz, n, qblob, qoff, out_term, out_dist, out_true,
-	    e->stream, e->n_sms, &launches) != 0)
+	if (fuzzy_run(e->fz, e->fz_scratch, n, qblob, qoff, out_term, out_dist, out_true,
+	    0, nullptr, nullptr, e->stream, &launches) != 0)
 		return fail(e, "fuzzy scan failed: %s",
 		    cudaGetErrorString(cudaGetLastError()));
 	e->launches += launches;
 	mark(e, "end");
+	return 0;
+}
+
+extern "C" int
+nxsb_engine_fuzzy_candidates(nxsb_engine_t *e, uint32_t n, const char *qblob,
+    const uint32_t *qoff, uint32_t cap, uint32_t *out_term, uint32_t *out_dist,
+    uint32_t *out_n, uint32_t *cand_term, uint8_t *cand_dist, uint8_t *cand_flags)
+{
+	CK(e, cudaSetDevice(e->device));
+	if (!e->fz.loaded)
+		return fail(e, "no vocabulary image loaded");
+	if (cap == 0 || (uint64_t)n * cap > (1ull << 28))
+		return fail(e, "candidate capacity %u x %u queries is out of range", cap, n);
+	std::vector<uint4> recs((size_t)n * cap);
+	std::vector<uint32_t> cnt(n), term(n), dist(n);
+	int launches = 0;
+
+	begin_run(e);
+	mark(e, "fuzzy_scan");
+	if (fuzzy_run(e->fz, e->fz_scratch, n, qblob, qoff, out_term ? out_term : term.data(),
+	    out_dist ? out_dist : dist.data(), nullptr, cap, cnt.data(), recs.data(),
+	    e->stream, &launches) != 0)
+		return fail(e, "fuzzy scan failed: %s", cudaGetErrorString(cudaGetLastError()));
+	e->launches += launches;
+	mark(e, "end");
+	for (uint32_t i = 0; i < n; i++) {
+		uint4 *r = recs.data() + (size_t)i * cap;
+		const uint32_t m = std::min(cnt[i], cap);
+
+		/* BFS rank order: the reached ones, in this order, are the reference's deque. */
+		std::sort(r, r + m, [](const uint4 &a, const uint4 &b) { return a.x < b.x; });
+		out_n[i] = cnt[i];
+		for (uint32_t j = 0; j < m; j++) {
+			cand_term[(size_t)i * cap + j] = r[j].y + 1;
+			cand_dist[(size_t)i * cap + j] = (uint8_t)(r[j].z & 0xffu);
+			cand_flags[(size_t)i * cap + j] = (uint8_t)((r[j].z >> 8) & 3u);
+		}
+	}
 	return 0;
 }

@@ -54,6 +54,10 @@
 #define FZ_MAX_QLEN	64	/* pattern bits */
 #define FZ_ROOT		0xffffffffu
 
+/* Allocation counters of engine.cu (nxsb_alloc_events). */
+static cudaError_t counted_malloc(void **p, size_t bytes);
+static void counted_free(void *p);
+
 struct FuzzyImage {
 	bool		loaded = false;
 	uint32_t	n_terms = 0;
@@ -265,14 +269,42 @@ struct FuzzyBest {
 	uint32_t rank, term, dist;
 };
 
+/*
+ * Optional candidate lists (nxsb_engine_fuzzy_candidates): every vocabulary
+ * term within the tolerance is recorded, with whether the reference's pruned
+ * BK-tree walk would visit it (ref bktree.c:252-254 pushes exactly those) and
+ * whether its total is non-zero.  list[q * cap + i] = { BFS rank, term index,
+ * distance | reached << 8 | live << 9, 0 }; cnt[q] counts past cap.
+ */
+struct FuzzyCandOut {
+	uint32_t *	cnt = nullptr;
+	uint4 *		list = nullptr;
+	uint32_t	cap = 0;
+};
+
 template <typename W>
 __device__ __forceinline__ void
 fuzzy_consider(const FuzzyImage &f, const W *peq, int m, uint32_t t, int d,
-    FuzzyBest &best, uint32_t &n_true)
+    FuzzyBest &best, uint32_t &n_true, const FuzzyCandOut &co, uint32_t qi)
 {
 	if (d > FZ_TOLERANCE)
 		return;
 	n_true++;
+	if (co.cnt) {
+		/* The diagnostic path: every match, reached or not. */
+		const bool reached = bk_reachable<W>(f, peq, m, t);
+		const uint32_t at = atomicAdd(co.cnt + qi, 1u);
+
+		if (at < co.cap)
+			co.list[(size_t)qi * co.cap + at] = make_uint4(f.d_rank[t], t,
+			    (uint32_t)d | (reached ? 0x100u : 0u) | (f.d_live[t] ? 0x200u : 0u), 0u);
+		if (reached && f.d_live[t] && f.d_rank[t] < best.rank) {
+			best.rank = f.d_rank[t];
+			best.term = t;
+			best.dist = d;
+		}
+		return;
+	}
 	if (!f.d_live[t])		/* idxterm.c:239: total must be > 0 */
 		return;
 	const uint32_t r = f.d_rank[t];
@@ -292,7 +324,8 @@ __global__ void __launch_bounds__((NW + 1) * 32)
 fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
     const uint32_t *__restrict__ qoff, const uint32_t *__restrict__ qsel,
     uint32_t n_sel, uint32_t *__restrict__ out_term,
-    uint32_t *__restrict__ out_dist, uint32_t *__restrict__ out_true)
+    uint32_t *__restrict__ out_dist, uint32_t *__restrict__ out_true,
+    const FuzzyCandOut co)
 {
 	__shared__ W s_peq[NW][256];
 	__shared__ __align__(128) uint32_t s_sig[FZ_STAGES][FZ_CHUNK];
@@ -375,7 +408,7 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 			}
 			if (st.score <= FZ_TOLERANCE)
 				fuzzy_consider<W>(f, peq, m, __ldg(f.d_slot16_term + s),
-				    st.score, best, n_true);
+				    st.score, best, n_true, co, qi);
 		}
 		__syncwarp();
 	};
@@ -517,7 +550,7 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 		if (diff > FZ_TOLERANCE || diff < -FZ_TOLERANCE)
 			continue;
 		const int d = myers_blob<W>(peq, m, f.d_blob + s, len);
-		fuzzy_consider<W>(f, peq, m, t, d, best, n_true);
+		fuzzy_consider<W>(f, peq, m, t, d, best, n_true, co, qi);
 	}
 
 	/* Warp argmin over BFS rank. */
@@ -541,20 +574,62 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 	}
 }
 
-static int
-fuzzy_run(FuzzyImage &f, uint32_t n, const char *qblob, const uint32_t *qoff,
-    uint32_t *out_term, uint32_t *out_dist, uint32_t *out_true,
-    cudaStream_t st, int n_sms, int *launches)
-{
-	unsigned char *d_qblob = nullptr;
-	uint32_t *d_qoff = nullptr, *d_sel32 = nullptr, *d_sel64 = nullptr;
-	uint32_t *d_term = nullptr, *d_dist = nullptr, *d_true = nullptr;
+/*
+ * Device buffers of the lookups, grown on demand and kept: a stream of
+ * batches allocates nothing (cudaFree synchronises the whole device).
+ */
+struct FuzzyScratch {
+	unsigned char *	d_qblob = nullptr;
+	uint32_t *	d_words = nullptr;	/* [qoff | sel32 | sel64 | term | dist | true | cand cnt] */
+	uint4 *		d_cand = nullptr;
+	size_t		blob_cap = 0, words_cap = 0, cand_cap = 0;
 	std::vector<uint32_t> sel32, sel64;
-	int rc = -1;
+};
 
-	(void)n_sms;
+static void
+fuzzy_scratch_free(FuzzyScratch &z)
+{
+	counted_free(z.d_qblob);
+	counted_free(z.d_words);
+	counted_free(z.d_cand);
+	z = FuzzyScratch();
+}
+
+template <typename T>
+static bool
+fuzzy_grow(T *&p, size_t &cap, size_t want)
+{
+	if (want <= cap)
+		return true;
+	counted_free(p);
+	p = nullptr;
+	cap = 0;
+	const size_t n = want + want / 2 + 1024;
+
+	if (counted_malloc(reinterpret_cast<void **>(&p), n * sizeof(T)) != cudaSuccess) {
+		p = nullptr;
+		return false;
+	}
+	cap = n;
+	return true;
+}
+
+/*
+ * out_*: host arrays [n].  cand_cap > 0: also the candidate lists, host arrays
+ * cand_cnt[n] and cand[n * cand_cap] (see FuzzyCandOut), unsorted.
+ */
+static int
+fuzzy_run(FuzzyImage &f, FuzzyScratch &z, uint32_t n, const char *qblob, const uint32_t *qoff,
+    uint32_t *out_term, uint32_t *out_dist, uint32_t *out_true,
+    uint32_t cand_cap, uint32_t *cand_cnt, uint4 *cand,
+    cudaStream_t st, int *launches)
+{
+	std::vector<uint32_t> &sel32 = z.sel32, &sel64 = z.sel64;
+
 	if (n == 0)
 		return 0;
+	sel32.clear();
+	sel64.clear();
 	for (uint32_t i = 0; i < n; i++) {
 		const uint32_t m = qoff[i + 1] - qoff[i];
 
@@ -577,43 +652,49 @@ fuzzy_run(FuzzyImage &f, uint32_t n, const char *qblob, const uint32_t *qoff,
 	};
 	std::stable_sort(sel32.begin(), sel32.end(), by_len);
 	std::stable_sort(sel64.begin(), sel64.end(), by_len);
-	do {
-		if (cudaMalloc(&d_qblob, qoff[n] + 16) || cudaMalloc(&d_qoff, ((size_t)n + 1) * 4) ||
-		    cudaMalloc(&d_sel32, (sel32.size() + 1) * 4) ||
-		    cudaMalloc(&d_sel64, (sel64.size() + 1) * 4) ||
-		    cudaMalloc(&d_term, (size_t)n * 4) || cudaMalloc(&d_dist, (size_t)n * 4) ||
-		    cudaMalloc(&d_true, (size_t)n * 4))
-			break;
-		cudaMemcpyAsync(d_qblob, qblob, qoff[n], cudaMemcpyHostToDevice, st);
-		cudaMemcpyAsync(d_qoff, qoff, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st);
-		cudaMemcpyAsync(d_sel32, sel32.data(), sel32.size() * 4, cudaMemcpyHostToDevice, st);
-		cudaMemcpyAsync(d_sel64, sel64.data(), sel64.size() * 4, cudaMemcpyHostToDevice, st);
-		cudaMemsetAsync(d_term, 0, (size_t)n * 4, st);
-		cudaMemsetAsync(d_dist, 0, (size_t)n * 4, st);
-		cudaMemsetAsync(d_true, 0, (size_t)n * 4, st);
-		if (!sel32.empty()) {
-			fuzzy_scan_kernel<uint32_t, FZ_WARPS32><<<(sel32.size() + FZ_WARPS32 - 1) / FZ_WARPS32,
-			    (FZ_WARPS32 + 1) * 32, 0, st>>>(f, d_qblob, d_qoff, d_sel32,
-			    sel32.size(), d_term, d_dist, d_true);
-			(*launches)++;
-		}
-		if (!sel64.empty()) {
-			fuzzy_scan_kernel<unsigned long long, FZ_WARPS><<<(sel64.size() + FZ_WARPS - 1) / FZ_WARPS,
-			    (FZ_WARPS + 1) * 32, 0, st>>>(f, d_qblob, d_qoff, d_sel64,
-			    sel64.size(), d_term, d_dist, d_true);
-			(*launches)++;
-		}
-		cudaMemcpyAsync(out_term, d_term, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
-		cudaMemcpyAsync(out_dist, d_dist, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
-		if (out_true)
-			cudaMemcpyAsync(out_true, d_true, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
-		if (cudaStreamSynchronize(st) != cudaSuccess)
-			break;
-		rc = 0;
-	} while (0);
-	cudaFree(d_qblob); cudaFree(d_qoff); cudaFree(d_sel32); cudaFree(d_sel64);
-	cudaFree(d_term); cudaFree(d_dist); cudaFree(d_true);
-	return rc;
+
+	const size_t nn = n;
+	const size_t o_qoff = 0, o_s32 = o_qoff + nn + 1, o_s64 = o_s32 + nn, o_term = o_s64 + nn,
+	    o_dist = o_term + nn, o_true = o_dist + nn, o_cnt = o_true + nn, words = o_cnt + nn;
+
+	if (!fuzzy_grow(z.d_qblob, z.blob_cap, (size_t)qoff[n] + 16) ||
+	    !fuzzy_grow(z.d_words, z.words_cap, words) ||
+	    (cand_cap && !fuzzy_grow(z.d_cand, z.cand_cap, nn * cand_cap)))
+		return -1;
+	uint32_t *w = z.d_words;
+	FuzzyCandOut co;
+
+	if (cand_cap) {
+		co.cnt = w + o_cnt;
+		co.list = z.d_cand;
+		co.cap = cand_cap;
+	}
+	cudaMemcpyAsync(z.d_qblob, qblob, qoff[n], cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(w + o_qoff, qoff, (nn + 1) * 4, cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(w + o_s32, sel32.data(), sel32.size() * 4, cudaMemcpyHostToDevice, st);
+	cudaMemcpyAsync(w + o_s64, sel64.data(), sel64.size() * 4, cudaMemcpyHostToDevice, st);
+	cudaMemsetAsync(w + o_term, 0, 4 * nn * 4, st);		/* term, dist, true, cand cnt */
+	if (!sel32.empty()) {
+		fuzzy_scan_kernel<uint32_t, FZ_WARPS32><<<(sel32.size() + FZ_WARPS32 - 1) / FZ_WARPS32,
+		    (FZ_WARPS32 + 1) * 32, 0, st>>>(f, z.d_qblob, w + o_qoff, w + o_s32,
+		    sel32.size(), w + o_term, w + o_dist, w + o_true, co);
+		(*launches)++;
+	}
+	if (!sel64.empty()) {
+		fuzzy_scan_kernel<unsigned long long, FZ_WARPS><<<(sel64.size() + FZ_WARPS - 1) / FZ_WARPS,
+		    (FZ_WARPS + 1) * 32, 0, st>>>(f, z.d_qblob, w + o_qoff, w + o_s64,
+		    sel64.size(), w + o_term, w + o_dist, w + o_true, co);
+		(*launches)++;
+	}
+	cudaMemcpyAsync(out_term, w + o_term, nn * 4, cudaMemcpyDeviceToHost, st);
+	cudaMemcpyAsync(out_dist, w + o_dist, nn * 4, cudaMemcpyDeviceToHost, st);
+	if (out_true)
+		cudaMemcpyAsync(out_true, w + o_true, nn * 4, cudaMemcpyDeviceToHost, st);
+	if (cand_cap) {
+		cudaMemcpyAsync(cand_cnt, w + o_cnt, nn * 4, cudaMemcpyDeviceToHost, st);
+		cudaMemcpyAsync(cand, z.d_cand, nn * cand_cap * sizeof(uint4), cudaMemcpyDeviceToHost, st);
+	}
+	return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -1;
 }
 
 #endif

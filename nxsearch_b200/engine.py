@@ -66,6 +66,7 @@ def _bind():
         "nxsb_engine_search_begin_dev": (i, [vp, vp, vp]),
         "nxsb_engine_search_end": (i, [vp, i, vp, vp, vp]),
         "nxsb_engine_fuzzy": (i, [vp, u32, vp, vp, vp, vp, vp]),
+        "nxsb_engine_fuzzy_candidates": (i, [vp, u32, vp, vp, u32, vp, vp, vp, vp, vp, vp]),
         "nxsb_engine_last_timings": (i, [vp, vp, vp, i]),
         "nxsb_engine_timings": (i, [vp, u32, vp, vp, i]),
         "nxsb_engine_launch_count": (u64, [vp]),
@@ -293,6 +294,26 @@ class Engine:
                                                 term.ctypes.data, dist.ctypes.data,
                                                 None if true is None else true.ctypes.data))
         return term, dist, true
+
+    def fuzzy_candidates(self, queries: list[bytes], cap: int = 1024):
+        """Per query: (chosen term, its distance, number of terms within
+        distance 2, [(term id, distance, reached, live)] in BFS order) -- the
+        reached entries are the reference's bktree_search list."""
+        n = len(queries)
+        off = np.zeros(n + 1, dtype=np.uint32)
+        off[1:] = np.cumsum([len(q) for q in queries])
+        blob = b"".join(queries)
+        buf = C.create_string_buffer(blob, len(blob) + 1)
+        term = np.zeros(n, dtype=np.uint32)
+        dist = np.zeros(n, dtype=np.uint32)
+        cnt = np.zeros(n, dtype=np.uint32)
+        ct = np.zeros((n, cap), dtype=np.uint32)
+        cd = np.zeros((n, cap), dtype=np.uint8)
+        cf = np.zeros((n, cap), dtype=np.uint8)
+        self._check(self._lib.nxsb_engine_fuzzy_candidates(
+            self._h, n, C.cast(buf, C.c_void_p), off.ctypes.data, cap, term.ctypes.data, dist.ctypes.data,
+            cnt.ctypes.data, ct.ctypes.data, cd.ctypes.data, cf.ctypes.data))
+        return term, dist, cnt, ct, cd, cf
 
     def timings(self, last_runs: int = 1) -> dict[str, float]:
         """Device milliseconds per kernel family, summed over the last runs

@@ -713,3 +713,37 @@ ora_fuzzy(ora_index_t *ix, const char *q, size_t len, uint32_t *cands,
 	free(queue);
 	return chosen;
 }
+
+/*
+ * Every vocabulary term within LEV_TOLERANCE of q, by brute force over the
+ * whole vocabulary (no tree): the "true <= 2 set" SURVEY 8a F3 asks to be
+ * reported next to the BK-tree's pruned candidate list (the half-open child
+ * range of ref src/algo/bktree.c:151-157 makes that list a subset).  Terms in
+ * id order; returns the count (entries past cap are counted, not stored).
+ */
+size_t
+ora_fuzzy_true(ora_index_t *ix, const char *q, size_t len, uint32_t *terms,
+    uint32_t *dists, size_t cap)
+{
+	size_t n = 0;
+
+	for (uint32_t t = 0; t < ix->n_terms; t++) {
+		size_t tl;
+		const char *ts = term_str(ix, t, &tl);
+		int d;
+
+		if (tl > len + LEV_TOLERANCE || len > tl + LEV_TOLERANCE)
+			continue;
+		d = ora_levdist(q, len, ts, tl);
+		if (d > LEV_TOLERANCE)
+			continue;
+		if (n < cap) {
+			if (terms)
+				terms[n] = t + 1;
+			if (dists)
+				dists[n] = (uint32_t)d;
+		}
+		n++;
+	}
+	return n;
+}

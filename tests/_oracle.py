@@ -123,8 +123,8 @@ class OracleIndex:
         tokens = np.ascontiguousarray(tokens, dtype=np.uint32)
         prog = np.ascontiguousarray(self.or_program(len(tokens)) if prog is None else prog, dtype=np.int32)
         cap = max(self.corpus.n_docs, 1)
-        ids = np.zeros(cap, dtype=np.uint64)
-        sc = np.zeros(cap, dtype=np.float32)
+        ids = np.empty(cap, dtype=np.uint64)        # untouched pages cost nothing
+        sc = np.empty(cap, dtype=np.float32)
         n = self.lib.ora_search_all(self.h, algo, len(tokens), tokens.ctypes.data, len(prog),
                                     prog.ctypes.data, ids.ctypes.data, sc.ctypes.data, cap)
         assert n >= 0, "malformed program"
@@ -138,6 +138,16 @@ class OracleIndex:
                                C.byref(nc), C.byref(nv))
         n = min(nc.value, cap)
         return t, cands[:n].copy(), dists[:n].copy(), nv.value
+
+    def fuzzy_true(self, q: bytes, cap: int = 65536):
+        """Every term within distance 2 of q by brute force: (term ids, distances), id order."""
+        self.lib.ora_fuzzy_true.restype = C.c_size_t
+        self.lib.ora_fuzzy_true.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]
+        terms = np.zeros(cap, dtype=np.uint32)
+        dists = np.zeros(cap, dtype=np.uint32)
+        n = self.lib.ora_fuzzy_true(self.h, q, len(q), terms.ctypes.data, dists.ctypes.data, cap)
+        assert n <= cap
+        return terms[:n].copy(), dists[:n].copy()
 
     def close(self):
         if self.h:

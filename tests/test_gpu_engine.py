@@ -144,3 +144,30 @@ def test_fuzzy_matches_reference_choice(c1_corpus, c1_oracle, c1_engine):
             assert dist[i] == _oracle.port().ora_levdist(q, len(q), c1_corpus.term(t).encode(), len(c1_corpus.term(t)))
         assert true[i] >= len(cands)
     assert found > 1000
+
+
+def test_fuzzy_candidate_sets(c1_corpus, c1_oracle, c1_engine):
+    """SURVEY 8a F3 "producing the same candidate set and distances": the
+    entries flagged as reached are, in order, the list the reference's pruned
+    BK-tree walk builds (term ids and distances), and all entries together are
+    the brute-force set of terms within distance 2."""
+    parent, edge, rank = c1_corpus.bk_mirror()
+    c1_engine.load_vocab(c1_corpus.term_blob, c1_corpus.term_off, c1_corpus.term_total, parent, edge, rank)
+    qs = c1_corpus.fuzzy_terms(500)
+    term, dist, cnt, ct, cd, cf = c1_engine.fuzzy_candidates(qs, cap=2048)
+    plain_term, plain_dist, plain_true = c1_engine.fuzzy(qs, want_true=True)
+    assert np.array_equal(term, plain_term) and np.array_equal(dist, plain_dist) and np.array_equal(cnt, plain_true)
+    pruned_away = 0
+    for i, q in enumerate(qs):
+        n = int(cnt[i])
+        assert n <= 2048
+        pick, cands, dists, _ = c1_oracle.fuzzy(q, cap=8192)
+        reached = [(int(t), int(d)) for t, d, f in zip(ct[i, :n], cd[i, :n], cf[i, :n]) if f & 1]
+        assert reached == list(zip(cands.tolist(), dists.tolist())), q
+        true_t, true_d = c1_oracle.fuzzy_true(q)
+        assert sorted(zip(ct[i, :n].tolist(), cd[i, :n].tolist())) == sorted(zip(true_t.tolist(), true_d.tolist())), q
+        # the pick is the first reached candidate with a non-zero total
+        live = [int(t) for t, f in zip(ct[i, :n], cf[i, :n]) if (f & 3) == 3]
+        assert term[i] == (live[0] if live else 0) == pick, q
+        pruned_away += n - len(reached)
+    assert pruned_away > 0, "the BK-tree's half-open range should lose some true matches"

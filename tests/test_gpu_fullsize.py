@@ -162,16 +162,71 @@ def test_delta_segment_and_removals_equal_the_whole_index(corpus, whole):
 
 
 def test_sample_against_the_oracle(corpus, whole):
+    """128 OR + 64 boolean queries of the full-size index against the oracle
+    port (every match scored on the CPU, a host thread per query)."""
+    from concurrent.futures import ThreadPoolExecutor
     from nxsearch_b200 import engine
 
     ors, bools = queries(corpus)
     ora = _oracle.OracleIndex(corpus)
+    workers = max(1, min(16, len(os.sched_getaffinity(0))))
     try:
-        for algo, k, qs in ((BM25, 10, ors[:12]), (TFIDF, 100, bools[:6])):
+        for algo, k, qs in ((BM25, 10, ors[:128]), (TFIDF, 100, bools[:64]), (TFIDF, 10, ors[128:160])):
             counts, ids, scores = whole.search(engine.Batch.from_lists(algo, k, qs))
-            for i, (toks, prog) in enumerate(qs):
-                all_ids, all_sc = ora.search_all(algo, toks, prog)
+            with ThreadPoolExecutor(max_workers=workers) as pool:
+                truth = list(pool.map(lambda q: ora.search_all(algo, q[0], q[1]), qs))
+            for i, (all_ids, all_sc) in enumerate(truth):
                 check_topk(ids[i, :counts[i]], scores[i, :counts[i]], all_ids, all_sc, k,
                            exact_scores=(algo == TFIDF))
     finally:
         ora.close()
+
+
+def test_c4_fuzzy_at_a_million_terms():
+    """BASELINE config 4 at size: 100 000 query terms against a 1M-term
+    vocabulary in one call; 2 000 of them against the reference's BK-tree
+    search (oracle port, host threads) -- chosen term and distance -- and, for
+    a sample, the candidate sets: the reached list in the reference's order
+    and the brute-force set of terms within distance 2."""
+    from concurrent.futures import ThreadPoolExecutor
+    from nxsearch_b200 import engine, tools
+
+    corpus = tools.Corpus.generate(2000, N_TERMS)           # only the vocabulary matters
+    e = engine.Engine(0)
+    ora = _oracle.OracleIndex(corpus)
+    workers = max(1, min(16, len(os.sched_getaffinity(0))))
+    try:
+        e.load_corpus(corpus)
+        parent, edge, rank = corpus.bk_mirror()
+        e.load_vocab(corpus.term_blob, corpus.term_off, corpus.term_total, parent, edge, rank)
+        qs = corpus.fuzzy_terms(100_000)
+        term, dist, true = e.fuzzy(qs, want_true=True)
+        assert int((term != 0).sum()) > 20_000
+        step = len(qs) // 2000
+        sample = list(range(0, len(qs), step))[:2000]
+        ora.fuzzy(qs[0])                                    # builds the BK-tree once, before the threads
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            ref = list(pool.map(lambda i: ora.fuzzy(qs[i], cap=1 << 16), sample))
+        lev = _oracle.port().ora_levdist
+        for i, (t, cands, dists, _) in zip(sample, ref):
+            assert term[i] == t, (qs[i], term[i], t)
+            if t:
+                s = corpus.term(int(t)).encode()
+                assert dist[i] == lev(qs[i], len(qs[i]), s, len(s))
+            assert true[i] >= len(cands)
+        # candidate sets
+        sub = sample[:96]
+        _, _, cnt, ct, cd, cf = e.fuzzy_candidates([qs[i] for i in sub], cap=1 << 14)
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            brute = list(pool.map(lambda i: ora.fuzzy_true(qs[i], cap=1 << 16), sub))
+        for j, i in enumerate(sub):
+            n = int(cnt[j])
+            assert n == true[i] and n <= 1 << 14
+            _, cands, dists, _ = ref[sample.index(i)]
+            reached = [(int(t), int(d)) for t, d, f in zip(ct[j, :n], cd[j, :n], cf[j, :n]) if f & 1]
+            assert reached == list(zip(cands.tolist(), dists.tolist())), qs[i]
+            assert sorted(zip(ct[j, :n].tolist(), cd[j, :n].tolist())) == sorted(zip(brute[j][0].tolist(), brute[j][1].tolist())), qs[i]
+    finally:
+        ora.close()
+        e.close()
+        corpus.close()

@@ -184,6 +184,30 @@ def test_port_fuzzy_equals_reference(c1_corpus, c1_oracle, ref_c1):
     assert hits > 700
 
 
+def test_port_fuzzy_candidate_list_equals_reference(c1_corpus, c1_oracle, ref_c1):
+    """The whole candidate list, in order: what the reference's own
+    bktree_search() pushes (ref src/algo/bktree.c:252-254, read through
+    oracle/shims/probe_shim.c) == the restated BFS; and it is a subset of the
+    brute-force <= 2 set (the half-open child range loses matches)."""
+    lib = _oracle.ref()
+    if not hasattr(lib, "nxsb_ref_fuzzy_list"):
+        pytest.skip("oracle/_ref was built without the probe shim")
+    lib.nxsb_ref_fuzzy_list.restype = C.c_size_t
+    lib.nxsb_ref_fuzzy_list.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    buf = np.zeros(8192, dtype=np.uint32)
+    nonempty = lost = 0
+    for q in c1_corpus.fuzzy_terms(600):
+        n = lib.nxsb_ref_fuzzy_list(ref_c1.h, q, len(q), buf.ctypes.data, len(buf))
+        _, cands, dists, _ = c1_oracle.fuzzy(q, cap=8192)
+        assert n <= len(buf) and buf[:n].tolist() == cands.tolist(), q
+        true_t, true_d = c1_oracle.fuzzy_true(q)
+        truth = dict(zip(true_t.tolist(), true_d.tolist()))
+        assert all(truth.get(int(t)) == int(d) for t, d in zip(cands, dists)), q
+        nonempty += n > 0
+        lost += len(truth) - n
+    assert nonempty > 300 and lost > 0
+
+
 # ---------------------------------------------------------------------------
 # against the committed reference-made fixtures (no oracle/_ref needed)
 
