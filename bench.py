@@ -48,13 +48,31 @@ sys.path.insert(0, str(ROOT / "tests"))
 METRIC = "BM25 top-10 queries/s, 10M-doc synthetic index"
 UNIT = "queries/s"
 
+# BASELINE.json configs served by this file (--config): the query shape, the
+# ranking algorithm and the limit.  c2 is the headline; c5 is c2 at 100M
+# documents, document-sharded; c4 (fuzzy) has its own step, see run_c4().
+CONFIGS = {
+    "c2": dict(algo="BM25", limit=10, docs=10_000_000, shape="or"),
+    "c3": dict(algo="TF-IDF", limit=100, docs=10_000_000, shape="bool"),
+    "c5": dict(algo="BM25", limit=10, docs=100_000_000, shape="or"),
+}
+
+
+def algo_ids(args):
+    """(engine constant, oracle constant, C API parameter value) of the run's algorithm."""
+    import _oracle
+    from nxsearch_b200 import engine as eng_mod
+    return ((eng_mod.ALGO_BM25, _oracle.BM25, "BM25") if args.algo == "BM25"
+            else (eng_mod.ALGO_TFIDF, _oracle.TFIDF, "TF-IDF"))
+
 
 def metric_name(args) -> str:
-    """BASELINE.json's metric; a run at another size (--docs, --limit) says so."""
-    if args.docs == 10_000_000 and args.limit == 10:
+    """BASELINE.json's metric; a run of another config or size says so."""
+    if args.config == "c2" and args.docs == 10_000_000 and args.limit == 10:
         return METRIC
     docs = f"{args.docs // 1_000_000}M" if args.docs % 1_000_000 == 0 else str(args.docs)
-    return f"BM25 top-{args.limit} queries/s, {docs}-doc synthetic index"
+    kind = "" if args.shape == "or" else " nested AND/OR/NOT"
+    return f"{args.algo}{kind} top-{args.limit} queries/s, {docs}-doc synthetic index"
 
 
 def log(*a):
@@ -80,15 +98,26 @@ def emit(line: dict) -> None:
 # workload
 
 
-def make_queries(term_ids: np.ndarray, n_queries: int):
-    """n_queries OR-queries with 1..4 terms (cycling), as (tokens, program, string-ids).
+def make_queries(term_ids: np.ndarray, n_queries: int, shape: str = "or"):
+    """n_queries queries as (tokens, program, query-string template).
 
-    Token order follows the reference: leaves right-to-left, duplicates merged
-    (ref src/query/query.c:89-103, src/core/tokenizer.c:94-117)."""
-    OP_OR = -3
+    shape "or": 1..4 terms (cycling) joined by OR; "bool":
+    the four C3 templates.  Token order follows the reference: leaves
+    right-to-left, duplicates merged (ref src/query/query.c:89-103,
+    src/core/tokenizer.c:94-117).  The template holds {0}, {1} ... for the
+    leaves' strings; query_string() fills it."""
+    OP_AND, OP_OR, OP_ANDNOT = -2, -3, -4
+    bool_shapes = [("ab&", "{0} AND {1}"), ("ab|c&", "({0} OR {1}) AND {2}"), ("ab-", "{0} AND NOT {1}"),
+                   ("ab|cd|&ef|-", "({0} OR {1}) AND ({2} OR {3}) AND NOT ({4} OR {5})")]
     out, pos = [], 0
     for i in range(n_queries):
-        nt = 1 + (i % 4)
+        if shape == "or":
+            nt = 1 + (i % 4)
+            postfix = "a" + "".join(chr(ord("a") + j) + "|" for j in range(1, nt))
+            text = " OR ".join("{%d}" % j for j in range(nt))
+        else:
+            postfix, text = bool_shapes[i % 4]
+            nt = sum(ch.isalpha() for ch in postfix)
         leaves = [int(t) for t in term_ids[pos:pos + nt]]
         pos += nt
         toks: list[int] = []
@@ -96,11 +125,17 @@ def make_queries(term_ids: np.ndarray, n_queries: int):
             if t not in toks:
                 toks.append(t)
         slot = {t: s for s, t in enumerate(toks)}
-        prog = [slot[leaves[0]]]
-        for t in leaves[1:]:
-            prog += [slot[t], OP_OR]
-        out.append((toks, prog, leaves))
+        prog = []
+        for ch in postfix:
+            prog.append({"&": OP_AND, "|": OP_OR, "-": OP_ANDNOT}[ch] if not ch.isalpha()
+                        else slot[leaves[ord(ch) - ord("a")]])
+        out.append((toks, prog, (text, leaves)))
     return out
+
+
+def query_string(corpus, item) -> str:
+    text, leaves = item[2]
+    return text.format(*(corpus.term(t) for t in leaves))
 
 
 def batch_bytes(batch_items, df) -> int:
@@ -185,6 +220,37 @@ def run_reference(args, rank: int, world: int) -> None:
     from nxsearch_b200 import tools
     import _oracle
 
+    if args.config == "c4":
+        # The reference's BK-tree search (oracle port) over the same vocabulary, all host threads.
+        corpus = tools.Corpus.generate(2000, args.vocab)
+        ora = _oracle.OracleIndex(corpus)
+        cores = len(os.sched_getaffinity(0))
+        per_step = max(cores, min(args.ref_sample * 4, args.fuzzy_terms))
+        n_steps = args.warmup + args.steps
+        qs = corpus.fuzzy_terms(per_step * n_steps)
+        ora.fuzzy(qs[0])
+        times = []
+        with ThreadPoolExecutor(max_workers=cores) as pool:
+            for s in range(n_steps):
+                t0 = time.perf_counter()
+                list(pool.map(lambda q: ora.fuzzy(q)[0], qs[s * per_step:(s + 1) * per_step]))
+                if s >= args.warmup:
+                    times.append(time.perf_counter() - t0)
+                if sum(times) > args.ref_budget and times:
+                    break
+        value = per_step * len(times) / sum(times)
+        emit({"metric": f"fuzzy term lookups/s (Levenshtein <= 2), {args.vocab}-term vocabulary", "value": value,
+              "unit": "lookups/s", "n_gpus": world, "steps": len(times), "warmup": args.warmup,
+              "ms_per_step": 1000 * sum(times) / len(times), "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "u32", "data": "synthetic", "impl": "reference",
+              "config": {"workload": f"C4: {per_step} query terms per step against {corpus.n_terms} vocabulary terms",
+                         "vocab": corpus.n_terms, "terms_per_step": per_step},
+              "cpu_baseline": {"value": value, "unit": "lookups/s", "cores": cores, "kind": "port",
+                               "sample": f"{per_step} query terms/step x {len(times)} steps"},
+              "e2e": {"value": value, "unit": "lookups/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+              "gpu_launches": 0})
+        return
+
     t0 = time.time()
     corpus = tools.Corpus.generate(args.docs, args.vocab)
     log(f"[ref] corpus {corpus.n_docs} docs / {corpus.n_pairs} postings in {time.time() - t0:.1f}s")
@@ -195,11 +261,12 @@ def run_reference(args, rank: int, world: int) -> None:
     per_step = max(cores, min(args.ref_sample, args.batch))
     n_steps = args.warmup + args.steps
     qt = corpus.query_terms(4 * per_step * n_steps)
-    queries = make_queries(qt, per_step * n_steps)
+    queries = make_queries(qt, per_step * n_steps, args.shape)
+    _, ora_algo, _ = algo_ids(args)
 
     def one(q):
         toks, prog, _ = q
-        return ora.search(_oracle.BM25, args.limit, toks, prog)
+        return ora.search(ora_algo, args.limit, toks, prog)
 
     times = []
     with ThreadPoolExecutor(max_workers=cores) as pool:
@@ -258,11 +325,12 @@ def compiled_reference_check(args):
         ridx = rn.open_index("r")
         open_s = time.perf_counter() - t0
         qt = corpus.query_terms(4 * 64)
-        queries = make_queries(qt, 64)
-        strings = [" OR ".join(corpus.term(t) for t in leaves) for _, _, leaves in queries]
+        queries = make_queries(qt, 64, args.shape)
+        strings = [query_string(corpus, q) for q in queries]
+        _, ora_algo, api_algo = algo_ids(args)
         done, t0 = 0, time.perf_counter()
         for q in strings:
-            ridx.search(q, limit=args.limit, algo="BM25")
+            ridx.search(q, limit=args.limit, algo=api_algo)
             done += 1
             if time.perf_counter() - t0 > 10:
                 break
@@ -272,7 +340,7 @@ def compiled_reference_check(args):
         ora = _oracle.OracleIndex(corpus)
         t0 = time.perf_counter()
         for toks, prog, _ in queries[:done]:
-            ora.search(_oracle.BM25, args.limit, toks, prog)
+            ora.search(ora_algo, args.limit, toks, prog)
         port_qps = done / (time.perf_counter() - t0)
         ora.close()
         return {"docs": args.ref_real_docs, "index_open_s": round(open_s, 1), "queries": done,
@@ -283,8 +351,12 @@ def compiled_reference_check(args):
 
 
 def workload_name(args) -> str:
-    return (f"C2: {args.docs} synthetic docs (Zipf(1.0) over {args.vocab} terms, 16-111 tokens), "
-            f"batches of {args.batch} BM25 OR-queries (1-4 terms), top-{args.limit}")
+    what = ("BM25 OR-queries (1-4 terms)" if args.shape == "or" and args.algo == "BM25"
+            else f"{args.algo} OR-queries (1-4 terms)" if args.shape == "or"
+            else f"{args.algo} queries of the templates a AND b | (a OR b) AND c | a AND NOT b | "
+                 "(a OR b) AND (c OR d) AND NOT (e OR f)")
+    return (f"{args.config.upper()}: {args.docs} synthetic docs (Zipf(1.0) over {args.vocab} terms, 16-111 tokens), "
+            f"batches of {args.batch} {what}, top-{args.limit}")
 
 
 # --------------------------------------------------------------------------
@@ -370,11 +442,11 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         """The batches of the run: queries, their algorithmic bytes on this GPU, resident handles."""
         n_distinct = min(args.warmup + args.steps, 48)
         qt = tools.query_terms(corpus.n_terms, df, 4 * args.batch * n_distinct, seed=seed)
-        queries = make_queries(qt, args.batch * n_distinct)
+        queries = make_queries(qt, args.batch * n_distinct, args.shape)
         batches = [queries[i * args.batch:(i + 1) * args.batch] for i in range(n_distinct)]
         local_df = np.asarray(corpus.term_df)
         bytes_local = [batch_bytes(b, local_df) for b in batches]
-        host_batches = [eng_mod.Batch.from_lists(eng_mod.ALGO_BM25, args.limit, [(t, p) for t, p, _ in b]) for b in batches]
+        host_batches = [eng_mod.Batch.from_lists(algo_ids(args)[0], args.limit, [(t, p) for t, p, _ in b]) for b in batches]
         handles = [engine.upload(hb) for hb in host_batches]
         return batches, bytes_local, host_batches, handles
 
@@ -417,16 +489,22 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     achieved = timed_bytes / (tile_ms / 1000) / 1e9 if tile_ms > 0 else 0.0
     rec = recorded_traffic(args, corpus.n_docs)
     roofline = {
-        "bound": "hbm", "kernel": "score_bmw_kernel<BM25, 32-document blocks> (exact top-k with block-max pruning)",
+        "bound": "hbm",
+        "kernel": ("score_bmw_kernel<%s, 32-document blocks> (exact top-k with block-max pruning)" % args.algo
+                   if args.shape == "or" and args.limit <= 128 else
+                   "score_stream_kernel<LOGIC, %s> (TMA-fed stream of every posting, membership byte + truth table)" % args.algo),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": rec["dram_bytes_per_launch"] if rec else None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": timed_bytes / max(runs_timed, 1),
         "kernel_ms_per_launch": tile_ms / max(runs_timed, 1),
         "kernel_share_of_step": (tile_ms / runs_timed) / (elapsed_ms / args.steps) if tile_ms else None,
         "other_kernels_ms_per_step": {k: v / runs_timed for k, v in kern.items() if k != "score_tiles"},
-        "note": "achieved = SURVEY 8d's algorithmic bytes (8 B x sum of df over query tokens: what the reference's "
-                "exhaustive loop and the round-1 streaming kernel touch) / kernel time, so frac > 1 measures work "
-                "AVOIDED by pruning, not HBM utilisation; see `physical` for what the kernel really moves",
+        "note": ("achieved = SURVEY 8d's algorithmic bytes (8 B x sum of df over query tokens: what the reference's "
+                 "exhaustive loop and the round-1 streaming kernel touch) / kernel time, so frac > 1 measures work "
+                 "AVOIDED by pruning, not HBM utilisation; see `physical` for what the kernel really moves"
+                 if args.shape == "or" else
+                 "achieved = SURVEY 8d's algorithmic bytes (8 B x sum of df over query tokens) / kernel time; "
+                 "head-term slices are re-read from L2 across the queries of a batch, so DRAM traffic is lower"),
     }
     if rec and tile_ms > 0:
         ms = tile_ms / max(runs_timed, 1)
@@ -468,6 +546,123 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     for h in handles:
         engine.release(h)
     engine.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_c4(args, rank: int, world: int, local_rank: int) -> None:
+    """BASELINE config 4: a step = one call resolving --fuzzy-terms misspelt
+    query terms against a 1M-term vocabulary (Levenshtein <= 2, the term the
+    reference's idxterm_fuzzysearch picks).  N > 1: every GPU holds the
+    vocabulary and takes its own call per step (no collective)."""
+    import torch
+    import torch.distributed as dist
+    import _oracle
+    from nxsearch_b200 import engine as eng_mod, tools
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    corpus = tools.Corpus.generate(2000, args.vocab)           # only the vocabulary matters
+    e = eng_mod.Engine(local_rank)
+    e.load_corpus(corpus)
+    parent, edge, rank_bfs = corpus.bk_mirror()
+    e.load_vocab(corpus.term_blob, corpus.term_off, corpus.term_total, parent, edge, rank_bfs)
+    n = args.fuzzy_terms
+    qs = corpus.fuzzy_terms(n, seed=tools.SEED + 2 + 7919 * rank)
+    for _ in range(args.warmup):
+        e.fuzzy(qs)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0, dev_ms, kern = e.launches, 0.0, {}
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        term, dist_, _ = e.fuzzy(qs)                            # host strings in, host arrays out, synchronous
+        for k, v in e.last_timings().items():
+            kern[k] = kern.get(k, 0.0) + v
+            dev_ms += v
+    wall = time.perf_counter() - t0
+    barrier()
+    clocks = sampler.stop()
+    launches = e.launches - l0
+    if world > 1:
+        t = torch.tensor([dev_ms, wall], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall = float(t[0].item()), float(t[1].item())
+    lens = np.diff(np.asarray(corpus.term_off)).astype(np.int64)
+    value = world * n * args.steps / (dev_ms / 1e3)
+    steps_per_s = world * float(n) * float(lens.sum()) * args.steps / (dev_ms / 1e3)
+    rec = None
+    try:
+        rec = json.loads((ROOT / "profiles" / "ncu_fuzzy.json").read_text())
+    except Exception:
+        pass
+    blob_bytes = sum(len(q) for q in qs)
+    line = {
+        "metric": f"fuzzy term lookups/s (Levenshtein <= 2), {args.vocab}-term vocabulary", "value": value,
+        "unit": "lookups/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": f"C4: {n} query terms (a vocabulary term with 1-2 byte edits) per step against "
+                               f"{corpus.n_terms} vocabulary terms, the reference's BK-tree choice reproduced",
+                   "vocab": corpus.n_terms, "terms_per_step": n, "layout": "replica",
+                   "l2": "the vocabulary image (slots + signatures, ~40 MB) is L2-resident by design; every step "
+                         "re-reads all of it for every query term"},
+        "clocks": clocks,
+        "e2e": {"value": world * n * args.steps / wall, "unit": "lookups/s", "h2d_bytes_per_step": blob_bytes + 4 * (n + 1),
+                "d2h_bytes_per_step": 8 * n,
+                "path": "nxsb_engine_fuzzy (engine C ABI: query strings in host memory in, term ids and distances "
+                        "out to host arrays, synchronous) -- what nxs_index_search calls for unresolved tokens"},
+        "gpu_launches": int(launches) * world,
+        "roofline": {"bound": "int-alu", "kernel": "fuzzy_scan_kernel<u32> (signature prefilter + Myers bit-parallel)",
+                     "achieved": steps_per_s / 1e9, "peak": None, "unit": "G Myers column steps/s (SURVEY 8d: sum of "
+                     "len(vocabulary term) per query term)", "frac": None,
+                     "pairs_per_s": world * float(n) * corpus.n_terms * args.steps / (dev_ms / 1e3),
+                     "kernel_ms_per_launch": kern.get("fuzzy_scan", dev_ms) / args.steps,
+                     "int_pipe": rec, "traffic": rec.get("dram_bytes_per_launch") if rec else None,
+                     "note": "integer-pipe bound (SURVEY 8d); the signature tests skip most Myers steps the "
+                             "algorithmic figure counts, so steps/s is a throughput score, not pipe utilisation"},
+        "resolved_terms": int((term != 0).sum()),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from concurrent.futures import ThreadPoolExecutor
+        ora = _oracle.OracleIndex(corpus)
+        ora.fuzzy(qs[0])                                        # builds the BK-tree
+        done, t1 = 0, time.perf_counter()
+        for q in qs[:args.cpu_sample * 8]:
+            ora.fuzzy(q)
+            done += 1
+            if time.perf_counter() - t1 > args.cpu_budget:
+                break
+        cpu_dt = time.perf_counter() - t1
+        sample = list(range(0, n, max(1, n // 2000)))[:2000]
+        with ThreadPoolExecutor(max_workers=max(1, min(16, len(os.sched_getaffinity(0))))) as pool:
+            ref = list(pool.map(lambda i: ora.fuzzy(qs[i])[0], sample))
+        lev = _oracle.port().ora_levdist
+        for i, t_ref in zip(sample, ref):
+            assert term[i] == t_ref, (qs[i], int(term[i]), t_ref)
+            if t_ref:
+                s_ = corpus.term(int(t_ref)).encode()
+                assert dist_[i] == lev(qs[i], len(qs[i]), s_, len(s_))
+        ora.close()
+        line["cpu_baseline"] = {"value": done / cpu_dt, "unit": "lookups/s", "cores": 1, "kind": "port",
+                                "sample": f"first {done} query terms, BK-tree walk over the same vocabulary",
+                                "parity_checked_terms": len(sample),
+                                "parity": "chosen term id and edit distance exact on %d terms" % len(sample)}
+    if rank == 0:
+        emit(line)
+    e.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -526,12 +721,12 @@ def e2e_capi(args, corpus, batches, capi, rank=0, world=1, local_rank=0, dist=No
         AUX["nxs_index_open_s"] = round(time.time() - t1, 2)
         log(f"[{rank}] index opened through nxs_index_open in {time.time() - t1:.1f}s")
         import ctypes as C
-        strings = [[" OR ".join(corpus.term(t) for t in leaves).encode() for _, _, leaves in b] for b in batches]
+        strings = [[query_string(corpus, q).encode() for q in b] for b in batches]
         # Host buffers as a C caller holds them: an array of C strings in, and
         # every result drained through the public iterator into host arrays
         # (nxsb_resp_collect) -- no Python objects per result.
         arrays = [(C.c_char_p * len(s))(*s) for s in strings]
-        params = dict(algo="BM25", fuzzymatch=False)
+        params = dict(algo=algo_ids(args)[2], fuzzymatch=False)
         t0 = time.time()
         idx.search_batch(strings[0][:8], limit=args.limit, **params)          # builds the HBM image
         AUX["first_search_image_build_s"] = round(time.time() - t0, 2)
@@ -625,6 +820,7 @@ def cpu_baseline(args, corpus, batch_items, engine, host_batch):
     queries double as an in-run parity check of the GPU results."""
     import _oracle
 
+    _, ora_algo, _ = algo_ids(args)
     t0 = time.time()
     ora = _oracle.OracleIndex(corpus)
     log(f"[0] oracle index built in {time.time() - t0:.1f}s")
@@ -632,19 +828,25 @@ def cpu_baseline(args, corpus, batch_items, engine, host_batch):
     done, checked = 0, 0
     t0 = time.perf_counter()
     for i, (toks, prog, _) in enumerate(batch_items[:args.cpu_sample]):
-        ora.search(_oracle.BM25, args.limit, toks, prog)
+        ora.search(ora_algo, args.limit, toks, prog)
         done += 1
         if time.perf_counter() - t0 > args.cpu_budget:
             break
     dt = time.perf_counter() - t0
-    for i, (toks, prog, _) in enumerate(batch_items[:min(done, 8)]):
-        all_ids, all_sc = ora.search_all(_oracle.BM25, toks, prog)
-        _oracle.check_topk(ids[i, :counts[i]], scores[i, :counts[i]], all_ids, all_sc, args.limit)
+    from concurrent.futures import ThreadPoolExecutor
+    n_check = min(len(batch_items), args.parity_queries)
+    with ThreadPoolExecutor(max_workers=max(1, min(16, len(os.sched_getaffinity(0))))) as pool:
+        truth = list(pool.map(lambda q: ora.search_all(ora_algo, q[0], q[1]), batch_items[:n_check]))
+    for i, (all_ids, all_sc) in enumerate(truth):
+        _oracle.check_topk(ids[i, :counts[i]], scores[i, :counts[i]], all_ids, all_sc, args.limit,
+                           exact_scores=(args.algo != "BM25"))
         checked += 1
     ora.close()
     return {"value": done / dt, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"first {done} queries of one timed batch, full {args.docs}-doc index",
-            "parity_checked_queries": checked}
+            "parity_checked_queries": checked,
+            "parity": "ids exact, scores %s, order modulo ties -- every match scored by the port on %d queries"
+                      % ("bit-equal" if args.algo != "BM25" else "within 1e-5 relative", checked)}
 
 
 def main() -> None:
@@ -653,10 +855,16 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--docs", type=int, default=10_000_000)
+    ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"],
+                    help="BASELINE.json config: c2 BM25 OR top-10 (headline), c3 TF-IDF boolean top-100, "
+                         "c4 fuzzy lookups, c5 = c2 at 100M documents, document-sharded")
+    ap.add_argument("--docs", type=int, default=None)
     ap.add_argument("--vocab", type=int, default=1_000_000)
     ap.add_argument("--batch", type=int, default=1024)
-    ap.add_argument("--limit", type=int, default=10)
+    ap.add_argument("--limit", type=int, default=None)
+    ap.add_argument("--algo", default=None, choices=["BM25", "TF-IDF"])
+    ap.add_argument("--parity-queries", type=int, default=64, help="queries of one batch checked against the oracle")
+    ap.add_argument("--fuzzy-terms", type=int, default=100_000, help="c4: query terms per step")
     ap.add_argument("--cpu-sample", type=int, default=64)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for cpu_baseline")
     ap.add_argument("--ref-sample", type=int, default=64, help="queries per step of the reference arm")
@@ -670,6 +878,13 @@ def main() -> None:
     ap.add_argument("--tmpdir", default=None)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = CONFIGS.get(args.config, CONFIGS["c2"])
+    args.docs = args.docs or cfg["docs"]
+    args.limit = args.limit or cfg["limit"]
+    args.algo = args.algo or cfg["algo"]
+    args.shape = cfg["shape"]
+    if args.config == "c5" and args.layout == "auto":
+        args.layout = "shard"
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -679,7 +894,10 @@ def main() -> None:
     else:
         if world != args.gpus:
             log(f"note: --gpus {args.gpus} but WORLD_SIZE={world}; using {world} rank(s)")
-        run_ours(args, rank, world, local_rank)
+        if args.config == "c4":
+            run_c4(args, rank, world, local_rank)
+        else:
+            run_ours(args, rank, world, local_rank)
 
 
 if __name__ == "__main__":
