@@ -535,6 +535,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     }
     if doc_sharded:
         line["doc_sharded"] = doc_sharded
+    if "latency" in AUX:
+        line["latency"] = AUX.pop("latency")
     if AUX:
         line["index_load"] = dict(AUX, note="10M-document index through the public C API: nxs_index_open of the "
                                             "reference-format files, then the HBM image build inside the first search")
@@ -774,6 +776,22 @@ def e2e_capi(args, corpus, batches, capi, rank=0, world=1, local_rank=0, dist=No
         d2h = int(args.batch * args.limit * 16 + 4 * args.batch) * world
         idx.close()
         nxs.close()
+        if rank == 0 and not args.no_latency:
+            # The call every caller of the reference makes: ONE query per
+            # nxs_index_search (ref src/core/lua.c:341-367, src/utils/benchmark.c:204),
+            # from a C program linked with libnxsearch.so, its own process and nxs_t.
+            import _ccaller
+            try:
+                singles = [q.decode() for q in strings[0][:args.latency_queries]]
+                t0 = time.time()
+                lat = _ccaller.latency(base, "bench", algo_ids(args)[2], args.limit, singles, device=local_rank)
+                lat["path"] = ("nxs_index_search, one query per call, from tests/c/nxs_caller.c (C, linked with "
+                               "libnxsearch.so); includes parsing, term lookup, H2D, kernels, D2H, response")
+                AUX["latency"] = lat
+                log(f"[0] single-query nxs_index_search: p50 {lat['p50_us']:.0f} us, p99 {lat['p99_us']:.0f} us, "
+                    f"{lat['serial_queries_per_s']:.0f} q/s serial ({time.time() - t0:.1f}s incl. open + image build)")
+            except Exception as exc:            # the leg is informational
+                log(f"[0] latency leg failed: {exc}")
         if world > 1:
             barrier()
         return (world * args.batch * args.steps / dt, h2d, d2h,
@@ -872,6 +890,8 @@ def main() -> None:
     ap.add_argument("--ref-real-docs", type=int, default=500_000,
                     help="reference arm: also time the compiled reference on an index of this many documents (0: skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the single-query nxs_index_search leg")
+    ap.add_argument("--latency-queries", type=int, default=1024)
     ap.add_argument("--layout", default="auto", choices=["auto", "replica", "shard"],
                     help="N > 1: whole index on every GPU with its own query stream, or document shards + NCCL merge")
     ap.add_argument("--no-shard-leg", action="store_true", help="replica layout: skip the doc_sharded side measurement")

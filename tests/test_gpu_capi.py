@@ -392,3 +392,29 @@ def test_one_oversized_query_does_not_take_the_batch_down(nxs):
     ok = "aa" + "".join(" AND (aa" for _ in range(20)) + ")" * 20
     assert len(idx.search(ok, limit=50)) == 29
     idx.close()
+
+
+def test_a_c_program_links_the_library_and_gets_the_same_answers(nxs):
+    """The boundary from C: tests/c/nxs_caller.c, compiled against
+    include/nxs.h and linked with libnxsearch.so (as the reference's own CLI
+    is, ref src/utils/benchmark.c:199-215), opens the index files another
+    process wrote and returns what the ctypes binding returns."""
+    import _ccaller
+
+    corpus = tools.Corpus.generate(20_000, 5_000)
+    nxs.create_index("c").close()
+    corpus.write(f"{nxs.base}/data/c/nxsterms", f"{nxs.base}/data/c/nxsdtmap")
+    idx = nxs.open_index("c")
+    qt = corpus.query_terms(400)
+    queries = [" OR ".join(corpus.term(int(t)) for t in qt[i:i + 1 + i % 4]) for i in range(0, 300, 4)]
+    queries += [f"{corpus.term(int(qt[300 + i]))} AND NOT {corpus.term(int(qt[350 + i]))}" for i in range(20)]
+    for algo, limit in (("BM25", 10), ("TF-IDF", 100)):
+        got = _ccaller.results(nxs.base, "c", algo, limit, queries)
+        assert len(got) == len(queries)
+        for q, g in zip(queries, got):
+            ref = idx.search(q, limit=limit, algo=algo, fuzzymatch=False)
+            assert [d for d, _ in g] == [d for d, _ in ref], q
+            assert all(np.float32(a) == np.float32(b) for (_, a), (_, b) in zip(g, ref)), q
+    lat = _ccaller.latency(nxs.base, "c", "BM25", 10, queries)
+    assert lat["queries"] == len(queries) and lat["p50_us"] > 0
+    idx.close()

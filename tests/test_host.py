@@ -224,6 +224,25 @@ def test_no_gpu_means_a_loud_error_not_a_fallback(nxs):
         engine.Engine(0)
 
 
+def test_a_c_program_compiles_against_the_header_and_links_the_library(nxs):
+    """tests/c/nxs_caller.c builds with -Wall -Wextra -Werror against
+    include/nxs.h and libnxsearch.so and runs; without a GPU every search is the
+    loud NXS_ERR_SYSTEM, with one the answers are checked in test_gpu_capi.py."""
+    import _ccaller
+    from nxsearch_b200 import engine
+
+    idx = nxs.create_index("c")
+    idx.add(1, "alpha beta")
+    idx.add(2, "beta gamma")
+    idx.close()
+    out = _ccaller.run(nxs.base, "c", "BM25", 10, ["alpha", "beta OR gamma"]).splitlines()
+    assert len(out) == 2
+    if engine.device_count() == 0:
+        assert all(line.startswith("error 2 ") for line in out), out
+    else:
+        assert out[0].split()[0] == "1" and out[1].split()[0] == "2", out
+
+
 def test_index_files_are_interchangeable_with_the_reference(nxs, c1_corpus):
     """Files written through nxs_index_add here open in the compiled reference
     and vice versa, byte-identical for the same sequence of adds."""
