@@ -492,7 +492,9 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         "bound": "hbm",
         "kernel": ("score_bmw_kernel<%s, 32-document blocks> (exact top-k with block-max pruning)" % args.algo
                    if args.shape == "or" and args.limit <= 128 else
-                   "score_stream_kernel<LOGIC, %s> (TMA-fed stream of every posting, membership byte + truth table)" % args.algo),
+                   "score_bmw_kernel<LOGIC, %s> (block bounds + present-token masks + a membership byte per document) for "
+                   "queries with <= 3 positive terms, score_stream_kernel<LOGIC> (every posting streamed) for the rest; "
+                   "kernel time is their sum" % args.algo),
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
         "traffic": rec["dram_bytes_per_launch"] if rec else None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": timed_bytes / max(runs_timed, 1),

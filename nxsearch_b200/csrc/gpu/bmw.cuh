@@ -36,6 +36,17 @@
  *        finalize_cells_kernel merges for the stream kernel, and the query's
  *        threshold becomes the exact k-th best of all its cells so far.
  *
+ * LOGIC = true serves boolean queries of at most 8 tokens (ref get_expr_bitmap,
+ * src/query/search.c:118-174): every token of a matching document scores, NOT
+ * side included (search.c:235-272), so the bound is the same sum.  What is
+ * added is set membership: a block (superblock) bounds to zero when the tokens
+ * present in it cannot satisfy the program (the subset closure of the query's
+ * truth table -- this is where "a AND b" skips everything without both), and
+ * the block accumulator keeps a membership byte per document next to the sum,
+ * tested against the truth table when candidates are picked.  No threshold
+ * priming: a term's k-th weight says nothing about documents that also
+ * satisfy an AND.
+ *
  * Arithmetic is st_score() of stream.cuh, hence identical bits; ties still
  * fall to the higher document id because a bound is compared as the key
  * (bound, last document of the block).
@@ -56,7 +67,10 @@
 #define BMW_SEL		512u			/* blocks selected per round */
 #define BMW_K_MAX	128u			/* limit served by this kernel */
 #define BMW_HIST	64u
-#define BMW_ROUND_BLOCKS 64u			/* blocks of a partial round */
+#define BMW_ROUND_BLOCKS 64u			/* blocks of a partial round, at least */
+#ifndef BMW_ROUND_K
+#define BMW_ROUND_K	2u			/* ... and this many per requested result */
+#endif
 #define BMW_BCOL_NONE	0xffffffffu
 #define BMW_SHIFT_MIN	5
 #define BMW_SHIFT_MAX	8
@@ -91,6 +105,7 @@ struct BmwParams {
 	const float *		bmax;		/* [n_bcol][row_stride], the batch's algorithm */
 	const float *		smax;		/* [n_bcol][sb_stride]: maxima per superblock of 32 blocks */
 	uint32_t		sb_stride, n_mt;
+	const uint32_t *	tt;		/* boolean queries: [n_q][8] truth table, then [n_q][8] its subset closure */
 	unsigned long long *	thr;		/* [n_q] */
 	uint32_t *		tile_count;	/* [n_q][nchunks] */
 	unsigned long long *	cand;		/* [n_q][nchunks][k] */
@@ -111,15 +126,21 @@ struct BmwTok {
 	float			prime;		/* its k-th largest score (0: fewer postings) */
 	const uint8_t *		mtmax;		/* mini-tile maxima bytes, or NULL */
 	float			step;		/* what one unit of those bytes is worth */
+	float			bidf;		/* idf in bounds: 0 for a token no matching document can hold */
 };
+static_assert(sizeof(BmwTok) == 64, "token records are 64 bytes");
 
-template <uint32_t BSHIFT>
+#define BMW_LOGIC_SHIFT	5u			/* block size boolean queries are served at */
+#define BMW_LOGIC_TOKENS	8u			/* tokens of a boolean query served here (a membership byte) */
+
+template <uint32_t BSHIFT, bool LOGIC = false>
 struct BmwCfg {
 	static constexpr uint32_t BS = 1u << BSHIFT;
 	static constexpr uint32_t NP = BS / 32;
+	static constexpr uint32_t MAXTOK = LOGIC ? BMW_LOGIC_TOKENS : NXSB_MAX_QUERY_TOKENS;
 	static constexpr size_t SMEM = BMW_CH_BLOCKS * 4 + BMW_CAND * 8 + BMW_K_MAX * 8 +
-	    BMW_WARPS * BS * 4 + BMW_SEL * 2 + LOGTAB_N * 4 +
-	    NXSB_MAX_QUERY_TOKENS * sizeof(BmwTok);
+	    BMW_WARPS * BS * 4 * (LOGIC ? 2 : 1) + BMW_SEL * 2 + LOGTAB_N * 4 +
+	    MAXTOK * sizeof(BmwTok);
 };
 
 /* ---- image side: block offsets and block maxima of the column terms ---- */
@@ -609,11 +630,11 @@ term_kth_merge_kernel(const uint2 *__restrict__ longs, uint32_t n_long,
 
 /* ---- the scorer --------------------------------------------------------- */
 
-template <int ALGO, uint32_t BSHIFT>
+template <int ALGO, uint32_t BSHIFT, bool LOGIC>
 __global__ void __launch_bounds__(BMW_THREADS, 4)
 score_bmw_kernel(const BmwParams p)
 {
-	using Cfg = BmwCfg<BSHIFT>;
+	using Cfg = BmwCfg<BSHIFT, LOGIC>;
 	constexpr uint32_t BS = Cfg::BS, NP = Cfg::NP;
 	constexpr uint32_t FULL = 0xffffffffu;
 	constexpr uint32_t SBB = 32u, SB_SHIFT = BSHIFT + 5u;
@@ -624,13 +645,15 @@ score_bmw_kernel(const BmwParams p)
 	unsigned long long *s_cand = reinterpret_cast<unsigned long long *>(ub + BMW_CH_BLOCKS);
 	unsigned long long *s_top = s_cand + BMW_CAND;			/* [K_MAX] cut buffer */
 	float *s_acc = reinterpret_cast<float *>(s_top + BMW_K_MAX);	/* [WARPS][BS] */
-	BmwTok *s_tok = reinterpret_cast<BmwTok *>(s_acc + BMW_WARPS * BS);
-	float *s_logtab = reinterpret_cast<float *>(s_tok + NXSB_MAX_QUERY_TOKENS);
+	uint32_t *s_accm = reinterpret_cast<uint32_t *>(s_acc + BMW_WARPS * BS);	/* LOGIC: [WARPS][BS] membership */
+	BmwTok *s_tok = reinterpret_cast<BmwTok *>(s_accm + (LOGIC ? BMW_WARPS * BS : 0));
+	float *s_logtab = reinterpret_cast<float *>(s_tok + Cfg::MAXTOK);
 	uint16_t *s_sel = reinterpret_cast<uint16_t *>(s_logtab + LOGTAB_N);
 
 	__shared__ uint32_t s_item, s_selw[2], s_next, s_ncand, s_overflow, s_cut;
 	__shared__ uint32_t s_hist[BMW_HIST];
 	__shared__ unsigned long long s_theta, s_kth;
+	__shared__ uint32_t s_tt[16];		/* LOGIC: truth table, subset closure */
 	/*
 	 * Scratch of the bound passes, in buffers that are idle until the first
 	 * block is scored (4 CTAs per SM must stay within the 196 KB carve-out:
@@ -639,12 +662,18 @@ score_bmw_kernel(const BmwParams p)
 	float *s_sbs = reinterpret_cast<float *>(s_cand);		/* [CH_SB] short lists' part of a superblock's bound */
 	uint32_t *s_tmp = reinterpret_cast<uint32_t *>(s_cand) + BMW_CH_SB;	/* [CH_SB] one list's superblock maxima */
 	uint32_t *s_wtmp = reinterpret_cast<uint32_t *>(s_top);		/* [WARPS * 32] one list's block maxima, per warp */
+	uint8_t *s_sbmask = reinterpret_cast<uint8_t *>(s_tmp + BMW_CH_SB);	/* LOGIC: [CH_SB] lists without block arrays present in a superblock */
+	auto sat = [&](uint32_t m) -> bool { return (s_tt[m >> 5] >> (m & 31u)) & 1u; };		/* documents with exactly tokens m match */
+	auto satisfiable = [&](uint32_t m) -> bool { return (s_tt[8 + (m >> 5)] >> (m & 31u)) & 1u; };	/* ... some subset of m */
 	static_assert(BMW_CAND * 8 >= 2 * BMW_CH_SB * 4 && BMW_K_MAX * 8 >= BMW_WARPS * 32 * 4, "scratch fits");
 
 	const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	const uint32_t n_items = p.n_q * p.nchunks;
 	const uint32_t k = p.k;
+	/* Blocks of a partial round: enough to hold a few times k documents. */
+	const uint32_t round_blocks = min(BMW_SEL - 64u, max(BMW_ROUND_BLOCKS, BMW_ROUND_K * k));
 	float *wacc = s_acc + warp * BS;
+	uint32_t *wmem = s_accm + (LOGIC ? warp * BS : 0);
 	unsigned long long st_blocks = 0, st_post = 0, st_rounds = 0, st_items = 0;
 
 	for (uint32_t i = tid; i < LOGTAB_N; i += BMW_THREADS)
@@ -700,6 +729,23 @@ score_bmw_kernel(const BmwParams p)
 			bt.prime = __fmul_rn(t.wk, t.idf);
 			bt.mtmax = t.mtmax;
 			bt.step = mt_step(t.wmax);
+			bt.bidf = t.idf;
+			if (LOGIC) {
+				/*
+				 * A token only ever seen under NOT -- no satisfying
+				 * membership holds it -- adds nothing to a matching
+				 * document's score: it stays out of the bounds (its
+				 * postings still decide membership).
+				 */
+				const uint32_t *tt = p.tt + (size_t)slot * 8;
+				const uint32_t pat[5] = { 0xaaaaaaaau, 0xccccccccu, 0xf0f0f0f0u, 0xff00ff00u, 0xffff0000u };
+				uint32_t any = 0;
+
+				for (uint32_t w = 0; w < 8; w++)
+					any |= __ldg(tt + w) & (tid < 5 ? pat[tid] : ((w >> (tid - 5)) & 1u ? 0xffffffffu : 0u));
+				if (!any)
+					bt.bidf = 0.f;
+			}
 			s_tok[tid] = bt;
 		}
 		__syncthreads();
@@ -711,11 +757,11 @@ score_bmw_kernel(const BmwParams p)
 		float prime = 0.f;		/* at least k documents score this much */
 		for (uint32_t j = 0; j < ntok; j++) {
 			any_list |= s_tok[j].col == BMW_BCOL_NONE;
-			best_sum = __fadd_ru(best_sum, s_tok[j].best);
+			best_sum = __fadd_ru(best_sum, s_tok[j].bidf != 0.f ? s_tok[j].best : 0.f);
 			prime = fmaxf(prime, s_tok[j].prime);
 		}
 		/* As a key: every document scoring >= prime stays above it. */
-		const unsigned long long prime_key = prime > 0.f ? make_key(prime, 0u) - 1ull : 0ull;
+		const unsigned long long prime_key = (!LOGIC && prime > 0.f) ? make_key(prime, 0u) - 1ull : 0ull;
 		/*
 		 * A block's bound is summed columns first, short lists after:
 		 * another order than the token list's, which can round a few ulp
@@ -726,6 +772,8 @@ score_bmw_kernel(const BmwParams p)
 		if (tid == 0)
 			s_theta = max(prime_key, *(volatile unsigned long long *)(p.thr + slot));
 		s_wtmp[tid] = 0u;
+		if (LOGIC && tid < 16)
+			s_tt[tid] = __ldg(p.tt + (tid < 8 ? (size_t)slot * 8 + tid : (size_t)(p.n_q + slot) * 8 + tid - 8));
 		__syncthreads();
 
 		BPROF(6);
@@ -737,6 +785,7 @@ score_bmw_kernel(const BmwParams p)
 		 * threshold get block bounds at all.
 		 */
 		const uint32_t nsb = (nb + SBB - 1) / SBB;
+		uint32_t sb_present = 0;	/* LOGIC: tokens with a posting in this thread's superblock */
 		if (any_list) {
 			s_sbs[tid] = 0.f;
 			for (uint32_t j = 0; j < ntok; j++) {
@@ -756,7 +805,10 @@ score_bmw_kernel(const BmwParams p)
 					atomicMax(&s_tmp[(v[0].x - doc0) >> SB_SHIFT], __float_as_uint(sc[0]));
 				}
 				__syncthreads();
-				s_sbs[tid] = __fadd_rn(s_sbs[tid], __uint_as_float(s_tmp[tid]));
+				if (bt.bidf != 0.f)
+					s_sbs[tid] = __fadd_rn(s_sbs[tid], __uint_as_float(s_tmp[tid]));
+				if (LOGIC && s_tmp[tid])
+					sb_present |= 1u << j;
 			}
 			BPROF(1);
 		}
@@ -772,7 +824,18 @@ score_bmw_kernel(const BmwParams p)
 				const float m = tid < nsb ? __ldg(p.smax + (size_t)bt.col * p.sb_stride +
 				    chunk * BMW_CH_SB + tid) : 0.f;
 
-				u = __fadd_rn(u, __fmul_rn(m, bt.idf));
+				u = __fadd_rn(u, __fmul_rn(m, bt.bidf));
+				if (LOGIC && m > 0.f)
+					sb_present |= 1u << j;
+			}
+			uint32_t nc_present = LOGIC ? sb_present & 0xffu : 0u;	/* without the columns: so far only short lists */
+			if (LOGIC) {
+				uint32_t cols = 0;
+
+				for (uint32_t j = 0; j < ntok; j++)
+					if (s_tok[j].col != BMW_BCOL_NONE)
+						cols |= 1u << j;
+				nc_present &= ~cols;
 			}
 			if (any_list) {
 				/* Long lists: the bytes of the superblock's mini-tiles. */
@@ -788,11 +851,21 @@ score_bmw_kernel(const BmwParams p)
 #pragma unroll
 					for (uint32_t m = 0; m < MPS; m++)
 						qm = max(qm, (uint32_t)__ldg(q + m));
-					u = __fadd_rn(u, __fmul_ru(mt_bound(qm, bt.step), bt.idf));
+					u = __fadd_rn(u, __fmul_ru(mt_bound(qm, bt.step), bt.bidf));
+					if (LOGIC && qm) {
+						sb_present |= 1u << j;
+						nc_present |= 1u << j;
+					}
 				}
 				u = __fadd_rn(u, s_sbs[tid]);
 			}
 			u = tid < nsb ? __fmul_ru(u, infl) : 0.f;
+			if (LOGIC) {
+				/* The tokens present here cannot satisfy the program: nothing to find. */
+				if (!satisfiable(sb_present))
+					u = 0.f;
+				s_sbmask[tid] = (uint8_t)nc_present;
+			}
 			const bool a = u != 0.f &&
 			    make_key(u, doc0 + ((tid + 1u) << SB_SHIFT) - 1u) > s_theta;
 			/* Warp w owns superblocks [32 w, 32 w + 32): its live ones are a mask. */
@@ -813,7 +886,7 @@ score_bmw_kernel(const BmwParams p)
 			for (uint32_t j = 0; j < ntok; j++) {
 				const BmwTok bt = s_tok[j];
 
-				if (bt.col != BMW_BCOL_NONE)
+				if (bt.col != BMW_BCOL_NONE || bt.bidf == 0.f)
 					continue;
 				const uint2 *list = p.post + bt.post_off;
 
@@ -856,8 +929,11 @@ score_bmw_kernel(const BmwParams p)
 			const uint32_t base = gb << BSHIFT;
 
 #pragma unroll
-			for (uint32_t r = 0; r < NP; r++)
+			for (uint32_t r = 0; r < NP; r++) {
 				wacc[lane + 32 * r] = 0.f;
+				if (LOGIC)
+					wmem[lane + 32 * r] = 0u;
+			}
 			/* Lane j finds token j's slice of the block. */
 			uint32_t my_lo = 0, my_hi = 0;
 			if (lane < ntok) {
@@ -943,6 +1019,8 @@ score_bmw_kernel(const BmwParams p)
 							float *a = wacc + (v[g][r].x - base);
 
 							*a = __fadd_rn(*a, sc[r]);
+							if (LOGIC)
+								wmem[v[g][r].x - base] |= 1u << j;
 							st_post++;
 						}
 					}
@@ -960,6 +1038,9 @@ score_bmw_kernel(const BmwParams p)
 
 				keys[r] = make_key(val, base + lane + 32 * r);
 				if (val == 0.f || keys[r] <= th)
+					keys[r] = 0;
+				/* get_expr_bitmap: the document's tokens must satisfy the program. */
+				if (LOGIC && !sat(wmem[lane + 32 * r]))
 					keys[r] = 0;
 				mine += keys[r] != 0;
 			}
@@ -1153,10 +1234,14 @@ score_bmw_kernel(const BmwParams p)
 				/* Block of (warp, i, lane) = 32 (32 warp + i) + lane: superblock 32 warp + i. */
 				for (uint32_t i0 = 0; i0 < (BMW_CH_BLOCKS / BMW_THREADS); i0 += U) {
 					float u[U];
+					uint32_t pm[LOGIC ? U : 1];	/* tokens that may have a posting in the block */
 
 #pragma unroll
-					for (uint32_t x = 0; x < U; x++)
+					for (uint32_t x = 0; x < U; x++) {
 						u[x] = 0.f;
+						if (LOGIC)	/* lists without block arrays: as coarse as their superblock */
+							pm[x] = s_sbmask[warp * 32u + i0 + x];
+					}
 					for (uint32_t j = 0; j < ntok; j++) {
 						const BmwTok &bt = s_tok[j];
 
@@ -1172,8 +1257,11 @@ score_bmw_kernel(const BmwParams p)
 							m[x] = b < nb ? __ldg(row + b) : 0.f;
 						}
 #pragma unroll
-						for (uint32_t x = 0; x < U; x++)
-							u[x] = __fadd_rn(u[x], __fmul_rn(m[x], bt.idf));
+						for (uint32_t x = 0; x < U; x++) {
+							u[x] = __fadd_rn(u[x], __fmul_rn(m[x], bt.bidf));
+							if (LOGIC && m[x] > 0.f)
+								pm[x] |= 1u << j;
+						}
 					}
 #pragma unroll
 					for (uint32_t x = 0; x < U; x++) {
@@ -1182,6 +1270,8 @@ score_bmw_kernel(const BmwParams p)
 						if (any_list)
 							u[x] = __fadd_rn(u[x], ub[b]);
 						u[x] = b < nb ? __fmul_ru(u[x], infl) : 0.f;
+						if (LOGIC && !satisfiable(pm[x]))
+							u[x] = 0.f;
 						ub[b] = u[x];
 					}
 #pragma unroll
@@ -1202,6 +1292,7 @@ score_bmw_kernel(const BmwParams p)
 				const uint32_t b = sb * SBB + lane;
 				const bool vb = b < nb;
 				float u = 0.f;
+				uint32_t pm = 0;	/* LOGIC: tokens with a posting in the block */
 
 				if (first) {
 					for (uint32_t j = 0; j < ntok; j++) {
@@ -1211,7 +1302,9 @@ score_bmw_kernel(const BmwParams p)
 							continue;
 						const float m = vb ? __ldg(p.bmax + (size_t)bt.col * p.row_stride + cb0 + b) : 0.f;
 
-						u = __fadd_rn(u, __fmul_rn(m, bt.idf));
+						u = __fadd_rn(u, __fmul_rn(m, bt.bidf));
+						if (LOGIC && m > 0.f)
+							pm |= 1u << j;
 					}
 					if (any_list) {
 						const uint32_t sbdoc0 = doc0 + (sb << SB_SHIFT);
@@ -1247,13 +1340,18 @@ score_bmw_kernel(const BmwParams p)
 								}
 							}
 							__syncwarp();
-							u = __fadd_rn(u, __uint_as_float(s_wtmp[warp * 32 + lane]));
+							if (bt.bidf != 0.f)
+								u = __fadd_rn(u, __uint_as_float(s_wtmp[warp * 32 + lane]));
+							if (LOGIC && s_wtmp[warp * 32 + lane])
+								pm |= 1u << j;
 							__syncwarp();
 							s_wtmp[warp * 32 + lane] = 0u;
 							__syncwarp();
 						}
 					}
 					u = vb ? __fmul_ru(u, infl) : 0.f;
+					if (LOGIC && !satisfiable(pm))
+						u = 0.f;
 					ub[b] = u;
 				}
 				if (__any_sync(FULL, alive(b, u)))
@@ -1277,7 +1375,7 @@ score_bmw_kernel(const BmwParams p)
 
 					for (; bin > 0; bin--) {
 						cum += s_hist[bin];
-						if (cum >= BMW_ROUND_BLOCKS)
+						if (cum >= round_blocks)
 							break;
 					}
 					s_cut = (uint32_t)bin;

@@ -131,6 +131,7 @@ struct Batch {
 	uint32_t	max_tokens_all = 0;	// over every query (plan record stride)
 	uint64_t	bytes = 0;		// algorithmic bytes
 	bool		bmw = false;		// OR queries go through score_bmw_kernel
+	uint32_t	n_logic_pruned = 0;	// ... and so do the first this many of q_logic
 	std::vector<uint32_t> q_or, q_logic;	// host lists
 	/*
 	 * Shared dense prefixes (stream.cuh "base columns"): the distinct ordered
@@ -208,6 +209,7 @@ struct nxsb_engine {
 	 * two postings per block of 2^bshift documents.
 	 */
 	bool		bmw_enabled = true;		// NXSB_BMW=0: every query streams
+	uint32_t	logic_pruned_max_pos = 3;	// boolean queries with more positive tokens stream (NXSB_BMW_LOGIC_POS)
 	uint32_t	bshift = 5, nblocks = 0, row_stride = 0, nchunks = 0, n_bcol = 0;
 	uint32_t *	d_bcol = nullptr;		// [V] row of a term or BMW_BCOL_NONE
 	uint32_t *	d_bcol_terms = nullptr;		// [n_bcol] term index of a row
@@ -538,6 +540,8 @@ nxsb_engine_create(int device)
 		/* NXSB_BMW=0: no block-max pruning, every query streams all its postings. */
 		if ((kv = getenv("NXSB_BMW")) != NULL)
 			e->bmw_enabled = atoi(kv) != 0;
+		if ((kv = getenv("NXSB_BMW_LOGIC_POS")) != NULL)
+			e->logic_pruned_max_pos = (uint32_t)atoi(kv);
 		/* NXSB_PRIME=0: pruning thresholds start at zero (A/B of the priming). */
 		if ((kv = getenv("NXSB_PRIME")) != NULL)
 			e->prime_enabled = atoi(kv) != 0;
@@ -1402,6 +1406,40 @@ validate_batch(nxsb_engine_t *e, const nxsb_batch_t *b)
  * buffers, pack all descriptors into one pinned block and copy it with a
  * single cudaMemcpyAsync.
  */
+/*
+ * How many token slots of a boolean query can be present in a matching
+ * document (a slot only ever under NOT cannot): polarity through the postfix
+ * program, AND NOT swapping its right operand's.  A routing estimate only.
+ */
+static uint32_t
+positive_tokens(const nxsb_batch_t *b, const nxsb_query_t &q)
+{
+	uint32_t pos[NXSB_MAX_QUERY_PROG / 2 + 2], neg[NXSB_MAX_QUERY_PROG / 2 + 2];
+	int sp = 0;
+
+	for (uint32_t c = 0; c < q.n_prog; c++) {
+		const int32_t op = b->prog[q.prog_off + c];
+
+		if (op >= 0) {
+			pos[sp] = 1u << (op & 31);
+			neg[sp++] = 0;
+		} else if (op == NXSB_OP_EMPTY) {
+			pos[sp] = neg[sp] = 0;
+			sp++;
+		} else if (sp >= 2) {
+			sp--;
+			if (op == NXSB_OP_ANDNOT) {
+				pos[sp - 1] |= neg[sp];
+				neg[sp - 1] |= pos[sp];
+			} else {
+				pos[sp - 1] |= pos[sp];
+				neg[sp - 1] |= neg[sp];
+			}
+		}
+	}
+	return sp ? (uint32_t)__builtin_popcount(pos[sp - 1]) : 0;
+}
+
 static int
 fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 {
@@ -1442,6 +1480,24 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 		}
 	}
 	static_assert(sizeof(QDesc) == sizeof(nxsb_query_t), "descriptor layout");
+
+	/*
+	 * Boolean queries: pruning pays while few tokens can add up in one
+	 * document (the block bound is the sum of their maxima and loosens with
+	 * every one: measured, 10M documents, top-100 -- a AND b 4.8 ms per
+	 * batch pruned against 9.1 streamed, (a OR b) AND c 8.0 against 13.1,
+	 * a AND NOT b 2.4 against 12.5, four positive terms 30 against 27).
+	 * Those go first in the list; the rest stream.
+	 */
+	B.n_logic_pruned = 0;
+	if (B.bmw && e->bshift == BMW_LOGIC_SHIFT) {
+		auto mid = std::stable_partition(B.q_logic.begin(), B.q_logic.end(), [&](uint32_t i) {
+			const nxsb_query_t &q = b->queries[i];
+
+			return q.n_tokens <= BMW_LOGIC_TOKENS && positive_tokens(b, q) <= e->logic_pruned_max_pos;
+		});
+		B.n_logic_pruned = (uint32_t)(mid - B.q_logic.begin());
+	}
 
 	/*
 	 * Shared dense prefixes.  The dense terms of an OR query contribute
@@ -1894,7 +1950,8 @@ launch_stream(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist,
  * over (query, chunk) items, then the same per-query merge of the cells.
  */
 static int
-run_bmw(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list, Rec *d_recs)
+run_bmw(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list, Rec *d_recs,
+    bool logic)
 {
 	cudaStream_t st = e->stream;
 	const uint32_t k = B.limit;
@@ -1906,6 +1963,10 @@ run_bmw(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list, Re
 	if (ensure_arena(e, e->d_cand, e->cand_bytes, slots * cells * 8, "candidate arena") == -1 ||
 	    ensure_arena(e, e->d_tile_cnt, e->tile_cnt_bytes, slots * e->nchunks * 4,
 	    "tile count") == -1)
+		return -1;
+	/* Boolean queries: truth tables and their subset closures, 8 + 8 words per query. */
+	if (logic && ensure_arena(e, e->d_tt, e->tt_bytes,
+	    std::max<size_t>(chunk, B.n_q) * 16 * 4, "truth table") == -1)
 		return -1;
 
 	for (uint32_t q0 = 0; q0 < n_list; q0 += chunk) {
@@ -1928,6 +1989,7 @@ run_bmw(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list, Re
 		p.smax = B.algo == NXSB_ALGO_BM25 ? e->d_smax_bm25 : e->d_smax_tfidf;
 		p.sb_stride = e->sb_stride;
 		p.n_mt = e->n_mt;
+		p.tt = e->d_tt;
 		p.thr = B.d_thr;
 		p.tile_count = e->d_tile_cnt;
 		p.cand = e->d_cand;
@@ -1941,10 +2003,17 @@ run_bmw(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list, Re
 		size_t smem = 0;
 #define BMW_PICK(S) do {								\
 		kern = B.algo == NXSB_ALGO_BM25						\
-		    ? (const void *)score_bmw_kernel<NXSB_ALGO_BM25, S>			\
-		    : (const void *)score_bmw_kernel<NXSB_ALGO_TFIDF, S>;		\
+		    ? (const void *)score_bmw_kernel<NXSB_ALGO_BM25, S, false>		\
+		    : (const void *)score_bmw_kernel<NXSB_ALGO_TFIDF, S, false>;	\
 		smem = BmwCfg<S>::SMEM;							\
 	} while (0)
+		if (logic) {
+			/* Boolean queries are served at the default block size only. */
+			kern = B.algo == NXSB_ALGO_BM25
+			    ? (const void *)score_bmw_kernel<NXSB_ALGO_BM25, BMW_LOGIC_SHIFT, true>
+			    : (const void *)score_bmw_kernel<NXSB_ALGO_TFIDF, BMW_LOGIC_SHIFT, true>;
+			smem = BmwCfg<BMW_LOGIC_SHIFT, true>::SMEM;
+		} else
 		switch (e->bshift) {
 		case 5: BMW_PICK(5); break;
 		case 6: BMW_PICK(6); break;
@@ -1968,6 +2037,12 @@ run_bmw(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list, Re
 		CK(e, cudaMemsetAsync(B.d_thr, 0, B.zero_bytes, st));
 #endif
 		CK(e, cudaMemsetAsync(e->d_tile_cnt, 0, (size_t)items * 4, st));
+		if (logic) {
+			mark(e, "plan");
+			truth_tables_kernel<<<n, 256, 0, st>>>(B.d_queries, d_qlist + q0, B.d_prog,
+			    e->d_tt, e->d_tt + (size_t)n * 8);
+			e->launches++;
+		}
 		mark(e, "score_tiles");
 		void *args[] = { &p };
 		CK(e, cudaLaunchKernel(kern, dim3(grid), dim3(BMW_THREADS), args, smem, st));
@@ -1997,7 +2072,7 @@ run_bmw(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list, Re
 template <bool LOGIC>
 static int
 run_list(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list,
-    Rec *d_recs)
+    Rec *d_recs, bool pruned, uint32_t list_off = 0)
 {
 	cudaStream_t st = e->stream;
 	const uint32_t k = B.limit;
@@ -2009,8 +2084,8 @@ run_list(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list,
 	if (n_list == 0)
 		return 0;
 
-	if (!LOGIC && B.bmw)
-		return run_bmw(e, B, d_qlist, n_list, d_recs);
+	if (pruned)
+		return run_bmw(e, B, d_qlist, n_list, d_recs, LOGIC);
 
 	const size_t slots = std::max<size_t>(n_list, slots_for(B.n_q));
 	if (ensure_arena(e, e->d_cand, e->cand_bytes,
@@ -2039,7 +2114,7 @@ run_list(nxsb_engine_t *e, Batch &B, const uint32_t *d_qlist, uint32_t n_list,
 	 */
 	const uint32_t n_virtual = LOGIC ? 0 : B.n_virtual;
 	const uint2 *d_qbase = !stream ? nullptr
-	    : LOGIC ? B.d_qbase_logic		/* no virtual queries: any chunking */
+	    : LOGIC ? B.d_qbase_logic + list_off	/* no virtual queries: any chunking */
 	    : (n_virtual && chunk >= n_list) ? B.d_qbase : nullptr;
 
 	for (uint32_t q0 = 0; q0 < n_list; q0 += chunk) {
@@ -2180,7 +2255,8 @@ run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
 	    B.d_tmp_skip, e->ntiles);
 	e->launches += 2;
 	CK(e, cudaGetLastError());
-	if (e->n_dense && !(B.bmw && B.q_logic.empty())) {
+	const uint32_t n_lp = B.n_logic_pruned, n_ls = (uint32_t)B.q_logic.size() - n_lp;
+	if (e->n_dense && !(B.bmw && n_ls == 0)) {
 		/* Score columns of the dense terms this batch refers to. */
 		const unsigned long long col_words = (unsigned long long)e->ntiles * TILE_DOCS;
 		const dim3 grid(e->n_sms * 4, e->n_dense);
@@ -2198,8 +2274,9 @@ run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
 		CK(e, cudaGetLastError());
 	}
 
-	if (run_list<false>(e, B, B.d_qlist_or, B.q_or.size(), d_recs) == -1 ||
-	    run_list<true>(e, B, B.d_qlist_logic, B.q_logic.size(), d_recs) == -1)
+	if (run_list<false>(e, B, B.d_qlist_or, B.q_or.size(), d_recs, B.bmw) == -1 ||
+	    run_list<true>(e, B, B.d_qlist_logic, n_lp, d_recs, true) == -1 ||
+	    run_list<true>(e, B, B.d_qlist_logic + n_lp, n_ls, d_recs, false, n_lp) == -1)
 		return -1;
 	mark(e, "end");
 	return 0;

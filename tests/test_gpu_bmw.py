@@ -284,3 +284,77 @@ def test_priming_only_raises_the_start(corpus, eng, monkeypatch):
         plain.close()
     assert_identical(primed, unprimed)
     assert s1["blocks_scored"] < s0["blocks_scored"], (s1, s0)
+
+
+@pytest.mark.parametrize("algo,limit", [(TFIDF, 100), (BM25, 10), (TFIDF, 1), (BM25, 128)])
+def test_boolean_pruned_equals_exhaustive_and_oracle(corpus, oracle, eng, algo, limit):
+    """AND / OR / NOT queries through the pruned scorer (block bounds +
+    present-token masks + a membership byte per document) against the
+    streaming scorer -- bit for bit -- and the oracle."""
+    from nxsearch_b200 import engine
+    from test_gpu_stream import bool_queries
+
+    qs = bool_queries(corpus, 384)
+    pruned, full, stats = both_ways(eng, engine.Batch.from_lists(algo, limit, qs))
+    assert_identical(pruned, full)
+    assert stats["items"] > 0, "boolean queries did not reach the block-max kernel"
+    counts, ids, scores = pruned
+    nonempty = 0
+    for i, (toks, prog) in enumerate(qs[:160]):
+        all_ids, all_sc = oracle.search_all(algo, toks, prog)
+        nonempty += len(all_ids) > 0
+        check_topk(ids[i, :counts[i]], scores[i, :counts[i]], all_ids, all_sc, limit,
+                   exact_scores=(algo == TFIDF))
+    assert nonempty > 80
+
+
+def test_boolean_edge_shapes_pruned(corpus, oracle, eng):
+    """Unresolved leaves (the empty set), NOT of everything, the same term on
+    both sides, rare AND rare, and a mixed batch of OR and boolean queries."""
+    from nxsearch_b200 import engine
+    from _oracle import OP_AND, OP_ANDNOT, OP_EMPTY
+
+    df = np.asarray(corpus.term_df)
+    order = np.argsort(df, kind="stable")
+    rare = [int(t) + 1 for t in order[df[order] >= 1][:8]]
+    mid = [int(t) + 1 for t in np.nonzero((df >= 200) & (df <= 2000))[0][:8]]
+    qs = [
+        ([1, 2], [0, 1, OP_AND]), ([1, 2], [0, 1, OP_ANDNOT]), ([2, 1], [1, 0, OP_ANDNOT]),
+        ([1], [0, OP_EMPTY, OP_AND]), ([1], [0, OP_EMPTY, OP_OR]), ([1], [OP_EMPTY, 0, OP_ANDNOT]),
+        ([rare[0], rare[1]], [0, 1, OP_AND]), ([rare[0], 1], [0, 1, OP_AND]), ([mid[0], mid[1]], [0, 1, OP_AND]),
+        ([mid[0], rare[2], 3], [0, 1, OP_OR, 2, OP_AND]), ([1, 2, 3, 4, 5, 6, 7, 8], [0, 1, OP_AND, 2, OP_AND, 3, OP_OR, 4, OP_ANDNOT, 5, OP_OR, 6, OP_AND, 7, OP_OR]),
+        ([1, 2], None), ([mid[2]], None), ([3, corpus.n_terms + 5], [0, 1, OP_AND]),
+    ]
+    for algo, limit in ((TFIDF, 100), (BM25, 10)):
+        pruned, full, _ = both_ways(eng, engine.Batch.from_lists(algo, limit, qs))
+        assert_identical(pruned, full)
+        counts, ids, scores = pruned
+        for i, (toks, prog) in enumerate(qs):
+            all_ids, all_sc = oracle.search_all(algo, toks, prog)
+            check_topk(ids[i, :counts[i]], scores[i, :counts[i]], all_ids, all_sc, limit,
+                       exact_scores=(algo == TFIDF))
+
+
+def test_boolean_queries_of_any_shape_can_be_pruned(corpus, eng, monkeypatch):
+    """The routing (queries with more than three positive tokens stream) is a
+    cost estimate, not a limit: with it lifted every template goes through the
+    pruned scorer and the answers stay bit-identical."""
+    from nxsearch_b200 import engine
+    from test_gpu_stream import bool_queries
+
+    monkeypatch.setenv("NXSB_BMW_LOGIC_POS", "8")
+    allp = engine.Engine(0)
+    try:
+        allp.load_corpus(corpus)
+        qs = bool_queries(corpus, 192)
+        for algo, limit in ((TFIDF, 100), (BM25, 10)):
+            batch = engine.Batch.from_lists(algo, limit, qs)
+            allp.pruning_stats(reset=True)
+            got = allp.search(batch)
+            assert allp.pruning_stats()["items"] >= len(qs), "not every query was pruned"
+            eng.set_pruning(False)
+            full = eng.search(batch)
+            eng.set_pruning(True)
+            assert_identical(got, full)
+    finally:
+        allp.close()
