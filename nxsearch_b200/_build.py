@@ -22,8 +22,15 @@ LIB = LIBDIR / "libnxsearch.so"
 
 HOST_SRCS = [
     "hashmap.c", "json.c", "params.c", "results.c", "query.c", "tokenizer.c",
-    "bkmirror.c", "index.c", "nxs.c", "search.c", "corpus.c",
+    "bkmirror.c", "index.c", "nxs.c", "search.c",
 ]
+# libnxsb_tools.so: the synthetic-corpus generator, the bulk index-file writer
+# and the query-front-end introspection the tests and benchmarks use
+# (include/nxsb200_tools.h).  Its own library, so that the product library
+# carries the search path only; it needs no CUDA.
+TOOLS_LIB = LIBDIR / "libnxsb_tools.so"
+TOOLS_SRCS = ["corpus.c", "querytools.c"]
+TOOLS_SHARED = ["hashmap.c", "json.c", "params.c", "query.c", "tokenizer.c", "bkmirror.c"]
 GPU_SRCS = ["engine.cu"]
 
 CFLAGS = [
@@ -88,6 +95,22 @@ def build(force: bool = False, verbose: bool = False) -> Path:
             print("link", LIB.name)
         _run([_nvcc(), "-shared", "-o", str(LIB), *map(str, objs),
               "-cudart", "static", "-lpthread", "-lm"])
+    tools_objs: list[Path] = [OBJDIR / (n + ".o") for n in TOOLS_SHARED]
+    relink_tools = force or relink or not TOOLS_LIB.exists()
+    for name in TOOLS_SRCS:
+        src = CSRC / "host" / name
+        obj = OBJDIR / (name + ".o")
+        if force or _newer(src, host_hdrs, obj):
+            if verbose:
+                print("cc  ", name)
+            _run(["gcc", *CFLAGS, "-c", str(src), "-o", str(obj)])
+            relink_tools = True
+        tools_objs.append(obj)
+    if relink_tools:
+        if verbose:
+            print("link", TOOLS_LIB.name)
+        _run(["gcc", "-shared", "-Wl,--no-undefined", "-o", str(TOOLS_LIB), *map(str, tools_objs),
+              "-lpthread", "-lm"])
     return LIB
 
 

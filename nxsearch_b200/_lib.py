@@ -27,3 +27,18 @@ def load_library() -> ctypes.CDLL:
                 "(there is no pure-Python or CPU fallback)")
         _LIB = ctypes.CDLL(str(path))
     return _LIB
+
+
+_TOOLS = None
+
+
+def load_tools_library() -> ctypes.CDLL:
+    """libnxsb_tools.so: corpus generator, index-file writer, query introspection
+    (test and benchmark tooling, kept out of the product library)."""
+    global _TOOLS
+    if _TOOLS is None:
+        path = Path(__file__).resolve().parent / "lib" / "libnxsb_tools.so"
+        if not path.exists():
+            raise RuntimeError(f"{path} is missing: build it with `python -m nxsearch_b200._build`")
+        _TOOLS = ctypes.CDLL(str(path))
+    return _TOOLS

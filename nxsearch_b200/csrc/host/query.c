@@ -8,6 +8,7 @@
 #include <strings.h>
 
 #include "query.h"
+#include "nxsb200_gpu.h"
 
 #define PARSE_DEPTH_MAX		2000	/* parenthesis recursion guard */
 
@@ -346,4 +347,27 @@ char *
 qtree_dump(const qtree_t *t)
 {
 	return t->root >= 0 ? dump_node(t, t->root) : NULL;
+}
+
+/* Post-order emission of the boolean program (depth is bounded by then). */
+void
+qtree_emit_program(const qtree_t *t, int32_t node, int32_t *prog, uint32_t *n)
+{
+	const qnode_t *nd = &t->nodes[node];
+
+	if (nd->type == QN_VALUE) {
+		/*
+		 * A leaf a filter discarded is the empty set (ref search.c:
+		 * 133-141).  A leaf without a term keeps its slot with term id
+		 * 0, which the engine treats as an empty list -- the reference
+		 * reads freed memory there; the empty set is the
+		 * defined behaviour here.
+		 */
+		prog[(*n)++] = nd->token >= 0 ? nd->token : NXSB_OP_EMPTY;
+		return;
+	}
+	qtree_emit_program(t, nd->left, prog, n);
+	qtree_emit_program(t, nd->right, prog, n);
+	prog[(*n)++] = nd->type == QN_AND ? NXSB_OP_AND :
+	    nd->type == QN_OR ? NXSB_OP_OR : NXSB_OP_ANDNOT;
 }

@@ -69,4 +69,8 @@ void		qtree_free(qtree_t *);
 /* "(AND (OR `A` `B`) `C`)"-style dump (ref tests/t_queryparser.c:139-162). */
 char *		qtree_dump(const qtree_t *);
 
+/* Post-order emission of the boolean program: token slots and NXSB_OP_* codes. */
+void		qtree_emit_program(const qtree_t *, int32_t node, int32_t *prog,
+		    uint32_t *n);
+
 #endif

@@ -221,31 +221,8 @@ prepare_query(const filter_pipeline_t *fp, qtree_t *t, qtokens_t *qt)
 	return ret;
 }
 
-/* Post-order emission of the boolean program (depth is bounded by then). */
-static void
-emit_program(const qtree_t *t, int32_t node, int32_t *prog, uint32_t *n)
-{
-	const qnode_t *nd = &t->nodes[node];
-
-	if (nd->type == QN_VALUE) {
-		/*
-		 * A leaf a filter discarded is the empty set (ref search.c:
-		 * 133-141).  A leaf without a term keeps its slot with term id
-		 * 0, which the engine treats as an empty list -- the reference
-		 * reads freed memory there; the empty set is the
-		 * defined behaviour here.
-		 */
-		prog[(*n)++] = nd->token >= 0 ? nd->token : NXSB_OP_EMPTY;
-		return;
-	}
-	emit_program(t, nd->left, prog, n);
-	emit_program(t, nd->right, prog, n);
-	prog[(*n)++] = nd->type == QN_AND ? NXSB_OP_AND :
-	    nd->type == QN_OR ? NXSB_OP_OR : NXSB_OP_ANDNOT;
-}
-
 /*
- * Operand stack the postfix program of emit_program() needs: the engine
+ * Operand stack the postfix program of qtree_emit_program() needs: the engine
  * evaluates it with a fixed stack (engine.cu validate_batch), and a query that
  * does not fit must fail on its own, not take the batch down.
  */
@@ -368,7 +345,7 @@ prepare_one(const prep_job_t *job, share_t *sh, size_t i)
 		sh->tokens[sh->n_tok++] = qt.tok[j].term_id;
 	}
 	d->prog_off = sh->n_prog;
-	emit_program(&tree, tree.root, sh->prog + sh->n_prog, &np);
+	qtree_emit_program(&tree, tree.root, sh->prog + sh->n_prog, &np);
 	d->n_prog = np;
 	sh->n_prog += np;
 	sh->n_run++;
@@ -795,100 +772,4 @@ nxs_index_search(nxs_index_t *idx, nxs_params_t *params, const char *query,
 	if (nxs_index_search_batch(idx, params, &query, 1, &resp) == -1)
 		return NULL;
 	return resp;
-}
-
-/*
- * Introspection for the tests (include/nxsb200_tools.h).
- */
-
-NXS_API size_t
-nxsb_query_lex(const char *query, int *kinds, size_t cap)
-{
-	qlexer_t lx;
-	qtok_t tok;
-	size_t n = 0;
-
-	qlex_init(&lx, query);
-	while ((tok = qlex_next(&lx)) != QTOK_EOF) {
-		if (tok == QTOK_FF_STRING || tok == QTOK_QUOTED_STRING) {
-			free(lx.str);
-			lx.str = NULL;
-		}
-		if (n < cap)
-			kinds[n] = (int)tok;
-		n++;
-	}
-	return n;
-}
-
-NXS_API char *
-nxsb_query_dump(const char *query, char **errmsg)
-{
-	qtree_t t;
-	char *out = NULL;
-
-	if (errmsg)
-		*errmsg = NULL;
-	qtree_parse(&t, query);
-	if (t.error) {
-		if (errmsg && t.errmsg)
-			*errmsg = strdup(t.errmsg);
-	} else {
-		out = qtree_dump(&t);
-	}
-	qtree_free(&t);
-	return out;
-}
-
-NXS_API int
-nxsb_query_compile(const char *query, char *tokens_buf, size_t buf_len,
-    uint32_t *n_tokens, int32_t *prog, uint32_t prog_cap, uint32_t *n_prog)
-{
-	filter_pipeline_t nofilters = { 0 };
-	tokenset_t *ts = NULL;
-	int32_t *stack = NULL;
-	qtree_t tree;
-	size_t off = 0;
-	int32_t sp = 0;
-	int ret = -1;
-
-	/* No engine limits here: the general token set, same walk as prepare_query(). */
-	*n_tokens = *n_prog = 0;
-	qtree_parse(&tree, query);
-	if (tree.error || (ts = tokenset_create()) == NULL ||
-	    (stack = malloc(sizeof(int32_t) * (tree.n_nodes + 2))) == NULL)
-		goto out;
-	if (tree.root >= 0)
-		stack[sp++] = tree.root;
-	while (sp) {
-		qnode_t *n = &tree.nodes[stack[--sp]];
-
-		if (n->type != QN_VALUE) {
-			stack[sp++] = n->left;
-			stack[sp++] = n->right;
-		} else if (tokenize_value(&nofilters, ts, n->value, strlen(n->value),
-		    &n->token) == -1) {
-			goto out;
-		}
-	}
-	for (uint32_t j = 0; j < ts->count; j++) {
-		const token_t *t = &ts->list[j];
-
-		if (off + t->len + 1 > buf_len)
-			goto out;
-		memcpy(tokens_buf + off, t->str, t->len + 1);
-		off += t->len + 1;
-	}
-	if (tree.root >= 0) {
-		if ((uint32_t)tree.n_nodes > prog_cap || tree.depth > NXS_QUERY_RLIMIT)
-			goto out;
-		emit_program(&tree, tree.root, prog, n_prog);
-	}
-	*n_tokens = ts->count;
-	ret = 0;
-out:
-	free(stack);
-	tokenset_destroy(ts);
-	qtree_free(&tree);
-	return ret;
 }

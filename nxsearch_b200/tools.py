@@ -5,7 +5,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import load_library
+from ._lib import load_tools_library as load_library
 
 SEED = 0x6E78735F42323030  # "nxs_B200", SURVEY section 8(d)
 

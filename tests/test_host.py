@@ -297,14 +297,30 @@ def test_stemmer_is_refused_loudly_not_passed_through(nxs, monkeypatch):
 
 
 def test_every_declared_symbol_is_exported():
+    """include/nxs.h + nxsb200_gpu.h <-> libnxsearch.so (the product),
+    include/nxsb200_tools.h <-> libnxsb_tools.so (test and benchmark tooling);
+    the product library carries none of the tooling."""
+    from nxsearch_b200._lib import load_tools_library
+
     lib = C.CDLL(str(library_path()))
-    declared = set()
-    for hdr in (ROOT / "include").glob("*.h"):
-        text = re.sub(r"/\*.*?\*/", "", hdr.read_text(), flags=re.S)
-        declared |= set(re.findall(r"\b(nxsb?_[a-z0-9_]+)\s*\(", text))
+    tools_lib = load_tools_library()
+
+    def declared_in(name):
+        text = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / name).read_text(), flags=re.S)
+        return set(re.findall(r"\b(nxsb?_[a-z0-9_]+)\s*\(", text))
+
+    declared = declared_in("nxs.h") | declared_in("nxsb200_gpu.h")
     assert len(declared) >= 55
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
+    on_handles = {"nxsb_index_term_df", "nxsb_index_image_stats", "nxsb_resp_collect", "nxsb_bkmirror_build"}
+    tooling = declared_in("nxsb200_tools.h")
+    assert len(tooling) >= 10
+    for s in sorted(tooling):
+        # introspection of live handles stays with the library that owns them
+        assert hasattr(lib if s in on_handles else tools_lib, s), s
+    for s in sorted(tooling - on_handles):
+        assert not hasattr(lib, s), f"{s} leaked into the product library"
     # the reference's 25 public symbols (SURVEY 8b)
     for s in ("nxs_open nxs_close nxs_luafilter_load nxs_get_error nxs_params_create nxs_params_fromjson "
               "nxs_params_set_strlist nxs_params_set_str nxs_params_set_uint nxs_params_set_bool nxs_params_tojson "
