@@ -2596,7 +2596,7 @@ nxsb_engine_fuzzy(nxsb_engine_t *e, uint32_t n, const char *qblob,
 	mark(e, "fuzzy_scan");
 	int launches = 0;
 	if (fuzzy_run(e->fz, e->fz_scratch, n, qblob, qoff, out_term, out_dist, out_true,
-	    0, nullptr, nullptr, e->stream, &launches) != 0)
+	    0, nullptr, nullptr, e->stream, e->n_sms, &launches) != 0)
 		return fail(e, "fuzzy scan failed: %s",
 		    cudaGetErrorString(cudaGetLastError()));
 	e->launches += launches;
@@ -2622,7 +2622,7 @@ nxsb_engine_fuzzy_candidates(nxsb_engine_t *e, uint32_t n, const char *qblob,
 	mark(e, "fuzzy_scan");
 	if (fuzzy_run(e->fz, e->fz_scratch, n, qblob, qoff, out_term ? out_term : term.data(),
 	    out_dist ? out_dist : dist.data(), nullptr, cap, cnt.data(), recs.data(),
-	    e->stream, &launches) != 0)
+	    e->stream, e->n_sms, &launches) != 0)
 		return fail(e, "fuzzy scan failed: %s", cudaGetErrorString(cudaGetLastError()));
 	e->launches += launches;
 	mark(e, "end");

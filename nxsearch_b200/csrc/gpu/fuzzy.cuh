@@ -325,8 +325,16 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
     const uint32_t *__restrict__ qoff, const uint32_t *__restrict__ qsel,
     uint32_t n_sel, uint32_t *__restrict__ out_term,
     uint32_t *__restrict__ out_dist, uint32_t *__restrict__ out_true,
-    const FuzzyCandOut co)
+    const FuzzyCandOut co, unsigned long long *__restrict__ out_key)
 {
+	/*
+	 * A call with few query terms would leave most SMs idle (one warp per
+	 * term, and a term's scan is ~4000 rounds long): gridDim.y CTAs then
+	 * share a group of terms, CTA y taking every gridDim.y-th chunk of the
+	 * signatures, and the answers meet in out_key by atomicMin over
+	 * (BFS rank, distance, term) -- see fuzzy_unpack_kernel.
+	 */
+	const uint32_t part = blockIdx.y, n_parts = gridDim.y;
 	__shared__ W s_peq[NW][256];
 	__shared__ __align__(128) uint32_t s_sig[FZ_STAGES][FZ_CHUNK];
 	__shared__ __align__(8) unsigned long long s_bar[2 * FZ_STAGES];	/* full[], empty[] */
@@ -435,7 +443,7 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 		if (lane == 0) {
 			uint32_t ps = 0, pph = 1;
 
-			for (uint32_t c0 = g0; c0 < g1; c0 += FZ_CHUNK) {
+			for (uint32_t c0 = g0 + part * FZ_CHUNK; c0 < g1; c0 += n_parts * FZ_CHUNK) {
 				const uint32_t n = g1 - c0 < FZ_CHUNK ? g1 - c0 : FZ_CHUNK;
 				const uint32_t bytes = ((n + 3u) & ~3u) * 4u;
 
@@ -492,7 +500,7 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 		__syncwarp();
 	};
 	uint32_t cs = 0, cph = 0;
-	for (uint32_t c0 = g0; c0 < g1; c0 += FZ_CHUNK) {
+	for (uint32_t c0 = g0 + part * FZ_CHUNK; c0 < g1; c0 += n_parts * FZ_CHUNK) {
 		const uint32_t n = g1 - c0 < FZ_CHUNK ? g1 - c0 : FZ_CHUNK;
 
 		mbar_wait(full0 + 8 * cs, cph);
@@ -542,7 +550,7 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 	drain(nq);
 
 	/* Terms longer than 16 bytes: byte-wise from the blob. */
-	for (uint32_t i = lane; i < f.n_long; i += 32) {
+	for (uint32_t i = lane + 32 * part; i < f.n_long; i += 32 * n_parts) {
 		const uint32_t t = f.d_long_term[i];
 		const uint32_t s = f.d_off[t], len = f.d_off[t + 1] - s;
 		const int diff = (int)len - m;
@@ -566,12 +574,33 @@ fuzzy_scan_kernel(const FuzzyImage f, const unsigned char *__restrict__ qblob,
 		}
 		n_true += __shfl_xor_sync(0xffffffffu, n_true, o);
 	}
-	if (lane == 0) {
+	if (lane == 0 && out_key) {
+		if (best.term != 0xffffffffu)
+			atomicMin(out_key + qi, ((unsigned long long)best.rank << 32) |
+			    ((unsigned long long)best.dist << 30) | best.term);
+		if (out_true && n_true)
+			atomicAdd(out_true + qi, n_true);
+	} else if (lane == 0) {
 		out_term[qi] = best.term == 0xffffffffu ? 0 : best.term + 1;
 		out_dist[qi] = best.dist;
 		if (out_true)
 			out_true[qi] = n_true;
 	}
+}
+
+/* out_key[i] = min over the parts of (rank << 32 | dist << 30 | term), ~0 = no match. */
+__global__ void __launch_bounds__(256)
+fuzzy_unpack_kernel(const unsigned long long *__restrict__ key, uint32_t n,
+    uint32_t *__restrict__ out_term, uint32_t *__restrict__ out_dist)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (i >= n)
+		return;
+	const unsigned long long k = key[i];
+
+	out_term[i] = k == ~0ull ? 0u : (uint32_t)(k & 0x3fffffffu) + 1u;
+	out_dist[i] = k == ~0ull ? 0u : (uint32_t)(k >> 30) & 3u;
 }
 
 /*
@@ -622,7 +651,7 @@ static int
 fuzzy_run(FuzzyImage &f, FuzzyScratch &z, uint32_t n, const char *qblob, const uint32_t *qoff,
     uint32_t *out_term, uint32_t *out_dist, uint32_t *out_true,
     uint32_t cand_cap, uint32_t *cand_cnt, uint4 *cand,
-    cudaStream_t st, int *launches)
+    cudaStream_t st, int n_sms, int *launches)
 {
 	std::vector<uint32_t> &sel32 = z.sel32, &sel64 = z.sel64;
 
@@ -655,7 +684,8 @@ fuzzy_run(FuzzyImage &f, FuzzyScratch &z, uint32_t n, const char *qblob, const u
 
 	const size_t nn = n;
 	const size_t o_qoff = 0, o_s32 = o_qoff + nn + 1, o_s64 = o_s32 + nn, o_term = o_s64 + nn,
-	    o_dist = o_term + nn, o_true = o_dist + nn, o_cnt = o_true + nn, words = o_cnt + nn;
+	    o_dist = o_term + nn, o_true = o_dist + nn, o_cnt = o_true + nn, o_key = (o_cnt + nn + 1) & ~(size_t)1,
+	    words = o_key + 2 * nn;
 
 	if (!fuzzy_grow(z.d_qblob, z.blob_cap, (size_t)qoff[n] + 16) ||
 	    !fuzzy_grow(z.d_words, z.words_cap, words) ||
@@ -674,16 +704,31 @@ fuzzy_run(FuzzyImage &f, FuzzyScratch &z, uint32_t n, const char *qblob, const u
 	cudaMemcpyAsync(w + o_s32, sel32.data(), sel32.size() * 4, cudaMemcpyHostToDevice, st);
 	cudaMemcpyAsync(w + o_s64, sel64.data(), sel64.size() * 4, cudaMemcpyHostToDevice, st);
 	cudaMemsetAsync(w + o_term, 0, 4 * nn * 4, st);		/* term, dist, true, cand cnt */
+	/* Few terms: several CTAs per group of terms, so that the whole GPU scans. */
+	const uint32_t ctas32 = (uint32_t)((sel32.size() + FZ_WARPS32 - 1) / FZ_WARPS32);
+	const uint32_t ctas64 = (uint32_t)((sel64.size() + FZ_WARPS - 1) / FZ_WARPS);
+	const uint32_t target = (uint32_t)n_sms * 4u;
+	uint32_t parts = ctas32 + ctas64 ? std::min(64u, std::max(1u, target / (ctas32 + ctas64))) : 1u;
+	if (f.n_terms >= (1u << 30))
+		parts = 1;		/* the packed key holds 30 bits of term */
+	unsigned long long *keys = parts > 1 ? reinterpret_cast<unsigned long long *>(w + o_key) : nullptr;
+
+	if (keys)
+		cudaMemsetAsync(keys, 0xff, nn * 8, st);
 	if (!sel32.empty()) {
-		fuzzy_scan_kernel<uint32_t, FZ_WARPS32><<<(sel32.size() + FZ_WARPS32 - 1) / FZ_WARPS32,
+		fuzzy_scan_kernel<uint32_t, FZ_WARPS32><<<dim3(ctas32, parts),
 		    (FZ_WARPS32 + 1) * 32, 0, st>>>(f, z.d_qblob, w + o_qoff, w + o_s32,
-		    sel32.size(), w + o_term, w + o_dist, w + o_true, co);
+		    sel32.size(), w + o_term, w + o_dist, w + o_true, co, keys);
 		(*launches)++;
 	}
 	if (!sel64.empty()) {
-		fuzzy_scan_kernel<unsigned long long, FZ_WARPS><<<(sel64.size() + FZ_WARPS - 1) / FZ_WARPS,
+		fuzzy_scan_kernel<unsigned long long, FZ_WARPS><<<dim3(ctas64, parts),
 		    (FZ_WARPS + 1) * 32, 0, st>>>(f, z.d_qblob, w + o_qoff, w + o_s64,
-		    sel64.size(), w + o_term, w + o_dist, w + o_true, co);
+		    sel64.size(), w + o_term, w + o_dist, w + o_true, co, keys);
+		(*launches)++;
+	}
+	if (keys) {
+		fuzzy_unpack_kernel<<<(n + 255) / 256, 256, 0, st>>>(keys, n, w + o_term, w + o_dist);
 		(*launches)++;
 	}
 	cudaMemcpyAsync(out_term, w + o_term, nn * 4, cudaMemcpyDeviceToHost, st);
