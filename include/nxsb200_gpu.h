@@ -296,6 +296,16 @@ int		nxsb_engine_set_pruning(nxsb_engine_t *, int on);
  * values of n terms (1-based ids) to out[n][NXSB_KTH_STEPS]; 0 = the list has
  * fewer postings than that step (or the id is not a term).
  */
+/*
+ * Diagnostic: the score of n (term count, document length, idf) triples through
+ * the kernels' own arithmetic (st_score: fp32, log table, rcp.approx), with the
+ * K0 / K1 of the loaded image -- what scripts/bm25_deviation.py compares with
+ * the reference's fp64 evaluation (ref src/algo/ranking.c:135-176).
+ * tf < 65536, dl < 65536 (the packed image's ranges).
+ */
+int		nxsb_engine_score_pairs(nxsb_engine_t *, int algo, uint32_t n,
+		    const uint32_t *tf, const uint32_t *dl, const float *idf, float *out);
+
 #define NXSB_KTH_STEPS	8
 int		nxsb_engine_term_kth(nxsb_engine_t *, int algo, const uint32_t *term_ids,
 		    uint32_t n, float *out);

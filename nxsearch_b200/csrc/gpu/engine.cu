@@ -445,6 +445,67 @@ nxsb_engine_set_pruning(nxsb_engine_t *e, int on)
 
 static_assert(NXSB_KTH_STEPS == BMW_LADDER, "header and kernel agree on the ladder");
 
+/* One thread per (tf, dl, idf) triple through the scorers' own arithmetic. */
+__global__ void __launch_bounds__(256)
+score_pairs_kernel(int algo, uint32_t n, const uint32_t *__restrict__ tf,
+    const uint32_t *__restrict__ dl, const float *__restrict__ idf,
+    const float *__restrict__ logtab, float K0, float K1, float *__restrict__ out)
+{
+	__shared__ float s_logtab[LOGTAB_N];
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+
+	for (uint32_t x = threadIdx.x; x < LOGTAB_N; x += blockDim.x)
+		s_logtab[x] = logtab[x];
+	__syncthreads();
+	if (i >= n)
+		return;
+	StreamParams sp;
+	sp.K0 = K0;
+	sp.K1 = K1;
+	sp.doc_len = nullptr;
+	const uint2 v[1] = { make_uint2(0u, (tf[i] & 0xffffu) | (dl[i] << 16)) };
+	float sc[1];
+
+	if (algo == NXSB_ALGO_BM25)
+		st_score<false, NXSB_ALGO_BM25, 1>(sp, s_logtab, v, idf[i], sc);
+	else
+		st_score<false, NXSB_ALGO_TFIDF, 1>(sp, s_logtab, v, idf[i], sc);
+	out[i] = sc[0];
+}
+
+extern "C" int
+nxsb_engine_score_pairs(nxsb_engine_t *e, int algo, uint32_t n, const uint32_t *tf,
+    const uint32_t *dl, const float *idf, float *out)
+{
+	uint32_t *d_tf = nullptr, *d_dl = nullptr;
+	float *d_idf = nullptr, *d_out = nullptr;
+	int rc = -1;
+
+	if (!e->loaded)
+		return fail(e, "no image loaded (the scores use its K0 / K1)");
+	CK(e, cudaSetDevice(e->device));
+	do {
+		if (n == 0) {
+			rc = 0;
+			break;
+		}
+		if (cudaMalloc(&d_tf, (size_t)n * 4) || cudaMalloc(&d_dl, (size_t)n * 4) ||
+		    cudaMalloc(&d_idf, (size_t)n * 4) || cudaMalloc(&d_out, (size_t)n * 4))
+			break;
+		cudaMemcpyAsync(d_tf, tf, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream);
+		cudaMemcpyAsync(d_dl, dl, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream);
+		cudaMemcpyAsync(d_idf, idf, (size_t)n * 4, cudaMemcpyHostToDevice, e->stream);
+		score_pairs_kernel<<<(n + 255) / 256, 256, 0, e->stream>>>(algo, n, d_tf, d_dl, d_idf,
+		    e->d_logtab, e->K0, e->K1, d_out);
+		cudaMemcpyAsync(out, d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream);
+		if (cudaStreamSynchronize(e->stream) != cudaSuccess)
+			break;
+		rc = 0;
+	} while (0);
+	cudaFree(d_tf); cudaFree(d_dl); cudaFree(d_idf); cudaFree(d_out);
+	return rc == 0 ? 0 : fail(e, "score probe failed: %s", cudaGetErrorString(cudaGetLastError()));
+}
+
 extern "C" int
 nxsb_engine_term_kth(nxsb_engine_t *e, int algo, const uint32_t *term_ids, uint32_t n, float *out)
 {

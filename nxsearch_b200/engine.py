@@ -74,6 +74,7 @@ def _bind():
         "nxsb_engine_set_pruning": (i, [vp, i]),
         "nxsb_engine_pruning_stats": (i, [vp, vp, i]),
         "nxsb_engine_term_kth": (i, [vp, i, vp, C.c_uint32, vp]),
+        "nxsb_engine_score_pairs": (i, [vp, i, u32, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)
@@ -341,6 +342,16 @@ class Engine:
         ids = np.ascontiguousarray(term_ids, dtype=np.uint32)
         out = np.zeros((len(ids), len(self.KTH_STEPS)), dtype=np.float32)
         self._check(self._lib.nxsb_engine_term_kth(self._h, algo, ids.ctypes.data, len(ids), out.ctypes.data))
+        return out
+
+    def score_pairs(self, algo: int, tf, dl, idf) -> np.ndarray:
+        """Scores of (tf, dl, idf) triples through the kernels' arithmetic (diagnostic)."""
+        tf = np.ascontiguousarray(tf, dtype=np.uint32)
+        dl = np.ascontiguousarray(dl, dtype=np.uint32)
+        idf = np.ascontiguousarray(idf, dtype=np.float32)
+        out = np.zeros(len(tf), dtype=np.float32)
+        self._check(self._lib.nxsb_engine_score_pairs(self._h, algo, len(tf), tf.ctypes.data, dl.ctypes.data,
+                                                      idf.ctypes.data, out.ctypes.data))
         return out
 
     def pruning_stats(self, reset: bool = False) -> dict[str, int]:
