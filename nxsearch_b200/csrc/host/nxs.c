@@ -160,96 +160,116 @@ find_open_index(nxs_t *nxs, const char *name)
 	return NULL;
 }
 
+/*
+ * $basedir/data/<index>[/<file>]: every path of an index comes from here.
+ * NULL (with the error slot set) when memory runs out.
+ */
+static char *
+index_path(nxs_t *nxs, const char *index, const char *file)
+{
+	char *path = NULL;
+
+	if (asprintf(&path, file ? "%s/data/%s/%s" : "%s/data/%s", nxs->basedir, index, file) == -1) {
+		nxs_set_error(nxs, NXS_ERR_SYSTEM, "out of memory");
+		return NULL;
+	}
+	return path;
+}
+
+/* Index names are path components: [A-Za-z0-9_-]+ only (ref nxs.c:227). */
+static bool
+index_name_ok(nxs_t *nxs, const char *name)
+{
+	if (str_isalnumdu(name) == 0)
+		return true;
+	nxs_set_error(nxs, NXS_ERR_INVALID, "invalid characters in index name");
+	return false;
+}
+
+/* What an index created without the key gets (ref nxs.c:249-268). */
+static int
+apply_index_defaults(nxs_params_t *params)
+{
+	static const struct { const char *key, *val; } strs[] = {
+		{ "algo", NXS_DEFAULT_RANKING_ALGO },
+		{ "lang", NXS_DEFAULT_LANGUAGE },
+	};
+	size_t n = 0;
+	const char **list = nxs_params_get_strlist(params, "filters", &n);
+	const bool has_filters = list != NULL;
+
+	free(list);
+	if (!has_filters && nxs_params_set_strlist(params, "filters", default_filters,
+	    sizeof(default_filters) / sizeof(default_filters[0])) == -1)
+		return -1;
+	for (size_t i = 0; i < sizeof(strs) / sizeof(strs[0]); i++) {
+		if (!nxs_params_get_str(params, strs[i].key) &&
+		    nxs_params_set_str(params, strs[i].key, strs[i].val) == -1)
+			return -1;
+	}
+	return 0;
+}
+
 NXS_API nxs_index_t *
 nxs_index_create(nxs_t *nxs, const char *name, nxs_params_t *params)
 {
-	nxs_params_t *def_params = NULL;
-	const char **filters = NULL;
+	nxs_params_t *own = NULL;
 	nxs_index_t *idx = NULL;
-	size_t nfilters;
-	char *path = NULL;
+	char *dir, *db = NULL;
 
 	nxs_clear_error(nxs);
-	if (str_isalnumdu(name) == -1) {
-		nxs_set_error(nxs, NXS_ERR_INVALID, "invalid characters in index name");
+	if (!index_name_ok(nxs, name) || (dir = index_path(nxs, name, NULL)) == NULL)
+		return NULL;
+
+	/* The directory is the claim on the name: whoever makes it owns the index. */
+	if (mkdir(dir, 0755) == -1) {
+		const bool taken = errno == EEXIST;
+
+		nxs_set_syserror(nxs, taken ? NXS_ERR_EXISTS : NXS_ERR_SYSTEM,
+		    taken ? "index `%s' already exists" : "could not create directory at %s",
+		    taken ? name : dir);
+		free(dir);
+		nxs_error_checkpoint(nxs);
 		return NULL;
 	}
-	if (asprintf(&path, "%s/data/%s", nxs->basedir, name) == -1)
-		return NULL;
-	if (mkdir(path, 0755) == -1) {
-		if (errno == EEXIST)
-			nxs_set_syserror(nxs, NXS_ERR_EXISTS,
-			    "index `%s' already exists", name);
-		else
-			nxs_set_syserror(nxs, NXS_ERR_SYSTEM,
-			    "could not create directory at %s", path);
-		goto out;
-	}
-	free(path);
-	path = NULL;
+	free(dir);
 
-	/* Defaults (nxs.c:249-268). */
-	if (!params) {
-		if ((def_params = nxs_params_create()) == NULL)
-			goto out;
-		params = def_params;
-	}
-	filters = nxs_params_get_strlist(params, "filters", &nfilters);
-	if (!filters && nxs_params_set_strlist(params, "filters",
-	    default_filters, sizeof(default_filters) / sizeof(default_filters[0])) == -1)
-		goto out;
-	if (!nxs_params_get_str(params, "algo") &&
-	    nxs_params_set_str(params, "algo", NXS_DEFAULT_RANKING_ALGO) == -1)
-		goto out;
-	if (!nxs_params_get_str(params, "lang") &&
-	    nxs_params_set_str(params, "lang", NXS_DEFAULT_LANGUAGE) == -1)
-		goto out;
-
-	if (asprintf(&path, "%s/data/%s/params.db", nxs->basedir, name) == -1)
-		goto out;
-	if (nxs_params_serialize(nxs, params, path) == -1)
-		goto out;
-	idx = nxs_index_open(nxs, name);
-out:
+	if (!params)
+		params = own = nxs_params_create();
+	if (params && apply_index_defaults(params) == 0 &&
+	    (db = index_path(nxs, name, "params.db")) != NULL &&
+	    nxs_params_serialize(nxs, params, db) == 0)
+		idx = nxs_index_open(nxs, name);
 	if (!idx)
 		nxs_error_checkpoint(nxs);
-	if (def_params)
-		nxs_params_release(def_params);
-	free(filters);
-	free(path);
+	if (own)
+		nxs_params_release(own);
+	free(db);
 	return idx;
 }
 
 NXS_API int
 nxs_index_destroy(nxs_t *nxs, const char *name)
 {
-	static const char *files[] = { "params.db", "nxsterms", "nxsdtmap", "" };
-	int ret = -1;
+	/* The three files, then the directory that held them (file == NULL). */
+	static const char *const parts[] = { "params.db", "nxsterms", "nxsdtmap", NULL };
 
 	nxs_clear_error(nxs);
-	if (str_isalnumdu(name) == -1) {
-		nxs_set_error(nxs, NXS_ERR_INVALID, "invalid characters in index name");
+	if (!index_name_ok(nxs, name))
 		return -1;
-	}
-	for (unsigned i = 0; i < 4; i++) {
-		char *path;
-		int rc;
+	for (size_t i = 0; i < sizeof(parts) / sizeof(parts[0]); i++) {
+		char *path = index_path(nxs, name, parts[i]);
+		const int rc = !path ? -1 : parts[i] ? unlink(path) : rmdir(path);
 
-		if (asprintf(&path, "%s/data/%s/%s", nxs->basedir, name, files[i]) == -1)
-			goto out;
-		rc = i < 3 ? unlink(path) : rmdir(path);
-		if (rc == -1) {
+		if (path && rc == -1)
 			nxs_set_syserror(nxs, NXS_ERR_SYSTEM, "could not remove `%s'", path);
-			free(path);
-			goto out;
-		}
 		free(path);
+		if (rc == -1) {
+			nxs_error_checkpoint(nxs);
+			return -1;
+		}
 	}
-	ret = 0;
-out:
-	if (ret != 0)
-		nxs_error_checkpoint(nxs);
-	return ret;
+	return 0;
 }
 
 static int
@@ -262,20 +282,54 @@ algo_id(const char *name)
 	return -1;
 }
 
+/* params.db -> ranking algorithm and filter pipeline of the index. */
+static int
+open_params(nxs_t *nxs, nxs_index_t *idx, const char *name)
+{
+	char *db = index_path(nxs, name, "params.db");
+	const char *algo;
+	struct stat sb;
+
+	if (!db)
+		return -1;
+	if (stat(db, &sb) == -1 && errno == ENOENT) {
+		nxs_set_error(nxs, NXS_ERR_MISSING, "index `%s' does not exist", name);
+		free(db);
+		return -1;
+	}
+	idx->params = nxs_params_unserialize(nxs, db);
+	free(db);
+	if (!idx->params)
+		return -1;
+	if ((algo = nxs_params_get_str(idx->params, "algo")) == NULL) {
+		nxs_set_error(nxs, NXS_ERR_FATAL, "corrupted index params");
+		return -1;
+	}
+	idx->algo = algo_id(algo);
+	idx->fp = filter_pipeline_create(nxs, idx->params);
+	return idx->fp ? 0 : -1;
+}
+
+/* One of the two append-only files of the index through its opener. */
+static int
+open_file(nxs_t *nxs, nxs_index_t *idx, const char *name, const char *file,
+    int (*opener)(nxs_index_t *, const char *))
+{
+	char *path = index_path(nxs, name, file);
+	const int rc = path ? opener(idx, path) : -1;
+
+	free(path);
+	return rc;
+}
+
 NXS_API nxs_index_t *
 nxs_index_open(nxs_t *nxs, const char *name)
 {
 	nxs_index_t *idx;
-	struct stat sb;
-	const char *algo;
-	char *path = NULL;
-	int ret;
 
 	nxs_clear_error(nxs);
-	if (str_isalnumdu(name) == -1) {
-		nxs_set_error(nxs, NXS_ERR_INVALID, "invalid characters in index name");
+	if (!index_name_ok(nxs, name))
 		return NULL;
-	}
 	if (find_open_index(nxs, name)) {
 		nxs_set_error(nxs, NXS_ERR_EXISTS, "index `%s' is already open", name);
 		return NULL;
@@ -286,52 +340,19 @@ nxs_index_open(nxs_t *nxs, const char *name)
 	}
 	idx->nxs = nxs;
 	idx->algo = -1;
-
-	if (asprintf(&path, "%s/data/%s/params.db", nxs->basedir, name) == -1)
-		goto err;
-	if (stat(path, &sb) == -1 && errno == ENOENT) {
-		nxs_set_error(nxs, NXS_ERR_MISSING, "index `%s' does not exist", name);
-		goto err;
+	if (open_params(nxs, idx, name) == -1 ||
+	    open_file(nxs, idx, name, "nxsterms", idx_terms_open) == -1 ||
+	    open_file(nxs, idx, name, "nxsdtmap", idx_dtmap_open) == -1 ||
+	    (idx->name = strdup(name)) == NULL) {
+		nxs_error_checkpoint(nxs);
+		nxs_index_close(idx);	/* not on the list yet: name is unset or just set */
+		return NULL;
 	}
-	idx->params = nxs_params_unserialize(nxs, path);
-	free(path);
-	path = NULL;
-	if (!idx->params)
-		goto err;
-	if ((algo = nxs_params_get_str(idx->params, "algo")) == NULL) {
-		nxs_set_error(nxs, NXS_ERR_FATAL, "corrupted index params");
-		goto err;
-	}
-	idx->algo = algo_id(algo);
-	if ((idx->fp = filter_pipeline_create(nxs, idx->params)) == NULL)
-		goto err;
-
-	if (asprintf(&path, "%s/data/%s/nxsterms", nxs->basedir, name) == -1)
-		goto err;
-	ret = idx_terms_open(idx, path);
-	free(path);
-	path = NULL;
-	if (ret == -1)
-		goto err;
-	if (asprintf(&path, "%s/data/%s/nxsdtmap", nxs->basedir, name) == -1)
-		goto err;
-	ret = idx_dtmap_open(idx, path);
-	free(path);
-	path = NULL;
-	if (ret == -1)
-		goto err;
-
-	if ((idx->name = strdup(name)) == NULL)
-		goto err;
+	/* Nothing is in HBM until the first search asks for it. */
 	idx->image_dirty = idx->vocab_dirty = true;
 	idx->next = nxs->indexes;
 	nxs->indexes = idx;
 	return idx;
-err:
-	free(path);
-	nxs_error_checkpoint(nxs);
-	nxs_index_close(idx);
-	return NULL;
 }
 
 NXS_API nxs_params_t *
