@@ -374,26 +374,27 @@ def pick_layout(args, world: int) -> str:
     return "replica" if image_gb < 90 else "shard"
 
 
-def timed_value_leg(args, torch, dist, world, dev, stream, engine, searcher, handles, bytes_local, barrier):
+def timed_value_leg(args, torch, dist, world, dev, stream, engine, searcher, handles, bytes_local, barrier, rot=0):
     """W warm-up steps, then K timed steps bracketed by barrier + synchronize,
     device time from CUDA events on the engine's stream, max over ranks."""
     n_distinct = len(handles)
+    # rot: replicas draw from the same batches, each starting `rank` batches in.
     for s in range(args.warmup):
-        searcher.run(handles[s % n_distinct], args.batch, args.limit)
+        searcher.run(handles[(s + rot) % n_distinct], args.batch, args.limit)
     barrier()
     launches0 = engine.launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
     for s in range(args.steps):
-        searcher.run(handles[(args.warmup + s) % n_distinct], args.batch, args.limit)
+        searcher.run(handles[(args.warmup + s + rot) % n_distinct], args.batch, args.limit)
     ev1.record(stream)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = engine.launches - launches0
     runs_timed = min(args.steps, 256)
     kern = engine.timings(runs_timed)
-    timed_bytes = sum(bytes_local[(args.warmup + s) % n_distinct] for s in range(max(0, args.steps - 256), args.steps))
+    timed_bytes = sum(bytes_local[(args.warmup + s + rot) % n_distinct] for s in range(max(0, args.steps - 256), args.steps))
     if world > 1:
         t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -455,18 +456,21 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     if layout == "replica":
         # ---- every GPU holds the whole index and takes its own query stream
         corpus, engine, df = load(0, args.docs)
-        batches, bytes_local, host_batches, handles = stage(corpus, engine, df, tools.SEED + 1 + 7919 * rank)
+        # Every replica serves the same query distribution: the same batches,
+        # rank r starting r batches into the cycle.
+        batches, bytes_local, host_batches, handles = stage(corpus, engine, df, tools.SEED + 1)
         searcher = nxdist.ShardedSearcher(engine, 0, 1)
         sampler = ClockSampler(local_rank)
         sampler.start()
         elapsed_ms, launches, kern, timed_bytes, runs_timed = timed_value_leg(
-            args, torch, dist, world, dev, stream, engine, searcher, handles, bytes_local, barrier)
+            args, torch, dist, world, dev, stream, engine, searcher, handles, bytes_local, barrier, rot=rank)
         clocks = sampler.stop()
         value = world * args.batch * args.steps / (elapsed_ms / 1000)
         e2e, h2d, d2h, e2e_note = e2e_capi(args, corpus, batches, capi, rank, world, local_rank, dist, barrier, dev)
         if world > 1 and not args.no_shard_leg:
             doc_sharded = shard_leg(args, rank, world, torch, dist, dev, stream, barrier, load, stage, nxdist, tools)
-        parallelism = f"replica x{world}: whole index on every GPU, {world} batches of {args.batch} per step"
+        parallelism = (f"replica x{world}: whole index on every GPU, {world} batches of {args.batch} per step "
+                       "(the same cycle of batches on every GPU, rank r starting r batches in)")
         scaling = "weak"
     else:
         # ---- document shards + NCCL all-gather merge
@@ -739,6 +743,8 @@ def e2e_capi(args, corpus, batches, capi, rank=0, world=1, local_rank=0, dist=No
         AUX["first_search_image_build_s"] = round(time.time() - t0, 2)
         log(f"[{rank}] first search (image build) {time.time() - t0:.1f}s")
         n = len(batches)
+        arrays = arrays[rank % n:] + arrays[:rank % n]          # rank r starts r batches into the cycle
+        strings = strings[rank % n:] + strings[:rank % n]
         for s in range(args.warmup):
             idx.search_batch_arrays(arrays[s % n], args.limit, **params)
         # K steps per measurement are a few tens of milliseconds here, so one
