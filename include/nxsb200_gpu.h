@@ -57,6 +57,17 @@ int		nxsb_gpu_device_count(void);
 const char *	nxsb_last_error(void);
 
 nxsb_engine_t *	nxsb_engine_create(int device);
+/*
+ * One engine object over n devices, a complete replica of the image on each:
+ * load_shard / segment_add / set_dead / set_global_stats go to every replica
+ * (side by side on host threads), a batch's queries are split in n contiguous
+ * shares that run concurrently, and the results come back in query order --
+ * the host library's NXS_GPU_DEVICES.  An index of 10M documents is ~6 GB per
+ * device; when the index outgrows one GPU, shard instead (nxsearch_b200/dist.py).
+ * Resident batches, external streams, _begin_dev and merge_topk are refused.
+ */
+nxsb_engine_t *	nxsb_engine_create_replicated(const int *devices, int n);
+int		nxsb_engine_replica_count(const nxsb_engine_t *);
 void		nxsb_engine_destroy(nxsb_engine_t *);
 const char *	nxsb_engine_errmsg(const nxsb_engine_t *);
 

@@ -264,6 +264,20 @@ struct nxsb_engine {
 	cudaEvent_t	pipe_done[PIPE_DEPTH] = { nullptr };
 	bool		pipe_busy[PIPE_DEPTH] = { false };
 
+	/*
+	 * A replicated engine (nxsb_engine_create_replicated): this object only
+	 * dispatches; every replica is a complete engine on its own device and
+	 * takes a contiguous share of each batch's queries.
+	 */
+	std::vector<nxsb_engine *> replicas;
+	struct RepSplit {
+		bool		busy = false;
+		uint32_t	limit = 0;
+		std::vector<uint32_t> q0;	// [replicas + 1] query ranges
+		std::vector<int> h;		// child handles, -1 = no queries
+	};
+	RepSplit	rep_pipe[PIPE_DEPTH];
+
 	/* vocabulary (fuzzy) */
 	FuzzyImage	fz;
 	FuzzyScratch	fz_scratch;
@@ -387,6 +401,145 @@ kernel_fit(nxsb_engine_t *e, const void *fn, int threads, size_t smem, int *per_
 	return 0;
 }
 
+
+/* ---- replicated engines -------------------------------------------------- */
+
+extern "C" nxsb_engine_t *nxsb_engine_create(int device);
+extern "C" void nxsb_engine_destroy(nxsb_engine_t *e);
+
+static inline bool
+is_multi(const nxsb_engine_t *e)
+{
+	return !e->replicas.empty();
+}
+
+static int
+multi_fail(nxsb_engine_t *e, const nxsb_engine_t *child, int r)
+{
+	return fail(e, "replica %d (device %d): %s", r, child->device, child->err);
+}
+
+#define NOT_ON_REPLICATED(e, what) do {						\
+	if (is_multi(e))							\
+		return fail((e), what " is not available on a replicated engine");\
+} while (0)
+
+/* fn(replica, index) on every replica, one host thread each; 0 if all returned 0. */
+template <typename F>
+static int
+multi_each(nxsb_engine_t *e, bool parallel, F fn)
+{
+	const size_t n = e->replicas.size();
+	std::vector<int> rc(n, 0);
+
+	if (parallel && n > 1) {
+		std::vector<std::thread> th;
+
+		for (size_t r = 0; r < n; r++)
+			th.emplace_back([&, r] { rc[r] = fn(e->replicas[r], (int)r); });
+		for (auto &t : th)
+			t.join();
+	} else {
+		for (size_t r = 0; r < n; r++)
+			rc[r] = fn(e->replicas[r], (int)r);
+	}
+	for (size_t r = 0; r < n; r++)
+		if (rc[r] != 0)
+			return multi_fail(e, e->replicas[r], (int)r);
+	return 0;
+}
+
+static int
+multi_search_begin(nxsb_engine_t *e, const nxsb_batch_t *b)
+{
+	const uint32_t R = (uint32_t)e->replicas.size();
+	int s = -1;
+
+	for (int i = 0; i < PIPE_DEPTH; i++)
+		if (!e->rep_pipe[i].busy) {
+			s = i;
+			break;
+		}
+	if (s < 0)
+		return fail(e, "too many searches in flight (%d)", PIPE_DEPTH);
+	nxsb_engine::RepSplit &sp = e->rep_pipe[s];
+
+	sp.limit = b->limit;
+	sp.q0.assign(R + 1, 0);
+	sp.h.assign(R, -1);
+	for (uint32_t r = 0; r <= R; r++)
+		sp.q0[r] = (uint32_t)((uint64_t)b->n_queries * r / R);
+	for (uint32_t r = 0; r < R; r++) {
+		nxsb_batch_t sub = *b;
+
+		sub.queries = b->queries + sp.q0[r];
+		sub.n_queries = sp.q0[r + 1] - sp.q0[r];
+		if (sub.n_queries == 0)
+			continue;
+		/* Token and program arrays go whole: the queries' offsets stay valid. */
+		if ((sp.h[r] = nxsb_engine_search_begin(e->replicas[r], &sub)) < 0) {
+			for (uint32_t x = 0; x < r; x++)
+				if (sp.h[x] >= 0)
+					nxsb_engine_search_end(e->replicas[x], sp.h[x], nullptr, nullptr, nullptr);
+			return multi_fail(e, e->replicas[r], (int)r);
+		}
+	}
+	sp.busy = true;
+	return s;
+}
+
+static int
+multi_search_end(nxsb_engine_t *e, int s, uint32_t *counts, uint64_t *ids, float *scores)
+{
+	if (s < 0 || s >= PIPE_DEPTH || !e->rep_pipe[s].busy)
+		return fail(e, "bad search handle %d", s);
+	nxsb_engine::RepSplit &sp = e->rep_pipe[s];
+	int rc = 0;
+
+	sp.busy = false;
+	for (size_t r = 0; r < e->replicas.size(); r++) {
+		const size_t at = sp.q0[r];
+
+		if (sp.h[r] < 0)
+			continue;
+		if (nxsb_engine_search_end(e->replicas[r], sp.h[r], counts ? counts + at : nullptr,
+		    counts ? ids + at * sp.limit : nullptr, counts ? scores + at * sp.limit : nullptr) != 0 &&
+		    rc == 0)
+			rc = multi_fail(e, e->replicas[r], (int)r);
+	}
+	return rc;
+}
+
+extern "C" nxsb_engine_t *
+nxsb_engine_create_replicated(const int *devices, int n)
+{
+	if (n < 1) {
+		snprintf(g_last_error, sizeof(g_last_error), "a replicated engine needs at least one device");
+		return nullptr;
+	}
+	nxsb_engine_t *e = new nxsb_engine();
+
+	e->device = devices[0];
+	for (int i = 0; i < n; i++) {
+		nxsb_engine_t *c = nxsb_engine_create(devices[i]);
+
+		if (!c) {
+			for (auto *x : e->replicas)
+				nxsb_engine_destroy(x);
+			delete e;
+			return nullptr;
+		}
+		e->replicas.push_back(c);
+	}
+	return e;
+}
+
+extern "C" int
+nxsb_engine_replica_count(const nxsb_engine_t *e)
+{
+	return (int)e->replicas.size();
+}
+
 extern "C" int
 nxsb_gpu_device_count(void)
 {
@@ -425,6 +578,13 @@ nxsb_engine_prof(nxsb_engine_t *e, unsigned long long *out)
 extern "C" uint64_t
 nxsb_engine_launch_count(const nxsb_engine_t *e)
 {
+	if (is_multi(e)) {
+		uint64_t n = 0;
+
+		for (auto *c : e->replicas)
+			n += nxsb_engine_launch_count(c);
+		return n;
+	}
 	uint64_t n = e->launches;
 
 	for (const nxsb_engine *c : e->segs)
@@ -435,6 +595,13 @@ nxsb_engine_launch_count(const nxsb_engine_t *e)
 extern "C" int
 nxsb_engine_set_pruning(nxsb_engine_t *e, int on)
 {
+	if (is_multi(e)) {
+		int was = 0;
+
+		for (auto *c : e->replicas)
+			was = nxsb_engine_set_pruning(c, on);
+		return was;
+	}
 	const int was = e->bmw_enabled;
 
 	e->bmw_enabled = on != 0;
@@ -477,6 +644,9 @@ extern "C" int
 nxsb_engine_score_pairs(nxsb_engine_t *e, int algo, uint32_t n, const uint32_t *tf,
     const uint32_t *dl, const float *idf, float *out)
 {
+	if (is_multi(e))
+		return nxsb_engine_score_pairs(e->replicas[0], algo, n, tf, dl, idf, out) == 0 ? 0
+		    : multi_fail(e, e->replicas[0], 0);
 	uint32_t *d_tf = nullptr, *d_dl = nullptr;
 	float *d_idf = nullptr, *d_out = nullptr;
 	int rc = -1;
@@ -509,6 +679,9 @@ nxsb_engine_score_pairs(nxsb_engine_t *e, int algo, uint32_t n, const uint32_t *
 extern "C" int
 nxsb_engine_term_kth(nxsb_engine_t *e, int algo, const uint32_t *term_ids, uint32_t n, float *out)
 {
+	if (is_multi(e))
+		return nxsb_engine_term_kth(e->replicas[0], algo, term_ids, n, out) == 0 ? 0
+		    : multi_fail(e, e->replicas[0], 0);
 	const float *tab = algo == NXSB_ALGO_BM25 ? e->d_kth_bm25 : e->d_kth_tfidf;
 
 	if (!e->loaded || !tab)
@@ -531,6 +704,18 @@ nxsb_engine_term_kth(nxsb_engine_t *e, int algo, const uint32_t *term_ids, uint3
 extern "C" int
 nxsb_engine_pruning_stats(nxsb_engine_t *e, uint64_t out[16], int reset)
 {
+	if (is_multi(e)) {
+		uint64_t one[16];
+
+		memset(out, 0, 16 * sizeof(uint64_t));
+		for (size_t r = 0; r < e->replicas.size(); r++) {
+			if (nxsb_engine_pruning_stats(e->replicas[r], one, reset) != 0)
+				return multi_fail(e, e->replicas[r], (int)r);
+			for (int i = 0; i < 16; i++)
+				out[i] += one[i];
+		}
+		return 0;
+	}
 	unsigned long long v[16];
 
 	CK(e, cudaSetDevice(e->device));
@@ -708,6 +893,12 @@ drop_segments(nxsb_engine_t *e)
 extern "C" void
 nxsb_engine_destroy(nxsb_engine_t *e)
 {
+	if (e && is_multi(e)) {
+		for (auto *c : e->replicas)
+			nxsb_engine_destroy(c);
+		delete e;
+		return;
+	}
 	if (!e)
 		return;
 	cudaSetDevice(e->device);
@@ -752,6 +943,7 @@ nxsb_engine_destroy(nxsb_engine_t *e)
 extern "C" int
 nxsb_engine_set_stream(nxsb_engine_t *e, void *s)
 {
+	NOT_ON_REPLICATED(e, "an external stream");
 	e->stream = s ? (cudaStream_t)s : e->own_stream;
 	for (nxsb_engine *c : e->segs)
 		c->stream = e->stream;
@@ -761,6 +953,8 @@ nxsb_engine_set_stream(nxsb_engine_t *e, void *s)
 extern "C" int
 nxsb_engine_sync(nxsb_engine_t *e)
 {
+	if (is_multi(e))
+		return multi_each(e, false, [](nxsb_engine_t *c, int) { return nxsb_engine_sync(c); });
 	CK(e, cudaSetDevice(e->device));
 	CK(e, cudaStreamSynchronize(e->stream));
 	return 0;
@@ -890,6 +1084,8 @@ upload_stats(nxsb_engine_t *e)
 extern "C" int
 nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 {
+	if (is_multi(e))	/* the same image on every device, built side by side */
+		return multi_each(e, true, [&](nxsb_engine_t *c, int) { return nxsb_engine_load_shard(c, sd); });
 	const uint32_t N = sd->n_docs, V = sd->n_terms;
 	const bool raw = sd->raw != nullptr;
 	std::vector<uint64_t> raw_doc_off, raw_rel;
@@ -1259,6 +1455,8 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 extern "C" int
 nxsb_engine_get_df(nxsb_engine_t *e, uint32_t *df, uint32_t n_terms)
 {
+	if (is_multi(e))
+		return nxsb_engine_get_df(e->replicas[0], df, n_terms) == 0 ? 0 : multi_fail(e, e->replicas[0], 0);
 	if (!e->loaded || n_terms != e->n_terms)
 		return fail(e, "get_df: no image or vocabulary size mismatch");
 	memcpy(df, e->h_df_local.data(), (size_t)n_terms * 4);
@@ -1269,6 +1467,10 @@ extern "C" int
 nxsb_engine_set_global_stats(nxsb_engine_t *e, const uint32_t *df,
     uint32_t n_terms, uint64_t token_count, uint32_t doc_count)
 {
+	if (is_multi(e))
+		return multi_each(e, true, [&](nxsb_engine_t *c, int) {
+			return nxsb_engine_set_global_stats(c, df, n_terms, token_count, doc_count);
+		});
 	/*
 	 * The vocabulary only grows: a segment built when it had fewer terms
 	 * takes the leading part of a longer table.
@@ -1294,6 +1496,13 @@ nxsb_engine_set_global_stats(nxsb_engine_t *e, const uint32_t *df,
 extern "C" int
 nxsb_engine_segment_add(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 {
+	if (is_multi(e)) {
+		if (multi_each(e, true, [&](nxsb_engine_t *c, int) {
+			return nxsb_engine_segment_add(c, sd) < 0 ? -1 : 0;
+		}) != 0)
+			return -1;
+		return nxsb_engine_segment_count(e->replicas[0]);
+	}
 	if (!e->loaded)
 		return fail(e, "segment_add: no base image loaded");
 	if (e->segs.size() >= NXSB_MAX_SEGMENTS)
@@ -1323,12 +1532,16 @@ nxsb_engine_segment_add(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 extern "C" int
 nxsb_engine_segment_count(const nxsb_engine_t *e)
 {
+	if (is_multi(e))
+		return nxsb_engine_segment_count(e->replicas[0]);
 	return (int)e->segs.size();
 }
 
 extern "C" int
 nxsb_engine_segments_drop(nxsb_engine_t *e)
 {
+	if (is_multi(e))
+		return multi_each(e, false, [](nxsb_engine_t *c, int) { return nxsb_engine_segments_drop(c); });
 	CK(e, cudaSetDevice(e->device));
 	CK(e, cudaStreamSynchronize(e->stream));
 	drop_segments(e);
@@ -1339,6 +1552,8 @@ extern "C" int
 nxsb_engine_set_dead(nxsb_engine_t *e, uint32_t segment, const uint64_t *ids,
     uint32_t n)
 {
+	if (is_multi(e))
+		return multi_each(e, false, [&](nxsb_engine_t *c, int) { return nxsb_engine_set_dead(c, segment, ids, n); });
 	if (!e->loaded || segment > e->segs.size())
 		return fail(e, "set_dead: no such segment %u", segment);
 	for (uint32_t i = 1; i < n; i++)
@@ -1802,6 +2017,7 @@ fill_batch(nxsb_engine_t *e, Batch &B, const nxsb_batch_t *b)
 extern "C" int
 nxsb_engine_batch_upload(nxsb_engine_t *e, const nxsb_batch_t *b)
 {
+	NOT_ON_REPLICATED(e, "a resident batch");
 	int h = -1;
 
 	CK(e, cudaSetDevice(e->device));
@@ -2477,6 +2693,11 @@ extern "C" int
 nxsb_engine_search(nxsb_engine_t *e, const nxsb_batch_t *b, uint32_t *counts,
     uint64_t *ids, float *scores)
 {
+	if (is_multi(e)) {
+		const int h = multi_search_begin(e, b);
+
+		return h < 0 ? -1 : multi_search_end(e, h, counts, ids, scores);
+	}
 	Batch &B = e->oneshot;
 
 	CK(e, cudaSetDevice(e->device));
@@ -2529,6 +2750,8 @@ search_begin(nxsb_engine_t *e, const nxsb_batch_t *b, Rec *d_recs)
 extern "C" int
 nxsb_engine_search_begin(nxsb_engine_t *e, const nxsb_batch_t *b)
 {
+	if (is_multi(e))
+		return multi_search_begin(e, b);
 	return search_begin(e, b, nullptr);
 }
 
@@ -2540,6 +2763,7 @@ nxsb_engine_search_begin(nxsb_engine_t *e, const nxsb_batch_t *b)
 extern "C" int
 nxsb_engine_search_begin_dev(nxsb_engine_t *e, const nxsb_batch_t *b, void *d_recs)
 {
+	NOT_ON_REPLICATED(e, "a search into caller-owned device memory");
 	if (!d_recs)
 		return fail(e, "search_begin_dev needs a device buffer");
 	return search_begin(e, b, (Rec *)d_recs);
@@ -2549,6 +2773,8 @@ extern "C" int
 nxsb_engine_search_end(nxsb_engine_t *e, int s, uint32_t *counts, uint64_t *ids,
     float *scores)
 {
+	if (is_multi(e))
+		return multi_search_end(e, s, counts, ids, scores);
 	if (s < 0 || s >= PIPE_DEPTH || !e->pipe_busy[s])
 		return fail(e, "bad search handle %d", s);
 	e->pipe_busy[s] = false;
@@ -2563,6 +2789,7 @@ extern "C" int
 nxsb_engine_merge_topk(nxsb_engine_t *e, const void *d_in, uint32_t n_shards,
     uint32_t n_queries, uint32_t limit, void *d_out)
 {
+	NOT_ON_REPLICATED(e, "the cross-shard merge");
 	const unsigned long long total = (unsigned long long)n_queries * n_shards * limit;
 
 	CK(e, cudaSetDevice(e->device));
@@ -2580,6 +2807,8 @@ extern "C" int
 nxsb_engine_timings(nxsb_engine_t *e, uint32_t last_runs, const char **names,
     float *ms, int cap)
 {
+	if (is_multi(e))
+		return nxsb_engine_timings(e->replicas[0], last_runs, names, ms, cap);
 	int n = 0;
 
 	if (cudaStreamSynchronize(e->stream) != cudaSuccess)
@@ -2628,6 +2857,9 @@ nxsb_engine_load_vocab(nxsb_engine_t *e, uint32_t n_terms, const char *blob,
     const uint32_t *term_off, const uint64_t *term_total,
     const uint32_t *bk_parent, const uint8_t *bk_edge, const uint32_t *bk_rank)
 {
+	if (is_multi(e))	/* lookups are a small share of a batch: one replica serves them */
+		return nxsb_engine_load_vocab(e->replicas[0], n_terms, blob, term_off, term_total,
+		    bk_parent, bk_edge, bk_rank) == 0 ? 0 : multi_fail(e, e->replicas[0], 0);
 	CK(e, cudaSetDevice(e->device));
 	if (fuzzy_load(e->fz, n_terms, blob, term_off, term_total, bk_parent,
 	    bk_edge, bk_rank, e->stream) != 0)
@@ -2639,6 +2871,9 @@ nxsb_engine_load_vocab(nxsb_engine_t *e, uint32_t n_terms, const char *blob,
 extern "C" int
 nxsb_engine_update_term_totals(nxsb_engine_t *e, uint32_t n_terms, const uint64_t *term_total)
 {
+	if (is_multi(e))
+		return nxsb_engine_update_term_totals(e->replicas[0], n_terms, term_total) == 0 ? 0
+		    : multi_fail(e, e->replicas[0], 0);
 	CK(e, cudaSetDevice(e->device));
 	if (fuzzy_update_live(e->fz, n_terms, term_total, e->stream) != 0)
 		return fail(e, "term totals do not match the vocabulary image (%u terms)", n_terms);
@@ -2650,6 +2885,9 @@ nxsb_engine_fuzzy(nxsb_engine_t *e, uint32_t n, const char *qblob,
     const uint32_t *qoff, uint32_t *out_term, uint32_t *out_dist,
     uint32_t *out_true)
 {
+	if (is_multi(e))
+		return nxsb_engine_fuzzy(e->replicas[0], n, qblob, qoff, out_term, out_dist, out_true) == 0 ? 0
+		    : multi_fail(e, e->replicas[0], 0);
 	CK(e, cudaSetDevice(e->device));
 	if (!e->fz.loaded)
 		return fail(e, "no vocabulary image loaded");
@@ -2670,6 +2908,9 @@ nxsb_engine_fuzzy_candidates(nxsb_engine_t *e, uint32_t n, const char *qblob,
     const uint32_t *qoff, uint32_t cap, uint32_t *out_term, uint32_t *out_dist,
     uint32_t *out_n, uint32_t *cand_term, uint8_t *cand_dist, uint8_t *cand_flags)
 {
+	if (is_multi(e))
+		return nxsb_engine_fuzzy_candidates(e->replicas[0], n, qblob, qoff, cap, out_term, out_dist,
+		    out_n, cand_term, cand_dist, cand_flags) == 0 ? 0 : multi_fail(e, e->replicas[0], 0);
 	CK(e, cudaSetDevice(e->device));
 	if (!e->fz.loaded)
 		return fail(e, "no vocabulary image loaded");

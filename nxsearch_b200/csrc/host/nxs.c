@@ -103,6 +103,37 @@ nxs_get_error(const nxs_t *nxs, const char **msg)
 	return nxs->errcode;
 }
 
+/* "0-3", "0,2,5", "1": anything else leaves the single device of NXS_GPU_DEVICE. */
+static void
+parse_device_list(nxs_t *nxs, const char *s)
+{
+	int n = 0;
+
+	while (*s && n < NXS_MAX_GPU_DEVICES) {
+		char *end;
+		long a = strtol(s, &end, 10), b;
+
+		if (end == s || a < 0)
+			return;
+		b = a;
+		if (*end == '-') {
+			s = end + 1;
+			b = strtol(s, &end, 10);
+			if (end == s || b < a)
+				return;
+		}
+		for (long d = a; d <= b && n < NXS_MAX_GPU_DEVICES; d++)
+			nxs->devices[n++] = (int)d;
+		if (*end != ',' && *end != '\0')
+			return;
+		s = *end ? end + 1 : end;
+	}
+	if (n >= 1) {
+		nxs->n_devices = n;
+		nxs->device = nxs->devices[0];
+	}
+}
+
 NXS_API nxs_t *
 nxs_open(const char *basedir)
 {
@@ -122,6 +153,8 @@ nxs_open(const char *basedir)
 	free(path);
 	if ((s = getenv("NXS_GPU_DEVICE")) != NULL)
 		nxs->device = atoi(s);
+	if ((s = getenv("NXS_GPU_DEVICES")) != NULL)
+		parse_device_list(nxs, s);
 	return nxs;
 err:
 	free(path);

@@ -18,6 +18,7 @@
 #define NXS_DEFAULT_RESULTS_LIMIT	1000		/* ref nxs_impl.h:39 */
 #define NXS_DEFAULT_RANKING_ALGO	"BM25"		/* ref nxs_impl.h:40 */
 #define NXS_DEFAULT_LANGUAGE		"en"		/* ref nxs_impl.h:41 */
+#define NXS_MAX_GPU_DEVICES	16
 #define NXS_QUERY_RLIMIT		100		/* ref search.c:70 */
 
 struct nxs {
@@ -26,6 +27,13 @@ struct nxs {
 	nxs_err_t	errcode;
 	nxs_index_t *	indexes;	/* singly linked list of open indexes */
 	int		device;		/* CUDA device ordinal ($NXS_GPU_DEVICE) */
+	/*
+	 * $NXS_GPU_DEVICES ("0-7", "0,2,3"): more than one device => every
+	 * index of this instance keeps a replica of its image on each and a
+	 * batch's queries are split between them (nxsb_engine_create_replicated).
+	 */
+	int		devices[NXS_MAX_GPU_DEVICES];
+	int		n_devices;
 };
 
 struct nxs_params {

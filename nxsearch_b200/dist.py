@@ -70,6 +70,11 @@ class ShardedSearcher:
 
         self.engine, self.rank, self.world = engine, rank, world
         self.torch = torch
+        # The engine's kernels, the NCCL collective and the merge must be on ONE
+        # stream (the all-gather reads what the scorer wrote): bind the engine to
+        # torch's current stream here rather than trust the caller to have done it.
+        if torch.cuda.is_available():
+            engine.set_stream(torch.cuda.current_stream().cuda_stream)
         self._bufs: dict[tuple[int, int], tuple] = {}
         self._slots: dict[tuple[int, int, int], list] = {}
         self._next: dict[tuple[int, int, int], int] = {}

@@ -418,3 +418,52 @@ def test_a_c_program_links_the_library_and_gets_the_same_answers(nxs):
     lat = _ccaller.latency(nxs.base, "c", "BM25", 10, queries)
     assert lat["queries"] == len(queries) and lat["p50_us"] > 0
     idx.close()
+
+
+def test_replicated_engine_behind_the_c_api(nxs, monkeypatch):
+    """NXS_GPU_DEVICES: one nxs_t, a replica of the image per listed device, a
+    batch's queries split between them.  Three replicas (all on device 0 here,
+    every visible device on a multi-GPU box) must answer exactly as one engine
+    does: batches, single searches, fuzzy terms, and after add / remove."""
+    from nxsearch_b200 import engine
+
+    corpus = tools.Corpus.generate(30_000, 8_000)
+    nxs.create_index("r").close()
+    corpus.write(f"{nxs.base}/data/r/nxsterms", f"{nxs.base}/data/r/nxsdtmap")
+    qt = corpus.query_terms(600)
+    queries = [" OR ".join(corpus.term(int(t)) for t in qt[i:i + 1 + i % 4]) for i in range(0, 400, 4)]
+    queries += [f"{corpus.term(int(qt[400 + i]))} AND NOT {corpus.term(int(qt[450 + i]))}" for i in range(30)]
+    queries += [q.decode() for q in corpus.fuzzy_terms(12)]            # resolved by the vocabulary scan
+    queries += ["(", "zzzzzzzzzzzzzz"]                                # one syntax error, one no-match
+    ndev = engine.device_count()
+    devs = ",".join(str(d % ndev) for d in range(max(3, ndev)))
+
+    def run(base_nxs):
+        idx = base_nxs.open_index("r")
+        out = {}
+        for algo, limit in (("BM25", 10), ("TF-IDF", 100)):
+            out[algo, "batch"] = idx.search_batch(queries, limit=limit, algo=algo)
+            out[algo, "two"] = idx.search_batch(queries[:2], limit=limit, algo=algo)   # fewer queries than replicas
+            out[algo, "single"] = [idx.search(q, limit=limit, algo=algo) for q in queries[:5]]
+        top = out["BM25", "batch"][0][0][0]
+        idx.add(10_000_000 + len(out), f"{corpus.term(int(qt[0]))} {corpus.term(int(qt[1]))} brandnewterm")
+        idx.remove(top)
+        out["after"] = idx.search_batch(queries[:64] + ["brandnewterm"], limit=10, algo="BM25")
+        idx.close()
+        return out
+
+    one = run(nxs)
+    # undo the edits: the second run must start from the same files
+    shutil.rmtree(f"{nxs.base}/data/r")
+    nxs.create_index("r").close()
+    corpus.write(f"{nxs.base}/data/r/nxsterms", f"{nxs.base}/data/r/nxsdtmap")
+    monkeypatch.setenv("NXS_GPU_DEVICES", devs)
+    multi_nxs = capi.Nxs(nxs.base)
+    try:
+        many = run(multi_nxs)
+    finally:
+        multi_nxs.close()
+    assert one.keys() == many.keys()
+    for k in one:
+        assert one[k] == many[k], k
+    assert one["after"][-1] and one["BM25", "batch"][-2] is None and one["BM25", "batch"][-1] == []
