@@ -544,6 +544,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         line["doc_sharded"] = doc_sharded
     if "latency" in AUX:
         line["latency"] = AUX.pop("latency")
+    if "e2e_single_process" in AUX:
+        line["e2e_single_process"] = AUX.pop("e2e_single_process")
     if "e2e_fuzzymatch_default" in AUX:
         line["e2e_fuzzymatch_default"] = AUX.pop("e2e_fuzzymatch_default")
     if AUX:
@@ -851,6 +853,44 @@ def e2e_capi(args, corpus, batches, capi, rank=0, world=1, local_rank=0, dist=No
                     f"{lat['serial_queries_per_s']:.0f} q/s serial ({time.time() - t0:.1f}s incl. open + image build)")
             except Exception as exc:            # the leg is informational
                 log(f"[0] latency leg failed: {exc}")
+        if rank == 0 and world > 1 and not args.no_single_process_leg:
+            # ONE process, one nxs_t, all the GPUs: NXS_GPU_DEVICES makes the library keep a
+            # replica of the image per device and split each batch between them.  The other
+            # ranks are idle (they wait at the barrier below); a call carries `world` batches.
+            os.environ["NXS_GPU_DEVICES"] = f"0-{world - 1}"
+            try:
+                t0 = time.time()
+                nxs2 = capi.Nxs(base)
+                idx2 = nxs2.open_index("bench")
+                big = [(C.c_char_p * (world * args.batch))(*sum((strings[(j * world + r) % n] for r in range(world)), []))
+                       for j in range(min(n, 8))]
+                idx2.search_batch_arrays(big[0], args.limit, **params)        # builds the replicas
+                built = time.time() - t0
+                for s in range(args.warmup):
+                    idx2.search_batch_arrays(big[s % len(big)], args.limit, **params)
+                reps = []
+                for rep in range(E2E_REPS):
+                    t0 = time.perf_counter()
+                    ticket = idx2.search_batch_begin(big[0], args.limit, **params)
+                    for s in range(args.steps):
+                        nxt = (idx2.search_batch_begin(big[(s + 1) % len(big)], args.limit, **params)
+                               if s + 1 < args.steps else None)
+                        idx2.search_batch_end_arrays(ticket)
+                        ticket = nxt
+                    reps.append(time.perf_counter() - t0)
+                dts = sorted(reps)[len(reps) // 2]
+                AUX["e2e_single_process"] = {
+                    "value": world * args.batch * args.steps / dts, "unit": UNIT,
+                    "path": f"one process, one nxs_t, NXS_GPU_DEVICES=0-{world - 1}: nxs_index_search_batch_begin/_end "
+                            f"with {world * args.batch} queries per call, split over {world} replicas inside the library",
+                    "open_and_build_s": round(built, 2)}
+                log(f"[0] e2e, one process driving {world} GPUs: {world * args.batch * args.steps / dts:.0f} q/s")
+                idx2.close()
+                nxs2.close()
+            except Exception as exc:
+                log(f"[0] single-process leg failed: {exc}")
+            finally:
+                os.environ.pop("NXS_GPU_DEVICES", None)
         if world > 1:
             barrier()
         return (world * args.batch * args.steps / dt, h2d, d2h,
@@ -951,6 +991,8 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-query nxs_index_search leg")
     ap.add_argument("--no-fuzzy-leg", action="store_true", help="skip the fuzzymatch-on end-to-end leg")
+    ap.add_argument("--no-single-process-leg", action="store_true",
+                    help="N > 1: skip the one-process-all-GPUs leg (NXS_GPU_DEVICES)")
     ap.add_argument("--latency-queries", type=int, default=1024)
     ap.add_argument("--layout", default="auto", choices=["auto", "replica", "shard"],
                     help="N > 1: whole index on every GPU with its own query stream, or document shards + NCCL merge")

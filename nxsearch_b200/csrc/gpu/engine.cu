@@ -469,20 +469,28 @@ multi_search_begin(nxsb_engine_t *e, const nxsb_batch_t *b)
 	sp.h.assign(R, -1);
 	for (uint32_t r = 0; r <= R; r++)
 		sp.q0[r] = (uint32_t)((uint64_t)b->n_queries * r / R);
-	for (uint32_t r = 0; r < R; r++) {
+	/* The replicas stage their shares side by side (descriptor layout, H2D, launches). */
+	std::vector<std::thread> th;
+	auto begin_share = [&](uint32_t r) {
 		nxsb_batch_t sub = *b;
 
 		sub.queries = b->queries + sp.q0[r];
 		sub.n_queries = sp.q0[r + 1] - sp.q0[r];
-		if (sub.n_queries == 0)
-			continue;
 		/* Token and program arrays go whole: the queries' offsets stay valid. */
-		if ((sp.h[r] = nxsb_engine_search_begin(e->replicas[r], &sub)) < 0) {
-			for (uint32_t x = 0; x < r; x++)
-				if (sp.h[x] >= 0)
-					nxsb_engine_search_end(e->replicas[x], sp.h[x], nullptr, nullptr, nullptr);
-			return multi_fail(e, e->replicas[r], (int)r);
-		}
+		sp.h[r] = sub.n_queries ? nxsb_engine_search_begin(e->replicas[r], &sub) : -2;
+	};
+	for (uint32_t r = 1; r < R; r++)
+		th.emplace_back(begin_share, r);
+	begin_share(0);
+	for (auto &t : th)
+		t.join();
+	for (uint32_t r = 0; r < R; r++) {
+		if (sp.h[r] != -1)
+			continue;
+		for (uint32_t x = 0; x < R; x++)
+			if (sp.h[x] >= 0)
+				nxsb_engine_search_end(e->replicas[x], sp.h[x], nullptr, nullptr, nullptr);
+		return multi_fail(e, e->replicas[r], (int)r);
 	}
 	sp.busy = true;
 	return s;
