@@ -66,6 +66,7 @@ struct DTok {
 	float			wmax;		// the list's largest weight
 	float			wk;		// its k-th largest, k = the batch's ladder step (bmw.cuh); 0 = none
 	const uint8_t *		mtmax;		// long list without block arrays: bytes per mini-tile (bmw.cuh)
+	const uint32_t *	mtbits;		// ... and which of the mini-tile's blocks hold a posting
 };
 
 /* 16-byte result record (also the NCCL all-gather payload). */

@@ -219,6 +219,7 @@ struct nxsb_engine {
 	uint32_t	sb_stride = 0;
 	/* Long lists without block arrays: a byte per mini-tile (bmw.cuh). */
 	uint8_t *	d_mt_bm25 = nullptr, *d_mt_tfidf = nullptr;	// [n_long][mt_stride]
+	uint32_t *	d_mt_bits = nullptr;				// [n_long][mt_stride] blocks with a posting
 	uint32_t *	d_long_terms = nullptr;				// [n_long] term index of a row
 	uint32_t	mt_stride = 0;
 	float *		d_wmax_bm25 = nullptr, *d_wmax_tfidf = nullptr;	// [V] largest weight of a term
@@ -850,6 +851,7 @@ free_image(nxsb_engine_t *e)
 	dev_free(e->d_smax_tfidf);
 	dev_free(e->d_mt_bm25);
 	dev_free(e->d_mt_tfidf);
+	dev_free(e->d_mt_bits);
 	dev_free(e->d_long_terms);
 	dev_free(e->d_wmax_bm25);
 	dev_free(e->d_wmax_tfidf);
@@ -1054,10 +1056,11 @@ upload_stats(nxsb_engine_t *e)
 
 			CK(e, cudaMemsetAsync(e->d_mt_bm25, 0, bytes, e->stream));
 			CK(e, cudaMemsetAsync(e->d_mt_tfidf, 0, bytes, e->stream));
+			CK(e, cudaMemsetAsync(e->d_mt_bits, 0, bytes * 4, e->stream));
 			minitile_max_kernel<<<e->n_sms * 16, 256, 0, e->stream>>>(e->d_post, e->d_term_off,
 			    e->d_long_terms, e->d_bcol, e->d_skip_mt, e->n_long, e->n_mt, e->mt_stride,
 			    e->d_logtab, e->K0, e->K1, e->d_wmax_bm25, e->d_wmax_tfidf,
-			    e->d_mt_bm25, e->d_mt_tfidf);
+			    e->d_mt_bm25, e->d_mt_tfidf, e->d_mt_bits, e->bshift);
 			e->launches++;
 		}
 		if (e->d_kth_bm25) {
@@ -1389,7 +1392,8 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 			    dev_alloc(&e->d_wmax_tfidf, V) == cudaSuccess));
 			if (ok && !e->wide && e->bmw_enabled && e->n_long)
 				ok = dev_alloc(&e->d_mt_bm25, (size_t)e->n_long * e->mt_stride) == cudaSuccess &&
-				    dev_alloc(&e->d_mt_tfidf, (size_t)e->n_long * e->mt_stride) == cudaSuccess;
+				    dev_alloc(&e->d_mt_tfidf, (size_t)e->n_long * e->mt_stride) == cudaSuccess &&
+				    dev_alloc(&e->d_mt_bits, (size_t)e->n_long * e->mt_stride) == cudaSuccess;
 			/* Threshold priming (bmw.cuh): the ladder tables and, for the
 			 * lists longer than one part, the units of the two-level pass. */
 			std::vector<uint2> units, longs;
@@ -2534,7 +2538,8 @@ run_batch(nxsb_engine_t *e, Batch &B, Rec *d_recs)
 	    B.algo == NXSB_ALGO_BM25 ? e->d_wmax_bm25 : e->d_wmax_tfidf,
 	    B.bmw ? (B.algo == NXSB_ALGO_BM25 ? e->d_kth_bm25 : e->d_kth_tfidf) : nullptr,
 	    bmw_ladder_step(B.limit),
-	    B.bmw ? (B.algo == NXSB_ALGO_BM25 ? e->d_mt_bm25 : e->d_mt_tfidf) : nullptr, e->mt_stride,
+	    B.bmw ? (B.algo == NXSB_ALGO_BM25 ? e->d_mt_bm25 : e->d_mt_tfidf) : nullptr,
+	    B.bmw ? e->d_mt_bits : nullptr, e->mt_stride,
 	    e->ntiles, B.d_toks);
 	build_temp_skips_kernel<<<B.n_tok_all, 128, 0, st>>>(e->d_post, B.d_toks,
 	    B.d_tmp_skip, e->ntiles);

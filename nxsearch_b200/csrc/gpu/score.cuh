@@ -67,7 +67,7 @@ resolve_tokens_kernel(const uint32_t *__restrict__ term_ids, uint32_t n,
     const uint32_t *__restrict__ skip_mt, uint32_t n_mt,
     uint32_t *__restrict__ tmp_skip, const float *__restrict__ idf,
     const float *__restrict__ wmax, const float *__restrict__ kth, uint32_t kth_step,
-    const uint8_t *__restrict__ mtmax, uint32_t mt_stride,
+    const uint8_t *__restrict__ mtmax, const uint32_t *__restrict__ mtbits, uint32_t mt_stride,
     uint32_t ntiles, DTok *__restrict__ out)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -78,6 +78,7 @@ resolve_tokens_kernel(const uint32_t *__restrict__ term_ids, uint32_t n,
 	t.wk = 0.f;
 	t.wmax = 0.f;
 	t.mtmax = nullptr;
+	t.mtbits = nullptr;
 	const uint32_t id = term_ids[i];
 
 	if (id == 0 || id > n_terms) {
@@ -109,8 +110,10 @@ resolve_tokens_kernel(const uint32_t *__restrict__ term_ids, uint32_t n,
 		    : tmp_skip + (size_t)i * (ntiles + 1);
 		t.fine = row >= 0 && skip_mt ? skip_mt + (size_t)row * (n_mt + 1) : t.skip;
 		t.fine_shift = row >= 0 && skip_mt ? MT_SHIFT : TILE_SHIFT;
-		if (row >= 0 && mtmax && t.bcol == 0xffffffffu)
+		if (row >= 0 && mtmax && t.bcol == 0xffffffffu) {
 			t.mtmax = mtmax + (size_t)row * mt_stride;
+			t.mtbits = mtbits ? mtbits + (size_t)row * mt_stride : nullptr;
+		}
 	}
 	out[i] = t;
 }
