@@ -853,6 +853,13 @@ def e2e_capi(args, corpus, batches, capi, rank=0, world=1, local_rank=0, dist=No
                     f"{lat['serial_queries_per_s']:.0f} q/s serial ({time.time() - t0:.1f}s incl. open + image build)")
             except Exception as exc:            # the leg is informational
                 log(f"[0] latency leg failed: {exc}")
+        # The other ranks must not wait inside an NCCL barrier here (its kernel
+        # spins on their GPUs, which this leg uses): a gloo barrier on the CPU.
+        cpu_group = None
+        if world > 1 and not args.no_single_process_leg:
+            cpu_group = dist.new_group(backend="gloo")
+            barrier()
+            dist.barrier(group=cpu_group)
         if rank == 0 and world > 1 and not args.no_single_process_leg:
             # ONE process, one nxs_t, all the GPUs: NXS_GPU_DEVICES makes the library keep a
             # replica of the image per device and split each batch between them.  The other
@@ -891,6 +898,8 @@ def e2e_capi(args, corpus, batches, capi, rank=0, world=1, local_rank=0, dist=No
                 log(f"[0] single-process leg failed: {exc}")
             finally:
                 os.environ.pop("NXS_GPU_DEVICES", None)
+        if cpu_group is not None:
+            dist.barrier(group=cpu_group)
         if world > 1:
             barrier()
         return (world * args.batch * args.steps / dt, h2d, d2h,

@@ -22,6 +22,50 @@
 #include "query.h"
 #include "nxsb200_tools.h"
 
+/*
+ * NXSB_HOST_PROF=1: where a batch call's host time goes, printed at exit
+ * (development aid; a clock_gettime pair per stage when enabled, one branch
+ * when not).
+ */
+#include <time.h>
+enum { HP_PREPARE, HP_MERGE, HP_FUZZY, HP_BEGIN, HP_WAIT, HP_RESP, HP_N };
+static struct {
+	int		on;		/* 0 unknown, 1 yes, -1 no */
+	double		us[HP_N];
+	unsigned long	calls, queries;
+} g_hp;
+
+static void
+hp_report(void)
+{
+	static const char *names[HP_N] = { "prepare (pool)", "merge shares", "fuzzy lookups",
+	    "engine begin (layout, H2D, launches)", "engine end (wait + unpack)", "responses" };
+
+	if (!g_hp.calls)
+		return;
+	fprintf(stderr, "nxsearch-b200 host profile: %lu batch calls, %lu queries\n", g_hp.calls, g_hp.queries);
+	for (int i = 0; i < HP_N; i++)
+		fprintf(stderr, "  %-38s %9.1f us/call  %6.3f us/query\n", names[i],
+		    g_hp.us[i] / g_hp.calls, g_hp.us[i] / (g_hp.queries ? g_hp.queries : 1));
+}
+
+static inline double
+hp_now(void)
+{
+	struct timespec ts;
+
+	if (g_hp.on == 0) {
+		g_hp.on = getenv("NXSB_HOST_PROF") ? 1 : -1;
+		if (g_hp.on == 1)
+			atexit(hp_report);
+	}
+	if (g_hp.on != 1)
+		return 0;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e6 + ts.tv_nsec / 1e3;
+}
+#define HP_ADD(stage, t0) do { if (g_hp.on == 1) { const double _t = hp_now(); g_hp.us[stage] += _t - (t0); (t0) = _t; } } while (0)
+
 typedef struct {
 	uint64_t	limit;
 	int		algo;
@@ -503,6 +547,7 @@ nxs_index_search_batch_begin(nxs_index_t *idx, nxs_params_t *params,
 	nxs_batch_t *bt = NULL;
 	uint32_t k;
 	int ret = -1;
+	double hp_t = hp_now();
 
 	nxs_clear_error(nxs);
 	if (get_search_params(idx, params, &sp) == -1)
@@ -545,6 +590,7 @@ nxs_index_search_batch_begin(nxs_index_t *idx, nxs_params_t *params,
 		if (!job.shares)
 			goto oom;
 	}
+	HP_ADD(HP_PREPARE, hp_t);
 
 	/* Errors in query order (the slot keeps the last one, as a loop of single searches would). */
 	for (size_t i = 0; i < n; i++) {
@@ -601,6 +647,7 @@ nxs_index_search_batch_begin(nxs_index_t *idx, nxs_params_t *params,
 		blob_len += sh->blob_len;
 	}
 
+	HP_ADD(HP_MERGE, hp_t);
 	/* One batched fuzzy scan for every token that missed. */
 	if (n_miss && idx->n_terms) {
 		uint32_t *oterm = malloc(sizeof(uint32_t) * n_miss);
@@ -626,6 +673,7 @@ nxs_index_search_batch_begin(nxs_index_t *idx, nxs_params_t *params,
 			goto out;
 	}
 
+	HP_ADD(HP_FUZZY, hp_t);
 	/* More results than live documents cannot exist: clamp the limit. */
 	k = sp.limit > idx->n_live ? idx->n_live : (uint32_t)sp.limit;
 	if (k == 0)
@@ -649,6 +697,11 @@ nxs_index_search_batch_begin(nxs_index_t *idx, nxs_params_t *params,
 		}
 	}
 	ret = 0;
+	HP_ADD(HP_BEGIN, hp_t);
+	if (g_hp.on == 1) {
+		g_hp.calls++;
+		g_hp.queries += n;
+	}
 	goto out;
 oom:
 	nxs_set_error(nxs, NXS_ERR_SYSTEM, "out of memory");
@@ -698,6 +751,7 @@ nxs_index_search_batch_end(nxs_batch_t *bt, nxs_resp_t **resps)
 
 	if (!bt)
 		return -1;
+	double hp_t = hp_now();
 	idx = bt->idx;
 	nxs = idx->nxs;
 	n = bt->n;
@@ -722,6 +776,7 @@ nxs_index_search_batch_end(nxs_batch_t *bt, nxs_resp_t **resps)
 			goto out;
 		}
 	}
+	HP_ADD(HP_WAIT, hp_t);
 	for (size_t i = 0; resps && i < n; i++) {
 		if (bt->failed[i])
 			continue;
@@ -733,6 +788,7 @@ nxs_index_search_batch_end(nxs_batch_t *bt, nxs_resp_t **resps)
 		}
 	}
 	ret = 0;
+	HP_ADD(HP_RESP, hp_t);
 out:
 	if (ret != 0) {
 		for (size_t i = 0; resps && i < n; i++) {
