@@ -76,6 +76,18 @@ const char *	nxsb_engine_errmsg(const nxsb_engine_t *);
  * passed as void *; NULL restores the engine's own stream).
  */
 int		nxsb_engine_set_stream(nxsb_engine_t *, void *cuda_stream);
+/*
+ * Without an external stream the engine runs searches on two streams of its
+ * own ("lanes"): nxsb_engine_search_begin slots and nxsb_engine_batch_run
+ * handles alternate between them, so that two batches in flight overlap on
+ * the GPU (the image is shared, arenas exist per lane; NXSB_LANES=1 turns it
+ * off).  lane_stream returns a lane's cudaStream_t (as void *) for callers
+ * that time with their own events; lanes_join makes lane 0 wait for what the
+ * other lanes have been given so far, so that an event recorded on lane 0
+ * afterwards closes a region that spans both.
+ */
+void *		nxsb_engine_lane_stream(nxsb_engine_t *, int lane);
+int		nxsb_engine_lanes_join(nxsb_engine_t *);
 
 /*
  * One document shard in document-major form (host memory), documents in

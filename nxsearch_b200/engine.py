@@ -46,6 +46,8 @@ def _bind():
         "nxsb_engine_destroy": (None, [vp]),
         "nxsb_engine_errmsg": (C.c_char_p, [vp]),
         "nxsb_engine_set_stream": (i, [vp, vp]),
+        "nxsb_engine_lane_stream": (vp, [vp, i]),
+        "nxsb_engine_lanes_join": (i, [vp]),
         "nxsb_engine_load_shard": (i, [vp, C.POINTER(ShardDesc)]),
         "nxsb_engine_segment_add": (i, [vp, C.POINTER(ShardDesc)]),
         "nxsb_engine_segment_count": (i, [vp]),
@@ -146,6 +148,14 @@ class Engine:
 
     def set_stream(self, cuda_stream: int | None) -> None:
         self._check(self._lib.nxsb_engine_set_stream(self._h, cuda_stream))
+
+    def lane_stream(self, lane: int = 0) -> int:
+        """cudaStream_t (as an integer) of one of the engine's own streams."""
+        return int(self._lib.nxsb_engine_lane_stream(self._h, lane) or 0)
+
+    def lanes_join(self) -> None:
+        """Lane 0 waits for what the other lanes have been given so far."""
+        self._check(self._lib.nxsb_engine_lanes_join(self._h))
 
     def load_corpus(self, corpus, *, lo: int = 0, hi: int | None = None, df=None,
                     token_count: int | None = None, doc_count: int | None = None,
