@@ -48,7 +48,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 METRIC = "BM25 top-10 queries/s, 10M-doc synthetic index"
 UNIT = "queries/s"
 E2E_REPS = 5       # repetitions of the K-step end-to-end measurement (median reported)
-E2E_DEPTH = int(os.environ.get("NXSB_BENCH_DEPTH", "3"))      # batches in flight in the pipelined end-to-end leg (the library allows 4)
+E2E_DEPTH = int(os.environ.get("NXSB_BENCH_DEPTH", "4"))      # batches in flight in the pipelined end-to-end leg (the library's maximum)
 
 # BASELINE.json configs served by this file (--config): the query shape, the
 # ranking algorithm and the limit.  c2 is the headline; c5 is c2 at 100M
@@ -935,7 +935,7 @@ def e2e_capi(args, corpus, batches, capi, rank=0, world=1, local_rank=0, dist=No
             barrier()
         return (world * args.batch * args.steps / dt, h2d, d2h,
                 "nxs_index_search_batch_begin/_end (C API: C strings in, results drained via "
-                "nxs_resp_iter_result into host arrays; three batches in flight, two at a time on the GPU)%s; median of 5 K-step "
+                "nxs_resp_iter_result into host arrays; four batches in flight, two at a time on the GPU)%s; median of 5 K-step "
                 "measurements; synchronous nxs_index_search_batch: %.0f queries/s"
                 % (f" on each of {world} processes, one GPU each, sharing the index files" if world > 1 else "",
                    world * args.batch * args.steps / dt_serial))
