@@ -1266,7 +1266,8 @@ score_bmw_kernel(const BmwParams p)
 						for (uint32_t x = 0; x < U; x++) {
 							const uint32_t b = warp * (BMW_CH_BLOCKS / BMW_WARPS) + (i0 + x) * 32u + lane;
 
-							m[x] = b < nb ? __ldg(row + b) : 0.f;
+							/* A superblock the first pass ruled out costs no loads. */
+							m[x] = (b < nb && ((live_mask >> (i0 + x)) & 1u)) ? __ldg(row + b) : 0.f;
 						}
 #pragma unroll
 						for (uint32_t x = 0; x < U; x++) {
@@ -1292,7 +1293,8 @@ score_bmw_kernel(const BmwParams p)
 								const uint32_t b = warp * (BMW_CH_BLOCKS / BMW_WARPS) + (i0 + x) * 32u + lane;
 								const uint32_t doc = (cb0 + b) << BSHIFT;
 
-								if (b < nb && ((__ldg(bt.mtbits + (doc >> MT_SHIFT)) >>
+								if (b < nb && ((live_mask >> (i0 + x)) & 1u) &&
+								    ((__ldg(bt.mtbits + (doc >> MT_SHIFT)) >>
 								    ((doc & ((1u << MT_SHIFT) - 1u)) >> BSHIFT)) & 1u))
 									pm[x] |= 1u << j;
 							}
@@ -1304,7 +1306,7 @@ score_bmw_kernel(const BmwParams p)
 
 						if (any_list)
 							u[x] = __fadd_rn(u[x], ub[b]);
-						u[x] = b < nb ? __fmul_ru(u[x], infl) : 0.f;
+						u[x] = (b < nb && ((live_mask >> (i0 + x)) & 1u)) ? __fmul_ru(u[x], infl) : 0.f;
 						if (LOGIC && !satisfiable(pm[x]))
 							u[x] = 0.f;
 						ub[b] = u[x];

@@ -10,6 +10,6 @@ mkdir -p "$out"
 nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
     -Xcompiler -fPIC,-fvisibility=hidden -I"$root/include" "$@" \
     -c "$root/nxsearch_b200/csrc/gpu/engine.cu" -o "$out/engine.o"
-objs=$(ls "$root"/nxsearch_b200/lib/obj/*.c.o)
+objs=$(ls "$root"/nxsearch_b200/lib/obj/*.c.o | grep -v "corpus.c.o\|querytools.c.o")
 nvcc -shared -o "$out/libnxsearch.so" $objs "$out/engine.o" -cudart static -lpthread -lm
 echo "$out/libnxsearch.so"
