@@ -171,3 +171,41 @@ def test_fuzzy_candidate_sets(c1_corpus, c1_oracle, c1_engine):
         assert term[i] == (live[0] if live else 0) == pick, q
         pruned_away += n - len(reached)
     assert pruned_away > 0, "the BK-tree's half-open range should lose some true matches"
+
+
+def test_four_searches_in_flight_on_two_lanes(c1_corpus, monkeypatch):
+    """nxsb_engine_search_begin x4 before the first _end: the slots alternate
+    between the engine's two streams (arenas per lane, one shared image).
+    Every batch -- OR, boolean, different limits and algorithms, rerun several
+    times in different orders -- must come back exactly as from an engine that
+    runs everything on one stream (NXSB_LANES=1)."""
+    from nxsearch_b200 import engine
+    from test_gpu_stream import bool_queries, or_queries
+
+    lanes = engine.Engine(0)
+    monkeypatch.setenv("NXSB_LANES", "1")
+    single = engine.Engine(0)
+    monkeypatch.delenv("NXSB_LANES")
+    try:
+        lanes.load_corpus(c1_corpus)
+        single.load_corpus(c1_corpus)
+        batches = [engine.Batch.from_lists(BM25, 10, or_queries(c1_corpus, 300)),
+                   engine.Batch.from_lists(TFIDF, 100, bool_queries(c1_corpus, 200)),
+                   engine.Batch.from_lists(TFIDF, 10, or_queries(c1_corpus, 257, seed_off=5)),
+                   engine.Batch.from_lists(BM25, 500, or_queries(c1_corpus, 64, seed_off=9)),    # beyond the pruned limits
+                   engine.Batch.from_lists(BM25, 100, bool_queries(c1_corpus, 129))]
+        want = [single.search(b) for b in batches]
+        for rnd in range(6):
+            order = [(rnd + i) % len(batches) for i in range(4)]
+            tickets = [lanes.search_begin(batches[j]) for j in order]
+            for j, t in zip(order, tickets):
+                b = batches[j]
+                counts, ids, scores = lanes.search_end(t, len(b.queries), b.limit)
+                assert np.array_equal(counts, want[j][0]), (rnd, j)
+                for q in range(len(counts)):
+                    n = int(counts[q])
+                    assert np.array_equal(ids[q, :n], want[j][1][q, :n]), (rnd, j, q)
+                    assert np.array_equal(scores[q, :n].view(np.uint32), want[j][2][q, :n].view(np.uint32)), (rnd, j, q)
+    finally:
+        lanes.close()
+        single.close()
