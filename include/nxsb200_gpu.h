@@ -194,6 +194,19 @@ int		nxsb_engine_search_begin(nxsb_engine_t *, const nxsb_batch_t *);
 int		nxsb_engine_search_end(nxsb_engine_t *, int handle,
 		    uint32_t *counts, uint64_t *ids, float *scores);
 /*
+ * begin for a batch some of whose tokens still need a fuzzy lookup (the
+ * reference resolves them one by one before it scores, ref src/index/
+ * idxterm.c:210-249 from src/core/tokenizer.c): miss i is the byte string
+ * miss_blob[miss_off[i] .. miss_off[i+1]) and its answer -- the term
+ * nxsb_engine_fuzzy would return, 0 = none = an empty list -- replaces
+ * batch.tokens[miss_pos[i]] ON THE DEVICE, between the descriptor copy and
+ * the scoring kernels of the same stream: the host never waits for the scan.
+ * (Replicated engines and segmented images run the lookups first instead.)
+ */
+int		nxsb_engine_search_begin_fz(nxsb_engine_t *, const nxsb_batch_t *,
+		    uint32_t n_miss, const char *miss_blob, const uint32_t *miss_off,
+		    const uint32_t *miss_pos);
+/*
  * begin for a sharded index: this shard's 16-byte records (see batch_run) are
  * written to d_recs, device memory owned by the caller -- the send buffer of
  * the all-gather -- and nothing is copied to the host.  End it with

@@ -317,6 +317,7 @@ struct nxsb_engine {
 	/* vocabulary (fuzzy) */
 	FuzzyImage	fz;
 	FuzzyScratch	fz_scratch;
+	FuzzyScratch	fz_pipe[PIPE_DEPTH];	// lookups queued with a search, per slot
 
 	/*
 	 * Delta segments (incremental refresh): child engines on the same
@@ -1022,6 +1023,8 @@ nxsb_engine_destroy(nxsb_engine_t *e)
 	free_image(e);
 	fuzzy_free(e->fz);
 	fuzzy_scratch_free(e->fz_scratch);
+	for (auto &z : e->fz_pipe)
+		fuzzy_scratch_free(z);
 	for (int i = 0; i < N_LANES; i++) {
 		nxsb_engine::Lane &l = e->lanes[i];
 
@@ -2900,8 +2903,16 @@ nxsb_engine_search(nxsb_engine_t *e, const nxsb_batch_t *b, uint32_t *counts,
  * copy, every kernel and the result copy on the engine's stream and records
  * an event; end waits for that event only.
  */
+/* Lookups whose answers the batch's token list is waiting for (search_begin_fz). */
+struct FzPending {
+	uint32_t		n;
+	const char *		blob;
+	const uint32_t *	off;	/* [n + 1] */
+	const uint32_t *	pos;	/* [n] index into batch.tokens */
+};
+
 static int
-search_begin(nxsb_engine_t *e, const nxsb_batch_t *b, Rec *d_recs)
+search_begin(nxsb_engine_t *e, const nxsb_batch_t *b, Rec *d_recs, const FzPending *fz = nullptr)
 {
 	int s = -1;
 
@@ -2924,9 +2935,30 @@ search_begin(nxsb_engine_t *e, const nxsb_batch_t *b, Rec *d_recs)
 	if (segmented(e)) {
 		if (run_segmented(e, B, e->seg_pipe[s], b, d_recs, s) == -1)
 			return -1;
-	} else if (fill_batch(e, B, b) == -1 ||
-	    run_batch(e, B, d_recs ? d_recs : B.d_recs) == -1) {
-		return -1;
+	} else {
+		if (fill_batch(e, B, b) == -1)
+			return -1;
+		if (fz && fz->n) {
+			/*
+			 * Behind the descriptor copy, ahead of the token resolve, on
+			 * the same stream: the vocabulary scan of the missing terms
+			 * and a kernel that writes the picks into the token list.
+			 * Nothing waits on the host.
+			 */
+			FuzzyOut o;
+			int launches = 0;
+
+			if (fuzzy_enqueue(e->fz, e->fz_pipe[s], fz->n, fz->blob, fz->off, 0, fz->n,
+			    e->stream, e->n_sms, &launches, &o) != 0)
+				return fail(e, "fuzzy scan failed: %s", cudaGetErrorString(cudaGetLastError()));
+			CK(e, cudaMemcpyAsync(o.extra, fz->pos, (size_t)fz->n * 4, cudaMemcpyHostToDevice, e->stream));
+			fuzzy_patch_tokens_kernel<<<(fz->n + 255) / 256, 256, 0, e->stream>>>(B.d_tokens,
+			    o.extra, o.term, fz->n);
+			e->launches += launches + 1;
+			CK(e, cudaGetLastError());
+		}
+		if (run_batch(e, B, d_recs ? d_recs : B.d_recs) == -1)
+			return -1;
 	}
 	if (!d_recs && enqueue_fetch(e, B) == -1)
 		return -1;
@@ -2948,6 +2980,41 @@ nxsb_engine_search_begin(nxsb_engine_t *e, const nxsb_batch_t *b)
  * (the send buffer of the cross-shard all-gather); end the search with
  * counts = NULL once whatever consumes d_recs has been enqueued.
  */
+extern "C" int
+nxsb_engine_search_begin_fz(nxsb_engine_t *e, const nxsb_batch_t *b, uint32_t n_miss,
+    const char *miss_blob, const uint32_t *miss_off, const uint32_t *miss_pos)
+{
+	if (n_miss == 0)
+		return nxsb_engine_search_begin(e, b);
+	for (uint32_t i = 0; i < n_miss; i++)
+		if (miss_pos[i] >= b->n_tokens) {
+			return fail(e, "search_begin_fz: token position %u out of range", miss_pos[i]);
+		}
+	nxsb_engine_t *fe = is_multi(e) ? e->replicas[0] : e;	/* who holds the vocabulary */
+
+	if (!fe->fz.loaded)
+		return fail(e, "no vocabulary image loaded");
+	if (!is_multi(e) && !segmented(e)) {
+		const FzPending fz = { n_miss, miss_blob, miss_off, miss_pos };
+
+		return search_begin(e, b, nullptr, &fz);
+	}
+	/*
+	 * Replicas (the vocabulary lives on the first) and segmented images
+	 * (every segment stages its own copy of the tokens): the lookups run
+	 * first and their answers go into a host copy of the token list.
+	 */
+	std::vector<uint32_t> term(n_miss), dist(n_miss), toks(b->tokens, b->tokens + b->n_tokens);
+	nxsb_batch_t b2 = *b;
+
+	if (nxsb_engine_fuzzy(fe, n_miss, miss_blob, miss_off, term.data(), dist.data(), nullptr) != 0)
+		return is_multi(e) ? multi_fail(e, fe, 0) : -1;
+	for (uint32_t i = 0; i < n_miss; i++)
+		toks[miss_pos[i]] = term[i];
+	b2.tokens = toks.data();
+	return nxsb_engine_search_begin(e, &b2);
+}
+
 extern "C" int
 nxsb_engine_search_begin_dev(nxsb_engine_t *e, const nxsb_batch_t *b, void *d_recs)
 {

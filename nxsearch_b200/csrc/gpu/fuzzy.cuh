@@ -647,25 +647,30 @@ fuzzy_grow(T *&p, size_t &cap, size_t want)
  * out_*: host arrays [n].  cand_cap > 0: also the candidate lists, host arrays
  * cand_cnt[n] and cand[n * cand_cap] (see FuzzyCandOut), unsorted.
  */
+/* Where fuzzy_enqueue left its results (device memory of the scratch). */
+struct FuzzyOut {
+	uint32_t *	term = nullptr;		/* [n] 1-based term id, 0 = none */
+	uint32_t *	dist = nullptr;
+	uint32_t *	n_true = nullptr;
+	uint32_t *	cand_cnt = nullptr;
+	uint32_t *	extra = nullptr;	/* [extra_words] for the caller */
+};
+
+/*
+ * Everything of a lookup call that can be queued: copies in, kernels, results
+ * left on the device (n >= 1).  No host synchronisation.
+ */
 static int
-fuzzy_run(FuzzyImage &f, FuzzyScratch &z, uint32_t n, const char *qblob, const uint32_t *qoff,
-    uint32_t *out_term, uint32_t *out_dist, uint32_t *out_true,
-    uint32_t cand_cap, uint32_t *cand_cnt, uint4 *cand,
-    cudaStream_t st, int n_sms, int *launches)
+fuzzy_enqueue(FuzzyImage &f, FuzzyScratch &z, uint32_t n, const char *qblob, const uint32_t *qoff,
+    uint32_t cand_cap, size_t extra_words, cudaStream_t st, int n_sms, int *launches, FuzzyOut *out)
 {
 	std::vector<uint32_t> &sel32 = z.sel32, &sel64 = z.sel64;
 
-	if (n == 0)
-		return 0;
 	sel32.clear();
 	sel64.clear();
 	for (uint32_t i = 0; i < n; i++) {
 		const uint32_t m = qoff[i + 1] - qoff[i];
 
-		out_term[i] = 0;
-		out_dist[i] = 0;
-		if (out_true)
-			out_true[i] = 0;
 		/*
 		 * Empty queries never reach the fuzzy search; patterns beyond
 		 * 64 bytes are reported as "no match" (documented limit).
@@ -685,7 +690,7 @@ fuzzy_run(FuzzyImage &f, FuzzyScratch &z, uint32_t n, const char *qblob, const u
 	const size_t nn = n;
 	const size_t o_qoff = 0, o_s32 = o_qoff + nn + 1, o_s64 = o_s32 + nn, o_term = o_s64 + nn,
 	    o_dist = o_term + nn, o_true = o_dist + nn, o_cnt = o_true + nn, o_key = (o_cnt + nn + 1) & ~(size_t)1,
-	    words = o_key + 2 * nn;
+	    o_extra = o_key + 2 * nn, words = o_extra + extra_words;
 
 	if (!fuzzy_grow(z.d_qblob, z.blob_cap, (size_t)qoff[n] + 16) ||
 	    !fuzzy_grow(z.d_words, z.words_cap, words) ||
@@ -731,15 +736,47 @@ fuzzy_run(FuzzyImage &f, FuzzyScratch &z, uint32_t n, const char *qblob, const u
 		fuzzy_unpack_kernel<<<(n + 255) / 256, 256, 0, st>>>(keys, n, w + o_term, w + o_dist);
 		(*launches)++;
 	}
-	cudaMemcpyAsync(out_term, w + o_term, nn * 4, cudaMemcpyDeviceToHost, st);
-	cudaMemcpyAsync(out_dist, w + o_dist, nn * 4, cudaMemcpyDeviceToHost, st);
+	out->term = w + o_term;
+	out->dist = w + o_dist;
+	out->n_true = w + o_true;
+	out->cand_cnt = w + o_cnt;
+	out->extra = w + o_extra;
+	return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+static int
+fuzzy_run(FuzzyImage &f, FuzzyScratch &z, uint32_t n, const char *qblob, const uint32_t *qoff,
+    uint32_t *out_term, uint32_t *out_dist, uint32_t *out_true,
+    uint32_t cand_cap, uint32_t *cand_cnt, uint4 *cand,
+    cudaStream_t st, int n_sms, int *launches)
+{
+	const size_t nn = n;
+	FuzzyOut o;
+
+	if (n == 0)
+		return 0;
+	if (fuzzy_enqueue(f, z, n, qblob, qoff, cand_cap, 0, st, n_sms, launches, &o) != 0)
+		return -1;
+	cudaMemcpyAsync(out_term, o.term, nn * 4, cudaMemcpyDeviceToHost, st);
+	cudaMemcpyAsync(out_dist, o.dist, nn * 4, cudaMemcpyDeviceToHost, st);
 	if (out_true)
-		cudaMemcpyAsync(out_true, w + o_true, nn * 4, cudaMemcpyDeviceToHost, st);
+		cudaMemcpyAsync(out_true, o.n_true, nn * 4, cudaMemcpyDeviceToHost, st);
 	if (cand_cap) {
-		cudaMemcpyAsync(cand_cnt, w + o_cnt, nn * 4, cudaMemcpyDeviceToHost, st);
+		cudaMemcpyAsync(cand_cnt, o.cand_cnt, nn * 4, cudaMemcpyDeviceToHost, st);
 		cudaMemcpyAsync(cand, z.d_cand, nn * cand_cap * sizeof(uint4), cudaMemcpyDeviceToHost, st);
 	}
 	return cudaStreamSynchronize(st) == cudaSuccess ? 0 : -1;
+}
+
+/* tokens[pos[i]] = term[i]: the lookups' answers take their places in a batch's token list. */
+__global__ void __launch_bounds__(256)
+fuzzy_patch_tokens_kernel(uint32_t *__restrict__ tokens, const uint32_t *__restrict__ pos,
+    const uint32_t *__restrict__ term, uint32_t n)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+
+	if (i < n)
+		tokens[pos[i]] = term[i];
 }
 
 #endif

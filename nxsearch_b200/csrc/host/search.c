@@ -648,31 +648,19 @@ nxs_index_search_batch_begin(nxs_index_t *idx, nxs_params_t *params,
 	}
 
 	HP_ADD(HP_MERGE, hp_t);
-	/* One batched fuzzy scan for every token that missed. */
+	/*
+	 * Tokens that missed keep id 0 here; their strings go to the engine with
+	 * the batch, which scans the vocabulary for them on the GPU and writes
+	 * the picks into the device copy of the token list before it scores --
+	 * no wait on the host (nxsb_engine_search_begin_fz).
+	 */
 	if (n_miss && idx->n_terms) {
-		uint32_t *oterm = malloc(sizeof(uint32_t) * n_miss);
-		uint32_t *odist = malloc(sizeof(uint32_t) * n_miss);
-		int rc = -1;
-
 		miss_off[n_miss] = blob_len;
-		if (!oterm || !odist) {
-			nxs_set_error(nxs, NXS_ERR_SYSTEM, "out of memory");
-		} else if (idx_gpu_prepare(idx, true) == 0) {
-			rc = nxsb_engine_fuzzy(idx->engine, n_miss, miss_blob, miss_off,
-			    oterm, odist, NULL);
-			if (rc == -1)
-				nxs_set_error(nxs, NXS_ERR_SYSTEM, "GPU fuzzy match "
-				    "failed: %s", nxsb_engine_errmsg(idx->engine));
-		}
-		/* A token nothing matched keeps id 0: an empty list. */
-		for (size_t m = 0; rc == 0 && m < n_miss; m++)
-			tokens[miss_pos[m]] = oterm[m];
-		free(oterm);
-		free(odist);
-		if (rc != 0)
+		if (idx_gpu_prepare(idx, true) == -1)
 			goto out;
+	} else {
+		n_miss = 0;
 	}
-
 	HP_ADD(HP_FUZZY, hp_t);
 	/* More results than live documents cannot exist: clamp the limit. */
 	k = sp.limit > idx->n_live ? idx->n_live : (uint32_t)sp.limit;
@@ -689,7 +677,8 @@ nxs_index_search_batch_begin(nxs_index_t *idx, nxs_params_t *params,
 
 		if (idx_gpu_prepare(idx, false) == -1)
 			goto out;
-		bt->handle = nxsb_engine_search_begin(idx->engine, &batch);
+		bt->handle = nxsb_engine_search_begin_fz(idx->engine, &batch, (uint32_t)n_miss,
+		    miss_blob, miss_off, miss_pos);
 		if (bt->handle == -1) {
 			nxs_set_error(nxs, NXS_ERR_SYSTEM, "GPU search failed: %s",
 			    nxsb_engine_errmsg(idx->engine));
