@@ -176,6 +176,7 @@ idx_terms_open(nxs_index_t *idx, const char *path)
 		goto err;
 	idx->terms_consumed = 0;
 	idx->n_terms = 0;
+	idx->max_term_len = 0;
 	flock(idx->tfile.fd, LOCK_UN);
 	return idx_terms_sync(idx);
 err:
@@ -232,6 +233,8 @@ term_register(nxs_index_t *idx, const char *val, size_t len, size_t total_off)
 	idx->blob_len += len;
 	idx->term_blob[idx->blob_len] = '\0';
 	idx->term_total_off[idx->n_terms] = total_off;
+	if (len > idx->max_term_len)
+		idx->max_term_len = (uint32_t)len;
 	idx->n_terms++;
 	idx->term_off[idx->n_terms] = idx->blob_len;
 	/*

@@ -44,6 +44,7 @@ struct nxs_index {
 	idxfile_t		tfile;
 	size_t			terms_consumed;
 	uint32_t		n_terms;	/* == last term id */
+	uint32_t		max_term_len;	/* longest vocabulary term, bytes */
 	uint32_t		terms_cap;
 	strmap_t *		term_map;	/* value -> term id */
 	char *			term_blob;

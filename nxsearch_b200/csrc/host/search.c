@@ -28,6 +28,8 @@
  * when not).
  */
 #include <time.h>
+#define NXS_FUZZY_MAX_LEN	64u	/* fuzzy.cuh FZ_MAX_QLEN: the Myers pattern is one 64-bit word */
+
 enum { HP_PREPARE, HP_MERGE, HP_FUZZY, HP_BEGIN, HP_WAIT, HP_RESP, HP_N };
 static struct {
 	int		on;		/* 0 unknown, 1 yes, -1 no */
@@ -352,6 +354,20 @@ prepare_one(const prep_job_t *job, share_t *sh, size_t i)
 		if (qt.tok[j].term_id) {
 			n_resolved++;
 		} else if (job->sp->fuzzymatch) {
+			/*
+			 * The GPU scan takes patterns of up to NXS_FUZZY_MAX_LEN
+			 * bytes.  A longer one can only match a term within 2
+			 * bytes of its length: none that long in the vocabulary
+			 * means "no match" is the exact answer; otherwise the
+			 * query fails alone, loudly, rather than miss silently.
+			 */
+			if (qt.tok[j].len > NXS_FUZZY_MAX_LEN &&
+			    idx->max_term_len + 2 >= qt.tok[j].len) {
+				query_fail(err, NXS_ERR_LIMIT, "fuzzy match of a %u-byte term is "
+				    "not supported (limit %u bytes)", (unsigned)qt.tok[j].len,
+				    NXS_FUZZY_MAX_LEN);
+				goto out;
+			}
 			n_miss++;
 			miss_bytes += qt.tok[j].len;
 		}

@@ -467,3 +467,27 @@ def test_replicated_engine_behind_the_c_api(nxs, monkeypatch):
     for k in one:
         assert one[k] == many[k], k
     assert one["after"][-1] and one["BM25", "batch"][-2] is None and one["BM25", "batch"][-1] == []
+
+
+def test_long_fuzzy_patterns_are_exact_or_loud(nxs):
+    """The vocabulary scan takes patterns of up to 64 bytes.  A longer query
+    term can only match a vocabulary term within 2 bytes of its length: with
+    none that long "no match" is the exact answer; with one, the query fails
+    alone with NXS_ERR_LIMIT instead of missing silently (the reference would
+    find it, ref src/index/idxterm.c:210-249)."""
+    idx = nxs.create_index("f", filters=["normalizer"])
+    idx.add(1, "alpha beta gamma")
+    idx.add(2, "beta delta")
+    long_q = "x" * 70
+    res = idx.search_batch([long_q, "beta", f"{long_q} OR delta"], limit=10, algo="BM25")
+    assert res[0] == [] and [d for d, _ in res[1]] == [2, 1] and [d for d, _ in res[2]] == [2]
+    idx.add(3, "y" * 69 + " beta")                       # now the vocabulary has a term that long
+    res = idx.search_batch([long_q, "beta", "y" * 69], limit=10, algo="BM25")
+    assert res[0] is None and len(res[1]) == 3 and [d for d, _ in res[2]] == [3]
+    code, msg = nxs.error()
+    assert code == capi.ERR_LIMIT and "fuzzy match" in msg
+    with pytest.raises(capi.NxsError) as e:
+        idx.search(long_q, limit=10)
+    assert e.value.code == capi.ERR_LIMIT
+    assert [d for d, _ in idx.search(long_q, limit=10, fuzzymatch=False)] == []
+    idx.close()
