@@ -55,6 +55,9 @@
 #define NXSB_GPU_BMW_CUH
 
 #define BMW_THREADS	256
+#ifndef BMW_MIN_CTAS
+#define BMW_MIN_CTAS	4			/* CTAs per SM the register budget is set for */
+#endif
 #define BMW_WARPS	(BMW_THREADS / 32)
 #define BMW_CH_BLOCKS	8192u			/* blocks per chunk */
 #define BMW_CH_SB	(BMW_CH_BLOCKS / 32u)		/* superblocks (32 blocks) per chunk */
@@ -646,7 +649,7 @@ term_kth_merge_kernel(const uint2 *__restrict__ longs, uint32_t n_long,
 /* ---- the scorer --------------------------------------------------------- */
 
 template <int ALGO, uint32_t BSHIFT, bool LOGIC>
-__global__ void __launch_bounds__(BMW_THREADS, 4)
+__global__ void __launch_bounds__(BMW_THREADS, BMW_MIN_CTAS)
 score_bmw_kernel(const BmwParams p)
 {
 	using Cfg = BmwCfg<BSHIFT, LOGIC>;
