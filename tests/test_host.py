@@ -243,6 +243,29 @@ def test_a_c_program_compiles_against_the_header_and_links_the_library(nxs):
         assert out[0].split()[0] == "1" and out[1].split()[0] == "2", out
 
 
+@pytest.mark.parametrize("spec", ["0-3,5", "3-1", "0,,x"])
+def test_gpu_device_list_is_parsed_or_ignored(spec, monkeypatch):
+    """NXS_GPU_DEVICES takes ranges and lists; anything malformed leaves the
+    single device of NXS_GPU_DEVICE.  Without a GPU the search then fails as
+    loudly as ever (and with one, answers are checked in test_gpu_capi.py)."""
+    from nxsearch_b200 import engine
+
+    monkeypatch.setenv("NXS_GPU_DEVICES", spec)
+    base = tempfile.mkdtemp(prefix="nxsb_t_")
+    n = capi.Nxs(base)
+    try:
+        idx = n.create_index("d")
+        idx.add(1, "alpha beta")
+        if engine.device_count() == 0:
+            with pytest.raises(capi.NxsError) as e:
+                idx.search("alpha")
+            assert e.value.code == capi.ERR_SYSTEM
+        idx.close()
+    finally:
+        n.close()
+        shutil.rmtree(base, ignore_errors=True)
+
+
 def test_index_files_are_interchangeable_with_the_reference(nxs, c1_corpus):
     """Files written through nxs_index_add here open in the compiled reference
     and vice versa, byte-identical for the same sequence of adds."""
