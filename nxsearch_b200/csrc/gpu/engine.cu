@@ -516,9 +516,18 @@ multi_search_begin(nxsb_engine_t *e, const nxsb_batch_t *b)
 		/* Token and program arrays go whole: the queries' offsets stay valid. */
 		sp.h[r] = sub.n_queries ? nxsb_engine_search_begin(e->replicas[r], &sub) : -2;
 	};
-	for (uint32_t r = 1; r < R; r++)
-		th.emplace_back(begin_share, r);
-	begin_share(0);
+	/* Empty shares cost nothing (a single query wakes one replica, no thread). */
+	uint32_t mine = R;
+	for (uint32_t r = 0; r < R; r++) {
+		if (sp.q0[r + 1] == sp.q0[r])
+			sp.h[r] = -2;
+		else if (mine == R)
+			mine = r;
+		else
+			th.emplace_back(begin_share, r);
+	}
+	if (mine < R)
+		begin_share(mine);
 	for (auto &t : th)
 		t.join();
 	for (uint32_t r = 0; r < R; r++) {
