@@ -291,8 +291,9 @@ def run_reference(args, rank: int, world: int) -> None:
         "warmup": args.warmup, "ms_per_step": 1000 * total / steps_done, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "impl": "reference",
+        # our arm's config; what one timed step of THIS arm covers is `sample_queries_per_step`
         "config": {"workload": workload_name(args), "docs": args.docs, "vocab": args.vocab,
-                   "batch": per_step, "limit": args.limit},
+                   "batch": args.batch, "limit": args.limit, "sample_queries_per_step": per_step},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
