@@ -35,3 +35,25 @@ def test_other_ranks_of_the_reference_arm_do_no_work():
     proc = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2"],
                           capture_output=True, text=True, timeout=120, env=env)
     assert proc.returncode == 0 and proc.stdout.strip() == ""
+
+
+def test_bench_query_strings_compile_to_the_programs_the_device_leg_uses():
+    """bench.py scores resident batches from (tokens, program) lists and runs the
+    e2e leg from query strings: for every C2 / C3 template the host parser must
+    turn the string into exactly the token order and postfix program the
+    generator wrote (ref grammar.y precedence NOT > AND > OR, query.c:89-103
+    right-to-left token order)."""
+    import numpy as np
+    import bench
+    from nxsearch_b200 import tools
+
+    corpus = tools.Corpus.generate(2_000, 3_000)
+    qt = corpus.query_terms(6 * 64)
+    for shape in ("or", "bool"):
+        for item in bench.make_queries(qt, 64, shape):
+            toks, prog, _ = item
+            compiled = tools.query_compile(bench.query_string(corpus, item))
+            assert compiled is not None
+            leaves, cprog = compiled
+            assert [corpus.term(t) for t in toks] == leaves, bench.query_string(corpus, item)
+            assert list(prog) == list(cprog), bench.query_string(corpus, item)
