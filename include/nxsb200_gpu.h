@@ -68,6 +68,27 @@ nxsb_engine_t *	nxsb_engine_create(int device);
  */
 nxsb_engine_t *	nxsb_engine_create_replicated(const int *devices, int n);
 int		nxsb_engine_replica_count(const nxsb_engine_t *);
+/*
+ * One engine object over n devices, a contiguous range of the
+ * documents on each -- for an index that outgrows one GPU, behind the same
+ * calls (the host library's NXS_GPU_DEVICES with NXS_GPU_LAYOUT=shards):
+ *   load_shard    cuts the documents (ascending ids) into n ranges of about
+ *                 equal posting counts; every device builds its range with the
+ *                 whole-index df / N / token count, as ranking needs
+ *                 (ref ranking.c:77-78,149-150,163);
+ *   segment_add   a delta segment goes whole to one device, round robin;
+ *   set_dead      ids of the base image go to the device whose range holds
+ *                 them, ids of a delta segment to the device that has it;
+ *   search[_begin/_end]  every device scores the WHOLE batch on its documents
+ *                 into device memory, the per-device top-k lists travel to
+ *                 the first device (cudaMemcpyPeerAsync: NVLink where peers
+ *                 can map each other) and one kernel merges them in
+ *                 (score desc, id desc) order ahead of a single D2H copy.
+ * Results are bit-identical to one engine over the whole index.  The same
+ * calls are refused as on a replicated engine.
+ */
+nxsb_engine_t *	nxsb_engine_create_sharded(const int *devices, int n);
+int		nxsb_engine_is_sharded(const nxsb_engine_t *);
 void		nxsb_engine_destroy(nxsb_engine_t *);
 const char *	nxsb_engine_errmsg(const nxsb_engine_t *);
 

@@ -314,6 +314,33 @@ struct nxsb_engine {
 	};
 	RepSplit	rep_pipe[PIPE_DEPTH];
 
+	/*
+	 * A sharded engine (nxsb_engine_create_sharded): the same dispatcher,
+	 * but every child holds a contiguous range of the documents (split in
+	 * load_shard, scored with whole-index statistics), every child scores
+	 * the whole batch, and the children's top-k lists meet on the first
+	 * device -- peer copies over NVLink, one merge kernel -- before a
+	 * single copy to the host.
+	 */
+	bool		sharded = false;
+	cudaStream_t	shard_stream = nullptr;		// merge + D2H, first device
+	std::vector<uint64_t> shard_last_id;		// [children] largest base document id
+	struct SegAt { uint32_t child, local; };
+	std::vector<SegAt> seg_at;			// delta segment g lives at seg_at[g - 1]
+	struct ShardRun {
+		bool		busy = false;
+		uint32_t	limit = 0, n_q = 0;
+		std::vector<int> h;			// child handles
+		std::vector<DevBuf> part;		// [children] [query][limit] records, child's device
+		std::vector<cudaEvent_t> part_done;	// ... and "copied to the first device"
+		DevBuf		gather;			// [children][query][limit] records, first device
+		DevBuf		out;			// [query][limit] records | [query] counts
+		PinnedBuf	h_out;
+		size_t		out_bytes = 0, counts_at = 0;
+		cudaEvent_t	done = nullptr;
+	};
+	ShardRun	shard_pipe[PIPE_DEPTH];
+
 	/* vocabulary (fuzzy) */
 	FuzzyImage	fz;
 	FuzzyScratch	fz_scratch;
@@ -453,7 +480,8 @@ is_multi(const nxsb_engine_t *e)
 static int
 multi_fail(nxsb_engine_t *e, const nxsb_engine_t *child, int r)
 {
-	return fail(e, "replica %d (device %d): %s", r, child->device, child->err);
+	return fail(e, "%s %d (device %d): %s", e->sharded ? "shard" : "replica", r, child->device,
+	    child->err);
 }
 
 #define NOT_ON_REPLICATED(e, what) do {						\
@@ -564,6 +592,318 @@ multi_search_end(nxsb_engine_t *e, int s, uint32_t *counts, uint64_t *ids, float
 	return rc;
 }
 
+/* ---- sharded engines ----------------------------------------------------- */
+
+extern "C" int nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd);
+extern "C" int nxsb_engine_get_df(nxsb_engine_t *e, uint32_t *df, uint32_t n_terms);
+extern "C" int nxsb_engine_set_global_stats(nxsb_engine_t *e, const uint32_t *df,
+    uint32_t n_terms, uint64_t token_count, uint32_t doc_count);
+extern "C" int nxsb_engine_segment_add(nxsb_engine_t *e, const nxsb_shard_desc_t *sd);
+extern "C" int nxsb_engine_set_dead(nxsb_engine_t *e, uint32_t segment, const uint64_t *ids,
+    uint32_t n);
+extern "C" int nxsb_engine_search_begin(nxsb_engine_t *e, const nxsb_batch_t *b);
+extern "C" int nxsb_engine_search_begin_dev(nxsb_engine_t *e, const nxsb_batch_t *b, void *d_recs);
+extern "C" int nxsb_engine_sync(nxsb_engine_t *e);
+extern "C" int nxsb_engine_search_end(nxsb_engine_t *e, int s, uint32_t *counts, uint64_t *ids,
+    float *scores);
+
+/*
+ * The documents of sd, ascending by id, are cut into one contiguous range per
+ * child with about the same number of postings each; every child builds its
+ * range as a shard of its own (the whole-index df / N / token count of sd, or
+ * -- when sd carries no df -- the sum of the children's, as the all-reduce of
+ * nxsearch_b200/dist.py does between processes).
+ */
+static int
+shard_load(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
+{
+	const uint32_t R = (uint32_t)e->replicas.size(), N = sd->n_docs;
+	const bool raw = sd->raw != nullptr;
+	std::vector<uint32_t> cut(R + 1, N);
+	std::vector<std::vector<uint64_t>> rebased(R);
+	uint64_t P = 0, acc = 0;
+
+	if (!raw && N && !sd->doc_off)
+		return fail(e, "load_shard: neither raw blocks nor doc_off/pairs given");
+	for (uint32_t d = 0; d < N; d++)
+		P += raw ? sd->raw_n[d] : sd->doc_off[d + 1] - sd->doc_off[d];
+	cut[0] = 0;
+	for (uint32_t d = 0, r = 1; d < N && r < R; d++) {
+		/* Child r starts at the first document at or past its share of the postings. */
+		while (r < R && acc >= (P * r + R - 1) / R)
+			cut[r++] = d;
+		acc += raw ? sd->raw_n[d] : sd->doc_off[d + 1] - sd->doc_off[d];
+	}
+	e->shard_last_id.assign(R, 0);
+	for (uint32_t r = 0; r < R; r++)
+		e->shard_last_id[r] = cut[r + 1] > cut[r] ? sd->doc_ids[cut[r + 1] - 1]
+		    : (r ? e->shard_last_id[r - 1] : 0);
+	e->seg_at.clear();
+
+	if (multi_each(e, true, [&](nxsb_engine_t *c, int r) {
+		const uint32_t a = cut[r], n = cut[r + 1] - cut[r];
+		nxsb_shard_desc_t sub = *sd;
+
+		sub.n_docs = n;
+		sub.doc_ids = sd->doc_ids + a;
+		sub.doc_len = sd->doc_len + a;
+		if (raw) {
+			sub.raw_off = sd->raw_off + a;
+			sub.raw_n = sd->raw_n + a;
+		} else if (sd->doc_off) {
+			std::vector<uint64_t> &off = rebased[r];
+
+			off.resize((size_t)n + 1);
+			for (uint32_t i = 0; i <= n; i++)
+				off[i] = sd->doc_off[a + i] - sd->doc_off[a];
+			sub.doc_off = off.data();
+			sub.pairs = sd->pairs + 2 * sd->doc_off[a];
+		}
+		return nxsb_engine_load_shard(c, &sub);
+	}) != 0)
+		return -1;
+	if (!sd->df) {
+		std::vector<uint32_t> df(sd->n_terms);
+
+		if (nxsb_engine_get_df(e, df.data(), sd->n_terms) != 0 ||
+		    nxsb_engine_set_global_stats(e, df.data(), sd->n_terms, sd->token_count,
+		    sd->doc_count) != 0)
+			return -1;
+	}
+	return 0;
+}
+
+/* Removed ids of the base image go to the child whose range holds them. */
+static int
+shard_set_dead(nxsb_engine_t *e, uint32_t segment, const uint64_t *ids, uint32_t n)
+{
+	const uint32_t R = (uint32_t)e->replicas.size();
+
+	if (segment > e->seg_at.size())
+		return fail(e, "set_dead: no such segment %u", segment);
+	if (segment) {
+		const nxsb_engine::SegAt at = e->seg_at[segment - 1];
+		nxsb_engine_t *c = e->replicas[at.child];
+
+		return nxsb_engine_set_dead(c, at.local, ids, n) == 0 ? 0 : multi_fail(e, c, (int)at.child);
+	}
+	for (uint32_t i = 1; i < n; i++)
+		if (ids[i - 1] >= ids[i])
+			return fail(e, "set_dead: ids must be strictly ascending");
+	uint32_t a = 0;
+	for (uint32_t r = 0; r < R; r++) {
+		const uint32_t z = r + 1 == R ? n
+		    : (uint32_t)(std::upper_bound(ids + a, ids + n, e->shard_last_id[r]) - ids);
+
+		if (nxsb_engine_set_dead(e->replicas[r], 0, ids + a, z - a) != 0)
+			return multi_fail(e, e->replicas[r], (int)r);
+		a = z;
+	}
+	return 0;
+}
+
+/* A delta segment goes whole to one child, round robin. */
+static int
+shard_segment_add(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
+{
+	if (e->seg_at.size() >= NXSB_MAX_SEGMENTS)
+		return fail(e, "segment_add: %d delta segments already", NXSB_MAX_SEGMENTS);
+	const uint32_t r = (uint32_t)(e->seg_at.size() % e->replicas.size());
+	nxsb_engine_t *c = e->replicas[r];
+	const int local = nxsb_engine_segment_add(c, sd);
+
+	if (local < 0)
+		return multi_fail(e, c, (int)r);
+	e->seg_at.push_back({ r, (uint32_t)local });
+	return (int)e->seg_at.size();
+}
+
+static int
+shard_search_begin(nxsb_engine_t *e, const nxsb_batch_t *b)
+{
+	const uint32_t R = (uint32_t)e->replicas.size();
+	const int dev0 = e->replicas[0]->device;
+	int s = -1;
+
+	for (int i = 0; i < PIPE_DEPTH; i++)
+		if (!e->shard_pipe[i].busy) {
+			s = i;
+			break;
+		}
+	if (s < 0)
+		return fail(e, "too many searches in flight (%d)", PIPE_DEPTH);
+	if (b->limit == 0)
+		return fail(e, "limit must be at least 1");
+	nxsb_engine::ShardRun &S = e->shard_pipe[s];
+	const size_t nq = std::max(b->n_queries, 1u);
+	const size_t part_bytes = nq * b->limit * sizeof(Rec);
+
+	CK(e, cudaSetDevice(dev0));
+	if (!S.done)
+		CK(e, cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+	S.limit = b->limit;
+	S.n_q = b->n_queries;
+	S.counts_at = align16(part_bytes);
+	S.out_bytes = S.counts_at + nq * 4;
+	if (S.gather.ensure(part_bytes * R) || S.out.ensure(S.out_bytes) || S.h_out.ensure(S.out_bytes))
+		return fail(e, "allocation failed for a %u-shard search (%u queries, limit %u): %s", R,
+		    b->n_queries, b->limit, cudaGetErrorString(cudaGetLastError()));
+	S.h.assign(R, -1);
+	S.part.resize(R);
+	S.part_done.resize(R, nullptr);
+
+	/* Every child scores the whole batch on its own documents, side by side. */
+	std::vector<int> rc(R, 0);
+	auto begin_part = [&](uint32_t r) {
+		nxsb_engine_t *c = e->replicas[r];
+
+		rc[r] = -1;
+		if (cudaSetDevice(c->device) != cudaSuccess || S.part[r].ensure(part_bytes) != cudaSuccess ||
+		    (!S.part_done[r] && cudaEventCreateWithFlags(&S.part_done[r],
+		    cudaEventDisableTiming) != cudaSuccess)) {
+			snprintf(c->err, sizeof(c->err), "record buffer: %s",
+			    cudaGetErrorString(cudaGetLastError()));
+			return;
+		}
+		if ((S.h[r] = nxsb_engine_search_begin_dev(c, b, S.part[r].p)) < 0)
+			return;
+		/* Behind the child's kernels, on its stream: its list to the first device. */
+		if (cudaMemcpyPeerAsync((char *)S.gather.p + part_bytes * r, dev0, S.part[r].p,
+		    c->device, part_bytes, c->stream) != cudaSuccess ||
+		    cudaEventRecord(S.part_done[r], c->stream) != cudaSuccess) {
+			snprintf(c->err, sizeof(c->err), "peer copy: %s",
+			    cudaGetErrorString(cudaGetLastError()));
+			return;
+		}
+		rc[r] = 0;
+	};
+	std::vector<std::thread> th;
+
+	for (uint32_t r = 1; r < R; r++)
+		th.emplace_back(begin_part, r);
+	begin_part(0);
+	for (auto &t : th)
+		t.join();
+	int bad = -1;
+	for (uint32_t r = 0; r < R; r++)
+		if (rc[r] != 0 && bad < 0)
+			bad = (int)r;
+	if (bad >= 0) {
+		for (uint32_t r = 0; r < R; r++)
+			if (S.h[r] >= 0)
+				nxsb_engine_search_end(e->replicas[r], S.h[r], nullptr, nullptr, nullptr);
+		return multi_fail(e, e->replicas[bad], bad);
+	}
+
+	CK(e, cudaSetDevice(dev0));
+	for (uint32_t r = 0; r < R; r++)
+		CK(e, cudaStreamWaitEvent(e->shard_stream, S.part_done[r], 0));
+	CK(e, cudaMemsetAsync(S.out.p, 0, S.out_bytes, e->shard_stream));
+	const unsigned long long total = (unsigned long long)b->n_queries * R * b->limit;
+	if (total) {
+		/* (score desc, id desc) over all lists; the ids of the shards never meet. */
+		merge_segments_kernel<<<(unsigned)((total + 255) / 256), 256, 0, e->shard_stream>>>(
+		    (const Rec *)S.gather.p, R, b->n_queries, b->limit, b->limit, (Rec *)S.out.p,
+		    (uint32_t *)((char *)S.out.p + S.counts_at));
+		e->launches++;
+		CK(e, cudaGetLastError());
+	}
+	CK(e, cudaMemcpyAsync(S.h_out.p, S.out.p, S.out_bytes, cudaMemcpyDeviceToHost, e->shard_stream));
+	CK(e, cudaEventRecord(S.done, e->shard_stream));
+	S.busy = true;
+	return s;
+}
+
+static int
+shard_search_end(nxsb_engine_t *e, int s, uint32_t *counts, uint64_t *ids, float *scores)
+{
+	if (s < 0 || s >= PIPE_DEPTH || !e->shard_pipe[s].busy)
+		return fail(e, "bad search handle %d", s);
+	nxsb_engine::ShardRun &S = e->shard_pipe[s];
+	int rc = 0;
+
+	S.busy = false;
+	CK(e, cudaSetDevice(e->replicas[0]->device));
+	CK(e, cudaEventSynchronize(S.done));
+	for (size_t r = 0; r < e->replicas.size(); r++)
+		if (nxsb_engine_search_end(e->replicas[r], S.h[r], nullptr, nullptr, nullptr) != 0 && rc == 0)
+			rc = multi_fail(e, e->replicas[r], (int)r);
+	if (rc == 0 && counts) {
+		const Rec *recs = (const Rec *)S.h_out.p;
+		const size_t nrec = (size_t)S.n_q * S.limit;
+
+		memcpy(counts, (const char *)S.h_out.p + S.counts_at, (size_t)S.n_q * 4);
+		for (size_t i = 0; i < nrec; i++) {
+			ids[i] = recs[i].doc_id;
+			scores[i] = recs[i].score;
+		}
+	}
+	return rc;
+}
+
+static void
+shard_release(nxsb_engine_t *e)
+{
+	for (auto &S : e->shard_pipe) {
+		for (size_t r = 0; r < S.part.size(); r++) {
+			cudaSetDevice(e->replicas[r]->device);
+			S.part[r].release();
+			if (S.part_done[r])
+				cudaEventDestroy(S.part_done[r]);
+		}
+		S.part.clear();
+		S.part_done.clear();
+		cudaSetDevice(e->replicas[0]->device);
+		S.gather.release();
+		S.out.release();
+		S.h_out.release();
+		if (S.done)
+			cudaEventDestroy(S.done);
+		S.done = nullptr;
+	}
+	if (e->shard_stream) {
+		cudaSetDevice(e->replicas[0]->device);
+		cudaStreamDestroy(e->shard_stream);
+		e->shard_stream = nullptr;
+	}
+}
+
+extern "C" nxsb_engine_t *nxsb_engine_create_replicated(const int *devices, int n);
+
+extern "C" nxsb_engine_t *
+nxsb_engine_create_sharded(const int *devices, int n)
+{
+	/* A device may be listed twice (two ranges on it): what a one-GPU box can test. */
+	nxsb_engine_t *e = nxsb_engine_create_replicated(devices, n);
+
+	if (!e)
+		return nullptr;
+	e->sharded = true;
+	/* The lists travel device to device where the fabric allows it (else through the host). */
+	for (int i = 1; i < n; i++) {
+		int can = 0;
+
+		if (cudaDeviceCanAccessPeer(&can, devices[i], devices[0]) == cudaSuccess && can &&
+		    cudaSetDevice(devices[i]) == cudaSuccess)
+			cudaDeviceEnablePeerAccess(devices[0], 0);
+		cudaGetLastError();
+	}
+	if (cudaSetDevice(devices[0]) != cudaSuccess ||
+	    cudaStreamCreateWithFlags(&e->shard_stream, cudaStreamNonBlocking) != cudaSuccess) {
+		snprintf(g_last_error, sizeof(g_last_error), "sharded engine: %s",
+		    cudaGetErrorString(cudaGetLastError()));
+		nxsb_engine_destroy(e);
+		return nullptr;
+	}
+	return e;
+}
+
+extern "C" int
+nxsb_engine_is_sharded(const nxsb_engine_t *e)
+{
+	return e->sharded ? 1 : 0;
+}
+
 extern "C" nxsb_engine_t *
 nxsb_engine_create_replicated(const int *devices, int n)
 {
@@ -637,7 +977,7 @@ nxsb_engine_launch_count(const nxsb_engine_t *e)
 
 		for (auto *c : e->replicas)
 			n += nxsb_engine_launch_count(c);
-		return n;
+		return n + e->launches;	/* + the cross-shard merges */
 	}
 	uint64_t n = e->launches;
 
@@ -1006,6 +1346,9 @@ nxsb_engine_destroy(nxsb_engine_t *e)
 {
 	if (e && is_multi(e)) {
 		for (auto *c : e->replicas)
+			nxsb_engine_sync(c);
+		shard_release(e);
+		for (auto *c : e->replicas)
 			nxsb_engine_destroy(c);
 		delete e;
 		return;
@@ -1121,8 +1464,15 @@ nxsb_engine_lanes_join(nxsb_engine_t *e)
 extern "C" int
 nxsb_engine_sync(nxsb_engine_t *e)
 {
-	if (is_multi(e))
-		return multi_each(e, false, [](nxsb_engine_t *c, int) { return nxsb_engine_sync(c); });
+	if (is_multi(e)) {
+		if (multi_each(e, false, [](nxsb_engine_t *c, int) { return nxsb_engine_sync(c); }) != 0)
+			return -1;
+		if (e->shard_stream) {
+			CK(e, cudaSetDevice(e->replicas[0]->device));
+			CK(e, cudaStreamSynchronize(e->shard_stream));
+		}
+		return 0;
+	}
 	sync_lanes(e);
 	CK(e, cudaGetLastError());
 	return 0;
@@ -1253,6 +1603,8 @@ upload_stats(nxsb_engine_t *e)
 extern "C" int
 nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 {
+	if (is_multi(e) && e->sharded)
+		return shard_load(e, sd);
 	if (is_multi(e))	/* the same image on every device, built side by side */
 		return multi_each(e, true, [&](nxsb_engine_t *c, int) { return nxsb_engine_load_shard(c, sd); });
 	/* The image is about to change: both lanes drain first. */
@@ -1629,6 +1981,19 @@ nxsb_engine_load_shard(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 extern "C" int
 nxsb_engine_get_df(nxsb_engine_t *e, uint32_t *df, uint32_t n_terms)
 {
+	if (is_multi(e) && e->sharded) {
+		/* Whole-index df = the sum over the shards. */
+		std::vector<uint32_t> one(n_terms);
+
+		memset(df, 0, (size_t)n_terms * 4);
+		for (size_t r = 0; r < e->replicas.size(); r++) {
+			if (nxsb_engine_get_df(e->replicas[r], one.data(), n_terms) != 0)
+				return multi_fail(e, e->replicas[r], (int)r);
+			for (uint32_t t = 0; t < n_terms; t++)
+				df[t] += one[t];
+		}
+		return 0;
+	}
 	if (is_multi(e))
 		return nxsb_engine_get_df(e->replicas[0], df, n_terms) == 0 ? 0 : multi_fail(e, e->replicas[0], 0);
 	if (!e->loaded || n_terms != e->n_terms)
@@ -1674,6 +2039,8 @@ nxsb_engine_set_global_stats(nxsb_engine_t *e, const uint32_t *df,
 extern "C" int
 nxsb_engine_segment_add(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 {
+	if (is_multi(e) && e->sharded)
+		return shard_segment_add(e, sd);
 	if (is_multi(e)) {
 		if (multi_each(e, true, [&](nxsb_engine_t *c, int) {
 			return nxsb_engine_segment_add(c, sd) < 0 ? -1 : 0;
@@ -1714,6 +2081,8 @@ nxsb_engine_segment_add(nxsb_engine_t *e, const nxsb_shard_desc_t *sd)
 extern "C" int
 nxsb_engine_segment_count(const nxsb_engine_t *e)
 {
+	if (is_multi(e) && e->sharded)
+		return (int)e->seg_at.size();
 	if (is_multi(e))
 		return nxsb_engine_segment_count(e->replicas[0]);
 	return (int)e->segs.size();
@@ -1722,8 +2091,10 @@ nxsb_engine_segment_count(const nxsb_engine_t *e)
 extern "C" int
 nxsb_engine_segments_drop(nxsb_engine_t *e)
 {
-	if (is_multi(e))
+	if (is_multi(e)) {
+		e->seg_at.clear();
 		return multi_each(e, false, [](nxsb_engine_t *c, int) { return nxsb_engine_segments_drop(c); });
+	}
 	/* The image is about to change: both lanes drain first. */
 	sync_lanes(e);
 	if (use_lane(e, 0) == -1)
@@ -1738,6 +2109,8 @@ extern "C" int
 nxsb_engine_set_dead(nxsb_engine_t *e, uint32_t segment, const uint64_t *ids,
     uint32_t n)
 {
+	if (is_multi(e) && e->sharded)
+		return shard_set_dead(e, segment, ids, n);
 	if (is_multi(e))
 		return multi_each(e, false, [&](nxsb_engine_t *c, int) { return nxsb_engine_set_dead(c, segment, ids, n); });
 	/* The image is about to change: both lanes drain first. */
@@ -2888,9 +3261,9 @@ nxsb_engine_search(nxsb_engine_t *e, const nxsb_batch_t *b, uint32_t *counts,
     uint64_t *ids, float *scores)
 {
 	if (is_multi(e)) {
-		const int h = multi_search_begin(e, b);
+		const int h = nxsb_engine_search_begin(e, b);
 
-		return h < 0 ? -1 : multi_search_end(e, h, counts, ids, scores);
+		return h < 0 ? -1 : nxsb_engine_search_end(e, h, counts, ids, scores);
 	}
 	Batch &B = e->oneshot;
 
@@ -2980,7 +3353,7 @@ extern "C" int
 nxsb_engine_search_begin(nxsb_engine_t *e, const nxsb_batch_t *b)
 {
 	if (is_multi(e))
-		return multi_search_begin(e, b);
+		return e->sharded ? shard_search_begin(e, b) : multi_search_begin(e, b);
 	return search_begin(e, b, nullptr);
 }
 
@@ -3038,7 +3411,8 @@ nxsb_engine_search_end(nxsb_engine_t *e, int s, uint32_t *counts, uint64_t *ids,
     float *scores)
 {
 	if (is_multi(e))
-		return multi_search_end(e, s, counts, ids, scores);
+		return e->sharded ? shard_search_end(e, s, counts, ids, scores)
+		    : multi_search_end(e, s, counts, ids, scores);
 	if (s < 0 || s >= PIPE_DEPTH || !e->pipe_busy[s])
 		return fail(e, "bad search handle %d", s);
 	e->pipe_busy[s] = false;

@@ -1357,9 +1357,10 @@ int
 idx_gpu_prepare(nxs_index_t *idx, bool need_vocab)
 {
 	if (!idx->engine) {
-		idx->engine = idx->nxs->n_devices > 1
-		    ? nxsb_engine_create_replicated(idx->nxs->devices, idx->nxs->n_devices)
-		    : nxsb_engine_create(idx->nxs->device);
+		idx->engine = idx->nxs->n_devices <= 1 ? nxsb_engine_create(idx->nxs->device)
+		    : idx->nxs->shards
+		    ? nxsb_engine_create_sharded(idx->nxs->devices, idx->nxs->n_devices)
+		    : nxsb_engine_create_replicated(idx->nxs->devices, idx->nxs->n_devices);
 		if (!idx->engine) {
 			nxs_set_error(idx->nxs, NXS_ERR_SYSTEM,
 			    "GPU engine unavailable: %s", nxsb_last_error());

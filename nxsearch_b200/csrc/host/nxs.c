@@ -151,10 +151,19 @@ nxs_open(const char *basedir)
 	if (mkdir(path, 0755) == -1 && errno != EEXIST)
 		goto err;
 	free(path);
+	path = NULL;
 	if ((s = getenv("NXS_GPU_DEVICE")) != NULL)
 		nxs->device = atoi(s);
 	if ((s = getenv("NXS_GPU_DEVICES")) != NULL)
 		parse_device_list(nxs, s);
+	if ((s = getenv("NXS_GPU_LAYOUT")) != NULL) {
+		if (strcmp(s, "shards") == 0) {
+			nxs->shards = true;
+		} else if (strcmp(s, "replicas") != 0) {
+			errno = EINVAL;	/* a typo must not fall back to the other layout */
+			goto err;
+		}
+	}
 	return nxs;
 err:
 	free(path);

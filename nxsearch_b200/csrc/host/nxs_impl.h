@@ -34,6 +34,12 @@ struct nxs {
 	 */
 	int		devices[NXS_MAX_GPU_DEVICES];
 	int		n_devices;
+	/*
+	 * $NXS_GPU_LAYOUT=shards: the devices hold one range of the documents
+	 * each instead (nxsb_engine_create_sharded) -- an index larger than one
+	 * GPU; every device scores every query and the top-N lists are merged.
+	 */
+	bool		shards;
 };
 
 struct nxs_params {

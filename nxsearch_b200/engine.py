@@ -43,6 +43,10 @@ def _bind():
         "nxsb_gpu_device_count": (i, []),
         "nxsb_last_error": (C.c_char_p, []),
         "nxsb_engine_create": (vp, [i]),
+        "nxsb_engine_create_replicated": (vp, [C.POINTER(C.c_int), i]),
+        "nxsb_engine_create_sharded": (vp, [C.POINTER(C.c_int), i]),
+        "nxsb_engine_replica_count": (i, [vp]),
+        "nxsb_engine_is_sharded": (i, [vp]),
         "nxsb_engine_destroy": (None, [vp]),
         "nxsb_engine_errmsg": (C.c_char_p, [vp]),
         "nxsb_engine_set_stream": (i, [vp, vp]),
@@ -130,9 +134,20 @@ class Batch:
 class Engine:
     """One CUDA device / one document shard.  Raises if no GPU is usable."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, *, devices=None, layout: str = "replicas"):
+        """devices=[...]: one engine over several devices -- layout "replicas" (the whole
+        image on each, a batch's queries split) or "shards" (a range of the documents on
+        each, every query scored everywhere, lists merged on the first device)."""
         self._lib = _bind()
-        self._h = self._lib.nxsb_engine_create(device)
+        if devices is None:
+            self._h = self._lib.nxsb_engine_create(device)
+        else:
+            if layout not in ("replicas", "shards"):
+                raise ValueError(f"unknown layout {layout!r}")
+            arr = (C.c_int * len(devices))(*devices)
+            make = self._lib.nxsb_engine_create_sharded if layout == "shards" \
+                else self._lib.nxsb_engine_create_replicated
+            self._h = make(arr, len(devices))
         if not self._h:
             raise RuntimeError("nxsb_engine_create failed: " + self._lib.nxsb_last_error().decode())
 

@@ -420,11 +420,16 @@ def test_a_c_program_links_the_library_and_gets_the_same_answers(nxs):
     idx.close()
 
 
-def test_replicated_engine_behind_the_c_api(nxs, monkeypatch):
-    """NXS_GPU_DEVICES: one nxs_t, a replica of the image per listed device, a
-    batch's queries split between them.  Three replicas (all on device 0 here,
-    every visible device on a multi-GPU box) must answer exactly as one engine
-    does: batches, single searches, fuzzy terms, and after add / remove."""
+@pytest.mark.parametrize("layout", ["replicas", "shards"])
+def test_replicated_engine_behind_the_c_api(nxs, monkeypatch, layout):
+    """NXS_GPU_DEVICES: one nxs_t over every listed device -- a replica of the
+    image on each and a batch's queries split between them, or
+    (NXS_GPU_LAYOUT=shards) a range of the documents on each, every query
+    scored everywhere and the lists merged on the first device.  Three of them
+    (all on device 0 here, every visible device on a multi-GPU box) must answer
+    exactly as one engine does: batches, single searches, fuzzy terms, and
+    after adds and removes with searches in between (delta segments, removal
+    notes)."""
     from nxsearch_b200 import engine
 
     corpus = tools.Corpus.generate(30_000, 8_000)
@@ -449,6 +454,16 @@ def test_replicated_engine_behind_the_c_api(nxs, monkeypatch):
         idx.add(10_000_000 + len(out), f"{corpus.term(int(qt[0]))} {corpus.term(int(qt[1]))} brandnewterm")
         idx.remove(top)
         out["after"] = idx.search_batch(queries[:64] + ["brandnewterm"], limit=10, algo="BM25")
+        # more edits, a search after each: several delta segments and removal notes
+        for j in range(1, 6):
+            idx.add(20_000_000 + j, f"{corpus.term(int(qt[j]))} {corpus.term(int(qt[j + 1]))} brandnewterm")
+            res = idx.search_batch(queries[4 * j: 4 * j + 24] + ["brandnewterm"], limit=10, algo="BM25")
+            out["edit", j] = res
+            if res[0]:
+                idx.remove(res[0][0][0])
+            if j == 3:
+                idx.remove(20_000_001)
+        out["after edits"] = idx.search_batch(queries + ["brandnewterm"], limit=100, algo="TF-IDF")
         idx.close()
         return out
 
@@ -458,6 +473,7 @@ def test_replicated_engine_behind_the_c_api(nxs, monkeypatch):
     nxs.create_index("r").close()
     corpus.write(f"{nxs.base}/data/r/nxsterms", f"{nxs.base}/data/r/nxsdtmap")
     monkeypatch.setenv("NXS_GPU_DEVICES", devs)
+    monkeypatch.setenv("NXS_GPU_LAYOUT", layout)
     multi_nxs = capi.Nxs(nxs.base)
     try:
         many = run(multi_nxs)

@@ -90,3 +90,104 @@ def test_submit_collect_pipeline_equals_search(c1_corpus):
         assert all(np.array_equal(a, b) for a, b in zip(r, w))
     torch.cuda.set_stream(torch.cuda.default_stream())
     e.close()
+
+
+def _devices(n):
+    """n device ordinals: every visible device first, wrapping on a small box."""
+    from nxsearch_b200 import engine
+
+    ndev = engine.device_count()
+    return [d % ndev for d in range(max(n, ndev))]
+
+
+@pytest.mark.parametrize("n_shards", [2, 5])
+def test_one_sharded_engine_equals_one_engine(c1_corpus, n_shards):
+    """nxsb_engine_create_sharded: one engine object, a range of the documents per
+    device, every device scores the whole batch, lists merged on the first
+    device.  Counts, ids and scores equal the single-engine answer bit for bit,
+    from pairs and from dtmap bytes, synchronously and with four in flight."""
+    from nxsearch_b200 import engine
+    from test_gpu_engine import c1_queries
+    from test_gpu_segments import assert_same, boolean_queries
+
+    c = c1_corpus
+    devs = _devices(n_shards)
+    whole = engine.Engine(0)
+    whole.load_corpus(c)
+    sh = engine.Engine(devices=devs, layout="shards")
+    # no df handed over: the dispatcher sums the shards' own (the all-reduce of dist.py)
+    sh.load_corpus(c)
+    assert np.array_equal(sh.get_df(c.n_terms), whole.get_df(c.n_terms))
+    qs = c1_queries(c, 300) + boolean_queries(c, 90)
+    for algo in (BM25, TFIDF):
+        for k in (1, 10, 100, 200):
+            batch = engine.Batch.from_lists(algo, k, qs)
+            want = whole.search(batch)
+            assert_same(sh.search(batch), want)
+            hs = [sh.search_begin(batch) for _ in range(4)]
+            for h in reversed(hs):
+                assert_same(sh.search_end(h, len(qs), k), want)
+    # a batch of one query, and a query nobody matches
+    one = engine.Batch.from_lists(BM25, 10, qs[:1])
+    assert_same(sh.search(one), whole.search(one))
+    # with whole-index df given, as the host library does
+    sh.load_corpus(c, df=c.term_df)
+    batch = engine.Batch.from_lists(BM25, 10, qs)
+    assert_same(sh.search(batch), whole.search(batch))
+    with pytest.raises(RuntimeError, match="replicated|sharded"):
+        sh.upload(batch)
+    sh.close()
+    whole.close()
+
+
+def test_sharded_engine_segments_and_removals(c1_corpus):
+    """Delta segments go whole to one device each (round robin) and removal
+    notes to whoever holds the document: the sharded engine still answers like
+    one image rebuilt from the live documents."""
+    from nxsearch_b200 import engine
+    from test_gpu_engine import c1_queries
+    from test_gpu_segments import assert_same, boolean_queries, stats, subset
+
+    c = c1_corpus
+    N = c.n_docs
+    rng = np.random.default_rng(11)
+    # ids of the base and of four deltas interleave: ties are ordered by id, not by device
+    part = rng.integers(0, 20, N)
+    seg_docs = [np.flatnonzero(part < 14)] + [np.flatnonzero(part == 14 + i) for i in range(4)]
+    seg_docs.append(np.flatnonzero(part >= 18))
+    dead = [rng.choice(s, size=min(k, len(s)), replace=False) for s, k in zip(seg_docs, (50, 7, 0, 3, 1, 9))]
+    dead_all = np.concatenate(dead)
+    live = np.setdiff1d(np.arange(N), dead_all)
+    df, tokens, ndocs = stats(c, live)
+    truth = engine.Engine(0)
+    truth.load_docs(*subset(c, live), c.n_terms, tokens, ndocs, df)
+
+    sh = engine.Engine(devices=_devices(3), layout="shards")
+    sh.load_docs(*subset(c, seg_docs[0]), c.n_terms, c.token_count, c.doc_count, c.term_df)
+    for g, s in enumerate(seg_docs[1:], 1):
+        sh.load_docs(*subset(c, s), c.n_terms, c.token_count, c.doc_count, c.term_df, segment=True)
+        assert sh.segment_count() == g
+    for g, d in enumerate(dead):
+        sh.set_dead(g, c.doc_ids[d])
+    sh.set_global_stats(df, tokens, ndocs)
+    qs = c1_queries(c, 300) + boolean_queries(c, 90)
+    dead_ids = set(int(x) for x in c.doc_ids[dead_all])
+    for algo in (BM25, TFIDF):
+        for k in (1, 10, 100):
+            batch = engine.Batch.from_lists(algo, k, qs)
+            want = truth.search(batch)
+            got = sh.search(batch)
+            assert_same(got, want)
+            assert not dead_ids.intersection(int(x) for x in got[1].ravel())
+    # notes are replaced, not accumulated: clearing them brings the documents back
+    for g in range(len(dead)):
+        sh.set_dead(g, [])
+    df_all, tok_all, n_all = stats(c, np.arange(N))
+    sh.set_global_stats(df_all, tok_all, n_all)
+    truth.load_corpus(c)
+    batch = engine.Batch.from_lists(BM25, 10, qs)
+    assert_same(sh.search(batch), truth.search(batch))
+    sh.segments_drop()
+    assert sh.segment_count() == 0
+    sh.close()
+    truth.close()

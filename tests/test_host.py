@@ -266,6 +266,22 @@ def test_gpu_device_list_is_parsed_or_ignored(spec, monkeypatch):
         shutil.rmtree(base, ignore_errors=True)
 
 
+def test_gpu_layout_is_replicas_or_shards_nothing_else(monkeypatch):
+    """NXS_GPU_LAYOUT picks what several devices hold (replicas of the image, or
+    a range of the documents each).  A misspelt value fails nxs_open instead of
+    quietly choosing the other layout."""
+    base = tempfile.mkdtemp(prefix="nxsb_t_")
+    try:
+        for ok in ("replicas", "shards"):
+            monkeypatch.setenv("NXS_GPU_LAYOUT", ok)
+            capi.Nxs(base).close()
+        monkeypatch.setenv("NXS_GPU_LAYOUT", "shard")
+        with pytest.raises(OSError):
+            capi.Nxs(base)
+    finally:
+        shutil.rmtree(base, ignore_errors=True)
+
+
 def test_index_files_are_interchangeable_with_the_reference(nxs, c1_corpus):
     """Files written through nxs_index_add here open in the compiled reference
     and vice versa, byte-identical for the same sequence of adds."""
