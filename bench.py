@@ -578,6 +578,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         line["latency"] = AUX.pop("latency")
     if "e2e_single_process" in AUX:
         line["e2e_single_process"] = AUX.pop("e2e_single_process")
+    if "e2e_single_process_shards" in AUX:
+        line["e2e_single_process_shards"] = AUX.pop("e2e_single_process_shards")
     if "e2e_fuzzymatch_default" in AUX:
         line["e2e_fuzzymatch_default"] = AUX.pop("e2e_fuzzymatch_default")
     if AUX:
@@ -898,38 +900,55 @@ def e2e_capi(args, corpus, batches, capi, rank=0, world=1, local_rank=0, dist=No
             # ranks are idle (they wait at the barrier below); a call carries `world` batches.
             os.environ["NXS_GPU_DEVICES"] = f"0-{world - 1}"
             try:
-                t0 = time.time()
-                nxs2 = capi.Nxs(base)
-                idx2 = nxs2.open_index("bench")
                 big = [(C.c_char_p * (world * args.batch))(*sum((strings[(j * world + r) % n] for r in range(world)), []))
                        for j in range(min(n, 8))]
-                idx2.search_batch_arrays(big[0], args.limit, **params)        # builds the replicas
-                built = time.time() - t0
-                for s in range(args.warmup):
-                    idx2.search_batch_arrays(big[s % len(big)], args.limit, **params)
-                reps = []
-                for rep in range(E2E_REPS):
-                    t0 = time.perf_counter()
-                    flight, issued = [], 0
-                    for s in range(args.steps):
-                        while issued < args.steps and len(flight) < E2E_DEPTH:
-                            flight.append(idx2.search_batch_begin(big[issued % len(big)], args.limit, **params))
-                            issued += 1
-                        idx2.search_batch_end_arrays(flight.pop(0))
-                    reps.append(time.perf_counter() - t0)
-                dts = sorted(reps)[len(reps) // 2]
-                AUX["e2e_single_process"] = {
-                    "value": world * args.batch * args.steps / dts, "unit": UNIT,
-                    "path": f"one process, one nxs_t, NXS_GPU_DEVICES=0-{world - 1}: nxs_index_search_batch_begin/_end "
-                            f"with {world * args.batch} queries per call, split over {world} replicas inside the library",
-                    "open_and_build_s": round(built, 2)}
-                log(f"[0] e2e, one process driving {world} GPUs: {world * args.batch * args.steps / dts:.0f} q/s")
-                idx2.close()
-                nxs2.close()
+                seen = None
+                # ... and the same calls with NXS_GPU_LAYOUT=shards: a range of the documents per
+                # device, every device scores every query, the lists merge on the first device
+                # (what an index larger than one GPU needs; the answers must be the same).
+                for layout in ("replicas", "shards"):
+                    os.environ["NXS_GPU_LAYOUT"] = layout
+                    t0 = time.time()
+                    nxs2 = capi.Nxs(base)
+                    idx2 = nxs2.open_index("bench")
+                    first = idx2.search_batch_arrays(big[0], args.limit, **params)  # builds the images
+                    built = time.time() - t0
+                    if seen is None:
+                        seen = [a.copy() for a in first]
+                    else:
+                        assert all(np.array_equal(a, b) for a, b in zip(seen, first)), \
+                            "shards and replicas disagree"
+                    for s in range(args.warmup):
+                        idx2.search_batch_arrays(big[s % len(big)], args.limit, **params)
+                    reps = []
+                    for rep in range(E2E_REPS):
+                        t0 = time.perf_counter()
+                        flight, issued = [], 0
+                        for s in range(args.steps):
+                            while issued < args.steps and len(flight) < E2E_DEPTH:
+                                flight.append(idx2.search_batch_begin(big[issued % len(big)], args.limit, **params))
+                                issued += 1
+                            idx2.search_batch_end_arrays(flight.pop(0))
+                        reps.append(time.perf_counter() - t0)
+                    dts = sorted(reps)[len(reps) // 2]
+                    how = (f"split over {world} replicas inside the library" if layout == "replicas" else
+                           f"every query scored on all {world} document ranges, top-{args.limit} lists merged on "
+                           f"device 0 over NVLink; results equal to the replicas' bit for bit")
+                    AUX["e2e_single_process" + ("" if layout == "replicas" else "_shards")] = {
+                        "value": world * args.batch * args.steps / dts, "unit": UNIT,
+                        "path": f"one process, one nxs_t, NXS_GPU_DEVICES=0-{world - 1}"
+                                f"{'' if layout == 'replicas' else ' NXS_GPU_LAYOUT=shards'}: "
+                                f"nxs_index_search_batch_begin/_end with {world * args.batch} queries per call, {how}",
+                        "open_and_build_s": round(built, 2)}
+                    log(f"[0] e2e, one process driving {world} GPUs ({layout}): "
+                        f"{world * args.batch * args.steps / dts:.0f} q/s")
+                    idx2.close()
+                    nxs2.close()
             except Exception as exc:
                 log(f"[0] single-process leg failed: {exc}")
             finally:
                 os.environ.pop("NXS_GPU_DEVICES", None)
+                os.environ.pop("NXS_GPU_LAYOUT", None)
         if cpu_group is not None:
             dist.barrier(group=cpu_group)
         if world > 1:
