@@ -103,6 +103,27 @@ def test_shards_plus_merge_equal_the_whole_index(corpus, whole):
         e.close()
 
 
+def test_one_sharded_engine_equals_the_whole_index(corpus, whole):
+    """nxsb_engine_create_sharded at full size: three posting-balanced document
+    ranges (every visible device, wrapping on a one-GPU box), peer copies and
+    the on-device merge -- bit for bit the single-engine answer, with four
+    searches in flight."""
+    from nxsearch_b200 import engine
+
+    ors, bools = queries(corpus)
+    ndev = engine.device_count()
+    sh = engine.Engine(devices=[d % ndev for d in range(max(3, ndev))], layout="shards")
+    sh.load_corpus(corpus, df=corpus.term_df)
+    for algo, k, qs in ((BM25, 10, ors), (TFIDF, 100, bools), (BM25, 200, ors[:48])):
+        batch = engine.Batch.from_lists(algo, k, qs)
+        want = whole.search(batch)
+        same(sh.search(batch), want)
+        hs = [sh.search_begin(batch) for _ in range(4)]
+        for h in hs:
+            same(sh.search_end(h, len(qs), k), want)
+    sh.close()
+
+
 def test_both_kernels_agree(corpus, whole):
     from nxsearch_b200 import engine
 
