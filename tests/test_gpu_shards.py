@@ -191,3 +191,38 @@ def test_sharded_engine_segments_and_removals(c1_corpus):
     assert sh.segment_count() == 0
     sh.close()
     truth.close()
+
+
+def test_sharded_engine_with_fewer_documents_than_devices():
+    """Three documents over five ranges: the empty ranges answer nothing, the
+    merge still returns what one engine returns; then an index with no
+    documents at all, and a delta segment next to empty base ranges."""
+    from nxsearch_b200 import engine
+    from test_gpu_segments import assert_same
+
+    ids, lens = [7, 9, 12], [13, 5, 4]
+    off, pairs = [0, 2, 3, 5], [1, 10, 2, 3, 2, 5, 1, 1, 3, 3]
+    qs = [([1], [0]), ([2, 1], [1, 0, -3]), ([3], [0]), ([2, 1], [1, 0, -2]), ([3, 2], [1, 0, -4])]
+    one = engine.Engine(0)
+    sh = engine.Engine(devices=_devices(5), layout="shards")
+    for e in (one, sh):
+        e.load_docs(ids, lens, off, pairs, 3, sum(lens), 3)
+    for algo in (BM25, TFIDF):
+        for k in (1, 2, 10):
+            batch = engine.Batch.from_lists(algo, k, qs)
+            assert_same(sh.search(batch), one.search(batch))
+    # a delta segment and a removal; statistics move with them
+    df = np.array([3, 2, 2], dtype=np.uint32)
+    for e in (one, sh):
+        e.load_docs([20], [6], [0, 2], [1, 2, 3, 4], 3, sum(lens) + 6, 4, df, segment=True)
+        e.set_dead(0, [9])
+        e.set_global_stats(np.array([3, 1, 2], dtype=np.uint32), sum(lens) + 6 - 5, 3)
+    batch = engine.Batch.from_lists(BM25, 10, qs)
+    got = sh.search(batch)
+    assert_same(got, one.search(batch))
+    assert 9 not in got[1] and 20 in got[1]
+    for e in (one, sh):
+        e.load_docs([], [], [0], [], 3, 0, 0)
+    assert list(sh.search(batch)[0]) == [0] * len(qs)
+    one.close()
+    sh.close()
