@@ -486,7 +486,8 @@ multi_fail(nxsb_engine_t *e, const nxsb_engine_t *child, int r)
 
 #define NOT_ON_REPLICATED(e, what) do {						\
 	if (is_multi(e))							\
-		return fail((e), what " is not available on a replicated engine");\
+		return fail((e), what " is not available on a %s engine",	\
+		    (e)->sharded ? "sharded" : "replicated");			\
 } while (0)
 
 /* fn(replica, index) on every replica, one host thread each; 0 if all returned 0. */
