@@ -133,6 +133,20 @@ int		nxsb_query_compile(const char *query, char *tokens_buf,
 		    uint32_t prog_cap, uint32_t *n_prog);
 
 /*
+ * The text front end on its own (the tokenizer is internal): the distinct
+ * words of `text` in first-seen order, NUL-separated into tokens_buf, with
+ * their occurrence counts -- what nxs_index_add hands to the term table
+ * (ref src/core/tokenizer.c:234-302, token sets :94-117).  normalize != 0
+ * runs the "normalizer" filter over every word.  Used by the tests that pin
+ * the segmentation to the reference's golden cases
+ * (ref src/tests/t_tokenize.c:17-62, src/tests/t_utf8.c:70-74).
+ * Returns 0, or -1 on insufficient capacity.
+ */
+int		nxsb_tokenize(const char *text, size_t len, int normalize,
+		    char *tokens_buf, size_t buf_len, uint32_t *n_tokens,
+		    uint32_t *counts, uint32_t counts_cap);
+
+/*
  * Drain n responses of a batch the way a C caller would -- with the public
  * iterator nxs_resp_iter_reset() / nxs_resp_iter_result() (ref
  * src/core/results.c:222-247) -- into flat arrays: counts[i] results of

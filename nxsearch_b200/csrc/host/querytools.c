@@ -121,3 +121,35 @@ out:
 	qtree_free(&tree);
 	return ret;
 }
+
+NXS_API int
+nxsb_tokenize(const char *text, size_t len, int normalize, char *tokens_buf,
+    size_t buf_len, uint32_t *n_tokens, uint32_t *counts, uint32_t counts_cap)
+{
+	filter_pipeline_t fp = { 0 };
+	tokenset_t *ts;
+	size_t off = 0;
+	int ret = -1;
+
+	*n_tokens = 0;
+	if (normalize)
+		fp.kinds[fp.count++] = FILT_NORMALIZER;
+	if ((ts = tokenize(&fp, text, len)) == NULL)
+		return -1;
+	for (uint32_t j = 0; j < ts->count; j++) {
+		const token_t *t = &ts->list[j];
+
+		if (off + t->len + 1 > buf_len || (counts && j >= counts_cap))
+			goto out;
+		memcpy(tokens_buf + off, t->str, t->len);
+		tokens_buf[off + t->len] = '\0';
+		off += t->len + 1;
+		if (counts)
+			counts[j] = t->count;
+	}
+	*n_tokens = ts->count;
+	ret = 0;
+out:
+	tokenset_destroy(ts);
+	return ret;
+}

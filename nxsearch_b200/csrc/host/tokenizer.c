@@ -139,6 +139,68 @@ tokenset_destroy(tokenset_t *ts)
 }
 
 /*
+ * Simple lower-case mapping of a code point below U+0800, 0 = unchanged.
+ * Only mappings that keep the UTF-8 length (two bytes stay two bytes): the
+ * Latin-1 Supplement, Latin Extended-A, Greek and Cyrillic blocks -- what the
+ * reference's golden case exercises (ref src/tests/t_utf8.c:73-74,
+ * "ĄČĘĖĮŠŲŪŽ" -> "ąčęėįšųūž").  U+0130 (whose lower case is one byte) and
+ * everything from U+0800 up are left alone.
+ */
+static uint32_t
+lower_2byte(uint32_t cp)
+{
+	if ((cp >= 0xc0 && cp <= 0xde && cp != 0xd7) ||		/* Latin-1 */
+	    (cp >= 0x391 && cp <= 0x3ab && cp != 0x3a2) ||	/* Greek */
+	    (cp >= 0x410 && cp <= 0x42f))			/* Cyrillic */
+		return cp + 0x20;
+	if (cp >= 0x400 && cp <= 0x40f)
+		return cp + 0x50;
+	if (cp == 0x178)
+		return 0xff;
+	if (cp == 0x386)
+		return 0x3ac;
+	if (cp >= 0x388 && cp <= 0x38a)
+		return cp + 0x25;
+	if (cp == 0x38c)
+		return 0x3cc;
+	if (cp == 0x38e || cp == 0x38f)
+		return cp + 0x3f;
+	/* Pairs (upper, upper + 1): even upper ... */
+	if (((cp >= 0x100 && cp <= 0x12f) || (cp >= 0x132 && cp <= 0x137) ||
+	    (cp >= 0x14a && cp <= 0x177) || (cp >= 0x460 && cp <= 0x481) ||
+	    (cp >= 0x48a && cp <= 0x4bf) || (cp >= 0x4d0 && cp <= 0x4ff)) && !(cp & 1))
+		return cp + 1;
+	/* ... and odd upper. */
+	if (((cp >= 0x139 && cp <= 0x148) || (cp >= 0x179 && cp <= 0x17e) ||
+	    (cp >= 0x4c1 && cp <= 0x4ce)) && (cp & 1))
+		return cp + 1;
+	return 0;
+}
+
+/*
+ * "normalizer": the reference lower-cases and applies NFKC through ICU
+ * (ref src/utils/utf8.c:263-330).  Here: ASCII and the two-byte blocks above
+ * are lower-cased in place; compatibility decomposition is not attempted.
+ */
+static void
+utf8_lower_inplace(unsigned char *buf, size_t len)
+{
+	for (size_t k = 0; k < len; k++) {
+		if (buf[k] >= 'A' && buf[k] <= 'Z') {
+			buf[k] += 'a' - 'A';
+		} else if ((buf[k] & 0xe0) == 0xc0 && k + 1 < len && (buf[k + 1] & 0xc0) == 0x80) {
+			const uint32_t lo = lower_2byte(((uint32_t)(buf[k] & 0x1f) << 6) | (buf[k + 1] & 0x3f));
+
+			if (lo) {
+				buf[k] = 0xc0 | (lo >> 6);
+				buf[k + 1] = 0x80 | (lo & 0x3f);
+			}
+			k++;
+		}
+	}
+}
+
+/*
  * The filter pipeline over one word, in place.  Returns 1 to keep the token,
  * 0 if a filter discarded it (or left it empty: ref filters.c:206-208).
  */
@@ -150,10 +212,7 @@ filter_apply(const filter_pipeline_t *fp, char *buf, size_t *lenp)
 	for (unsigned i = 0; i < fp->count; i++) {
 		switch (fp->kinds[i]) {
 		case FILT_NORMALIZER:
-			for (size_t k = 0; k < len; k++) {
-				if (buf[k] >= 'A' && buf[k] <= 'Z')
-					buf[k] += 'a' - 'A';
-			}
+			utf8_lower_inplace((unsigned char *)buf, len);
 			break;
 		case FILT_STOPWORDS:
 			if (fp->stopwords && strmap_get(fp->stopwords, buf, len, NULL))
@@ -222,11 +281,34 @@ out:
 	return ret;
 }
 
-static inline bool
-is_word_byte(unsigned char c)
+/*
+ * Word segmentation: the reference walks ICU's UBRK_WORD boundaries and keeps
+ * the segments whose rule status is not UBRK_WORD_NONE (ref
+ * src/core/tokenizer.c:234-302).  These are the UAX #29 word-break rules over
+ * the ASCII classes (ICU's tailoring: the colon is not MidLetter), with every
+ * byte >= 0x80 taken as a letter:
+ *   WB5, WB8-10, WB13, WB13a/b   letters, digits and '_' join;
+ *   WB6/7    letter ( . | ' ) letter joins ("i.b.m", "doesn't");
+ *   WB11/12  digit ( . | ' | , | ; ) digit joins ("3.14", "1,000").
+ * A segment without a letter or a digit is not a word.  Pinned by the
+ * reference's golden cases (ref src/tests/t_tokenize.c:17-62).
+ */
+enum { WC_OTHER, WC_LETTER, WC_DIGIT, WC_EXTNUMLET, WC_MIDNUMLET, WC_MIDNUM };
+
+static inline int
+word_class(unsigned char c)
 {
-	return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') ||
-	    (c >= 'A' && c <= 'Z') || c >= 0x80;
+	if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c >= 0x80)
+		return WC_LETTER;
+	if (c >= '0' && c <= '9')
+		return WC_DIGIT;
+	if (c == '_')
+		return WC_EXTNUMLET;
+	if (c == '.' || c == '\'')
+		return WC_MIDNUMLET;
+	if (c == ',' || c == ';')
+		return WC_MIDNUM;
+	return WC_OTHER;
 }
 
 tokenset_t *
@@ -238,15 +320,30 @@ tokenize(filter_pipeline_t *fp, const char *text, size_t len)
 	if (!ts)
 		return NULL;
 	while (i < len && text[i]) {
-		size_t s;
+		bool word = false;
+		int last = WC_OTHER;
 		int32_t slot;
+		size_t s;
 
-		while (i < len && text[i] && !is_word_byte(text[i]))
+		while (i < len && text[i] && word_class(text[i]) != WC_LETTER &&
+		    word_class(text[i]) != WC_DIGIT && word_class(text[i]) != WC_EXTNUMLET)
 			i++;
 		s = i;
-		while (i < len && is_word_byte(text[i]))
+		while (i < len && text[i]) {
+			const int c = word_class(text[i]);
+			const int next = i + 1 < len ? word_class(text[i + 1]) : WC_OTHER;
+
+			if (c == WC_LETTER || c == WC_DIGIT || c == WC_EXTNUMLET) {
+				word |= c != WC_EXTNUMLET;
+				last = c;
+			} else if (!((c == WC_MIDNUMLET && last == next &&
+			    (last == WC_LETTER || last == WC_DIGIT)) ||
+			    (c == WC_MIDNUM && last == WC_DIGIT && next == WC_DIGIT))) {
+				break;
+			}
 			i++;
-		if (i > s && tokenize_value(fp, ts, text + s, i - s, &slot) == -1) {
+		}
+		if (word && tokenize_value(fp, ts, text + s, i - s, &slot) == -1) {
 			tokenset_destroy(ts);
 			return NULL;
 		}

@@ -5,13 +5,16 @@
  * uses ICU UAX#29 word breaking, ICU NFKC case folding / transliteration and
  * the Snowball stemmer (ref src/core/tokenizer.c:234-302,
  * src/core/filters_builtin.c); none of those libraries exist here, so this
- * front end implements the ASCII subset:
- *   - a word is a maximal run of [A-Za-z0-9] or bytes >= 0x80;
- *   - "normalizer" lower-cases ASCII letters;
+ * front end implements the part that needs no Unicode tables:
+ *   - words by the UAX #29 rules over the ASCII classes, bytes >= 0x80 taken
+ *     as letters ("i.b.m", "doesn't", "snake_case", "3.14" are one word each;
+ *     ref src/tests/t_tokenize.c:17-62 are the golden cases);
+ *   - "normalizer" lower-cases ASCII and the two-byte Latin / Greek /
+ *     Cyrillic blocks (ref src/tests/t_utf8.c:70-74); no NFKC;
  *   - "stopwords" drops words listed in <basedir>/filters/stopwords/<lang>
  *     (one per line), exactly where the reference looks for them
  *     (filters_builtin.c:93-127);
- *   - "stemmer" passes words through unchanged.
+ *   - "stemmer" is refused (NXS_ERR_INVALID) unless NXSB_STEMMER_PASSTHROUGH=1.
  * Token-set semantics (dedup by string, first-seen order, per-token counts)
  * are the reference's (tokenizer.c:94-117).
  */

@@ -163,6 +163,22 @@ def query_compile(query: str) -> tuple[list[str], list[int]] | None:
     return [t.decode() for t in toks], [prog[i] for i in range(npg.value)]
 
 
+def tokenize(text: str | bytes, *, normalize: bool = True) -> list[tuple[str, int]]:
+    """The text front end on its own: [(word, occurrences)] in first-seen order."""
+    lib = _bind()
+    lib.nxsb_tokenize.restype = C.c_int
+    lib.nxsb_tokenize.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t,
+                                  C.POINTER(C.c_uint32), C.c_void_p, C.c_uint32]
+    raw = text.encode() if isinstance(text, str) else text
+    buf = C.create_string_buffer(2 * len(raw) + 16)
+    counts = (C.c_uint32 * (len(raw) + 1))()
+    n = C.c_uint32()
+    if lib.nxsb_tokenize(raw, len(raw), int(normalize), buf, len(buf), C.byref(n), counts, len(raw) + 1) != 0:
+        raise RuntimeError("nxsb_tokenize failed")
+    toks = buf.raw.split(b"\0")[: n.value]
+    return [(t.decode(), counts[i]) for i, t in enumerate(toks)]
+
+
 def query_terms(n_terms: int, df, n: int, *, seed: int = SEED + 1) -> np.ndarray:
     """n Zipf(1.0) term ids over a vocabulary of n_terms, restricted to df >= 1.
 

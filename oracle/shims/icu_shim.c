@@ -4,8 +4,11 @@
  * Replaces the two pieces of ICU the reference's indexing/query front end
  * needs -- UBRK_WORD segmentation (core/tokenizer.c:234-302) and the
  * UTF-8 <-> UTF-16 helpers of utils/utf8.c:112-190 -- with an ASCII-only
- * equivalent.  A "word" is a maximal run of [A-Za-z0-9] or non-ASCII units;
- * everything else is a UBRK_WORD_NONE segment.
+ * equivalent: the UAX #29 word-break rules over the ASCII classes (letters,
+ * digits and '_' join; letter (.|') letter and digit (.|'|,|;) digit join;
+ * the colon does not, as in ICU's tailoring), non-ASCII units taken as
+ * letters.  A segment without a letter or a digit -- and everything else --
+ * is a UBRK_WORD_NONE segment.
  */
 #include <stdlib.h>
 #include <string.h>
@@ -24,11 +27,22 @@ struct UBreakIterator {
 	int32_t		status;
 };
 
+enum { WC_OTHER, WC_LETTER, WC_DIGIT, WC_EXTNUMLET, WC_MIDNUMLET, WC_MIDNUM };
+
 static int
-is_word_unit(UChar c)
+word_class(UChar c)
 {
-	return (c >= '0' && c <= '9') || (c >= 'a' && c <= 'z') ||
-	    (c >= 'A' && c <= 'Z') || c >= 0x80;
+	if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c >= 0x80)
+		return WC_LETTER;
+	if (c >= '0' && c <= '9')
+		return WC_DIGIT;
+	if (c == '_')
+		return WC_EXTNUMLET;
+	if (c == '.' || c == '\'')
+		return WC_MIDNUMLET;
+	if (c == ',' || c == ';')
+		return WC_MIDNUM;
+	return WC_OTHER;
 }
 
 const char *
@@ -78,10 +92,26 @@ ubrk_next(UBreakIterator *it)
 	if (p >= it->len) {
 		return UBRK_DONE;
 	}
-	if (is_word_unit(it->text[p])) {
-		while (p < it->len && is_word_unit(it->text[p]))
+	const int first = word_class(it->text[p]);
+
+	if (first == WC_LETTER || first == WC_DIGIT || first == WC_EXTNUMLET) {
+		int last = WC_OTHER, word = 0;
+
+		while (p < it->len) {
+			const int c = word_class(it->text[p]);
+			const int next = p + 1 < it->len ? word_class(it->text[p + 1]) : WC_OTHER;
+
+			if (c == WC_LETTER || c == WC_DIGIT || c == WC_EXTNUMLET) {
+				word |= c != WC_EXTNUMLET;
+				last = c;
+			} else if (!((c == WC_MIDNUMLET && last == next &&
+			    (last == WC_LETTER || last == WC_DIGIT)) ||
+			    (c == WC_MIDNUM && last == WC_DIGIT && next == WC_DIGIT))) {
+				break;
+			}
 			p++;
-		it->status = UBRK_WORD_LETTER;
+		}
+		it->status = word ? UBRK_WORD_LETTER : UBRK_WORD_NONE;
 	} else {
 		p++;
 		it->status = UBRK_WORD_NONE;

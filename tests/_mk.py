@@ -121,3 +121,20 @@ PARSER_CASES = [
     ("a b OR (c OR d) AND (e", None, [FF, FF, OR_, BO, FF, OR_, FF, BC, AND_, BO, FF]),
     ("A\nand\nB", "(AND `A` `B`)", [FF, AND_, FF]),
 ]
+
+# src/tests/t_tokenize.c:17-62 (text, tokens in first-seen order; "normalizer" only).
+# The reference keeps a seventh case out of its own run (t_tokenize.c:64-79, "TODO").
+TOKENIZE_CASES = [
+    ("a", ["a"]),
+    ("The quick brown fox jumped over the lazy dog.",
+     ["the", "quick", "brown", "fox", "jumped", "over", "lazy", "dog"]),
+    ("We will play with I.B.M.", ["we", "will", "play", "with", "i.b.m"]),
+    ("Hello_I_m_arbitrary_concatenated, foo and bar", ["hello_i_m_arbitrary_concatenated", "foo", "and", "bar"]),
+    ("the [client] is <foo>, some *bold* marks.", ["the", "client", "is", "foo", "some", "bold", "marks"]),
+    ("Text,which doesn't  have spaces right;one;two;three..",
+     ["text", "which", "doesn't", "have", "spaces", "right", "one", "two", "three"]),
+    ("", []),
+]
+
+# src/tests/t_utf8.c:70-74 (utf8_tolower)
+LOWER_CASES = [("TEST", "test"), ("ĄČĘĖĮŠŲŪŽ", "ąčęėįšųūž")]

@@ -266,6 +266,27 @@ def test_gpu_device_list_is_parsed_or_ignored(spec, monkeypatch):
         shutil.rmtree(base, ignore_errors=True)
 
 
+def test_tokenizer_matches_the_reference_goldens():
+    """Word segmentation and the normalizer against the reference's own cases
+    (ref src/tests/t_tokenize.c:17-62, src/tests/t_utf8.c:70-74), plus the
+    UAX #29 rules they imply for digits and what stays out of reach here."""
+    for text, want in _mk.TOKENIZE_CASES:
+        assert [w for w, _ in tools.tokenize(text)] == want, text
+    assert tools.tokenize("The quick brown fox jumped over the lazy dog.")[0] == ("the", 2)
+    for text, want in _mk.LOWER_CASES:
+        assert tools.tokenize(text) == [(want, 1)]
+    assert tools.tokenize("Київ ДНІПР Ελλάδα ÅNGSTRÖM straße") == \
+        [("київ", 1), ("дніпр", 1), ("ελλάδα", 1), ("ångström", 1), ("straße", 1)]
+    # WB11/12: digits join over . , ; ' -- letters only over . and '
+    assert [w for w, _ in tools.tokenize("pi is 3.14, or 1,000;5 a,b a;b x.y 1.a a.1 v2.0")] == \
+        ["pi", "is", "3.14", "or", "1,000;5", "a", "b", "x.y", "1", "v2.0"]
+    # a segment without a letter or a digit is not a word; '_' joins (WB13a/b); ':' and '-' never do
+    assert [w for w, _ in tools.tokenize("_ __ _x_ year-end 10:30 a:b 'quoted' ..")] == \
+        ["_x_", "year", "end", "10", "30", "a", "b", "quoted"]
+    # without the normalizer the case stays
+    assert tools.tokenize("Some.Text", normalize=False) == [("Some.Text", 1)]
+
+
 def test_gpu_layout_is_replicas_or_shards_nothing_else(monkeypatch):
     """NXS_GPU_LAYOUT picks what several devices hold (replicas of the image, or
     a range of the documents each).  A misspelt value fails nxs_open instead of
@@ -289,6 +310,9 @@ def test_index_files_are_interchangeable_with_the_reference(nxs, c1_corpus):
     if ref is None:
         pytest.skip("oracle/_ref not built")
     texts = [(5, "the cat sat on the mat"), (9, "a cat and a dog"), (2, "dog eat dog world"), (11, "mat")]
+    # the reference's own tokenizer cases: punctuation, acronyms, snake case go the same way on both sides
+    texts += [(20 + i, t) for i, (t, _) in enumerate(_mk.TOKENIZE_CASES) if t]
+    texts.append((40, "pi is 3.14, or 1,000;5 -- v2.0 at 10:30, year-end _x_ 'quoted'"))
     ours = nxs.create_index("a")
     for d, t in texts:
         ours.add(d, t)
@@ -308,7 +332,8 @@ def test_index_files_are_interchangeable_with_the_reference(nxs, c1_corpus):
         shutil.copy(Path(nxs.base) / "data/a/nxsterms", Path(rbase) / "data/a/nxsterms")
         shutil.copy(Path(nxs.base) / "data/a/nxsdtmap", Path(rbase) / "data/a/nxsdtmap")
         again = rn.open_index("a")
-        assert sorted(d for d, _ in again.search("dog OR mat")) == [2, 5, 11]
+        assert sorted(d for d, _ in again.search("dog OR mat")) == [2, 5, 11, 21]
+        assert [d for d, _ in again.search("'i.b.m'")] == [22]
         again.close()
         rn.close()
     finally:
