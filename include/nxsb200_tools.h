@@ -136,10 +136,11 @@ int		nxsb_query_compile(const char *query, char *tokens_buf,
  * The text front end on its own (the tokenizer is internal): the distinct
  * words of `text` in first-seen order, NUL-separated into tokens_buf, with
  * their occurrence counts -- what nxs_index_add hands to the term table
- * (ref src/core/tokenizer.c:234-302, token sets :94-117).  normalize != 0
- * runs the "normalizer" filter over every word.  Used by the tests that pin
- * the segmentation to the reference's golden cases
- * (ref src/tests/t_tokenize.c:17-62, src/tests/t_utf8.c:70-74).
+ * (ref src/core/tokenizer.c:234-302, token sets :94-117).  Bit 0 of
+ * `normalize' runs the "normalizer" filter over every word, bit 1 the
+ * English "stemmer" after it.  Used by the tests that pin the segmentation
+ * to the reference's golden cases (ref src/tests/t_tokenize.c:17-62,
+ * src/tests/t_utf8.c:70-74) and the stemmer to the published vocabulary.
  * Returns 0, or -1 on insufficient capacity.
  */
 int		nxsb_tokenize(const char *text, size_t len, int normalize,

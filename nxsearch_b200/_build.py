@@ -21,7 +21,7 @@ OBJDIR = LIBDIR / "obj"
 LIB = LIBDIR / "libnxsearch.so"
 
 HOST_SRCS = [
-    "hashmap.c", "json.c", "params.c", "results.c", "query.c", "tokenizer.c",
+    "hashmap.c", "json.c", "params.c", "results.c", "query.c", "tokenizer.c", "stem_en.c",
     "bkmirror.c", "index.c", "nxs.c", "search.c",
 ]
 # libnxsb_tools.so: the synthetic-corpus generator, the bulk index-file writer
@@ -30,7 +30,7 @@ HOST_SRCS = [
 # carries the search path only; it needs no CUDA.
 TOOLS_LIB = LIBDIR / "libnxsb_tools.so"
 TOOLS_SRCS = ["corpus.c", "querytools.c"]
-TOOLS_SHARED = ["hashmap.c", "json.c", "params.c", "query.c", "tokenizer.c", "bkmirror.c"]
+TOOLS_SHARED = ["hashmap.c", "json.c", "params.c", "query.c", "tokenizer.c", "stem_en.c", "bkmirror.c"]
 GPU_SRCS = ["engine.cu"]
 
 CFLAGS = [

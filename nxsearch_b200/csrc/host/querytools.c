@@ -132,8 +132,12 @@ nxsb_tokenize(const char *text, size_t len, int normalize, char *tokens_buf,
 	int ret = -1;
 
 	*n_tokens = 0;
-	if (normalize)
+	if (normalize & 1)
 		fp.kinds[fp.count++] = FILT_NORMALIZER;
+	if (normalize & 2) {
+		fp.kinds[fp.count++] = FILT_STEMMER;
+		fp.stem_english = true;
+	}
 	if ((ts = tokenize(&fp, text, len)) == NULL)
 		return -1;
 	for (uint32_t j = 0; j < ts->count; j++) {

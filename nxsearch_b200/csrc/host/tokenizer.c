@@ -69,31 +69,37 @@ filter_pipeline_create(nxs_t *nxs, nxs_params_t *params)
 			return NULL;
 		}
 		/*
-		 * No Snowball in this build: a pipeline that names the stemmer
-		 * would index and query UNSTEMMED terms under parameters that
-		 * promise stemmed ones (and miss the terms of an index the
-		 * reference built).  That is an error, not a silent pass-through;
-		 * NXSB_STEMMER_PASSTHROUGH=1 accepts it knowingly (identity
-		 * stemmer -- what the tests' compiled reference is built with).
+		 * libstemmer is not in this build; the English algorithm is
+		 * restated in stem_en.c.  For any other language a pipeline that
+		 * names the stemmer would index and query UNSTEMMED terms under
+		 * parameters that promise stemmed ones (and miss the terms of an
+		 * index the reference built): an error, not a silent
+		 * pass-through.  NXSB_STEMMER_PASSTHROUGH=1 asks for the identity
+		 * knowingly, whatever the language (what the tests' compiled
+		 * reference is built with).
 		 */
 		if (kind == FILT_STEMMER) {
 			const char *ok = getenv("NXSB_STEMMER_PASSTHROUGH");
+			const char *lang = nxs_params_get_str(params, "lang");
 			static bool warned;
 
-			if (!ok || strcmp(ok, "1") != 0) {
+			if (ok && strcmp(ok, "1") == 0) {
+				if (!warned) {
+					warned = true;
+					fprintf(stderr, "nxsearch-b200: warning: the `stemmer' filter "
+					    "passes terms through unchanged (NXSB_STEMMER_PASSTHROUGH=1)\n");
+				}
+			} else if (!lang || strcmp(lang, "en") == 0 || strcmp(lang, "english") == 0) {
+				fp->stem_english = true;
+			} else {
 				nxs_set_error(nxs, NXS_ERR_INVALID,
-				    "filter `stemmer' is not available in this build (no "
-				    "Snowball); drop it from `filters' or set "
-				    "NXSB_STEMMER_PASSTHROUGH=1 to index unstemmed terms");
+				    "filter `stemmer' is not available for language `%s' in this "
+				    "build (no libstemmer; English only); drop it from `filters' "
+				    "or set NXSB_STEMMER_PASSTHROUGH=1 to index unstemmed terms", lang);
 				free(names);
 				strmap_destroy(fp->stopwords);
 				free(fp);
 				return NULL;
-			}
-			if (!warned) {
-				warned = true;
-				fprintf(stderr, "nxsearch-b200: warning: the `stemmer' filter "
-				    "passes terms through unchanged (NXSB_STEMMER_PASSTHROUGH=1)\n");
 			}
 		}
 		fp->kinds[fp->count++] = kind;
@@ -207,7 +213,7 @@ utf8_lower_inplace(unsigned char *buf, size_t len)
 int
 filter_apply(const filter_pipeline_t *fp, char *buf, size_t *lenp)
 {
-	const size_t len = *lenp;
+	size_t len = *lenp;
 
 	for (unsigned i = 0; i < fp->count; i++) {
 		switch (fp->kinds[i]) {
@@ -219,11 +225,16 @@ filter_apply(const filter_pipeline_t *fp, char *buf, size_t *lenp)
 				return 0;
 			break;
 		case FILT_STEMMER:
-			break;	/* identity: only with NXSB_STEMMER_PASSTHROUGH=1 */
+			if (fp->stem_english) {	/* else the identity (NXSB_STEMMER_PASSTHROUGH=1) */
+				len = stem_english(buf, len);
+				buf[len] = '\0';
+			}
+			break;
 		}
 		if (len == 0)
 			return 0;
 	}
+	*lenp = len;
 	return len != 0;
 }
 

@@ -14,7 +14,9 @@
  *   - "stopwords" drops words listed in <basedir>/filters/stopwords/<lang>
  *     (one per line), exactly where the reference looks for them
  *     (filters_builtin.c:93-127);
- *   - "stemmer" is refused (NXS_ERR_INVALID) unless NXSB_STEMMER_PASSTHROUGH=1.
+ *   - "stemmer" is the Snowball english algorithm, restated in stem_en.c, for
+ *     lang = "en"; any other language is refused (NXS_ERR_INVALID) unless
+ *     NXSB_STEMMER_PASSTHROUGH=1 asks for the identity.
  * Token-set semantics (dedup by string, first-seen order, per-token counts)
  * are the reference's (tokenizer.c:94-117).
  */
@@ -29,7 +31,11 @@ typedef struct {
 	unsigned	count;
 	filter_kind_t	kinds[8];
 	strmap_t *	stopwords;	/* NULL = none for this language */
+	bool		stem_english;	/* "stemmer" with lang = en; else it is the identity */
 } filter_pipeline_t;
+
+/* The Snowball "english" stemmer over a lower-case word in place; returns the new length. */
+size_t		stem_english(char *w, size_t len);
 
 typedef struct {
 	char *		str;

@@ -163,8 +163,9 @@ def query_compile(query: str) -> tuple[list[str], list[int]] | None:
     return [t.decode() for t in toks], [prog[i] for i in range(npg.value)]
 
 
-def tokenize(text: str | bytes, *, normalize: bool = True) -> list[tuple[str, int]]:
-    """The text front end on its own: [(word, occurrences)] in first-seen order."""
+def tokenize(text: str | bytes, *, normalize: bool = True, stem: bool = False) -> list[tuple[str, int]]:
+    """The text front end on its own: [(word, occurrences)] in first-seen order
+    (stem=True: the English stemmer after the normalizer)."""
     lib = _bind()
     lib.nxsb_tokenize.restype = C.c_int
     lib.nxsb_tokenize.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t,
@@ -173,7 +174,7 @@ def tokenize(text: str | bytes, *, normalize: bool = True) -> list[tuple[str, in
     buf = C.create_string_buffer(2 * len(raw) + 16)
     counts = (C.c_uint32 * (len(raw) + 1))()
     n = C.c_uint32()
-    if lib.nxsb_tokenize(raw, len(raw), int(normalize), buf, len(buf), C.byref(n), counts, len(raw) + 1) != 0:
+    if lib.nxsb_tokenize(raw, len(raw), int(normalize) | (2 if stem else 0), buf, len(buf), C.byref(n), counts, len(raw) + 1) != 0:
         raise RuntimeError("nxsb_tokenize failed")
     toks = buf.raw.split(b"\0")[: n.value]
     return [(t.decode(), counts[i]) for i, t in enumerate(toks)]

@@ -56,8 +56,7 @@ def make_corpus(docs, vocabulary=None):
 
 
 # The reference's own scoring fixtures (src/tests/t_scoring.c:16-158).  Cases 2
-# and 3 need real stemming ("foxes" -> "fox") and are not reproducible with an
-# ASCII front end; they are listed in DESIGN.md as documentation only.
+# and 3 need the stemmer ("foxes" -> "fox"): STEMMED_SCORING_CASES below.
 SCORING_CASES = [
     # (docs, query, {doc_id: (tfidf, bm25)})
     ([(1, "The quick brown fox jumped over the lazy dog"),
@@ -74,6 +73,17 @@ SCORING_CASES = [
           "All kind of cats including the tabby and other cats"),
       (2, "cats cats cats"), (3, "cats cats dogs")],
      "cats", {1: (1.386294, 0.048411), 2: (1.386294, 0.091469), 3: (1.098612, 0.084499)}),
+]
+
+# src/tests/t_scoring.c:16-68, the two cases that need the stemmer ("fox" finds "foxes"):
+# run with filters normalizer + stopwords + stemmer, the reference's defaults.
+STEMMED_SCORING_CASES = [
+    ([(1, "The quick brown fox jumped over the lazy dog"),
+      (2, "Once upon a time there were three little foxes")],
+     "fox", {1: (0.693147, 0.066754), 2: (0.693147, 0.066754)}),
+    ([(1, "The quick brown fox jumped over the lazy dog"),
+      (2, "Once upon a time there were three little foxes")],
+     "fox dog", {1: (1.1736 + 0.693147, 0.253785 + 0.066754), 2: (0.693147, 0.066754)}),
 ]
 
 # src/tests/t_querylogic.c:16-52

@@ -70,6 +70,23 @@ def test_reference_scoring_goldens(nxs, case):
     idx.close()
 
 
+@pytest.mark.parametrize("case", range(len(_mk.STEMMED_SCORING_CASES)))
+def test_reference_scoring_goldens_that_need_the_stemmer(nxs, case, monkeypatch):
+    """ref tests/t_scoring.c cases 2 and 3 with the reference's default filters:
+    "fox" finds "foxes" (the restated Snowball english stemmer, stem_en.c)."""
+    monkeypatch.delenv("NXSB_STEMMER_PASSTHROUGH", raising=False)
+    docs, query, expected = _mk.STEMMED_SCORING_CASES[case]
+    idx = nxs.create_index("t", filters=["normalizer", "stopwords", "stemmer"])
+    for d, text in docs:
+        idx.add(d, text)
+    for algo, col in (("TF-IDF", 0), ("BM25", 1)):
+        got = dict(idx.search(query, algo=algo))
+        assert set(got) == set(expected)
+        for d, vals in expected.items():
+            assert abs(got[d] - vals[col]) < 1e-4, (algo, d, got[d], vals[col])
+    idx.close()
+
+
 def test_reference_querylogic_goldens(nxs):
     idx = nxs.create_index("t")
     for d, text in _mk.LOGIC_DOCS:

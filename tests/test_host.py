@@ -340,17 +340,30 @@ def test_index_files_are_interchangeable_with_the_reference(nxs, c1_corpus):
         shutil.rmtree(rbase, ignore_errors=True)
 
 
-def test_stemmer_is_refused_loudly_not_passed_through(nxs, monkeypatch):
+def test_stemmer_is_english_or_refused_never_passed_through_silently(nxs, monkeypatch):
     """a pipeline naming `stemmer' must not silently index unstemmed
-    terms.  Creating or opening such an index fails with NXS_ERR_INVALID unless
-    the caller opts in to the identity stemmer."""
+    terms.  English is the restated Snowball algorithm (stem_en.c); any other
+    language fails with NXS_ERR_INVALID unless the caller opts in to the
+    identity stemmer."""
     monkeypatch.delenv("NXSB_STEMMER_PASSTHROUGH", raising=False)
-    with pytest.raises(capi.NxsError) as e:
-        nxs.create_index("s", filters=["normalizer", "stemmer"])
-    assert e.value.code == capi.ERR_INVALID and "stemmer" in str(e.value)
-    # an index the reference created with ITS defaults names the stemmer too
+    idx = nxs.create_index("s", filters=["normalizer", "stemmer"])
+    idx.add(1, "The quick brown foxes jumped over the lazy dogs, generously")
+    idx.close()
+    terms = tools.Corpus.read(f"{nxs.base}/data/s/nxsterms", f"{nxs.base}/data/s/nxsdtmap")
+    assert [terms.term(t) for t in range(1, terms.n_terms + 1)] == \
+        ["the", "quick", "brown", "fox", "jump", "over", "lazi", "dog", "generous"]
+    # an index the reference created with ITS defaults names the stemmer too: it opens
     (Path(nxs.base) / "data/s/params.db").write_text(
         json.dumps({"filters": ["normalizer", "stopwords", "stemmer"], "algo": "BM25", "lang": "en"}))
+    idx = nxs.open_index("s")
+    assert idx.params_json()["filters"] == ["normalizer", "stopwords", "stemmer"]
+    idx.close()
+    # ... but not for a language whose algorithm is not here
+    with pytest.raises(capi.NxsError) as e:
+        nxs.create_index("d", filters=["normalizer", "stemmer"], lang="de")
+    assert e.value.code == capi.ERR_INVALID and "stemmer" in str(e.value)
+    (Path(nxs.base) / "data/s/params.db").write_text(
+        json.dumps({"filters": ["normalizer", "stopwords", "stemmer"], "algo": "BM25", "lang": "de"}))
     with pytest.raises(capi.NxsError) as e:
         nxs.open_index("s")
     assert e.value.code == capi.ERR_INVALID
@@ -358,6 +371,57 @@ def test_stemmer_is_refused_loudly_not_passed_through(nxs, monkeypatch):
     idx = nxs.open_index("s")
     assert idx.params_json()["filters"] == ["normalizer", "stopwords", "stemmer"]
     idx.close()
+
+
+def test_english_stemmer_on_the_published_vocabulary():
+    """The Snowball english algorithm as published (snowballstem.org): the
+    worked examples of its description and the sample vocabulary shown beside
+    it, through the same filter the index uses."""
+    pairs = """
+    caresses caress ponies poni ties tie caress caress cats cat feed feed agreed agre plastered plaster
+    bled bled motoring motor sing sing conflated conflat troubled troubl sized size hopping hop tanned tan
+    falling fall hissing hiss fizzed fizz failing fail filing file happy happi sky sky
+    relational relat conditional condit rational ration valenci valenc digitizer digit conformabli conform
+    radicalli radic differentli differ vileli vile analogousli analog vietnamization vietnam
+    predication predic operator oper feudalism feudal decisiveness decis hopefulness hope callousness callous
+    formaliti formal sensitiviti sensit sensibiliti sensibl triplicate triplic formative format formalize formal
+    electriciti electr electrical electr hopeful hope goodness good revival reviv allowance allow
+    inference infer airliner airlin gyroscopic gyroscop adjustable adjust defensible defens irritant irrit
+    replacement replac adjustment adjust dependent depend adoption adopt homologous homolog activate activ
+    angulariti angular effective effect bowdlerize bowdler probate probat rate rate cease ceas
+    controll control roll roll
+    generate generat generates generat generated generat generating generat general general
+    generally general generic generic generically generic generous generous generously generous
+    consign consign consigned consign consigning consign consignment consign consist consist
+    consisted consist consistency consist consistent consist consistently consist consisting consist
+    consists consist consolation consol consolations consol consolatory consolatori console consol
+    consoled consol consoles consol consolidate consolid consolidated consolid consolidating consolid
+    consoling consol consolingly consol consols consol consonant conson consort consort consorted consort
+    consorting consort conspicuous conspicu conspicuously conspicu conspiracy conspiraci
+    conspirator conspir conspirators conspir conspire conspir conspired conspir conspiring conspir
+    constable constabl constables constabl constance constanc constancy constanc constant constant
+    knack knack knackeries knackeri knacks knack knag knag knave knave knaves knave knavish knavish
+    kneaded knead kneading knead knee knee kneel kneel kneeled kneel kneeling kneel kneels kneel
+    knees knee knell knell knelt knelt knew knew knick knick knif knif knife knife knight knight
+    knightly knight knights knight knit knit knits knit knitted knit knitting knit knives knive
+    knob knob knobs knob knock knock knocked knock knocker knocker knockers knocker knocking knock
+    knocks knock knopp knopp knot knot knots knot
+    skis ski skies sky dying die lying lie tying tie idly idl gently gentl ugly ugli early earli
+    only onli singly singl news news howe howe atlas atlas cosmos cosmos bias bias andes andes
+    inning inning outing outing canning canning herring herring earring earring proceed proceed
+    exceed exceed succeed succeed
+    cries cri tied tie gas gas this this gaps gap kiwis kiwi luxuriated luxuri hoped hope hoping hope
+    by by say say cry cri boy's boy owed owe foxes fox jumped jump lazy lazi
+    argument argument arguing argu agreement agreement university univers national nation
+    running run happiness happi organization organ easily easili fairly fair something someth
+    beautiful beauti flies fli died die yields yield playing play
+    """.split()
+    assert len(pairs) % 2 == 0 and len(pairs) > 400
+    for word, want in zip(pairs[0::2], pairs[1::2]):
+        assert tools.tokenize(word, stem=True) == [(want, 1)], word
+    # two letters or fewer stay; the normalizer runs first; other bytes are consonants
+    assert [w for w, _ in tools.tokenize("As IS Foxes ąžuolas 12345s", stem=True)] == \
+        ["as", "is", "fox", "ąžuola", "12345s"]
 
 
 def test_every_declared_symbol_is_exported():

@@ -81,6 +81,36 @@ def test_scoring_goldens(case):
             assert abs(got[d] - vals[col]) < 1e-4, (d, got[d], vals[col])
 
 
+@pytest.mark.parametrize("case", range(len(_mk.STEMMED_SCORING_CASES)))
+def test_scoring_goldens_that_need_the_stemmer(case):
+    """ref tests/t_scoring.c cases 2 and 3: the documents go through this tree's
+    front end (UAX #29 words, normalizer, the restated Snowball english stemmer,
+    nxsearch_b200/csrc/host/stem_en.c) and the port scores them -- "fox" finds
+    "foxes" with the reference's own scores."""
+    from nxsearch_b200 import tools
+
+    docs, query, expected = _mk.STEMMED_SCORING_CASES[case]
+    stem = lambda text: [w for w, n in tools.tokenize(text, stem=True) for _ in range(n)]
+    corpus = _mk.make_corpus([(d, stem(t)) for d, t in docs])
+    assert corpus.tid("fox") and not corpus.tid("foxes") and corpus.tid("jump") and corpus.tid("lazi")
+    ora = _oracle.OracleIndex(corpus)
+    leaves = [corpus.tid(w) for w in stem(query)]
+    toks = []
+    for t in reversed(leaves):
+        if t not in toks:
+            toks.append(t)
+    slot = {t: s for s, t in enumerate(toks)}
+    prog = [slot[leaves[0]]]
+    for t in leaves[1:]:
+        prog += [slot[t], OP_OR]
+    for algo, col in ((TFIDF, 0), (BM25, 1)):
+        ids, sc = ora.search(algo, 1000, toks, prog)
+        got = dict(zip(ids.tolist(), sc.tolist()))
+        assert set(got) == set(expected)
+        for d, vals in expected.items():
+            assert abs(got[d] - vals[col]) < 1e-4, (d, got[d], vals[col])
+
+
 def test_querylogic_goldens():
     """ref tests/t_querylogic.c:16-52."""
     from nxsearch_b200 import tools
