@@ -145,12 +145,9 @@ tokenset_destroy(tokenset_t *ts)
 }
 
 /*
- * Simple lower-case mapping of a code point below U+0800, 0 = unchanged.
- * Only mappings that keep the UTF-8 length (two bytes stay two bytes): the
- * Latin-1 Supplement, Latin Extended-A, Greek and Cyrillic blocks -- what the
- * reference's golden case exercises (ref src/tests/t_utf8.c:73-74,
- * "ĄČĘĖĮŠŲŪŽ" -> "ąčęėįšųūž").  U+0130 (whose lower case is one byte) and
- * everything from U+0800 up are left alone.
+ * Simple lower-case mapping of a code point below U+0800, 0 = unchanged:
+ * the Latin-1 Supplement, Latin Extended-A, Greek and Cyrillic blocks
+ * (ref src/tests/t_utf8.c:73-74, "ĄČĘĖĮŠŲŪŽ" -> "ąčęėįšųūž").
  */
 static uint32_t
 lower_2byte(uint32_t cp)
@@ -184,26 +181,108 @@ lower_2byte(uint32_t cp)
 }
 
 /*
- * "normalizer": the reference lower-cases and applies NFKC through ICU
- * (ref src/utils/utf8.c:263-330).  Here: ASCII and the two-byte blocks above
- * are lower-cased in place; compatibility decomposition is not attempted.
+ * What the reference's transliteration "NFKD; [:Nonspacing Mark:] Remove;
+ * Latin-ASCII; NFKC" (ref src/utils/utf8.c:30-31) leaves of a lower-case code
+ * point below U+0800: an ASCII string (returned through *ascii), another code
+ * point (Greek without tonos, Cyrillic without breve / diaeresis), 0 for a
+ * combining mark (removed), or the code point itself.
  */
-static void
-utf8_lower_inplace(unsigned char *buf, size_t len)
+static uint32_t
+fold_2byte(uint32_t cp, const char **ascii)
 {
-	for (size_t k = 0; k < len; k++) {
-		if (buf[k] >= 'A' && buf[k] <= 'Z') {
-			buf[k] += 'a' - 'A';
-		} else if ((buf[k] & 0xe0) == 0xc0 && k + 1 < len && (buf[k + 1] & 0xc0) == 0x80) {
-			const uint32_t lo = lower_2byte(((uint32_t)(buf[k] & 0x1f) << 6) | (buf[k + 1] & 0x3f));
+	static const char *const latin1[32] = {	/* U+00E0 .. U+00FF */
+		"a", "a", "a", "a", "a", "a", "ae", "c", "e", "e", "e", "e", "i", "i", "i", "i",
+		"d", "n", "o", "o", "o", "o", "o", NULL, "o", "u", "u", "u", "u", "y", "th", "y",
+	};
+	static const char *const ext_a[128] = {	/* U+0100 .. U+017F, either case */
+		"a", "a", "a", "a", "a", "a", "c", "c", "c", "c", "c", "c", "c", "c", "d", "d",
+		"d", "d", "e", "e", "e", "e", "e", "e", "e", "e", "e", "e", "g", "g", "g", "g",
+		"g", "g", "g", "g", "h", "h", "h", "h", "i", "i", "i", "i", "i", "i", "i", "i",
+		"i", "i", "ij", "ij", "j", "j", "k", "k", "q", "l", "l", "l", "l", "l", "l", NULL,
+		NULL, "l", "l", "n", "n", "n", "n", "n", "n", "'n", "ng", "ng", "o", "o", "o", "o",
+		"o", "o", "oe", "oe", "r", "r", "r", "r", "r", "r", "s", "s", "s", "s", "s", "s",
+		"s", "s", "t", "t", "t", "t", "t", "t", "u", "u", "u", "u", "u", "u", "u", "u",
+		"u", "u", "u", "u", "w", "w", "y", "y", "y", "z", "z", "z", "z", "z", "z", "s",
+	};
 
-			if (lo) {
-				buf[k] = 0xc0 | (lo >> 6);
-				buf[k + 1] = 0x80 | (lo & 0x3f);
-			}
+	*ascii = NULL;
+	if (cp >= 0xe0 && cp <= 0xff)
+		*ascii = latin1[cp - 0xe0];
+	else if (cp >= 0x100 && cp <= 0x17f)
+		*ascii = ext_a[cp - 0x100];
+	else if (cp == 0xdf)
+		*ascii = "ss";
+	else if (cp == 0xaa)
+		*ascii = "a";
+	else if (cp == 0xba)
+		*ascii = "o";
+	else if (cp == 0xb2 || cp == 0xb3)
+		*ascii = cp == 0xb2 ? "2" : "3";
+	else if (cp == 0xb9)
+		*ascii = "1";
+	if (*ascii)
+		return cp;
+	if (cp >= 0x300 && cp <= 0x36f)
+		return 0;
+	switch (cp) {
+	case 0xb5:  return 0x3bc;			/* micro sign -> mu */
+	case 0x3ac: return 0x3b1;
+	case 0x3ad: return 0x3b5;
+	case 0x3ae: return 0x3b7;
+	case 0x3af: case 0x3ca: case 0x390: return 0x3b9;
+	case 0x3cc: return 0x3bf;
+	case 0x3cd: case 0x3cb: case 0x3b0: return 0x3c5;
+	case 0x3ce: return 0x3c9;
+	case 0x3c2: return 0x3c3;			/* final sigma (case folding) */
+	case 0x439: case 0x45d: return 0x438;
+	case 0x451: case 0x450: return 0x435;
+	case 0x457: return 0x456;
+	case 0x453: return 0x433;
+	case 0x45c: return 0x43a;
+	case 0x45e: return 0x443;
+	}
+	return cp;
+}
+
+/*
+ * "normalizer": the reference applies NFKC case folding and then strips
+ * diacritics with the transliteration above (ref src/core/filters_builtin.c:
+ * 55-74, src/utils/utf8.c:263-330,212-255), all through ICU.  Here, in place
+ * (the result is never longer): ASCII is lower-cased; code points of two
+ * UTF-8 bytes -- Latin-1, Latin Extended-A, Greek, Cyrillic, the combining
+ * marks -- are lower-cased and folded as the reference's golden cases show
+ * (ref src/tests/t_utf8.c:70-74,124-127); longer sequences are kept as they
+ * are (no compatibility decomposition: "Ⅷ" stays).
+ */
+static size_t
+normalize_inplace(unsigned char *buf, size_t len)
+{
+	size_t o = 0;
+
+	for (size_t k = 0; k < len; k++) {
+		const unsigned char c = buf[k];
+
+		if (c >= 'A' && c <= 'Z') {
+			buf[o++] = c + ('a' - 'A');
+		} else if ((c & 0xe0) == 0xc0 && k + 1 < len && (buf[k + 1] & 0xc0) == 0x80) {
+			uint32_t cp = ((uint32_t)(c & 0x1f) << 6) | (buf[k + 1] & 0x3f);
+			const uint32_t lo = lower_2byte(cp);
+			const char *ascii;
+
+			cp = fold_2byte(lo ? lo : cp, &ascii);
 			k++;
+			if (ascii) {
+				while (*ascii)
+					buf[o++] = (unsigned char)*ascii++;
+			} else if (cp) {
+				buf[o++] = 0xc0 | (cp >> 6);
+				buf[o++] = 0x80 | (cp & 0x3f);
+			}
+		} else {
+			buf[o++] = c;
 		}
 	}
+	return o;
 }
 
 /*
@@ -218,7 +297,8 @@ filter_apply(const filter_pipeline_t *fp, char *buf, size_t *lenp)
 	for (unsigned i = 0; i < fp->count; i++) {
 		switch (fp->kinds[i]) {
 		case FILT_NORMALIZER:
-			utf8_lower_inplace((unsigned char *)buf, len);
+			len = normalize_inplace((unsigned char *)buf, len);
+			buf[len] = '\0';
 			break;
 		case FILT_STOPWORDS:
 			if (fp->stopwords && strmap_get(fp->stopwords, buf, len, NULL))

@@ -9,8 +9,11 @@
  *   - words by the UAX #29 rules over the ASCII classes, bytes >= 0x80 taken
  *     as letters ("i.b.m", "doesn't", "snake_case", "3.14" are one word each;
  *     ref src/tests/t_tokenize.c:17-62 are the golden cases);
- *   - "normalizer" lower-cases ASCII and the two-byte Latin / Greek /
- *     Cyrillic blocks (ref src/tests/t_utf8.c:70-74); no NFKC;
+ *   - "normalizer" lower-cases and strips diacritics (the reference's NFKC
+ *     case folding + "NFKD; [:Nonspacing Mark:] Remove; Latin-ASCII") for
+ *     code points of up to two UTF-8 bytes: Latin-1, Latin Extended-A,
+ *     Greek, Cyrillic, combining marks (ref src/tests/t_utf8.c:70-74,
+ *     124-127); no compatibility decomposition beyond that;
  *   - "stopwords" drops words listed in <basedir>/filters/stopwords/<lang>
  *     (one per line), exactly where the reference looks for them
  *     (filters_builtin.c:93-127);

@@ -146,5 +146,14 @@ TOKENIZE_CASES = [
     ("", []),
 ]
 
-# src/tests/t_utf8.c:70-74 (utf8_tolower)
-LOWER_CASES = [("TEST", "test"), ("ĄČĘĖĮŠŲŪŽ", "ąčęėįšųūž")]
+# The "normalizer" filter = utf8_normalize (NFKC case folding) then utf8_subs_diacritics
+# (src/core/filters_builtin.c:55-74).  The reference's cases for the two halves
+# (src/tests/t_utf8.c:70-74 lower-casing, :124-127 diacritics), composed in that order:
+NORMALIZER_CASES = [
+    ("TEST", "test"),
+    ("ĄČĘĖĮŠŲŪŽ", "aceeisuuz"),         # lower: "ąčęėįšųūž", then without the marks
+    ("azúl", "azul"),
+    ("ĄŽUOLĖLIS", "azuolelis"),          # diacritics: "AZUOLELIS", lower-cased first
+    ("Fuglafjørður", "fuglafjordur"),
+    ("Árbæ", "arbae"),
+]
