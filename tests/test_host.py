@@ -290,6 +290,30 @@ def test_tokenizer_matches_the_reference_goldens():
     assert tools.tokenize("Some.Text", normalize=False) == [("Some.Text", 1)]
 
 
+def test_index_limits_of_the_reference(nxs):
+    """ref src/tests/t_index_limits.c: one document with 65 535 distinct terms
+    (ids in order of first appearance, every count 1, the header counters
+    follow), a term of 65 535 bytes is stored, one byte more is NXS_ERR_LIMIT
+    with the reference's message."""
+    idx = nxs.create_index("l", filters=["normalizer"])
+    n = 0xffff
+    words = [f"w{i:07d}" for i in range(n)]
+    idx.add(1001, " ".join(words))
+    idx.add(1002, "a" * 0xffff)
+    with pytest.raises(capi.NxsError) as e:
+        idx.add(1003, "b" * 0x10000)
+    assert e.value.code == capi.ERR_LIMIT and e.value.msg == "term too long (65536)"
+    idx.close()
+    c = tools.Corpus.read(f"{nxs.base}/data/l/nxsterms", f"{nxs.base}/data/l/nxsdtmap")
+    assert c.n_terms == n + 1 and c.n_docs == 2 and c.token_count == n + 1
+    assert c.term(1) == words[0] and c.term(n) == words[-1] and c.term(n + 1) == "a" * 0xffff
+    first = c.pairs[: 2 * n].reshape(n, 2)
+    assert int(c.doc_len[0]) == n and np.array_equal(first[:, 0], np.arange(1, n + 1)) and np.all(first[:, 1] == 1)
+    # a new term starts at the adding document's count (ref terms.c:260) and the document
+    # is then counted again (ref dtmap.c:236): the files say 2, as the reference's do
+    assert np.all(c.term_df[:n] == 1) and np.all(c.term_total == 2)
+
+
 def test_gpu_layout_is_replicas_or_shards_nothing_else(monkeypatch):
     """NXS_GPU_LAYOUT picks what several devices hold (replicas of the image, or
     a range of the documents each).  A misspelt value fails nxs_open instead of
