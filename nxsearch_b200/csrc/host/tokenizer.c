@@ -278,6 +278,11 @@ normalize_inplace(unsigned char *buf, size_t len)
 				buf[o++] = 0xc0 | (cp >> 6);
 				buf[o++] = 0x80 | (cp & 0x3f);
 			}
+		} else if (c == 0xe2 && k + 2 < len && buf[k + 1] == 0x80 &&
+		    (buf[k + 2] == 0x98 || buf[k + 2] == 0x99 || buf[k + 2] == 0xa4)) {
+			/* Latin-ASCII: the curly apostrophes and the one-dot leader inside a word */
+			buf[o++] = buf[k + 2] == 0xa4 ? '.' : '\'';
+			k += 2;
 		} else {
 			buf[o++] = c;
 		}
@@ -375,64 +380,148 @@ out:
 /*
  * Word segmentation: the reference walks ICU's UBRK_WORD boundaries and keeps
  * the segments whose rule status is not UBRK_WORD_NONE (ref
- * src/core/tokenizer.c:234-302).  These are the UAX #29 word-break rules over
- * the ASCII classes (ICU's tailoring: the colon is not MidLetter), with every
- * byte >= 0x80 taken as a letter:
+ * src/core/tokenizer.c:234-302).  These are the UAX #29 word-break rules with
+ * the character classes that need no Unicode tables (ICU's tailoring: the
+ * colon is not MidLetter):
  *   WB5, WB8-10, WB13, WB13a/b   letters, digits and '_' join;
- *   WB6/7    letter ( . | ' ) letter joins ("i.b.m", "doesn't");
+ *   WB6/7    letter ( . | ' | U+2019 | U+00B7 ... ) letter joins ("i.b.m", "doesn't");
  *   WB11/12  digit ( . | ' | , | ; ) digit joins ("3.14", "1,000").
- * A segment without a letter or a digit is not a word.  Pinned by the
- * reference's golden cases (ref src/tests/t_tokenize.c:17-62).
+ * Outside ASCII a code point is a letter unless it lies in one of the blocks
+ * that hold no letters -- Latin-1 punctuation, General Punctuation (curly
+ * quotes, dashes, the ellipsis, typographic spaces), currency signs, arrows
+ * and mathematical / technical / box / dingbat symbols, CJK and full-width
+ * punctuation, emoji (Extended_Pictographic has no word status in ICU) --
+ * where it breaks words like ASCII punctuation does.  Scripts that ICU
+ * segments with a dictionary (CJK, Thai) stay one word per run.  A segment
+ * without a letter or a digit is not a word.  Pinned by the reference's
+ * golden cases (ref src/tests/t_tokenize.c:17-62, and :64-79 for the emoji).
  */
-enum { WC_OTHER, WC_LETTER, WC_DIGIT, WC_EXTNUMLET, WC_MIDNUMLET, WC_MIDNUM };
+enum { WC_OTHER, WC_LETTER, WC_DIGIT, WC_EXTNUMLET, WC_MIDNUMLET, WC_MIDNUM, WC_MIDLETTER };
 
-static inline int
-word_class(unsigned char c)
+static int
+class_of(uint32_t cp)
 {
-	if ((c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || c >= 0x80)
+	if (cp < 0x80) {
+		if ((cp >= 'a' && cp <= 'z') || (cp >= 'A' && cp <= 'Z'))
+			return WC_LETTER;
+		if (cp >= '0' && cp <= '9')
+			return WC_DIGIT;
+		if (cp == '_')
+			return WC_EXTNUMLET;
+		if (cp == '.' || cp == '\'')
+			return WC_MIDNUMLET;
+		if (cp == ',' || cp == ';')
+			return WC_MIDNUM;
+		return WC_OTHER;
+	}
+	if (cp < 0xc0)		/* C1 controls, Latin-1 punctuation and signs */
+		return cp == 0xaa || cp == 0xb5 || cp == 0xba ? WC_LETTER :
+		    cp == 0xb7 ? WC_MIDLETTER : WC_OTHER;
+	if (cp == 0xd7 || cp == 0xf7)
+		return WC_OTHER;
+	if (cp < 0x2000)
 		return WC_LETTER;
-	if (c >= '0' && c <= '9')
-		return WC_DIGIT;
-	if (c == '_')
-		return WC_EXTNUMLET;
-	if (c == '.' || c == '\'')
-		return WC_MIDNUMLET;
-	if (c == ',' || c == ';')
-		return WC_MIDNUM;
-	return WC_OTHER;
+	if (cp <= 0x206f) {	/* General Punctuation */
+		if (cp == 0x2018 || cp == 0x2019 || cp == 0x2024)
+			return WC_MIDNUMLET;
+		if (cp == 0x2027)
+			return WC_MIDLETTER;
+		if (cp == 0x2044)
+			return WC_MIDNUM;
+		if (cp == 0x203f || cp == 0x2040 || cp == 0x2054)
+			return WC_EXTNUMLET;
+		if (cp == 0x200c || cp == 0x200d)	/* joiners are transparent (WB4) */
+			return WC_LETTER;
+		return WC_OTHER;
+	}
+	if ((cp >= 0x20a0 && cp <= 0x20cf) ||	/* currency */
+	    (cp >= 0x2190 && cp <= 0x23ff) ||	/* arrows, mathematical, technical */
+	    (cp >= 0x2460 && cp <= 0x24b5) ||	/* enclosed digits */
+	    (cp >= 0x24ea && cp <= 0x27bf) ||	/* ..., box drawing, shapes, dingbats */
+	    (cp >= 0x2900 && cp <= 0x2bff) ||	/* more arrows and operators */
+	    (cp >= 0x2e00 && cp <= 0x2e7f) ||	/* supplemental punctuation */
+	    (cp >= 0x3000 && cp <= 0x3004) || (cp >= 0x3008 && cp <= 0x3020) ||
+	    cp == 0x3030 || (cp >= 0x303d && cp <= 0x303f) ||	/* CJK punctuation */
+	    (cp >= 0xfe50 && cp <= 0xfe6b) ||	/* small form variants */
+	    (cp >= 0xff01 && cp <= 0xff0f) || (cp >= 0xff1a && cp <= 0xff20) ||
+	    (cp >= 0xff3b && cp <= 0xff40 && cp != 0xff3f) ||
+	    (cp >= 0xff5b && cp <= 0xff65) ||	/* full-width punctuation */
+	    cp == 0xfffd || (cp >= 0x1f000 && cp <= 0x1faff))	/* emoji */
+		return WC_OTHER;
+	return WC_LETTER;
+}
+
+/*
+ * The class of the code point at text[i] and its length in bytes; the end of
+ * the text (or a NUL) is WC_OTHER of length 0.  A byte that does not start a
+ * well-formed sequence counts as a letter of one byte.
+ */
+static int
+class_at(const unsigned char *t, size_t i, size_t len, size_t *adv)
+{
+	uint32_t cp;
+	size_t n;
+
+	*adv = 0;
+	if (i >= len || t[i] == 0)
+		return WC_OTHER;
+	*adv = 1;
+	if (t[i] < 0x80)
+		return class_of(t[i]);
+	n = (t[i] & 0xe0) == 0xc0 ? 2 : (t[i] & 0xf0) == 0xe0 ? 3 : (t[i] & 0xf8) == 0xf0 ? 4 : 1;
+	if (n == 1 || i + n > len)
+		return WC_LETTER;
+	cp = t[i] & (0xffu >> (n + 1));
+	for (size_t k = 1; k < n; k++) {
+		if ((t[i + k] & 0xc0) != 0x80)
+			return WC_LETTER;
+		cp = (cp << 6) | (t[i + k] & 0x3f);
+	}
+	*adv = n;
+	return class_of(cp);
 }
 
 tokenset_t *
 tokenize(filter_pipeline_t *fp, const char *text, size_t len)
 {
+	const unsigned char *t = (const unsigned char *)text;
 	tokenset_t *ts = tokenset_create();
 	size_t i = 0;
 
 	if (!ts)
 		return NULL;
-	while (i < len && text[i]) {
+	while (i < len && t[i]) {
 		bool word = false;
 		int last = WC_OTHER;
+		size_t s, adv, nadv;
 		int32_t slot;
-		size_t s;
 
-		while (i < len && text[i] && word_class(text[i]) != WC_LETTER &&
-		    word_class(text[i]) != WC_DIGIT && word_class(text[i]) != WC_EXTNUMLET)
-			i++;
+		for (;;) {
+			const int c = class_at(t, i, len, &adv);
+
+			if (adv == 0 || c == WC_LETTER || c == WC_DIGIT || c == WC_EXTNUMLET)
+				break;
+			i += adv;
+		}
 		s = i;
-		while (i < len && text[i]) {
-			const int c = word_class(text[i]);
-			const int next = i + 1 < len ? word_class(text[i + 1]) : WC_OTHER;
+		for (;;) {
+			const int c = class_at(t, i, len, &adv);
 
+			if (adv == 0)
+				break;
 			if (c == WC_LETTER || c == WC_DIGIT || c == WC_EXTNUMLET) {
 				word |= c != WC_EXTNUMLET;
 				last = c;
-			} else if (!((c == WC_MIDNUMLET && last == next &&
-			    (last == WC_LETTER || last == WC_DIGIT)) ||
-			    (c == WC_MIDNUM && last == WC_DIGIT && next == WC_DIGIT))) {
-				break;
+			} else {
+				const int next = class_at(t, i + adv, len, &nadv);
+
+				if (!((c == WC_MIDNUMLET && last == next &&
+				    (last == WC_LETTER || last == WC_DIGIT)) ||
+				    (c == WC_MIDLETTER && last == WC_LETTER && next == WC_LETTER) ||
+				    (c == WC_MIDNUM && last == WC_DIGIT && next == WC_DIGIT)))
+					break;
 			}
-			i++;
+			i += adv;
 		}
 		if (word && tokenize_value(fp, ts, text + s, i - s, &slot) == -1) {
 			tokenset_destroy(ts);

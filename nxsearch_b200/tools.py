@@ -177,7 +177,7 @@ def tokenize(text: str | bytes, *, normalize: bool = True, stem: bool = False) -
     if lib.nxsb_tokenize(raw, len(raw), int(normalize) | (2 if stem else 0), buf, len(buf), C.byref(n), counts, len(raw) + 1) != 0:
         raise RuntimeError("nxsb_tokenize failed")
     toks = buf.raw.split(b"\0")[: n.value]
-    return [(t.decode(), counts[i]) for i, t in enumerate(toks)]
+    return [(t.decode(errors="replace"), counts[i]) for i, t in enumerate(toks)]
 
 
 def query_terms(n_terms: int, df, n: int, *, seed: int = SEED + 1) -> np.ndarray:

@@ -288,6 +288,22 @@ def test_tokenizer_matches_the_reference_goldens():
         ["_x_", "year", "end", "10", "30", "a", "b", "quoted"]
     # without the normalizer the case stays
     assert tools.tokenize("Some.Text", normalize=False) == [("Some.Text", 1)]
+    # the case the reference keeps out of its own run (t_tokenize.c:64-79): ICU keeps the
+    # underscores and "some.text" in one piece, and an emoji is not a word
+    assert [w for w, _ in tools.tokenize("_underscore_, year-end, join--double Some.Text, 🥎")] == \
+        ["_underscore_", "year", "end", "join", "double", "some.text"]
+    # punctuation outside ASCII breaks words like ASCII punctuation does; U+2019 and U+00B7
+    # join letters (WB6/7) and the apostrophe comes out in ASCII (Latin-ASCII)
+    assert [w for w, _ in tools.tokenize("“Quoted” text — with dashes…and ellipsis")] == \
+        ["quoted", "text", "with", "dashes", "and", "ellipsis"]
+    assert [w for w, _ in tools.tokenize("doesn’t l’été rock’n’roll ‘quoted’ a·b")] == \
+        ["doesn't", "l'ete", "rock'n'roll", "quoted", "a·b"]
+    assert [w for w, _ in tools.tokenize("10\u00a0000 €5 café\u00a0au lait x→y 3×4 ½ ① ＡＢＣ！ｄ")] == \
+        ["10", "000", "5", "cafe", "au", "lait", "x", "y", "3", "4", "ＡＢＣ", "ｄ"]
+    # no dictionary here: a run of ideographs or kana is one word, CJK punctuation still breaks it
+    assert [w for w, _ in tools.tokenize("日本語のテキスト。次の文")] == ["日本語のテキスト", "次の文"]
+    # malformed UTF-8 neither crashes nor disappears: stray bytes are letters of one byte
+    assert len(tools.tokenize(b"bad \xff\xfe bytes \xc3 \xe2\x80 end\xe2")) == 6
 
 
 def test_index_limits_of_the_reference(nxs):
