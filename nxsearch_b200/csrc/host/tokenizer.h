@@ -6,9 +6,10 @@
  * the Snowball stemmer (ref src/core/tokenizer.c:234-302,
  * src/core/filters_builtin.c); none of those libraries exist here, so this
  * front end implements the part that needs no Unicode tables:
- *   - words by the UAX #29 rules over the ASCII classes, bytes >= 0x80 taken
- *     as letters ("i.b.m", "doesn't", "snake_case", "3.14" are one word each;
- *     ref src/tests/t_tokenize.c:17-62 are the golden cases);
+ *   - words by the UAX #29 rules ("i.b.m", "doesn't", "snake_case", "3.14"
+ *     are one word each; ref src/tests/t_tokenize.c:17-62 are the golden
+ *     cases); outside ASCII a code point is a letter unless its block holds
+ *     none (punctuation, symbols, emoji), no dictionary segmentation;
  *   - "normalizer" lower-cases and strips diacritics (the reference's NFKC
  *     case folding + "NFKD; [:Nonspacing Mark:] Remove; Latin-ASCII") for
  *     code points of up to two UTF-8 bytes: Latin-1, Latin Extended-A,
