@@ -251,8 +251,10 @@ fold_2byte(uint32_t cp, const char **ascii)
  * (the result is never longer): ASCII is lower-cased; code points of two
  * UTF-8 bytes -- Latin-1, Latin Extended-A, Greek, Cyrillic, the combining
  * marks -- are lower-cased and folded as the reference's golden cases show
- * (ref src/tests/t_utf8.c:70-74,124-127); longer sequences are kept as they
- * are (no compatibility decomposition: "Ⅷ" stays).
+ * (ref src/tests/t_utf8.c:70-74,124-127); of the longer sequences the curly
+ * apostrophes, the full-width letters and digits and the Latin ligatures
+ * fold to ASCII, everything else is kept as it is (no general compatibility
+ * decomposition: "Ⅷ" stays, since "viii" would not fit in place).
  */
 static size_t
 normalize_inplace(unsigned char *buf, size_t len)
@@ -282,6 +284,31 @@ normalize_inplace(unsigned char *buf, size_t len)
 		    (buf[k + 2] == 0x98 || buf[k + 2] == 0x99 || buf[k + 2] == 0xa4)) {
 			/* Latin-ASCII: the curly apostrophes and the one-dot leader inside a word */
 			buf[o++] = buf[k + 2] == 0xa4 ? '.' : '\'';
+			k += 2;
+		} else if (c == 0xef && k + 2 < len && (buf[k + 1] == 0xbc || buf[k + 1] == 0xbd) &&
+		    (buf[k + 2] & 0xc0) == 0x80) {
+			/* NFKC case folding of the full-width forms: U+FF10-19, U+FF21-3A, U+FF41-5A */
+			const uint32_t cp = 0xff00u | ((uint32_t)(buf[k + 1] & 0x03) << 6) | (buf[k + 2] & 0x3f);
+
+			if (cp >= 0xff10 && cp <= 0xff19) {
+				buf[o++] = (unsigned char)('0' + (cp - 0xff10));
+			} else if (cp >= 0xff21 && cp <= 0xff3a) {
+				buf[o++] = (unsigned char)('a' + (cp - 0xff21));
+			} else if (cp >= 0xff41 && cp <= 0xff5a) {
+				buf[o++] = (unsigned char)('a' + (cp - 0xff41));
+			} else {
+				buf[o++] = c;
+				buf[o++] = buf[k + 1];
+				buf[o++] = buf[k + 2];
+			}
+			k += 2;
+		} else if (c == 0xef && k + 2 < len && buf[k + 1] == 0xac && buf[k + 2] >= 0x80 &&
+		    buf[k + 2] <= 0x86) {
+			/* ... and of the Latin ligatures U+FB00-06 */
+			static const char *const lig[7] = { "ff", "fi", "fl", "ffi", "ffl", "st", "st" };
+
+			for (const char *p = lig[buf[k + 2] - 0x80]; *p; p++)
+				buf[o++] = (unsigned char)*p;
 			k += 2;
 		} else {
 			buf[o++] = c;

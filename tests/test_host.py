@@ -279,7 +279,9 @@ def test_tokenizer_matches_the_reference_goldens():
     assert [w for w, _ in tools.tokenize("Київ ДНІПР ЁЖИК Ελλάδα ΆΝΘΡΩΠΟΣ ÅNGSTRÖM straße Þór œuvre Łódź İstanbul")] == \
         ["киів", "дніпр", "ежик", "ελλαδα", "ανθρωποσ", "angstrom", "strasse", "thor", "oeuvre", "lodz", "istanbul"]
     assert tools.tokenize("cafe\u0301 café") == [("cafe", 2)]       # decomposed and precomposed meet
-    assert tools.tokenize("Henry Ⅷ") == [("henry", 1), ("Ⅷ", 1)]    # no compatibility decomposition (t_utf8.c:93)
+    assert tools.tokenize("Henry Ⅷ") == [("henry", 1), ("Ⅷ", 1)]    # no general compatibility decomposition (t_utf8.c:93)
+    # ... but the forms that fold in place do: full-width letters and digits, Latin ligatures
+    assert [w for w, _ in tools.tokenize("ＡＢＣ１２３ｘｙｚ ﬁnance oﬃce ﬆop")] == ["abc123xyz", "finance", "office", "stop"]
     # WB11/12: digits join over . , ; ' -- letters only over . and '
     assert [w for w, _ in tools.tokenize("pi is 3.14, or 1,000;5 a,b a;b x.y 1.a a.1 v2.0")] == \
         ["pi", "is", "3.14", "or", "1,000;5", "a", "b", "x.y", "1", "v2.0"]
@@ -299,7 +301,7 @@ def test_tokenizer_matches_the_reference_goldens():
     assert [w for w, _ in tools.tokenize("doesn’t l’été rock’n’roll ‘quoted’ a·b")] == \
         ["doesn't", "l'ete", "rock'n'roll", "quoted", "a·b"]
     assert [w for w, _ in tools.tokenize("10\u00a0000 €5 café\u00a0au lait x→y 3×4 ½ ① ＡＢＣ！ｄ")] == \
-        ["10", "000", "5", "cafe", "au", "lait", "x", "y", "3", "4", "ＡＢＣ", "ｄ"]
+        ["10", "000", "5", "cafe", "au", "lait", "x", "y", "3", "4", "abc", "d"]
     # no dictionary here: a run of ideographs or kana is one word, CJK punctuation still breaks it
     assert [w for w, _ in tools.tokenize("日本語のテキスト。次の文")] == ["日本語のテキスト", "次の文"]
     # malformed UTF-8 neither crashes nor disappears: stray bytes are letters of one byte
